@@ -1,0 +1,499 @@
+// T0 oracle harness: drives the UNMODIFIED reference (oracle/_ref/libstage_ref.so, built by
+// oracle/build_ref.sh from /root/reference) and records what its raycast hot path does.
+// TEST INFRASTRUCTURE ONLY: loaded by tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs through ctypes. Never linked into stage_b200.
+//
+// How the recording works without touching reference sources: libstage_ref.so is built -fPIC with
+// default (interposable) symbol visibility, so its internal calls to Block::Map, Block::UnMap and
+// World::Raytrace(const Ray&) go through the PLT. This library defines those three symbols
+// itself; being earlier in the lookup scope it is bound first, logs the call, and forwards to the
+// real definition found with dlsym() on the libstage_ref.so handle.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+#include <dlfcn.h>
+
+// the harness needs Block::pts, Block::global_z, World::models ... (all private/protected)
+#define private public
+#define protected public
+#include "stage.hh"
+#include "region.hh"
+#undef private
+#undef protected
+
+#include "trace_format.h"
+
+using namespace Stg;
+
+namespace {
+
+struct Recorder {
+  std::mutex mu;
+  bool active = false;
+  std::vector<TraceEvent> events;
+  std::vector<int32_t> verts;
+  std::vector<TraceRay> rays;
+  std::map<const Block *, uint32_t> block_ids;
+  std::map<ray_test_func_t, int> kinds;
+  uint32_t n_ticks = 0;
+  World *world = NULL;
+} rec;
+
+thread_local int tl_quiet = 0; // >0: calls made by the harness itself are not recorded
+
+void *ref_handle()
+{
+  static void *h = dlopen("libstage_ref.so", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) {
+    fprintf(stderr, "ref_harness: libstage_ref.so not loaded: %s\n", dlerror());
+    abort();
+  }
+  return h;
+}
+
+template <class F> F real(const char *mangled)
+{
+  void *p = dlsym(ref_handle(), mangled);
+  if (!p) {
+    fprintf(stderr, "ref_harness: missing %s\n", mangled);
+    abort();
+  }
+  return (F)p;
+}
+
+uint32_t block_id_locked(const Block *b)
+{
+  std::map<const Block *, uint32_t>::iterator it = rec.block_ids.find(b);
+  if (it != rec.block_ids.end())
+    return it->second;
+  uint32_t id = (uint32_t)rec.block_ids.size();
+  rec.block_ids[b] = id;
+  return id;
+}
+
+// harness-owned predicates with the same meaning as the reference's file-static ones
+bool h_ranger_match(Model *hit, const Model *finder, const void *)
+{ // model_ranger.cc:158-170
+  if ((hit == finder->Parent()) || (hit == finder))
+    return false;
+  return ((!hit->IsRelated(finder)) && (sgn(hit->vis.ranger_return) != -1));
+}
+bool h_unrelated_match(Model *hit, const Model *finder, const void *)
+{ // model_fiducial.cc:103-107
+  return (!finder->IsRelated(hit));
+}
+bool h_gripper_match(Model *hit, const Model *finder, const void *)
+{ // model_gripper.cc:329-336
+  return ((hit != finder) && hit->vis.gripper_return);
+}
+
+int classify(const Ray &r)
+{
+  if (r.func == h_ranger_match)
+    return TRACE_KIND_RANGER;
+  if (r.func == h_unrelated_match)
+    return TRACE_KIND_UNRELATED;
+  if (r.func == h_gripper_match)
+    return TRACE_KIND_GRIPPER;
+  std::map<ray_test_func_t, int>::iterator it = rec.kinds.find(r.func);
+  if (it != rec.kinds.end())
+    return it->second;
+  // the reference's predicates are file-static; tell them apart by who is looking
+  const std::string &t = r.mod->type;
+  int k = (t == "ranger") ? TRACE_KIND_RANGER : (t == "gripper") ? TRACE_KIND_GRIPPER : TRACE_KIND_UNRELATED;
+  rec.kinds[r.func] = k;
+  return k;
+}
+
+uint32_t root_id(const Model *m)
+{
+  while (m->parent)
+    m = m->parent;
+  return m->id;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------- interposed reference symbols
+
+void Block::Map(unsigned int layer)
+{
+  typedef void (*fn_t)(Block *, unsigned int);
+  static fn_t fn = real<fn_t>("_ZN3Stg5Block3MapEj");
+  fn(this, layer);
+  if (!rec.active || tl_quiet)
+    return;
+  // what MapPoly was given (block.cc:174) and the z bounds Map left behind (block.cc:177-180)
+  const std::vector<point_int_t> px = group->mod.LocalToPixels(pts);
+  std::lock_guard<std::mutex> g(rec.mu);
+  TraceEvent e;
+  memset(&e, 0, sizeof(e));
+  e.type = TRACE_EV_MAP;
+  e.layer = (uint8_t)layer;
+  e.n_pts = (uint16_t)px.size();
+  e.block = block_id_locked(this);
+  e.model = group->mod.id;
+  e.first = (uint32_t)(rec.verts.size() / 2);
+  e.zmin = global_z.min;
+  e.zmax = global_z.max;
+  for (size_t i = 0; i < px.size(); i++) {
+    rec.verts.push_back(px[i].x);
+    rec.verts.push_back(px[i].y);
+  }
+  rec.events.push_back(e);
+}
+
+void Block::UnMap(unsigned int layer)
+{
+  typedef void (*fn_t)(Block *, unsigned int);
+  static fn_t fn = real<fn_t>("_ZN3Stg5Block5UnMapEj");
+  const bool was_mapped = !rendered_cells[layer].empty();
+  fn(this, layer);
+  if (!rec.active || tl_quiet || !was_mapped)
+    return;
+  std::lock_guard<std::mutex> g(rec.mu);
+  TraceEvent e;
+  memset(&e, 0, sizeof(e));
+  e.type = TRACE_EV_UNMAP;
+  e.layer = (uint8_t)layer;
+  e.block = block_id_locked(this);
+  e.model = group->mod.id;
+  rec.events.push_back(e);
+}
+
+RaytraceResult World::Raytrace(const Ray &r)
+{
+  typedef RaytraceResult (*fn_t)(World *, const Ray &);
+  static fn_t fn = real<fn_t>("_ZN3Stg5World8RaytraceERKNS_3RayE");
+  const unsigned int layer = (updates + 1) % 2; // world.cc:804
+  RaytraceResult res = fn(this, r);
+  if (!rec.active || tl_quiet)
+    return res;
+  std::lock_guard<std::mutex> g(rec.mu);
+  TraceRay t;
+  memset(&t, 0, sizeof(t));
+  t.ox = r.origin.x;
+  t.oy = r.origin.y;
+  t.oz = r.origin.z;
+  t.oa = r.origin.a;
+  t.range = r.range;
+  t.res_range = res.range;
+  t.hit_model = res.mod ? (int32_t)res.mod->id : -1;
+  t.finder = r.mod->id;
+  t.kind = (uint8_t)classify(r);
+  t.ztest = r.ztest ? 1 : 0;
+  t.layer = (uint8_t)layer;
+  if (!rec.events.empty() && rec.events.back().type == TRACE_EV_RAYS) {
+    rec.events.back().model++;
+  } else {
+    TraceEvent e;
+    memset(&e, 0, sizeof(e));
+    e.type = TRACE_EV_RAYS;
+    e.model = 1;
+    e.first = (uint32_t)rec.rays.size();
+    rec.events.push_back(e);
+  }
+  rec.rays.push_back(t);
+  return res;
+}
+
+// ---------------------------------------------------------------- C interface for ctypes
+
+extern "C" {
+
+typedef struct {
+  double ox, oy, oz, oa, range;
+  uint32_t finder;
+  uint8_t kind, ztest, pad[2];
+} RefRayIn; // 48 B
+
+typedef struct {
+  double range;
+  int32_t hit_model;
+  int32_t pad;
+} RefRayOut; // 16 B
+
+static bool g_inited = false;
+static void ensure_init()
+{
+  if (g_inited)
+    return;
+  int argc = 1;
+  char arg0[] = "ref_harness";
+  char *argv0[] = { arg0, NULL };
+  char **argv = argv0;
+  Stg::Init(&argc, &argv);
+  g_inited = true;
+}
+
+// Start recording. Everything the reference maps / unmaps / traces from here on is logged.
+void ref_trace_begin(void)
+{
+  std::lock_guard<std::mutex> g(rec.mu);
+  rec.events.clear();
+  rec.verts.clear();
+  rec.rays.clear();
+  rec.block_ids.clear();
+  rec.kinds.clear();
+  rec.n_ticks = 0;
+  rec.active = true;
+}
+
+// Load a world from a file (World::Load, world.cc:380-400). The World is leaked on purpose:
+// ~World crashes in the reference itself.
+void *ref_world_load_file(const char *path)
+{
+  ensure_init();
+  World *w = new World("oracle");
+  if (!w->Load(std::string(path)))
+    return NULL;
+  rec.world = w;
+  return w;
+}
+
+// Load a world from worldfile text held in memory (World::Load(istream&), world.cc:385).
+void *ref_world_load_text(const char *text, const char *path_hint)
+{
+  ensure_init();
+  World *w = new World("oracle");
+  std::istringstream ss(text);
+  if (!w->Load(ss, std::string(path_hint ? path_hint : "")))
+    return NULL;
+  rec.world = w;
+  return w;
+}
+
+// Run n simulation ticks (World::Update, world.cc:605-676), logging a TICK event after each.
+// Returns the number of ticks actually run (stops early at quit_time).
+int ref_world_update(void *wv, int n)
+{
+  World *w = (World *)wv;
+  int done = 0;
+  for (int i = 0; i < n; i++) {
+    bool quit = w->Update();
+    done++;
+    if (rec.active) {
+      std::lock_guard<std::mutex> g(rec.mu);
+      TraceEvent e;
+      memset(&e, 0, sizeof(e));
+      e.type = TRACE_EV_TICK;
+      e.block = (uint32_t)w->updates;
+      rec.events.push_back(e);
+      rec.n_ticks++;
+    }
+    if (quit)
+      break;
+  }
+  return done;
+}
+
+double ref_world_ppm(void *wv) { return ((World *)wv)->ppm; }
+uint64_t ref_world_updates(void *wv) { return ((World *)wv)->updates; }
+
+// Stop recording and write the trace (oracle/trace_format.h). Returns 0 on success.
+int ref_trace_end(void *wv, const char *path)
+{
+  World *w = (World *)wv;
+  std::lock_guard<std::mutex> g(rec.mu);
+  rec.active = false;
+  std::vector<TraceModel> models;
+  // World::models is a std::set<Model*> (stage.hh:788); emit sorted by id for stable files
+  for (std::set<Model *>::iterator it = w->models.begin(); it != w->models.end(); ++it) {
+    const Model *m = *it;
+    TraceModel tm;
+    memset(&tm, 0, sizeof(tm));
+    tm.id = m->id;
+    tm.parent = m->parent ? m->parent->id : 0xffffffffu;
+    tm.root = root_id(m);
+    tm.fiducial_return = m->vis.fiducial_return;
+    tm.fiducial_key = m->vis.fiducial_key;
+    tm.flags = (m->vis.gripper_return ? TRACE_FLAG_GRIPPER_RETURN : 0) |
+               (m->vis.obstacle_return ? TRACE_FLAG_OBSTACLE_RETURN : 0) |
+               (m->vis.blob_return ? TRACE_FLAG_BLOB_RETURN : 0);
+    tm.ranger_return = m->vis.ranger_return;
+    tm.color[0] = m->color.r;
+    tm.color[1] = m->color.g;
+    tm.color[2] = m->color.b;
+    tm.color[3] = m->color.a;
+    strncpy(tm.type, m->type.c_str(), sizeof(tm.type) - 1);
+    models.push_back(tm);
+  }
+  std::sort(models.begin(), models.end(),
+            [](const TraceModel &a, const TraceModel &b) { return a.id < b.id; });
+  TraceHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, STG_TRACE_MAGIC, 8);
+  h.ppm = w->ppm;
+  h.n_models = (uint32_t)models.size();
+  h.n_events = (uint32_t)rec.events.size();
+  h.n_verts = (uint32_t)(rec.verts.size() / 2);
+  h.n_rays = (uint32_t)rec.rays.size();
+  h.n_ticks = rec.n_ticks;
+  FILE *f = fopen(path, "wb");
+  if (!f)
+    return -1;
+  fwrite(&h, sizeof(h), 1, f);
+  fwrite(models.data(), sizeof(TraceModel), models.size(), f);
+  fwrite(rec.events.data(), sizeof(TraceEvent), rec.events.size(), f);
+  fwrite(rec.verts.data(), sizeof(int32_t), rec.verts.size(), f);
+  fwrite(rec.rays.data(), sizeof(TraceRay), rec.rays.size(), f);
+  fclose(f);
+  return 0;
+}
+
+// Trace n rays with the reference's own World::Raytrace (world.cc:746-754 -> :756-963), split
+// over nthreads host threads (the world must be quiescent: Raytrace is read-only). Not recorded.
+// Returns the wall-clock seconds spent inside the tracing loops (max over threads).
+double ref_raytrace_batch(void *wv, uint64_t n, const RefRayIn *in, RefRayOut *out, int nthreads)
+{
+  World *w = (World *)wv;
+  if (nthreads < 1)
+    nthreads = 1;
+  std::vector<Model *> byid;
+  for (std::set<Model *>::iterator it = w->models.begin(); it != w->models.end(); ++it) {
+    if ((*it)->id >= byid.size())
+      byid.resize((*it)->id + 1, NULL);
+    byid[(*it)->id] = *it;
+  }
+  std::vector<double> secs(nthreads, 0.0);
+  auto work = [&](int t) {
+    tl_quiet++;
+    const uint64_t lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+    auto t0 = std::chrono::steady_clock::now();
+    for (uint64_t i = lo; i < hi; i++) {
+      const RefRayIn &r = in[i];
+      ray_test_func_t fn = r.kind == TRACE_KIND_RANGER
+                               ? h_ranger_match
+                               : r.kind == TRACE_KIND_GRIPPER ? h_gripper_match : h_unrelated_match;
+      RaytraceResult res =
+          w->Raytrace(Pose(r.ox, r.oy, r.oz, r.oa), r.range, fn, byid[r.finder], NULL, r.ztest != 0);
+      out[i].range = res.range;
+      out[i].hit_model = res.mod ? (int32_t)res.mod->id : -1;
+    }
+    secs[t] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    tl_quiet--;
+  };
+  if (nthreads == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++)
+      th.emplace_back(work, t);
+    for (auto &x : th)
+      x.join();
+  }
+  return *std::max_element(secs.begin(), secs.end());
+}
+
+// Dump the reference's occupancy grid: one record per (layer, cell, position-in-list) entry of
+// Cell::blocks[layer] (region.hh:47), in list order. Blocks are named by the recorder's dense ids
+// (so call this between ref_trace_begin and ref_trace_end). out may be NULL to just count.
+// Record = {layer, x, y, pos, block} as int32[5]. Also returns Region::count per region when
+// counts != NULL: {rx, ry, count} int64[3] for regions with count > 0.
+int64_t ref_dump_grid(void *wv, int32_t *out, int64_t cap, int64_t *counts, int64_t counts_cap,
+                      int64_t *n_counts)
+{
+  World *w = (World *)wv;
+  int64_t n = 0, nc = 0;
+  std::lock_guard<std::mutex> g(rec.mu);
+  for (std::map<point_int_t, SuperRegion *>::iterator it = w->superregions.begin();
+       it != w->superregions.end(); ++it) {
+    SuperRegion *sr = it->second;
+    for (int ry = 0; ry < SUPERREGIONWIDTH; ry++)
+      for (int rx = 0; rx < SUPERREGIONWIDTH; rx++) {
+        Region *reg = sr->GetRegion(rx, ry);
+        const int64_t gx = ((int64_t)sr->origin.x << SBITS) + rx, gy = ((int64_t)sr->origin.y << SBITS) + ry;
+        if (reg->count) {
+          if (counts && nc < counts_cap) {
+            counts[3 * nc] = gx;
+            counts[3 * nc + 1] = gy;
+            counts[3 * nc + 2] = (int64_t)reg->count;
+          }
+          nc++;
+        }
+        if (reg->cells.empty())
+          continue;
+        for (int cy = 0; cy < REGIONWIDTH; cy++)
+          for (int cx = 0; cx < REGIONWIDTH; cx++) {
+            Cell &c = reg->cells[cx + cy * REGIONWIDTH];
+            for (int layer = 0; layer < 2; layer++)
+              for (size_t p = 0; p < c.blocks[layer].size(); p++) {
+                if (out && n < cap) {
+                  int32_t *o = out + 5 * n;
+                  o[0] = layer;
+                  o[1] = (int32_t)(gx * REGIONWIDTH + cx);
+                  o[2] = (int32_t)(gy * REGIONWIDTH + cy);
+                  o[3] = (int32_t)p;
+                  std::map<const Block *, uint32_t>::iterator bi = rec.block_ids.find(c.blocks[layer][p]);
+                  o[4] = bi == rec.block_ids.end() ? -1 : (int32_t)bi->second;
+                }
+                n++;
+              }
+          }
+      }
+  }
+  if (n_counts)
+    *n_counts = nc;
+  return n;
+}
+
+// Look a model up by name (World::GetModel, world.cc) -> Model::id, or -1.
+int32_t ref_model_id(void *wv, const char *name)
+{
+  World *w = (World *)wv;
+  Model *m = w->GetModel(std::string(name));
+  return m ? (int32_t)m->id : -1;
+}
+
+// Global pose of a model (Model::GetGlobalPose, model.cc:1205-1218).
+int ref_model_pose(void *wv, uint32_t id, double *xyza)
+{
+  World *w = (World *)wv;
+  for (std::set<Model *>::iterator it = w->models.begin(); it != w->models.end(); ++it)
+    if ((*it)->id == id) {
+      Pose p = (*it)->GetGlobalPose();
+      xyza[0] = p.x;
+      xyza[1] = p.y;
+      xyza[2] = p.z;
+      xyza[3] = p.a;
+      return 0;
+    }
+  return -1;
+}
+
+// Copy a ranger sensor's latest scan (ModelRanger::Sensor, stage.hh:2643-2645). Returns
+// sample_count, or -1. Any of the output pointers may be NULL.
+int ref_ranger_scan(void *wv, uint32_t id, int sensor, double *ranges, double *intensities,
+                    double *bearings, int cap)
+{
+  World *w = (World *)wv;
+  for (std::set<Model *>::iterator it = w->models.begin(); it != w->models.end(); ++it)
+    if ((*it)->id == id) {
+      ModelRanger *r = dynamic_cast<ModelRanger *>(*it);
+      if (!r || sensor >= (int)r->GetSensors().size())
+        return -1;
+      const ModelRanger::Sensor &s = r->GetSensors()[sensor];
+      const int n = (int)s.ranges.size();
+      for (int i = 0; i < n && i < cap; i++) {
+        if (ranges)
+          ranges[i] = s.ranges[i];
+        if (intensities)
+          intensities[i] = s.intensities[i];
+        if (bearings)
+          bearings[i] = s.bearings[i];
+      }
+      return n;
+    }
+  return -1;
+}
+
+} // extern "C"

@@ -1,0 +1,71 @@
+/* Event-trace format shared by the reference harness (oracle/ref_harness.cc, which WRITES traces
+ * by interposing the unmodified reference), the T1 restatement (oracle/t1_oracle.cc, which
+ * REPLAYS them) and the python reader (tests/trace_io.py). TEST INFRASTRUCTURE ONLY.
+ *
+ * A trace is everything the raycast hot path saw during a run of the reference, in call order:
+ *   MAP    Block::Map(layer)      block.cc:170-181  -> pixel-space polygon + global z bounds
+ *   UNMAP  Block::UnMap(layer)    block.cc:183-189
+ *   RAYS   World::Raytrace(Ray)   world.cc:756-963  -> inputs and the reference's answer
+ *   TICK   World::Update finished world.cc:605-676
+ * Layout: TraceHeader, TraceModel[n_models], TraceEvent[n_events], int32 verts[2*n_verts],
+ * TraceRay[n_rays]. Little-endian, natural alignment, no padding surprises (all structs are
+ * multiples of 8 bytes).
+ */
+#ifndef STG_TRACE_FORMAT_H
+#define STG_TRACE_FORMAT_H
+#include <stdint.h>
+
+#define STG_TRACE_MAGIC "STGTRC02"
+
+enum { TRACE_EV_MAP = 1, TRACE_EV_UNMAP = 2, TRACE_EV_RAYS = 3, TRACE_EV_TICK = 4 };
+
+/* predicate kinds: which of the reference's static ray_test_func_t a ray was traced with */
+enum {
+  TRACE_KIND_RANGER = 0,    /* ranger_match              model_ranger.cc:158-170 */
+  TRACE_KIND_UNRELATED = 1, /* fiducial_raytrace_match / blob_match / bumper_match
+                               model_fiducial.cc:103-107, model_blobfinder.cc:102-107,
+                               model_bumper.cc:157-162 */
+  TRACE_KIND_GRIPPER = 2    /* gripper_raytrace_match    model_gripper.cc:329-336 */
+};
+
+#define TRACE_FLAG_GRIPPER_RETURN 1u
+#define TRACE_FLAG_OBSTACLE_RETURN 2u
+#define TRACE_FLAG_BLOB_RETURN 4u
+
+typedef struct {
+  char magic[8];
+  double ppm;
+  uint32_t n_models, n_events, n_verts, n_rays;
+  uint32_t n_ticks, reserved;
+} TraceHeader; /* 40 B */
+
+typedef struct {
+  uint32_t id;     /* Model::id (stage.hh:1794) */
+  uint32_t parent; /* 0xffffffff for a top-level model */
+  uint32_t root;   /* id of the top of this model's tree; IsRelated == same root (model.cc:446-466) */
+  int32_t fiducial_return, fiducial_key;
+  uint32_t flags;
+  double ranger_return;
+  double color[4];
+  char type[16];
+} TraceModel; /* 80 B */
+
+typedef struct {
+  uint8_t type, layer;
+  uint16_t n_pts;  /* MAP: polygon vertex count */
+  uint32_t block;  /* MAP/UNMAP: dense block id (order of first appearance); TICK: World::updates */
+  uint32_t model;  /* MAP: owning model id; RAYS: ray count */
+  uint32_t first;  /* MAP: first vertex index; RAYS: first ray index */
+  double zmin, zmax; /* MAP: Block::global_z after the call */
+} TraceEvent; /* 32 B */
+
+typedef struct {
+  double ox, oy, oz, oa; /* Ray::origin (global) */
+  double range;          /* Ray::range */
+  double res_range;      /* RaytraceResult::range */
+  int32_t hit_model;     /* RaytraceResult::mod->id, or -1 */
+  uint32_t finder;       /* Ray::mod->id */
+  uint8_t kind, ztest, layer, pad[5];
+} TraceRay; /* 64 B */
+
+#endif
