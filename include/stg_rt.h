@@ -1,0 +1,245 @@
+/* stg_rt.h - C ABI of libstg_rt.so: Stage's per-tick sensor raycast path on one B200.
+ *
+ * This is the boundary a lightly patched libstage binds (INTEGRATION.md shows the patch): plain C,
+ * POD arguments, integer return codes, no STL / torch / CUDA types. Every entry point names the
+ * reference interface it stands in for (file:line under rtv/Stage 4.3.0, libstage/).
+ *
+ * Model of use, mirroring one World::Update (world.cc:605-676):
+ *   load time    stg_rt_create; stg_rt_model_upsert per Model; stg_rt_block_map per Block::Map
+ *   every tick   sensor Update()s call stg_rt_fans_submit instead of looping World::Raytrace;
+ *                Block::Map / Block::UnMap (from ModelPosition::Move, Model::SetPose ...) also call
+ *                stg_rt_block_map / stg_rt_block_unmap;
+ *                World::Update calls stg_rt_flush + stg_rt_sync before CallUpdateCallbacks
+ *                (world.cc:668), the first point anybody reads sensor data.
+ * Calls are applied in issue order: a fan sees exactly the map/unmap calls issued before it.
+ *
+ * Identity: models and blocks are named by dense uint32 ids chosen by the caller (Model::id,
+ * stage.hh:1794, for models). Pointers never cross the boundary.
+ *
+ * Threading: every entry point may be called from any thread (libstage runs fiducial Update()s on
+ * worker threads, world.cc:228-262); calls are serialised inside.
+ *
+ * Errors: 0 = ok, negative = error (STG_RT_E*); stg_rt_last_error gives text. The library never
+ * calls exit() and has NO CPU fallback: if the GPU path cannot run, the call fails.
+ */
+#ifndef STG_RT_H
+#define STG_RT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STG_RT_ABI_VERSION 1
+
+enum {
+  STG_RT_OK = 0,
+  STG_RT_EINVAL = -1,   /* bad argument */
+  STG_RT_ECUDA = -2,    /* CUDA runtime error (text in stg_rt_last_error) */
+  STG_RT_ENOMEM = -3,   /* a fixed-capacity table is full (models, blocks, cell entries) */
+  STG_RT_EEXTENT = -4,  /* a polygon leaves the device grid extent given at create */
+  STG_RT_ESTATE = -5,   /* call not valid in the current state (e.g. map of a mapped block) */
+  STG_RT_ENODEV = -6    /* no usable CUDA device */
+};
+
+/* Ray filter predicates: the reference's five static ray_test_func_t (stage.hh:569). */
+enum {
+  STG_RT_PRED_RANGER = 0,    /* ranger_match, model_ranger.cc:158-170: hit is outside the finder's
+                                model tree and hit.vis.ranger_return >= 0 */
+  STG_RT_PRED_UNRELATED = 1, /* fiducial_raytrace_match model_fiducial.cc:103-107, blob_match
+                                model_blobfinder.cc:102-107, bumper_match model_bumper.cc:157-162:
+                                hit is outside the finder's model tree (Model::IsRelated,
+                                model.cc:446-466) */
+  STG_RT_PRED_GRIPPER = 2    /* gripper_raytrace_match, model_gripper.cc:329-336:
+                                hit != finder and hit.vis.gripper_return */
+};
+
+/* How the per-beam headings of a fan are generated. */
+enum {
+  STG_RT_ANGLES_RANGER = 0,  /* ModelRanger::Sensor::Update, model_ranger.cc:232-255: heading of
+                                beam t is (double)(float)a_t, a_0 = origin.a,
+                                a_{t+1} = (double)(float)a_t + fov/max(n-1,1). origin is the pose
+                                of the FIRST ray (rayorg after LocalToGlobal, :226-230) */
+  STG_RT_ANGLES_EVEN_FOV = 1,/* World::Raytrace(gpose,range,fov,...), world.cc:721-744: heading of
+                                beam s is s*fov/(n-1) - (fov/2 - origin.a) */
+  STG_RT_ANGLES_EXPLICIT = 2 /* headings[] supplied by the caller (single rays: fiducial line of
+                                sight model_fiducial.cc:179, bumper, gripper) */
+};
+
+/* Model::Visibility bits the predicates read (stage.hh:1924-1937). */
+#define STG_RT_VIS_GRIPPER_RETURN 1u
+#define STG_RT_VIS_OBSTACLE_RETURN 2u
+#define STG_RT_VIS_BLOB_RETURN 4u
+
+/* stg_rt_config.flags */
+#define STG_RT_CFG_DEFAULT 0u
+
+typedef struct stg_rt_ctx stg_rt_ctx;
+
+typedef struct {
+  uint32_t struct_size;   /* sizeof(stg_rt_config), for ABI growth */
+  int32_t device;         /* CUDA device ordinal */
+  double ppm;             /* World::ppm = 1/resolution (world.cc:406) */
+  /* Dense device grid extent in SuperRegion units (1024 x 1024 cells each, region.hh:13-18):
+     superregions [sreg_x0, sreg_x0+sreg_nx) x [sreg_y0, sreg_y0+sreg_ny). Rays may leave it
+     (outside is empty space, as for a missing SuperRegion, world.cc:820-823); polygons may not. */
+  int32_t sreg_x0, sreg_y0, sreg_nx, sreg_ny;
+  uint32_t max_models;    /* capacity of the model table */
+  uint32_t max_blocks;    /* capacity of the block table */
+  uint32_t max_cell_entries; /* expected peak number of (cell, block) entries per layer; the
+                                per-layer cell-entry table is sized to >= 2x this. 0 = 1<<22 */
+  uint32_t flags;
+} stg_rt_config;
+
+/* One sensor fan = one call of ModelRanger::Sensor::Update, one World::Raytrace(fan), or a group of
+   explicit single rays sharing finder / origin / range. 64 bytes. */
+typedef struct {
+  uint32_t finder;        /* Ray::mod (stage.hh:718) */
+  uint32_t n_samples;     /* sample_count / results.size() / number of explicit headings */
+  uint8_t pred;           /* STG_RT_PRED_* */
+  uint8_t ztest;          /* Ray::ztest */
+  uint8_t layer;          /* layer to read: (World::updates + 1) % 2 at call time (world.cc:804) */
+  uint8_t angles;         /* STG_RT_ANGLES_* */
+  uint32_t first_heading; /* EXPLICIT: index of this fan's first heading in headings[] */
+  double ox, oy, oz, oa;  /* global origin pose (Ray::origin; see STG_RT_ANGLES_*) */
+  double range;           /* Ray::range (Sensor::range.max, fiducial max_range_anon, ...) */
+  double fov;             /* RANGER / EVEN_FOV */
+} stg_rt_fan;
+
+/* Where the results of one submit go. All arrays are indexed by beam in fan order (fan 0's
+   beams, then fan 1's, ...), length = sum of n_samples. NULL = not wanted (not computed or not
+   copied back). Buffers stay owned by the caller and must remain valid until stg_rt_sync returns.
+   Buffers obtained from stg_rt_host_alloc are written by the GPU directly (no staging copy). */
+typedef struct {
+  double *ranges;       /* RaytraceResult::range -> Sensor::ranges (model_ranger.cc:244-248) */
+  double *intensities;  /* hit ? hit.vis.ranger_return : 0 -> Sensor::intensities (:250) */
+  double *bearings;     /* RANGER: start_angle + t*sample_incr -> Sensor::bearings (:251);
+                           others: the beam heading relative to origin.a */
+  int32_t *hit_model;   /* RaytraceResult::mod as a model id, -1 = no hit */
+  int32_t *hit_cell;    /* 2 x int32 per beam: global cell index of the hit cell */
+  uint32_t *steps;      /* 2 x uint32 per beam: cell visits C, region probes R (diagnostics) */
+} stg_rt_fan_out;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+
+/* Replaces: nothing in the reference (the CPU grid is created lazily, world.cc:1058-1093).
+   Called from World::LoadWorldPostHook (world.cc:402) once ppm is known. */
+int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out);
+/* Called from atexit, NOT from ~World (which crashes in the reference). */
+int stg_rt_destroy(stg_rt_ctx *ctx);
+/* Text of the last error on this context (or of a failed create when ctx == NULL). */
+const char *stg_rt_last_error(const stg_rt_ctx *ctx);
+int stg_rt_abi_version(void);
+
+/* ---- world state ------------------------------------------------------------------------ */
+
+/* Publish the attributes of a model that the ray predicates read: Model::vis (stage.hh:1924-1937),
+   the root of its tree (Model::IsRelated == same root, model.cc:446-466) and its colour
+   (RaytraceResult::color, world.cc:853). Call at creation and whenever one changes
+   (SetRangerReturn, SetFiducialReturn, SetParent, SetColor ...). rgba may be NULL. */
+int stg_rt_model_upsert(stg_rt_ctx *ctx, uint32_t id, uint32_t root_id, double ranger_return,
+                        int32_t fiducial_return, int32_t fiducial_key, uint32_t vis_flags,
+                        const double *rgba);
+
+/* Block::Map(layer), block.cc:170-181: xy = the n_pts pixel-space vertices Model::LocalToPixels
+   produced (model.cc:474-491), i.e. the argument of World::MapPoly (world.cc:990); zmin/zmax =
+   Block::global_z after the call (shared by both layers). The block must not be mapped on that
+   layer (the reference always UnMaps first). */
+int stg_rt_block_map(stg_rt_ctx *ctx, uint32_t block_id, uint32_t model_id, int layer, double zmin,
+                     double zmax, int n_pts, const int32_t *xy);
+/* Block::UnMap(layer), block.cc:183-189. Unmapping an unmapped block is a no-op, as there. */
+int stg_rt_block_unmap(stg_rt_ctx *ctx, uint32_t block_id, int layer);
+
+/* ---- rays --------------------------------------------------------------------------------- */
+
+/* Queue fans. Replaces the beam loops of ModelRanger::Sensor::Update (model_ranger.cc:232-255),
+   World::Raytrace(fan) (world.cc:721-744, used by ModelBlobfinder::Update model_blobfinder.cc:170)
+   and single World::Raytrace(Ray) calls (world.cc:756; ModelFiducial::AddModelIfVisible
+   model_fiducial.cc:179). fans[] and headings[] are copied before the call returns.
+   headings: one double per beam of the EXPLICIT fans (global heading, Ray::origin.a), else NULL.
+   trig: NULL, or 2 doubles (cos, sin of the heading the reference would pass to cos()/sin(),
+   world.cc:773-775) per beam of this submit in beam order - "strict" mode: use the host libm's
+   values instead of the device's, for bit-for-bit agreement with a CPU run on that host. */
+int stg_rt_fans_submit(stg_rt_ctx *ctx, uint32_t n_fans, const stg_rt_fan *fans,
+                       const double *headings, const double *trig, const stg_rt_fan_out *out);
+
+/* Start everything queued (deltas, then fans) on the GPU without waiting. Implicitly done by
+   stg_rt_sync, and by a map/unmap issued while fans are still queued (ordering rule above). */
+int stg_rt_flush(stg_rt_ctx *ctx);
+/* Wait for all started work and deliver results into the stg_rt_fan_out buffers. Called from
+   World::Update after the worker threads finished (world.cc:650-657), before :668. */
+int stg_rt_sync(stg_rt_ctx *ctx);
+
+/* Page-locked host memory the GPU can write results into directly. */
+void *stg_rt_host_alloc(stg_rt_ctx *ctx, size_t bytes);
+int stg_rt_host_free(stg_rt_ctx *ctx, void *p);
+
+/* ---- resident fan sets: inputs and outputs stay in HBM ------------------------------------ */
+/* For callers that keep sensor geometry on the device across ticks (and for measuring the kernels
+   alone). A set is a batch of fans uploaded once; stg_rt_set_trace re-traces it against the current
+   grid; results stay on the device until stg_rt_set_download. */
+typedef struct stg_rt_set stg_rt_set;
+int stg_rt_set_create(stg_rt_ctx *ctx, uint32_t n_fans, const stg_rt_fan *fans, const double *headings,
+                      const double *trig, uint32_t want /* STG_RT_WANT_* */, stg_rt_set **out);
+int stg_rt_set_destroy(stg_rt_ctx *ctx, stg_rt_set *set);
+/* Replace the origin pose / layer of every fan of the set (robots moved): n_fans entries. */
+int stg_rt_set_update_origins(stg_rt_ctx *ctx, stg_rt_set *set, const double *xyza, int layer);
+/* Asynchronous: applies queued deltas first, then traces. */
+int stg_rt_set_trace(stg_rt_ctx *ctx, stg_rt_set *set);
+int stg_rt_set_download(stg_rt_ctx *ctx, stg_rt_set *set, const stg_rt_fan_out *out);
+/* Device pointers of the set's result arrays (NULL members for arrays not in `want`). */
+int stg_rt_set_device_ptrs(stg_rt_ctx *ctx, stg_rt_set *set, stg_rt_fan_out *dev);
+uint64_t stg_rt_set_beams(const stg_rt_set *set);
+
+#define STG_RT_WANT_RANGES 1u
+#define STG_RT_WANT_INTENSITIES 2u
+#define STG_RT_WANT_BEARINGS 4u
+#define STG_RT_WANT_HIT_MODEL 8u
+#define STG_RT_WANT_HIT_CELL 16u
+#define STG_RT_WANT_STEPS 32u
+
+/* ---- grid inspection (parity tests; World::Raytrace debug aids rt_cells, stage.hh:873) ------ */
+
+/* Copy out every (cell, block) entry of the device grid as int32[5] records
+   {layer, x, y, seq_rank, block}: seq_rank = position of the entry in the reference's per-cell
+   list order (Cell::blocks[layer], region.hh:47). Returns the entry count (may exceed cap), < 0 on
+   error. Also Region::count (both layers, region.cc:19-34) as int64[3] {rx, ry, count} records. */
+int64_t stg_rt_grid_dump(stg_rt_ctx *ctx, int32_t *records, int64_t cap, int64_t *region_counts,
+                         int64_t counts_cap, int64_t *n_counts);
+
+/* ---- multi-GPU: moved-block deltas ---------------------------------------------------------- */
+/* Robots are sharded over ranks (one process per GPU), the grid is replicated. Each tick every rank
+   serialises the deltas its own robots produced, the ranks all-gather the byte blobs (NCCL over
+   NVLink, done by the caller: torch.distributed / ncclAllGather), and every rank applies the other
+   ranks' blobs. Blobs are applied in rank order so that all replicas, and a single-GPU run that
+   issues the same maps in rank order, hold identical grids. */
+
+/* Move the deltas queued since the last flush into a device buffer owned by the context and return
+   its address and size (fixed-size records). They are NOT applied locally yet. */
+int stg_rt_delta_export(stg_rt_ctx *ctx, int rank, void **dev_blob, size_t *n_bytes);
+/* Size every rank must use as the per-rank slot of the all-gather buffer. */
+size_t stg_rt_delta_slot_bytes(const stg_rt_ctx *ctx);
+/* Apply n_ranks blobs laid out back to back, slot_bytes apart, in a DEVICE buffer (the all-gather
+   output), in rank order, directly out of that buffer. Includes this rank's own blob. */
+int stg_rt_delta_apply_gathered(stg_rt_ctx *ctx, const void *dev_gathered, int n_ranks, size_t slot_bytes);
+
+/* ---- plumbing -------------------------------------------------------------------------------- */
+/* Run all work of this context on the given cudaStream_t (e.g. torch's current stream) instead of
+   the context's own stream. NULL restores the own stream. */
+int stg_rt_set_stream(stg_rt_ctx *ctx, void *cuda_stream);
+void *stg_rt_get_stream(stg_rt_ctx *ctx);
+
+/* Counters since create: kernel launches by kind, rays traced, bytes copied each way. */
+typedef struct {
+  uint64_t launches_rasterise, launches_march, launches_post, launches_other;
+  uint64_t beams, fans, map_calls, unmap_calls, edge_steps;
+  uint64_t h2d_bytes, d2h_bytes;
+} stg_rt_stats;
+int stg_rt_get_stats(stg_rt_ctx *ctx, stg_rt_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STG_RT_H */

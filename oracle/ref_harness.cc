@@ -42,6 +42,7 @@ struct Recorder {
   std::vector<TraceEvent> events;
   std::vector<int32_t> verts;
   std::vector<TraceRay> rays;
+  std::vector<double> aux;
   std::map<const Block *, uint32_t> block_ids;
   std::map<ray_test_func_t, int> kinds;
   uint32_t n_ticks = 0;
@@ -206,6 +207,40 @@ RaytraceResult World::Raytrace(const Ray &r)
   return res;
 }
 
+void ModelRanger::Sensor::Update(ModelRanger *mod)
+{
+  typedef void (*fn_t)(ModelRanger::Sensor *, ModelRanger *);
+  static fn_t fn = real<fn_t>("_ZN3Stg11ModelRanger6Sensor6UpdateEPS0_");
+  // what a patched libstage would hand to stg_rt_fans_submit: the pose of the first ray,
+  // computed exactly as model_ranger.cc:222-230 does before the beam loop
+  const double start_angle = (sample_count > 1 ? -fov / 2.0 : 0.0);
+  Pose rayorg(pose);
+  rayorg.a += start_angle;
+  rayorg.z += size.z / 2.0;
+  rayorg = mod->LocalToGlobal(rayorg);
+  const unsigned int layer = (mod->world->updates + 1) % 2;
+  fn(this, mod);
+  if (!rec.active || tl_quiet || range_noise != 0 || range_noise_const != 0 || angle_noise != 0)
+    return;
+  std::lock_guard<std::mutex> g(rec.mu);
+  TraceEvent e;
+  memset(&e, 0, sizeof(e));
+  e.type = TRACE_EV_RANGER_SCAN;
+  e.layer = (uint8_t)layer;
+  e.n_pts = (uint16_t)sample_count;
+  e.model = mod->id;
+  for (size_t i = 0; i < mod->sensors.size(); i++)
+    if (&mod->sensors[i] == this)
+      e.block = (uint32_t)i;
+  e.first = (uint32_t)rec.aux.size();
+  const double hdr[TRACE_SCAN_HEADER_DOUBLES] = { rayorg.x, rayorg.y, rayorg.z, rayorg.a, range.max, fov };
+  rec.aux.insert(rec.aux.end(), hdr, hdr + TRACE_SCAN_HEADER_DOUBLES);
+  rec.aux.insert(rec.aux.end(), ranges.begin(), ranges.end());
+  rec.aux.insert(rec.aux.end(), intensities.begin(), intensities.end());
+  rec.aux.insert(rec.aux.end(), bearings.begin(), bearings.end());
+  rec.events.push_back(e);
+}
+
 // ---------------------------------------------------------------- C interface for ctypes
 
 extern "C" {
@@ -242,6 +277,7 @@ void ref_trace_begin(void)
   rec.events.clear();
   rec.verts.clear();
   rec.rays.clear();
+  rec.aux.clear();
   rec.block_ids.clear();
   rec.kinds.clear();
   rec.n_ticks = 0;
@@ -338,6 +374,7 @@ int ref_trace_end(void *wv, const char *path)
   h.n_verts = (uint32_t)(rec.verts.size() / 2);
   h.n_rays = (uint32_t)rec.rays.size();
   h.n_ticks = rec.n_ticks;
+  h.n_aux = (uint32_t)rec.aux.size();
   FILE *f = fopen(path, "wb");
   if (!f)
     return -1;
@@ -346,6 +383,7 @@ int ref_trace_end(void *wv, const char *path)
   fwrite(rec.events.data(), sizeof(TraceEvent), rec.events.size(), f);
   fwrite(rec.verts.data(), sizeof(int32_t), rec.verts.size(), f);
   fwrite(rec.rays.data(), sizeof(TraceRay), rec.rays.size(), f);
+  fwrite(rec.aux.data(), sizeof(double), rec.aux.size(), f);
   fclose(f);
   return 0;
 }

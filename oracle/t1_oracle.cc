@@ -336,6 +336,17 @@ static void trace_one(const T1World *w, const T1RayIn &r, const double *trig, T1
   }
 }
 
+// (cos, sin) of each heading exactly as World::Raytrace would compute them on this host
+// (world.cc:773-775: a heading of exactly 0 is replaced by 1e-12). out = 2 doubles per angle.
+void t1_libm_trig(uint64_t n, const double *headings, double *out)
+{
+  for (uint64_t i = 0; i < n; i++) {
+    const double ang = (headings[i] == 0.0) ? 1e-12 : headings[i];
+    out[2 * i] = cos(ang);
+    out[2 * i + 1] = sin(ang);
+  }
+}
+
 // trig: NULL, or 2 doubles per ray (cos, sin) to use instead of libm.
 void t1_raytrace(void *wv, uint64_t n, const T1RayIn *in, const double *trig, T1Hit *out)
 {
@@ -447,6 +458,7 @@ int64_t t1_dump_grid(void *wv, int32_t *out, int64_t cap, int64_t *counts, int64
 typedef struct {
   uint64_t rays, range_mismatch, model_mismatch, maps, unmaps, ticks;
   uint64_t cell_visits, region_probes;
+  uint64_t scans, scan_mismatch;
   double max_range_err;
 } T1ReplayStats;
 
@@ -467,10 +479,12 @@ void *t1_replay(const char *path, T1ReplayStats *st)
   std::vector<TraceEvent> events(h.n_events);
   std::vector<int32_t> verts(2 * (size_t)h.n_verts);
   std::vector<TraceRay> rays(h.n_rays);
+  std::vector<double> aux(h.n_aux);
   bool ok = fread(models.data(), sizeof(TraceModel), models.size(), f) == models.size() &&
             fread(events.data(), sizeof(TraceEvent), events.size(), f) == events.size() &&
             fread(verts.data(), sizeof(int32_t), verts.size(), f) == verts.size() &&
-            fread(rays.data(), sizeof(TraceRay), rays.size(), f) == rays.size();
+            fread(rays.data(), sizeof(TraceRay), rays.size(), f) == rays.size() &&
+            fread(aux.data(), sizeof(double), aux.size(), f) == aux.size();
   fclose(f);
   if (!ok)
     return NULL;
@@ -488,6 +502,15 @@ void *t1_replay(const char *path, T1ReplayStats *st)
       st->unmaps++;
     } else if (e.type == TRACE_EV_TICK) {
       st->ticks++;
+    } else if (e.type == TRACE_EV_RANGER_SCAN) {
+      const uint32_t n = e.n_pts;
+      const double *a = &aux[e.first];
+      std::vector<double> rg(n), in(n), be(n);
+      t1_ranger_fan(w, e.model, e.layer, a, a[4], a[5], n, rg.data(), in.data(), be.data(), NULL);
+      const double *ref = a + TRACE_SCAN_HEADER_DOUBLES;
+      st->scans++;
+      if (memcmp(rg.data(), ref, 8 * n) || memcmp(in.data(), ref + n, 8 * n) || memcmp(be.data(), ref + 2 * n, 8 * n))
+        st->scan_mismatch++;
     } else if (e.type == TRACE_EV_RAYS) {
       for (uint32_t k = 0; k < e.model; k++) {
         const TraceRay &tr = rays[e.first + k];

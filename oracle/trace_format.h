@@ -7,17 +7,20 @@
  *   UNMAP  Block::UnMap(layer)    block.cc:183-189
  *   RAYS   World::Raytrace(Ray)   world.cc:756-963  -> inputs and the reference's answer
  *   TICK   World::Update finished world.cc:605-676
+ *   RANGER_SCAN  ModelRanger::Sensor::Update model_ranger.cc:211-256 -> the fan's inputs and the
+ *          ranges / intensities / bearings it left in the Sensor (logged AFTER its RAYS)
  * Layout: TraceHeader, TraceModel[n_models], TraceEvent[n_events], int32 verts[2*n_verts],
- * TraceRay[n_rays]. Little-endian, natural alignment, no padding surprises (all structs are
+ * TraceRay[n_rays], double aux[n_aux]. Little-endian, natural alignment, no padding surprises (all structs are
  * multiples of 8 bytes).
  */
 #ifndef STG_TRACE_FORMAT_H
 #define STG_TRACE_FORMAT_H
 #include <stdint.h>
 
-#define STG_TRACE_MAGIC "STGTRC02"
+#define STG_TRACE_MAGIC "STGTRC03"
 
-enum { TRACE_EV_MAP = 1, TRACE_EV_UNMAP = 2, TRACE_EV_RAYS = 3, TRACE_EV_TICK = 4 };
+enum { TRACE_EV_MAP = 1, TRACE_EV_UNMAP = 2, TRACE_EV_RAYS = 3, TRACE_EV_TICK = 4,
+       TRACE_EV_RANGER_SCAN = 5 };
 
 /* predicate kinds: which of the reference's static ray_test_func_t a ray was traced with */
 enum {
@@ -36,7 +39,7 @@ typedef struct {
   char magic[8];
   double ppm;
   uint32_t n_models, n_events, n_verts, n_rays;
-  uint32_t n_ticks, reserved;
+  uint32_t n_ticks, n_aux;
 } TraceHeader; /* 40 B */
 
 typedef struct {
@@ -55,7 +58,7 @@ typedef struct {
   uint16_t n_pts;  /* MAP: polygon vertex count */
   uint32_t block;  /* MAP/UNMAP: dense block id (order of first appearance); TICK: World::updates */
   uint32_t model;  /* MAP: owning model id; RAYS: ray count */
-  uint32_t first;  /* MAP: first vertex index; RAYS: first ray index */
+  uint32_t first;  /* MAP: first vertex index; RAYS: first ray index; RANGER_SCAN: first aux index */
   double zmin, zmax; /* MAP: Block::global_z after the call */
 } TraceEvent; /* 32 B */
 
@@ -67,5 +70,11 @@ typedef struct {
   uint32_t finder;       /* Ray::mod->id */
   uint8_t kind, ztest, layer, pad[5];
 } TraceRay; /* 64 B */
+
+/* RANGER_SCAN: event.model = ranger model id, event.block = sensor index, event.n_pts = sample
+ * count n, event.layer = layer the rays read, aux[first..] = { ox, oy, oz, oa (the global pose of
+ * the first ray, rayorg after LocalToGlobal, model_ranger.cc:226-230), range_max, fov,
+ * ranges[n], intensities[n], bearings[n] }. */
+#define TRACE_SCAN_HEADER_DOUBLES 6
 
 #endif

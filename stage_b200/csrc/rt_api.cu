@@ -1,0 +1,1168 @@
+// Host runtime behind the C ABI of include/stg_rt.h: context, host shadow of the mapped blocks,
+// delta coalescing and blob building, fan batching, pinned staging, stream plumbing.
+// The compute is in rt_kernels.cu; there is no CPU implementation of any of it here.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/stg_rt.h"
+#include "rt_device.h"
+
+namespace stg {
+void launch_rehash(const unsigned long long *src, unsigned long long *dst, uint32_t slot_mask, void *stream);
+}
+
+using namespace stg;
+
+static_assert(sizeof(stg_rt_fan) == sizeof(FanRec), "stg_rt_fan and FanRec must share a layout");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct BlockShadow {
+  bool known = false;
+  uint32_t model = 0;
+  double zmin = 0, zmax = 0;
+  bool z_dirty = false;
+  // what the caller last said (host_*) and what the device grid currently holds (dev_*)
+  bool host_mapped[2] = { false, false }, dev_mapped[2] = { false, false }, dirty[2] = { false, false };
+  uint32_t map_seq[2] = { 0, 0 };
+  std::vector<int32_t> host_xy[2], dev_xy[2];
+};
+
+struct Submit {
+  uint64_t first_beam, n_beams;
+  stg_rt_fan_out out;
+};
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct FanArrays { // device arrays of one batch / resident set
+  DevBuf fans, first, headings_in, trig, heading;
+  DevBuf ranges, intens, bearings, hit_model, hit_cell, steps;
+};
+
+} // namespace
+
+struct stg_rt_set {
+  std::vector<FanRec> fans;
+  std::vector<uint32_t> first;
+  uint64_t n_beams = 0;
+  uint32_t want = 0;
+  bool has_trig = false, has_headings = false;
+  FanArrays d;
+  bool fans_dirty = true;
+};
+
+struct stg_rt_ctx {
+  std::mutex mu;
+  stg_rt_config cfg;
+  std::string err;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  GridView g;
+  size_t n_regions = 0;
+  uint32_t slot_cap = 0;
+  unsigned long long *spare_slots = nullptr;
+  int32_t cell_x0 = 0, cell_y0 = 0, cell_x1 = 0, cell_y1 = 0; // inclusive cell extent
+
+  std::vector<BlockShadow> blocks;
+  std::vector<uint32_t> dirty_units; // block*2 + layer, in order of first touch
+  std::vector<ModelUpd> model_upd;
+  std::vector<bool> model_known;
+  uint64_t epoch = 0;
+  uint32_t local_seq = 0;
+  int64_t live_entries[2] = { 0, 0 }; // cell visits currently rendered, per layer
+  int64_t used_upper[2] = { 0, 0 };   // upper bound of non-empty slots (entries + tombstones)
+
+  PinBuf h_blob;
+  DevBuf d_blob;
+  size_t blob_cap = 0;
+  cudaEvent_t blob_uploaded = nullptr; // the pinned blob may be rewritten once this has fired
+
+  // fans queued by stg_rt_fans_submit and not launched yet
+  std::vector<FanRec> q_fans;
+  std::vector<uint32_t> q_first;
+  std::vector<double> q_headings, q_trig;
+  std::vector<Submit> q_subs;
+  uint64_t q_beams = 0;
+  bool q_has_trig = false;
+  // launched, results not delivered yet
+  std::vector<Submit> f_subs;
+  uint64_t f_beams = 0;
+  FanArrays d;
+  PinBuf h_in, h_ranges, h_intens, h_bearings, h_hit_model, h_hit_cell, h_steps;
+
+  std::map<char *, size_t> host_allocs; // stg_rt_host_alloc regions
+  stg_rt_stats stats;
+
+  stg_rt_ctx() { memset(&stats, 0, sizeof(stats)); memset(&g, 0, sizeof(g)); }
+};
+
+namespace {
+
+int fail(stg_rt_ctx *c, int code, const char *fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c)
+    c->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define CU(ctx, call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, STG_RT_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+int dev_reserve(stg_rt_ctx *c, DevBuf &b, size_t bytes)
+{
+  if (bytes <= b.cap)
+    return 0;
+  if (b.p)
+    CU(c, cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t want = std::max(bytes + bytes / 4, (size_t)4096);
+  CU(c, cudaMalloc(&b.p, want));
+  b.cap = want;
+  return 0;
+}
+
+int pin_reserve(stg_rt_ctx *c, PinBuf &b, size_t bytes)
+{
+  if (bytes <= b.cap)
+    return 0;
+  if (b.p)
+    CU(c, cudaFreeHost(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t want = std::max(bytes + bytes / 4, (size_t)4096);
+  CU(c, cudaMallocHost(&b.p, want));
+  b.cap = want;
+  return 0;
+}
+
+void free_fan_arrays(FanArrays &a)
+{
+  DevBuf *all[] = { &a.fans, &a.first, &a.headings_in, &a.trig, &a.heading, &a.ranges,
+                    &a.intens, &a.bearings, &a.hit_model, &a.hit_cell, &a.steps };
+  for (DevBuf *b : all) {
+    if (b->p)
+      cudaFree(b->p);
+    b->p = nullptr;
+    b->cap = 0;
+  }
+}
+
+uint32_t next_pow2(uint64_t v)
+{
+  uint64_t p = 1;
+  while (p < v)
+    p <<= 1;
+  return (uint32_t)std::min<uint64_t>(p, 1ull << 31);
+}
+
+bool is_host_alloc(stg_rt_ctx *c, const void *p, size_t bytes)
+{
+  if (!p || c->host_allocs.empty())
+    return false;
+  auto it = c->host_allocs.upper_bound((char *)p);
+  if (it == c->host_allocs.begin())
+    return false;
+  --it;
+  return (char *)p >= it->first && (char *)p + bytes <= it->first + it->second;
+}
+
+// ---- deltas -----------------------------------------------------------------------------------
+
+uint32_t edges_of(const std::vector<int32_t> &xy, uint32_t block, uint32_t layer, uint32_t &step_cursor,
+                  std::vector<EdgeRec> &out)
+{
+  const size_t n = xy.size() / 2;
+  uint32_t steps = 0;
+  for (size_t i = 0; i < n; i++) {
+    const size_t j = (i + 1) % n;
+    EdgeRec e;
+    e.x0 = xy[2 * i];
+    e.y0 = xy[2 * i + 1];
+    e.x1 = xy[2 * j];
+    e.y1 = xy[2 * j + 1];
+    const int64_t adx = std::llabs((int64_t)e.x1 - e.x0), ady = std::llabs((int64_t)e.y1 - e.y0);
+    e.n_steps = (uint32_t)(adx + ady);
+    if (!e.n_steps)
+      continue;
+    e.block = block;
+    e.layer = layer;
+    e.first_step = step_cursor;
+    step_cursor += e.n_steps;
+    steps += e.n_steps;
+    out.push_back(e);
+  }
+  return steps;
+}
+
+struct BlobBuild {
+  std::vector<EdgeRec> rem, ins;
+  std::vector<BlockUpd> bupd;
+  uint32_t rem_steps = 0, ins_steps = 0;
+  int64_t d_live[2] = { 0, 0 };
+  size_t bytes(size_t n_model) const
+  {
+    return sizeof(DeltaHeader) + (rem.size() + ins.size()) * sizeof(EdgeRec) + bupd.size() * sizeof(BlockUpd) +
+           n_model * sizeof(ModelUpd);
+  }
+};
+
+size_t write_blob(unsigned char *dst, const BlobBuild &b, const std::vector<ModelUpd> &mupd, int rank)
+{
+  DeltaHeader h;
+  memset(&h, 0, sizeof(h));
+  h.n_remove = (uint32_t)b.rem.size();
+  h.n_insert = (uint32_t)b.ins.size();
+  h.n_block_upd = (uint32_t)b.bupd.size();
+  h.n_model_upd = (uint32_t)mupd.size();
+  h.steps_remove = b.rem_steps;
+  h.steps_insert = b.ins_steps;
+  h.rank = (uint32_t)rank;
+  unsigned char *p = dst;
+  memcpy(p, &h, sizeof(h));
+  p += sizeof(h);
+  memcpy(p, b.rem.data(), b.rem.size() * sizeof(EdgeRec));
+  p += b.rem.size() * sizeof(EdgeRec);
+  memcpy(p, b.ins.data(), b.ins.size() * sizeof(EdgeRec));
+  p += b.ins.size() * sizeof(EdgeRec);
+  memcpy(p, b.bupd.data(), b.bupd.size() * sizeof(BlockUpd));
+  p += b.bupd.size() * sizeof(BlockUpd);
+  memcpy(p, mupd.data(), mupd.size() * sizeof(ModelUpd));
+  p += mupd.size() * sizeof(ModelUpd);
+  return (size_t)(p - dst);
+}
+
+// Units sorted so that the blob (and, when it has to be split, successive blobs) insert in Map-call
+// order: pure removals first, then by the sequence number of the final Map.
+void sort_units(stg_rt_ctx *c)
+{
+  std::stable_sort(c->dirty_units.begin(), c->dirty_units.end(), [c](uint32_t a, uint32_t b) {
+    const BlockShadow &ba = c->blocks[a >> 1], &bb = c->blocks[b >> 1];
+    const uint32_t sa = ba.host_mapped[a & 1] ? ba.map_seq[a & 1] : 0, sb = bb.host_mapped[b & 1] ? bb.map_seq[b & 1] : 0;
+    return sa < sb;
+  });
+}
+
+// Keep probe chains short: tombstones never turn back into empty slots on their own, so once the
+// upper bound of non-empty slots would pass 3/4 of the table, re-insert the live entries into the
+// spare table and swap.
+int ensure_table_room(stg_rt_ctx *c, const int64_t add[2])
+{
+  for (int L = 0; L < 2; L++) {
+    if (c->used_upper[L] + add[L] <= (int64_t)c->slot_cap * 3 / 4)
+      continue;
+    CU(c, cudaMemsetAsync(c->spare_slots, 0, (size_t)c->slot_cap * 8, c->stream));
+    launch_rehash(c->g.slots[L], c->spare_slots, c->g.slot_mask, c->stream);
+    c->stats.launches_other++;
+    std::swap(c->g.slots[L], c->spare_slots);
+    c->used_upper[L] = c->live_entries[L];
+    if (c->used_upper[L] + add[L] > (int64_t)c->slot_cap * 3 / 4)
+      return fail(c, STG_RT_ENOMEM, "cell-entry table of layer %d too small (%u slots); raise max_cell_entries", L, c->slot_cap);
+  }
+  return 0;
+}
+
+// Emit the queued deltas as one or more blobs. apply == true: upload and apply each blob locally.
+// apply == false (multi-GPU export): exactly one blob, uploaded to d_blob, not applied.
+int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes)
+{
+  sort_units(c);
+  size_t unit = 0;
+  bool first_round = true;
+  if (out_bytes)
+    *out_bytes = 0;
+  while (first_round || unit < c->dirty_units.size()) {
+    BlobBuild bb;
+    uint32_t rem_cursor = 0, ins_cursor = 0;
+    const size_t n_model = first_round ? c->model_upd.size() : 0;
+    while (unit < c->dirty_units.size()) {
+      const uint32_t u = c->dirty_units[unit];
+      BlockShadow &b = c->blocks[u >> 1];
+      const int L = u & 1;
+      const size_t add_edges = (b.dev_mapped[L] ? b.dev_xy[L].size() / 2 : 0) + (b.host_mapped[L] ? b.host_xy[L].size() / 2 : 0);
+      if (bb.bytes(n_model) + add_edges * sizeof(EdgeRec) + sizeof(BlockUpd) > c->blob_cap) {
+        if (bb.rem.empty() && bb.ins.empty() && bb.bupd.empty())
+          return fail(c, STG_RT_ENOMEM, "one block's outline (%zu edges) exceeds the delta buffer", add_edges);
+        break;
+      }
+      if (b.dev_mapped[L]) {
+        const uint32_t s = edges_of(b.dev_xy[L], u >> 1, L, rem_cursor, bb.rem);
+        bb.rem_steps += s;
+        bb.d_live[L] -= s;
+      }
+      if (b.host_mapped[L]) {
+        const uint32_t s = edges_of(b.host_xy[L], u >> 1, L, ins_cursor, bb.ins);
+        bb.ins_steps += s;
+        bb.d_live[L] += s;
+        BlockUpd up;
+        up.block = u >> 1;
+        up.model = b.model;
+        up.zmin = b.zmin;
+        up.zmax = b.zmax;
+        up.seq_local = b.map_seq[L];
+        up.layer = (uint32_t)L;
+        bb.bupd.push_back(up);
+      }
+      b.dev_mapped[L] = b.host_mapped[L];
+      b.dev_xy[L] = b.host_xy[L];
+      b.dirty[L] = false;
+      unit++;
+    }
+    if (!apply && unit < c->dirty_units.size())
+      return fail(c, STG_RT_ENOMEM, "deltas of one tick exceed the all-gather slot (%zu bytes)", c->blob_cap);
+    if (apply) {
+      int64_t ins_per_layer[2] = { 0, 0 };
+      for (const EdgeRec &e : bb.ins)
+        ins_per_layer[e.layer & 1] += e.n_steps;
+      for (int L = 0; L < 2; L++)
+        if (c->live_entries[L] + bb.d_live[L] > (int64_t)c->slot_cap / 2)
+          return fail(c, STG_RT_ENOMEM, "cell-entry table of layer %d full (%lld entries, capacity %u/2); raise max_cell_entries",
+                      L, (long long)(c->live_entries[L] + bb.d_live[L]), c->slot_cap);
+      // live entries grow by the net change, used slots (entries + tombstones) by every insertion
+      int rc = ensure_table_room(c, ins_per_layer);
+      if (rc)
+        return rc;
+      for (int L = 0; L < 2; L++)
+        c->used_upper[L] += ins_per_layer[L];
+    }
+    CU(c, cudaEventSynchronize(c->blob_uploaded));
+    const std::vector<ModelUpd> no_models;
+    const size_t nbytes = write_blob((unsigned char *)c->h_blob.p, bb, first_round ? c->model_upd : no_models, rank);
+    CU(c, cudaMemcpyAsync(c->d_blob.p, c->h_blob.p, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaEventRecord(c->blob_uploaded, c->stream));
+    c->stats.h2d_bytes += nbytes;
+    c->stats.edge_steps += bb.rem_steps + bb.ins_steps;
+    for (int L = 0; L < 2; L++)
+      c->live_entries[L] += bb.d_live[L];
+    if (apply) {
+      c->epoch++;
+      launch_apply_deltas(c->g, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, c->stream,
+                          &c->stats.launches_rasterise);
+      CU(c, cudaGetLastError());
+    }
+    if (out_bytes)
+      *out_bytes = nbytes;
+    first_round = false;
+    if (unit < c->dirty_units.size() || !apply) // the pinned blob is about to be reused / handed out
+      CU(c, cudaStreamSynchronize(c->stream));
+  }
+  c->dirty_units.clear();
+  c->model_upd.clear();
+  c->local_seq = 0;
+  return 0;
+}
+
+int apply_deltas_locked(stg_rt_ctx *c)
+{
+  if (c->dirty_units.empty() && c->model_upd.empty())
+    return 0;
+  return build_and_send_deltas(c, true, 0, nullptr);
+}
+
+// ---- fans -------------------------------------------------------------------------------------
+
+uint32_t want_of(const stg_rt_fan_out &o)
+{
+  return (o.ranges ? STG_RT_WANT_RANGES : 0) | (o.intensities ? STG_RT_WANT_INTENSITIES : 0) |
+         (o.bearings ? STG_RT_WANT_BEARINGS : 0) | (o.hit_model ? STG_RT_WANT_HIT_MODEL : 0) |
+         (o.hit_cell ? STG_RT_WANT_HIT_CELL : 0) | (o.steps ? STG_RT_WANT_STEPS : 0);
+}
+
+int reserve_outputs(stg_rt_ctx *c, FanArrays &a, uint64_t beams, uint32_t want)
+{
+  int rc = dev_reserve(c, a.heading, beams * 8);
+  if (!rc && (want & STG_RT_WANT_RANGES)) rc = dev_reserve(c, a.ranges, beams * 8);
+  if (!rc && (want & STG_RT_WANT_INTENSITIES)) rc = dev_reserve(c, a.intens, beams * 8);
+  if (!rc && (want & STG_RT_WANT_BEARINGS)) rc = dev_reserve(c, a.bearings, beams * 8);
+  if (!rc && (want & STG_RT_WANT_HIT_MODEL)) rc = dev_reserve(c, a.hit_model, beams * 4);
+  if (!rc && (want & STG_RT_WANT_HIT_CELL)) rc = dev_reserve(c, a.hit_cell, beams * 8);
+  if (!rc && (want & STG_RT_WANT_STEPS)) rc = dev_reserve(c, a.steps, beams * 8);
+  return rc;
+}
+
+FanBatchView view_of(const FanArrays &a, uint32_t n_fans, uint64_t beams, uint32_t want, bool trig, bool headings)
+{
+  FanBatchView v;
+  memset(&v, 0, sizeof(v));
+  v.n_fans = n_fans;
+  v.n_beams = beams;
+  v.fans = (const FanRec *)a.fans.p;
+  v.fan_first_beam = (const uint32_t *)a.first.p;
+  v.headings_in = headings ? (const double *)a.headings_in.p : nullptr;
+  v.trig_in = trig ? (const double *)a.trig.p : nullptr;
+  v.heading = (double *)a.heading.p;
+  v.ranges = (want & STG_RT_WANT_RANGES) ? (double *)a.ranges.p : nullptr;
+  v.intensities = (want & STG_RT_WANT_INTENSITIES) ? (double *)a.intens.p : nullptr;
+  v.bearings = (want & STG_RT_WANT_BEARINGS) ? (double *)a.bearings.p : nullptr;
+  v.hit_model = (want & STG_RT_WANT_HIT_MODEL) ? (int32_t *)a.hit_model.p : nullptr;
+  v.hit_cell = (want & STG_RT_WANT_HIT_CELL) ? (int32_t *)a.hit_cell.p : nullptr;
+  v.steps = (want & STG_RT_WANT_STEPS) ? (uint32_t *)a.steps.p : nullptr;
+  return v;
+}
+
+int validate_fans(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *fans, const double *headings)
+{
+  for (uint32_t i = 0; i < n_fans; i++) {
+    const stg_rt_fan &f = fans[i];
+    if (f.finder >= c->cfg.max_models || !c->model_known[f.finder])
+      return fail(c, STG_RT_EINVAL, "fan %u: unknown finder model %u", i, f.finder);
+    if (f.pred > STG_RT_PRED_GRIPPER || f.angles > STG_RT_ANGLES_EXPLICIT || f.layer > 1)
+      return fail(c, STG_RT_EINVAL, "fan %u: bad pred/angles/layer", i);
+    if (f.angles == STG_RT_ANGLES_EXPLICIT && !headings)
+      return fail(c, STG_RT_EINVAL, "fan %u: explicit headings missing", i);
+  }
+  return 0;
+}
+
+// copy one result array back: straight into caller memory when it is page-locked memory of ours,
+// otherwise into the pinned staging buffer (delivered by deliver_locked)
+int fetch_array(stg_rt_ctx *c, void *user, const void *dev, PinBuf &stage, uint64_t first, uint64_t n, size_t elt)
+{
+  if (!user)
+    return 0;
+  const size_t bytes = n * elt;
+  void *dst = is_host_alloc(c, user, bytes) ? user : (char *)stage.p + first * elt;
+  CU(c, cudaMemcpyAsync(dst, (const char *)dev + first * elt, bytes, cudaMemcpyDeviceToHost, c->stream));
+  c->stats.d2h_bytes += bytes;
+  return 0;
+}
+
+void deliver_array(stg_rt_ctx *c, void *user, const PinBuf &stage, uint64_t first, uint64_t n, size_t elt)
+{
+  if (!user || is_host_alloc(c, user, n * elt))
+    return;
+  memcpy(user, (const char *)stage.p + first * elt, n * elt);
+}
+
+int deliver_locked(stg_rt_ctx *c)
+{
+  if (c->f_subs.empty())
+    return 0;
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (const Submit &s : c->f_subs) {
+    deliver_array(c, s.out.ranges, c->h_ranges, s.first_beam, s.n_beams, 8);
+    deliver_array(c, s.out.intensities, c->h_intens, s.first_beam, s.n_beams, 8);
+    deliver_array(c, s.out.bearings, c->h_bearings, s.first_beam, s.n_beams, 8);
+    deliver_array(c, s.out.hit_model, c->h_hit_model, s.first_beam, s.n_beams, 4);
+    deliver_array(c, s.out.hit_cell, c->h_hit_cell, s.first_beam, s.n_beams, 8);
+    deliver_array(c, s.out.steps, c->h_steps, s.first_beam, s.n_beams, 8);
+  }
+  c->f_subs.clear();
+  c->f_beams = 0;
+  return 0;
+}
+
+int launch_fans_locked(stg_rt_ctx *c)
+{
+  if (c->q_subs.empty())
+    return 0;
+  int rc = deliver_locked(c); // staging buffers are single-buffered
+  if (rc)
+    return rc;
+  const uint32_t n_fans = (uint32_t)c->q_fans.size();
+  const uint64_t beams = c->q_beams;
+  uint32_t want = 0;
+  for (const Submit &s : c->q_subs)
+    want |= want_of(s.out);
+  c->q_first.push_back((uint32_t)beams);
+
+  // one pinned block: fans | first | headings | trig
+  const size_t b_fans = (size_t)n_fans * sizeof(FanRec), b_first = (size_t)(n_fans + 1) * 4;
+  const size_t b_head = c->q_headings.size() * 8, b_trig = c->q_has_trig ? beams * 16 : 0;
+  const size_t o_first = b_fans, o_head = (o_first + b_first + 15) & ~(size_t)15, o_trig = o_head + b_head;
+  if ((rc = pin_reserve(c, c->h_in, o_trig + b_trig)))
+    return rc;
+  char *hp = (char *)c->h_in.p;
+  memcpy(hp, c->q_fans.data(), b_fans);
+  memcpy(hp + o_first, c->q_first.data(), b_first);
+  if (b_head)
+    memcpy(hp + o_head, c->q_headings.data(), b_head);
+  if (b_trig)
+    memcpy(hp + o_trig, c->q_trig.data(), b_trig);
+  if ((rc = dev_reserve(c, c->d.fans, b_fans)) || (rc = dev_reserve(c, c->d.first, b_first)) ||
+      (rc = dev_reserve(c, c->d.headings_in, std::max<size_t>(b_head, 8))) ||
+      (rc = dev_reserve(c, c->d.trig, std::max<size_t>(b_trig, 8))) || (rc = reserve_outputs(c, c->d, beams, want)))
+    return rc;
+  CU(c, cudaMemcpyAsync(c->d.fans.p, hp, b_fans, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->d.first.p, hp + o_first, b_first, cudaMemcpyHostToDevice, c->stream));
+  if (b_head)
+    CU(c, cudaMemcpyAsync(c->d.headings_in.p, hp + o_head, b_head, cudaMemcpyHostToDevice, c->stream));
+  if (b_trig)
+    CU(c, cudaMemcpyAsync(c->d.trig.p, hp + o_trig, b_trig, cudaMemcpyHostToDevice, c->stream));
+  c->stats.h2d_bytes += b_fans + b_first + b_head + b_trig;
+
+  const FanBatchView v = view_of(c->d, n_fans, beams, want, c->q_has_trig, b_head != 0);
+  launch_fan_headings(v, c->stream);
+  launch_ray_march(c->g, v, c->stream);
+  CU(c, cudaGetLastError());
+  c->stats.launches_post += 1;
+  c->stats.launches_march += 1;
+  c->stats.beams += beams;
+  c->stats.fans += n_fans;
+
+  if ((want & STG_RT_WANT_RANGES) && (rc = pin_reserve(c, c->h_ranges, beams * 8))) return rc;
+  if ((want & STG_RT_WANT_INTENSITIES) && (rc = pin_reserve(c, c->h_intens, beams * 8))) return rc;
+  if ((want & STG_RT_WANT_BEARINGS) && (rc = pin_reserve(c, c->h_bearings, beams * 8))) return rc;
+  if ((want & STG_RT_WANT_HIT_MODEL) && (rc = pin_reserve(c, c->h_hit_model, beams * 4))) return rc;
+  if ((want & STG_RT_WANT_HIT_CELL) && (rc = pin_reserve(c, c->h_hit_cell, beams * 8))) return rc;
+  if ((want & STG_RT_WANT_STEPS) && (rc = pin_reserve(c, c->h_steps, beams * 8))) return rc;
+  for (const Submit &s : c->q_subs) {
+    if ((rc = fetch_array(c, s.out.ranges, c->d.ranges.p, c->h_ranges, s.first_beam, s.n_beams, 8)) ||
+        (rc = fetch_array(c, s.out.intensities, c->d.intens.p, c->h_intens, s.first_beam, s.n_beams, 8)) ||
+        (rc = fetch_array(c, s.out.bearings, c->d.bearings.p, c->h_bearings, s.first_beam, s.n_beams, 8)) ||
+        (rc = fetch_array(c, s.out.hit_model, c->d.hit_model.p, c->h_hit_model, s.first_beam, s.n_beams, 4)) ||
+        (rc = fetch_array(c, s.out.hit_cell, c->d.hit_cell.p, c->h_hit_cell, s.first_beam, s.n_beams, 8)) ||
+        (rc = fetch_array(c, s.out.steps, c->d.steps.p, c->h_steps, s.first_beam, s.n_beams, 8)))
+      return rc;
+  }
+  c->f_subs.swap(c->q_subs);
+  c->f_beams = beams;
+  c->q_subs.clear();
+  c->q_fans.clear();
+  c->q_first.clear();
+  c->q_headings.clear();
+  c->q_trig.clear();
+  c->q_beams = 0;
+  c->q_has_trig = false;
+  return 0;
+}
+
+int flush_locked(stg_rt_ctx *c)
+{
+  int rc = apply_deltas_locked(c);
+  if (rc)
+    return rc;
+  return launch_fans_locked(c);
+}
+
+void touch_unit(stg_rt_ctx *c, uint32_t block, int layer)
+{
+  BlockShadow &b = c->blocks[block];
+  if (!b.dirty[layer]) {
+    b.dirty[layer] = true;
+    c->dirty_units.push_back(block * 2 + (uint32_t)layer);
+  }
+}
+
+} // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+
+extern "C" {
+
+int stg_rt_abi_version(void) { return STG_RT_ABI_VERSION; }
+
+const char *stg_rt_last_error(const stg_rt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
+{
+  if (!cfg || !out || cfg->struct_size != sizeof(stg_rt_config))
+    return fail(nullptr, STG_RT_EINVAL, "stg_rt_create: bad config (struct_size %u, expected %zu)",
+                cfg ? cfg->struct_size : 0u, sizeof(stg_rt_config));
+  if (!(cfg->ppm > 0) || cfg->sreg_nx < 1 || cfg->sreg_ny < 1 || (int64_t)cfg->sreg_nx * cfg->sreg_ny > 4095 ||
+      cfg->max_models < 1 || cfg->max_blocks < 1)
+    return fail(nullptr, STG_RT_EINVAL, "stg_rt_create: bad ppm / extent / capacities");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
+    return fail(nullptr, STG_RT_ENODEV, "stg_rt_create: no CUDA device (%s); this library has no CPU path",
+                cudaGetErrorString(cudaGetLastError()));
+  if (cfg->device < 0 || cfg->device >= n_dev)
+    return fail(nullptr, STG_RT_ENODEV, "stg_rt_create: device %d of %d", cfg->device, n_dev);
+  stg_rt_ctx *c = new stg_rt_ctx;
+  c->cfg = *cfg;
+#define CUC(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      fail(nullptr, STG_RT_ECUDA, "%s: %s", #call, cudaGetErrorString(e_));                        \
+      delete c;                                                                                    \
+      return STG_RT_ECUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+  CUC(cudaSetDevice(cfg->device));
+  CUC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  CUC(cudaEventCreateWithFlags(&c->blob_uploaded, cudaEventDisableTiming));
+  GridView &g = c->g;
+  g.ppm = cfg->ppm;
+  g.rx0 = cfg->sreg_x0 * 32;
+  g.ry0 = cfg->sreg_y0 * 32;
+  g.nrx = cfg->sreg_nx * 32;
+  g.nry = cfg->sreg_ny * 32;
+  c->n_regions = (size_t)g.nrx * g.nry;
+  c->cell_x0 = g.rx0 * 32;
+  c->cell_y0 = g.ry0 * 32;
+  c->cell_x1 = c->cell_x0 + g.nrx * 32 - 1;
+  c->cell_y1 = c->cell_y0 + g.nry * 32 - 1;
+  const uint64_t entries = cfg->max_cell_entries ? cfg->max_cell_entries : (1u << 22);
+  c->slot_cap = next_pow2(2 * entries);
+  g.slot_mask = c->slot_cap - 1;
+  g.n_blocks = cfg->max_blocks;
+  g.n_models = cfg->max_models;
+  CUC(cudaMalloc(&g.reg_count, c->n_regions * 4));
+  CUC(cudaMemsetAsync(g.reg_count, 0, c->n_regions * 4, c->stream));
+  for (int L = 0; L < 2; L++) {
+    CUC(cudaMalloc(&g.occ[L], c->n_regions * 128));
+    CUC(cudaMemsetAsync(g.occ[L], 0, c->n_regions * 128, c->stream));
+    CUC(cudaMalloc(&g.slots[L], (size_t)c->slot_cap * 8));
+    CUC(cudaMemsetAsync(g.slots[L], 0, (size_t)c->slot_cap * 8, c->stream));
+    CUC(cudaMalloc(&g.blk_seq[L], (size_t)cfg->max_blocks * 8));
+    CUC(cudaMemsetAsync(g.blk_seq[L], 0, (size_t)cfg->max_blocks * 8, c->stream));
+  }
+  CUC(cudaMalloc(&c->spare_slots, (size_t)c->slot_cap * 8));
+  CUC(cudaMalloc(&g.blk_model, (size_t)cfg->max_blocks * 4));
+  CUC(cudaMalloc(&g.blk_zmin, (size_t)cfg->max_blocks * 8));
+  CUC(cudaMalloc(&g.blk_zmax, (size_t)cfg->max_blocks * 8));
+  CUC(cudaMemsetAsync(g.blk_model, 0, (size_t)cfg->max_blocks * 4, c->stream));
+  CUC(cudaMalloc(&g.mdl_root, (size_t)cfg->max_models * 4));
+  CUC(cudaMalloc(&g.mdl_ranger_return, (size_t)cfg->max_models * 8));
+  CUC(cudaMalloc(&g.mdl_flags, (size_t)cfg->max_models * 4));
+  CUC(cudaMemsetAsync(g.mdl_root, 0, (size_t)cfg->max_models * 4, c->stream));
+  CUC(cudaMemsetAsync(g.mdl_ranger_return, 0, (size_t)cfg->max_models * 8, c->stream));
+  CUC(cudaMemsetAsync(g.mdl_flags, 0, (size_t)cfg->max_models * 4, c->stream));
+  c->blob_cap = 8u << 20;
+  CUC(cudaMalloc(&c->d_blob.p, c->blob_cap));
+  c->d_blob.cap = c->blob_cap;
+  CUC(cudaMallocHost(&c->h_blob.p, c->blob_cap));
+  c->h_blob.cap = c->blob_cap;
+  CUC(cudaStreamSynchronize(c->stream));
+#undef CUC
+  c->blocks.resize(cfg->max_blocks);
+  c->model_known.assign(cfg->max_models, false);
+  *out = c;
+  return STG_RT_OK;
+}
+
+int stg_rt_destroy(stg_rt_ctx *c)
+{
+  if (!c)
+    return STG_RT_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  cudaStreamSynchronize(c->stream);
+  GridView &g = c->g;
+  void *dev[] = { g.reg_count, g.occ[0], g.occ[1], g.slots[0], g.slots[1], g.blk_seq[0], g.blk_seq[1], c->spare_slots,
+                  g.blk_model, g.blk_zmin, g.blk_zmax, g.mdl_root, g.mdl_ranger_return, g.mdl_flags, c->d_blob.p };
+  for (void *p : dev)
+    if (p)
+      cudaFree(p);
+  free_fan_arrays(c->d);
+  PinBuf *pins[] = { &c->h_blob, &c->h_in, &c->h_ranges, &c->h_intens, &c->h_bearings, &c->h_hit_model, &c->h_hit_cell, &c->h_steps };
+  for (PinBuf *p : pins)
+    if (p->p)
+      cudaFreeHost(p->p);
+  for (auto &kv : c->host_allocs)
+    cudaFreeHost(kv.first);
+  cudaEventDestroy(c->blob_uploaded);
+  cudaStreamDestroy(c->own_stream);
+  delete c;
+  return STG_RT_OK;
+}
+
+int stg_rt_model_upsert(stg_rt_ctx *c, uint32_t id, uint32_t root_id, double ranger_return, int32_t fiducial_return,
+                        int32_t fiducial_key, uint32_t vis_flags, const double *rgba)
+{
+  if (!c)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  (void)rgba;
+  if (id >= c->cfg.max_models || root_id >= c->cfg.max_models)
+    return fail(c, STG_RT_ENOMEM, "model id %u / root %u beyond max_models %u", id, root_id, c->cfg.max_models);
+  if (!c->q_subs.empty()) { // fans queued before this change must not see it
+    int rc = flush_locked(c);
+    if (rc)
+      return rc;
+  }
+  ModelUpd u;
+  memset(&u, 0, sizeof(u));
+  u.id = id;
+  u.root = root_id;
+  u.ranger_return = ranger_return;
+  u.fiducial_return = fiducial_return;
+  u.fiducial_key = fiducial_key;
+  u.flags = vis_flags;
+  c->model_upd.push_back(u);
+  c->model_known[id] = true;
+  if (sizeof(DeltaHeader) + c->model_upd.size() * sizeof(ModelUpd) > c->blob_cap / 2)
+    return apply_deltas_locked(c);
+  return STG_RT_OK;
+}
+
+int stg_rt_block_map(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id, int layer, double zmin, double zmax, int n_pts,
+                     const int32_t *xy)
+{
+  if (!c)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (layer < 0 || layer > 1 || n_pts < 0 || (n_pts && !xy))
+    return fail(c, STG_RT_EINVAL, "block_map: bad layer / points");
+  if (block_id >= c->cfg.max_blocks)
+    return fail(c, STG_RT_ENOMEM, "block id %u beyond max_blocks %u", block_id, c->cfg.max_blocks);
+  if (model_id >= c->cfg.max_models || !c->model_known[model_id])
+    return fail(c, STG_RT_EINVAL, "block_map: unknown model %u (call stg_rt_model_upsert first)", model_id);
+  BlockShadow &b = c->blocks[block_id];
+  if (b.host_mapped[layer])
+    return fail(c, STG_RT_ESTATE, "block %u is already mapped on layer %d (Block::UnMap first, block.cc:183)", block_id, layer);
+  for (int i = 0; i < n_pts; i++)
+    if (xy[2 * i] < c->cell_x0 || xy[2 * i] > c->cell_x1 || xy[2 * i + 1] < c->cell_y0 || xy[2 * i + 1] > c->cell_y1)
+      return fail(c, STG_RT_EEXTENT, "block %u vertex (%d,%d) outside the device grid [%d..%d]x[%d..%d]", block_id, xy[2 * i],
+                  xy[2 * i + 1], c->cell_x0, c->cell_x1, c->cell_y0, c->cell_y1);
+  if (!c->q_subs.empty()) { // issue order: queued fans must be traced against the grid as it was
+    int rc = flush_locked(c);
+    if (rc)
+      return rc;
+  }
+  b.known = true;
+  b.model = model_id;
+  b.zmin = zmin;
+  b.zmax = zmax;
+  b.host_mapped[layer] = true;
+  b.host_xy[layer].assign(xy, xy + 2 * (size_t)n_pts);
+  b.map_seq[layer] = ++c->local_seq;
+  touch_unit(c, block_id, layer);
+  c->stats.map_calls++;
+  return STG_RT_OK;
+}
+
+int stg_rt_block_unmap(stg_rt_ctx *c, uint32_t block_id, int layer)
+{
+  if (!c)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (layer < 0 || layer > 1)
+    return fail(c, STG_RT_EINVAL, "block_unmap: bad layer");
+  if (block_id >= c->cfg.max_blocks)
+    return fail(c, STG_RT_ENOMEM, "block id %u beyond max_blocks %u", block_id, c->cfg.max_blocks);
+  BlockShadow &b = c->blocks[block_id];
+  if (!b.host_mapped[layer])
+    return STG_RT_OK;
+  if (!c->q_subs.empty()) {
+    int rc = flush_locked(c);
+    if (rc)
+      return rc;
+  }
+  b.host_mapped[layer] = false;
+  b.host_xy[layer].clear();
+  touch_unit(c, block_id, layer);
+  c->stats.unmap_calls++;
+  return STG_RT_OK;
+}
+
+int stg_rt_fans_submit(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *fans, const double *headings, const double *trig,
+                       const stg_rt_fan_out *out)
+{
+  if (!c)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!n_fans)
+    return STG_RT_OK;
+  if (!fans || !out)
+    return fail(c, STG_RT_EINVAL, "fans_submit: null fans / out");
+  int rc = validate_fans(c, n_fans, fans, headings);
+  if (rc)
+    return rc;
+  if (!c->q_subs.empty() && c->q_has_trig != (trig != nullptr)) { // a batch is all-strict or all-device trig
+    if ((rc = flush_locked(c)))
+      return rc;
+  }
+  Submit s;
+  s.first_beam = c->q_beams;
+  s.out = *out;
+  uint64_t beams = 0;
+  const size_t head_base = c->q_headings.size();
+  uint32_t max_head = 0;
+  for (uint32_t i = 0; i < n_fans; i++) {
+    FanRec r;
+    memcpy(&r, &fans[i], sizeof(r));
+    c->q_first.push_back((uint32_t)(c->q_beams + beams));
+    if (r.angles == STG_RT_ANGLES_EXPLICIT) {
+      max_head = std::max(max_head, r.first_heading + r.n_samples);
+      r.first_heading += (uint32_t)head_base;
+    }
+    c->q_fans.push_back(r);
+    beams += r.n_samples;
+  }
+  if (c->q_beams + beams >= (1ull << 32))
+    return fail(c, STG_RT_EINVAL, "more than 2^32 beams in one batch");
+  if (max_head)
+    c->q_headings.insert(c->q_headings.end(), headings, headings + max_head);
+  if (trig) {
+    c->q_trig.insert(c->q_trig.end(), trig, trig + 2 * beams);
+    c->q_has_trig = true;
+  }
+  s.n_beams = beams;
+  c->q_beams += beams;
+  c->q_subs.push_back(s);
+  return STG_RT_OK;
+}
+
+int stg_rt_flush(stg_rt_ctx *c)
+{
+  if (!c)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  return flush_locked(c);
+}
+
+int stg_rt_sync(stg_rt_ctx *c)
+{
+  if (!c)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = flush_locked(c);
+  if (rc)
+    return rc;
+  if ((rc = deliver_locked(c)))
+    return rc;
+  CU(c, cudaStreamSynchronize(c->stream));
+  return STG_RT_OK;
+}
+
+void *stg_rt_host_alloc(stg_rt_ctx *c, size_t bytes)
+{
+  if (!c || !bytes)
+    return nullptr;
+  std::lock_guard<std::mutex> lk(c->mu);
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    fail(c, STG_RT_ECUDA, "cudaMallocHost(%zu) failed", bytes);
+    return nullptr;
+  }
+  c->host_allocs[(char *)p] = bytes;
+  return p;
+}
+
+int stg_rt_host_free(stg_rt_ctx *c, void *p)
+{
+  if (!c)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  auto it = c->host_allocs.find((char *)p);
+  if (it == c->host_allocs.end())
+    return fail(c, STG_RT_EINVAL, "host_free: not a stg_rt_host_alloc pointer");
+  deliver_locked(c);
+  cudaFreeHost(p);
+  c->host_allocs.erase(it);
+  return STG_RT_OK;
+}
+
+// ---- resident sets ------------------------------------------------------------------------------
+
+int stg_rt_set_create(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *fans, const double *headings, const double *trig,
+                      uint32_t want, stg_rt_set **out)
+{
+  if (!c || !out || !fans || !n_fans)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = validate_fans(c, n_fans, fans, headings);
+  if (rc)
+    return rc;
+  stg_rt_set *s = new stg_rt_set;
+  s->want = want;
+  uint64_t beams = 0;
+  uint32_t max_head = 0;
+  for (uint32_t i = 0; i < n_fans; i++) {
+    FanRec r;
+    memcpy(&r, &fans[i], sizeof(r));
+    s->first.push_back((uint32_t)beams);
+    if (r.angles == STG_RT_ANGLES_EXPLICIT)
+      max_head = std::max(max_head, r.first_heading + r.n_samples);
+    s->fans.push_back(r);
+    beams += r.n_samples;
+  }
+  s->first.push_back((uint32_t)beams);
+  s->n_beams = beams;
+  s->has_trig = trig != nullptr;
+  s->has_headings = max_head != 0;
+  if ((rc = dev_reserve(c, s->d.fans, (size_t)n_fans * sizeof(FanRec))) || (rc = dev_reserve(c, s->d.first, (size_t)(n_fans + 1) * 4)) ||
+      (rc = dev_reserve(c, s->d.headings_in, std::max<size_t>((size_t)max_head * 8, 8))) ||
+      (rc = dev_reserve(c, s->d.trig, std::max<size_t>(trig ? beams * 16 : 0, 8))) || (rc = reserve_outputs(c, s->d, beams, want))) {
+    free_fan_arrays(s->d);
+    delete s;
+    return rc;
+  }
+  CU(c, cudaMemcpyAsync(s->d.first.p, s->first.data(), (size_t)(n_fans + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+  if (max_head)
+    CU(c, cudaMemcpyAsync(s->d.headings_in.p, headings, (size_t)max_head * 8, cudaMemcpyHostToDevice, c->stream));
+  if (trig)
+    CU(c, cudaMemcpyAsync(s->d.trig.p, trig, beams * 16, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(s->d.fans.p, s->fans.data(), (size_t)n_fans * sizeof(FanRec), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream)); // sources are pageable caller memory
+  s->fans_dirty = false;
+  *out = s;
+  return STG_RT_OK;
+}
+
+int stg_rt_set_destroy(stg_rt_ctx *c, stg_rt_set *s)
+{
+  if (!c || !s)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaStreamSynchronize(c->stream);
+  free_fan_arrays(s->d);
+  delete s;
+  return STG_RT_OK;
+}
+
+int stg_rt_set_update_origins(stg_rt_ctx *c, stg_rt_set *s, const double *xyza, int layer)
+{
+  if (!c || !s || !xyza || layer < 0 || layer > 1)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  for (size_t i = 0; i < s->fans.size(); i++) {
+    FanRec &r = s->fans[i];
+    r.ox = xyza[4 * i];
+    r.oy = xyza[4 * i + 1];
+    r.oz = xyza[4 * i + 2];
+    r.oa = xyza[4 * i + 3];
+    r.layer = (uint8_t)layer;
+  }
+  s->fans_dirty = true;
+  return STG_RT_OK;
+}
+
+int stg_rt_set_trace(stg_rt_ctx *c, stg_rt_set *s)
+{
+  if (!c || !s)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = flush_locked(c);
+  if (rc)
+    return rc;
+  if (s->fans_dirty) {
+    CU(c, cudaStreamSynchronize(c->stream)); // the previous upload may still read s->fans
+    CU(c, cudaMemcpyAsync(s->d.fans.p, s->fans.data(), s->fans.size() * sizeof(FanRec), cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2d_bytes += s->fans.size() * sizeof(FanRec);
+    s->fans_dirty = false;
+  }
+  const FanBatchView v = view_of(s->d, (uint32_t)s->fans.size(), s->n_beams, s->want, s->has_trig, s->has_headings);
+  launch_fan_headings(v, c->stream);
+  launch_ray_march(c->g, v, c->stream);
+  CU(c, cudaGetLastError());
+  c->stats.launches_post += 1;
+  c->stats.launches_march += 1;
+  c->stats.beams += s->n_beams;
+  c->stats.fans += s->fans.size();
+  return STG_RT_OK;
+}
+
+int stg_rt_set_download(stg_rt_ctx *c, stg_rt_set *s, const stg_rt_fan_out *out)
+{
+  if (!c || !s || !out)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (want_of(*out) & ~s->want)
+    return fail(c, STG_RT_EINVAL, "set_download: array not part of the set's want mask");
+  const uint64_t n = s->n_beams;
+  if (out->ranges) CU(c, cudaMemcpyAsync(out->ranges, s->d.ranges.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (out->intensities) CU(c, cudaMemcpyAsync(out->intensities, s->d.intens.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (out->bearings) CU(c, cudaMemcpyAsync(out->bearings, s->d.bearings.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (out->hit_model) CU(c, cudaMemcpyAsync(out->hit_model, s->d.hit_model.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (out->hit_cell) CU(c, cudaMemcpyAsync(out->hit_cell, s->d.hit_cell.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (out->steps) CU(c, cudaMemcpyAsync(out->steps, s->d.steps.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return STG_RT_OK;
+}
+
+int stg_rt_set_device_ptrs(stg_rt_ctx *c, stg_rt_set *s, stg_rt_fan_out *dev)
+{
+  if (!c || !s || !dev)
+    return STG_RT_EINVAL;
+  const FanBatchView v = view_of(s->d, (uint32_t)s->fans.size(), s->n_beams, s->want, false, false);
+  dev->ranges = v.ranges;
+  dev->intensities = v.intensities;
+  dev->bearings = v.bearings;
+  dev->hit_model = v.hit_model;
+  dev->hit_cell = v.hit_cell;
+  dev->steps = v.steps;
+  return STG_RT_OK;
+}
+
+uint64_t stg_rt_set_beams(const stg_rt_set *s) { return s ? s->n_beams : 0; }
+
+// ---- grid inspection ------------------------------------------------------------------------------
+
+int64_t stg_rt_grid_dump(stg_rt_ctx *c, int32_t *records, int64_t cap, int64_t *region_counts, int64_t counts_cap,
+                         int64_t *n_counts)
+{
+  if (!c)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = flush_locked(c);
+  if (rc)
+    return rc;
+  if ((rc = deliver_locked(c)))
+    return rc;
+  const GridView &g = c->g;
+  std::vector<unsigned long long> slots(c->slot_cap), seq(c->cfg.max_blocks);
+  std::vector<uint32_t> counts(c->n_regions);
+  struct Rec {
+    int32_t layer, x, y;
+    unsigned long long seq;
+    int32_t block;
+  };
+  std::vector<Rec> recs;
+  for (int L = 0; L < 2; L++) {
+    CU(c, cudaMemcpyAsync(slots.data(), g.slots[L], (size_t)c->slot_cap * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(seq.data(), g.blk_seq[L], (size_t)c->cfg.max_blocks * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < slots.size(); i++) {
+      const unsigned long long e = slots[i];
+      if (e == kSlotEmpty || e == kSlotTomb)
+        continue;
+      const uint32_t key = (uint32_t)(e >> 32), blk = (uint32_t)e - 1u;
+      const uint32_t region = key >> 10, cy = (key >> 5) & 31, cx = key & 31;
+      Rec r;
+      r.layer = L;
+      r.x = (g.rx0 + (int32_t)(region % (uint32_t)g.nrx)) * 32 + (int32_t)cx;
+      r.y = (g.ry0 + (int32_t)(region / (uint32_t)g.nrx)) * 32 + (int32_t)cy;
+      r.seq = blk < seq.size() ? seq[blk] : 0;
+      r.block = (int32_t)blk;
+      recs.push_back(r);
+    }
+  }
+  std::sort(recs.begin(), recs.end(), [](const Rec &a, const Rec &b) {
+    if (a.layer != b.layer) return a.layer < b.layer;
+    if (a.y != b.y) return a.y < b.y;
+    if (a.x != b.x) return a.x < b.x;
+    if (a.seq != b.seq) return a.seq < b.seq;
+    return a.block < b.block;
+  });
+  int64_t n = 0;
+  int32_t pos = 0;
+  for (size_t i = 0; i < recs.size(); i++) {
+    pos = (i && recs[i - 1].layer == recs[i].layer && recs[i - 1].x == recs[i].x && recs[i - 1].y == recs[i].y) ? pos + 1 : 0;
+    if (records && n < cap) {
+      int32_t *o = records + 5 * n;
+      o[0] = recs[i].layer;
+      o[1] = recs[i].x;
+      o[2] = recs[i].y;
+      o[3] = pos;
+      o[4] = recs[i].block;
+    }
+    n++;
+  }
+  CU(c, cudaMemcpyAsync(counts.data(), g.reg_count, c->n_regions * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  int64_t nc = 0;
+  for (size_t r = 0; r < counts.size(); r++)
+    if (counts[r]) {
+      if (region_counts && nc < counts_cap) {
+        region_counts[3 * nc] = g.rx0 + (int64_t)(r % (size_t)g.nrx);
+        region_counts[3 * nc + 1] = g.ry0 + (int64_t)(r / (size_t)g.nrx);
+        region_counts[3 * nc + 2] = counts[r];
+      }
+      nc++;
+    }
+  if (n_counts)
+    *n_counts = nc;
+  return n;
+}
+
+// ---- multi-GPU deltas ------------------------------------------------------------------------------
+
+size_t stg_rt_delta_slot_bytes(const stg_rt_ctx *c) { return c ? c->blob_cap : 0; }
+
+int stg_rt_delta_export(stg_rt_ctx *c, int rank, void **dev_blob, size_t *n_bytes)
+{
+  if (!c || !dev_blob || !n_bytes || rank < 0 || rank > 255)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = launch_fans_locked(c); // fans queued so far see the grid before these deltas
+  if (rc)
+    return rc;
+  // the entry accounting of exported deltas happens here for this rank's own share
+  if ((rc = build_and_send_deltas(c, false, rank, n_bytes)))
+    return rc;
+  *dev_blob = c->d_blob.p;
+  return STG_RT_OK;
+}
+
+int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_ranks, size_t slot_bytes)
+{
+  if (!c || !dev_gathered || n_ranks < 1 || n_ranks > 256 || slot_bytes < sizeof(DeltaHeader))
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = launch_fans_locked(c);
+  if (rc)
+    return rc;
+  // learn what the other ranks inserted / removed so the table accounting stays an upper bound
+  std::vector<DeltaHeader> hdrs(n_ranks);
+  CU(c, cudaMemcpy2DAsync(hdrs.data(), sizeof(DeltaHeader), dev_gathered, slot_bytes, sizeof(DeltaHeader), n_ranks,
+                          cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  int64_t ins = 0;
+  for (const DeltaHeader &h : hdrs)
+    ins += h.steps_insert;
+  // layers are not split in the headers: charge both (upper bound)
+  const int64_t add[2] = { ins, ins };
+  if ((rc = ensure_table_room(c, add)))
+    return rc;
+  for (int L = 0; L < 2; L++)
+    c->used_upper[L] += ins;
+  c->epoch++;
+  launch_apply_deltas(c->g, (const unsigned char *)dev_gathered, n_ranks, slot_bytes, c->epoch, c->stream,
+                      &c->stats.launches_rasterise);
+  CU(c, cudaGetLastError());
+  return STG_RT_OK;
+}
+
+// ---- plumbing --------------------------------------------------------------------------------------
+
+int stg_rt_set_stream(stg_rt_ctx *c, void *cuda_stream)
+{
+  if (!c)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = flush_locked(c);
+  if (rc)
+    return rc;
+  if ((rc = deliver_locked(c)))
+    return rc;
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  return STG_RT_OK;
+}
+
+void *stg_rt_get_stream(stg_rt_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int stg_rt_get_stats(stg_rt_ctx *c, stg_rt_stats *out)
+{
+  if (!c || !out)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  *out = c->stats;
+  return STG_RT_OK;
+}
+
+} // extern "C"

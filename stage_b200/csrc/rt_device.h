@@ -1,0 +1,112 @@
+// Device-side data layout shared by the kernels (rt_kernels.cu) and the host runtime (rt_api.cu).
+// See DESIGN.md "Data layout in HBM".
+#pragma once
+#include <stdint.h>
+
+namespace stg {
+
+constexpr int kRBits = 5;                    // region.hh:13 RBITS: a Region is 32 x 32 cells
+constexpr int kRegionWidth = 1 << kRBits;    // region.hh:17
+constexpr int kSRBits = 10;                  // region.hh:15 SRBITS: a SuperRegion is 1024 x 1024 cells
+
+constexpr unsigned long long kSlotEmpty = 0ull;
+constexpr unsigned long long kSlotTomb = ~0ull;
+
+// The replicated world state one GPU holds. Passed to kernels by value.
+//
+//  reg_count[r]        Region::count (region.cc:19-34): number of (cell, block) entries of BOTH
+//                      layers in region r. r = (gry - ry0) * nrx + (grx - rx0), row-major over the
+//                      dense extent. 4 B / region.
+//  occ[L][r*32 + cy]   occupancy tile of region r, layer L: bit cx of word cy is set iff the cell's
+//                      block list Cell::blocks[L] (region.hh:47) is non-empty. One region = one
+//                      128-byte line = eight 128-bit words; this is what the ray march reads.
+//  slots[L][h]         open-addressing multimap (cell -> block) holding the CONTENT of the occupied
+//                      cells: entry = (cell_key << 32) | (block_id + 1), cell_key = r*1024 + cy*32
+//                      + cx. 0 = empty, ~0 = tombstone. Only consulted where an occ bit is set.
+//  blk_* / mdl_*       what the hit test and the predicates read (Block::global_z block.cc:177-180,
+//                      Model::vis stage.hh:1924-1937, tree root for Model::IsRelated).
+//  blk_seq[L][b]       order key of block b's latest Map on layer L: entries of one cell sorted by
+//                      it reproduce the insertion order of Cell::blocks[L].
+struct GridView {
+  int32_t rx0, ry0, nrx, nry;
+  double ppm;
+  uint32_t *reg_count;
+  uint32_t *occ[2];
+  unsigned long long *slots[2];
+  uint32_t slot_mask;
+  uint32_t n_blocks, n_models;
+  uint32_t *blk_model;
+  double *blk_zmin, *blk_zmax;
+  unsigned long long *blk_seq[2];
+  uint32_t *mdl_root;
+  double *mdl_ranger_return;
+  uint32_t *mdl_flags;
+};
+
+// ---- moved-block delta blob (host -> device, and rank -> rank through the all-gather) ----------
+// [DeltaHeader][EdgeRec x (n_remove + n_insert)][BlockUpd x n_block_upd][ModelUpd x n_model_upd]
+struct DeltaHeader {
+  uint32_t n_remove, n_insert;       // edge records: removals first, then insertions
+  uint32_t n_block_upd, n_model_upd;
+  uint32_t steps_remove, steps_insert; // total cell visits of the remove / insert edges
+  uint32_t rank, reserved;
+};
+static_assert(sizeof(DeltaHeader) == 32, "DeltaHeader");
+
+// One polygon edge = one integer line of World::MapPoly (world.cc:995-1052): start cell included,
+// end cell excluded, n_steps = |dx| + |dy| cell visits. first_step = running sum within its group.
+struct EdgeRec {
+  int32_t x0, y0, x1, y1;
+  uint32_t block;
+  uint32_t layer;
+  uint32_t first_step, n_steps;
+};
+static_assert(sizeof(EdgeRec) == 32, "EdgeRec");
+
+struct BlockUpd {
+  uint32_t block, model;
+  double zmin, zmax;
+  uint32_t seq_local; // order of the Map call within this rank's blob
+  uint32_t layer;
+};
+static_assert(sizeof(BlockUpd) == 32, "BlockUpd");
+
+struct ModelUpd {
+  uint32_t id, root;
+  double ranger_return;
+  int32_t fiducial_return, fiducial_key;
+  uint32_t flags, pad;
+};
+static_assert(sizeof(ModelUpd) == 32, "ModelUpd");
+
+// ---- fans -----------------------------------------------------------------------------------
+// Device copy of stg_rt_fan (include/stg_rt.h) - same 64-byte layout.
+struct FanRec {
+  uint32_t finder, n_samples;
+  uint8_t pred, ztest, layer, angles;
+  uint32_t first_heading;
+  double ox, oy, oz, oa, range, fov;
+};
+static_assert(sizeof(FanRec) == 64, "FanRec");
+
+struct FanBatchView {
+  uint32_t n_fans;
+  uint64_t n_beams;
+  const FanRec *fans;
+  const uint32_t *fan_first_beam; // n_fans + 1 prefix sums
+  const double *headings_in;      // EXPLICIT headings (may be null)
+  const double *trig_in;          // strict mode (cos, sin) per beam (may be null)
+  double *heading;                // per beam: the heading World::Raytrace receives
+  // outputs (any may be null)
+  double *ranges, *intensities, *bearings;
+  int32_t *hit_model, *hit_cell;
+  uint32_t *steps;
+};
+
+// launch wrappers implemented in rt_kernels.cu; all asynchronous on `stream`
+void launch_apply_deltas(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
+                         unsigned long long epoch, void *stream, uint64_t *launch_counter);
+void launch_fan_headings(const FanBatchView &b, void *stream);
+void launch_ray_march(const GridView &g, const FanBatchView &b, void *stream);
+
+} // namespace stg

@@ -1,0 +1,544 @@
+// sm_100a kernels of the Stage sensor-raycast path.
+//   K1  apply_deltas_*   block rasterisation: per-tick moved-block deltas -> occupancy tiles,
+//                        region counts and the cell-content table
+//                        (World::MapPoly world.cc:990-1056, Cell::AddBlock/RemoveBlock
+//                        region.cc:283-299, Block::UnMap block.cc:183-189)
+//   K2a fan_headings     per-beam headings (ModelRanger::Sensor::Update model_ranger.cc:232-255,
+//                        World::Raytrace(fan) world.cc:731-743)
+//   K2  ray_march        batched DDA march, one lane per beam, predicates in-kernel
+//                        (World::Raytrace world.cc:756-963) with the K3 ranger epilogue fused
+//                        (intensity / bearing, model_ranger.cc:243-251)
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false  (the traversal's FP64 address
+// math must round exactly like the reference's x86-64 -O2 build, which never contracts a*b+c).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rt_device.h"
+
+namespace stg {
+
+// ------------------------------------------------------------------------------------------
+// shared helpers
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t mix32(uint32_t k)
+{
+  k ^= k >> 16;
+  k *= 0x7feb352du;
+  k ^= k >> 15;
+  k *= 0x846ca68bu;
+  k ^= k >> 16;
+  return k;
+}
+
+__device__ __forceinline__ unsigned long long ld_slot(const unsigned long long *p)
+{
+  return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+
+// Cell visit k (0-based) of the integer line (x0,y0)->(x1,y1) walked as World::MapPoly does
+// (world.cc:1000-1052): error term exy starts at ay-ax; exy<0 -> x step, exy+=2ay; else y step,
+// exy-=2ax. exy stays in [-2ax, 2ay), so the number of x steps among the first k steps is the
+// unique i with -2ax <= (ay-ax) - 2ax*k + i*(2ax+2ay) < 2ay, i.e. floor((2ax*k+ax+ay-1)/(2ax+2ay)).
+__device__ __forceinline__ void edge_cell(const EdgeRec &e, uint32_t k, int32_t &x, int32_t &y)
+{
+  const int32_t dx = e.x1 - e.x0, dy = e.y1 - e.y0;
+  const int32_t sx = dx < 0 ? -1 : 1, sy = dy < 0 ? -1 : 1;
+  const long long ax = dx < 0 ? -(long long)dx : dx, ay = dy < 0 ? -(long long)dy : dy;
+  const long long i = (2 * ax * (long long)k + ax + ay - 1) / (2 * (ax + ay));
+  x = e.x0 + sx * (int32_t)i;
+  y = e.y0 + sy * (int32_t)((long long)k - i);
+}
+
+// Find the edge whose step range contains global step t (first_step is a running sum).
+__device__ __forceinline__ uint32_t find_edge(const EdgeRec *edges, uint32_t n, uint32_t t)
+{
+  uint32_t lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (edges[mid].first_step <= t)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+struct CellAddr {
+  uint32_t region; // row-major region index inside the extent
+  uint32_t key;    // region*1024 + cy*32 + cx
+  uint32_t cx, cy;
+};
+
+__device__ __forceinline__ CellAddr cell_addr(const GridView &g, int32_t x, int32_t y)
+{
+  CellAddr c;
+  const int32_t rix = (x >> kRBits) - g.rx0, riy = (y >> kRBits) - g.ry0;
+  c.region = (uint32_t)(riy * g.nrx + rix);
+  c.cx = (uint32_t)x & (kRegionWidth - 1);
+  c.cy = (uint32_t)y & (kRegionWidth - 1);
+  c.key = (c.region << (2 * kRBits)) | (c.cy << kRBits) | c.cx;
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: delta application. One thread per cell visit of every edge of every rank's blob.
+// Three phases with a grid-wide order between them (separate launches on one stream):
+//   remove : drop (cell, block) entries, decrement Region::count, clear the occupancy bit
+//   fixup  : re-set the bit of every cell touched by a removal that still holds another block
+//   insert : add entries, increment Region::count, set the bit
+// ------------------------------------------------------------------------------------------
+
+struct BlobView {
+  const DeltaHeader *hdr;
+  const EdgeRec *remove_edges, *insert_edges;
+  const BlockUpd *block_upd;
+  const ModelUpd *model_upd;
+};
+
+__device__ __forceinline__ BlobView blob_view(const unsigned char *blobs, int rank, size_t slot_bytes)
+{
+  BlobView v;
+  const unsigned char *p = blobs + (size_t)rank * slot_bytes;
+  v.hdr = reinterpret_cast<const DeltaHeader *>(p);
+  v.remove_edges = reinterpret_cast<const EdgeRec *>(p + sizeof(DeltaHeader));
+  v.insert_edges = v.remove_edges + v.hdr->n_remove;
+  v.block_upd = reinterpret_cast<const BlockUpd *>(v.insert_edges + v.hdr->n_insert);
+  v.model_upd = reinterpret_cast<const ModelUpd *>(v.block_upd + v.hdr->n_block_upd);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k1_table_updates(GridView g, const unsigned char *blobs, int n_ranks,
+                                                         size_t slot_bytes, unsigned long long epoch)
+{
+  for (int rank = 0; rank < n_ranks; rank++) {
+    const BlobView v = blob_view(blobs, rank, slot_bytes);
+    const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t i = t0; i < v.hdr->n_model_upd; i += stride) {
+      const ModelUpd u = v.model_upd[i];
+      if (u.id < g.n_models) {
+        g.mdl_root[u.id] = u.root;
+        g.mdl_ranger_return[u.id] = u.ranger_return;
+        g.mdl_flags[u.id] = u.flags;
+      }
+    }
+    for (uint32_t i = t0; i < v.hdr->n_block_upd; i += stride) {
+      const BlockUpd u = v.block_upd[i];
+      if (u.block < g.n_blocks) {
+        g.blk_model[u.block] = u.model;
+        g.blk_zmin[u.block] = u.zmin;
+        g.blk_zmax[u.block] = u.zmax;
+        // insertion order across the whole job: epoch, then rank, then call order within the rank
+        g.blk_seq[u.layer & 1][u.block] =
+            (epoch << 40) | ((unsigned long long)(v.hdr->rank & 0xff) << 32) | u.seq_local;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k1_remove(GridView g, const unsigned char *blobs, int n_ranks, size_t slot_bytes)
+{
+  for (int rank = 0; rank < n_ranks; rank++) {
+    const BlobView v = blob_view(blobs, rank, slot_bytes);
+    const uint32_t steps = v.hdr->steps_remove, stride = gridDim.x * blockDim.x;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < steps; t += stride) {
+      const EdgeRec e = v.remove_edges[find_edge(v.remove_edges, v.hdr->n_remove, t)];
+      int32_t x, y;
+      edge_cell(e, t - e.first_step, x, y);
+      const CellAddr c = cell_addr(g, x, y);
+      const unsigned long long entry = ((unsigned long long)c.key << 32) | (unsigned long long)(e.block + 1u);
+      unsigned long long *slots = g.slots[e.layer & 1];
+      uint32_t h = mix32(c.key) & g.slot_mask;
+      for (uint32_t probes = 0; probes <= g.slot_mask; probes++) { // EraseAll: every copy goes
+        const unsigned long long cur = ld_slot(slots + h);
+        if (cur == kSlotEmpty)
+          break;
+        if (cur == entry)
+          atomicCAS(slots + h, entry, kSlotTomb);
+        h = (h + 1) & g.slot_mask;
+      }
+      atomicSub(g.reg_count + c.region, 1u);
+      atomicAnd(g.occ[e.layer & 1] + c.region * kRegionWidth + c.cy, ~(1u << c.cx));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k1_fixup(GridView g, const unsigned char *blobs, int n_ranks, size_t slot_bytes)
+{
+  for (int rank = 0; rank < n_ranks; rank++) {
+    const BlobView v = blob_view(blobs, rank, slot_bytes);
+    const uint32_t steps = v.hdr->steps_remove, stride = gridDim.x * blockDim.x;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < steps; t += stride) {
+      const EdgeRec e = v.remove_edges[find_edge(v.remove_edges, v.hdr->n_remove, t)];
+      int32_t x, y;
+      edge_cell(e, t - e.first_step, x, y);
+      const CellAddr c = cell_addr(g, x, y);
+      const unsigned long long *slots = g.slots[e.layer & 1];
+      uint32_t h = mix32(c.key) & g.slot_mask;
+      for (uint32_t probes = 0; probes <= g.slot_mask; probes++) {
+        const unsigned long long cur = ld_slot(slots + h);
+        if (cur == kSlotEmpty)
+          break;
+        if ((uint32_t)(cur >> 32) == c.key) { // tombstones carry key 0xffffffff, never a cell key
+          atomicOr(g.occ[e.layer & 1] + c.region * kRegionWidth + c.cy, 1u << c.cx);
+          break;
+        }
+        h = (h + 1) & g.slot_mask;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k1_insert(GridView g, const unsigned char *blobs, int n_ranks, size_t slot_bytes)
+{
+  for (int rank = 0; rank < n_ranks; rank++) {
+    const BlobView v = blob_view(blobs, rank, slot_bytes);
+    const uint32_t steps = v.hdr->steps_insert, stride = gridDim.x * blockDim.x;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < steps; t += stride) {
+      const EdgeRec e = v.insert_edges[find_edge(v.insert_edges, v.hdr->n_insert, t)];
+      int32_t x, y;
+      edge_cell(e, t - e.first_step, x, y);
+      const CellAddr c = cell_addr(g, x, y);
+      const unsigned long long entry = ((unsigned long long)c.key << 32) | (unsigned long long)(e.block + 1u);
+      unsigned long long *slots = g.slots[e.layer & 1];
+      uint32_t h = mix32(c.key) & g.slot_mask;
+      for (uint32_t probes = 0; probes <= g.slot_mask;) {
+        const unsigned long long cur = ld_slot(slots + h);
+        if (cur == kSlotEmpty || cur == kSlotTomb) {
+          if (atomicCAS(slots + h, cur, entry) == cur)
+            break;
+          continue; // lost the race for this slot: look at it again
+        }
+        h = (h + 1) & g.slot_mask;
+        probes++;
+      }
+      atomicAdd(g.reg_count + c.region, 1u);
+      atomicOr(g.occ[e.layer & 1] + c.region * kRegionWidth + c.cy, 1u << c.cx);
+    }
+  }
+}
+
+// Compaction of one layer's cell-content table: re-insert the live entries into a clean table
+// (tombstones only ever turn into entries again, never into empty slots, so probe chains grow
+// until this runs). Host policy: rt_api.cu.
+__global__ void __launch_bounds__(256) k1_rehash(const unsigned long long *src, unsigned long long *dst, uint32_t slot_mask)
+{
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint64_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= slot_mask; i += stride) {
+    const unsigned long long cur = src[i];
+    if (cur == kSlotEmpty || cur == kSlotTomb)
+      continue;
+    uint32_t h = mix32((uint32_t)(cur >> 32)) & slot_mask;
+    for (;;) {
+      if (atomicCAS(dst + h, kSlotEmpty, cur) == kSlotEmpty)
+        break;
+      h = (h + 1) & slot_mask;
+    }
+  }
+}
+
+static int delta_grid_blocks()
+{
+  static int blocks = 0;
+  if (!blocks) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    blocks = sms * 8; // 8 resident 256-thread CTAs per SM, grid-stride over the steps
+  }
+  return blocks;
+}
+
+void launch_apply_deltas(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
+                         unsigned long long epoch, void *stream, uint64_t *launch_counter)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  const int blocks = delta_grid_blocks();
+  k1_table_updates<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes, epoch);
+  k1_remove<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes);
+  k1_fixup<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes);
+  k1_insert<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes);
+  if (launch_counter)
+    *launch_counter += 4;
+}
+
+void launch_rehash(const unsigned long long *src, unsigned long long *dst, uint32_t slot_mask, void *stream)
+{
+  k1_rehash<<<delta_grid_blocks(), 256, 0, (cudaStream_t)stream>>>(src, dst, slot_mask);
+}
+
+// ------------------------------------------------------------------------------------------
+// K2a: per-beam headings. One thread per fan; the ranger rule is a sequential float-rounding
+// recurrence (model_ranger.cc:237-241,254), so it cannot be evaluated per beam independently.
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128) k2_fan_headings(FanBatchView b)
+{
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= b.n_fans)
+    return;
+  const FanRec fan = b.fans[f];
+  const uint32_t first = b.fan_first_beam[f], n = fan.n_samples;
+  double *heading = b.heading + first;
+  double *bearing = b.bearings ? b.bearings + first : nullptr;
+  if (fan.angles == 0 /* STG_RT_ANGLES_RANGER */) {
+    const uint32_t nm1 = n - 1u; // unsigned, like std::max(sample_count - 1, 1u)
+    const double incr = fan.fov / (double)(nm1 > 1u ? nm1 : 1u);
+    const double start = n > 1 ? -fan.fov / 2.0 : 0.0;
+    double a = fan.oa;
+    for (uint32_t t = 0; t < n; t++) {
+      const float fa = (float)a; // float savedAngle / distortedAngle with zero angle noise
+      heading[t] = (double)fa;
+      if (bearing)
+        bearing[t] = start + ((double)t) * incr;
+      a = (double)fa + incr;
+    }
+  } else if (fan.angles == 1 /* STG_RT_ANGLES_EVEN_FOV */) {
+    const double starta = fan.fov / 2.0 - fan.oa;
+    for (uint32_t s = 0; s < n; s++) {
+      const double h = ((double)s * fan.fov / (double)(n - 1u)) - starta;
+      heading[s] = h;
+      if (bearing)
+        bearing[s] = h - fan.oa;
+    }
+  } else {
+    for (uint32_t s = 0; s < n; s++) {
+      const double h = b.headings_in[fan.first_heading + s];
+      heading[s] = h;
+      if (bearing)
+        bearing[s] = h - fan.oa;
+    }
+  }
+}
+
+void launch_fan_headings(const FanBatchView &b, void *stream)
+{
+  if (!b.n_fans)
+    return;
+  k2_fan_headings<<<(b.n_fans + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b);
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: the ray march. One thread (lane) per beam; consecutive lanes are consecutive beams of a fan,
+// so a warp reads a handful of neighbouring 128-byte occupancy tiles and its lanes stop at about
+// the same wall. State machine and arithmetic follow World::Raytrace (world.cc:756-963) exactly:
+// truncating double->int conversions, the stale error term across empty-region jumps, int -=
+// double for the remaining distance.
+// ------------------------------------------------------------------------------------------
+
+struct HitTest {
+  uint32_t finder, finder_root;
+  uint32_t pred, ztest;
+  double oz;
+};
+
+// Resolve an occupied cell: among the blocks rendered into it that pass the z test and the
+// predicate, the one first in Cell::blocks[layer] order wins (world.cc:841-862).
+__device__ __forceinline__ int32_t resolve_cell(const GridView &g, const HitTest &ht, int layer, uint32_t key)
+{
+  const unsigned long long *slots = g.slots[layer];
+  const unsigned long long *seq = g.blk_seq[layer];
+  unsigned long long best_seq = ~0ull;
+  int32_t best_model = -1;
+  uint32_t h = mix32(key) & g.slot_mask;
+  for (uint32_t probes = 0; probes <= g.slot_mask; probes++) {
+    const unsigned long long cur = __ldg(slots + h);
+    if (cur == kSlotEmpty)
+      break;
+    if ((uint32_t)(cur >> 32) == key) {
+      const uint32_t blk = (uint32_t)cur - 1u;
+      const bool z_ok = !ht.ztest || !(ht.oz < __ldg(g.blk_zmin + blk) || ht.oz > __ldg(g.blk_zmax + blk));
+      if (z_ok) {
+        const uint32_t m = __ldg(g.blk_model + blk);
+        bool pass;
+        if (ht.pred == 0u) // ranger_match
+          pass = __ldg(g.mdl_root + m) != ht.finder_root && !(__ldg(g.mdl_ranger_return + m) < 0.0);
+        else if (ht.pred == 2u) // gripper_raytrace_match
+          pass = m != ht.finder && (__ldg(g.mdl_flags + m) & 1u);
+        else // fiducial / blob / bumper: unrelated
+          pass = __ldg(g.mdl_root + m) != ht.finder_root;
+        if (pass) {
+          const unsigned long long s = __ldg(seq + blk);
+          if (s < best_seq) {
+            best_seq = s;
+            best_model = (int32_t)m;
+          }
+        }
+      }
+    }
+    h = (h + 1) & g.slot_mask;
+  }
+  return best_model;
+}
+
+__global__ void __launch_bounds__(128) k2_ray_march(GridView g, FanBatchView b)
+{
+  const uint64_t beam = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (beam >= b.n_beams)
+    return;
+
+  // which fan does this beam belong to
+  uint32_t lo = 0, hi = b.n_fans;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(b.fan_first_beam + mid) <= beam)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  const FanRec fan = b.fans[lo];
+
+  HitTest ht;
+  ht.finder = fan.finder;
+  ht.finder_root = __ldg(g.mdl_root + fan.finder);
+  ht.pred = fan.pred;
+  ht.ztest = fan.ztest;
+  ht.oz = fan.oz;
+  const int layer = fan.layer & 1;
+  const double ppm = g.ppm;
+
+  double gx = fan.ox * ppm, gy = fan.oy * ppm;
+  const double x_start = gx, y_start = gy;
+  const double heading = b.heading[beam];
+  const double ang = heading == 0.0 ? 1e-12 : heading;
+  double sina, cosa;
+  if (b.trig_in) {
+    cosa = b.trig_in[2 * beam];
+    sina = b.trig_in[2 * beam + 1];
+  } else {
+    sina = sin(ang);
+    cosa = cos(ang);
+  }
+  const double tana = sina / cosa;
+  const double dx = ppm * fan.range * cosa, dy = ppm * fan.range * sina;
+  const int32_t sx = dx < 0 ? -1 : 1, sy = dy < 0 ? -1 : 1;
+  const int32_t ax = __double2int_rz(fabs(dx)), ay = __double2int_rz(fabs(dy));
+  const int32_t bx = 2 * ax, by = 2 * ay;
+  int32_t exy = ay - ax;
+  int32_t n = ax + ay;
+
+  const double xjumpx = sx * kRegionWidth, xjumpy = sx * kRegionWidth * tana;
+  const double yjumpx = sy * kRegionWidth / tana, yjumpy = sy * kRegionWidth;
+  const double xjumpdist = fabs(xjumpx) + fabs(xjumpy);
+  const double yjumpdist = fabs(yjumpx) + fabs(yjumpy);
+
+  double xcrossx = 0, xcrossy = 0, ycrossx = 0, ycrossy = 0, distX = 0, distY = 0;
+  bool need_crossings = true;
+
+  double range = fan.range;
+  int32_t hit_model = -1, hit_x = 0, hit_y = 0;
+  uint32_t cell_visits = 0, region_probes = 0;
+  const uint32_t *occ = g.occ[layer];
+
+  while (n > 0) {
+    region_probes++;
+    const int32_t ix0 = __double2int_rz(gx), iy0 = __double2int_rz(gy);
+    const int32_t grx = ix0 >> kRBits, gry = iy0 >> kRBits;
+    const int32_t rix = grx - g.rx0, riy = gry - g.ry0;
+    uint32_t region = 0, count = 0;
+    if ((uint32_t)rix < (uint32_t)g.nrx && (uint32_t)riy < (uint32_t)g.nry) {
+      region = (uint32_t)(riy * g.nrx + rix);
+      count = __ldg(g.reg_count + region);
+    }
+    if (count) {
+      need_crossings = true;
+      int32_t cx = ix0 & (kRegionWidth - 1), cy = iy0 & (kRegionWidth - 1);
+      const uint32_t *tile = occ + region * kRegionWidth;
+      uint32_t row = __ldg(tile + cy);
+      while ((uint32_t)cx < (uint32_t)kRegionWidth && (uint32_t)cy < (uint32_t)kRegionWidth && n > 0) {
+        cell_visits++;
+        if ((row >> cx) & 1u) {
+          const uint32_t key = (region << (2 * kRBits)) | ((uint32_t)cy << kRBits) | (uint32_t)cx;
+          const int32_t m = resolve_cell(g, ht, layer, key);
+          if (m >= 0) {
+            hit_model = m;
+            hit_x = grx * kRegionWidth + cx;
+            hit_y = gry * kRegionWidth + cy;
+            if (ax > ay)
+              range = fabs((gx - x_start) / cosa) / ppm;
+            else
+              range = fabs((gy - y_start) / sina) / ppm;
+            n = 0; // leave both loops
+            break;
+          }
+        }
+        if (exy < 0) {
+          gx += sx;
+          exy += by;
+          cx += sx;
+        } else {
+          gy += sy;
+          exy -= bx;
+          cy += sy;
+          if ((uint32_t)cy < (uint32_t)kRegionWidth)
+            row = __ldg(tile + cy);
+        }
+        --n;
+      }
+    } else {
+      if (need_crossings) {
+        need_crossings = false;
+        const int32_t ix = ix0, iy = iy0;
+        double regionx = (double)(ix / kRegionWidth * kRegionWidth);
+        double regiony = (double)(iy / kRegionWidth * kRegionWidth);
+        if ((gx < 0) && (ix % kRegionWidth))
+          regionx -= kRegionWidth;
+        if ((gy < 0) && (iy % kRegionWidth))
+          regiony -= kRegionWidth;
+        const double xdx = sx < 0 ? regionx - gx - 1.0 : regionx + kRegionWidth - gx;
+        const double xdy = xdx * tana;
+        const double ydy = sy < 0 ? regiony - gy - 1.0 : regiony + kRegionWidth - gy;
+        const double ydx = ydy / tana;
+        xcrossx = gx + xdx;
+        xcrossy = gy + xdy;
+        ycrossx = gx + ydx;
+        ycrossy = gy + ydy;
+        distX = fabs(xdx) + fabs(xdy);
+        distY = fabs(ydx) + fabs(ydy);
+      }
+      if (distX < distY) {
+        gx = xcrossx;
+        gy = xcrossy;
+        n = __double2int_rz((double)n - distX);
+        xcrossx += xjumpx;
+        xcrossy += xjumpy;
+        distY -= distX;
+        distX = xjumpdist;
+      } else {
+        gx = ycrossx;
+        gy = ycrossy;
+        n = __double2int_rz((double)n - distY);
+        ycrossx += yjumpx;
+        ycrossy += yjumpy;
+        distX -= distY;
+        distY = yjumpdist;
+      }
+    }
+  }
+
+  // K3 (ranger epilogue, fused): model_ranger.cc:243-251 with zero noise
+  if (b.ranges)
+    b.ranges[beam] = range;
+  if (b.intensities)
+    b.intensities[beam] = hit_model >= 0 ? __ldg(g.mdl_ranger_return + hit_model) : 0.0;
+  if (b.hit_model)
+    b.hit_model[beam] = hit_model;
+  if (b.hit_cell) {
+    b.hit_cell[2 * beam] = hit_x;
+    b.hit_cell[2 * beam + 1] = hit_y;
+  }
+  if (b.steps) {
+    b.steps[2 * beam] = cell_visits;
+    b.steps[2 * beam + 1] = region_probes;
+  }
+}
+
+void launch_ray_march(const GridView &g, const FanBatchView &b, void *stream)
+{
+  if (!b.n_beams)
+    return;
+  const uint64_t blocks = (b.n_beams + 127) / 128;
+  k2_ray_march<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(g, b);
+}
+
+} // namespace stg

@@ -1,0 +1,289 @@
+"""ctypes binding of libstg_rt.so (include/stg_rt.h): the same entry points a patched libstage
+calls, with numpy arrays for the bulk arguments. Nothing here computes: every call goes to the
+CUDA library, and importing fails loudly if that library cannot be built or loaded.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+PRED_RANGER, PRED_UNRELATED, PRED_GRIPPER = 0, 1, 2
+ANGLES_RANGER, ANGLES_EVEN_FOV, ANGLES_EXPLICIT = 0, 1, 2
+VIS_GRIPPER_RETURN, VIS_OBSTACLE_RETURN, VIS_BLOB_RETURN = 1, 2, 4
+WANT_RANGES, WANT_INTENSITIES, WANT_BEARINGS, WANT_HIT_MODEL, WANT_HIT_CELL, WANT_STEPS = 1, 2, 4, 8, 16, 32
+WANT_ALL = 63
+
+# stg_rt_fan, 64 bytes
+FAN_DTYPE = np.dtype([
+    ("finder", "<u4"), ("n_samples", "<u4"), ("pred", "u1"), ("ztest", "u1"), ("layer", "u1"),
+    ("angles", "u1"), ("first_heading", "<u4"), ("ox", "<f8"), ("oy", "<f8"), ("oz", "<f8"),
+    ("oa", "<f8"), ("range", "<f8"), ("fov", "<f8")])
+assert FAN_DTYPE.itemsize == 64
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("device", ctypes.c_int32), ("ppm", ctypes.c_double),
+                ("sreg_x0", ctypes.c_int32), ("sreg_y0", ctypes.c_int32), ("sreg_nx", ctypes.c_int32),
+                ("sreg_ny", ctypes.c_int32), ("max_models", ctypes.c_uint32), ("max_blocks", ctypes.c_uint32),
+                ("max_cell_entries", ctypes.c_uint32), ("flags", ctypes.c_uint32)]
+
+
+class FanOut(ctypes.Structure):
+    _fields_ = [("ranges", ctypes.c_void_p), ("intensities", ctypes.c_void_p), ("bearings", ctypes.c_void_p),
+                ("hit_model", ctypes.c_void_p), ("hit_cell", ctypes.c_void_p), ("steps", ctypes.c_void_p)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in (
+        "launches_rasterise", "launches_march", "launches_post", "launches_other", "beams", "fans",
+        "map_calls", "unmap_calls", "edge_steps", "h2d_bytes", "d2h_bytes")]
+
+
+class StgRtError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("stg_rt error %d: %s" % (code, text))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load (building first if stale and nvcc is here) the CUDA library. No fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    L = ctypes.CDLL(path)
+    vp, u32, i32, f64, u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int32, ctypes.c_double, ctypes.c_uint64
+    sz = ctypes.c_size_t
+    sigs = {
+        "stg_rt_abi_version": (ctypes.c_int, []),
+        "stg_rt_create": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.POINTER(vp)]),
+        "stg_rt_destroy": (ctypes.c_int, [vp]),
+        "stg_rt_last_error": (ctypes.c_char_p, [vp]),
+        "stg_rt_model_upsert": (ctypes.c_int, [vp, u32, u32, f64, i32, i32, u32, vp]),
+        "stg_rt_block_map": (ctypes.c_int, [vp, u32, u32, ctypes.c_int, f64, f64, ctypes.c_int, vp]),
+        "stg_rt_block_unmap": (ctypes.c_int, [vp, u32, ctypes.c_int]),
+        "stg_rt_fans_submit": (ctypes.c_int, [vp, u32, vp, vp, vp, ctypes.POINTER(FanOut)]),
+        "stg_rt_flush": (ctypes.c_int, [vp]),
+        "stg_rt_sync": (ctypes.c_int, [vp]),
+        "stg_rt_host_alloc": (vp, [vp, sz]),
+        "stg_rt_host_free": (ctypes.c_int, [vp, vp]),
+        "stg_rt_set_create": (ctypes.c_int, [vp, u32, vp, vp, vp, u32, ctypes.POINTER(vp)]),
+        "stg_rt_set_destroy": (ctypes.c_int, [vp, vp]),
+        "stg_rt_set_update_origins": (ctypes.c_int, [vp, vp, vp, ctypes.c_int]),
+        "stg_rt_set_trace": (ctypes.c_int, [vp, vp]),
+        "stg_rt_set_download": (ctypes.c_int, [vp, vp, ctypes.POINTER(FanOut)]),
+        "stg_rt_set_device_ptrs": (ctypes.c_int, [vp, vp, ctypes.POINTER(FanOut)]),
+        "stg_rt_set_beams": (u64, [vp]),
+        "stg_rt_grid_dump": (ctypes.c_int64, [vp, vp, ctypes.c_int64, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
+        "stg_rt_delta_export": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(sz)]),
+        "stg_rt_delta_slot_bytes": (sz, [vp]),
+        "stg_rt_delta_apply_gathered": (ctypes.c_int, [vp, vp, ctypes.c_int, sz]),
+        "stg_rt_set_stream": (ctypes.c_int, [vp, vp]),
+        "stg_rt_get_stream": (vp, [vp]),
+        "stg_rt_get_stats": (ctypes.c_int, [vp, ctypes.POINTER(Stats)]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)  # AttributeError if the library does not export what the header declares
+        fn.restype, fn.argtypes = res, args
+    if L.stg_rt_abi_version() != 1:
+        raise RuntimeError("libstg_rt.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = (
+    "stg_rt_abi_version stg_rt_create stg_rt_destroy stg_rt_last_error stg_rt_model_upsert stg_rt_block_map "
+    "stg_rt_block_unmap stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
+    "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
+    "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
+    "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats").split()
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def make_fans(n):
+    return np.zeros(n, FAN_DTYPE)
+
+
+class Outputs:
+    """numpy result arrays for a batch of fans, plus the FanOut struct pointing at them."""
+
+    def __init__(self, n_beams, want=WANT_ALL, alloc=None):
+        def mk(flag, dtype, shape):
+            if not (want & flag):
+                return None
+            if alloc is None:
+                return np.empty(shape, dtype)
+            return alloc(shape, dtype)
+        self.ranges = mk(WANT_RANGES, np.float64, (n_beams,))
+        self.intensities = mk(WANT_INTENSITIES, np.float64, (n_beams,))
+        self.bearings = mk(WANT_BEARINGS, np.float64, (n_beams,))
+        self.hit_model = mk(WANT_HIT_MODEL, np.int32, (n_beams,))
+        self.hit_cell = mk(WANT_HIT_CELL, np.int32, (n_beams, 2))
+        self.steps = mk(WANT_STEPS, np.uint32, (n_beams, 2))
+        self.struct = FanOut(*[_ptr(a) for a in (self.ranges, self.intensities, self.bearings,
+                                                 self.hit_model, self.hit_cell, self.steps)])
+
+
+class Context:
+    """One stg_rt_ctx: the replicated world state of one GPU plus its queues."""
+
+    def __init__(self, ppm, sreg_x0, sreg_y0, sreg_nx, sreg_ny, max_models=1 << 16, max_blocks=1 << 16,
+                 max_cell_entries=0, device=0):
+        self._L = lib()
+        cfg = Config(ctypes.sizeof(Config), device, ppm, sreg_x0, sreg_y0, sreg_nx, sreg_ny, max_models,
+                     max_blocks, max_cell_entries, 0)
+        h = ctypes.c_void_p()
+        rc = self._L.stg_rt_create(ctypes.byref(cfg), ctypes.byref(h))
+        if rc:
+            raise StgRtError(rc, (self._L.stg_rt_last_error(None) or b"").decode())
+        self._h = h
+        self._keep = []  # arrays the library writes into asynchronously
+        self._pinned = []
+
+    def close(self):
+        if self._h:
+            self._L.stg_rt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise StgRtError(rc, (self._L.stg_rt_last_error(self._h) or b"").decode())
+        return rc
+
+    # ---- world state
+    def model_upsert(self, mid, root, ranger_return=1.0, fiducial_return=0, fiducial_key=0, vis_flags=VIS_OBSTACLE_RETURN,
+                     rgba=None):
+        c = None if rgba is None else np.ascontiguousarray(rgba, np.float64)
+        self._check(self._L.stg_rt_model_upsert(self._h, mid, root, ranger_return, fiducial_return, fiducial_key,
+                                                vis_flags, _ptr(c)))
+
+    def block_map(self, block, model, layer, zmin, zmax, xy):
+        xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
+        self._check(self._L.stg_rt_block_map(self._h, block, model, layer, zmin, zmax, len(xy), _ptr(xy)))
+
+    def block_unmap(self, block, layer):
+        self._check(self._L.stg_rt_block_unmap(self._h, block, layer))
+
+    # ---- rays
+    def fans_submit(self, fans, out, headings=None, trig=None):
+        fans = np.ascontiguousarray(fans, FAN_DTYPE)
+        headings = None if headings is None else np.ascontiguousarray(headings, np.float64)
+        trig = None if trig is None else np.ascontiguousarray(trig, np.float64)
+        self._keep.append(out)
+        self._check(self._L.stg_rt_fans_submit(self._h, len(fans), _ptr(fans), _ptr(headings), _ptr(trig),
+                                               ctypes.byref(out.struct)))
+
+    def flush(self):
+        self._check(self._L.stg_rt_flush(self._h))
+
+    def sync(self):
+        self._check(self._L.stg_rt_sync(self._h))
+        self._keep.clear()
+
+    def trace(self, fans, want=WANT_ALL, headings=None, trig=None):
+        """submit + sync convenience: returns the Outputs of this batch."""
+        out = Outputs(int(np.sum(fans["n_samples"])), want)
+        self.fans_submit(fans, out, headings, trig)
+        self.sync()
+        return out
+
+    def pinned_empty(self, shape, dtype):
+        """numpy array over page-locked memory the GPU writes results into directly."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = self._L.stg_rt_host_alloc(self._h, max(n, 1))
+        if not p:
+            raise StgRtError(-2, (self._L.stg_rt_last_error(self._h) or b"").decode())
+        buf = (ctypes.c_char * max(n, 1)).from_address(p)
+        arr = np.frombuffer(buf, dtype, int(np.prod(shape))).reshape(shape)
+        self._pinned.append(p)
+        return arr
+
+    # ---- resident sets
+    def set_create(self, fans, want=WANT_ALL, headings=None, trig=None):
+        return FanSet(self, fans, want, headings, trig)
+
+    # ---- inspection
+    def grid_dump(self):
+        """(records[n,5] int32 {layer,x,y,pos,block}, region_counts[m,3] int64 {rx,ry,count})."""
+        nc = ctypes.c_int64(0)
+        n = self._check(self._L.stg_rt_grid_dump(self._h, None, 0, None, 0, ctypes.byref(nc)))
+        rec = np.zeros((max(n, 1), 5), np.int32)
+        cnt = np.zeros((max(nc.value, 1), 3), np.int64)
+        n2 = self._check(self._L.stg_rt_grid_dump(self._h, _ptr(rec), n, _ptr(cnt), nc.value, ctypes.byref(nc)))
+        assert n2 == n
+        return rec[:n], cnt[:nc.value]
+
+    def stats(self):
+        s = Stats()
+        self._check(self._L.stg_rt_get_stats(self._h, ctypes.byref(s)))
+        return {n: getattr(s, n) for n, _ in Stats._fields_}
+
+    # ---- multi-GPU deltas / plumbing
+    def delta_slot_bytes(self):
+        return self._L.stg_rt_delta_slot_bytes(self._h)
+
+    def delta_export(self, rank):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        self._check(self._L.stg_rt_delta_export(self._h, rank, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def delta_apply_gathered(self, dev_ptr, n_ranks, slot_bytes):
+        self._check(self._L.stg_rt_delta_apply_gathered(self._h, dev_ptr, n_ranks, slot_bytes))
+
+    def set_stream(self, cuda_stream):
+        self._check(self._L.stg_rt_set_stream(self._h, cuda_stream))
+
+    def get_stream(self):
+        return self._L.stg_rt_get_stream(self._h)
+
+
+class FanSet:
+    def __init__(self, ctx, fans, want, headings, trig):
+        self.ctx = ctx
+        fans = np.ascontiguousarray(fans, FAN_DTYPE)
+        headings = None if headings is None else np.ascontiguousarray(headings, np.float64)
+        trig = None if trig is None else np.ascontiguousarray(trig, np.float64)
+        h = ctypes.c_void_p()
+        ctx._check(ctx._L.stg_rt_set_create(ctx._h, len(fans), _ptr(fans), _ptr(headings), _ptr(trig), want,
+                                            ctypes.byref(h)))
+        self._h = h
+        self.want = want
+        self.n_fans = len(fans)
+        self.n_beams = int(ctx._L.stg_rt_set_beams(h))
+
+    def update_origins(self, xyza, layer):
+        xyza = np.ascontiguousarray(xyza, np.float64).reshape(self.n_fans, 4)
+        self.ctx._check(self.ctx._L.stg_rt_set_update_origins(self.ctx._h, self._h, _ptr(xyza), layer))
+
+    def trace(self):
+        self.ctx._check(self.ctx._L.stg_rt_set_trace(self.ctx._h, self._h))
+
+    def download(self, want=None):
+        out = Outputs(self.n_beams, self.want if want is None else want)
+        self.ctx._check(self.ctx._L.stg_rt_set_download(self.ctx._h, self._h, ctypes.byref(out.struct)))
+        return out
+
+    def device_ptrs(self):
+        d = FanOut()
+        self.ctx._check(self.ctx._L.stg_rt_set_device_ptrs(self.ctx._h, self._h, ctypes.byref(d)))
+        return d
+
+    def destroy(self):
+        if self._h:
+            self.ctx._L.stg_rt_set_destroy(self.ctx._h, self._h)
+            self._h = None

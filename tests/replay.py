@@ -1,0 +1,160 @@
+"""Drive the C ABI (stage_b200.rt.Context) and/or the T1 oracle with a recorded reference trace, in
+the order a patched libstage would issue the calls. Test infrastructure."""
+import numpy as np
+
+import oracle_lib
+import trace_io
+from stage_b200 import rt
+
+
+def extent_of(trace, margin_sregs=0):
+    """smallest superregion rectangle (x0, y0, nx, ny) holding every mapped polygon"""
+    v = trace.verts
+    x0, y0 = int(v[:, 0].min()) >> 10, int(v[:, 1].min()) >> 10
+    x1, y1 = int(v[:, 0].max()) >> 10, int(v[:, 1].max()) >> 10
+    return x0 - margin_sregs, y0 - margin_sregs, x1 - x0 + 1 + 2 * margin_sregs, y1 - y0 + 1 + 2 * margin_sregs
+
+
+def make_context(trace, **kw):
+    x0, y0, nx, ny = extent_of(trace)
+    n_blocks = int(trace.events["block"][trace.events["type"] == trace_io.EV_MAP].max()) + 1
+    ctx = rt.Context(trace.ppm, x0, y0, nx, ny, max_models=int(trace.models["id"].max()) + 1,
+                     max_blocks=n_blocks, max_cell_entries=1 << 20, **kw)
+    for m in trace.models:
+        ctx.model_upsert(int(m["id"]), int(m["root"]), float(m["ranger_return"]), int(m["fiducial_return"]),
+                         int(m["fiducial_key"]), int(m["flags"]), m["color"])
+    return ctx
+
+
+def make_t1(trace):
+    w = oracle_lib.T1World(trace.ppm)
+    for m in trace.models:
+        w.model_upsert(int(m["id"]), int(m["root"]), float(m["ranger_return"]), int(m["fiducial_return"]),
+                       int(m["fiducial_key"]), int(m["flags"]))
+    return w
+
+
+def rays_to_fans(rays):
+    fans = rt.make_fans(len(rays))
+    fans["finder"] = rays["finder"]
+    fans["n_samples"] = 1
+    fans["pred"] = rays["kind"]
+    fans["ztest"] = rays["ztest"]
+    fans["layer"] = rays["layer"]
+    fans["angles"] = rt.ANGLES_EXPLICIT
+    fans["first_heading"] = np.arange(len(rays), dtype=np.uint32)
+    for k in ("ox", "oy", "oz", "oa", "range"):
+        fans[k] = rays[k]
+    return fans, np.ascontiguousarray(rays["oa"])
+
+
+def rays_to_t1(rays):
+    r = np.zeros(len(rays), oracle_lib.T1_RAY)
+    for k in ("ox", "oy", "oz", "oa", "range", "finder", "kind", "ztest", "layer"):
+        r[k] = rays[k]
+    return r
+
+
+def scan_to_fan(ev, sc):
+    fan = rt.make_fans(1)
+    fan["finder"] = ev["model"]
+    fan["n_samples"] = sc["n"]
+    fan["pred"] = rt.PRED_RANGER
+    fan["ztest"] = 1
+    fan["layer"] = ev["layer"]
+    fan["angles"] = rt.ANGLES_RANGER
+    fan["ox"], fan["oy"], fan["oz"], fan["oa"] = sc["origin"]
+    fan["range"] = sc["range_max"]
+    fan["fov"] = sc["fov"]
+    return fan
+
+
+class GpuReplay:
+    """Results of pushing a whole trace through the C ABI."""
+
+    def __init__(self, trace, strict, max_ticks=None, sync_every_tick=True, want=rt.WANT_ALL):
+        self.trace = trace
+        ctx = self.ctx = make_context(trace)
+        n = len(trace.rays)
+        self.ranges = np.full(n, np.nan)
+        self.hit_model = np.full(n, -2, np.int32)
+        self.hit_cell = np.zeros((n, 2), np.int32)
+        self.steps = np.zeros((n, 2), np.uint32)
+        self.scans = []  # (event, Outputs)
+        pending = []
+        ticks = 0
+        for ev in trace.events:
+            t = ev["type"]
+            if t == trace_io.EV_MAP:
+                ctx.block_map(int(ev["block"]), int(ev["model"]), int(ev["layer"]), float(ev["zmin"]),
+                              float(ev["zmax"]), trace.polygon(ev))
+            elif t == trace_io.EV_UNMAP:
+                ctx.block_unmap(int(ev["block"]), int(ev["layer"]))
+            elif t == trace_io.EV_RAYS:
+                first, cnt = int(ev["first"]), int(ev["model"])
+                rays = trace.rays[first:first + cnt]
+                fans, headings = rays_to_fans(rays)
+                out = rt.Outputs(cnt, want)
+                ctx.fans_submit(fans, out, headings=headings,
+                                trig=oracle_lib.libm_trig(headings) if strict else None)
+                pending.append((first, cnt, out))
+            elif t == trace_io.EV_RANGER_SCAN:
+                sc = trace.scan(ev)
+                fan = scan_to_fan(ev, sc)
+                out = rt.Outputs(sc["n"], want)
+                trig = None
+                if strict:
+                    trig = oracle_lib.libm_trig(oracle_lib.ranger_headings(sc["origin"][3], sc["fov"], sc["n"]))
+                ctx.fans_submit(fan, out, trig=trig)
+                self.scans.append((ev, sc, out))
+            elif t == trace_io.EV_TICK:
+                ticks += 1
+                if sync_every_tick:
+                    ctx.sync()
+                    self._collect(pending)
+                if max_ticks is not None and ticks >= max_ticks:
+                    break
+        ctx.sync()
+        self._collect(pending)
+        self.n_ticks = ticks
+
+    def _collect(self, pending):
+        for first, cnt, out in pending:
+            if out.ranges is not None:
+                self.ranges[first:first + cnt] = out.ranges
+            if out.hit_model is not None:
+                self.hit_model[first:first + cnt] = out.hit_model
+            if out.hit_cell is not None:
+                self.hit_cell[first:first + cnt] = out.hit_cell
+            if out.steps is not None:
+                self.steps[first:first + cnt] = out.steps
+        pending.clear()
+
+
+class T1Replay:
+    """The same trace through the T1 oracle, keeping the per-ray hit cells and step counters."""
+
+    def __init__(self, trace, max_ticks=None):
+        w = self.world = make_t1(trace)
+        self.hits = np.zeros(len(trace.rays), oracle_lib.T1_HIT)
+        self.scans = []
+        ticks = 0
+        for ev in trace.events:
+            t = ev["type"]
+            if t == trace_io.EV_MAP:
+                w.block_map(int(ev["block"]), int(ev["model"]), int(ev["layer"]), float(ev["zmin"]),
+                            float(ev["zmax"]), trace.polygon(ev))
+            elif t == trace_io.EV_UNMAP:
+                w.block_unmap(int(ev["block"]), int(ev["layer"]))
+            elif t == trace_io.EV_RAYS:
+                first, cnt = int(ev["first"]), int(ev["model"])
+                self.hits[first:first + cnt] = w.raytrace(rays_to_t1(trace.rays[first:first + cnt]))
+            elif t == trace_io.EV_RANGER_SCAN:
+                sc = trace.scan(ev)
+                self.scans.append(w.ranger_fan(int(ev["model"]), int(ev["layer"]), sc["origin"], sc["range_max"],
+                                               sc["fov"], sc["n"]))
+            elif t == trace_io.EV_TICK:
+                ticks += 1
+                if max_ticks is not None and ticks >= max_ticks:
+                    break
+        self.n_ticks = ticks

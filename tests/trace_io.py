@@ -1,14 +1,17 @@
 """Reader for the reference event traces written by oracle/ref_harness.cc (format:
 oracle/trace_format.h). Test infrastructure only."""
 import gzip
+import lzma
+
 import numpy as np
 
-MAGIC = b"STGTRC02"
-EV_MAP, EV_UNMAP, EV_RAYS, EV_TICK = 1, 2, 3, 4
+MAGIC = b"STGTRC03"
+EV_MAP, EV_UNMAP, EV_RAYS, EV_TICK, EV_RANGER_SCAN = 1, 2, 3, 4, 5
+SCAN_HEADER_DOUBLES = 6
 KIND_RANGER, KIND_UNRELATED, KIND_GRIPPER = 0, 1, 2
 
 HEADER = np.dtype([("magic", "S8"), ("ppm", "<f8"), ("n_models", "<u4"), ("n_events", "<u4"),
-                   ("n_verts", "<u4"), ("n_rays", "<u4"), ("n_ticks", "<u4"), ("reserved", "<u4")])
+                   ("n_verts", "<u4"), ("n_rays", "<u4"), ("n_ticks", "<u4"), ("n_aux", "<u4")])
 MODEL = np.dtype([("id", "<u4"), ("parent", "<u4"), ("root", "<u4"), ("fiducial_return", "<i4"),
                   ("fiducial_key", "<i4"), ("flags", "<u4"), ("ranger_return", "<f8"),
                   ("color", "<f8", (4,)), ("type", "S16")])
@@ -21,10 +24,17 @@ assert HEADER.itemsize == 40 and MODEL.itemsize == 80 and EVENT.itemsize == 32 a
 
 
 class Trace:
-    def __init__(self, header, models, events, verts, rays):
+    def __init__(self, header, models, events, verts, rays, aux):
         self.ppm = float(header["ppm"])
         self.n_ticks = int(header["n_ticks"])
-        self.models, self.events, self.verts, self.rays = models, events, verts, rays
+        self.models, self.events, self.verts, self.rays, self.aux = models, events, verts, rays, aux
+
+    def scan(self, ev):
+        """RANGER_SCAN event -> dict(origin[4], range_max, fov, n, ranges, intensities, bearings)."""
+        n, a = int(ev["n_pts"]), self.aux[ev["first"]:]
+        h = SCAN_HEADER_DOUBLES
+        return dict(origin=a[0:4], range_max=float(a[4]), fov=float(a[5]), n=n, ranges=a[h:h + n],
+                    intensities=a[h + n:h + 2 * n], bearings=a[h + 2 * n:h + 3 * n])
 
     def polygon(self, ev):
         """(n_pts, 2) int32 pixel-space vertices of a MAP event."""
@@ -32,7 +42,8 @@ class Trace:
 
 
 def load(path):
-    opener = gzip.open if str(path).endswith(".gz") else open
+    path = str(path)
+    opener = gzip.open if path.endswith(".gz") else lzma.open if path.endswith(".xz") else open
     with opener(path, "rb") as f:
         buf = f.read()
     h = np.frombuffer(buf, HEADER, 1)[0]
@@ -43,6 +54,7 @@ def load(path):
     events = np.frombuffer(buf, EVENT, h["n_events"], off); off += events.nbytes
     verts = np.frombuffer(buf, "<i4", 2 * int(h["n_verts"]), off).reshape(-1, 2); off += verts.nbytes
     rays = np.frombuffer(buf, RAY, h["n_rays"], off); off += rays.nbytes
+    aux = np.frombuffer(buf, "<f8", h["n_aux"], off); off += aux.nbytes
     if off != len(buf):
         raise ValueError("trailing bytes in trace %r" % (path,))
-    return Trace(h, models, events, verts, rays)
+    return Trace(h, models, events, verts, rays, aux)
