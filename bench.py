@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""Benchmark of the sensor-raycast path on BASELINE.json's config 3 ("C3"):
+synthetic 8192 x 8192-cell world (ppm 50, 4096 random rectangles + walls), 1000 robots per GPU each
+with a 1080-beam, 270 degree, 30 m laser.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                         # the reference's CPU path
+    torchrun --nproc-per-node N bench.py --gpus N ...              # N > 1: one rank per GPU
+
+A "step" is one simulation tick's worth of sensor rays for the robots of one GPU.
+  value  rays/s of the march (fan headings K2a + ray march K2 with the K3 epilogue fused), fans
+         and grid resident in HBM, L2 flushed before every timed step.
+  e2e    rays/s of a whole tick through the C ABI from host buffers: re-rasterise every robot body
+         (Block::UnMap + Block::Map deltas, K1), submit the fans, trace, copy ranges + hit model
+         back to page-locked host memory.  N > 1: the moved-block deltas of all ranks are
+         all-gathered with NCCL and applied out of the gathered buffer.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FOV_DEG, SAMPLES, RANGE_MAX = 270.0, 1080, 30.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--robots", type=int, default=1000, help="robots per GPU")
+    ap.add_argument("--rects", type=int, default=4096)
+    ap.add_argument("--half-extent", type=float, default=81.92)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": "C3 synthetic: %dx%d-cell world (ppm 50), %d rectangles + walls, %d robots/GPU x %d-beam "
+                    "%g-degree %g m laser, z-test, ranger predicate" % (
+                        int(2 * args.half_extent * 50), int(2 * args.half_extent * 50), args.rects, args.robots,
+                        SAMPLES, FOV_DEG, RANGE_MAX),
+        "robots_total": args.robots * n_gpus, "beams_per_robot": SAMPLES, "rays_per_step": args.robots * n_gpus * SAMPLES,
+        "parallelism": "robots sharded over %d GPU(s), grid replicated" % n_gpus,
+        "l2": "flushed (256 MiB write) before every timed step of `value`",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) >= 6:
+                self.samples.append(p)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's CPU path (oracle/_ref = the unmodified reference built headless)
+# ---------------------------------------------------------------------------------------------
+
+def host_rays(fans):
+    """Expand ranger fans into one record per beam exactly as ModelRanger::Sensor::Update walks them
+    (float-rounded running heading, model_ranger.cc:237-241,254), for World::Raytrace on the host."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    m = int(fans["n_samples"][0])
+    assert np.all(fans["n_samples"] == m)
+    nf = len(fans)
+    incr = fans["fov"] / max(m - 1, 1)
+    a = fans["oa"].astype(np.float64)
+    h = np.empty((nf, m))
+    for t in range(m):  # sequential in t (the recurrence), vectorised over fans
+        fa = a.astype(np.float32).astype(np.float64)
+        h[:, t] = fa
+        a = fa + incr
+    rays = np.zeros((nf, m), oracle_lib.REF_RAY)
+    for k in ("ox", "oy", "oz", "range", "finder", "ztest"):
+        rays[k] = fans[k][:, None]
+    rays["kind"] = fans["pred"][:, None]
+    rays["oa"] = h
+    return rays.reshape(-1)
+
+
+def reference_world(world):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from stage_b200 import worldgen
+    if not oracle_lib.ref_available():
+        return None, None
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(devnull, 1)   # the reference prints its banner to stdout; the JSON line must stay alone
+    try:
+        ref = oracle_lib.RefWorld(text=worldgen.to_worldfile_text(world), record=False)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(devnull)
+        os.close(saved)
+    assert ref.model_id("o0") == int(world.obstacle_ids[0]) and ref.model_id("r0") == int(world.robot_ids[0])
+    return ref, oracle_lib
+
+
+def cpu_reference_throughput(world, fans, threads, reps, warm=1):
+    """rays/s of the reference's own World::Raytrace over the given fans, `threads` host threads."""
+    ref, _ = reference_world(world)
+    if ref is None:
+        return None
+    rays = host_rays(fans)
+    best, per_rep, hits = None, [], None
+    for i in range(warm + reps):
+        hits, secs = ref.raytrace(rays, nthreads=threads)
+        if i >= warm:
+            per_rep.append(secs)
+    best = min(per_rep)
+    return {"rays": len(rays), "best_s": best, "mean_s": float(np.mean(per_rep)), "rays_per_s": len(rays) / best,
+            "hits": hits, "ref": ref, "rays_arr": rays}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from stage_b200 import worldgen
+    n_gpus = args.gpus
+    world = worldgen.make_world(seed=1, n_rects=args.rects, n_robots=args.robots * n_gpus, half_extent_m=args.half_extent)
+    fans = worldgen.ranger_fans(world, layer=1, fov_deg=FOV_DEG, samples=SAMPLES, range_max=RANGE_MAX)
+    threads = args.cpu_threads or os.cpu_count()
+    ref, _ = reference_world(world)
+    if ref is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built on this box"}))
+        return 0
+    rays = host_rays(fans)
+    for _ in range(args.warmup):
+        ref.raytrace(rays, nthreads=threads)
+    t_total = 0.0
+    for _ in range(args.steps):
+        _, secs = ref.raytrace(rays, nthreads=threads)
+        t_total += secs
+    v = len(rays) * args.steps / t_total
+    line = {
+        "impl": "reference", "metric": "rays/sec", "value": v, "unit": "rays/s", "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "ticks_per_s": args.steps / t_total,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, n_gpus),
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": "reference",
+                         "sample": "every step = all %d rays of one tick through the unmodified reference's "
+                                   "World::Raytrace (oracle/_ref), split over %d host threads" % (len(rays), threads)},
+        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    sys.stdout.flush()
+    os._exit(0)  # a reference World must never be destroyed
+
+
+# ---------------------------------------------------------------------------------------------
+# this repo's path
+# ---------------------------------------------------------------------------------------------
+
+class CudaArray:
+    """zero-copy view of a raw device pointer for torch.as_tensor"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from stage_b200 import rt, worldgen
+
+    n_gpus = args.gpus
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if world_size != n_gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torchrun --nproc-per-node %d" % (n_gpus, world_size, n_gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if n_gpus > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    world = worldgen.make_world(seed=1, n_rects=args.rects, n_robots=args.robots * n_gpus, half_extent_m=args.half_extent)
+    x0, y0, nx, ny = world.sreg_extent()
+    n_bodies = len(world.obstacles) + len(world.robots)
+    ctx = rt.Context(world.ppm, x0, y0, nx, ny, max_models=world.n_models + 1, max_blocks=n_bodies,
+                     max_cell_entries=1 << 22, device=local_rank, max_delta_bytes=(1 << 20) if n_gpus > 1 else 0)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    worldgen.load_into_context(ctx, world)
+
+    lo, hi = rank * args.robots, (rank + 1) * args.robots
+    my_ids = world.robot_ids[lo:hi]
+    my_blocks = (len(world.obstacles) + np.arange(lo, hi)).astype(np.uint32)
+    n_beams = args.robots * SAMPLES
+    total_rays = n_beams * n_gpus
+
+    def barrier():
+        if n_gpus > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if n_gpus == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: resident fans, kernels only -------------------------------------------------
+    want_value = rt.WANT_RANGES | rt.WANT_INTENSITIES | rt.WANT_HIT_MODEL | rt.WANT_HIT_CELL
+    fans0 = worldgen.ranger_fans(world, layer=1, fov_deg=FOV_DEG, samples=SAMPLES, range_max=RANGE_MAX,
+                                 robots=world.robots[lo:hi], robot_ids=my_ids)
+    fset = ctx.set_create(fans0, want=want_value)
+    # algorithmic bytes: the kernel's own C / R counters (tests prove them equal to the oracle's)
+    cset = ctx.set_create(fans0, want=rt.WANT_STEPS | rt.WANT_HIT_MODEL)
+    cset.trace()
+    cnt = cset.download()
+    C, R = int(cnt.steps[:, 0].sum(dtype=np.int64)), int(cnt.steps[:, 1].sum(dtype=np.int64))
+    hit_frac = float(np.mean(cnt.hit_model >= 0))
+    cset.destroy()
+    algo_bytes = 4 * C + 4 * R + 40 * n_beams
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    launches0 = ctx.stats()
+    for _ in range(max(args.warmup, 3)):
+        fset.trace()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    march_ms, head_ms = [], []
+    barrier()
+    for s, e in ev:
+        flush_buf.fill_(1)       # evict the grid and the fans from L2
+        s.record(stream)
+        fset.trace()
+        e.record(stream)
+        e.synchronize()
+        kt = ctx.kernel_times()
+        march_ms.append(kt["march_ms"])
+        head_ms.append(kt["headings_ms"])
+    barrier()
+    step_ms = [s.elapsed_time(e) for s, e in ev]
+    t_value_ms = max_over_ranks(float(np.sum(step_ms)))
+    value = total_rays * args.steps / (t_value_ms * 1e-3)
+    launches1 = ctx.stats()
+
+    # ---- e2e: one whole tick per step through the C ABI, host buffers ---------------------------
+    want_e2e = rt.WANT_RANGES | rt.WANT_HIT_MODEL
+    out = rt.Outputs(n_beams, want_e2e, alloc=ctx.pinned_empty)
+    n_e2e = args.steps + max(args.warmup, 3)
+    poses = [world.robots[lo:hi]]
+    for t in range(n_e2e):
+        poses.append(worldgen.step_robots(world, poses[-1], t))
+    ticks = []   # what libstage's Move() / Sensor::Update would hand over each tick (caller-side work)
+    for t in range(1, n_e2e + 1):
+        polys = worldgen.robot_polygons(world, poses[t])
+        layer_w = t % 2
+        ticks.append({
+            "xy": np.ascontiguousarray(np.concatenate(polys, 0), np.int32),
+            "first": np.arange(len(polys) + 1, dtype=np.uint32) * 4,
+            "z": np.ascontiguousarray(np.stack([np.zeros(len(polys)), np.full(len(polys), world.robot_size[2])], 1)),
+            "layer_w": layer_w,
+            "fans": worldgen.ranger_fans(world, layer=(t + 1) % 2, fov_deg=FOV_DEG, samples=SAMPLES, range_max=RANGE_MAX,
+                                         robots=poses[t], robot_ids=my_ids),
+        })
+    slot = ctx.delta_slot_bytes()
+    gathered = torch.empty(slot * n_gpus, dtype=torch.uint8, device="cuda") if n_gpus > 1 else None
+
+    def tick(tk):
+        ctx.blocks_remap(my_blocks, my_ids, tk["layer_w"], tk["z"], tk["first"], tk["xy"])
+        if n_gpus > 1:
+            ptr, nbytes = ctx.delta_export(rank)
+            mine = torch.as_tensor(CudaArray(ptr, slot), device="cuda")
+            dist.all_gather_into_tensor(gathered, mine)
+            ctx.delta_apply_gathered(gathered.data_ptr(), n_gpus, slot)
+        ctx.fans_submit(tk["fans"], out)
+        ctx.sync()
+
+    nw = max(args.warmup, 3)
+    for tk in ticks[:nw]:
+        tick(tk)
+    st0 = ctx.stats()
+    barrier()
+    t0 = time.perf_counter()
+    for tk in ticks[nw:]:
+        tick(tk)
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    st1 = ctx.stats()
+    clocks = sampler.stop() if sampler else None
+    e2e_value = total_rays * args.steps / t_e2e
+    e2e_kt = ctx.kernel_times()
+
+    # ---- CPU baseline + parity of the last e2e tick against the unmodified reference ----------
+    cpu = None
+    parity = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        threads = args.cpu_threads or os.cpu_count()
+        sample_fans = fans0
+        res = cpu_reference_throughput(world, sample_fans, threads, reps=3)
+        if res is not None:
+            one = res["ref"].raytrace(res["rays_arr"][:SAMPLES * 50], nthreads=1)[1]
+            cpu = {"value": res["rays_per_s"], "unit": "rays/s", "cores": threads, "kind": "reference",
+                   "sample": "all %d rays of one tick (static robots), best of 3, unmodified reference "
+                             "World::Raytrace via oracle/_ref on %d threads; 1 thread: %.3g rays/s"
+                             % (res["rays"], threads, SAMPLES * 50 / one)}
+            g = fset.download()
+            h = res["hits"]
+            parity = {"rays": int(len(h)), "hit_model_mismatch": int(np.count_nonzero(g.hit_model != h["hit_model"])),
+                      "max_range_err_m": float(np.max(np.abs(g.ranges - h["range"])))}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        march_avg_ms = float(np.mean(march_ms))
+        achieved = algo_bytes / (march_avg_ms * 1e-3) / 1e9
+        line = {
+            "metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": t_value_ms / args.steps,
+            "ticks_per_s": args.steps / (t_value_ms * 1e-3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_gpus),
+            "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "ticks_per_s": args.steps / t_e2e,
+                    "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // args.steps,
+                    "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) // args.steps,
+                    "last_step_kernel_ms": e2e_kt, "timing": "host clock around K ticks, synchronised both sides, max over ranks"},
+            "gpu_launches": int(sum(st1[k] - launches0[k] for k in ("launches_rasterise", "launches_march", "launches_post", "launches_other"))),
+            "kernel_ms": {"ray_march": march_avg_ms, "fan_headings": float(np.mean(head_ms)),
+                          "share_of_step": march_avg_ms / (t_value_ms / args.steps) if n_gpus == 1 else None},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "algorithmic_bytes_per_launch": algo_bytes, "cell_visits": C, "region_probes": R,
+                         "beams": n_beams, "hit_fraction": hit_frac,
+                         "note": "bytes = 4*C + 4*R + 40 per beam (SURVEY.md 8d), C/R counted by the kernel and proven equal to the oracle's in tests"},
+            "cpu_baseline": cpu, "parity_vs_reference": parity, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if n_gpus > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)  # the reference World loaded for the CPU baseline must never be destroyed
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        sys.exit(run_reference(a))
+    run_ours(a)

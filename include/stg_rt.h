@@ -91,6 +91,9 @@ typedef struct {
   uint32_t max_cell_entries; /* expected peak number of (cell, block) entries per layer; the
                                 per-layer cell-entry table is sized to >= 2x this. 0 = 1<<22 */
   uint32_t flags;
+  uint32_t max_delta_bytes; /* size of the moved-block delta buffer = the per-rank slot of the
+                               all-gather; bounds the deltas of one flush round. 0 = 8 MiB */
+  uint32_t reserved;
 } stg_rt_config;
 
 /* One sensor fan = one call of ModelRanger::Sensor::Update, one World::Raytrace(fan), or a group of
@@ -151,6 +154,13 @@ int stg_rt_block_map(stg_rt_ctx *ctx, uint32_t block_id, uint32_t model_id, int 
                      double zmax, int n_pts, const int32_t *xy);
 /* Block::UnMap(layer), block.cc:183-189. Unmapping an unmapped block is a no-op, as there. */
 int stg_rt_block_unmap(stg_rt_ctx *ctx, uint32_t block_id, int layer);
+
+/* n times { stg_rt_block_unmap(blocks[i], layer); stg_rt_block_map(blocks[i], models[i], layer,
+   z[2i], z[2i+1], first_pt[i+1]-first_pt[i], xy + 2*first_pt[i]); } in one call: what
+   ModelPosition::Move does for every moving model each tick (model_position.cc:549-552), for
+   callers that move many bodies at once. first_pt has n+1 entries. */
+int stg_rt_blocks_remap(stg_rt_ctx *ctx, uint32_t n, const uint32_t *blocks, const uint32_t *models, int layer,
+                        const double *z, const uint32_t *first_pt, const int32_t *xy);
 
 /* ---- rays --------------------------------------------------------------------------------- */
 
@@ -238,6 +248,12 @@ typedef struct {
   uint64_t h2d_bytes, d2h_bytes;
 } stg_rt_stats;
 int stg_rt_get_stats(stg_rt_ctx *ctx, stg_rt_stats *out);
+
+/* Device time in milliseconds of the most recent launch of each kernel group, measured with CUDA
+   events recorded on the context's stream around the launches: ms[0] = delta application (K1),
+   ms[1] = fan headings (K2a), ms[2] = ray march with fused epilogue (K2+K3). -1 = never launched.
+   Waits for the stream. */
+int stg_rt_kernel_times(stg_rt_ctx *ctx, float ms[3]);
 
 #ifdef __cplusplus
 }

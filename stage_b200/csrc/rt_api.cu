@@ -94,6 +94,8 @@ struct stg_rt_ctx {
   DevBuf d_blob;
   size_t blob_cap = 0;
   cudaEvent_t blob_uploaded = nullptr; // the pinned blob may be rewritten once this has fired
+  cudaEvent_t t_ev[3][2] = {};          // [deltas, headings, march][start, stop]
+  bool t_rec[3] = { false, false, false };
 
   // fans queued by stg_rt_fans_submit and not launched yet
   std::vector<FanRec> q_fans;
@@ -365,8 +367,11 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
       c->live_entries[L] += bb.d_live[L];
     if (apply) {
       c->epoch++;
+      CU(c, cudaEventRecord(c->t_ev[0][0], c->stream));
       launch_apply_deltas(c->g, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, c->stream,
                           &c->stats.launches_rasterise);
+      CU(c, cudaEventRecord(c->t_ev[0][1], c->stream));
+      c->t_rec[0] = true;
       CU(c, cudaGetLastError());
     }
     if (out_bytes)
@@ -521,8 +526,13 @@ int launch_fans_locked(stg_rt_ctx *c)
   c->stats.h2d_bytes += b_fans + b_first + b_head + b_trig;
 
   const FanBatchView v = view_of(c->d, n_fans, beams, want, c->q_has_trig, b_head != 0);
+  CU(c, cudaEventRecord(c->t_ev[1][0], c->stream));
   launch_fan_headings(v, c->stream);
+  CU(c, cudaEventRecord(c->t_ev[1][1], c->stream));
+  CU(c, cudaEventRecord(c->t_ev[2][0], c->stream));
   launch_ray_march(c->g, v, c->stream);
+  CU(c, cudaEventRecord(c->t_ev[2][1], c->stream));
+  c->t_rec[1] = c->t_rec[2] = true;
   CU(c, cudaGetLastError());
   c->stats.launches_post += 1;
   c->stats.launches_march += 1;
@@ -614,6 +624,9 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
   CUC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   CUC(cudaEventCreateWithFlags(&c->blob_uploaded, cudaEventDisableTiming));
+  for (int k = 0; k < 3; k++)
+    for (int j = 0; j < 2; j++)
+      CUC(cudaEventCreate(&c->t_ev[k][j]));
   GridView &g = c->g;
   g.ppm = cfg->ppm;
   g.rx0 = cfg->sreg_x0 * 32;
@@ -651,7 +664,7 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
   CUC(cudaMemsetAsync(g.mdl_root, 0, (size_t)cfg->max_models * 4, c->stream));
   CUC(cudaMemsetAsync(g.mdl_ranger_return, 0, (size_t)cfg->max_models * 8, c->stream));
   CUC(cudaMemsetAsync(g.mdl_flags, 0, (size_t)cfg->max_models * 4, c->stream));
-  c->blob_cap = 8u << 20;
+  c->blob_cap = cfg->max_delta_bytes ? std::max<size_t>(cfg->max_delta_bytes, 4096) : (8u << 20);
   CUC(cudaMalloc(&c->d_blob.p, c->blob_cap));
   c->d_blob.cap = c->blob_cap;
   CUC(cudaMallocHost(&c->h_blob.p, c->blob_cap));
@@ -684,6 +697,9 @@ int stg_rt_destroy(stg_rt_ctx *c)
   for (auto &kv : c->host_allocs)
     cudaFreeHost(kv.first);
   cudaEventDestroy(c->blob_uploaded);
+  for (int k = 0; k < 3; k++)
+    for (int j = 0; j < 2; j++)
+      cudaEventDestroy(c->t_ev[k][j]);
   cudaStreamDestroy(c->own_stream);
   delete c;
   return STG_RT_OK;
@@ -718,12 +734,47 @@ int stg_rt_model_upsert(stg_rt_ctx *c, uint32_t id, uint32_t root_id, double ran
   return STG_RT_OK;
 }
 
+static int block_map_locked(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id, int layer, double zmin, double zmax, int n_pts,
+                            const int32_t *xy);
+static int block_unmap_locked(stg_rt_ctx *c, uint32_t block_id, int layer);
+
 int stg_rt_block_map(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id, int layer, double zmin, double zmax, int n_pts,
                      const int32_t *xy)
 {
   if (!c)
     return STG_RT_EINVAL;
   std::lock_guard<std::mutex> lk(c->mu);
+  return block_map_locked(c, block_id, model_id, layer, zmin, zmax, n_pts, xy);
+}
+
+int stg_rt_block_unmap(stg_rt_ctx *c, uint32_t block_id, int layer)
+{
+  if (!c)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  return block_unmap_locked(c, block_id, layer);
+}
+
+int stg_rt_blocks_remap(stg_rt_ctx *c, uint32_t n, const uint32_t *blocks, const uint32_t *models, int layer, const double *z,
+                        const uint32_t *first_pt, const int32_t *xy)
+{
+  if (!c || (n && (!blocks || !models || !z || !first_pt || !xy)))
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  for (uint32_t i = 0; i < n; i++) {
+    int rc = block_unmap_locked(c, blocks[i], layer);
+    if (!rc)
+      rc = block_map_locked(c, blocks[i], models[i], layer, z[2 * i], z[2 * i + 1], (int)(first_pt[i + 1] - first_pt[i]),
+                            xy + 2 * (size_t)first_pt[i]);
+    if (rc)
+      return rc;
+  }
+  return STG_RT_OK;
+}
+
+static int block_map_locked(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id, int layer, double zmin, double zmax, int n_pts,
+                            const int32_t *xy)
+{
   if (layer < 0 || layer > 1 || n_pts < 0 || (n_pts && !xy))
     return fail(c, STG_RT_EINVAL, "block_map: bad layer / points");
   if (block_id >= c->cfg.max_blocks)
@@ -754,11 +805,8 @@ int stg_rt_block_map(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id, int la
   return STG_RT_OK;
 }
 
-int stg_rt_block_unmap(stg_rt_ctx *c, uint32_t block_id, int layer)
+static int block_unmap_locked(stg_rt_ctx *c, uint32_t block_id, int layer)
 {
-  if (!c)
-    return STG_RT_EINVAL;
-  std::lock_guard<std::mutex> lk(c->mu);
   if (layer < 0 || layer > 1)
     return fail(c, STG_RT_EINVAL, "block_unmap: bad layer");
   if (block_id >= c->cfg.max_blocks)
@@ -966,8 +1014,13 @@ int stg_rt_set_trace(stg_rt_ctx *c, stg_rt_set *s)
     s->fans_dirty = false;
   }
   const FanBatchView v = view_of(s->d, (uint32_t)s->fans.size(), s->n_beams, s->want, s->has_trig, s->has_headings);
+  CU(c, cudaEventRecord(c->t_ev[1][0], c->stream));
   launch_fan_headings(v, c->stream);
+  CU(c, cudaEventRecord(c->t_ev[1][1], c->stream));
+  CU(c, cudaEventRecord(c->t_ev[2][0], c->stream));
   launch_ray_march(c->g, v, c->stream);
+  CU(c, cudaEventRecord(c->t_ev[2][1], c->stream));
+  c->t_rec[1] = c->t_rec[2] = true;
   CU(c, cudaGetLastError());
   c->stats.launches_post += 1;
   c->stats.launches_march += 1;
@@ -1131,8 +1184,11 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_r
   for (int L = 0; L < 2; L++)
     c->used_upper[L] += ins;
   c->epoch++;
+  CU(c, cudaEventRecord(c->t_ev[0][0], c->stream));
   launch_apply_deltas(c->g, (const unsigned char *)dev_gathered, n_ranks, slot_bytes, c->epoch, c->stream,
                       &c->stats.launches_rasterise);
+  CU(c, cudaEventRecord(c->t_ev[0][1], c->stream));
+  c->t_rec[0] = true;
   CU(c, cudaGetLastError());
   return STG_RT_OK;
 }
@@ -1155,6 +1211,20 @@ int stg_rt_set_stream(stg_rt_ctx *c, void *cuda_stream)
 }
 
 void *stg_rt_get_stream(stg_rt_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int stg_rt_kernel_times(stg_rt_ctx *c, float ms[3])
+{
+  if (!c || !ms)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 3; k++) {
+    ms[k] = -1.0f;
+    if (c->t_rec[k])
+      CU(c, cudaEventElapsedTime(&ms[k], c->t_ev[k][0], c->t_ev[k][1]));
+  }
+  return STG_RT_OK;
+}
 
 int stg_rt_get_stats(stg_rt_ctx *c, stg_rt_stats *out)
 {

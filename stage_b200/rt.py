@@ -27,7 +27,8 @@ class Config(ctypes.Structure):
     _fields_ = [("struct_size", ctypes.c_uint32), ("device", ctypes.c_int32), ("ppm", ctypes.c_double),
                 ("sreg_x0", ctypes.c_int32), ("sreg_y0", ctypes.c_int32), ("sreg_nx", ctypes.c_int32),
                 ("sreg_ny", ctypes.c_int32), ("max_models", ctypes.c_uint32), ("max_blocks", ctypes.c_uint32),
-                ("max_cell_entries", ctypes.c_uint32), ("flags", ctypes.c_uint32)]
+                ("max_cell_entries", ctypes.c_uint32), ("flags", ctypes.c_uint32),
+                ("max_delta_bytes", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 class FanOut(ctypes.Structure):
@@ -67,6 +68,7 @@ def lib():
         "stg_rt_model_upsert": (ctypes.c_int, [vp, u32, u32, f64, i32, i32, u32, vp]),
         "stg_rt_block_map": (ctypes.c_int, [vp, u32, u32, ctypes.c_int, f64, f64, ctypes.c_int, vp]),
         "stg_rt_block_unmap": (ctypes.c_int, [vp, u32, ctypes.c_int]),
+        "stg_rt_blocks_remap": (ctypes.c_int, [vp, u32, vp, vp, ctypes.c_int, vp, vp, vp]),
         "stg_rt_fans_submit": (ctypes.c_int, [vp, u32, vp, vp, vp, ctypes.POINTER(FanOut)]),
         "stg_rt_flush": (ctypes.c_int, [vp]),
         "stg_rt_sync": (ctypes.c_int, [vp]),
@@ -86,6 +88,7 @@ def lib():
         "stg_rt_set_stream": (ctypes.c_int, [vp, vp]),
         "stg_rt_get_stream": (vp, [vp]),
         "stg_rt_get_stats": (ctypes.c_int, [vp, ctypes.POINTER(Stats)]),
+        "stg_rt_kernel_times": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_float * 3)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)  # AttributeError if the library does not export what the header declares
@@ -98,10 +101,10 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "stg_rt_abi_version stg_rt_create stg_rt_destroy stg_rt_last_error stg_rt_model_upsert stg_rt_block_map "
-    "stg_rt_block_unmap stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
+    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
-    "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats").split()
+    "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times").split()
 
 
 def _ptr(a):
@@ -136,10 +139,10 @@ class Context:
     """One stg_rt_ctx: the replicated world state of one GPU plus its queues."""
 
     def __init__(self, ppm, sreg_x0, sreg_y0, sreg_nx, sreg_ny, max_models=1 << 16, max_blocks=1 << 16,
-                 max_cell_entries=0, device=0):
+                 max_cell_entries=0, device=0, max_delta_bytes=0):
         self._L = lib()
         cfg = Config(ctypes.sizeof(Config), device, ppm, sreg_x0, sreg_y0, sreg_nx, sreg_ny, max_models,
-                     max_blocks, max_cell_entries, 0)
+                     max_blocks, max_cell_entries, 0, max_delta_bytes, 0)
         h = ctypes.c_void_p()
         rc = self._L.stg_rt_create(ctypes.byref(cfg), ctypes.byref(h))
         if rc:
@@ -177,6 +180,16 @@ class Context:
 
     def block_unmap(self, block, layer):
         self._check(self._L.stg_rt_block_unmap(self._h, block, layer))
+
+    def blocks_remap(self, blocks, models, layer, z, first_pt, xy):
+        blocks = np.ascontiguousarray(blocks, np.uint32)
+        models = np.ascontiguousarray(models, np.uint32)
+        z = np.ascontiguousarray(z, np.float64)
+        first_pt = np.ascontiguousarray(first_pt, np.uint32)
+        xy = np.ascontiguousarray(xy, np.int32)
+        assert len(first_pt) == len(blocks) + 1 and len(models) == len(blocks) and z.size == 2 * len(blocks)
+        self._check(self._L.stg_rt_blocks_remap(self._h, len(blocks), _ptr(blocks), _ptr(models), layer, _ptr(z),
+                                                _ptr(first_pt), _ptr(xy)))
 
     # ---- rays
     def fans_submit(self, fans, out, headings=None, trig=None):
@@ -232,6 +245,12 @@ class Context:
         s = Stats()
         self._check(self._L.stg_rt_get_stats(self._h, ctypes.byref(s)))
         return {n: getattr(s, n) for n, _ in Stats._fields_}
+
+    def kernel_times(self):
+        """dict(deltas_ms, headings_ms, march_ms) of the most recent launches (device time)."""
+        ms = (ctypes.c_float * 3)()
+        self._check(self._L.stg_rt_kernel_times(self._h, ctypes.byref(ms)))
+        return {"deltas_ms": ms[0], "headings_ms": ms[1], "march_ms": ms[2]}
 
     # ---- multi-GPU deltas / plumbing
     def delta_slot_bytes(self):

@@ -1,0 +1,209 @@
+"""Synthetic worlds for the raycast path (BASELINE.json configs 3-5).
+
+A world is described in metres exactly as a Stage world file would describe it (every obstacle and
+robot is a `model` with a pose and a size, body = the default unit-square block scaled to the size),
+so the same description can be (a) turned into pixel-space polygons for the GPU path here and
+(b) written out as world-file text. `pixel_polygon` follows Model::LocalToPixels
+(model.cc:474-491) after BlockGroup::CalcSize (blockgroup.cc:84-112) operation for operation, with
+the host libm's cos/sin, so both routes rasterise identical polygons.
+
+All coordinates live on a 1 mm / 0.001 degree lattice so that their decimal text form parses back
+to the same doubles.
+"""
+import math
+
+import numpy as np
+
+from . import rt
+
+
+class World:
+    def __init__(self, ppm, half_extent_m, obstacles, robots, obstacle_height=1.0, robot_size=(0.44, 0.38, 0.6)):
+        self.ppm = ppm
+        self.half_extent_m = half_extent_m
+        self.obstacles = obstacles      # (n, 4) float64: centre x, centre y, size x, size y  [m]
+        self.robots = robots            # (n, 3) float64: x, y [m], heading [degrees]
+        self.obstacle_height = obstacle_height
+        self.robot_size = robot_size
+        # ids as the reference assigns them: 0 is the world's ground model, then file order
+        self.obstacle_ids = 1 + np.arange(len(obstacles), dtype=np.uint32)
+        self.robot_ids = 1 + len(obstacles) + np.arange(len(robots), dtype=np.uint32)
+
+    @property
+    def n_models(self):
+        return 1 + len(self.obstacles) + len(self.robots)
+
+    def sreg_extent(self):
+        """(x0, y0, nx, ny) in superregions (1024 cells) covering the world"""
+        half_cells = int(math.ceil(self.half_extent_m * self.ppm))
+        lo = (-half_cells) >> 10
+        hi = (half_cells - 1) >> 10
+        return lo, lo, hi - lo + 1, hi - lo + 1
+
+
+def _lattice(v, step=0.001):
+    return np.round(np.asarray(v, np.float64) / step) * 1.0 / (1.0 / step)
+
+
+def make_world(seed=1, n_rects=4096, n_robots=1000, half_extent_m=81.92, ppm=50.0, side_range=(0.5, 4.0)):
+    """Seeded random axis-aligned rectangles plus four boundary walls, and robots at poses that are
+    outside every rectangle (0.5 m clearance) and at least 0.6 m from each other."""
+    rng = np.random.RandomState(seed)
+    H = half_extent_m
+    margin = 0.5
+    sides = rng.uniform(side_range[0], side_range[1], size=(n_rects, 2))
+    sides = np.maximum(np.round(sides * 1000) / 1000.0, 0.04)
+    cx = rng.uniform(-H + margin, H - margin, size=n_rects)
+    cy = rng.uniform(-H + margin, H - margin, size=n_rects)
+    # keep rectangles inside the walls
+    cx = np.clip(cx, -H + margin + sides[:, 0] / 2, H - margin - sides[:, 0] / 2)
+    cy = np.clip(cy, -H + margin + sides[:, 1] / 2, H - margin - sides[:, 1] / 2)
+    cx, cy = np.round(cx * 1000) / 1000.0, np.round(cy * 1000) / 1000.0
+    wall_t = 0.1
+    walls = np.array([[0.0, -H + 0.25, 2 * H - 0.4, wall_t], [0.0, H - 0.25, 2 * H - 0.4, wall_t],
+                      [-H + 0.25, 0.0, wall_t, 2 * H - 0.4], [H - 0.25, 0.0, wall_t, 2 * H - 0.4]])
+    obstacles = np.concatenate([np.stack([cx, cy, sides[:, 0], sides[:, 1]], 1), walls], 0)
+
+    robots = np.zeros((n_robots, 3))
+    placed = 0
+    clear = 0.5
+    cell = 1.0
+    occupied = {}
+    ox0, ox1 = obstacles[:, 0] - obstacles[:, 2] / 2 - clear, obstacles[:, 0] + obstacles[:, 2] / 2 + clear
+    oy0, oy1 = obstacles[:, 1] - obstacles[:, 3] / 2 - clear, obstacles[:, 1] + obstacles[:, 3] / 2 + clear
+    while placed < n_robots:
+        cand = rng.uniform(-H + 1.5, H - 1.5, size=(4 * (n_robots - placed) + 16, 2))
+        cand = np.round(cand * 1000) / 1000.0
+        for x, y in cand:
+            if np.any((x > ox0) & (x < ox1) & (y > oy0) & (y < oy1)):
+                continue
+            key = (int(math.floor(x / cell)), int(math.floor(y / cell)))
+            near = False
+            for dx in (-1, 0, 1):
+                for dy in (-1, 0, 1):
+                    for (px, py) in occupied.get((key[0] + dx, key[1] + dy), ()):
+                        if (px - x) ** 2 + (py - y) ** 2 < 0.6 ** 2:
+                            near = True
+            if near:
+                continue
+            occupied.setdefault(key, []).append((x, y))
+            robots[placed] = (x, y, np.round(rng.uniform(-180.0, 180.0) * 1000) / 1000.0)
+            placed += 1
+            if placed == n_robots:
+                break
+    return World(ppm, half_extent_m, obstacles, robots)
+
+
+def pixel_polygon(x, y, a_rad, sx, sy, ppm):
+    """The 4 pixel-space vertices Model::LocalToPixels yields for a model at global pose (x, y, a)
+    whose body is the default unit-square block scaled to (sx, sy).
+
+    model.cc:378-392 AddBlockRect(-0.5,-0.5,1,1): vertices (-.5,-.5) (.5,-.5) (.5,.5) (-.5,.5);
+    blockgroup.cc:84-112 CalcSize: (pt - offset) * (modsize / size) with size 1, offset 0;
+    model.cc:474-491: gpose = GetGlobalPose() + geom.pose; pt -> gpose + Pose(pt) (stage.hh:297-304:
+    x + px*cos(a) - py*sin(a), y + px*sin(a) + py*cos(a)); pixel = floor(coordinate * ppm)."""
+    cosa, sina = math.cos(a_rad), math.sin(a_rad)
+    # gpose + geom.pose with geom.pose == 0: x + 0*cosa - 0*sina
+    gx = x + 0.0 * cosa - 0.0 * sina
+    gy = y + 0.0 * sina + 0.0 * cosa
+    out = np.zeros((4, 2), np.int32)
+    for i, (ux, uy) in enumerate(((-0.5, -0.5), (0.5, -0.5), (0.5, 0.5), (-0.5, 0.5))):
+        lx = (ux - 0.0) * (sx / 1.0)
+        ly = (uy - 0.0) * (sy / 1.0)
+        px = gx + lx * cosa - ly * sina
+        py = gy + lx * sina + ly * cosa
+        out[i, 0] = int(math.floor(px * ppm))
+        out[i, 1] = int(math.floor(py * ppm))
+    return out
+
+
+def heading_rad(deg):
+    """world-file degrees -> radians as Worldfile::ReadTuple does (worldfile.cc:63,1616)"""
+    return deg * (math.pi / 180.0)
+
+
+def obstacle_polygons(w):
+    return [pixel_polygon(o[0], o[1], 0.0, o[2], o[3], w.ppm) for o in w.obstacles]
+
+
+def robot_polygons(w, robots=None):
+    robots = w.robots if robots is None else robots
+    return [pixel_polygon(r[0], r[1], heading_rad(r[2]), w.robot_size[0], w.robot_size[1], w.ppm) for r in robots]
+
+
+def load_into_context(ctx, w, robot_slice=None):
+    """Publish every model and map every body on BOTH layers, as World::LoadWorldPostHook does
+    (world.cc:459-465). Block ids: obstacle i -> i, robot j -> n_obstacles + j."""
+    ctx.model_upsert(0, 0, 1.0)  # the ground model
+    for mid in w.obstacle_ids:
+        ctx.model_upsert(int(mid), int(mid), 0.5)
+    for mid in w.robot_ids:
+        ctx.model_upsert(int(mid), int(mid), 0.5)
+    polys = obstacle_polygons(w) + robot_polygons(w)
+    models = np.concatenate([w.obstacle_ids, w.robot_ids])
+    zmax = np.concatenate([np.full(len(w.obstacles), w.obstacle_height), np.full(len(w.robots), w.robot_size[2])])
+    first = np.arange(len(polys) + 1, dtype=np.uint32) * 4
+    xy = np.concatenate(polys, 0)
+    z = np.stack([np.zeros(len(polys)), zmax], 1)
+    blocks = np.arange(len(polys), dtype=np.uint32)
+    for layer in (0, 1):
+        ctx.blocks_remap(blocks, models, layer, z, first, xy)
+    ctx.sync()
+    return len(polys)
+
+
+def ranger_fans(w, layer, fov_deg=270.0, samples=1080, range_max=30.0, z=0.5, robots=None, robot_ids=None):
+    """One laser fan per robot, mounted at the robot centre: the fan record a patched
+    ModelRanger::Sensor::Update would submit (origin = pose of the first ray, model_ranger.cc:222-230)."""
+    robots = w.robots if robots is None else robots
+    robot_ids = w.robot_ids if robot_ids is None else robot_ids
+    fov = fov_deg * (math.pi / 180.0)
+    fans = rt.make_fans(len(robots))
+    fans["finder"] = robot_ids
+    fans["n_samples"] = samples
+    fans["pred"] = rt.PRED_RANGER
+    fans["ztest"] = 1
+    fans["layer"] = layer
+    fans["angles"] = rt.ANGLES_RANGER
+    fans["ox"] = robots[:, 0]
+    fans["oy"] = robots[:, 1]
+    fans["oz"] = z
+    start = -fov / 2.0 if samples > 1 else 0.0
+    a = np.array([heading_rad(d) for d in robots[:, 2]]) + start
+    # Pose::operator+ normalises the heading into [-pi, pi] (stage.hh:163-170, :303)
+    for i in range(len(a)):
+        while a[i] < -math.pi:
+            a[i] += 2.0 * math.pi
+        while a[i] > math.pi:
+            a[i] -= 2.0 * math.pi
+    fans["oa"] = a
+    fans["range"] = range_max
+    fans["fov"] = fov
+    return fans
+
+
+def to_worldfile_text(w):
+    """The same world as Stage world-file text (resolution = 1/ppm)."""
+    lines = ["resolution %.17g" % (1.0 / w.ppm), "interval_sim 100", "threads 1", "quit_time 3600", ""]
+    for i, o in enumerate(w.obstacles):
+        lines.append('model ( name "o%d" pose [ %.3f %.3f 0 0 ] size [ %.3f %.3f %.3f ] ranger_return 0.5 )'
+                     % (i, o[0], o[1], o[2], o[3], w.obstacle_height))
+    for i, r in enumerate(w.robots):
+        lines.append('model ( name "r%d" pose [ %.3f %.3f 0 %.3f ] size [ %.3f %.3f %.3f ] ranger_return 0.5 )'
+                     % (i, r[0], r[1], r[2], w.robot_size[0], w.robot_size[1], w.robot_size[2]))
+    return "\n".join(lines) + "\n"
+
+
+def step_robots(w, robots, tick, speed_m=0.05):
+    """A deterministic per-tick motion: every robot creeps forward along its heading by speed_m and
+    turns by 1 degree; robots that would leave the free area are turned round instead."""
+    out = robots.copy()
+    a = out[:, 2] * (math.pi / 180.0)
+    nx = np.round((out[:, 0] + speed_m * np.cos(a)) * 1000) / 1000.0
+    ny = np.round((out[:, 1] + speed_m * np.sin(a)) * 1000) / 1000.0
+    H = w.half_extent_m - 1.5
+    ok = (np.abs(nx) < H) & (np.abs(ny) < H)
+    out[ok, 0], out[ok, 1] = nx[ok], ny[ok]
+    out[:, 2] = np.where(ok, out[:, 2] + 1.0, out[:, 2] + 180.0)
+    out[:, 2] = np.round(((out[:, 2] + 180.0) % 360.0 - 180.0) * 1000) / 1000.0
+    return out

@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_struct_layouts_match_the_header():
     assert rt.FAN_DTYPE.itemsize == 64
-    assert ctypes.sizeof(rt.Config) == 48
+    assert ctypes.sizeof(rt.Config) == 56
     assert ctypes.sizeof(rt.FanOut) == 6 * 8
     assert ctypes.sizeof(rt.Stats) == 11 * 8
     assert rt.lib().stg_rt_abi_version() == 1
@@ -50,7 +50,7 @@ def test_no_cpu_fallback_create_fails_loudly_without_a_gpu():
 
 def test_bad_config_is_rejected():
     L = rt.lib()
-    cfg = rt.Config(12, 0, 50.0, 0, 0, 1, 1, 16, 16, 0, 0)  # wrong struct_size
+    cfg = rt.Config(12, 0, 50.0, 0, 0, 1, 1, 16, 16, 0, 0, 0, 0)  # wrong struct_size
     h = ctypes.c_void_p()
     assert L.stg_rt_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
     assert b"struct_size" in L.stg_rt_last_error(None)
