@@ -234,7 +234,10 @@ def run_ours(args):
     n_bodies = len(world.obstacles) + len(world.robots)
     ctx = rt.Context(world.ppm, x0, y0, nx, ny, max_models=world.n_models + 1, max_blocks=n_bodies,
                      max_cell_entries=1 << 22, device=local_rank, max_delta_bytes=(1 << 20) if n_gpus > 1 else 0)
-    stream = torch.cuda.current_stream()
+    # all of the context's work goes on a torch-owned stream so torch.cuda.Event can bracket it
+    # (the default stream's handle is NULL, which stg_rt_set_stream reads as "use your own")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     worldgen.load_into_context(ctx, world)
 
@@ -280,7 +283,7 @@ def run_ours(args):
     march_ms, head_ms = [], []
     barrier()
     for s, e in ev:
-        flush_buf.fill_(1)       # evict the grid and the fans from L2
+        flush_buf.fill_(1)       # evict the grid and the fans from L2 (same stream, before the start event)
         s.record(stream)
         fset.trace()
         e.record(stream)
