@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libstg_rt.so")
-SOURCES = ["rt_kernels.cu", "rt_api.cu"]
+SOURCES = ["rt_kernels.cu", "rt_march.cu", "rt_api.cu"]
 HEADERS = ["rt_device.h", os.path.join("..", "..", "include", "stg_rt.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -646,8 +646,8 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
   CUC(cudaMalloc(&g.reg_count, c->n_regions * 4));
   CUC(cudaMemsetAsync(g.reg_count, 0, c->n_regions * 4, c->stream));
   for (int L = 0; L < 2; L++) {
-    CUC(cudaMalloc(&g.occ[L], c->n_regions * 128));
-    CUC(cudaMemsetAsync(g.occ[L], 0, c->n_regions * 128, c->stream));
+    CUC(cudaMalloc(&g.occ[L], c->n_regions * kTileWords * 4));
+    CUC(cudaMemsetAsync(g.occ[L], 0, c->n_regions * kTileWords * 4, c->stream));
     CUC(cudaMalloc(&g.slots[L], (size_t)c->slot_cap * 8));
     CUC(cudaMemsetAsync(g.slots[L], 0, (size_t)c->slot_cap * 8, c->stream));
     CUC(cudaMalloc(&g.blk_seq[L], (size_t)cfg->max_blocks * 8));

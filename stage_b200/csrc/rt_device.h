@@ -7,6 +7,7 @@ namespace stg {
 
 constexpr int kRBits = 5;                    // region.hh:13 RBITS: a Region is 32 x 32 cells
 constexpr int kRegionWidth = 1 << kRBits;    // region.hh:17
+constexpr int kTileWords = 2 * kRegionWidth; // row masks then column masks
 constexpr int kSRBits = 10;                  // region.hh:15 SRBITS: a SuperRegion is 1024 x 1024 cells
 
 constexpr unsigned long long kSlotEmpty = 0ull;
@@ -17,9 +18,12 @@ constexpr unsigned long long kSlotTomb = ~0ull;
 //  reg_count[r]        Region::count (region.cc:19-34): number of (cell, block) entries of BOTH
 //                      layers in region r. r = (gry - ry0) * nrx + (grx - rx0), row-major over the
 //                      dense extent. 4 B / region.
-//  occ[L][r*32 + cy]   occupancy tile of region r, layer L: bit cx of word cy is set iff the cell's
-//                      block list Cell::blocks[L] (region.hh:47) is non-empty. One region = one
-//                      128-byte line = eight 128-bit words; this is what the ray march reads.
+//  occ[L][r*64 + ..]   occupancy tile of region r, layer L, 256 bytes = two 128-byte lines:
+//                      words 0..31  row masks:    bit cx of word cy      is set iff the cell's block
+//                      words 32..63 column masks: bit cy of word 32 + cx   list Cell::blocks[L]
+//                      (region.hh:47) is non-empty. This is what the ray march reads: an x-major
+//                      ray tests a whole run of cells of one row with one AND, a y-major ray does
+//                      the same on a column.
 //  slots[L][h]         open-addressing multimap (cell -> block) holding the CONTENT of the occupied
 //                      cells: entry = (cell_key << 32) | (block_id + 1), cell_key = r*1024 + cy*32
 //                      + cx. 0 = empty, ~0 = tombstone. Only consulted where an occ bit is set.

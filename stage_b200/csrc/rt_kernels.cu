@@ -158,7 +158,9 @@ __global__ void __launch_bounds__(256) k1_remove(GridView g, const unsigned char
         h = (h + 1) & g.slot_mask;
       }
       atomicSub(g.reg_count + c.region, 1u);
-      atomicAnd(g.occ[e.layer & 1] + c.region * kRegionWidth + c.cy, ~(1u << c.cx));
+      uint32_t *tile = g.occ[e.layer & 1] + (size_t)c.region * kTileWords;
+      atomicAnd(tile + c.cy, ~(1u << c.cx));
+      atomicAnd(tile + kRegionWidth + c.cx, ~(1u << c.cy));
     }
   }
 }
@@ -180,7 +182,9 @@ __global__ void __launch_bounds__(256) k1_fixup(GridView g, const unsigned char 
         if (cur == kSlotEmpty)
           break;
         if ((uint32_t)(cur >> 32) == c.key) { // tombstones carry key 0xffffffff, never a cell key
-          atomicOr(g.occ[e.layer & 1] + c.region * kRegionWidth + c.cy, 1u << c.cx);
+          uint32_t *tile = g.occ[e.layer & 1] + (size_t)c.region * kTileWords;
+          atomicOr(tile + c.cy, 1u << c.cx);
+          atomicOr(tile + kRegionWidth + c.cx, 1u << c.cy);
           break;
         }
         h = (h + 1) & g.slot_mask;
@@ -213,7 +217,9 @@ __global__ void __launch_bounds__(256) k1_insert(GridView g, const unsigned char
         probes++;
       }
       atomicAdd(g.reg_count + c.region, 1u);
-      atomicOr(g.occ[e.layer & 1] + c.region * kRegionWidth + c.cy, 1u << c.cx);
+      uint32_t *tile = g.occ[e.layer & 1] + (size_t)c.region * kTileWords;
+      atomicOr(tile + c.cy, 1u << c.cx);
+      atomicOr(tile + kRegionWidth + c.cx, 1u << c.cy);
     }
   }
 }
@@ -318,227 +324,6 @@ void launch_fan_headings(const FanBatchView &b, void *stream)
   k2_fan_headings<<<(b.n_fans + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b);
 }
 
-// ------------------------------------------------------------------------------------------
-// K2: the ray march. One thread (lane) per beam; consecutive lanes are consecutive beams of a fan,
-// so a warp reads a handful of neighbouring 128-byte occupancy tiles and its lanes stop at about
-// the same wall. State machine and arithmetic follow World::Raytrace (world.cc:756-963) exactly:
-// truncating double->int conversions, the stale error term across empty-region jumps, int -=
-// double for the remaining distance.
-// ------------------------------------------------------------------------------------------
-
-struct HitTest {
-  uint32_t finder, finder_root;
-  uint32_t pred, ztest;
-  double oz;
-};
-
-// Resolve an occupied cell: among the blocks rendered into it that pass the z test and the
-// predicate, the one first in Cell::blocks[layer] order wins (world.cc:841-862).
-__device__ __forceinline__ int32_t resolve_cell(const GridView &g, const HitTest &ht, int layer, uint32_t key)
-{
-  const unsigned long long *slots = g.slots[layer];
-  const unsigned long long *seq = g.blk_seq[layer];
-  unsigned long long best_seq = ~0ull;
-  int32_t best_model = -1;
-  uint32_t h = mix32(key) & g.slot_mask;
-  for (uint32_t probes = 0; probes <= g.slot_mask; probes++) {
-    const unsigned long long cur = __ldg(slots + h);
-    if (cur == kSlotEmpty)
-      break;
-    if ((uint32_t)(cur >> 32) == key) {
-      const uint32_t blk = (uint32_t)cur - 1u;
-      const bool z_ok = !ht.ztest || !(ht.oz < __ldg(g.blk_zmin + blk) || ht.oz > __ldg(g.blk_zmax + blk));
-      if (z_ok) {
-        const uint32_t m = __ldg(g.blk_model + blk);
-        bool pass;
-        if (ht.pred == 0u) // ranger_match
-          pass = __ldg(g.mdl_root + m) != ht.finder_root && !(__ldg(g.mdl_ranger_return + m) < 0.0);
-        else if (ht.pred == 2u) // gripper_raytrace_match
-          pass = m != ht.finder && (__ldg(g.mdl_flags + m) & 1u);
-        else // fiducial / blob / bumper: unrelated
-          pass = __ldg(g.mdl_root + m) != ht.finder_root;
-        if (pass) {
-          const unsigned long long s = __ldg(seq + blk);
-          if (s < best_seq) {
-            best_seq = s;
-            best_model = (int32_t)m;
-          }
-        }
-      }
-    }
-    h = (h + 1) & g.slot_mask;
-  }
-  return best_model;
-}
-
-__global__ void __launch_bounds__(128) k2_ray_march(GridView g, FanBatchView b)
-{
-  const uint64_t beam = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (beam >= b.n_beams)
-    return;
-
-  // which fan does this beam belong to
-  uint32_t lo = 0, hi = b.n_fans;
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(b.fan_first_beam + mid) <= beam)
-      lo = mid;
-    else
-      hi = mid;
-  }
-  const FanRec fan = b.fans[lo];
-
-  HitTest ht;
-  ht.finder = fan.finder;
-  ht.finder_root = __ldg(g.mdl_root + fan.finder);
-  ht.pred = fan.pred;
-  ht.ztest = fan.ztest;
-  ht.oz = fan.oz;
-  const int layer = fan.layer & 1;
-  const double ppm = g.ppm;
-
-  double gx = fan.ox * ppm, gy = fan.oy * ppm;
-  const double x_start = gx, y_start = gy;
-  const double heading = b.heading[beam];
-  const double ang = heading == 0.0 ? 1e-12 : heading;
-  double sina, cosa;
-  if (b.trig_in) {
-    cosa = b.trig_in[2 * beam];
-    sina = b.trig_in[2 * beam + 1];
-  } else {
-    sina = sin(ang);
-    cosa = cos(ang);
-  }
-  const double tana = sina / cosa;
-  const double dx = ppm * fan.range * cosa, dy = ppm * fan.range * sina;
-  const int32_t sx = dx < 0 ? -1 : 1, sy = dy < 0 ? -1 : 1;
-  const int32_t ax = __double2int_rz(fabs(dx)), ay = __double2int_rz(fabs(dy));
-  const int32_t bx = 2 * ax, by = 2 * ay;
-  int32_t exy = ay - ax;
-  int32_t n = ax + ay;
-
-  const double xjumpx = sx * kRegionWidth, xjumpy = sx * kRegionWidth * tana;
-  const double yjumpx = sy * kRegionWidth / tana, yjumpy = sy * kRegionWidth;
-  const double xjumpdist = fabs(xjumpx) + fabs(xjumpy);
-  const double yjumpdist = fabs(yjumpx) + fabs(yjumpy);
-
-  double xcrossx = 0, xcrossy = 0, ycrossx = 0, ycrossy = 0, distX = 0, distY = 0;
-  bool need_crossings = true;
-
-  double range = fan.range;
-  int32_t hit_model = -1, hit_x = 0, hit_y = 0;
-  uint32_t cell_visits = 0, region_probes = 0;
-  const uint32_t *occ = g.occ[layer];
-
-  while (n > 0) {
-    region_probes++;
-    const int32_t ix0 = __double2int_rz(gx), iy0 = __double2int_rz(gy);
-    const int32_t grx = ix0 >> kRBits, gry = iy0 >> kRBits;
-    const int32_t rix = grx - g.rx0, riy = gry - g.ry0;
-    uint32_t region = 0, count = 0;
-    if ((uint32_t)rix < (uint32_t)g.nrx && (uint32_t)riy < (uint32_t)g.nry) {
-      region = (uint32_t)(riy * g.nrx + rix);
-      count = __ldg(g.reg_count + region);
-    }
-    if (count) {
-      need_crossings = true;
-      int32_t cx = ix0 & (kRegionWidth - 1), cy = iy0 & (kRegionWidth - 1);
-      const uint32_t *tile = occ + region * kRegionWidth;
-      uint32_t row = __ldg(tile + cy);
-      while ((uint32_t)cx < (uint32_t)kRegionWidth && (uint32_t)cy < (uint32_t)kRegionWidth && n > 0) {
-        cell_visits++;
-        if ((row >> cx) & 1u) {
-          const uint32_t key = (region << (2 * kRBits)) | ((uint32_t)cy << kRBits) | (uint32_t)cx;
-          const int32_t m = resolve_cell(g, ht, layer, key);
-          if (m >= 0) {
-            hit_model = m;
-            hit_x = grx * kRegionWidth + cx;
-            hit_y = gry * kRegionWidth + cy;
-            if (ax > ay)
-              range = fabs((gx - x_start) / cosa) / ppm;
-            else
-              range = fabs((gy - y_start) / sina) / ppm;
-            n = 0; // leave both loops
-            break;
-          }
-        }
-        if (exy < 0) {
-          gx += sx;
-          exy += by;
-          cx += sx;
-        } else {
-          gy += sy;
-          exy -= bx;
-          cy += sy;
-          if ((uint32_t)cy < (uint32_t)kRegionWidth)
-            row = __ldg(tile + cy);
-        }
-        --n;
-      }
-    } else {
-      if (need_crossings) {
-        need_crossings = false;
-        const int32_t ix = ix0, iy = iy0;
-        double regionx = (double)(ix / kRegionWidth * kRegionWidth);
-        double regiony = (double)(iy / kRegionWidth * kRegionWidth);
-        if ((gx < 0) && (ix % kRegionWidth))
-          regionx -= kRegionWidth;
-        if ((gy < 0) && (iy % kRegionWidth))
-          regiony -= kRegionWidth;
-        const double xdx = sx < 0 ? regionx - gx - 1.0 : regionx + kRegionWidth - gx;
-        const double xdy = xdx * tana;
-        const double ydy = sy < 0 ? regiony - gy - 1.0 : regiony + kRegionWidth - gy;
-        const double ydx = ydy / tana;
-        xcrossx = gx + xdx;
-        xcrossy = gy + xdy;
-        ycrossx = gx + ydx;
-        ycrossy = gy + ydy;
-        distX = fabs(xdx) + fabs(xdy);
-        distY = fabs(ydx) + fabs(ydy);
-      }
-      if (distX < distY) {
-        gx = xcrossx;
-        gy = xcrossy;
-        n = __double2int_rz((double)n - distX);
-        xcrossx += xjumpx;
-        xcrossy += xjumpy;
-        distY -= distX;
-        distX = xjumpdist;
-      } else {
-        gx = ycrossx;
-        gy = ycrossy;
-        n = __double2int_rz((double)n - distY);
-        ycrossx += yjumpx;
-        ycrossy += yjumpy;
-        distX -= distY;
-        distY = yjumpdist;
-      }
-    }
-  }
-
-  // K3 (ranger epilogue, fused): model_ranger.cc:243-251 with zero noise
-  if (b.ranges)
-    b.ranges[beam] = range;
-  if (b.intensities)
-    b.intensities[beam] = hit_model >= 0 ? __ldg(g.mdl_ranger_return + hit_model) : 0.0;
-  if (b.hit_model)
-    b.hit_model[beam] = hit_model;
-  if (b.hit_cell) {
-    b.hit_cell[2 * beam] = hit_x;
-    b.hit_cell[2 * beam + 1] = hit_y;
-  }
-  if (b.steps) {
-    b.steps[2 * beam] = cell_visits;
-    b.steps[2 * beam + 1] = region_probes;
-  }
-}
-
-void launch_ray_march(const GridView &g, const FanBatchView &b, void *stream)
-{
-  if (!b.n_beams)
-    return;
-  const uint64_t blocks = (b.n_beams + 127) / 128;
-  k2_ray_march<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(g, b);
-}
+// K2, the ray march, lives in rt_march.cu.
 
 } // namespace stg
