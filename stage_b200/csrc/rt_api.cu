@@ -85,6 +85,8 @@ struct stg_rt_ctx {
   std::vector<uint32_t> dirty_units; // block*2 + layer, in order of first touch
   std::vector<ModelUpd> model_upd;
   std::vector<bool> model_known;
+  std::vector<ModelUpd> models;          // host copy of the model table
+  std::vector<uint32_t> models_changed;  // models whose root / visibility changed while blocks are mapped
   uint64_t epoch = 0;
   uint32_t local_seq = 0;
   int64_t live_entries[2] = { 0, 0 }; // cell visits currently rendered, per layer
@@ -263,6 +265,13 @@ size_t write_blob(unsigned char *dst, const BlobBuild &b, const std::vector<Mode
   return (size_t)(p - dst);
 }
 
+uint32_t root_flags_of(const stg_rt_ctx *c, uint32_t model)
+{
+  const ModelUpd &m = c->models[model];
+  return (m.root & kRecRootMask) | (m.ranger_return < 0 ? kRecNoRanger : 0u) |
+         ((m.flags & STG_RT_VIS_GRIPPER_RETURN) ? kRecGripper : 0u);
+}
+
 // Units sorted so that the blob (and, when it has to be split, successive blobs) insert in Map-call
 // order: pure removals first, then by the sequence number of the final Map.
 void sort_units(stg_rt_ctx *c)
@@ -306,6 +315,24 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
     BlobBuild bb;
     uint32_t rem_cursor = 0, ins_cursor = 0;
     const size_t n_model = first_round ? c->model_upd.size() : 0;
+    if (first_round && !c->models_changed.empty()) {
+      for (uint32_t bi = 0; bi < c->blocks.size(); bi++) {
+        const BlockShadow &b = c->blocks[bi];
+        if (!b.known || std::find(c->models_changed.begin(), c->models_changed.end(), b.model) == c->models_changed.end())
+          continue;
+        BlockUpd up;
+        up.block = bi;
+        up.model = b.model;
+        up.zmin = b.zmin;
+        up.zmax = b.zmax;
+        up.seq_local = 0;
+        up.layer = kUpdKeepSeq;
+        up.root_flags = root_flags_of(c, b.model);
+        up.pad = 0;
+        bb.bupd.push_back(up);
+      }
+      c->models_changed.clear();
+    }
     while (unit < c->dirty_units.size()) {
       const uint32_t u = c->dirty_units[unit];
       BlockShadow &b = c->blocks[u >> 1];
@@ -332,6 +359,8 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
         up.zmax = b.zmax;
         up.seq_local = b.map_seq[L];
         up.layer = (uint32_t)L;
+        up.root_flags = root_flags_of(c, b.model);
+        up.pad = 0;
         bb.bupd.push_back(up);
       }
       b.dev_mapped[L] = b.host_mapped[L];
@@ -601,7 +630,7 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
     return fail(nullptr, STG_RT_EINVAL, "stg_rt_create: bad config (struct_size %u, expected %zu)",
                 cfg ? cfg->struct_size : 0u, sizeof(stg_rt_config));
   if (!(cfg->ppm > 0) || cfg->sreg_nx < 1 || cfg->sreg_ny < 1 || (int64_t)cfg->sreg_nx * cfg->sreg_ny > 4095 ||
-      cfg->max_models < 1 || cfg->max_blocks < 1)
+      cfg->max_models < 1 || cfg->max_models >= (1u << 30) || cfg->max_blocks < 1)
     return fail(nullptr, STG_RT_EINVAL, "stg_rt_create: bad ppm / extent / capacities");
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
@@ -650,14 +679,10 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
     CUC(cudaMemsetAsync(g.occ[L], 0, c->n_regions * kTileWords * 4, c->stream));
     CUC(cudaMalloc(&g.slots[L], (size_t)c->slot_cap * 8));
     CUC(cudaMemsetAsync(g.slots[L], 0, (size_t)c->slot_cap * 8, c->stream));
-    CUC(cudaMalloc(&g.blk_seq[L], (size_t)cfg->max_blocks * 8));
-    CUC(cudaMemsetAsync(g.blk_seq[L], 0, (size_t)cfg->max_blocks * 8, c->stream));
+    CUC(cudaMalloc(&g.blk_rec[L], (size_t)cfg->max_blocks * sizeof(BlockRec)));
+    CUC(cudaMemsetAsync(g.blk_rec[L], 0, (size_t)cfg->max_blocks * sizeof(BlockRec), c->stream));
   }
   CUC(cudaMalloc(&c->spare_slots, (size_t)c->slot_cap * 8));
-  CUC(cudaMalloc(&g.blk_model, (size_t)cfg->max_blocks * 4));
-  CUC(cudaMalloc(&g.blk_zmin, (size_t)cfg->max_blocks * 8));
-  CUC(cudaMalloc(&g.blk_zmax, (size_t)cfg->max_blocks * 8));
-  CUC(cudaMemsetAsync(g.blk_model, 0, (size_t)cfg->max_blocks * 4, c->stream));
   CUC(cudaMalloc(&g.mdl_root, (size_t)cfg->max_models * 4));
   CUC(cudaMalloc(&g.mdl_ranger_return, (size_t)cfg->max_models * 8));
   CUC(cudaMalloc(&g.mdl_flags, (size_t)cfg->max_models * 4));
@@ -673,6 +698,7 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
 #undef CUC
   c->blocks.resize(cfg->max_blocks);
   c->model_known.assign(cfg->max_models, false);
+  c->models.resize(cfg->max_models);
   *out = c;
   return STG_RT_OK;
 }
@@ -684,8 +710,8 @@ int stg_rt_destroy(stg_rt_ctx *c)
   cudaSetDevice(c->cfg.device);
   cudaStreamSynchronize(c->stream);
   GridView &g = c->g;
-  void *dev[] = { g.reg_count, g.occ[0], g.occ[1], g.slots[0], g.slots[1], g.blk_seq[0], g.blk_seq[1], c->spare_slots,
-                  g.blk_model, g.blk_zmin, g.blk_zmax, g.mdl_root, g.mdl_ranger_return, g.mdl_flags, c->d_blob.p };
+  void *dev[] = { g.reg_count, g.occ[0], g.occ[1], g.slots[0], g.slots[1], g.blk_rec[0], g.blk_rec[1], c->spare_slots,
+                  g.mdl_root, g.mdl_ranger_return, g.mdl_flags, c->d_blob.p };
   for (void *p : dev)
     if (p)
       cudaFree(p);
@@ -728,6 +754,10 @@ int stg_rt_model_upsert(stg_rt_ctx *c, uint32_t id, uint32_t root_id, double ran
   u.fiducial_key = fiducial_key;
   u.flags = vis_flags;
   c->model_upd.push_back(u);
+  if (c->model_known[id] && (c->models[id].root != u.root || c->models[id].flags != u.flags ||
+                             (c->models[id].ranger_return < 0) != (u.ranger_return < 0)))
+    c->models_changed.push_back(id);
+  c->models[id] = u;
   c->model_known[id] = true;
   if (sizeof(DeltaHeader) + c->model_upd.size() * sizeof(ModelUpd) > c->blob_cap / 2)
     return apply_deltas_locked(c);
@@ -1077,7 +1107,8 @@ int64_t stg_rt_grid_dump(stg_rt_ctx *c, int32_t *records, int64_t cap, int64_t *
   if ((rc = deliver_locked(c)))
     return rc;
   const GridView &g = c->g;
-  std::vector<unsigned long long> slots(c->slot_cap), seq(c->cfg.max_blocks);
+  std::vector<unsigned long long> slots(c->slot_cap);
+  std::vector<BlockRec> recs_dev(c->cfg.max_blocks);
   std::vector<uint32_t> counts(c->n_regions);
   struct Rec {
     int32_t layer, x, y;
@@ -1087,7 +1118,7 @@ int64_t stg_rt_grid_dump(stg_rt_ctx *c, int32_t *records, int64_t cap, int64_t *
   std::vector<Rec> recs;
   for (int L = 0; L < 2; L++) {
     CU(c, cudaMemcpyAsync(slots.data(), g.slots[L], (size_t)c->slot_cap * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaMemcpyAsync(seq.data(), g.blk_seq[L], (size_t)c->cfg.max_blocks * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(recs_dev.data(), g.blk_rec[L], (size_t)c->cfg.max_blocks * sizeof(BlockRec), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     for (size_t i = 0; i < slots.size(); i++) {
       const unsigned long long e = slots[i];
@@ -1099,7 +1130,7 @@ int64_t stg_rt_grid_dump(stg_rt_ctx *c, int32_t *records, int64_t cap, int64_t *
       r.layer = L;
       r.x = (g.rx0 + (int32_t)(region % (uint32_t)g.nrx)) * 32 + (int32_t)cx;
       r.y = (g.ry0 + (int32_t)(region / (uint32_t)g.nrx)) * 32 + (int32_t)cy;
-      r.seq = blk < seq.size() ? seq[blk] : 0;
+      r.seq = blk < recs_dev.size() ? recs_dev[blk].seq : 0;
       r.block = (int32_t)blk;
       recs.push_back(r);
     }

@@ -31,6 +31,20 @@ constexpr unsigned long long kSlotTomb = ~0ull;
 //                      Model::vis stage.hh:1924-1937, tree root for Model::IsRelated).
 //  blk_seq[L][b]       order key of block b's latest Map on layer L: entries of one cell sorted by
 //                      it reproduce the insertion order of Cell::blocks[L].
+// Everything the hit test needs about one block on one layer, in ONE 32-byte sector, so resolving an
+// occupied cell costs two dependent loads (slot, then this) instead of a chain through block and
+// model tables. zmin/zmax/model/root_flags are per block (kept equal on both layers); seq is per layer.
+struct BlockRec {
+  double zmin, zmax;       // Block::global_z (block.cc:177-180)
+  unsigned long long seq;  // order key of the latest Map on this layer
+  uint32_t model;          // owning model id
+  uint32_t root_flags;     // root id of the model's tree | kRecNoRanger | kRecGripper
+};
+static_assert(sizeof(BlockRec) == 32, "BlockRec");
+constexpr uint32_t kRecNoRanger = 1u << 30; // vis.ranger_return < 0: invisible to rangers
+constexpr uint32_t kRecGripper = 1u << 31;  // vis.gripper_return
+constexpr uint32_t kRecRootMask = (1u << 30) - 1u;
+
 struct GridView {
   int32_t rx0, ry0, nrx, nry;
   double ppm;
@@ -39,9 +53,7 @@ struct GridView {
   unsigned long long *slots[2];
   uint32_t slot_mask;
   uint32_t n_blocks, n_models;
-  uint32_t *blk_model;
-  double *blk_zmin, *blk_zmax;
-  unsigned long long *blk_seq[2];
+  BlockRec *blk_rec[2];
   uint32_t *mdl_root;
   double *mdl_ranger_return;
   uint32_t *mdl_flags;
@@ -70,10 +82,13 @@ static_assert(sizeof(EdgeRec) == 32, "EdgeRec");
 struct BlockUpd {
   uint32_t block, model;
   double zmin, zmax;
-  uint32_t seq_local; // order of the Map call within this rank's blob
-  uint32_t layer;
+  uint32_t seq_local;  // order of the Map call within this rank's blob
+  uint32_t layer;      // 0/1, | kUpdKeepSeq when only the attributes changed (no new Map)
+  uint32_t root_flags; // BlockRec::root_flags
+  uint32_t pad;
 };
-static_assert(sizeof(BlockUpd) == 32, "BlockUpd");
+static_assert(sizeof(BlockUpd) == 40, "BlockUpd");
+constexpr uint32_t kUpdKeepSeq = 0x100u;
 
 struct ModelUpd {
   uint32_t id, root;
