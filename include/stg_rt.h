@@ -175,6 +175,77 @@ int stg_rt_blocks_remap(stg_rt_ctx *ctx, uint32_t n, const uint32_t *blocks, con
 int stg_rt_fans_submit(stg_rt_ctx *ctx, uint32_t n_fans, const stg_rt_fan *fans,
                        const double *headings, const double *trig, const stg_rt_fan_out *out);
 
+/* ---- fiducial finders ------------------------------------------------------------------------ */
+
+/* A model with fiducial_return != 0 (World::models_with_fiducials, stage.hh:798): what
+   ModelFiducial::AddModelIfVisible reads of "him" (model_fiducial.cc:109-224). 72 bytes. */
+typedef struct {
+  uint32_t model;           /* model id */
+  int32_t fiducial_return;  /* him->vis.fiducial_return */
+  int32_t fiducial_key;     /* him->vis.fiducial_key */
+  uint32_t reserved;
+  double x, y, z, a;        /* him->GetGlobalPose() */
+  double sx, sy, sz;        /* him->GetGeom().size */
+} stg_rt_fid_target;
+
+/* One ModelFiducial::Update (model_fiducial.cc:229-293). 104 bytes. */
+typedef struct {
+  uint32_t finder;          /* model id of the fiducial sensor */
+  int32_t fiducial_key;     /* this->vis.fiducial_key (:117) */
+  uint8_t ignore_zloc;      /* ModelFiducial::ignore_zloc (:184) */
+  uint8_t layer;            /* layer the line-of-sight rays read: (World::updates + 1) % 2 */
+  uint8_t pad[6];
+  double x, y, z, a;        /* GetGlobalPose() (mypose, :124) */
+  double ox, oy, oz, oa;    /* GetGlobalPose() + geom.pose: the frame Model::LocalToGlobal composes
+                               the ray pose on (stage.hh:2296; used by Model::Raytrace, :2003) */
+  double max_range_anon, max_range_id, fov;
+} stg_rt_fid_finder;
+
+/* ModelFiducial::Fiducial (stage.hh:2555-2566). 88 bytes. */
+typedef struct {
+  uint32_t target;          /* index into the submitted targets[] (-> Fiducial::mod) */
+  int32_t id;               /* Fiducial::id: fiducial_return, or 0 beyond max_range_id */
+  double range, bearing;
+  double geom[4];           /* size x, y, z and heading relative to the finder */
+  double pose[4];           /* target's global pose */
+} stg_rt_fiducial;
+
+/* Replaces the body of ModelFiducial::Update for n_finders sensors at once: the candidate query
+   (x/y window over the fiducial-bearing models), AddModelIfVisible's culls (key, range, field of
+   view, relatedness), one line-of-sight ray per surviving candidate and the accept step. targets[]
+   must be in the order the reference visits candidates (ascending Model*, :266-283); each finder's
+   fiducials come back in that order: out[f * max_per_finder + k], k < min(out_count[f],
+   max_per_finder). out / out_count are delivered by stg_rt_sync like fan results. */
+int stg_rt_fiducials_submit(stg_rt_ctx *ctx, uint32_t n_targets, const stg_rt_fid_target *targets,
+                            uint32_t n_finders, const stg_rt_fid_finder *finders,
+                            uint32_t max_per_finder, stg_rt_fiducial *out, uint32_t *out_count);
+
+/* ---- blobfinders ----------------------------------------------------------------------------- */
+
+/* One ModelBlobfinder::Update (model_blobfinder.cc:165-250). 72 bytes. */
+typedef struct {
+  uint32_t finder;          /* model id of the blobfinder */
+  uint32_t scan_width, scan_height;
+  uint8_t layer, pad[3];
+  uint32_t first_color, n_colors; /* this sensor's tracked colours in colors_rgb[]; 0 = all */
+  double ox, oy, oz, oa;    /* LocalToGlobal(Pose(0,0,0,pan)): global pose of the scan centre */
+  double range, fov;
+} stg_rt_blob_finder;
+
+/* ModelBlobfinder::Blob (stage.hh:2333-2338). 32 bytes. Blob::color = colour of `model`. */
+typedef struct {
+  uint32_t model;           /* the model seen by the blob's first sample */
+  uint32_t left, top, right, bottom, pad;
+  double range;
+} stg_rt_blob;
+
+/* Replaces ModelBlobfinder::Update for n_finders sensors: the scan_width-ray fan (no z test, stop
+   at any unrelated model) and the run-length colour segmentation. Model colours are the rgba given
+   to stg_rt_model_upsert. colors_rgb = 3 doubles per tracked colour. Results as for fiducials. */
+int stg_rt_blobs_submit(stg_rt_ctx *ctx, uint32_t n_finders, const stg_rt_blob_finder *finders,
+                        uint32_t n_colors, const double *colors_rgb, uint32_t max_per_finder,
+                        stg_rt_blob *out, uint32_t *out_count);
+
 /* Start everything queued (deltas, then fans) on the GPU without waiting. Implicitly done by
    stg_rt_sync, and by a map/unmap issued while fans are still queued (ordering rule above). */
 int stg_rt_flush(stg_rt_ctx *ctx);

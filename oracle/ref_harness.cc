@@ -50,6 +50,7 @@ struct Recorder {
 } rec;
 
 thread_local int tl_quiet = 0; // >0: calls made by the harness itself are not recorded
+bool g_fiducials_on_main = false;
 
 void *ref_handle()
 {
@@ -238,6 +239,97 @@ void ModelRanger::Sensor::Update(ModelRanger *mod)
   rec.aux.insert(rec.aux.end(), ranges.begin(), ranges.end());
   rec.aux.insert(rec.aux.end(), intensities.begin(), intensities.end());
   rec.aux.insert(rec.aux.end(), bearings.begin(), bearings.end());
+  rec.events.push_back(e);
+}
+
+unsigned int World::GetEventQueue(Model *mod) const
+{
+  typedef unsigned int (*fn_t)(const World *, Model *);
+  static fn_t fn = real<fn_t>("_ZNK3Stg5World13GetEventQueueEPNS_5ModelE");
+  if (g_fiducials_on_main && dynamic_cast<ModelFiducial *>(mod))
+    return 0;
+  return fn(this, mod);
+}
+
+void ModelFiducial::Update(void)
+{
+  typedef void (*fn_t)(ModelFiducial *);
+  static fn_t fn = real<fn_t>("_ZN3Stg13ModelFiducial6UpdateEv");
+  if (!rec.active || tl_quiet || subs < 1) {
+    fn(this);
+    return;
+  }
+  // inputs, as a patched libstage would gather them for stg_rt_fiducials_submit
+  const Pose my = GetGlobalPose();
+  const Pose org = GetGlobalPose() + geom.pose; // the frame Model::LocalToGlobal composes on
+  const unsigned int layer = (world->updates + 1) % 2;
+  std::vector<Model *> targets(world->models_with_fiducials.begin(), world->models_with_fiducials.end());
+  std::sort(targets.begin(), targets.end()); // candidates are visited in ascending Model* order
+  std::vector<double> a;
+  const double hdr[TRACE_FID_HEADER_DOUBLES] = { my.x, my.y, my.z, my.a, org.x, org.y, org.z, org.a, max_range_anon,
+                                                 max_range_id, fov, (double)vis.fiducial_key,
+                                                 ignore_zloc ? 1.0 : 0.0, (double)targets.size() };
+  a.insert(a.end(), hdr, hdr + TRACE_FID_HEADER_DOUBLES);
+  for (size_t i = 0; i < targets.size(); i++) {
+    const Model *m = targets[i];
+    const Pose p = m->GetGlobalPose();
+    const Size sz = m->GetGeom().size;
+    const double t[TRACE_FID_TARGET_DOUBLES] = { (double)m->id, (double)m->vis.fiducial_return, (double)m->vis.fiducial_key,
+                                                 p.x, p.y, p.z, p.a, sz.x, sz.y, sz.z };
+    a.insert(a.end(), t, t + TRACE_FID_TARGET_DOUBLES);
+  }
+  fn(this);
+  for (size_t i = 0; i < fiducials.size(); i++) {
+    const Fiducial &f = fiducials[i];
+    const double r[TRACE_FID_RESULT_DOUBLES] = { (double)f.mod->id, (double)f.id, f.range, f.bearing, f.geom.x, f.geom.y,
+                                                 f.geom.z, f.geom.a, f.pose.x, f.pose.y, f.pose.z, f.pose.a };
+    a.insert(a.end(), r, r + TRACE_FID_RESULT_DOUBLES);
+  }
+  std::lock_guard<std::mutex> g(rec.mu);
+  TraceEvent e;
+  memset(&e, 0, sizeof(e));
+  e.type = TRACE_EV_FIDUCIAL;
+  e.layer = (uint8_t)layer;
+  e.model = id;
+  e.block = (uint32_t)fiducials.size();
+  e.first = (uint32_t)rec.aux.size();
+  rec.aux.insert(rec.aux.end(), a.begin(), a.end());
+  rec.events.push_back(e);
+}
+
+void ModelBlobfinder::Update(void)
+{
+  typedef void (*fn_t)(ModelBlobfinder *);
+  static fn_t fn = real<fn_t>("_ZN3Stg15ModelBlobfinder6UpdateEv");
+  if (!rec.active || tl_quiet) {
+    fn(this);
+    return;
+  }
+  const Pose org = LocalToGlobal(Pose(0, 0, 0, pan)); // what Model::Raytrace hands to World::Raytrace (stage.hh:2012)
+  const unsigned int layer = (world->updates + 1) % 2;
+  fn(this);
+  std::lock_guard<std::mutex> g(rec.mu);
+  TraceEvent e;
+  memset(&e, 0, sizeof(e));
+  e.type = TRACE_EV_BLOB;
+  e.layer = (uint8_t)layer;
+  e.model = id;
+  e.block = (uint32_t)blobs.size();
+  e.first = (uint32_t)rec.aux.size();
+  const double hdr[TRACE_BLOB_HEADER_DOUBLES] = { org.x, org.y, org.z, org.a, range, fov, (double)scan_width,
+                                                  (double)scan_height, (double)colors.size() };
+  rec.aux.insert(rec.aux.end(), hdr, hdr + TRACE_BLOB_HEADER_DOUBLES);
+  for (size_t i = 0; i < colors.size(); i++) {
+    rec.aux.push_back(colors[i].r);
+    rec.aux.push_back(colors[i].g);
+    rec.aux.push_back(colors[i].b);
+  }
+  for (size_t i = 0; i < blobs.size(); i++) {
+    const Blob &b = blobs[i];
+    const double r[TRACE_BLOB_RESULT_DOUBLES] = { b.color.r, b.color.g, b.color.b, (double)b.left, (double)b.top,
+                                                  (double)b.right, (double)b.bottom, b.range };
+    rec.aux.insert(rec.aux.end(), r, r + TRACE_BLOB_RESULT_DOUBLES);
+  }
   rec.events.push_back(e);
 }
 
@@ -483,6 +575,24 @@ int64_t ref_dump_grid(void *wv, int32_t *out, int64_t cap, int64_t *counts, int6
     *n_counts = nc;
   return n;
 }
+
+// Model::Subscribe (model.cc:521): what a controller or a Player client does to switch a sensor on.
+int ref_model_subscribe(void *wv, const char *name)
+{
+  World *w = (World *)wv;
+  Model *m = w->GetModel(std::string(name));
+  if (!m)
+    return -1;
+  m->Subscribe();
+  return 0;
+}
+
+// Keep every fiducial finder on the main thread's queue from now on (call BEFORE loading a world).
+// On worker threads ModelFiducial::Update reads poses that ModelPosition::Move is changing
+// concurrently (world.cc:647 vs model_fiducial.cc:124-127), so recordings would not be reproducible
+// (SURVEY.md 3.1). Done by answering World::GetEventQueue (world.cc:678-686, asked by
+// Model::Startup, model.cc:577) with queue 0 for them.
+void ref_fiducials_on_main_thread(int on) { g_fiducials_on_main = on != 0; }
 
 // Look a model up by name (World::GetModel, world.cc) -> Model::id, or -1.
 int32_t ref_model_id(void *wv, const char *name)

@@ -41,6 +41,7 @@ const int REGIONWIDTH = 1 << RBITS;  // region.hh:17
 const int REGIONSIZE = REGIONWIDTH * REGIONWIDTH;
 
 struct T1Model {
+  double color[4];
   uint32_t root;
   double ranger_return;
   int32_t fiducial_return, fiducial_key;
@@ -414,6 +415,177 @@ void t1_even_fan(void *wv, uint32_t finder, int layer, int kind, int ztest, cons
   }
 }
 
+// Model::color, read by the blobfinder through RaytraceResult::color (world.cc:853).
+void t1_model_color(void *wv, uint32_t id, const double *rgba)
+{
+  T1World *w = (T1World *)wv;
+  if (id < w->models.size())
+    memcpy(w->models[id].color, rgba, sizeof(double) * 4);
+}
+
+static double normalize_angle(double a) // stage.hh:163-170
+{
+  while (a < -M_PI)
+    a += 2.0 * M_PI;
+  while (a > M_PI)
+    a -= 2.0 * M_PI;
+  return a;
+}
+
+typedef struct {
+  uint32_t model;
+  int32_t fiducial_return, fiducial_key;
+  uint32_t reserved;
+  double x, y, z, a;
+  double sx, sy, sz;
+} T1FidTarget; // 72 B, same layout as stg_rt_fid_target
+
+typedef struct {
+  uint32_t finder;
+  int32_t fiducial_key;
+  uint8_t ignore_zloc, layer, pad[6];
+  double x, y, z, a;
+  double ox, oy, oz, oa;
+  double max_range_anon, max_range_id, fov;
+} T1FidFinder; // 104 B, same layout as stg_rt_fid_finder
+
+typedef struct {
+  uint32_t target;
+  int32_t id;
+  double range, bearing;
+  double geom[4], pose[4];
+} T1Fiducial; // 88 B, same layout as stg_rt_fiducial
+
+// ModelFiducial::Update + AddModelIfVisible (model_fiducial.cc:109-293) for one finder. targets are
+// World::models_with_fiducials in ascending Model* order. Returns the number of fiducials found
+// (records beyond max_out are counted but not stored).
+uint32_t t1_fiducial_update(void *wv, uint32_t n_targets, const T1FidTarget *targets, const T1FidFinder *fd,
+                            uint32_t max_out, T1Fiducial *out)
+{
+  const T1World *w = (const T1World *)wv;
+  uint32_t n = 0;
+  const double rng = fd->max_range_anon;
+  for (uint32_t t = 0; t < n_targets; t++) {
+    const T1FidTarget &him = targets[t];
+    // the sorted-set window query (:245-283): within +-rng on both axes, bounds inclusive
+    if (him.x < fd->x - rng || him.x > fd->x + rng || him.y < fd->y - rng || him.y > fd->y + rng)
+      continue;
+    if (fd->fiducial_key != him.fiducial_key) // :117
+      continue;
+    const double dx = him.x - fd->x, dy = him.y - fd->y;
+    const double range = hypot(dy, dx);
+    if (range >= fd->max_range_anon) // :134
+      continue;
+    const double bearing = atan2(dy, dx);
+    const double dtheta = normalize_angle(bearing - fd->a);
+    if (fabs(dtheta) > fd->fov / 2.0) // :147
+      continue;
+    if (w->models[him.model].root == w->models[fd->finder].root) // IsRelated, :152
+      continue;
+    T1RayIn r;
+    memset(&r, 0, sizeof(r));
+    r.ox = fd->ox; // LocalToGlobal(Pose(0,0,0,dtheta)), stage.hh:2296
+    r.oy = fd->oy;
+    r.oz = fd->oz;
+    r.oa = normalize_angle(fd->oa + dtheta);
+    r.range = fd->max_range_anon;
+    r.finder = fd->finder;
+    r.kind = TRACE_KIND_UNRELATED;
+    r.ztest = 1;
+    r.layer = fd->layer;
+    T1Hit h;
+    trace_one(w, r, NULL, &h);
+    int32_t seen = h.hit_model;
+    if (fd->ignore_zloc && seen < 0) // :184
+      seen = (int32_t)him.model;
+    if (seen != (int32_t)him.model) // :192
+      continue;
+    if (n < max_out) {
+      T1Fiducial &f = out[n];
+      f.target = t;
+      f.id = range < fd->max_range_id ? him.fiducial_return : 0; // :219
+      f.range = range;
+      f.bearing = dtheta;
+      f.geom[0] = him.sx;
+      f.geom[1] = him.sy;
+      f.geom[2] = him.sz;
+      f.geom[3] = normalize_angle(him.a - fd->a);
+      f.pose[0] = him.x;
+      f.pose[1] = him.y;
+      f.pose[2] = him.z;
+      f.pose[3] = him.a;
+    }
+    n++;
+  }
+  return n;
+}
+
+typedef struct {
+  uint32_t model, left, top, right, bottom, pad;
+  double range;
+} T1Blob; // 32 B, same layout as stg_rt_blob
+
+static bool color_match(const double *a, const double *b) // ColorMatchIgnoreAlpha, model_blobfinder.cc:109-113
+{
+  const double epsilon = 1e-5;
+  return fabs(a[0] - b[0]) < epsilon && fabs(a[1] - b[1]) < epsilon && fabs(a[2] - b[2]) < epsilon;
+}
+
+// ModelBlobfinder::Update (model_blobfinder.cc:165-250). origin = LocalToGlobal(Pose(0,0,0,pan)).
+uint32_t t1_blob_update(void *wv, uint32_t finder, int layer, const double *origin_xyza, double range, double fov,
+                        uint32_t scan_width, uint32_t scan_height, uint32_t n_colors, const double *colors_rgb,
+                        uint32_t max_out, T1Blob *out)
+{
+  const T1World *w = (const T1World *)wv;
+  std::vector<T1Hit> samples(scan_width);
+  t1_even_fan(wv, finder, layer, TRACE_KIND_UNRELATED, 0, origin_xyza, range, fov, scan_width, samples.data());
+  const double yRadsPerPixel = fov / scan_height;
+  uint32_t n = 0;
+  for (unsigned int s = 0; s < scan_width; s++) {
+    if (samples[s].hit_model < 0)
+      continue;
+    unsigned int right = s;
+    const int32_t blob_model = samples[s].hit_model;
+    const double *blobcol = w->models[blob_model].color;
+    while (s < scan_width && samples[s].hit_model >= 0 && color_match(w->models[samples[s].hit_model].color, blobcol))
+      s++;
+    unsigned int left = s - 1;
+    if (n_colors) {
+      bool found = false;
+      for (unsigned int c = 0; c < n_colors; c++)
+        if (color_match(blobcol, colors_rgb + 3 * c)) {
+          found = true;
+          break;
+        }
+      if (!found)
+        continue;
+    }
+    double robotHeight = 0.6;
+    double brange = 0;
+    for (unsigned int t = right; t <= left; t++)
+      brange += samples[t].range;
+    brange /= left - right + 1;
+    double startyangle = atan2(robotHeight / 2.0, brange);
+    double endyangle = -startyangle;
+    int blobtop = scan_height / 2 - (int)(startyangle / yRadsPerPixel);
+    int blobbottom = scan_height / 2 - (int)(endyangle / yRadsPerPixel);
+    blobtop = std::max(blobtop, 0);
+    blobbottom = std::min(blobbottom, (int)scan_height);
+    if (n < max_out) {
+      T1Blob &b = out[n];
+      b.model = (uint32_t)blob_model;
+      b.left = scan_width - left - 1;
+      b.top = (uint32_t)blobtop;
+      b.right = scan_width - right - 1;
+      b.bottom = (uint32_t)blobbottom;
+      b.pad = 0;
+      b.range = brange;
+    }
+    n++;
+  }
+  return n;
+}
+
 // Same record format as ref_dump_grid (oracle/ref_harness.cc): {layer, x, y, pos, block} int32[5],
 // sorted (layer, y, x, pos) by the caller. Returns the number of records.
 int64_t t1_dump_grid(void *wv, int32_t *out, int64_t cap, int64_t *counts, int64_t counts_cap, int64_t *n_counts)
@@ -459,6 +631,7 @@ typedef struct {
   uint64_t rays, range_mismatch, model_mismatch, maps, unmaps, ticks;
   uint64_t cell_visits, region_probes;
   uint64_t scans, scan_mismatch;
+  uint64_t fiducial_updates, fiducial_mismatch, blob_updates, blob_mismatch;
   double max_range_err;
 } T1ReplayStats;
 
@@ -489,9 +662,11 @@ void *t1_replay(const char *path, T1ReplayStats *st)
   if (!ok)
     return NULL;
   void *w = t1_create(h.ppm);
-  for (size_t i = 0; i < models.size(); i++)
+  for (size_t i = 0; i < models.size(); i++) {
     t1_model_upsert(w, models[i].id, models[i].root, models[i].ranger_return, models[i].fiducial_return,
                     models[i].fiducial_key, models[i].flags);
+    t1_model_color(w, models[i].id, models[i].color);
+  }
   for (size_t i = 0; i < events.size(); i++) {
     const TraceEvent &e = events[i];
     if (e.type == TRACE_EV_MAP) {
@@ -502,6 +677,59 @@ void *t1_replay(const char *path, T1ReplayStats *st)
       st->unmaps++;
     } else if (e.type == TRACE_EV_TICK) {
       st->ticks++;
+    } else if (e.type == TRACE_EV_FIDUCIAL) {
+      const double *a = &aux[e.first];
+      const uint32_t nt = (uint32_t)a[13], nf = e.block;
+      T1FidFinder fd;
+      memset(&fd, 0, sizeof(fd));
+      fd.finder = e.model;
+      fd.layer = e.layer;
+      fd.x = a[0]; fd.y = a[1]; fd.z = a[2]; fd.a = a[3];
+      fd.ox = a[4]; fd.oy = a[5]; fd.oz = a[6]; fd.oa = a[7];
+      fd.max_range_anon = a[8]; fd.max_range_id = a[9]; fd.fov = a[10];
+      fd.fiducial_key = (int32_t)a[11];
+      fd.ignore_zloc = a[12] != 0;
+      std::vector<T1FidTarget> tg(nt);
+      for (uint32_t k = 0; k < nt; k++) {
+        const double *t = a + TRACE_FID_HEADER_DOUBLES + TRACE_FID_TARGET_DOUBLES * k;
+        memset(&tg[k], 0, sizeof(T1FidTarget));
+        tg[k].model = (uint32_t)t[0];
+        tg[k].fiducial_return = (int32_t)t[1];
+        tg[k].fiducial_key = (int32_t)t[2];
+        tg[k].x = t[3]; tg[k].y = t[4]; tg[k].z = t[5]; tg[k].a = t[6];
+        tg[k].sx = t[7]; tg[k].sy = t[8]; tg[k].sz = t[9];
+      }
+      std::vector<T1Fiducial> found(nt + 1);
+      const uint32_t n = t1_fiducial_update(w, nt, tg.data(), &fd, nt + 1, found.data());
+      st->fiducial_updates++;
+      bool same = n == nf;
+      const double *ref = a + TRACE_FID_HEADER_DOUBLES + TRACE_FID_TARGET_DOUBLES * nt;
+      for (uint32_t k = 0; same && k < n; k++) {
+        const double *r = ref + TRACE_FID_RESULT_DOUBLES * k;
+        const T1Fiducial &f = found[k];
+        same = tg[f.target].model == (uint32_t)r[0] && f.id == (int32_t)r[1] && f.range == r[2] && f.bearing == r[3] &&
+               !memcmp(f.geom, r + 4, 32) && !memcmp(f.pose, r + 8, 32);
+      }
+      if (!same)
+        st->fiducial_mismatch++;
+    } else if (e.type == TRACE_EV_BLOB) {
+      const double *a = &aux[e.first];
+      const uint32_t nc = (uint32_t)a[8], nb = e.block, sw = (uint32_t)a[6], sh = (uint32_t)a[7];
+      std::vector<T1Blob> blobs(sw + 1);
+      const uint32_t n = t1_blob_update(w, e.model, e.layer, a, a[4], a[5], sw, sh, nc, a + TRACE_BLOB_HEADER_DOUBLES, sw + 1,
+                                        blobs.data());
+      st->blob_updates++;
+      bool same = n == nb;
+      const double *ref = a + TRACE_BLOB_HEADER_DOUBLES + 3 * nc;
+      for (uint32_t k = 0; same && k < n; k++) {
+        const double *r = ref + TRACE_BLOB_RESULT_DOUBLES * k;
+        const T1Blob &b = blobs[k];
+        const double *col = ((const T1World *)w)->models[b.model].color;
+        same = col[0] == r[0] && col[1] == r[1] && col[2] == r[2] && b.left == (uint32_t)r[3] && b.top == (uint32_t)r[4] &&
+               b.right == (uint32_t)r[5] && b.bottom == (uint32_t)r[6] && b.range == r[7];
+      }
+      if (!same)
+        st->blob_mismatch++;
     } else if (e.type == TRACE_EV_RANGER_SCAN) {
       const uint32_t n = e.n_pts;
       const double *a = &aux[e.first];

@@ -17,10 +17,10 @@
 #define STG_TRACE_FORMAT_H
 #include <stdint.h>
 
-#define STG_TRACE_MAGIC "STGTRC03"
+#define STG_TRACE_MAGIC "STGTRC04"
 
 enum { TRACE_EV_MAP = 1, TRACE_EV_UNMAP = 2, TRACE_EV_RAYS = 3, TRACE_EV_TICK = 4,
-       TRACE_EV_RANGER_SCAN = 5 };
+       TRACE_EV_RANGER_SCAN = 5, TRACE_EV_FIDUCIAL = 6, TRACE_EV_BLOB = 7 };
 
 /* predicate kinds: which of the reference's static ray_test_func_t a ray was traced with */
 enum {
@@ -76,5 +76,25 @@ typedef struct {
  * the first ray, rayorg after LocalToGlobal, model_ranger.cc:226-230), range_max, fov,
  * ranges[n], intensities[n], bearings[n] }. */
 #define TRACE_SCAN_HEADER_DOUBLES 6
+
+/* FIDUCIAL: one ModelFiducial::Update (model_fiducial.cc:229-293). event.model = finder model id,
+ * event.layer = layer its rays read, event.block = number of fiducials found, aux[first..] =
+ *   { x, y, z, a (GetGlobalPose), ox, oy, oz, oa (GetGlobalPose + geom.pose), max_range_anon,
+ *     max_range_id, fov, fiducial_key, ignore_zloc, n_targets }                      14 doubles
+ *   n_targets x { model id, fiducial_return, fiducial_key, x, y, z, a, sx, sy, sz }  10 doubles each,
+ *     World::models_with_fiducials in ascending Model* order (the order candidates are visited)
+ *   n_found  x { model id, id, range, bearing, geom[4], pose[4] }                    12 doubles each */
+#define TRACE_FID_HEADER_DOUBLES 14
+#define TRACE_FID_TARGET_DOUBLES 10
+#define TRACE_FID_RESULT_DOUBLES 12
+
+/* BLOB: one ModelBlobfinder::Update (model_blobfinder.cc:165-250). event.model = finder model id,
+ * event.layer, event.block = number of blobs, aux[first..] =
+ *   { ox, oy, oz, oa (LocalToGlobal(Pose(0,0,0,pan))), range, fov, scan_width, scan_height,
+ *     n_colors }                                                                       9 doubles
+ *   n_colors x { r, g, b }
+ *   n_blobs  x { r, g, b, left, top, right, bottom, range }                            8 doubles each */
+#define TRACE_BLOB_HEADER_DOUBLES 9
+#define TRACE_BLOB_RESULT_DOUBLES 8
 
 #endif

@@ -112,6 +112,19 @@ struct stg_rt_ctx {
   FanArrays d;
   PinBuf h_in, h_ranges, h_intens, h_bearings, h_hit_model, h_hit_cell, h_steps;
 
+  // sensor post-processing batches (fiducial finders, blobfinders): one in flight per kind
+  struct PostJob {
+    void *user_out = nullptr;
+    uint32_t *user_count = nullptr;
+    size_t out_bytes = 0, count_bytes = 0;
+    bool pending = false;
+  } fid_job, blob_job;
+  DevBuf d_fid_in, d_fid_out, d_fid_count, d_blob_in, d_blob_out, d_blob_count, d_mdl_color;
+  PinBuf h_fid_in, h_fid_out, h_fid_count, h_blob_in, h_blob_out, h_blob_count;
+  FanArrays bd; // the blobfinders' scan-line fans
+  std::vector<double> mdl_color; // rgba per model
+  bool mdl_color_dirty = true;
+
   std::map<char *, size_t> host_allocs; // stg_rt_host_alloc regions
   stg_rt_stats stats;
 
@@ -497,8 +510,29 @@ void deliver_array(stg_rt_ctx *c, void *user, const PinBuf &stage, uint64_t firs
   memcpy(user, (const char *)stage.p + first * elt, n * elt);
 }
 
+int deliver_post_locked(stg_rt_ctx *c)
+{
+  if (!c->fid_job.pending && !c->blob_job.pending)
+    return 0;
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (c->fid_job.pending) {
+    memcpy(c->fid_job.user_out, c->h_fid_out.p, c->fid_job.out_bytes);
+    memcpy(c->fid_job.user_count, c->h_fid_count.p, c->fid_job.count_bytes);
+    c->fid_job.pending = false;
+  }
+  if (c->blob_job.pending) {
+    memcpy(c->blob_job.user_out, c->h_blob_out.p, c->blob_job.out_bytes);
+    memcpy(c->blob_job.user_count, c->h_blob_count.p, c->blob_job.count_bytes);
+    c->blob_job.pending = false;
+  }
+  return 0;
+}
+
 int deliver_locked(stg_rt_ctx *c)
 {
+  int prc = deliver_post_locked(c);
+  if (prc)
+    return prc;
   if (c->f_subs.empty())
     return 0;
   CU(c, cudaStreamSynchronize(c->stream));
@@ -699,6 +733,7 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
   c->blocks.resize(cfg->max_blocks);
   c->model_known.assign(cfg->max_models, false);
   c->models.resize(cfg->max_models);
+  c->mdl_color.assign(4 * (size_t)cfg->max_models, 0.0);
   *out = c;
   return STG_RT_OK;
 }
@@ -716,6 +751,13 @@ int stg_rt_destroy(stg_rt_ctx *c)
     if (p)
       cudaFree(p);
   free_fan_arrays(c->d);
+  free_fan_arrays(c->bd);
+  for (DevBuf *b : { &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
+    if (b->p)
+      cudaFree(b->p);
+  for (PinBuf *b : { &c->h_fid_in, &c->h_fid_out, &c->h_fid_count, &c->h_blob_in, &c->h_blob_out, &c->h_blob_count })
+    if (b->p)
+      cudaFreeHost(b->p);
   PinBuf *pins[] = { &c->h_blob, &c->h_in, &c->h_ranges, &c->h_intens, &c->h_bearings, &c->h_hit_model, &c->h_hit_cell, &c->h_steps };
   for (PinBuf *p : pins)
     if (p->p)
@@ -737,7 +779,10 @@ int stg_rt_model_upsert(stg_rt_ctx *c, uint32_t id, uint32_t root_id, double ran
   if (!c)
     return STG_RT_EINVAL;
   std::lock_guard<std::mutex> lk(c->mu);
-  (void)rgba;
+  if (id < c->cfg.max_models && rgba) {
+    memcpy(&c->mdl_color[4 * (size_t)id], rgba, 4 * sizeof(double));
+    c->mdl_color_dirty = true;
+  }
   if (id >= c->cfg.max_models || root_id >= c->cfg.max_models)
     return fail(c, STG_RT_ENOMEM, "model id %u / root %u beyond max_models %u", id, root_id, c->cfg.max_models);
   if (!c->q_subs.empty()) { // fans queued before this change must not see it
@@ -1221,6 +1266,186 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_r
   CU(c, cudaEventRecord(c->t_ev[0][1], c->stream));
   c->t_rec[0] = true;
   CU(c, cudaGetLastError());
+  return STG_RT_OK;
+}
+
+// ---- sensor post-processing: fiducial finders and blobfinders ---------------------------------------
+
+int stg_rt_fiducials_submit(stg_rt_ctx *c, uint32_t n_targets, const stg_rt_fid_target *targets, uint32_t n_finders,
+                            const stg_rt_fid_finder *finders, uint32_t max_per_finder, stg_rt_fiducial *out, uint32_t *out_count)
+{
+  static_assert(sizeof(stg_rt_fid_target) == sizeof(FidTargetRec) && sizeof(stg_rt_fid_finder) == sizeof(FidFinderRec) &&
+                    sizeof(stg_rt_fiducial) == sizeof(FiducialRec), "fiducial record layouts");
+  if (!c || (n_targets && !targets) || (n_finders && (!finders || !out || !out_count)) || !max_per_finder)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!n_finders)
+    return STG_RT_OK;
+  for (uint32_t i = 0; i < n_finders; i++)
+    if (finders[i].finder >= c->cfg.max_models || !c->model_known[finders[i].finder] || finders[i].layer > 1)
+      return fail(c, STG_RT_EINVAL, "fiducial finder %u: unknown model %u or bad layer", i, finders[i].finder);
+  for (uint32_t i = 0; i < n_targets; i++)
+    if (targets[i].model >= c->cfg.max_models || !c->model_known[targets[i].model])
+      return fail(c, STG_RT_EINVAL, "fiducial target %u: unknown model %u", i, targets[i].model);
+  int rc = flush_locked(c); // issue order: everything submitted before is on the stream first
+  if (rc || (rc = deliver_post_locked(c)))
+    return rc;
+  const size_t b_t = (size_t)n_targets * sizeof(FidTargetRec), b_f = (size_t)n_finders * sizeof(FidFinderRec);
+  const size_t b_fan = (size_t)n_finders * sizeof(FanRec), b_in = b_t + b_f + b_fan;
+  const size_t b_out = (size_t)n_finders * max_per_finder * sizeof(FiducialRec), b_cnt = (size_t)n_finders * 4;
+  if ((rc = pin_reserve(c, c->h_fid_in, b_in)) || (rc = dev_reserve(c, c->d_fid_in, b_in)) ||
+      (rc = pin_reserve(c, c->h_fid_out, b_out)) || (rc = dev_reserve(c, c->d_fid_out, b_out)) ||
+      (rc = pin_reserve(c, c->h_fid_count, b_cnt)) || (rc = dev_reserve(c, c->d_fid_count, b_cnt)))
+    return rc;
+  char *hp = (char *)c->h_fid_in.p;
+  if (b_t)
+    memcpy(hp, targets, b_t);
+  memcpy(hp + b_t, finders, b_f);
+  FanRec *fans = (FanRec *)(hp + b_t + b_f);
+  for (uint32_t i = 0; i < n_finders; i++) { // the line-of-sight ray of AddModelIfVisible (model_fiducial.cc:179)
+    FanRec &r = fans[i];
+    memset(&r, 0, sizeof(r));
+    r.finder = finders[i].finder;
+    r.n_samples = 1;
+    r.pred = STG_RT_PRED_UNRELATED;
+    r.ztest = 1;
+    r.layer = finders[i].layer;
+    r.angles = STG_RT_ANGLES_EXPLICIT;
+    r.ox = finders[i].ox;
+    r.oy = finders[i].oy;
+    r.oz = finders[i].oz;
+    r.oa = finders[i].oa;
+    r.range = finders[i].max_range_anon;
+  }
+  CU(c, cudaMemcpyAsync(c->d_fid_in.p, hp, b_in, cudaMemcpyHostToDevice, c->stream));
+  c->stats.h2d_bytes += b_in;
+  FidBatchView v;
+  v.n_targets = n_targets;
+  v.n_finders = n_finders;
+  v.max_per_finder = max_per_finder;
+  v.targets = (const FidTargetRec *)c->d_fid_in.p;
+  v.finders = (const FidFinderRec *)((char *)c->d_fid_in.p + b_t);
+  v.fans = (const FanRec *)((char *)c->d_fid_in.p + b_t + b_f);
+  v.out = (FiducialRec *)c->d_fid_out.p;
+  v.out_count = (uint32_t *)c->d_fid_count.p;
+  launch_fiducials(c->g, v, c->stream);
+  CU(c, cudaGetLastError());
+  c->stats.launches_post++;
+  CU(c, cudaMemcpyAsync(c->h_fid_out.p, c->d_fid_out.p, b_out, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(c->h_fid_count.p, c->d_fid_count.p, b_cnt, cudaMemcpyDeviceToHost, c->stream));
+  c->stats.d2h_bytes += b_out + b_cnt;
+  c->fid_job.user_out = out;
+  c->fid_job.user_count = out_count;
+  c->fid_job.out_bytes = b_out;
+  c->fid_job.count_bytes = b_cnt;
+  c->fid_job.pending = true;
+  return STG_RT_OK;
+}
+
+int stg_rt_blobs_submit(stg_rt_ctx *c, uint32_t n_finders, const stg_rt_blob_finder *finders, uint32_t n_colors,
+                        const double *colors_rgb, uint32_t max_per_finder, stg_rt_blob *out, uint32_t *out_count)
+{
+  static_assert(sizeof(stg_rt_blob_finder) == sizeof(BlobFinderRec) && sizeof(stg_rt_blob) == sizeof(BlobRec), "blob record layouts");
+  if (!c || (n_finders && (!finders || !out || !out_count)) || (n_colors && !colors_rgb) || !max_per_finder)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!n_finders)
+    return STG_RT_OK;
+  uint64_t beams = 0;
+  for (uint32_t i = 0; i < n_finders; i++) {
+    const stg_rt_blob_finder &f = finders[i];
+    if (f.finder >= c->cfg.max_models || !c->model_known[f.finder] || f.layer > 1 || !f.scan_width || !f.scan_height ||
+        (uint64_t)f.first_color + f.n_colors > n_colors)
+      return fail(c, STG_RT_EINVAL, "blobfinder %u: unknown model %u, bad layer / image size / colours", i, f.finder);
+    beams += f.scan_width;
+  }
+  int rc = flush_locked(c);
+  if (rc || (rc = deliver_post_locked(c)))
+    return rc;
+  if (c->mdl_color_dirty) {
+    const size_t b_col = c->mdl_color.size() * 8;
+    if ((rc = dev_reserve(c, c->d_mdl_color, b_col)))
+      return rc;
+    CU(c, cudaMemcpyAsync(c->d_mdl_color.p, c->mdl_color.data(), b_col, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream)); // pageable source
+    c->stats.h2d_bytes += b_col;
+    c->mdl_color_dirty = false;
+  }
+  // pinned input block: finders | fans | first_beam | colours
+  const size_t b_f = (size_t)n_finders * sizeof(BlobFinderRec), b_fan = (size_t)n_finders * sizeof(FanRec);
+  const size_t b_first = ((size_t)(n_finders + 1) * 4 + 7) & ~(size_t)7, b_col = (size_t)n_colors * 24;
+  const size_t b_in = b_f + b_fan + b_first + b_col;
+  const size_t b_out = (size_t)n_finders * max_per_finder * sizeof(BlobRec), b_cnt = (size_t)n_finders * 4;
+  if ((rc = pin_reserve(c, c->h_blob_in, b_in)) || (rc = dev_reserve(c, c->d_blob_in, std::max<size_t>(b_in, 8))) ||
+      (rc = pin_reserve(c, c->h_blob_out, b_out)) || (rc = dev_reserve(c, c->d_blob_out, b_out)) ||
+      (rc = pin_reserve(c, c->h_blob_count, b_cnt)) || (rc = dev_reserve(c, c->d_blob_count, b_cnt)) ||
+      (rc = reserve_outputs(c, c->bd, beams, STG_RT_WANT_RANGES | STG_RT_WANT_HIT_MODEL)))
+    return rc;
+  char *hp = (char *)c->h_blob_in.p;
+  memcpy(hp, finders, b_f);
+  FanRec *fans = (FanRec *)(hp + b_f);
+  uint32_t *first = (uint32_t *)(hp + b_f + b_fan);
+  uint32_t cursor = 0;
+  for (uint32_t i = 0; i < n_finders; i++) { // Raytrace(Pose(0,0,0,pan), range, fov, blob_match, NULL, false, samples), :170
+    FanRec &r = fans[i];
+    memset(&r, 0, sizeof(r));
+    r.finder = finders[i].finder;
+    r.n_samples = finders[i].scan_width;
+    r.pred = STG_RT_PRED_UNRELATED;
+    r.ztest = 0;
+    r.layer = finders[i].layer;
+    r.angles = STG_RT_ANGLES_EVEN_FOV;
+    r.ox = finders[i].ox;
+    r.oy = finders[i].oy;
+    r.oz = finders[i].oz;
+    r.oa = finders[i].oa;
+    r.range = finders[i].range;
+    r.fov = finders[i].fov;
+    first[i] = cursor;
+    cursor += finders[i].scan_width;
+  }
+  first[n_finders] = cursor;
+  if (b_col)
+    memcpy(hp + b_f + b_fan + b_first, colors_rgb, b_col);
+  CU(c, cudaMemcpyAsync(c->d_blob_in.p, hp, b_in, cudaMemcpyHostToDevice, c->stream));
+  c->stats.h2d_bytes += b_in;
+  char *dp = (char *)c->d_blob_in.p;
+  FanBatchView fv;
+  memset(&fv, 0, sizeof(fv));
+  fv.n_fans = n_finders;
+  fv.n_beams = beams;
+  fv.fans = (const FanRec *)(dp + b_f);
+  fv.fan_first_beam = (const uint32_t *)(dp + b_f + b_fan);
+  fv.heading = (double *)c->bd.heading.p;
+  fv.ranges = (double *)c->bd.ranges.p;
+  fv.hit_model = (int32_t *)c->bd.hit_model.p;
+  launch_fan_headings(fv, c->stream);
+  launch_ray_march(c->g, fv, c->stream);
+  BlobBatchView bv;
+  bv.n_finders = n_finders;
+  bv.max_per_finder = max_per_finder;
+  bv.finders = (const BlobFinderRec *)dp;
+  bv.fan_first_beam = fv.fan_first_beam;
+  bv.hit_model = fv.hit_model;
+  bv.ranges = fv.ranges;
+  bv.mdl_color = (const double *)c->d_mdl_color.p;
+  bv.colors = (const double *)(dp + b_f + b_fan + b_first);
+  bv.out = (BlobRec *)c->d_blob_out.p;
+  bv.out_count = (uint32_t *)c->d_blob_count.p;
+  launch_blobs(c->g, bv, c->stream);
+  CU(c, cudaGetLastError());
+  c->stats.launches_post += 2;
+  c->stats.launches_march += 1;
+  c->stats.beams += beams;
+  c->stats.fans += n_finders;
+  CU(c, cudaMemcpyAsync(c->h_blob_out.p, c->d_blob_out.p, b_out, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(c->h_blob_count.p, c->d_blob_count.p, b_cnt, cudaMemcpyDeviceToHost, c->stream));
+  c->stats.d2h_bytes += b_out + b_cnt;
+  c->blob_job.user_out = out;
+  c->blob_job.user_count = out_count;
+  c->blob_job.out_bytes = b_out;
+  c->blob_job.count_bytes = b_cnt;
+  c->blob_job.pending = true;
   return STG_RT_OK;
 }
 

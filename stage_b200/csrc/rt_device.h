@@ -122,6 +122,74 @@ struct FanBatchView {
   uint32_t *steps;
 };
 
+// ---- fiducial finders (same layouts as stg_rt_fid_* in include/stg_rt.h) -----------------------
+struct FidTargetRec {
+  uint32_t model;
+  int32_t fiducial_return, fiducial_key;
+  uint32_t reserved;
+  double x, y, z, a;
+  double sx, sy, sz;
+};
+static_assert(sizeof(FidTargetRec) == 72, "FidTargetRec");
+
+struct FidFinderRec {
+  uint32_t finder;
+  int32_t fiducial_key;
+  uint8_t ignore_zloc, layer, pad[6];
+  double x, y, z, a;
+  double ox, oy, oz, oa;
+  double max_range_anon, max_range_id, fov;
+};
+static_assert(sizeof(FidFinderRec) == 104, "FidFinderRec");
+
+struct FiducialRec {
+  uint32_t target;
+  int32_t id;
+  double range, bearing;
+  double geom[4], pose[4];
+};
+static_assert(sizeof(FiducialRec) == 88, "FiducialRec");
+
+struct FidBatchView {
+  uint32_t n_targets, n_finders, max_per_finder;
+  const FidTargetRec *targets;
+  const FidFinderRec *finders;
+  const FanRec *fans; // one per finder: the line-of-sight ray's constants
+  FiducialRec *out;
+  uint32_t *out_count;
+};
+
+// ---- blobfinders ------------------------------------------------------------------------------
+struct BlobFinderRec {
+  uint32_t finder, scan_width, scan_height;
+  uint8_t layer, pad[3];
+  uint32_t first_color, n_colors;
+  double ox, oy, oz, oa;
+  double range, fov;
+};
+static_assert(sizeof(BlobFinderRec) == 72, "BlobFinderRec");
+
+struct BlobRec {
+  uint32_t model, left, top, right, bottom, pad;
+  double range;
+};
+static_assert(sizeof(BlobRec) == 32, "BlobRec");
+
+struct BlobBatchView {
+  uint32_t n_finders, max_per_finder;
+  const BlobFinderRec *finders;
+  const uint32_t *fan_first_beam;
+  const int32_t *hit_model; // the traced scan lines
+  const double *ranges;
+  const double *mdl_color;  // 4 doubles (rgba) per model
+  const double *colors;     // 3 doubles per tracked colour
+  BlobRec *out;
+  uint32_t *out_count;
+};
+
+void launch_fiducials(const GridView &g, const FidBatchView &b, void *stream);
+void launch_blobs(const GridView &g, const BlobBatchView &b, void *stream);
+
 // launch wrappers implemented in rt_kernels.cu; all asynchronous on `stream`
 void launch_apply_deltas(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
                          unsigned long long epoch, void *stream, uint64_t *launch_counter);

@@ -279,89 +279,48 @@ void launch_rehash(const unsigned long long *src, unsigned long long *dst, uint3
 }
 
 // ------------------------------------------------------------------------------------------
-// K2a: per-beam headings. The ranger rule is a sequential float-rounding recurrence
-// (model_ranger.cc:237-241,254: the running angle goes through a `float` every beam), so a fan's
-// headings cannot be evaluated independently. One lane per fan, one warp per 32 fans; every 32 steps
-// the warp's 32x32 tile of headings is transposed through shared memory so that the global stores
-// are coalesced (each fan's 32 consecutive headings = one 256-byte row).
+// K2a: per-beam headings. One thread per fan; the ranger rule is a sequential float-rounding
+// recurrence (model_ranger.cc:237-241,254: the running angle goes through a `float` every beam),
+// so a fan's headings cannot be evaluated per beam independently.
 // ------------------------------------------------------------------------------------------
-
-// (double)(float)x for x in the normal float range, with integer ops on the bit pattern (round to
-// nearest even on the 29 dropped mantissa bits) instead of two conversion-unit instructions on the
-// critical path of the recurrence. Everything else (0, float subnormals, huge) takes the conversions.
-__device__ __forceinline__ double round_through_float(double x)
-{
-  long long bits = __double_as_longlong(x);
-  const int e = (int)((bits >> 52) & 0x7ff);
-  if (e < 1023 - 126 || e > 1023 + 126)
-    return (double)(float)x;
-  bits += 0x0fffffffll + ((bits >> 29) & 1ll);
-  bits &= ~0x1fffffffll;
-  return __longlong_as_double(bits);
-}
 
 __global__ void __launch_bounds__(32) k2_fan_headings(FanBatchView b)
 {
-  __shared__ double tile_h[32][33];
-  __shared__ double tile_b[32][33];
-  const uint32_t lane = threadIdx.x;
-  const uint32_t f0 = blockIdx.x * 32u, f = f0 + lane;
-  const bool live = f < b.n_fans;
-  FanRec fan;
-  uint32_t first = 0, n = 0;
-  if (live) {
-    fan = b.fans[f];
-    first = b.fan_first_beam[f];
-    n = fan.n_samples;
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= b.n_fans)
+    return;
+  const FanRec fan = b.fans[f];
+  const uint32_t first = b.fan_first_beam[f], n = fan.n_samples;
+  double *heading = b.heading + first;
+  double *bearing = b.bearings ? b.bearings + first : nullptr;
+  if (fan.angles == 0 /* STG_RT_ANGLES_RANGER */) {
+    const uint32_t nm1 = n - 1u; // unsigned, like std::max(sample_count - 1, 1u)
+    const double incr = fan.fov / (double)(nm1 > 1u ? nm1 : 1u);
+    const double start = n > 1 ? -fan.fov / 2.0 : 0.0;
+    double a = fan.oa;
+    for (uint32_t t = 0; t < n; t++) {
+      const float fa = (float)a; // float savedAngle / distortedAngle with zero angle noise
+      heading[t] = (double)fa;
+      a = (double)fa + incr;
+    }
+    if (bearing)
+      for (uint32_t t = 0; t < n; t++)
+        bearing[t] = start + ((double)t) * incr;
+  } else if (fan.angles == 1 /* STG_RT_ANGLES_EVEN_FOV */) {
+    const double starta = fan.fov / 2.0 - fan.oa;
+    for (uint32_t s = 0; s < n; s++) {
+      const double h = ((double)s * fan.fov / (double)(n - 1u)) - starta;
+      heading[s] = h;
+      if (bearing)
+        bearing[s] = h - fan.oa;
+    }
   } else {
-    fan.angles = 1;
-    fan.fov = fan.oa = 0;
-    fan.first_heading = 0;
-  }
-  uint32_t n_max = n;
-  for (int o = 16; o; o >>= 1)
-    n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, o));
-  const bool want_bearing = b.bearings != nullptr;
-
-  // per-rule constants
-  const uint32_t nm1 = n - 1u; // unsigned, like std::max(sample_count - 1, 1u)
-  const double incr = fan.fov / (double)(nm1 > 1u ? nm1 : 1u);
-  const double start = n > 1 ? -fan.fov / 2.0 : 0.0;
-  const double starta = fan.fov / 2.0 - fan.oa;
-  double a = fan.oa; // RANGER running angle
-
-  for (uint32_t t0 = 0; t0 < n_max; t0 += 32) {
-    for (uint32_t j = 0; j < 32; j++) {
-      const uint32_t t = t0 + j;
-      double h = 0.0, be = 0.0;
-      if (t < n) {
-        if (fan.angles == 0 /* STG_RT_ANGLES_RANGER */) {
-          h = round_through_float(a); // float savedAngle / distortedAngle with zero angle noise
-          a = h + incr;
-          be = start + ((double)t) * incr;
-        } else if (fan.angles == 1 /* STG_RT_ANGLES_EVEN_FOV */) {
-          h = ((double)t * fan.fov / (double)(n - 1u)) - starta;
-          be = h - fan.oa;
-        } else {
-          h = b.headings_in[fan.first_heading + t];
-          be = h - fan.oa;
-        }
-      }
-      tile_h[lane][j] = h;
-      if (want_bearing)
-        tile_b[lane][j] = be;
+    for (uint32_t s = 0; s < n; s++) {
+      const double h = b.headings_in[fan.first_heading + s];
+      heading[s] = h;
+      if (bearing)
+        bearing[s] = h - fan.oa;
     }
-    __syncwarp();
-    for (uint32_t r = 0; r < 32; r++) {
-      const uint32_t n_r = __shfl_sync(0xffffffffu, n, r), first_r = __shfl_sync(0xffffffffu, first, r);
-      const uint32_t t = t0 + lane;
-      if (t < n_r) {
-        b.heading[first_r + t] = tile_h[r][lane];
-        if (want_bearing)
-          b.bearings[first_r + t] = tile_b[r][lane];
-      }
-    }
-    __syncwarp();
   }
 }
 

@@ -14,87 +14,11 @@
 //  * Empty regions are skipped with the reference's own crossing arithmetic (FP64, same operation
 //    order, no FMA contraction: build with -fmad=false), including its stale error term, the
 //    truncating double->int conversions and the int -= double of the remaining distance.
-#include <cuda_runtime.h>
-#include <stdint.h>
-
-#include "rt_device.h"
+#include "rt_trace.cuh"
 
 namespace stg {
 
 namespace {
-
-__device__ __forceinline__ uint32_t mix32(uint32_t k)
-{
-  k ^= k >> 16;
-  k *= 0x7feb352du;
-  k ^= k >> 15;
-  k *= 0x846ca68bu;
-  k ^= k >> 16;
-  return k;
-}
-
-// Resolve an occupied cell: among the blocks rendered into it that pass the z test and the
-// predicate, the one first in Cell::blocks[layer] order wins (world.cc:841-862). Reads the fan's
-// constants from its (L1-resident) record rather than holding them in registers during the march.
-__device__ __noinline__ int32_t resolve_cell(const unsigned long long *slots, uint32_t slot_mask, const uint4 *recs,
-                                             const uint32_t *mdl_root, const FanRec *fan, uint32_t key)
-{
-  const uint32_t finder = fan->finder, pred = fan->pred, ztest = fan->ztest;
-  const double oz = fan->oz;
-  const uint32_t finder_root = __ldg(mdl_root + finder);
-  unsigned long long best_seq = ~0ull;
-  int32_t best_model = -1;
-  uint32_t h = mix32(key) & slot_mask;
-  for (uint32_t probes = 0; probes <= slot_mask; probes++) {
-    const unsigned long long cur = __ldg(slots + h);
-    if (cur == kSlotEmpty)
-      break;
-    if ((uint32_t)(cur >> 32) == key) {
-      const uint32_t blk = (uint32_t)cur - 1u;
-      const uint4 z = __ldg(recs + 2 * (size_t)blk), o = __ldg(recs + 2 * (size_t)blk + 1);
-      const double zmin = __hiloint2double((int)z.y, (int)z.x), zmax = __hiloint2double((int)z.w, (int)z.z);
-      if (!ztest || !(oz < zmin || oz > zmax)) { // world.cc:846
-        const uint32_t model = o.z, root = o.w & kRecRootMask;
-        bool pass;
-        if (pred == 0u) // ranger_match, model_ranger.cc:158-170
-          pass = root != finder_root && !(o.w & kRecNoRanger);
-        else if (pred == 2u) // gripper_raytrace_match, model_gripper.cc:329-336
-          pass = model != finder && (o.w & kRecGripper);
-        else // fiducial / blob / bumper: not related, model.cc:446-466
-          pass = root != finder_root;
-        if (pass) {
-          const unsigned long long s = ((unsigned long long)o.y << 32) | o.x;
-          if (s < best_seq) {
-            best_seq = s;
-            best_model = (int32_t)model;
-          }
-        }
-      }
-    }
-    h = (h + 1) & slot_mask;
-  }
-  return best_model;
-}
-
-// The value the reference's `x += s` (s = +-1.0) reaches after k repetitions. Every one of those
-// additions is exact as long as the running value stays within the binade of x (or below it): all
-// intermediate values are multiples of ulp(x) and fit 53 bits. Then one addition of k*s gives the
-// same double. Otherwise (the magnitude grows across a power of two, or the sign changes) the
-// roundings happen one by one, as there.
-__device__ __forceinline__ double seq_add(double x, int32_t k, bool negative)
-{
-  const double ks = negative ? -(double)k : (double)k;
-  const double r = x + ks;
-  const int hx = __double2hiint(x), hr = __double2hiint(r);
-  if (k == 0 || ((hx ^ hr) >= 0 && (hr & 0x7ff00000) <= (hx & 0x7ff00000)))
-    return r;
-  const double ds = negative ? -1.0 : 1.0;
-  for (int32_t j = 0; j < k; j++)
-    x += ds;
-  return x;
-}
-
-enum : uint32_t { kYMajor = 1u, kRunNeg = 2u, kCrossNeg = 4u, kXNeg = 8u, kYNeg = 16u };
 
 template <bool kSteps>
 __global__ void __launch_bounds__(128, 8) k2_ray_march(GridView g, FanBatchView b)
@@ -113,206 +37,31 @@ __global__ void __launch_bounds__(128, 8) k2_ray_march(GridView g, FanBatchView 
       hi = mid;
   }
   const FanRec *fan = b.fans + lo;
-  const double ppm = g.ppm;
 
-  double gx = fan->ox * ppm, gy = fan->oy * ppm; // world.cc:765-766
-  double tana, trig_major, yjumpx;
-  int32_t n, E, b_run, b_cross, r_max, v1;
-  uint32_t flags;
-  {
-    const double heading = b.heading[beam];
-    const double ang = heading == 0.0 ? 1e-12 : heading; // world.cc:773
-    double sina, cosa;
-    if (b.trig_in) {
-      cosa = b.trig_in[2 * beam];
-      sina = b.trig_in[2 * beam + 1];
-    } else {
-      sina = sin(ang);
-      cosa = cos(ang);
-    }
-    tana = sina / cosa;
-    const double range = fan->range;
-    const double dx = ppm * range * cosa, dy = ppm * range * sina; // world.cc:780-781
-    const int32_t ax = __double2int_rz(fabs(dx)), ay = __double2int_rz(fabs(dy));
-    n = ax + ay; // manhattan distance left, world.cc:792
-    // The reference's error term exy (ay-ax; exy<0: x step, exy += 2ay; else y step, exy -= 2ax) in
-    // run form. A ray is walked along its major ("run") axis in runs of cells that share the cross
-    // coordinate:  E < 0 -> run step, E += b_run;  E >= 0 -> cross step, E -= b_cross.
-    //   x-major: E = exy,      b_run = 2ay, b_cross = 2ax, row masks
-    //   y-major: E = -exy - 1, b_run = 2ax, b_cross = 2ay, column masks
-    // Both forms describe the same cell sequence for any slope; the choice only makes runs long.
-    const bool ymajor = ay > ax;
-    b_run = ymajor ? 2 * ax : 2 * ay;
-    b_cross = ymajor ? 2 * ay : 2 * ax;
-    E = ymajor ? -(ay - ax) - 1 : (ay - ax);
-    const bool xneg = dx < 0, yneg = dy < 0;
-    flags = (ymajor ? kYMajor : 0u) | ((ymajor ? yneg : xneg) ? kRunNeg : 0u) | ((ymajor ? xneg : yneg) ? kCrossNeg : 0u) |
-            (xneg ? kXNeg : 0u) | (yneg ? kYNeg : 0u);
-    // r_max = min(ceil(b_cross / b_run), 33): the longest possible run; 33 = "past the region edge"
-    r_max = 33;
-    if (b_run > 0 && (long long)b_run * 33 > b_cross)
-      r_max = (b_cross + b_run - 1) / b_run;
-    v1 = (r_max - 1) * b_run;
-    trig_major = ax > ay ? cosa : sina; // the divisor of the hit range, world.cc:856-859
-    yjumpx = (yneg ? -(double)kRegionWidth : (double)kRegionWidth) / tana; // world.cc:797
+  double cosa, sina;
+  if (b.trig_in) { // strict mode: the host libm's values
+    cosa = b.trig_in[2 * beam];
+    sina = b.trig_in[2 * beam + 1];
+  } else {
+    trace::heading_trig(b.heading[beam], cosa, sina);
   }
-
-  double xcrossx = 0, xcrossy = 0, ycrossx = 0, ycrossy = 0, distX = 0, distY = 0;
-  bool need_crossings = true;
-  int32_t hit_model = -1, hit_x = 0, hit_y = 0;
-  uint32_t cell_visits = 0, region_probes = 0;
-  const bool layer1 = (fan->layer & 1) != 0;
-  const uint32_t *occ = layer1 ? g.occ[1] : g.occ[0];
-  bool hit = false;
-
-  while (n > 0) {
-    if (kSteps)
-      region_probes++;
-    const int32_t ix0 = __double2int_rz(gx), iy0 = __double2int_rz(gy); // GETSREG/GETREG(double), world.cc:820-821
-    const int32_t rix = (ix0 >> kRBits) - g.rx0, riy = (iy0 >> kRBits) - g.ry0;
-    uint32_t region = 0, count = 0;
-    if ((uint32_t)rix < (uint32_t)g.nrx && (uint32_t)riy < (uint32_t)g.nry) {
-      region = (uint32_t)(riy * g.nrx + rix);
-      count = __ldg(g.reg_count + region);
-    }
-    if (count) {
-      // ---- populated region: integer walk over the occupancy masks (world.cc:823-882) ----
-      need_crossings = true;
-      const int32_t cx0 = ix0 & (kRegionWidth - 1), cy0 = iy0 & (kRegionWidth - 1);
-      int32_t c = (flags & kYMajor) ? cx0 : cy0;   // cross coordinate
-      int32_t ap = (flags & kYMajor) ? cy0 : cx0;  // run coordinate ...
-      if (flags & kRunNeg)
-        ap = kRegionWidth - 1 - ap;                // ... counted in the direction of travel
-      int32_t ka = 0, kc = 0;                      // run / cross steps taken in this region
-      const uint32_t *tile = occ + (size_t)region * kTileWords + ((flags & kYMajor) ? kRegionWidth : 0);
-      uint32_t word = __ldg(tile + c);
-      if (flags & kRunNeg)
-        word = __brev(word);
-      for (;;) {
-        // r = run steps before the next cross step: the smallest r >= 0 with E + r*b_run >= 0.
-        // E >= -b_cross always, so r <= r_max, and right after a cross step r is r_max or r_max-1.
-        int32_t r = 0;
-        if (E < 0) {
-          const int32_t t = -E;
-          r = r_max;
-          if (v1 >= t) {
-            r = r_max - 1;
-            while (r > 0 && (r - 1) * b_run >= t)
-              r--;
-          }
-        }
-        int32_t m = min(min(r + 1, kRegionWidth - ap), n); // cells tested: a cell is only tested while n > 0
-        const uint32_t occupied = word & ((0xffffffffu >> (32 - m)) << ap);
-        if (occupied) {
-          const int32_t ah = __ffs(occupied) - 1;
-          const uint32_t areal = (flags & kRunNeg) ? (uint32_t)(kRegionWidth - 1 - ah) : (uint32_t)ah;
-          const uint32_t hx = (flags & kYMajor) ? (uint32_t)c : areal, hy = (flags & kYMajor) ? areal : (uint32_t)c;
-          const int32_t mdl = resolve_cell(layer1 ? g.slots[1] : g.slots[0], g.slot_mask,
-                                           reinterpret_cast<const uint4 *>(layer1 ? g.blk_rec[1] : g.blk_rec[0]),
-                                           g.mdl_root, fan, (region << (2 * kRBits)) | (hy << kRBits) | hx);
-          if (mdl >= 0) {
-            hit_model = mdl;
-            hit_x = (ix0 & ~(kRegionWidth - 1)) + (int32_t)hx;
-            hit_y = (iy0 & ~(kRegionWidth - 1)) + (int32_t)hy;
-            ka += ah - ap;
-            if (kSteps)
-              cell_visits += (uint32_t)(ah - ap) + 1u;
-            hit = true;
-            break;
-          }
-          word &= ~(1u << ah); // nothing in that cell stops this ray: look past it
-          continue;
-        }
-        if (kSteps)
-          cell_visits += (uint32_t)m;
-        n -= m;
-        if (m == r + 1) { // the whole run, then the cross step
-          ap += r;
-          ka += r;
-          c += (flags & kCrossNeg) ? -1 : 1;
-          kc += 1;
-          E += r * b_run - b_cross;
-          if ((uint32_t)c >= (uint32_t)kRegionWidth || n <= 0)
-            break;
-          word = __ldg(tile + c);
-          if (flags & kRunNeg)
-            word = __brev(word);
-        } else { // cut short by the region edge or by the end of the ray
-          ka += m;
-          E += m * b_run;
-          break;
-        }
-      }
-      // bring the double position up to date (world.cc:868-877 did it step by step)
-      gx = seq_add(gx, (flags & kYMajor) ? kc : ka, (flags & kXNeg) != 0);
-      gy = seq_add(gy, (flags & kYMajor) ? ka : kc, (flags & kYNeg) != 0);
-      if (hit)
-        break;
-    } else {
-      // ---- empty region: jump to the next region boundary (world.cc:884-957) ----
-      if (need_crossings) {
-        need_crossings = false;
-        double regionx = (double)(ix0 / kRegionWidth * kRegionWidth);
-        double regiony = (double)(iy0 / kRegionWidth * kRegionWidth);
-        if ((gx < 0) && (ix0 % kRegionWidth))
-          regionx -= kRegionWidth;
-        if ((gy < 0) && (iy0 % kRegionWidth))
-          regiony -= kRegionWidth;
-        const double xdx = (flags & kXNeg) ? regionx - gx - 1.0 : regionx + kRegionWidth - gx;
-        const double xdy = xdx * tana;
-        const double ydy = (flags & kYNeg) ? regiony - gy - 1.0 : regiony + kRegionWidth - gy;
-        const double ydx = ydy / tana;
-        xcrossx = gx + xdx;
-        xcrossy = gy + xdy;
-        ycrossx = gx + ydx;
-        ycrossy = gy + ydy;
-        distX = fabs(xdx) + fabs(xdy);
-        distY = fabs(ydx) + fabs(ydy);
-      }
-      if (distX < distY) {
-        gx = xcrossx;
-        gy = xcrossy;
-        n = __double2int_rz((double)n - distX); // int -= double, world.cc:931
-        // xjumpx = sx*32, xjumpy = sx*32*tana (a power-of-two scaling, exact), world.cc:795-796
-        const double xjumpy = ((flags & kXNeg) ? -(double)kRegionWidth : (double)kRegionWidth) * tana;
-        xcrossx += (flags & kXNeg) ? -(double)kRegionWidth : (double)kRegionWidth;
-        xcrossy += xjumpy;
-        distY -= distX;
-        distX = (double)kRegionWidth + fabs(xjumpy); // xjumpdist, world.cc:801
-      } else {
-        gx = ycrossx;
-        gy = ycrossy;
-        n = __double2int_rz((double)n - distY);
-        ycrossx += yjumpx;
-        ycrossy += (flags & kYNeg) ? -(double)kRegionWidth : (double)kRegionWidth;
-        distX -= distY;
-        distY = fabs(yjumpx) + (double)kRegionWidth; // yjumpdist, world.cc:802
-      }
-    }
-  }
+  trace::RayResult r;
+  trace::trace_ray<kSteps>(g, fan, cosa, sina, r);
 
   // K3 (ranger epilogue, fused): model_ranger.cc:243-251 with zero noise
-  double range = fan->range;
-  if (hit) { // world.cc:856-859
-    // ax > ay  <=>  x-major with strictly more x than y  <=>  !ymajor && b_cross > b_run
-    if (!(flags & kYMajor) && b_cross > b_run)
-      range = fabs((gx - fan->ox * ppm) / trig_major) / ppm;
-    else
-      range = fabs((gy - fan->oy * ppm) / trig_major) / ppm;
-  }
   if (b.ranges)
-    b.ranges[beam] = range;
+    b.ranges[beam] = r.range;
   if (b.intensities)
-    b.intensities[beam] = hit_model >= 0 ? __ldg(g.mdl_ranger_return + hit_model) : 0.0;
+    b.intensities[beam] = r.hit_model >= 0 ? __ldg(g.mdl_ranger_return + r.hit_model) : 0.0;
   if (b.hit_model)
-    b.hit_model[beam] = hit_model;
+    b.hit_model[beam] = r.hit_model;
   if (b.hit_cell) {
-    b.hit_cell[2 * beam] = hit_x;
-    b.hit_cell[2 * beam + 1] = hit_y;
+    b.hit_cell[2 * beam] = r.hit_x;
+    b.hit_cell[2 * beam + 1] = r.hit_y;
   }
   if (kSteps) {
-    b.steps[2 * beam] = cell_visits;
-    b.steps[2 * beam + 1] = region_probes;
+    b.steps[2 * beam] = r.cell_visits;
+    b.steps[2 * beam + 1] = r.region_probes;
   }
 }
 

@@ -22,6 +22,23 @@ FAN_DTYPE = np.dtype([
     ("oa", "<f8"), ("range", "<f8"), ("fov", "<f8")])
 assert FAN_DTYPE.itemsize == 64
 
+# stg_rt_fid_target (72 B), stg_rt_fid_finder (104 B), stg_rt_fiducial (88 B)
+FID_TARGET_DTYPE = np.dtype([("model", "<u4"), ("fiducial_return", "<i4"), ("fiducial_key", "<i4"), ("reserved", "<u4"),
+                             ("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("a", "<f8"), ("sx", "<f8"), ("sy", "<f8"), ("sz", "<f8")])
+FID_FINDER_DTYPE = np.dtype([("finder", "<u4"), ("fiducial_key", "<i4"), ("ignore_zloc", "u1"), ("layer", "u1"), ("pad", "u1", (6,)),
+                             ("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("a", "<f8"), ("ox", "<f8"), ("oy", "<f8"), ("oz", "<f8"),
+                             ("oa", "<f8"), ("max_range_anon", "<f8"), ("max_range_id", "<f8"), ("fov", "<f8")])
+FIDUCIAL_DTYPE = np.dtype([("target", "<u4"), ("id", "<i4"), ("range", "<f8"), ("bearing", "<f8"), ("geom", "<f8", (4,)),
+                           ("pose", "<f8", (4,))])
+# stg_rt_blob_finder (72 B), stg_rt_blob (32 B)
+BLOB_FINDER_DTYPE = np.dtype([("finder", "<u4"), ("scan_width", "<u4"), ("scan_height", "<u4"), ("layer", "u1"), ("pad", "u1", (3,)),
+                              ("first_color", "<u4"), ("n_colors", "<u4"), ("ox", "<f8"), ("oy", "<f8"), ("oz", "<f8"),
+                              ("oa", "<f8"), ("range", "<f8"), ("fov", "<f8")])
+BLOB_DTYPE = np.dtype([("model", "<u4"), ("left", "<u4"), ("top", "<u4"), ("right", "<u4"), ("bottom", "<u4"), ("pad", "<u4"),
+                       ("range", "<f8")])
+assert (FID_TARGET_DTYPE.itemsize, FID_FINDER_DTYPE.itemsize, FIDUCIAL_DTYPE.itemsize) == (72, 104, 88)
+assert (BLOB_FINDER_DTYPE.itemsize, BLOB_DTYPE.itemsize) == (72, 32)
+
 
 class Config(ctypes.Structure):
     _fields_ = [("struct_size", ctypes.c_uint32), ("device", ctypes.c_int32), ("ppm", ctypes.c_double),
@@ -70,6 +87,8 @@ def lib():
         "stg_rt_block_unmap": (ctypes.c_int, [vp, u32, ctypes.c_int]),
         "stg_rt_blocks_remap": (ctypes.c_int, [vp, u32, vp, vp, ctypes.c_int, vp, vp, vp]),
         "stg_rt_fans_submit": (ctypes.c_int, [vp, u32, vp, vp, vp, ctypes.POINTER(FanOut)]),
+        "stg_rt_fiducials_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
+        "stg_rt_blobs_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
         "stg_rt_flush": (ctypes.c_int, [vp]),
         "stg_rt_sync": (ctypes.c_int, [vp]),
         "stg_rt_host_alloc": (vp, [vp, sz]),
@@ -101,7 +120,7 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "stg_rt_abi_version stg_rt_create stg_rt_destroy stg_rt_last_error stg_rt_model_upsert stg_rt_block_map "
-    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
+    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_blobs_submit stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
     "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times").split()
@@ -199,6 +218,30 @@ class Context:
         self._keep.append(out)
         self._check(self._L.stg_rt_fans_submit(self._h, len(fans), _ptr(fans), _ptr(headings), _ptr(trig),
                                                ctypes.byref(out.struct)))
+
+    def fiducials_submit(self, targets, finders, max_per_finder=16):
+        """-> (out[n_finders, max_per_finder] of FIDUCIAL_DTYPE, count[n_finders]); valid after sync()."""
+        targets = np.ascontiguousarray(targets, FID_TARGET_DTYPE)
+        finders = np.ascontiguousarray(finders, FID_FINDER_DTYPE)
+        out = np.zeros((len(finders), max_per_finder), FIDUCIAL_DTYPE)
+        cnt = np.zeros(len(finders), np.uint32)
+        self._keep.append((out, cnt))
+        self._check(self._L.stg_rt_fiducials_submit(self._h, len(targets), _ptr(targets), len(finders), _ptr(finders),
+                                                    max_per_finder, _ptr(out), _ptr(cnt)))
+        return out, cnt
+
+    def blobs_submit(self, finders, colors_rgb=None, max_per_finder=None):
+        """-> (out[n_finders, max_per_finder] of BLOB_DTYPE, count[n_finders]); valid after sync()."""
+        finders = np.ascontiguousarray(finders, BLOB_FINDER_DTYPE)
+        colors = np.zeros((0, 3)) if colors_rgb is None else np.ascontiguousarray(colors_rgb, np.float64).reshape(-1, 3)
+        if max_per_finder is None:
+            max_per_finder = int(finders["scan_width"].max())
+        out = np.zeros((len(finders), max_per_finder), BLOB_DTYPE)
+        cnt = np.zeros(len(finders), np.uint32)
+        self._keep.append((out, cnt))
+        self._check(self._L.stg_rt_blobs_submit(self._h, len(finders), _ptr(finders), len(colors),
+                                                _ptr(colors) if len(colors) else None, max_per_finder, _ptr(out), _ptr(cnt)))
+        return out, cnt
 
     def flush(self):
         self._check(self._L.stg_rt_flush(self._h))

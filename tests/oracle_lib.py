@@ -27,7 +27,8 @@ assert T1_RAY.itemsize == 48 and T1_HIT.itemsize == 32 and REF_RAY.itemsize == 4
 class ReplayStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in (
         "rays", "range_mismatch", "model_mismatch", "maps", "unmaps", "ticks", "cell_visits",
-        "region_probes", "scans", "scan_mismatch")] + [("max_range_err", ctypes.c_double)]
+        "region_probes", "scans", "scan_mismatch", "fiducial_updates", "fiducial_mismatch", "blob_updates",
+        "blob_mismatch")] + [("max_range_err", ctypes.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -188,6 +189,8 @@ def ref():
         L.ref_model_id.restype, L.ref_model_id.argtypes = ctypes.c_int32, [vp, ctypes.c_char_p]
         L.ref_model_pose.argtypes = [vp, ctypes.c_uint32, vp]
         L.ref_ranger_scan.argtypes = [vp, ctypes.c_uint32, ctypes.c_int, vp, vp, vp, ctypes.c_int]
+        L.ref_model_subscribe.argtypes = [vp, ctypes.c_char_p]
+        L.ref_fiducials_on_main_thread.argtypes = [ctypes.c_int]
         _ref = L
     return _ref
 
@@ -195,8 +198,10 @@ def ref():
 class RefWorld:
     """A live World of the unmodified reference. Never destroyed (the reference's ~World crashes)."""
 
-    def __init__(self, path=None, text=None, record=True):
+    def __init__(self, path=None, text=None, record=True, fiducials_on_main_thread=True):
         self.L = ref()
+        # on worker threads fiducial updates race with Move() (SURVEY.md 3.1): not reproducible
+        self.L.ref_fiducials_on_main_thread(1 if fiducials_on_main_thread else 0)
         if record:
             self.L.ref_trace_begin()
         if path is not None:
@@ -230,6 +235,9 @@ class RefWorld:
         cnt = np.zeros((max(nc.value, 1), 3), np.int64)
         self.L.ref_dump_grid(self.h, _p(rec), n, _p(cnt), nc.value, ctypes.byref(nc))
         return sort_grid(rec[:n]), sort_counts(cnt[:nc.value])
+
+    def subscribe(self, name):
+        assert self.L.ref_model_subscribe(self.h, name.encode()) == 0, name
 
     def model_id(self, name):
         return self.L.ref_model_id(self.h, name.encode())

@@ -69,6 +69,30 @@ def scan_to_fan(ev, sc):
     return fan
 
 
+def fid_records(ev, d):
+    """FIDUCIAL trace event -> (targets, finder) arrays for stg_rt_fiducials_submit"""
+    t = d["targets"]
+    targets = np.zeros(len(t), rt.FID_TARGET_DTYPE)
+    targets["model"], targets["fiducial_return"], targets["fiducial_key"] = t[:, 0], t[:, 1], t[:, 2]
+    for i, k in enumerate(("x", "y", "z", "a", "sx", "sy", "sz")):
+        targets[k] = t[:, 3 + i]
+    f = np.zeros(1, rt.FID_FINDER_DTYPE)
+    f["finder"], f["fiducial_key"], f["ignore_zloc"], f["layer"] = ev["model"], int(d["fiducial_key"]), int(d["ignore_zloc"]), ev["layer"]
+    for k in ("x", "y", "z", "a", "ox", "oy", "oz", "oa", "max_range_anon", "max_range_id", "fov"):
+        f[k] = d[k]
+    return targets, f
+
+
+def blob_records(ev, d):
+    f = np.zeros(1, rt.BLOB_FINDER_DTYPE)
+    f["finder"], f["layer"] = ev["model"], ev["layer"]
+    f["scan_width"], f["scan_height"] = int(d["scan_width"]), int(d["scan_height"])
+    f["first_color"], f["n_colors"] = 0, len(d["colors"])
+    for k in ("ox", "oy", "oz", "oa", "range", "fov"):
+        f[k] = d[k]
+    return f, d["colors"]
+
+
 class GpuReplay:
     """Results of pushing a whole trace through the C ABI."""
 
@@ -81,6 +105,8 @@ class GpuReplay:
         self.hit_cell = np.zeros((n, 2), np.int32)
         self.steps = np.zeros((n, 2), np.uint32)
         self.scans = []  # (event, Outputs)
+        self.fiducials = []  # (event, dict, out, count)
+        self.blobs = []
         pending = []
         ticks = 0
         for ev in trace.events:
@@ -107,6 +133,18 @@ class GpuReplay:
                     trig = oracle_lib.libm_trig(oracle_lib.ranger_headings(sc["origin"][3], sc["fov"], sc["n"]))
                 ctx.fans_submit(fan, out, trig=trig)
                 self.scans.append((ev, sc, out))
+            elif t == trace_io.EV_FIDUCIAL:
+                d = trace.fiducial(ev)
+                targets, f = fid_records(ev, d)
+                out, cnt = ctx.fiducials_submit(targets, f, max_per_finder=max(len(targets), 1))
+                ctx.sync()  # one fiducial batch in flight at a time
+                self.fiducials.append((ev, d, out[0, :cnt[0]].copy(), int(cnt[0])))
+            elif t == trace_io.EV_BLOB:
+                d = trace.blob(ev)
+                f, colors = blob_records(ev, d)
+                out, cnt = ctx.blobs_submit(f, colors)
+                ctx.sync()
+                self.blobs.append((ev, d, out[0, :cnt[0]].copy(), int(cnt[0])))
             elif t == trace_io.EV_TICK:
                 ticks += 1
                 if sync_every_tick:

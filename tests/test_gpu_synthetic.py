@@ -76,3 +76,23 @@ def test_synthetic_world_matches_oracle(seed, half):
     assert np.array_equal(bits(r.ranges), bits(d.ranges)) and np.array_equal(r.hit_model, d.hit_model)
     s.destroy()
     ctx.close()
+
+
+def test_full_baseline_size_matches_oracle():
+    """BASELINE config 3 at full size (8192^2 cells, 4096 rectangles, 1000 robots x 1080 beams): every
+    beam against the T1 oracle in strict-trig mode, including the step counters."""
+    w = worldgen.make_world(seed=1, n_rects=4096, n_robots=1000, half_extent_m=81.92)
+    ctx, t1 = build_both(w)
+    fans = worldgen.ranger_fans(w, layer=1, samples=1080, range_max=30.0)
+    rg, it, hits = t1_fans(t1, fans)
+    head = np.concatenate([oracle_lib.ranger_headings(f["oa"], f["fov"], int(f["n_samples"])) for f in fans])
+    g = ctx.trace(fans, trig=oracle_lib.libm_trig(head))
+    bad = np.nonzero((g.hit_model != hits["hit_model"]) | (bits(g.ranges) != bits(rg)) |
+                     (g.steps[:, 0] != hits["cell_visits"]) | (g.steps[:, 1] != hits["region_probes"]))[0]
+    for i in bad[:5]:
+        f = fans[i // 1080]
+        print("mismatch beam", i, "t", i % 1080, "origin", f["ox"], f["oy"], "heading %.17g" % head[i],
+              "gpu", g.ranges[i], g.hit_model[i], g.hit_cell[i], g.steps[i], "oracle", hits[i])
+    assert len(bad) == 0, "%d of %d beams differ" % (len(bad), len(rg))
+    assert np.array_equal(bits(g.intensities), bits(it))
+    ctx.close()

@@ -14,7 +14,7 @@ import replay
 import trace_io
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-TRACES = ["simple_120", "fasr_300"]
+TRACES = ["simple_120", "fasr_300", "lsp_test_20"]
 
 
 @pytest.fixture(scope="module", params=TRACES)
@@ -29,12 +29,40 @@ def raw_trace(request, tmp_path_factory):
 def test_t1_reproduces_every_reference_ray(raw_trace):
     name, path = raw_trace
     st, _ = oracle_lib.t1_replay(path)
-    assert st["rays"] > 30000 and st["ticks"] >= 120
+    assert st["rays"] > (30000 if name != "lsp_test_20" else 3000) and st["ticks"] >= 20
     assert st["model_mismatch"] == 0
     # bit-exact on a host with the libm the traces were recorded with; never worse than an ulp or so
     assert st["max_range_err"] <= 1e-12, st
     assert st["range_mismatch"] == 0 or os.environ.get("STG_FOREIGN_LIBM"), st
-    assert st["scans"] > 0 and (st["scan_mismatch"] == 0 or os.environ.get("STG_FOREIGN_LIBM")), st
+    assert st["scan_mismatch"] == 0 or os.environ.get("STG_FOREIGN_LIBM"), st
+    assert st["fiducial_mismatch"] == 0 and st["blob_mismatch"] == 0, st
+    if name == "simple_120":
+        assert st["scans"] == 240
+    if name == "fasr_300":
+        assert st["scans"] > 1000 and st["fiducial_updates"] > 1000
+    if name == "lsp_test_20":
+        assert st["fiducial_updates"] == 40 and st["blob_updates"] == 40
+
+
+def test_reference_known_answers_lsp_test():
+    """The only answers the reference's own tests pin for this path (libstageplugin/test/
+    lsp_test_fiducial.cc:36-60, lsp_test_blobfinder.cc:19-59), restated at libstage level: r0's
+    fiducial finder sees exactly one fiducial, r1, with id 2; its 80x60 blobfinder sees three blobs
+    (wall, robot, wall), the middle one red and nearer."""
+    tr = trace_io.load(os.path.join(GOLDEN, "lsp_test_20.trc.xz"))
+    names = {int(m["id"]): m for m in tr.models}
+    fid = [tr.fiducial(e) for e in tr.events if e["type"] == trace_io.EV_FIDUCIAL]
+    r0 = [f for f in fid if len(f["found"]) and f["found"][0, 1] == 2]
+    assert len(r0) == 20
+    for f in r0:
+        assert len(f["found"]) == 1 and f["found"][0, 1] == 2 and names[int(f["found"][0, 0])]["fiducial_return"] == 2
+    blobs = [tr.blob(e) for e in tr.events if e["type"] == trace_io.EV_BLOB]
+    three = [b for b in blobs if len(b["blobs"]) == 3]
+    assert len(three) >= 20
+    b = three[0]
+    assert b["scan_width"] == 80 and b["scan_height"] == 60
+    mid = b["blobs"][1]
+    assert tuple(mid[:3]) == (1.0, 0.0, 0.0) and mid[7] < b["blobs"][0][7] and mid[7] < b["blobs"][2][7]
 
 
 def test_python_replay_matches_c_replay(raw_trace):

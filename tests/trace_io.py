@@ -5,8 +5,8 @@ import lzma
 
 import numpy as np
 
-MAGIC = b"STGTRC03"
-EV_MAP, EV_UNMAP, EV_RAYS, EV_TICK, EV_RANGER_SCAN = 1, 2, 3, 4, 5
+MAGIC = b"STGTRC04"
+EV_MAP, EV_UNMAP, EV_RAYS, EV_TICK, EV_RANGER_SCAN, EV_FIDUCIAL, EV_BLOB = 1, 2, 3, 4, 5, 6, 7
 SCAN_HEADER_DOUBLES = 6
 KIND_RANGER, KIND_UNRELATED, KIND_GRIPPER = 0, 1, 2
 
@@ -35,6 +35,26 @@ class Trace:
         h = SCAN_HEADER_DOUBLES
         return dict(origin=a[0:4], range_max=float(a[4]), fov=float(a[5]), n=n, ranges=a[h:h + n],
                     intensities=a[h + n:h + 2 * n], bearings=a[h + 2 * n:h + 3 * n])
+
+    def fiducial(self, ev):
+        """FIDUCIAL event -> dict(finder header fields, targets[n,10], found[m,12])."""
+        a = self.aux[ev["first"]:]
+        nt, nf = int(a[13]), int(ev["block"])
+        keys = ("x y z a ox oy oz oa max_range_anon max_range_id fov fiducial_key ignore_zloc").split()
+        d = {k: float(a[i]) for i, k in enumerate(keys)}
+        d["targets"] = a[14:14 + 10 * nt].reshape(nt, 10)
+        d["found"] = a[14 + 10 * nt:14 + 10 * nt + 12 * nf].reshape(nf, 12)
+        return d
+
+    def blob(self, ev):
+        """BLOB event -> dict(header fields, colors[n,3], blobs[m,8])."""
+        a = self.aux[ev["first"]:]
+        nc, nb = int(a[8]), int(ev["block"])
+        keys = "ox oy oz oa range fov scan_width scan_height".split()
+        d = {k: float(a[i]) for i, k in enumerate(keys)}
+        d["colors"] = a[9:9 + 3 * nc].reshape(nc, 3)
+        d["blobs"] = a[9 + 3 * nc:9 + 3 * nc + 8 * nb].reshape(nb, 8)
+        return d
 
     def polygon(self, ev):
         """(n_pts, 2) int32 pixel-space vertices of a MAP event."""
