@@ -205,17 +205,10 @@ def run_reference(args):
 # this repo's path
 # ---------------------------------------------------------------------------------------------
 
-class CudaArray:
-    """zero-copy view of a raw device pointer for torch.as_tensor"""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from stage_b200 import rt, worldgen
+    from stage_b200 import multi, rt, worldgen
 
     n_gpus = args.gpus
     rank = int(os.environ.get("RANK", "0"))
@@ -241,7 +234,7 @@ def run_ours(args):
     ctx.set_stream(stream.cuda_stream)
     worldgen.load_into_context(ctx, world)
 
-    lo, hi = rank * args.robots, (rank + 1) * args.robots
+    lo, hi = multi.shard_bounds(args.robots * n_gpus, rank, n_gpus)
     my_ids = world.robot_ids[lo:hi]
     my_blocks = (len(world.obstacles) + np.arange(lo, hi)).astype(np.uint32)
     n_beams = args.robots * SAMPLES
@@ -316,16 +309,12 @@ def run_ours(args):
             "fans": worldgen.ranger_fans(world, layer=(t + 1) % 2, fov_deg=FOV_DEG, samples=SAMPLES, range_max=RANGE_MAX,
                                          robots=poses[t], robot_ids=my_ids),
         })
-    slot = ctx.delta_slot_bytes()
-    gathered = torch.empty(slot * n_gpus, dtype=torch.uint8, device="cuda") if n_gpus > 1 else None
+    exchange = multi.DeltaExchange(ctx, rank, n_gpus, dist=dist) if n_gpus > 1 else None
 
     def tick(tk):
         ctx.blocks_remap(my_blocks, my_ids, tk["layer_w"], tk["z"], tk["first"], tk["xy"])
-        if n_gpus > 1:
-            ptr, nbytes = ctx.delta_export(rank)
-            mine = torch.as_tensor(CudaArray(ptr, slot), device="cuda")
-            dist.all_gather_into_tensor(gathered, mine)
-            ctx.delta_apply_gathered(gathered.data_ptr(), n_gpus, slot)
+        if exchange is not None:  # all-gather the moved-block deltas, apply all ranks' in rank order
+            exchange.step()
         ctx.fans_submit(tk["fans"], out)
         ctx.sync()
 
