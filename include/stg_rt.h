@@ -312,6 +312,11 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *ctx, const void *dev_gathered, int n
 int stg_rt_set_stream(stg_rt_ctx *ctx, void *cuda_stream);
 void *stg_rt_get_stream(stg_rt_ctx *ctx);
 
+/* Diagnostics: (cos, sin) of n headings exactly as the ray march computes them on the device
+   (World::Raytrace's zero-heading substitution included, world.cc:773-775). cos_sin = 2n doubles.
+   Synchronous. Used to check the device trig against the host C library. */
+int stg_rt_debug_trig(stg_rt_ctx *ctx, uint64_t n, const double *headings, double *cos_sin);
+
 /* Counters since create: kernel launches by kind, rays traced, bytes copied each way. */
 typedef struct {
   uint64_t launches_rasterise, launches_march, launches_post, launches_other;

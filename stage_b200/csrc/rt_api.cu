@@ -89,6 +89,7 @@ struct stg_rt_ctx {
   std::vector<uint32_t> models_changed;  // models whose root / visibility changed while blocks are mapped
   uint64_t epoch = 0;
   uint32_t local_seq = 0;
+  int last_export_rank = -1; // multi-GPU: this context's rank, learnt from stg_rt_delta_export
   int64_t live_entries[2] = { 0, 0 }; // cell visits currently rendered, per layer
   int64_t used_upper[2] = { 0, 0 };   // upper bound of non-empty slots (entries + tombstones)
 
@@ -296,21 +297,21 @@ void sort_units(stg_rt_ctx *c)
   });
 }
 
-// Keep probe chains short: tombstones never turn back into empty slots on their own, so once the
-// upper bound of non-empty slots would pass 3/4 of the table, re-insert the live entries into the
-// spare table and swap.
+// Keep probe chains short: tombstones never turn back into empty slots on their own, so when the
+// upper bound of non-empty slots (entries + tombstones) would pass 3/4 of the table, re-insert the
+// live entries into the spare table and swap. Runs between the removal and the insertion phase of a
+// blob, when the table holds exactly live_after - add[L] entries (live_entries is already updated).
 int ensure_table_room(stg_rt_ctx *c, const int64_t add[2])
 {
   for (int L = 0; L < 2; L++) {
-    if (c->used_upper[L] + add[L] <= (int64_t)c->slot_cap * 3 / 4)
-      continue;
-    CU(c, cudaMemsetAsync(c->spare_slots, 0, (size_t)c->slot_cap * 8, c->stream));
-    launch_rehash(c->g.slots[L], c->spare_slots, c->g.slot_mask, c->stream);
-    c->stats.launches_other++;
-    std::swap(c->g.slots[L], c->spare_slots);
-    c->used_upper[L] = c->live_entries[L];
-    if (c->used_upper[L] + add[L] > (int64_t)c->slot_cap * 3 / 4)
-      return fail(c, STG_RT_ENOMEM, "cell-entry table of layer %d too small (%u slots); raise max_cell_entries", L, c->slot_cap);
+    if (c->used_upper[L] + add[L] > (int64_t)c->slot_cap * 3 / 4) {
+      CU(c, cudaMemsetAsync(c->spare_slots, 0, (size_t)c->slot_cap * 8, c->stream));
+      launch_rehash(c->g.slots[L], c->spare_slots, c->g.slot_mask, c->stream);
+      c->stats.launches_other++;
+      std::swap(c->g.slots[L], c->spare_slots);
+      c->used_upper[L] = c->live_entries[L] - add[L];
+    }
+    c->used_upper[L] += add[L];
   }
   return 0;
 }
@@ -328,6 +329,7 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
     BlobBuild bb;
     uint32_t rem_cursor = 0, ins_cursor = 0;
     const size_t n_model = first_round ? c->model_upd.size() : 0;
+    int64_t ins_round[2] = { 0, 0 };
     if (first_round && !c->models_changed.empty()) {
       for (uint32_t bi = 0; bi < c->blocks.size(); bi++) {
         const BlockShadow &b = c->blocks[bi];
@@ -391,12 +393,8 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
         if (c->live_entries[L] + bb.d_live[L] > (int64_t)c->slot_cap / 2)
           return fail(c, STG_RT_ENOMEM, "cell-entry table of layer %d full (%lld entries, capacity %u/2); raise max_cell_entries",
                       L, (long long)(c->live_entries[L] + bb.d_live[L]), c->slot_cap);
-      // live entries grow by the net change, used slots (entries + tombstones) by every insertion
-      int rc = ensure_table_room(c, ins_per_layer);
-      if (rc)
-        return rc;
-      for (int L = 0; L < 2; L++)
-        c->used_upper[L] += ins_per_layer[L];
+      ins_round[0] = ins_per_layer[0];
+      ins_round[1] = ins_per_layer[1];
     }
     CU(c, cudaEventSynchronize(c->blob_uploaded));
     const std::vector<ModelUpd> no_models;
@@ -410,7 +408,12 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
     if (apply) {
       c->epoch++;
       CU(c, cudaEventRecord(c->t_ev[0][0], c->stream));
-      launch_apply_deltas(c->g, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, c->stream,
+      launch_apply_deltas(c->g, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, 0, c->stream,
+                          &c->stats.launches_rasterise);
+      int rc = ensure_table_room(c, ins_round); // live entries grew by the net change, used slots by every insertion
+      if (rc)
+        return rc;
+      launch_apply_deltas(c->g, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, 1, c->stream,
                           &c->stats.launches_rasterise);
       CU(c, cudaEventRecord(c->t_ev[0][1], c->stream));
       c->t_rec[0] = true;
@@ -1230,6 +1233,7 @@ int stg_rt_delta_export(stg_rt_ctx *c, int rank, void **dev_blob, size_t *n_byte
   int rc = launch_fans_locked(c); // fans queued so far see the grid before these deltas
   if (rc)
     return rc;
+  c->last_export_rank = rank;
   // the entry accounting of exported deltas happens here for this rank's own share
   if ((rc = build_and_send_deltas(c, false, rank, n_bytes)))
     return rc;
@@ -1253,15 +1257,23 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_r
   int64_t ins = 0;
   for (const DeltaHeader &h : hdrs)
     ins += h.steps_insert;
-  // layers are not split in the headers: charge both (upper bound)
-  const int64_t add[2] = { ins, ins };
-  if ((rc = ensure_table_room(c, add)))
-    return rc;
+  // the other ranks' entries: the headers do not split layers, so charge both (upper bound)
+  int64_t other_ins = 0, other_rem = 0;
+  for (int r = 0; r < n_ranks; r++)
+    if ((int)hdrs[r].rank != c->last_export_rank) {
+      other_ins += hdrs[r].steps_insert;
+      other_rem += hdrs[r].steps_remove;
+    }
   for (int L = 0; L < 2; L++)
-    c->used_upper[L] += ins;
+    c->live_entries[L] += std::max<int64_t>(other_ins - other_rem, 0);
+  const int64_t add[2] = { ins, ins };
   c->epoch++;
   CU(c, cudaEventRecord(c->t_ev[0][0], c->stream));
-  launch_apply_deltas(c->g, (const unsigned char *)dev_gathered, n_ranks, slot_bytes, c->epoch, c->stream,
+  launch_apply_deltas(c->g, (const unsigned char *)dev_gathered, n_ranks, slot_bytes, c->epoch, 0, c->stream,
+                      &c->stats.launches_rasterise);
+  if ((rc = ensure_table_room(c, add)))
+    return rc;
+  launch_apply_deltas(c->g, (const unsigned char *)dev_gathered, n_ranks, slot_bytes, c->epoch, 1, c->stream,
                       &c->stats.launches_rasterise);
   CU(c, cudaEventRecord(c->t_ev[0][1], c->stream));
   c->t_rec[0] = true;
@@ -1467,6 +1479,33 @@ int stg_rt_set_stream(stg_rt_ctx *c, void *cuda_stream)
 }
 
 void *stg_rt_get_stream(stg_rt_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int stg_rt_debug_trig(stg_rt_ctx *c, uint64_t n, const double *headings, double *cos_sin)
+{
+  if (!c || (n && (!headings || !cos_sin)))
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  DevBuf dx, dcs;
+  int rc = dev_reserve(c, dx, n * 8 + 8);
+  if (!rc)
+    rc = dev_reserve(c, dcs, n * 16 + 16);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(dx.p, headings, n * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+      launch_debug_trig(n, (const double *)dx.p, (double *)dcs.p, c->stream);
+      e = cudaMemcpyAsync(cos_sin, dcs.p, n * 16, cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (e == cudaSuccess)
+      e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess)
+      rc = fail(c, STG_RT_ECUDA, "debug_trig: %s", cudaGetErrorString(e));
+  }
+  if (dx.p)
+    cudaFree(dx.p);
+  if (dcs.p)
+    cudaFree(dcs.p);
+  return rc;
+}
 
 int stg_rt_kernel_times(stg_rt_ctx *c, float ms[3])
 {

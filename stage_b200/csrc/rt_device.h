@@ -189,10 +189,11 @@ struct BlobBatchView {
 
 void launch_fiducials(const GridView &g, const FidBatchView &b, void *stream);
 void launch_blobs(const GridView &g, const BlobBatchView &b, void *stream);
+void launch_debug_trig(uint64_t n, const double *x, double *cs, void *stream);
 
 // launch wrappers implemented in rt_kernels.cu; all asynchronous on `stream`
 void launch_apply_deltas(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
-                         unsigned long long epoch, void *stream, uint64_t *launch_counter);
+                         unsigned long long epoch, int phase, void *stream, uint64_t *launch_counter);
 void launch_fan_headings(const FanBatchView &b, void *stream);
 void launch_ray_march(const GridView &g, const FanBatchView &b, void *stream);
 

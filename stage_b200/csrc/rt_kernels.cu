@@ -260,17 +260,24 @@ static int delta_grid_blocks()
   return blocks;
 }
 
+// phase 0: table updates, removals, mask fix-up.  phase 1: insertions. The host may compact the
+// cell-entry table between the two (every tombstone of phase 0 is reclaimed before new entries land).
 void launch_apply_deltas(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
-                         unsigned long long epoch, void *stream, uint64_t *launch_counter)
+                         unsigned long long epoch, int phase, void *stream, uint64_t *launch_counter)
 {
   cudaStream_t s = (cudaStream_t)stream;
   const int blocks = delta_grid_blocks();
-  k1_table_updates<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes, epoch);
-  k1_remove<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes);
-  k1_fixup<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes);
-  k1_insert<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes);
-  if (launch_counter)
-    *launch_counter += 4;
+  if (phase == 0) {
+    k1_table_updates<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes, epoch);
+    k1_remove<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes);
+    k1_fixup<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes);
+    if (launch_counter)
+      *launch_counter += 3;
+  } else {
+    k1_insert<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes);
+    if (launch_counter)
+      *launch_counter += 1;
+  }
 }
 
 void launch_rehash(const unsigned long long *src, unsigned long long *dst, uint32_t slot_mask, void *stream)

@@ -157,7 +157,21 @@ __global__ void __launch_bounds__(64) k3_blobs(GridView g, BlobBatchView b)
   b.out_count[f] = n_out;
 }
 
+// diagnostics: the device's cos / sin of arbitrary headings (tests/test_gpu_trig.py)
+__global__ void __launch_bounds__(256) k_debug_trig(uint64_t n, const double *x, double *cs)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    trace::heading_trig(x[i], cs[2 * i], cs[2 * i + 1]);
+}
+
 } // namespace
+
+void launch_debug_trig(uint64_t n, const double *x, double *cs, void *stream)
+{
+  if (n)
+    k_debug_trig<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, x, cs);
+}
 
 void launch_fiducials(const GridView &g, const FidBatchView &b, void *stream)
 {

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "rt_device.h"
+#include "rt_libm.cuh"
 
 namespace stg {
 namespace trace {
@@ -277,12 +278,18 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
   res.region_probes = region_probes;
 }
 
-// cos / sin of a heading as World::Raytrace takes them (world.cc:773-775)
+// cos / sin of a heading as World::Raytrace takes them (world.cc:773-775): the host C library's
+// values, bit for bit (rt_libm.cuh), because the traversal is chaotic in their last bit.
 __device__ __forceinline__ void heading_trig(double heading, double &cosa, double &sina)
 {
   const double ang = heading == 0.0 ? 1e-12 : heading;
-  sina = sin(ang);
-  cosa = cos(ang);
+  if (libm::covered(ang)) {
+    sina = libm::sin_host_exact(ang);
+    cosa = libm::cos_host_exact(ang);
+  } else { // |heading| > 1e8 or not finite: no sensor produces this
+    sina = sin(ang);
+    cosa = cos(ang);
+  }
 }
 
 } // namespace trace

@@ -108,6 +108,7 @@ def lib():
         "stg_rt_get_stream": (vp, [vp]),
         "stg_rt_get_stats": (ctypes.c_int, [vp, ctypes.POINTER(Stats)]),
         "stg_rt_kernel_times": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_float * 3)]),
+        "stg_rt_debug_trig": (ctypes.c_int, [vp, u64, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)  # AttributeError if the library does not export what the header declares
@@ -123,7 +124,7 @@ EXPORTED_SYMBOLS = (
     "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_blobs_submit stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
-    "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times").split()
+    "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_debug_trig").split()
 
 
 def _ptr(a):
@@ -294,6 +295,13 @@ class Context:
         ms = (ctypes.c_float * 3)()
         self._check(self._L.stg_rt_kernel_times(self._h, ctypes.byref(ms)))
         return {"deltas_ms": ms[0], "headings_ms": ms[1], "march_ms": ms[2]}
+
+    def debug_trig(self, headings):
+        """(n, 2) array of the device's (cos, sin) for the given headings"""
+        h = np.ascontiguousarray(headings, np.float64)
+        out = np.empty((len(h), 2), np.float64)
+        self._check(self._L.stg_rt_debug_trig(self._h, len(h), _ptr(h), _ptr(out)))
+        return out
 
     # ---- multi-GPU deltas / plumbing
     def delta_slot_bytes(self):

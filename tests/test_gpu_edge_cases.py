@@ -1,0 +1,234 @@
+"""Edge cases of the path through the C ABI, each against the T1 oracle: the reference's quirks
+(truncation toward zero around the world axes, zero heading, stale layers, multi-block cells, z test,
+predicates), API error behaviour, and the moving-block stress of BASELINE config 5 in miniature."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from stage_b200 import rt
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+class Pair:
+    """the same calls into the GPU context and the oracle"""
+
+    def __init__(self, ppm=50.0, sregs=(-1, -1, 2, 2), **kw):
+        self.ctx = rt.Context(ppm, *sregs, max_models=64, max_blocks=kw.pop("max_blocks", 4096), max_cell_entries=kw.pop("entries", 1 << 18), **kw)
+        self.t1 = oracle_lib.T1World(ppm)
+
+    def model(self, mid, root, ranger_return=1.0, flags=rt.VIS_OBSTACLE_RETURN):
+        self.ctx.model_upsert(mid, root, ranger_return, 0, 0, flags)
+        self.t1.model_upsert(mid, root, ranger_return, 0, 0, flags)
+
+    def map(self, block, model, layer, z, xy):
+        self.ctx.block_map(block, model, layer, z[0], z[1], xy)
+        self.t1.block_map(block, model, layer, z[0], z[1], xy)
+
+    def unmap(self, block, layer):
+        self.ctx.block_unmap(block, layer)
+        self.t1.block_unmap(block, layer)
+
+    def rays(self, finder, origins, headings, rng, pred=rt.PRED_RANGER, ztest=1, layer=0, z=0.5):
+        n = len(headings)
+        origins = np.broadcast_to(np.asarray(origins, np.float64), (n, 2))
+        fans = rt.make_fans(n)
+        fans["finder"], fans["n_samples"], fans["pred"], fans["ztest"], fans["layer"] = finder, 1, pred, ztest, layer
+        fans["angles"], fans["first_heading"] = rt.ANGLES_EXPLICIT, np.arange(n)
+        fans["ox"], fans["oy"], fans["oz"], fans["oa"], fans["range"] = origins[:, 0], origins[:, 1], z, headings, rng
+        g = self.ctx.trace(fans, headings=headings, trig=oracle_lib.libm_trig(headings))
+        r = np.zeros(n, oracle_lib.T1_RAY)
+        r["ox"], r["oy"], r["oz"], r["oa"], r["range"] = origins[:, 0], origins[:, 1], z, headings, rng
+        r["finder"], r["kind"], r["ztest"], r["layer"] = finder, pred, ztest, layer
+        o = self.t1.raytrace(r)
+        assert np.array_equal(g.hit_model, o["hit_model"])
+        assert np.array_equal(bits(g.ranges), bits(o["range"]))
+        h = g.hit_model >= 0
+        assert np.array_equal(g.hit_cell[h, 0], o["hit_x"][h]) and np.array_equal(g.hit_cell[h, 1], o["hit_y"][h])
+        assert np.array_equal(g.steps[:, 0], o["cell_visits"]) and np.array_equal(g.steps[:, 1], o["region_probes"])
+        return g, o
+
+    def grids_equal(self):
+        rec_g, cnt_g = self.ctx.grid_dump()
+        rec_o, cnt_o = self.t1.dump_grid()
+        assert np.array_equal(oracle_lib.sort_grid(rec_g), rec_o)
+        assert np.array_equal(oracle_lib.sort_counts(cnt_g), cnt_o)
+
+
+def box(x0, y0, x1, y1):
+    return np.array([[x0, y0], [x1, y0], [x1, y1], [x0, y1]], np.int32)
+
+
+def test_boxes_in_all_four_quadrants_and_the_truncation_alias():
+    """A 1 m box at (+-5, +-5) m and rays that start 5 mm outside its wall, inside the populated
+    region: double->int truncates toward zero while MapPoly floors, so the answers differ by quadrant
+    (hard part 1). Plus fans of rays from the origin region and axis-aligned headings."""
+    p = Pair()
+    p.model(1, 1)
+    p.model(2, 2)
+    k = 0
+    for sx in (-1, 1):
+        for sy in (-1, 1):
+            cx, cy = sx * 250, sy * 250
+            for layer in (0, 1):
+                p.map(k, 1, layer, (0.0, 1.0), box(cx - 25, cy - 25, cx + 25, cy + 25))
+            k += 1
+    heads = np.array([0.0, np.pi, np.pi / 2, -np.pi / 2, 1e-12, np.pi / 4, -3 * np.pi / 4, 3.0, -0.1])
+    seen = set()
+    for sx in (-1, 1):
+        for sy in (-1, 1):
+            for dx, dy, a in ((0.505, 0.0, np.pi), (-0.505, 0.0, 0.0), (0.0, 0.505, -np.pi / 2), (0.0, -0.505, np.pi / 2)):
+                g, _ = p.rays(2, [sx * 5 + dx, sy * 5 + dy], np.array([a]), 2.0)
+                seen.add(round(float(g.ranges[0]), 3))
+            p.rays(2, [sx * 0.3, sy * 0.3], heads, 12.0)
+            p.rays(2, [sx * 5.0, sy * 5.0], heads, 12.0)        # origin inside the box, on integer coordinates
+    assert len(seen) >= 2  # the alias really shows
+    p.rays(2, [0.0, 0.0], np.linspace(-np.pi, np.pi, 721), 15.0)  # through the axes' empty regions
+    p.rays(2, [30.0, 30.0], heads, 5.0)                          # outside the device extent altogether
+    p.rays(2, [9.0, 9.0], np.array([np.pi / 4]), 30.0)           # leaves the extent
+    p.rays(2, [1.0, 1.0], heads, 0.0)                            # zero range
+    p.rays(2, [1.0, 1.0], heads, 0.019)                          # shorter than a cell
+    p.ctx.close()
+
+
+def test_multi_block_cells_order_ztest_predicates_and_attribute_changes():
+    p = Pair()
+    p.model(1, 1, 0.5)                       # wall A
+    p.model(2, 2, 0.7)                       # wall B, same cells, mapped later
+    p.model(3, 3, -1.0)                      # invisible to rangers
+    p.model(4, 4, 1.0, rt.VIS_GRIPPER_RETURN)
+    p.model(5, 5)                            # finder, own tree
+    p.model(6, 5)                            # finder's child (related)
+    wall = box(100, -50, 104, 50)
+    p.map(0, 1, 0, (0.0, 0.4), wall)         # low wall
+    p.map(1, 2, 0, (0.0, 1.0), wall)         # tall wall in the very same cells
+    p.map(2, 3, 0, (0.0, 1.0), box(50, -50, 54, 50))    # ranger-invisible screen in front
+    p.map(3, 4, 0, (0.0, 1.0), box(150, -50, 154, 50))  # gripper-visible post behind
+    p.map(4, 6, 0, (0.0, 1.0), box(20, -50, 24, 50))    # the finder's own child in front of everything
+    heads = np.linspace(-0.3, 0.3, 61)
+    g, _ = p.rays(5, [0.1, 0.1], heads, 5.0, z=0.2)      # both walls pass z: first mapped (A) wins
+    assert set(g.hit_model) == {1}
+    g, _ = p.rays(5, [0.1, 0.1], heads, 5.0, z=0.8)      # only B passes z
+    assert set(g.hit_model) == {2}
+    g, _ = p.rays(5, [0.1, 0.1], heads, 5.0, z=2.0, ztest=0)
+    assert set(g.hit_model) == {1}
+    g, _ = p.rays(5, [0.1, 0.1], heads, 5.0, z=2.0)      # above everything
+    assert set(g.hit_model) == {-1}
+    g, _ = p.rays(5, [0.1, 0.1], heads, 5.0, pred=rt.PRED_UNRELATED)   # sees the ranger-invisible screen
+    assert set(g.hit_model) == {3}
+    g, _ = p.rays(5, [0.1, 0.1], heads, 5.0, pred=rt.PRED_GRIPPER)
+    assert set(g.hit_model) == {4}
+    # re-map A: it now comes after B in every shared cell
+    p.unmap(0, 0)
+    p.map(0, 1, 0, (0.0, 1.0), wall)
+    g, _ = p.rays(5, [0.1, 0.1], heads, 5.0, z=0.2)
+    assert set(g.hit_model) == {2}
+    # the child leaves the finder's tree: now it blocks
+    p.model(6, 6)
+    g, _ = p.rays(5, [0.1, 0.1], heads, 5.0)
+    assert set(g.hit_model) == {6}
+    # the screen becomes visible to rangers
+    p.model(6, 5)
+    p.model(3, 3, 0.2)
+    g, _ = p.rays(5, [0.1, 0.1], heads, 5.0)
+    assert set(g.hit_model) == {3} and np.all(g.intensities == 0.2)
+    # layer 1 is empty: the populated-region walk still happens (Region::count spans both layers)
+    g, o = p.rays(5, [0.1, 0.1], heads, 5.0, layer=1)
+    assert set(g.hit_model) == {-1} and o["cell_visits"].min() > 100
+    p.grids_equal()
+    p.ctx.close()
+
+
+def test_api_errors_and_empty_calls():
+    p = Pair()
+    p.model(1, 1)
+    with pytest.raises(rt.StgRtError) as e:
+        p.ctx.block_map(0, 9, 0, 0, 1, box(0, 0, 5, 5))          # unknown model
+    assert e.value.code == -1
+    p.ctx.block_map(0, 1, 0, 0, 1, box(0, 0, 5, 5))
+    with pytest.raises(rt.StgRtError) as e:
+        p.ctx.block_map(0, 1, 0, 0, 1, box(0, 0, 5, 5))          # already mapped on this layer
+    assert e.value.code == -5
+    with pytest.raises(rt.StgRtError) as e:
+        p.ctx.block_map(1, 1, 0, 0, 1, box(0, 0, 5000, 5))       # leaves the extent
+    assert e.value.code == -4
+    with pytest.raises(rt.StgRtError) as e:
+        p.ctx.block_map(99999, 1, 0, 0, 1, box(0, 0, 5, 5))      # beyond max_blocks
+    assert e.value.code == -3
+    p.ctx.block_unmap(7, 1)                                       # unmapping what is not mapped: no-op
+    fans = rt.make_fans(1)
+    fans["finder"] = 33                                           # unknown finder
+    with pytest.raises(rt.StgRtError):
+        p.ctx.trace(fans)
+    out = p.ctx.trace(rt.make_fans(0))                            # empty submit
+    assert len(out.ranges) == 0
+    fans = rt.make_fans(2)                                        # a fan with zero samples next to a real one
+    fans["finder"], fans["n_samples"], fans["range"], fans["fov"] = 1, (0, 5), 3.0, 1.0
+    out = p.ctx.trace(fans)
+    assert len(out.ranges) == 5
+    p.ctx.sync()
+    p.ctx.close()
+
+
+def test_moving_blocks_stress_with_table_compaction():
+    """BASELINE config 5 in miniature: 1500 pucks re-rasterised every tick on alternating layers for
+    40 ticks, with a cell-entry table small enough that tombstone compaction (k1_rehash) must run;
+    the device grid stays equal to the oracle's, and rays agree, all along."""
+    p = Pair(entries=1 << 15, max_blocks=2048)
+    p.model(1, 1)
+    p.model(2, 2)
+    rng = np.random.RandomState(3)
+    n = 1500
+    pos = rng.randint(-900, 900, size=(n, 2))
+    for layer in (0, 1):
+        for b in range(n):
+            p.map(b, 1, layer, (0.0, 1.0), box(pos[b, 0], pos[b, 1], pos[b, 0] + 5, pos[b, 1] + 5))
+    p.grids_equal()
+    launches0 = p.ctx.stats()["launches_other"]
+    for tick in range(1, 41):
+        layer = tick % 2
+        pos = np.clip(pos + rng.randint(-6, 7, size=(n, 2)), -1000, 1000)
+        blocks = np.arange(n, dtype=np.uint32)
+        xy = np.concatenate([box(x, y, x + 5, y + 5) for x, y in pos], 0)
+        p.ctx.blocks_remap(blocks, np.full(n, 1, np.uint32), layer, np.tile([0.0, 1.0], (n, 1)),
+                           np.arange(n + 1, dtype=np.uint32) * 4, xy)
+        for b in range(n):
+            p.t1.block_unmap(b, layer)
+            p.t1.block_map(b, 1, layer, 0.0, 1.0, xy[4 * b:4 * b + 4])
+        if tick % 8 == 0:
+            p.grids_equal()
+            p.rays(2, [0.05, 0.07], np.linspace(-np.pi, np.pi, 400), 18.0, layer=(tick + 1) % 2)
+    assert p.ctx.stats()["launches_other"] > launches0  # compaction really ran
+    p.grids_equal()
+    p.ctx.close()
+
+
+def test_single_beam_sonar_fans():
+    """BASELINE config 4's ray shape: thousands of one-beam ranger sensors (sample_count 1 ->
+    start_angle 0, heading = (double)(float)origin.a)."""
+    p = Pair()
+    p.model(1, 1, 0.5)
+    p.model(2, 2)
+    rng = np.random.RandomState(8)
+    for b in range(300):
+        x, y = rng.randint(-950, 930, 2)
+        w, h = rng.randint(3, 60, 2)
+        p.map(b, 1, 1, (0.0, 1.0), box(x, y, min(x + w, 1000), min(y + h, 1000)))
+    n = 5000
+    fans = rt.make_fans(n)
+    fans["finder"], fans["n_samples"], fans["pred"], fans["ztest"], fans["layer"] = 2, 1, rt.PRED_RANGER, 1, 1
+    fans["angles"] = rt.ANGLES_RANGER
+    fans["ox"], fans["oy"] = rng.uniform(-19, 19, n), rng.uniform(-19, 19, n)
+    fans["oz"], fans["oa"], fans["range"], fans["fov"] = 0.3, rng.uniform(-np.pi, np.pi, n), 5.0, 0.26
+    head = np.float32(fans["oa"]).astype(np.float64)
+    g = p.ctx.trace(fans, trig=oracle_lib.libm_trig(head))
+    for i in range(0, n, 7):
+        f = fans[i]
+        rg, it, be, hits = p.t1.ranger_fan(2, 1, [f["ox"], f["oy"], f["oz"], f["oa"]], 5.0, 0.26, 1)
+        assert bits(g.ranges[i:i + 1])[0] == bits(rg)[0] and g.hit_model[i] == hits["hit_model"][0]
+        assert g.bearings[i] == be[0] == 0.0 and g.intensities[i] == it[0]
+    p.ctx.close()
