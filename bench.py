@@ -128,7 +128,7 @@ def host_rays(fans):
     return rays.reshape(-1)
 
 
-def reference_world(world):
+def reference_world(world, record=False):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     from stage_b200 import worldgen
@@ -139,7 +139,7 @@ def reference_world(world):
     sys.stdout.flush()
     os.dup2(devnull, 1)   # the reference prints its banner to stdout; the JSON line must stay alone
     try:
-        ref = oracle_lib.RefWorld(text=worldgen.to_worldfile_text(world), record=False)
+        ref = oracle_lib.RefWorld(text=worldgen.to_worldfile_text(world), record=record)
     finally:
         sys.stdout.flush()
         os.dup2(saved, 1)
@@ -149,9 +149,9 @@ def reference_world(world):
     return ref, oracle_lib
 
 
-def cpu_reference_throughput(world, fans, threads, reps, warm=1):
+def cpu_reference_throughput(world, fans, threads, reps, warm=1, record=False):
     """rays/s of the reference's own World::Raytrace over the given fans, `threads` host threads."""
-    ref, _ = reference_world(world)
+    ref, _ = reference_world(world, record=record)
     if ref is None:
         return None
     rays = host_rays(fans)
@@ -340,17 +340,36 @@ def run_ours(args):
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         threads = args.cpu_threads or os.cpu_count()
         sample_fans = fans0
-        res = cpu_reference_throughput(world, sample_fans, threads, reps=3)
+        res = cpu_reference_throughput(world, sample_fans, threads, reps=3, record=True)
         if res is not None:
             one = res["ref"].raytrace(res["rays_arr"][:SAMPLES * 50], nthreads=1)[1]
             cpu = {"value": res["rays_per_s"], "unit": "rays/s", "cores": threads, "kind": "reference",
                    "sample": "all %d rays of one tick (static robots), best of 3, unmodified reference "
                              "World::Raytrace via oracle/_ref on %d threads; 1 thread: %.3g rays/s"
                              % (res["rays"], threads, SAMPLES * 50 / one)}
-            g = fset.download()
+            # Parity of this very workload with the reference's answers. Which of two overlapping
+            # bodies a ray reports depends on the order the reference mapped them in while loading
+            # (its std::set<Model*> order, world.cc:459-465), so a second context is loaded from the
+            # reference's own recorded Map/UnMap calls and traces the same fans.
+            import tempfile
+            import replay
+            import trace_io
+            with tempfile.TemporaryDirectory() as td:
+                res["ref"].trace_end(os.path.join(td, "load.trc"))
+                tr = trace_io.load(os.path.join(td, "load.trc"))
+            ctx2 = replay.make_context(tr, max_cell_entries=1 << 22)
+            for ev in tr.events:
+                if ev["type"] == trace_io.EV_MAP:
+                    ctx2.block_map(int(ev["block"]), int(ev["model"]), int(ev["layer"]), float(ev["zmin"]), float(ev["zmax"]), tr.polygon(ev))
+                elif ev["type"] == trace_io.EV_UNMAP:
+                    ctx2.block_unmap(int(ev["block"]), int(ev["layer"]))
+            g = ctx2.trace(fans0, want=rt.WANT_RANGES | rt.WANT_HIT_MODEL)
+            ctx2.close()
             h = res["hits"]
             parity = {"rays": int(len(h)), "hit_model_mismatch": int(np.count_nonzero(g.hit_model != h["hit_model"])),
-                      "max_range_err_m": float(np.max(np.abs(g.ranges - h["range"])))}
+                      "range_bits_mismatch": int(np.count_nonzero(g.ranges.view(np.uint64) != h["range"].view(np.uint64))),
+                      "max_range_err_m": float(np.max(np.abs(g.ranges - h["range"]))),
+                      "how": "device trig; grid loaded from the reference's recorded Map/UnMap calls; vs the unmodified reference's World::Raytrace on this host"}
 
     if rank == 0:
         peaks = {}

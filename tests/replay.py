@@ -15,11 +15,11 @@ def extent_of(trace, margin_sregs=0):
     return x0 - margin_sregs, y0 - margin_sregs, x1 - x0 + 1 + 2 * margin_sregs, y1 - y0 + 1 + 2 * margin_sregs
 
 
-def make_context(trace, **kw):
+def make_context(trace, max_cell_entries=1 << 20, **kw):
     x0, y0, nx, ny = extent_of(trace)
     n_blocks = int(trace.events["block"][trace.events["type"] == trace_io.EV_MAP].max()) + 1
     ctx = rt.Context(trace.ppm, x0, y0, nx, ny, max_models=int(trace.models["id"].max()) + 1,
-                     max_blocks=n_blocks, max_cell_entries=1 << 20, **kw)
+                     max_blocks=n_blocks, max_cell_entries=max_cell_entries, **kw)
     for m in trace.models:
         ctx.model_upsert(int(m["id"]), int(m["root"]), float(m["ranger_return"]), int(m["fiducial_return"]),
                          int(m["fiducial_key"]), int(m["flags"]), m["color"])

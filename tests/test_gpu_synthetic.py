@@ -63,8 +63,9 @@ def test_synthetic_world_matches_oracle(seed, half):
     assert len(bad) == 0
     assert np.array_equal(g.steps[:, 0], hits["cell_visits"]) and np.array_equal(g.steps[:, 1], hits["region_probes"])
     assert np.array_equal(bits(g.intensities), bits(it))
-    # device trig: model and cell exact, range within tolerance
+    # device trig = the host libm's values bit for bit (rt_libm.cuh): identical again
     d = ctx.trace(fans)
+    assert np.array_equal(bits(d.ranges), bits(rg))
     assert np.array_equal(d.hit_model, hits["hit_model"])
     h = d.hit_model >= 0
     assert np.array_equal(d.hit_cell[h, 0], hits["hit_x"][h]) and np.array_equal(d.hit_cell[h, 1], hits["hit_y"][h])
