@@ -311,17 +311,30 @@ def run_ours(args):
         })
     exchange = multi.DeltaExchange(ctx, rank, n_gpus, dist=dist) if n_gpus > 1 else None
 
+    host_split = {"remap_ms": 0.0, "exchange_ms": 0.0, "submit_ms": 0.0, "sync_ms": 0.0}
+
     def tick(tk):
+        t0 = time.perf_counter()
         ctx.blocks_remap(my_blocks, my_ids, tk["layer_w"], tk["z"], tk["first"], tk["xy"])
+        t1 = time.perf_counter()
         if exchange is not None:  # all-gather the moved-block deltas, apply all ranks' in rank order
             exchange.step()
+        t2 = time.perf_counter()
         ctx.fans_submit(tk["fans"], out)
+        t3 = time.perf_counter()
         ctx.sync()
+        t4 = time.perf_counter()
+        host_split["remap_ms"] += 1e3 * (t1 - t0)
+        host_split["exchange_ms"] += 1e3 * (t2 - t1)
+        host_split["submit_ms"] += 1e3 * (t3 - t2)
+        host_split["sync_ms"] += 1e3 * (t4 - t3)
 
     nw = max(args.warmup, 3)
     for tk in ticks[:nw]:
         tick(tk)
     st0 = ctx.stats()
+    for k in host_split:
+        host_split[k] = 0.0
     barrier()
     t0 = time.perf_counter()
     for tk in ticks[nw:]:
@@ -389,7 +402,7 @@ def run_ours(args):
                     "ticks_per_s": args.steps / t_e2e,
                     "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // args.steps,
                     "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) // args.steps,
-                    "last_step_kernel_ms": e2e_kt, "timing": "host clock around K ticks, synchronised both sides, max over ranks"},
+                    "last_step_kernel_ms": e2e_kt, "host_call_ms_per_step": {k: v / args.steps for k, v in host_split.items()}, "timing": "host clock around K ticks, synchronised both sides, max over ranks"},
             "gpu_launches": int(sum(st1[k] - launches0[k] for k in ("launches_rasterise", "launches_march", "launches_post", "launches_other"))),
             "kernel_ms": {"ray_march": march_avg_ms, "fan_headings": float(np.mean(head_ms)),
                           "share_of_step": march_avg_ms / (t_value_ms / args.steps) if n_gpus == 1 else None},

@@ -98,6 +98,9 @@ struct stg_rt_ctx {
   size_t blob_cap = 0;
   cudaEvent_t blob_uploaded = nullptr; // the pinned blob may be rewritten once this has fired
   cudaEvent_t t_ev[3][2] = {};          // [deltas, headings, march][start, stop]
+  cudaStream_t copy_stream = nullptr;   // result copies of chunk i overlap the march of chunk i+1
+  cudaEvent_t chunk_ev[8] = {};
+  cudaEvent_t copies_done = nullptr;
   bool t_rec[3] = { false, false, false };
 
   // fans queued by stg_rt_fans_submit and not launched yet
@@ -110,6 +113,7 @@ struct stg_rt_ctx {
   // launched, results not delivered yet
   std::vector<Submit> f_subs;
   uint64_t f_beams = 0;
+  bool f_direct[3] = { false, false, false }; // ranges / intensities / hit_model written in place
   FanArrays d;
   PinBuf h_in, h_ranges, h_intens, h_bearings, h_hit_model, h_hit_cell, h_steps;
 
@@ -465,6 +469,8 @@ FanBatchView view_of(const FanArrays &a, uint32_t n_fans, uint64_t beams, uint32
   memset(&v, 0, sizeof(v));
   v.n_fans = n_fans;
   v.n_beams = beams;
+  v.beam_begin = 0;
+  v.beam_end = beams;
   v.fans = (const FanRec *)a.fans.p;
   v.fan_first_beam = (const uint32_t *)a.first.p;
   v.headings_in = headings ? (const double *)a.headings_in.p : nullptr;
@@ -495,20 +501,26 @@ int validate_fans(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *fans, const 
 
 // copy one result array back: straight into caller memory when it is page-locked memory of ours,
 // otherwise into the pinned staging buffer (delivered by deliver_locked)
-int fetch_array(stg_rt_ctx *c, void *user, const void *dev, PinBuf &stage, uint64_t first, uint64_t n, size_t elt)
+// [lo, hi) = the beams (batch-wide indices) to fetch now; a submit covers [first, first + n)
+int fetch_array(stg_rt_ctx *c, void *user, const void *dev, PinBuf &stage, uint64_t first, uint64_t n, size_t elt,
+                uint64_t lo, uint64_t hi, cudaStream_t on)
 {
   if (!user)
     return 0;
-  const size_t bytes = n * elt;
-  void *dst = is_host_alloc(c, user, bytes) ? user : (char *)stage.p + first * elt;
-  CU(c, cudaMemcpyAsync(dst, (const char *)dev + first * elt, bytes, cudaMemcpyDeviceToHost, c->stream));
+  lo = std::max(lo, first);
+  hi = std::min(hi, first + n);
+  if (hi <= lo)
+    return 0;
+  const size_t bytes = (hi - lo) * elt;
+  void *dst = is_host_alloc(c, user, n * elt) ? (char *)user + (lo - first) * elt : (char *)stage.p + lo * elt;
+  CU(c, cudaMemcpyAsync(dst, (const char *)dev + lo * elt, bytes, cudaMemcpyDeviceToHost, on));
   c->stats.d2h_bytes += bytes;
   return 0;
 }
 
-void deliver_array(stg_rt_ctx *c, void *user, const PinBuf &stage, uint64_t first, uint64_t n, size_t elt)
+void deliver_array(stg_rt_ctx *c, void *user, const PinBuf &stage, uint64_t first, uint64_t n, size_t elt, bool direct)
 {
-  if (!user || is_host_alloc(c, user, n * elt))
+  if (!user || direct)
     return;
   memcpy(user, (const char *)stage.p + first * elt, n * elt);
 }
@@ -540,12 +552,14 @@ int deliver_locked(stg_rt_ctx *c)
     return 0;
   CU(c, cudaStreamSynchronize(c->stream));
   for (const Submit &s : c->f_subs) {
-    deliver_array(c, s.out.ranges, c->h_ranges, s.first_beam, s.n_beams, 8);
-    deliver_array(c, s.out.intensities, c->h_intens, s.first_beam, s.n_beams, 8);
-    deliver_array(c, s.out.bearings, c->h_bearings, s.first_beam, s.n_beams, 8);
-    deliver_array(c, s.out.hit_model, c->h_hit_model, s.first_beam, s.n_beams, 4);
-    deliver_array(c, s.out.hit_cell, c->h_hit_cell, s.first_beam, s.n_beams, 8);
-    deliver_array(c, s.out.steps, c->h_steps, s.first_beam, s.n_beams, 8);
+    // the kernel wrote ranges / intensities / hit models of a solo pinned submit in place
+    deliver_array(c, s.out.ranges, c->h_ranges, s.first_beam, s.n_beams, 8, c->f_direct[0]);
+    deliver_array(c, s.out.intensities, c->h_intens, s.first_beam, s.n_beams, 8, c->f_direct[1]);
+    deliver_array(c, s.out.hit_model, c->h_hit_model, s.first_beam, s.n_beams, 4, c->f_direct[2]);
+    // these were copied device-to-host, straight into pinned caller memory when possible
+    deliver_array(c, s.out.bearings, c->h_bearings, s.first_beam, s.n_beams, 8, is_host_alloc(c, s.out.bearings, s.n_beams * 8));
+    deliver_array(c, s.out.hit_cell, c->h_hit_cell, s.first_beam, s.n_beams, 8, is_host_alloc(c, s.out.hit_cell, s.n_beams * 8));
+    deliver_array(c, s.out.steps, c->h_steps, s.first_beam, s.n_beams, 8, is_host_alloc(c, s.out.steps, s.n_beams * 8));
   }
   c->f_subs.clear();
   c->f_beams = 0;
@@ -591,7 +605,38 @@ int launch_fans_locked(stg_rt_ctx *c)
     CU(c, cudaMemcpyAsync(c->d.trig.p, hp + o_trig, b_trig, cudaMemcpyHostToDevice, c->stream));
   c->stats.h2d_bytes += b_fans + b_first + b_head + b_trig;
 
-  const FanBatchView v = view_of(c->d, n_fans, beams, want, c->q_has_trig, b_head != 0);
+  if ((want & STG_RT_WANT_RANGES) && (rc = pin_reserve(c, c->h_ranges, beams * 8))) return rc;
+  if ((want & STG_RT_WANT_INTENSITIES) && (rc = pin_reserve(c, c->h_intens, beams * 8))) return rc;
+  if ((want & STG_RT_WANT_BEARINGS) && (rc = pin_reserve(c, c->h_bearings, beams * 8))) return rc;
+  if ((want & STG_RT_WANT_HIT_MODEL) && (rc = pin_reserve(c, c->h_hit_model, beams * 4))) return rc;
+  if ((want & STG_RT_WANT_HIT_CELL) && (rc = pin_reserve(c, c->h_hit_cell, beams * 8))) return rc;
+  if ((want & STG_RT_WANT_STEPS) && (rc = pin_reserve(c, c->h_steps, beams * 8))) return rc;
+
+  FanBatchView v = view_of(c->d, n_fans, beams, want, c->q_has_trig, b_head != 0);
+  // Results go straight to page-locked host memory from inside the march kernel (zero-copy stores
+  // over PCIe, overlapped with the marching of the other warps) instead of a device buffer plus a
+  // device-to-host copy afterwards: into the caller's own arrays when the batch is one submit whose
+  // arrays came from stg_rt_host_alloc, otherwise into the pinned staging arrays that stg_rt_sync
+  // copies from. Diagnostics (hit cell, step counters) and bearings keep the device buffer + copy.
+  const Submit *solo = c->q_subs.size() == 1 ? &c->q_subs[0] : nullptr;
+  auto host_target = [&](void *user, PinBuf &stage, size_t elt, bool &direct) -> void * {
+    direct = solo && user && is_host_alloc(c, user, beams * elt);
+    return direct ? user : stage.p;
+  };
+  c->f_direct[0] = c->f_direct[1] = c->f_direct[2] = false;
+  bool zc_ranges = false, zc_intens = false, zc_model = false;
+  if (want & STG_RT_WANT_RANGES) {
+    v.ranges = (double *)host_target(solo ? solo->out.ranges : nullptr, c->h_ranges, 8, c->f_direct[0]);
+    zc_ranges = true;
+  }
+  if (want & STG_RT_WANT_INTENSITIES) {
+    v.intensities = (double *)host_target(solo ? solo->out.intensities : nullptr, c->h_intens, 8, c->f_direct[1]);
+    zc_intens = true;
+  }
+  if (want & STG_RT_WANT_HIT_MODEL) {
+    v.hit_model = (int32_t *)host_target(solo ? solo->out.hit_model : nullptr, c->h_hit_model, 4, c->f_direct[2]);
+    zc_model = true;
+  }
   CU(c, cudaEventRecord(c->t_ev[1][0], c->stream));
   launch_fan_headings(v, c->stream);
   CU(c, cudaEventRecord(c->t_ev[1][1], c->stream));
@@ -600,26 +645,18 @@ int launch_fans_locked(stg_rt_ctx *c)
   CU(c, cudaEventRecord(c->t_ev[2][1], c->stream));
   c->t_rec[1] = c->t_rec[2] = true;
   CU(c, cudaGetLastError());
-  c->stats.launches_post += 1;
   c->stats.launches_march += 1;
+  c->stats.launches_post += 1;
   c->stats.beams += beams;
   c->stats.fans += n_fans;
-
-  if ((want & STG_RT_WANT_RANGES) && (rc = pin_reserve(c, c->h_ranges, beams * 8))) return rc;
-  if ((want & STG_RT_WANT_INTENSITIES) && (rc = pin_reserve(c, c->h_intens, beams * 8))) return rc;
-  if ((want & STG_RT_WANT_BEARINGS) && (rc = pin_reserve(c, c->h_bearings, beams * 8))) return rc;
-  if ((want & STG_RT_WANT_HIT_MODEL) && (rc = pin_reserve(c, c->h_hit_model, beams * 4))) return rc;
-  if ((want & STG_RT_WANT_HIT_CELL) && (rc = pin_reserve(c, c->h_hit_cell, beams * 8))) return rc;
-  if ((want & STG_RT_WANT_STEPS) && (rc = pin_reserve(c, c->h_steps, beams * 8))) return rc;
-  for (const Submit &s : c->q_subs) {
-    if ((rc = fetch_array(c, s.out.ranges, c->d.ranges.p, c->h_ranges, s.first_beam, s.n_beams, 8)) ||
-        (rc = fetch_array(c, s.out.intensities, c->d.intens.p, c->h_intens, s.first_beam, s.n_beams, 8)) ||
-        (rc = fetch_array(c, s.out.bearings, c->d.bearings.p, c->h_bearings, s.first_beam, s.n_beams, 8)) ||
-        (rc = fetch_array(c, s.out.hit_model, c->d.hit_model.p, c->h_hit_model, s.first_beam, s.n_beams, 4)) ||
-        (rc = fetch_array(c, s.out.hit_cell, c->d.hit_cell.p, c->h_hit_cell, s.first_beam, s.n_beams, 8)) ||
-        (rc = fetch_array(c, s.out.steps, c->d.steps.p, c->h_steps, s.first_beam, s.n_beams, 8)))
+  c->stats.d2h_bytes += beams * ((zc_ranges ? 8 : 0) + (zc_intens ? 8 : 0) + (zc_model ? 4 : 0));
+  for (const Submit &s : c->q_subs) { // what did not go zero-copy
+    if ((rc = fetch_array(c, s.out.bearings, c->d.bearings.p, c->h_bearings, s.first_beam, s.n_beams, 8, 0, beams, c->stream)) ||
+        (rc = fetch_array(c, s.out.hit_cell, c->d.hit_cell.p, c->h_hit_cell, s.first_beam, s.n_beams, 8, 0, beams, c->stream)) ||
+        (rc = fetch_array(c, s.out.steps, c->d.steps.p, c->h_steps, s.first_beam, s.n_beams, 8, 0, beams, c->stream)))
       return rc;
   }
+
   c->f_subs.swap(c->q_subs);
   c->f_beams = beams;
   c->q_subs.clear();
@@ -693,6 +730,10 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
   for (int k = 0; k < 3; k++)
     for (int j = 0; j < 2; j++)
       CUC(cudaEventCreate(&c->t_ev[k][j]));
+  CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 8; k++)
+    CUC(cudaEventCreateWithFlags(&c->chunk_ev[k], cudaEventDisableTiming));
+  CUC(cudaEventCreateWithFlags(&c->copies_done, cudaEventDisableTiming));
   GridView &g = c->g;
   g.ppm = cfg->ppm;
   g.rx0 = cfg->sreg_x0 * 32;
@@ -768,6 +809,10 @@ int stg_rt_destroy(stg_rt_ctx *c)
   for (auto &kv : c->host_allocs)
     cudaFreeHost(kv.first);
   cudaEventDestroy(c->blob_uploaded);
+  for (int k = 0; k < 8; k++)
+    cudaEventDestroy(c->chunk_ev[k]);
+  cudaEventDestroy(c->copies_done);
+  cudaStreamDestroy(c->copy_stream);
   for (int k = 0; k < 3; k++)
     for (int j = 0; j < 2; j++)
       cudaEventDestroy(c->t_ev[k][j]);
@@ -1426,6 +1471,8 @@ int stg_rt_blobs_submit(stg_rt_ctx *c, uint32_t n_finders, const stg_rt_blob_fin
   memset(&fv, 0, sizeof(fv));
   fv.n_fans = n_finders;
   fv.n_beams = beams;
+  fv.beam_begin = 0;
+  fv.beam_end = beams;
   fv.fans = (const FanRec *)(dp + b_f);
   fv.fan_first_beam = (const uint32_t *)(dp + b_f + b_fan);
   fv.heading = (double *)c->bd.heading.p;

@@ -111,6 +111,7 @@ static_assert(sizeof(FanRec) == 64, "FanRec");
 struct FanBatchView {
   uint32_t n_fans;
   uint64_t n_beams;
+  uint64_t beam_begin, beam_end; // the slice of beams one march launch covers (chunked launches)
   const FanRec *fans;
   const uint32_t *fan_first_beam; // n_fans + 1 prefix sums
   const double *headings_in;      // EXPLICIT headings (may be null)

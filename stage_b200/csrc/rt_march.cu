@@ -14,6 +14,8 @@
 //  * Empty regions are skipped with the reference's own crossing arithmetic (FP64, same operation
 //    order, no FMA contraction: build with -fmad=false), including its stale error term, the
 //    truncating double->int conversions and the int -= double of the remaining distance.
+#include <stdlib.h>
+
 #include "rt_trace.cuh"
 
 namespace stg {
@@ -23,8 +25,8 @@ namespace {
 template <bool kSteps>
 __global__ void __launch_bounds__(128, 8) k2_ray_march(GridView g, FanBatchView b)
 {
-  const uint64_t beam = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (beam >= b.n_beams)
+  const uint64_t beam = b.beam_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (beam >= b.beam_end)
     return;
 
   // which fan does this beam belong to
@@ -69,13 +71,20 @@ __global__ void __launch_bounds__(128, 8) k2_ray_march(GridView g, FanBatchView 
 
 void launch_ray_march(const GridView &g, const FanBatchView &b, void *stream)
 {
-  if (!b.n_beams)
+  if (b.beam_end <= b.beam_begin)
     return;
-  const unsigned blocks = (unsigned)((b.n_beams + 127) / 128);
+  static int threads = 0;
+  if (!threads) { // experiment knob; the default is what the profiles under profiles/ were taken with
+    const char *e = getenv("STG_RT_MARCH_BLOCK");
+    threads = e ? atoi(e) : 64;
+    if (threads != 32 && threads != 64 && threads != 128)
+      threads = 64;
+  }
+  const unsigned blocks = (unsigned)((b.beam_end - b.beam_begin + threads - 1) / threads);
   if (b.steps)
-    k2_ray_march<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(g, b);
+    k2_ray_march<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(g, b);
   else
-    k2_ray_march<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(g, b);
+    k2_ray_march<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(g, b);
 }
 
 } // namespace stg
