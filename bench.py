@@ -72,7 +72,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -268,10 +268,10 @@ def run_ours(args):
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     launches0 = ctx.stats()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         fset.trace()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     march_ms, head_ms = [], []
     barrier()
@@ -391,6 +391,11 @@ def run_ours(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:  # DRAM bytes per launch of the march kernel from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
         march_avg_ms = float(np.mean(march_ms))
         achieved = algo_bytes / (march_avg_ms * 1e-3) / 1e9
         line = {
@@ -407,7 +412,7 @@ def run_ours(args):
             "kernel_ms": {"ray_march": march_avg_ms, "fan_headings": float(np.mean(head_ms)),
                           "share_of_step": march_avg_ms / (t_value_ms / args.steps) if n_gpus == 1 else None},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_launch": algo_bytes, "cell_visits": C, "region_probes": R,
                          "beams": n_beams, "hit_fraction": hit_frac,
                          "note": "bytes = 4*C + 4*R + 40 per beam (SURVEY.md 8d), C/R counted by the kernel and proven equal to the oracle's in tests"},
