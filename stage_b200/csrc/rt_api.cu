@@ -93,6 +93,7 @@ struct stg_rt_ctx {
   int64_t live_entries[2] = { 0, 0 }; // cell visits currently rendered, per layer
   int64_t used_upper[2] = { 0, 0 };   // upper bound of non-empty slots (entries + tombstones)
 
+  std::vector<uint32_t> attr_blocks;
   PinBuf h_blob;
   DevBuf d_blob;
   size_t blob_cap = 0;
@@ -115,6 +116,7 @@ struct stg_rt_ctx {
   uint64_t f_beams = 0;
   bool f_direct[3] = { false, false, false }; // ranges / intensities / hit_model written in place
   FanArrays d;
+  DevBuf d_in; // fans | first_beam | headings | trig of the batch in flight
   PinBuf h_in, h_ranges, h_intens, h_bearings, h_hit_model, h_hit_cell, h_steps;
 
   // sensor post-processing batches (fiducial finders, blobfinders): one in flight per kind
@@ -220,69 +222,6 @@ bool is_host_alloc(stg_rt_ctx *c, const void *p, size_t bytes)
 
 // ---- deltas -----------------------------------------------------------------------------------
 
-uint32_t edges_of(const std::vector<int32_t> &xy, uint32_t block, uint32_t layer, uint32_t &step_cursor,
-                  std::vector<EdgeRec> &out)
-{
-  const size_t n = xy.size() / 2;
-  uint32_t steps = 0;
-  for (size_t i = 0; i < n; i++) {
-    const size_t j = (i + 1) % n;
-    EdgeRec e;
-    e.x0 = xy[2 * i];
-    e.y0 = xy[2 * i + 1];
-    e.x1 = xy[2 * j];
-    e.y1 = xy[2 * j + 1];
-    const int64_t adx = std::llabs((int64_t)e.x1 - e.x0), ady = std::llabs((int64_t)e.y1 - e.y0);
-    e.n_steps = (uint32_t)(adx + ady);
-    if (!e.n_steps)
-      continue;
-    e.block = block;
-    e.layer = layer;
-    e.first_step = step_cursor;
-    step_cursor += e.n_steps;
-    steps += e.n_steps;
-    out.push_back(e);
-  }
-  return steps;
-}
-
-struct BlobBuild {
-  std::vector<EdgeRec> rem, ins;
-  std::vector<BlockUpd> bupd;
-  uint32_t rem_steps = 0, ins_steps = 0;
-  int64_t d_live[2] = { 0, 0 };
-  size_t bytes(size_t n_model) const
-  {
-    return sizeof(DeltaHeader) + (rem.size() + ins.size()) * sizeof(EdgeRec) + bupd.size() * sizeof(BlockUpd) +
-           n_model * sizeof(ModelUpd);
-  }
-};
-
-size_t write_blob(unsigned char *dst, const BlobBuild &b, const std::vector<ModelUpd> &mupd, int rank)
-{
-  DeltaHeader h;
-  memset(&h, 0, sizeof(h));
-  h.n_remove = (uint32_t)b.rem.size();
-  h.n_insert = (uint32_t)b.ins.size();
-  h.n_block_upd = (uint32_t)b.bupd.size();
-  h.n_model_upd = (uint32_t)mupd.size();
-  h.steps_remove = b.rem_steps;
-  h.steps_insert = b.ins_steps;
-  h.rank = (uint32_t)rank;
-  unsigned char *p = dst;
-  memcpy(p, &h, sizeof(h));
-  p += sizeof(h);
-  memcpy(p, b.rem.data(), b.rem.size() * sizeof(EdgeRec));
-  p += b.rem.size() * sizeof(EdgeRec);
-  memcpy(p, b.ins.data(), b.ins.size() * sizeof(EdgeRec));
-  p += b.ins.size() * sizeof(EdgeRec);
-  memcpy(p, b.bupd.data(), b.bupd.size() * sizeof(BlockUpd));
-  p += b.bupd.size() * sizeof(BlockUpd);
-  memcpy(p, mupd.data(), mupd.size() * sizeof(ModelUpd));
-  p += mupd.size() * sizeof(ModelUpd);
-  return (size_t)(p - dst);
-}
-
 uint32_t root_flags_of(const stg_rt_ctx *c, uint32_t model)
 {
   const ModelUpd &m = c->models[model];
@@ -294,11 +233,13 @@ uint32_t root_flags_of(const stg_rt_ctx *c, uint32_t model)
 // order: pure removals first, then by the sequence number of the final Map.
 void sort_units(stg_rt_ctx *c)
 {
-  std::stable_sort(c->dirty_units.begin(), c->dirty_units.end(), [c](uint32_t a, uint32_t b) {
-    const BlockShadow &ba = c->blocks[a >> 1], &bb = c->blocks[b >> 1];
-    const uint32_t sa = ba.host_mapped[a & 1] ? ba.map_seq[a & 1] : 0, sb = bb.host_mapped[b & 1] ? bb.map_seq[b & 1] : 0;
-    return sa < sb;
-  });
+  auto key = [c](uint32_t u) {
+    const BlockShadow &b = c->blocks[u >> 1];
+    return b.host_mapped[u & 1] ? b.map_seq[u & 1] : 0u;
+  };
+  auto less = [&key](uint32_t a, uint32_t b) { return key(a) < key(b); };
+  if (!std::is_sorted(c->dirty_units.begin(), c->dirty_units.end(), less)) // usually already in Map-call order
+    std::stable_sort(c->dirty_units.begin(), c->dirty_units.end(), less);
 }
 
 // Keep probe chains short: tombstones never turn back into empty slots on their own, so when the
@@ -322,6 +263,33 @@ int ensure_table_room(stg_rt_ctx *c, const int64_t add[2])
 
 // Emit the queued deltas as one or more blobs. apply == true: upload and apply each blob locally.
 // apply == false (multi-GPU export): exactly one blob, uploaded to d_blob, not applied.
+// Write the edge records of one outline straight into the blob. Zero-length edges are kept (they
+// own no step, so the kernels' edge search never lands on them).
+static inline uint32_t emit_edges(const std::vector<int32_t> &xy, uint32_t block, uint32_t layer, uint32_t &step_cursor,
+                                  EdgeRec *&dst)
+{
+  const size_t n = xy.size() / 2;
+  const int32_t *p = xy.data();
+  uint32_t steps = 0;
+  for (size_t i = 0; i < n; i++) {
+    const size_t j = i + 1 == n ? 0 : i + 1;
+    EdgeRec &e = *dst++;
+    e.x0 = p[2 * i];
+    e.y0 = p[2 * i + 1];
+    e.x1 = p[2 * j];
+    e.y1 = p[2 * j + 1];
+    const int64_t adx = e.x1 > e.x0 ? (int64_t)e.x1 - e.x0 : (int64_t)e.x0 - e.x1;
+    const int64_t ady = e.y1 > e.y0 ? (int64_t)e.y1 - e.y0 : (int64_t)e.y0 - e.y1;
+    e.n_steps = (uint32_t)(adx + ady);
+    e.block = block;
+    e.layer = layer;
+    e.first_step = step_cursor;
+    step_cursor += e.n_steps;
+    steps += e.n_steps;
+  }
+  return steps;
+}
+
 int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes)
 {
   sort_units(c);
@@ -330,48 +298,74 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
   if (out_bytes)
     *out_bytes = 0;
   while (first_round || unit < c->dirty_units.size()) {
-    BlobBuild bb;
-    uint32_t rem_cursor = 0, ins_cursor = 0;
-    const size_t n_model = first_round ? c->model_upd.size() : 0;
-    int64_t ins_round[2] = { 0, 0 };
+    // ---- pass 1: how much of the queue fits this blob, and where its sections start ----
+    std::vector<uint32_t> &attr_blocks = c->attr_blocks; // blocks whose model's attributes changed (no new Map)
+    attr_blocks.clear();
     if (first_round && !c->models_changed.empty()) {
       for (uint32_t bi = 0; bi < c->blocks.size(); bi++) {
         const BlockShadow &b = c->blocks[bi];
-        if (!b.known || std::find(c->models_changed.begin(), c->models_changed.end(), b.model) == c->models_changed.end())
-          continue;
-        BlockUpd up;
-        up.block = bi;
-        up.model = b.model;
-        up.zmin = b.zmin;
-        up.zmax = b.zmax;
-        up.seq_local = 0;
-        up.layer = kUpdKeepSeq;
-        up.root_flags = root_flags_of(c, b.model);
-        up.pad = 0;
-        bb.bupd.push_back(up);
+        if (b.known && std::find(c->models_changed.begin(), c->models_changed.end(), b.model) != c->models_changed.end())
+          attr_blocks.push_back(bi);
       }
       c->models_changed.clear();
     }
-    while (unit < c->dirty_units.size()) {
+    const size_t n_model = first_round ? c->model_upd.size() : 0;
+    size_t n_rem = 0, n_ins = 0, n_bupd = attr_blocks.size(), end_unit = unit;
+    size_t bytes = sizeof(DeltaHeader) + n_bupd * sizeof(BlockUpd) + n_model * sizeof(ModelUpd);
+    if (bytes > c->blob_cap)
+      return fail(c, STG_RT_ENOMEM, "model / block attribute updates exceed the delta buffer");
+    while (end_unit < c->dirty_units.size()) {
+      const uint32_t u = c->dirty_units[end_unit];
+      const BlockShadow &b = c->blocks[u >> 1];
+      const int L = u & 1;
+      const size_t re = b.dev_mapped[L] ? b.dev_xy[L].size() / 2 : 0, ie = b.host_mapped[L] ? b.host_xy[L].size() / 2 : 0;
+      const size_t add = (re + ie) * sizeof(EdgeRec) + (b.host_mapped[L] ? sizeof(BlockUpd) : 0);
+      if (bytes + add > c->blob_cap) {
+        if (end_unit == unit)
+          return fail(c, STG_RT_ENOMEM, "one block's outline (%zu edges) exceeds the delta buffer", re + ie);
+        break;
+      }
+      bytes += add;
+      n_rem += re;
+      n_ins += ie;
+      n_bupd += b.host_mapped[L] ? 1 : 0;
+      end_unit++;
+    }
+    if (!apply && end_unit < c->dirty_units.size())
+      return fail(c, STG_RT_ENOMEM, "deltas of one tick exceed the all-gather slot (%zu bytes)", c->blob_cap);
+
+    // ---- pass 2: write the records straight into the pinned blob ----
+    CU(c, cudaEventSynchronize(c->blob_uploaded)); // the previous upload has left the pinned buffer
+    unsigned char *base = (unsigned char *)c->h_blob.p;
+    DeltaHeader *hdr = (DeltaHeader *)base;
+    EdgeRec *rem = (EdgeRec *)(base + sizeof(DeltaHeader)), *ins = rem + n_rem;
+    BlockUpd *bupd = (BlockUpd *)(ins + n_ins);
+    ModelUpd *mupd = (ModelUpd *)(bupd + n_bupd);
+    for (uint32_t bi : attr_blocks) {
+      const BlockShadow &b = c->blocks[bi];
+      BlockUpd &up = *bupd++;
+      up.block = bi;
+      up.model = b.model;
+      up.zmin = b.zmin;
+      up.zmax = b.zmax;
+      up.seq_local = 0;
+      up.layer = kUpdKeepSeq;
+      up.root_flags = root_flags_of(c, b.model);
+      up.pad = 0;
+    }
+    uint32_t rem_cursor = 0, ins_cursor = 0;
+    int64_t d_live[2] = { 0, 0 }, ins_round[2] = { 0, 0 };
+    for (; unit < end_unit; unit++) {
       const uint32_t u = c->dirty_units[unit];
       BlockShadow &b = c->blocks[u >> 1];
       const int L = u & 1;
-      const size_t add_edges = (b.dev_mapped[L] ? b.dev_xy[L].size() / 2 : 0) + (b.host_mapped[L] ? b.host_xy[L].size() / 2 : 0);
-      if (bb.bytes(n_model) + add_edges * sizeof(EdgeRec) + sizeof(BlockUpd) > c->blob_cap) {
-        if (bb.rem.empty() && bb.ins.empty() && bb.bupd.empty())
-          return fail(c, STG_RT_ENOMEM, "one block's outline (%zu edges) exceeds the delta buffer", add_edges);
-        break;
-      }
-      if (b.dev_mapped[L]) {
-        const uint32_t s = edges_of(b.dev_xy[L], u >> 1, L, rem_cursor, bb.rem);
-        bb.rem_steps += s;
-        bb.d_live[L] -= s;
-      }
+      if (b.dev_mapped[L])
+        d_live[L] -= emit_edges(b.dev_xy[L], u >> 1, L, rem_cursor, rem);
       if (b.host_mapped[L]) {
-        const uint32_t s = edges_of(b.host_xy[L], u >> 1, L, ins_cursor, bb.ins);
-        bb.ins_steps += s;
-        bb.d_live[L] += s;
-        BlockUpd up;
+        const uint32_t st = emit_edges(b.host_xy[L], u >> 1, L, ins_cursor, ins);
+        d_live[L] += st;
+        ins_round[L] += st;
+        BlockUpd &up = *bupd++;
         up.block = u >> 1;
         up.model = b.model;
         up.zmin = b.zmin;
@@ -380,35 +374,35 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
         up.layer = (uint32_t)L;
         up.root_flags = root_flags_of(c, b.model);
         up.pad = 0;
-        bb.bupd.push_back(up);
+        b.dev_xy[L].swap(b.host_xy[L]); // host_xy is rewritten by the next Map before it is read again
+      } else {
+        b.dev_xy[L].clear();
       }
       b.dev_mapped[L] = b.host_mapped[L];
-      b.dev_xy[L] = b.host_xy[L];
       b.dirty[L] = false;
-      unit++;
     }
-    if (!apply && unit < c->dirty_units.size())
-      return fail(c, STG_RT_ENOMEM, "deltas of one tick exceed the all-gather slot (%zu bytes)", c->blob_cap);
-    if (apply) {
-      int64_t ins_per_layer[2] = { 0, 0 };
-      for (const EdgeRec &e : bb.ins)
-        ins_per_layer[e.layer & 1] += e.n_steps;
+    if (n_model)
+      memcpy(mupd, c->model_upd.data(), n_model * sizeof(ModelUpd));
+    memset(hdr, 0, sizeof(*hdr));
+    hdr->n_remove = (uint32_t)n_rem;
+    hdr->n_insert = (uint32_t)n_ins;
+    hdr->n_block_upd = (uint32_t)n_bupd;
+    hdr->n_model_upd = (uint32_t)n_model;
+    hdr->steps_remove = rem_cursor;
+    hdr->steps_insert = ins_cursor;
+    hdr->rank = (uint32_t)rank;
+    const size_t nbytes = bytes;
+    if (apply)
       for (int L = 0; L < 2; L++)
-        if (c->live_entries[L] + bb.d_live[L] > (int64_t)c->slot_cap / 2)
+        if (c->live_entries[L] + d_live[L] > (int64_t)c->slot_cap / 2)
           return fail(c, STG_RT_ENOMEM, "cell-entry table of layer %d full (%lld entries, capacity %u/2); raise max_cell_entries",
-                      L, (long long)(c->live_entries[L] + bb.d_live[L]), c->slot_cap);
-      ins_round[0] = ins_per_layer[0];
-      ins_round[1] = ins_per_layer[1];
-    }
-    CU(c, cudaEventSynchronize(c->blob_uploaded));
-    const std::vector<ModelUpd> no_models;
-    const size_t nbytes = write_blob((unsigned char *)c->h_blob.p, bb, first_round ? c->model_upd : no_models, rank);
+                      L, (long long)(c->live_entries[L] + d_live[L]), c->slot_cap);
     CU(c, cudaMemcpyAsync(c->d_blob.p, c->h_blob.p, nbytes, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaEventRecord(c->blob_uploaded, c->stream));
     c->stats.h2d_bytes += nbytes;
-    c->stats.edge_steps += bb.rem_steps + bb.ins_steps;
+    c->stats.edge_steps += rem_cursor + ins_cursor;
     for (int L = 0; L < 2; L++)
-      c->live_entries[L] += bb.d_live[L];
+      c->live_entries[L] += d_live[L];
     if (apply) {
       c->epoch++;
       CU(c, cudaEventRecord(c->t_ev[0][0], c->stream));
@@ -566,10 +560,14 @@ int deliver_locked(stg_rt_ctx *c)
   return 0;
 }
 
-int launch_fans_locked(stg_rt_ctx *c)
+int apply_deltas_locked(stg_rt_ctx *c);
+
+// with_deltas: apply the queued deltas between the headings kernel (which does not read the grid, so
+// it can run while the host is still building the delta blob) and the march (which must see them).
+int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
 {
   if (c->q_subs.empty())
-    return 0;
+    return with_deltas ? apply_deltas_locked(c) : 0;
   int rc = deliver_locked(c); // staging buffers are single-buffered
   if (rc)
     return rc;
@@ -593,17 +591,11 @@ int launch_fans_locked(stg_rt_ctx *c)
     memcpy(hp + o_head, c->q_headings.data(), b_head);
   if (b_trig)
     memcpy(hp + o_trig, c->q_trig.data(), b_trig);
-  if ((rc = dev_reserve(c, c->d.fans, b_fans)) || (rc = dev_reserve(c, c->d.first, b_first)) ||
-      (rc = dev_reserve(c, c->d.headings_in, std::max<size_t>(b_head, 8))) ||
-      (rc = dev_reserve(c, c->d.trig, std::max<size_t>(b_trig, 8))) || (rc = reserve_outputs(c, c->d, beams, want)))
+  // one device block with the same layout as the pinned one: a single upload per batch
+  if ((rc = dev_reserve(c, c->d_in, o_trig + b_trig + 16)) || (rc = reserve_outputs(c, c->d, beams, want)))
     return rc;
-  CU(c, cudaMemcpyAsync(c->d.fans.p, hp, b_fans, cudaMemcpyHostToDevice, c->stream));
-  CU(c, cudaMemcpyAsync(c->d.first.p, hp + o_first, b_first, cudaMemcpyHostToDevice, c->stream));
-  if (b_head)
-    CU(c, cudaMemcpyAsync(c->d.headings_in.p, hp + o_head, b_head, cudaMemcpyHostToDevice, c->stream));
-  if (b_trig)
-    CU(c, cudaMemcpyAsync(c->d.trig.p, hp + o_trig, b_trig, cudaMemcpyHostToDevice, c->stream));
-  c->stats.h2d_bytes += b_fans + b_first + b_head + b_trig;
+  CU(c, cudaMemcpyAsync(c->d_in.p, hp, o_trig + b_trig, cudaMemcpyHostToDevice, c->stream));
+  c->stats.h2d_bytes += o_trig + b_trig;
 
   if ((want & STG_RT_WANT_RANGES) && (rc = pin_reserve(c, c->h_ranges, beams * 8))) return rc;
   if ((want & STG_RT_WANT_INTENSITIES) && (rc = pin_reserve(c, c->h_intens, beams * 8))) return rc;
@@ -613,6 +605,10 @@ int launch_fans_locked(stg_rt_ctx *c)
   if ((want & STG_RT_WANT_STEPS) && (rc = pin_reserve(c, c->h_steps, beams * 8))) return rc;
 
   FanBatchView v = view_of(c->d, n_fans, beams, want, c->q_has_trig, b_head != 0);
+  v.fans = (const FanRec *)c->d_in.p;
+  v.fan_first_beam = (const uint32_t *)((const char *)c->d_in.p + o_first);
+  v.headings_in = b_head ? (const double *)((const char *)c->d_in.p + o_head) : nullptr;
+  v.trig_in = c->q_has_trig ? (const double *)((const char *)c->d_in.p + o_trig) : nullptr;
   // Results go straight to page-locked host memory from inside the march kernel (zero-copy stores
   // over PCIe, overlapped with the marching of the other warps) instead of a device buffer plus a
   // device-to-host copy afterwards: into the caller's own arrays when the batch is one submit whose
@@ -640,6 +636,8 @@ int launch_fans_locked(stg_rt_ctx *c)
   CU(c, cudaEventRecord(c->t_ev[1][0], c->stream));
   launch_fan_headings(v, c->stream);
   CU(c, cudaEventRecord(c->t_ev[1][1], c->stream));
+  if (with_deltas && (rc = apply_deltas_locked(c)))
+    return rc;
   CU(c, cudaEventRecord(c->t_ev[2][0], c->stream));
   launch_ray_march(c->g, v, c->stream);
   CU(c, cudaEventRecord(c->t_ev[2][1], c->stream));
@@ -671,10 +669,7 @@ int launch_fans_locked(stg_rt_ctx *c)
 
 int flush_locked(stg_rt_ctx *c)
 {
-  int rc = apply_deltas_locked(c);
-  if (rc)
-    return rc;
-  return launch_fans_locked(c);
+  return launch_fans_locked(c, true);
 }
 
 void touch_unit(stg_rt_ctx *c, uint32_t block, int layer)
@@ -796,6 +791,8 @@ int stg_rt_destroy(stg_rt_ctx *c)
       cudaFree(p);
   free_fan_arrays(c->d);
   free_fan_arrays(c->bd);
+  if (c->d_in.p)
+    cudaFree(c->d_in.p);
   for (DevBuf *b : { &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
     if (b->p)
       cudaFree(b->p);

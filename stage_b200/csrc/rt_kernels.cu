@@ -108,8 +108,8 @@ __device__ __forceinline__ BlobView blob_view(const unsigned char *blobs, int ra
   return v;
 }
 
-__global__ void __launch_bounds__(256) k1_table_updates(GridView g, const unsigned char *blobs, int n_ranks,
-                                                         size_t slot_bytes, unsigned long long epoch)
+__device__ __forceinline__ void k1_table_updates(const GridView &g, const unsigned char *blobs, int n_ranks,
+                                                 size_t slot_bytes, unsigned long long epoch)
 {
   for (int rank = 0; rank < n_ranks; rank++) {
     const BlobView v = blob_view(blobs, rank, slot_bytes);
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) k1_table_updates(GridView g, const unsign
   }
 }
 
-__global__ void __launch_bounds__(256) k1_remove(GridView g, const unsigned char *blobs, int n_ranks, size_t slot_bytes)
+__device__ __forceinline__ void k1_remove(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes)
 {
   for (int rank = 0; rank < n_ranks; rank++) {
     const BlobView v = blob_view(blobs, rank, slot_bytes);
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) k1_remove(GridView g, const unsigned char
   }
 }
 
-__global__ void __launch_bounds__(256) k1_fixup(GridView g, const unsigned char *blobs, int n_ranks, size_t slot_bytes)
+__device__ __forceinline__ void k1_fixup(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes)
 {
   for (int rank = 0; rank < n_ranks; rank++) {
     const BlobView v = blob_view(blobs, rank, slot_bytes);
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) k1_fixup(GridView g, const unsigned char 
   }
 }
 
-__global__ void __launch_bounds__(256) k1_insert(GridView g, const unsigned char *blobs, int n_ranks, size_t slot_bytes)
+__device__ __forceinline__ void k1_insert(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes)
 {
   for (int rank = 0; rank < n_ranks; rank++) {
     const BlobView v = blob_view(blobs, rank, slot_bytes);
@@ -227,6 +227,23 @@ __global__ void __launch_bounds__(256) k1_insert(GridView g, const unsigned char
       atomicOr(tile + kRegionWidth + c.cx, 1u << c.cy);
     }
   }
+}
+
+// phase 0: table updates and removals (independent of each other).
+__global__ void __launch_bounds__(256) k1_phase0(GridView g, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
+                                                 unsigned long long epoch)
+{
+  k1_table_updates(g, blobs, n_ranks, slot_bytes, epoch);
+  k1_remove(g, blobs, n_ranks, slot_bytes);
+}
+
+// phase 1, after every removal has landed: mask fix-up of the removed cells and the insertions. The
+// two only ever SET mask bits, and a fix-up that already sees a freshly inserted entry sets a bit the
+// insertion sets anyway, so they can share a launch.
+__global__ void __launch_bounds__(256) k1_phase1(GridView g, const unsigned char *blobs, int n_ranks, size_t slot_bytes)
+{
+  k1_fixup(g, blobs, n_ranks, slot_bytes);
+  k1_insert(g, blobs, n_ranks, slot_bytes);
 }
 
 // Compaction of one layer's cell-content table: re-insert the live entries into a clean table
@@ -260,24 +277,19 @@ static int delta_grid_blocks()
   return blocks;
 }
 
-// phase 0: table updates, removals, mask fix-up.  phase 1: insertions. The host may compact the
+// phase 0: table updates, removals.  phase 1: mask fix-up, insertions. The host may compact the
 // cell-entry table between the two (every tombstone of phase 0 is reclaimed before new entries land).
 void launch_apply_deltas(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
                          unsigned long long epoch, int phase, void *stream, uint64_t *launch_counter)
 {
   cudaStream_t s = (cudaStream_t)stream;
   const int blocks = delta_grid_blocks();
-  if (phase == 0) {
-    k1_table_updates<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes, epoch);
-    k1_remove<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes);
-    k1_fixup<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes);
-    if (launch_counter)
-      *launch_counter += 3;
-  } else {
-    k1_insert<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes);
-    if (launch_counter)
-      *launch_counter += 1;
-  }
+  if (phase == 0)
+    k1_phase0<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes, epoch);
+  else
+    k1_phase1<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes);
+  if (launch_counter)
+    *launch_counter += 1;
 }
 
 void launch_rehash(const unsigned long long *src, unsigned long long *dst, uint32_t slot_mask, void *stream)
