@@ -220,7 +220,41 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if n_gpus > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # keep each rank (and the page-locked result buffers it first-touches) on the NUMA node its GPU
+        # hangs off: the results travel GPU -> host every tick and cross-socket hops cost bandwidth
+        try:
+            bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+            import pynvml
+            pynvml.nvmlInit()
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            pci = pynvml.nvmlDeviceGetPciInfo(hnd).busId
+            pci = pci.decode() if isinstance(pci, bytes) else pci
+            node = int(open("/sys/bus/pci/devices/%s/numa_node" % pci.lower()[-12:]).read())
+            if node >= 0:
+                cpus = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+                ids = []
+                for part in cpus.split(","):
+                    a, _, b = part.partition("-")
+                    ids += list(range(int(a), int(b or a) + 1))
+                allowed = sorted(set(ids) & os.sched_getaffinity(0))
+                if allowed:
+                    os.sched_setaffinity(0, allowed)
+        except Exception:
+            pass
+    if n_gpus > 1:
+        # NCCL prints its version banner on stdout when the communicator is created; stdout must carry
+        # nothing but the JSON line, so it is pointed at stderr until the first collective is through
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     world = worldgen.make_world(seed=1, n_rects=args.rects, n_robots=args.robots * n_gpus, half_extent_m=args.half_extent)
     x0, y0, nx, ny = world.sreg_extent()

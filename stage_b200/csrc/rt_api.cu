@@ -90,6 +90,11 @@ struct stg_rt_ctx {
   uint64_t epoch = 0;
   uint32_t local_seq = 0;
   int last_export_rank = -1; // multi-GPU: this context's rank, learnt from stg_rt_delta_export
+  int64_t last_export_ins = 0, last_gather_ins = 0;
+  PinBuf h_hdrs;
+  cudaEvent_t hdrs_ready = nullptr;
+  bool hdrs_pending = false;
+  int hdrs_ranks = 0;
   int64_t live_entries[2] = { 0, 0 }; // cell visits currently rendered, per layer
   int64_t used_upper[2] = { 0, 0 };   // upper bound of non-empty slots (entries + tombstones)
 
@@ -401,6 +406,8 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
     CU(c, cudaEventRecord(c->blob_uploaded, c->stream));
     c->stats.h2d_bytes += nbytes;
     c->stats.edge_steps += rem_cursor + ins_cursor;
+    if (!apply)
+      c->last_export_ins = ins_cursor;
     for (int L = 0; L < 2; L++)
       c->live_entries[L] += d_live[L];
     if (apply) {
@@ -420,7 +427,7 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
     if (out_bytes)
       *out_bytes = nbytes;
     first_round = false;
-    if (unit < c->dirty_units.size() || !apply) // the pinned blob is about to be reused / handed out
+    if (unit < c->dirty_units.size()) // another round follows and reuses the pinned blob right away
       CU(c, cudaStreamSynchronize(c->stream));
   }
   c->dirty_units.clear();
@@ -729,6 +736,7 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
   for (int k = 0; k < 8; k++)
     CUC(cudaEventCreateWithFlags(&c->chunk_ev[k], cudaEventDisableTiming));
   CUC(cudaEventCreateWithFlags(&c->copies_done, cudaEventDisableTiming));
+  CUC(cudaEventCreateWithFlags(&c->hdrs_ready, cudaEventDisableTiming));
   GridView &g = c->g;
   g.ppm = cfg->ppm;
   g.rx0 = cfg->sreg_x0 * 32;
@@ -809,6 +817,9 @@ int stg_rt_destroy(stg_rt_ctx *c)
   for (int k = 0; k < 8; k++)
     cudaEventDestroy(c->chunk_ev[k]);
   cudaEventDestroy(c->copies_done);
+  cudaEventDestroy(c->hdrs_ready);
+  if (c->h_hdrs.p)
+    cudaFreeHost(c->h_hdrs.p);
   cudaStreamDestroy(c->copy_stream);
   for (int k = 0; k < 3; k++)
     for (int j = 0; j < 2; j++)
@@ -1291,23 +1302,35 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_r
   int rc = launch_fans_locked(c);
   if (rc)
     return rc;
-  // learn what the other ranks inserted / removed so the table accounting stays an upper bound
-  std::vector<DeltaHeader> hdrs(n_ranks);
-  CU(c, cudaMemcpy2DAsync(hdrs.data(), sizeof(DeltaHeader), dev_gathered, slot_bytes, sizeof(DeltaHeader), n_ranks,
-                          cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
-  int64_t ins = 0;
-  for (const DeltaHeader &h : hdrs)
-    ins += h.steps_insert;
-  // the other ranks' entries: the headers do not split layers, so charge both (upper bound)
-  int64_t other_ins = 0, other_rem = 0;
-  for (int r = 0; r < n_ranks; r++)
-    if ((int)hdrs[r].rank != c->last_export_rank) {
-      other_ins += hdrs[r].steps_insert;
-      other_rem += hdrs[r].steps_remove;
+  // Table accounting needs what the OTHER ranks inserted / removed, which only their headers (now on
+  // the device) know. They are read back asynchronously and booked one exchange late, so the host
+  // never waits for the GPU here; until then this tick is charged like the last one (the compaction
+  // threshold of 3/4 leaves ample slack for a tick's worth of error).
+  if (c->hdrs_pending) {
+    CU(c, cudaEventSynchronize(c->hdrs_ready));
+    const DeltaHeader *h = (const DeltaHeader *)c->h_hdrs.p;
+    int64_t other_ins = 0, other_rem = 0, all_ins = 0;
+    for (int r = 0; r < c->hdrs_ranks; r++) {
+      all_ins += h[r].steps_insert;
+      if ((int)h[r].rank != c->last_export_rank) {
+        other_ins += h[r].steps_insert;
+        other_rem += h[r].steps_remove;
+      }
     }
-  for (int L = 0; L < 2; L++)
-    c->live_entries[L] += std::max<int64_t>(other_ins - other_rem, 0);
+    for (int L = 0; L < 2; L++) // the headers do not split layers: charge both (upper bound)
+      c->live_entries[L] += std::max<int64_t>(other_ins - other_rem, 0);
+    c->last_gather_ins = all_ins;
+    c->hdrs_pending = false;
+  }
+  int rcp = pin_reserve(c, c->h_hdrs, (size_t)n_ranks * sizeof(DeltaHeader));
+  if (rcp)
+    return rcp;
+  CU(c, cudaMemcpy2DAsync(c->h_hdrs.p, sizeof(DeltaHeader), dev_gathered, slot_bytes, sizeof(DeltaHeader), n_ranks,
+                          cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaEventRecord(c->hdrs_ready, c->stream));
+  c->hdrs_pending = true;
+  c->hdrs_ranks = n_ranks;
+  const int64_t ins = std::max<int64_t>(c->last_gather_ins, (int64_t)n_ranks * c->last_export_ins);
   const int64_t add[2] = { ins, ins };
   c->epoch++;
   CU(c, cudaEventRecord(c->t_ev[0][0], c->stream));
