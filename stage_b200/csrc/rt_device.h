@@ -27,10 +27,11 @@ constexpr unsigned long long kSlotTomb = ~0ull;
 //  slots[L][h]         open-addressing multimap (cell -> block) holding the CONTENT of the occupied
 //                      cells: entry = (cell_key << 32) | (block_id + 1), cell_key = r*1024 + cy*32
 //                      + cx. 0 = empty, ~0 = tombstone. Only consulted where an occ bit is set.
-//  blk_* / mdl_*       what the hit test and the predicates read (Block::global_z block.cc:177-180,
-//                      Model::vis stage.hh:1924-1937, tree root for Model::IsRelated).
-//  blk_seq[L][b]       order key of block b's latest Map on layer L: entries of one cell sorted by
-//                      it reproduce the insertion order of Cell::blocks[L].
+//  blk_rec[L][b]       BlockRec below: what the hit test reads about block b (Block::global_z
+//                      block.cc:177-180, owning model, tree root for Model::IsRelated, Model::vis bits
+//                      stage.hh:1924-1937) plus seq, the order key of b's latest Map on layer L:
+//                      entries of one cell sorted by it reproduce the order of Cell::blocks[L].
+//  mdl_*               per model: root (for the finder), ranger_return (intensity output), vis flags.
 // Everything the hit test needs about one block on one layer, in ONE 32-byte sector, so resolving an
 // occupied cell costs two dependent loads (slot, then this) instead of a chain through block and
 // model tables. zmin/zmax/model/root_flags are per block (kept equal on both layers); seq is per layer.

@@ -97,3 +97,29 @@ def test_full_baseline_size_matches_oracle():
     assert len(bad) == 0, "%d of %d beams differ" % (len(bad), len(rg))
     assert np.array_equal(bits(g.intensities), bits(it))
     ctx.close()
+
+
+def test_resident_set_follows_moved_origins():
+    """stg_rt_set_update_origins: a resident fan set re-traced after its robots moved (and after the
+    moved bodies were re-rasterised on the other layer) equals a fresh submit of the moved fans."""
+    w = worldgen.make_world(seed=4, n_rects=200, n_robots=80, half_extent_m=20.48)
+    ctx, t1 = build_both(w)
+    fans = worldgen.ranger_fans(w, layer=1, samples=90, range_max=12.0)
+    s = ctx.set_create(fans, want=rt.WANT_RANGES | rt.WANT_HIT_MODEL)
+    s.trace()
+    a = s.download()
+    poses = worldgen.step_robots(w, w.robots, 1, speed_m=0.3)
+    polys = worldgen.robot_polygons(w, poses)
+    n_o = len(w.obstacles)
+    ctx.blocks_remap((n_o + np.arange(len(poses))).astype(np.uint32), w.robot_ids, 0,
+                     np.tile([0.0, w.robot_size[2]], (len(poses), 1)), np.arange(len(poses) + 1, dtype=np.uint32) * 4,
+                     np.concatenate(polys, 0))
+    moved = worldgen.ranger_fans(w, layer=0, samples=90, range_max=12.0, robots=poses)
+    s.update_origins(np.stack([moved["ox"], moved["oy"], moved["oz"], moved["oa"]], 1), 0)
+    s.trace()
+    b = s.download()
+    c = ctx.trace(moved, want=rt.WANT_RANGES | rt.WANT_HIT_MODEL)
+    assert np.array_equal(bits(b.ranges), bits(c.ranges)) and np.array_equal(b.hit_model, c.hit_model)
+    assert not np.array_equal(bits(a.ranges), bits(b.ranges))
+    s.destroy()
+    ctx.close()
