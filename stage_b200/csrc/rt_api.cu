@@ -131,7 +131,7 @@ struct stg_rt_ctx {
     size_t out_bytes = 0, count_bytes = 0;
     bool pending = false;
   } fid_job, blob_job;
-  DevBuf d_fid_in, d_fid_out, d_fid_count, d_blob_in, d_blob_out, d_blob_count, d_mdl_color;
+  DevBuf d_fid_grid, d_fid_in, d_fid_out, d_fid_count, d_blob_in, d_blob_out, d_blob_count, d_mdl_color;
   PinBuf h_fid_in, h_fid_out, h_fid_count, h_blob_in, h_blob_out, h_blob_count;
   FanArrays bd; // the blobfinders' scan-line fans
   std::vector<double> mdl_color; // rgba per model
@@ -801,7 +801,7 @@ int stg_rt_destroy(stg_rt_ctx *c)
   free_fan_arrays(c->bd);
   if (c->d_in.p)
     cudaFree(c->d_in.p);
-  for (DevBuf *b : { &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
+  for (DevBuf *b : { &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
     if (b->p)
       cudaFree(b->p);
   for (PinBuf *b : { &c->h_fid_in, &c->h_fid_out, &c->h_fid_count, &c->h_blob_in, &c->h_blob_out, &c->h_blob_count })
@@ -1405,9 +1405,47 @@ int stg_rt_fiducials_submit(stg_rt_ctx *c, uint32_t n_targets, const stg_rt_fid_
   v.fans = (const FanRec *)((char *)c->d_fid_in.p + b_t + b_f);
   v.out = (FiducialRec *)c->d_fid_out.p;
   v.out_count = (uint32_t *)c->d_fid_count.p;
-  launch_fiducials(c->g, v, c->stream);
+  // Candidate query: brute force over the target list for small problems, a per-submit uniform grid
+  // (bins as wide as the longest detection range) beyond ~4 M finder x target pairs.
+  // STG_RT_FID_GRID=0/1 forces one or the other (tests compare the two).
+  const char *force = getenv("STG_RT_FID_GRID");
+  const bool use_grid = force ? atoi(force) != 0 : (uint64_t)n_targets * n_finders > (4u << 20);
+  if (use_grid && n_targets) {
+    double x0 = targets[0].x, x1 = x0, y0 = targets[0].y, y1 = y0, cell = 0;
+    for (uint32_t i = 1; i < n_targets; i++) {
+      x0 = std::min(x0, targets[i].x);
+      x1 = std::max(x1, targets[i].x);
+      y0 = std::min(y0, targets[i].y);
+      y1 = std::max(y1, targets[i].y);
+    }
+    for (uint32_t i = 0; i < n_finders; i++)
+      cell = std::max(cell, finders[i].max_range_anon);
+    if (!(cell > 0))
+      cell = 1.0;
+    while ((x1 - x0) / cell * ((y1 - y0) / cell) > 4.0e6) // keep the bin table small
+      cell *= 2;
+    FidGridView gv;
+    gv.x0 = x0;
+    gv.y0 = y0;
+    gv.cell = cell;
+    gv.nbx = (int32_t)floor((x1 - x0) / cell) + 1;
+    gv.nby = (int32_t)floor((y1 - y0) / cell) + 1;
+    const size_t n_bins = (size_t)gv.nbx * gv.nby;
+    const size_t b_grid = ((size_t)n_targets * 2 + n_bins * 2 + 1) * 4;
+    if ((rc = dev_reserve(c, c->d_fid_grid, b_grid)))
+      return rc;
+    gv.bin_of = (uint32_t *)c->d_fid_grid.p;
+    gv.sorted = gv.bin_of + n_targets;
+    gv.start = gv.sorted + n_targets;
+    gv.cursor = gv.start + n_bins + 1;
+    CU(c, cudaMemsetAsync(gv.start, 0, (n_bins + 1) * 4, c->stream));
+    launch_fiducials_grid(c->g, v, gv, c->stream);
+    c->stats.launches_post += 4;
+  } else {
+    launch_fiducials(c->g, v, c->stream);
+    c->stats.launches_post++;
+  }
   CU(c, cudaGetLastError());
-  c->stats.launches_post++;
   CU(c, cudaMemcpyAsync(c->h_fid_out.p, c->d_fid_out.p, b_out, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaMemcpyAsync(c->h_fid_count.p, c->d_fid_count.p, b_cnt, cudaMemcpyDeviceToHost, c->stream));
   c->stats.d2h_bytes += b_out + b_cnt;

@@ -161,6 +161,16 @@ struct FidBatchView {
   uint32_t *out_count;
 };
 
+// uniform grid over the fiducial targets (candidate query of the fiducial finders)
+struct FidGridView {
+  double x0, y0, cell;   // bin (bx, by) covers [x0 + bx*cell, x0 + (bx+1)*cell) x ...
+  int32_t nbx, nby;
+  uint32_t *bin_of;      // [n_targets]
+  uint32_t *start;       // [n_bins + 1] counts, then exclusive prefix sums
+  uint32_t *cursor;      // [n_bins]
+  uint32_t *sorted;      // [n_targets] target indices grouped by bin
+};
+
 // ---- blobfinders ------------------------------------------------------------------------------
 struct BlobFinderRec {
   uint32_t finder, scan_width, scan_height;
@@ -190,6 +200,7 @@ struct BlobBatchView {
 };
 
 void launch_fiducials(const GridView &g, const FidBatchView &b, void *stream);
+void launch_fiducials_grid(const GridView &g, const FidBatchView &b, const FidGridView &v, void *stream);
 void launch_blobs(const GridView &g, const BlobBatchView &b, void *stream);
 void launch_debug_trig(uint64_t n, const double *x, double *cs, void *stream);
 

@@ -20,6 +20,51 @@ __device__ __forceinline__ double normalize_angle(double a)
   return a;
 }
 
+// AddModelIfVisible (model_fiducial.cc:109-224) for one (finder, target) pair, after the x / y
+// window of the candidate query (:245-262, bounds inclusive). True = the target is seen; rec filled.
+__device__ __forceinline__ bool fid_try(const GridView &g, const FidFinderRec &fd, const FanRec *fan, uint32_t finder_root,
+                                        const FidTargetRec &him, uint32_t t, FiducialRec &rec)
+{
+  if (him.model == fd.finder || him.x < fd.x - fd.max_range_anon || him.x > fd.x + fd.max_range_anon ||
+      him.y < fd.y - fd.max_range_anon || him.y > fd.y + fd.max_range_anon)
+    return false;
+  if (him.fiducial_key != fd.fiducial_key) // :117
+    return false;
+  const double dx = him.x - fd.x, dy = him.y - fd.y;
+  const double range = hypot(dy, dx);                              // :130
+  if (range >= fd.max_range_anon)                                   // :134
+    return false;
+  const double dtheta = normalize_angle(atan2(dy, dx) - fd.a);     // :144-145
+  if (fabs(dtheta) > fd.fov / 2.0)                                  // :147
+    return false;
+  if (__ldg(g.mdl_root + him.model) == finder_root)                // IsRelated, :152
+    return false;
+  // Raytrace(Pose(0,0,0,dtheta), max_range_anon, fiducial_raytrace_match, NULL, true), :179:
+  // LocalToGlobal adds the heading onto (GetGlobalPose() + geom.pose) and normalises it
+  double cosa, sina;
+  trace::heading_trig(normalize_angle(fd.oa + dtheta), cosa, sina);
+  trace::RayResult r;
+  trace::trace_ray<false>(g, fan, cosa, sina, r);
+  int32_t seen = r.hit_model;
+  if (fd.ignore_zloc && seen < 0) // :184
+    seen = (int32_t)him.model;
+  if (seen != (int32_t)him.model) // :192
+    return false;
+  rec.target = t;
+  rec.id = range < fd.max_range_id ? him.fiducial_return : 0; // :219
+  rec.range = range;
+  rec.bearing = dtheta;
+  rec.geom[0] = him.sx;
+  rec.geom[1] = him.sy;
+  rec.geom[2] = him.sz;
+  rec.geom[3] = normalize_angle(him.a - fd.a); // :209
+  rec.pose[0] = him.x;
+  rec.pose[1] = him.y;
+  rec.pose[2] = him.z;
+  rec.pose[3] = him.a;
+  return true;
+}
+
 // One warp per finder. Lanes take 32 targets at a time, in the caller's order (the reference visits
 // candidates in ascending Model* order, model_fiducial.cc:266-283, and controllers depend on it), so
 // the accepted records are compacted with a ballot prefix to keep that order.
@@ -34,50 +79,8 @@ __global__ void __launch_bounds__(128) k3_fiducials(GridView g, FidBatchView b)
   uint32_t n_out = 0;
   for (uint32_t t0 = 0; t0 < b.n_targets; t0 += 32) {
     const uint32_t t = t0 + lane;
-    bool accept = false;
     FiducialRec rec;
-    if (t < b.n_targets) {
-      const FidTargetRec him = b.targets[t];
-      // the x / y window of the sorted-set query (model_fiducial.cc:245-262), bounds inclusive
-      bool cand = him.model != fd.finder && him.x >= fd.x - fd.max_range_anon && him.x <= fd.x + fd.max_range_anon &&
-                  him.y >= fd.y - fd.max_range_anon && him.y <= fd.y + fd.max_range_anon;
-      cand = cand && him.fiducial_key == fd.fiducial_key; // :117
-      double range = 0, dtheta = 0;
-      if (cand) {
-        const double dx = him.x - fd.x, dy = him.y - fd.y;
-        range = hypot(dy, dx);                                   // :130
-        cand = !(range >= fd.max_range_anon);                    // :134
-        dtheta = normalize_angle(atan2(dy, dx) - fd.a);          // :144-145
-        cand = cand && !(fabs(dtheta) > fd.fov / 2.0);           // :147
-        cand = cand && __ldg(g.mdl_root + him.model) != finder_root; // IsRelated, :152
-      }
-      if (cand) {
-        // Raytrace(Pose(0,0,0,dtheta), max_range_anon, fiducial_raytrace_match, NULL, true), :179:
-        // LocalToGlobal adds the heading onto (GetGlobalPose() + geom.pose) and normalises it
-        double cosa, sina;
-        trace::heading_trig(normalize_angle(fd.oa + dtheta), cosa, sina);
-        trace::RayResult r;
-        trace::trace_ray<false>(g, fan, cosa, sina, r);
-        int32_t seen = r.hit_model;
-        if (fd.ignore_zloc && seen < 0) // :184
-          seen = (int32_t)him.model;
-        if (seen == (int32_t)him.model) { // :192
-          accept = true;
-          rec.target = t;
-          rec.id = range < fd.max_range_id ? him.fiducial_return : 0; // :219
-          rec.range = range;
-          rec.bearing = dtheta;
-          rec.geom[0] = him.sx;
-          rec.geom[1] = him.sy;
-          rec.geom[2] = him.sz;
-          rec.geom[3] = normalize_angle(him.a - fd.a); // :209
-          rec.pose[0] = him.x;
-          rec.pose[1] = him.y;
-          rec.pose[2] = him.z;
-          rec.pose[3] = him.a;
-        }
-      }
-    }
+    const bool accept = t < b.n_targets && fid_try(g, fd, fan, finder_root, b.targets[t], t, rec);
     const uint32_t votes = __ballot_sync(0xffffffffu, accept);
     if (accept) {
       const uint32_t slot = n_out + __popc(votes & ((1u << lane) - 1u));
@@ -88,6 +91,110 @@ __global__ void __launch_bounds__(128) k3_fiducials(GridView g, FidBatchView b)
   }
   if (lane == 0)
     b.out_count[warp] = n_out; // may exceed max_per_finder: the caller sees the truncation
+}
+
+// ---- the same with a uniform-grid candidate query -----------------------------
+// The reference rebuilds two position-sorted std::sets every tick (world.cc:623-629) and intersects
+// two range queries per finder (model_fiducial.cc:245-283). Here the targets are binned into square
+// cells at least as wide as the longest max_range_anon, so a finder's +-range window touches at
+// most 3 x 3 bins; bins are filled by a counting sort (count, scan, scatter) every submit.
+__global__ void __launch_bounds__(256) k3_fid_bin_count(FidGridView v, const FidTargetRec *targets, uint32_t n_targets)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_targets)
+    return;
+  const int32_t bx = min(max((int32_t)floor((targets[t].x - v.x0) / v.cell), 0), v.nbx - 1);
+  const int32_t by = min(max((int32_t)floor((targets[t].y - v.y0) / v.cell), 0), v.nby - 1);
+  const uint32_t bin = (uint32_t)(by * v.nbx + bx);
+  v.bin_of[t] = bin;
+  atomicAdd(v.start + bin, 1u);
+}
+
+// exclusive scan of v.start[0..n_bins) in place, start[n_bins] = total; one CTA, chunk per thread
+__global__ void __launch_bounds__(1024) k3_fid_bin_scan(FidGridView v)
+{
+  __shared__ uint32_t partial[1024];
+  const uint32_t n = (uint32_t)(v.nbx * v.nby), tid = threadIdx.x;
+  const uint32_t per = (n + 1023) / 1024, lo = min(tid * per, n), hi = min(lo + per, n);
+  uint32_t sum = 0;
+  for (uint32_t i = lo; i < hi; i++)
+    sum += v.start[i];
+  partial[tid] = sum;
+  __syncthreads();
+  for (uint32_t o = 1; o < 1024; o <<= 1) { // Hillis-Steele inclusive scan of the partial sums
+    const uint32_t add = tid >= o ? partial[tid - o] : 0;
+    __syncthreads();
+    partial[tid] += add;
+    __syncthreads();
+  }
+  uint32_t run = tid ? partial[tid - 1] : 0;
+  for (uint32_t i = lo; i < hi; i++) {
+    const uint32_t c = v.start[i];
+    v.start[i] = run;
+    v.cursor[i] = run;
+    run += c;
+  }
+  if (tid == 1023)
+    v.start[n] = partial[1023];
+}
+
+__global__ void __launch_bounds__(256) k3_fid_bin_scatter(FidGridView v, uint32_t n_targets)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_targets)
+    v.sorted[atomicAdd(v.cursor + v.bin_of[t], 1u)] = t;
+}
+
+__global__ void __launch_bounds__(128) k3_fiducials_grid(GridView g, FidBatchView b, FidGridView v)
+{
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= b.n_finders)
+    return;
+  const FidFinderRec fd = b.finders[warp];
+  const FanRec *fan = b.fans + warp;
+  const uint32_t finder_root = __ldg(g.mdl_root + fd.finder);
+  FiducialRec *out = b.out + (size_t)warp * b.max_per_finder;
+  const int32_t bx0 = min(max((int32_t)floor((fd.x - fd.max_range_anon - v.x0) / v.cell), 0), v.nbx - 1);
+  const int32_t bx1 = min(max((int32_t)floor((fd.x + fd.max_range_anon - v.x0) / v.cell), 0), v.nbx - 1);
+  const int32_t by0 = min(max((int32_t)floor((fd.y - fd.max_range_anon - v.y0) / v.cell), 0), v.nby - 1);
+  const int32_t by1 = min(max((int32_t)floor((fd.y + fd.max_range_anon - v.y0) / v.cell), 0), v.nby - 1);
+  uint32_t n_out = 0;
+  for (int32_t by = by0; by <= by1; by++)
+    for (int32_t bx = bx0; bx <= bx1; bx++) {
+      const uint32_t bin = (uint32_t)(by * v.nbx + bx);
+      const uint32_t lo = __ldg(v.start + bin), hi = __ldg(v.start + bin + 1);
+      for (uint32_t i0 = lo; i0 < hi; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        FiducialRec rec;
+        bool accept = false;
+        if (i < hi) {
+          const uint32_t t = __ldg(v.sorted + i);
+          accept = fid_try(g, fd, fan, finder_root, b.targets[t], t, rec);
+        }
+        const uint32_t votes = __ballot_sync(0xffffffffu, accept);
+        if (accept) {
+          const uint32_t slot = n_out + __popc(votes & ((1u << lane) - 1u));
+          if (slot < b.max_per_finder)
+            out[slot] = rec;
+        }
+        n_out += __popc(votes);
+      }
+    }
+  __syncwarp();
+  if (lane == 0) {
+    // bins were visited in grid order: put the records back into target order (ascending Model*)
+    const uint32_t k = min(n_out, b.max_per_finder);
+    for (uint32_t i = 1; i < k; i++) {
+      const FiducialRec r = out[i];
+      uint32_t j = i;
+      while (j > 0 && out[j - 1].target > r.target) {
+        out[j] = out[j - 1];
+        j--;
+      }
+      out[j] = r;
+    }
+    b.out_count[warp] = n_out; // beyond max_per_finder the kept records are an unspecified subset
+  }
 }
 
 // ColorMatchIgnoreAlpha, model_blobfinder.cc:109-113
@@ -179,6 +286,22 @@ void launch_fiducials(const GridView &g, const FidBatchView &b, void *stream)
     return;
   const unsigned blocks = (b.n_finders * 32 + 127) / 128;
   k3_fiducials<<<blocks, 128, 0, (cudaStream_t)stream>>>(g, b);
+}
+
+// v.start must be zeroed (n_bins + 1 words) before the call
+void launch_fiducials_grid(const GridView &g, const FidBatchView &b, const FidGridView &v, void *stream)
+{
+  if (!b.n_finders)
+    return;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (b.n_targets) {
+    k3_fid_bin_count<<<(b.n_targets + 255) / 256, 256, 0, s>>>(v, b.targets, b.n_targets);
+    k3_fid_bin_scan<<<1, 1024, 0, s>>>(v);
+    k3_fid_bin_scatter<<<(b.n_targets + 255) / 256, 256, 0, s>>>(v, b.n_targets);
+  } else {
+    k3_fid_bin_scan<<<1, 1024, 0, s>>>(v);
+  }
+  k3_fiducials_grid<<<(b.n_finders * 32 + 127) / 128, 128, 0, s>>>(g, b, v);
 }
 
 void launch_blobs(const GridView &g, const BlobBatchView &b, void *stream)

@@ -71,7 +71,11 @@ def make_world(seed=1, n_rects=4096, n_robots=1000, half_extent_m=81.92, ppm=50.
     occupied = {}
     ox0, ox1 = obstacles[:, 0] - obstacles[:, 2] / 2 - clear, obstacles[:, 0] + obstacles[:, 2] / 2 + clear
     oy0, oy1 = obstacles[:, 1] - obstacles[:, 3] / 2 - clear, obstacles[:, 1] + obstacles[:, 3] / 2 + clear
+    rounds = 0
     while placed < n_robots:
+        rounds += 1
+        if rounds > 200:
+            raise ValueError("cannot place %d robots 0.6 m apart in this world (placed %d)" % (n_robots, placed))
         cand = rng.uniform(-H + 1.5, H - 1.5, size=(4 * (n_robots - placed) + 16, 2))
         cand = np.round(cand * 1000) / 1000.0
         for x, y in cand:

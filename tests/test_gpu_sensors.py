@@ -106,3 +106,120 @@ def test_fiducials_synthetic_against_oracle():
         total += n
     assert total > 50
     ctx.close()
+
+
+def _fid_world(n_robots, n_targets, n_finders, half, seed=21):
+    import oracle_lib  # noqa: F401
+    from stage_b200 import worldgen
+    from test_gpu_synthetic import build_both
+    w = worldgen.make_world(seed=seed, n_rects=int(150 * (half / 20.48) ** 2), n_robots=n_robots, half_extent_m=half)
+    ctx, t1 = build_both(w)
+    rng = np.random.RandomState(seed)
+    targets = np.zeros(n_targets, rt.FID_TARGET_DTYPE)
+    targets["model"] = w.robot_ids[:n_targets]
+    targets["fiducial_return"] = rng.randint(1, 9, n_targets)
+    targets["x"], targets["y"] = w.robots[:n_targets, 0], w.robots[:n_targets, 1]
+    targets["a"] = w.robots[:n_targets, 2] * (np.pi / 180)
+    targets["sx"], targets["sy"], targets["sz"] = w.robot_size
+    fr = np.arange(n_robots - n_finders, n_robots)
+    finders = np.zeros(n_finders, rt.FID_FINDER_DTYPE)
+    finders["finder"] = w.robot_ids[fr]
+    finders["layer"] = 1
+    for k, col in (("x", 0), ("y", 1)):
+        finders[k] = finders["o" + k] = w.robots[fr, col]
+    finders["a"] = finders["oa"] = w.robots[fr, 2] * (np.pi / 180)
+    finders["oz"] = 0.3
+    finders["max_range_anon"] = rng.uniform(2.0, 6.0, n_finders)
+    finders["max_range_id"] = 3.0
+    finders["fov"] = rng.uniform(1.0, 2 * np.pi, n_finders)
+    return w, ctx, t1, targets, finders
+
+
+def test_fiducial_grid_query_equals_brute_force_and_oracle(monkeypatch):
+    """Row f-3: the uniform-grid candidate query gives exactly the brute-force result (records and
+    their order), and both match the T1 restatement."""
+    import ctypes
+    import oracle_lib
+    w, ctx, t1, targets, finders = _fid_world(3000, 2500, 1500, 40.96)
+    monkeypatch.setenv("STG_RT_FID_GRID", "0")
+    out_b, cnt_b = ctx.fiducials_submit(targets, finders, max_per_finder=48)
+    ctx.sync()
+    monkeypatch.setenv("STG_RT_FID_GRID", "1")
+    out_g, cnt_g = ctx.fiducials_submit(targets, finders, max_per_finder=48)
+    ctx.sync()
+    assert np.array_equal(cnt_b, cnt_g) and cnt_b.max() < 48 and cnt_b.sum() > 500
+    for i in range(len(finders)):
+        assert out_b[i, :cnt_b[i]].tobytes() == out_g[i, :cnt_g[i]].tobytes()
+    L = oracle_lib.t1()
+    L.t1_fiducial_update.restype = ctypes.c_uint32
+    L.t1_fiducial_update.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
+    for i in range(0, len(finders), 5):
+        ref = np.zeros(48, rt.FIDUCIAL_DTYPE)
+        f = np.ascontiguousarray(finders[i:i + 1])
+        n = L.t1_fiducial_update(t1.h, len(targets), targets.ctypes.data, f.ctypes.data, 48, ref.ctypes.data)
+        assert n == cnt_g[i]
+        assert np.array_equal(out_g[i, :n]["target"], ref[:n]["target"]) and np.array_equal(out_g[i, :n]["id"], ref[:n]["id"])
+        assert np.max(np.abs(out_g[i, :n]["range"] - ref[:n]["range"]), initial=0) <= 1e-9
+    ctx.close()
+
+
+def test_fiducial_query_at_config4_scale_timing():
+    """BASELINE config 4's fiducial load: 100k robots, each a target and a finder, on the config-3
+    obstacle field (detection range cut from 8 m to 3 m: at 3.7 robots/m^2 the +-3 m window already
+    holds ~130 candidates per finder). The robots carry no bodies here (ignore_zloc finders: a target
+    is seen unless an obstacle is in the way). Times the device path - the oracle would need hours -
+    and checks sanity: order, ranges, and agreement with the oracle on a few finders."""
+    import ctypes
+    import time
+    import oracle_lib
+    from stage_b200 import worldgen
+    from test_gpu_synthetic import build_both
+    n = 100000
+    w = worldgen.make_world(seed=1, n_rects=4096, n_robots=1, half_extent_m=81.92)
+    x0, y0, nx, ny = w.sreg_extent()
+    first_id = w.n_models + 1
+    ctx = rt.Context(w.ppm, x0, y0, nx, ny, max_models=first_id + n + 1, max_blocks=len(w.obstacles) + 2, max_cell_entries=1 << 22)
+    worldgen.load_into_context(ctx, w)
+    t1 = oracle_lib.T1World(w.ppm)
+    for mid in [0] + list(w.obstacle_ids) + list(w.robot_ids):
+        t1.model_upsert(int(mid), int(mid), 0.5)
+    polys = worldgen.obstacle_polygons(w) + worldgen.robot_polygons(w)
+    for b, (p, m) in enumerate(zip(polys, np.concatenate([w.obstacle_ids, w.robot_ids]))):
+        t1.block_map(b, int(m), 1, 0.0, 1.0, p)
+    rng = np.random.RandomState(33)
+    ids = first_id + np.arange(n)
+    for m in ids:
+        ctx.model_upsert(int(m), int(m), 0.5, 1)
+        t1.model_upsert(int(m), int(m), 0.5, 1)
+    xy = rng.uniform(-80, 80, (n, 2))
+    targets = np.zeros(n, rt.FID_TARGET_DTYPE)
+    targets["model"], targets["fiducial_return"] = ids, rng.randint(1, 9, n)
+    targets["x"], targets["y"], targets["a"] = xy[:, 0], xy[:, 1], rng.uniform(-np.pi, np.pi, n)
+    targets["sx"] = targets["sy"] = targets["sz"] = 0.1
+    finders = np.zeros(n, rt.FID_FINDER_DTYPE)
+    finders["finder"], finders["layer"], finders["ignore_zloc"] = ids, 1, 1
+    for k in ("x", "y", "a"):
+        finders[k] = finders["o" + k] = targets[k]
+    finders["oz"] = 0.5
+    finders["max_range_anon"], finders["max_range_id"], finders["fov"] = 3.0, 2.0, np.pi
+    ctx.fiducials_submit(targets, finders, max_per_finder=96)  # warm-up: sizes the device and pinned buffers
+    ctx.sync()
+    t0 = time.perf_counter()
+    out, cnt = ctx.fiducials_submit(targets, finders, max_per_finder=96)
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    seen = int(cnt.sum())
+    print("config-4 scale fiducial query: 100k finders x 100k targets, %d fiducials seen (max %d per finder), %.1f ms end to end (8.4 GB/s of it is the fixed-stride 845 MB result array coming back)"
+          % (seen, cnt.max(), 1e3 * dt))
+    assert seen > 100000 and cnt.max() <= 96
+    L = oracle_lib.t1()
+    L.t1_fiducial_update.restype = ctypes.c_uint32
+    L.t1_fiducial_update.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
+    for i in range(0, n, 9973):
+        tg = out[i, :cnt[i]]["target"]
+        assert np.all(np.diff(tg.astype(np.int64)) > 0)  # ascending target order
+        ref = np.zeros(96, rt.FIDUCIAL_DTYPE)
+        f = np.ascontiguousarray(finders[i:i + 1])
+        k = L.t1_fiducial_update(t1.h, n, targets.ctypes.data, f.ctypes.data, 96, ref.ctypes.data)
+        assert k == cnt[i] and np.array_equal(ref[:k]["target"], tg) and np.array_equal(ref[:k]["id"], out[i, :k]["id"])
+    ctx.close()
