@@ -175,6 +175,25 @@ int stg_rt_blocks_remap(stg_rt_ctx *ctx, uint32_t n, const uint32_t *blocks, con
 int stg_rt_fans_submit(stg_rt_ctx *ctx, uint32_t n_fans, const stg_rt_fan *fans,
                        const double *headings, const double *trig, const stg_rt_fan_out *out);
 
+/* Sensor noise of one ranger fan (ModelRanger::Sensor::range_noise_const / range_noise / angle_noise,
+   worldfile "noise [c p a]", model_ranger.cc:150, stage.hh:2637-2641). 32 bytes. */
+typedef struct {
+  double range_noise_const; /* VARIANCE of the additive Gaussian term, as generateGaussianNoise takes it */
+  double range_noise;       /* proportional term: range * range_noise * U, U in {-1, -0.998 .. 0.998} */
+  double angle_noise;       /* heading jitter: sample_incr * angle_noise * U * 0.5 */
+  uint64_t seed;            /* stream selector; 0 = derive from the fan's finder id */
+} stg_rt_fan_noise;
+
+/* stg_rt_fans_submit for RANGER fans with sensor noise (model_ranger.cc:232-249): beam t is traced
+   along (float)(a_t + sample_incr*angle_noise*U*0.5) and, if it hit closer than range.max, reports
+   range + range*range_noise*U' + N(0, range_noise_const). The reference draws U, U', N from libc
+   rand() in beam order, which cannot be replayed in parallel; here they come from a counter-based
+   generator keyed by (seed, beam, launch), so the noise has the reference's DISTRIBUTION (same discrete
+   uniform, same Box-Muller normal), not its values: statistical parity only (tests/test_gpu_noise.py).
+   noise[i] belongs to fans[i]; all-zero entries give exactly the noise-free result. */
+int stg_rt_fans_submit_noisy(stg_rt_ctx *ctx, uint32_t n_fans, const stg_rt_fan *fans,
+                             const stg_rt_fan_noise *noise, const stg_rt_fan_out *out);
+
 /* ---- fiducial finders ------------------------------------------------------------------------ */
 
 /* A model with fiducial_return != 0 (World::models_with_fiducials, stage.hh:798): what

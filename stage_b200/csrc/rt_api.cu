@@ -113,6 +113,9 @@ struct stg_rt_ctx {
   std::vector<FanRec> q_fans;
   std::vector<uint32_t> q_first;
   std::vector<double> q_headings, q_trig;
+  std::vector<FanNoiseRec> q_noise; // parallel to q_fans once any noisy fan is queued
+  bool q_has_noise = false;
+  uint64_t noise_epoch = 0;
   std::vector<Submit> q_subs;
   uint64_t q_beams = 0;
   bool q_has_trig = false;
@@ -472,6 +475,8 @@ FanBatchView view_of(const FanArrays &a, uint32_t n_fans, uint64_t beams, uint32
   v.n_beams = beams;
   v.beam_begin = 0;
   v.beam_end = beams;
+  v.noise = nullptr;
+  v.noise_epoch = 0;
   v.fans = (const FanRec *)a.fans.p;
   v.fan_first_beam = (const uint32_t *)a.first.p;
   v.headings_in = headings ? (const double *)a.headings_in.p : nullptr;
@@ -589,7 +594,8 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   const size_t b_fans = (size_t)n_fans * sizeof(FanRec), b_first = (size_t)(n_fans + 1) * 4;
   const size_t b_head = c->q_headings.size() * 8, b_trig = c->q_has_trig ? beams * 16 : 0;
   const size_t o_first = b_fans, o_head = (o_first + b_first + 15) & ~(size_t)15, o_trig = o_head + b_head;
-  if ((rc = pin_reserve(c, c->h_in, o_trig + b_trig)))
+  const size_t b_noise = c->q_has_noise ? (size_t)n_fans * sizeof(FanNoiseRec) : 0, o_noise = o_trig + b_trig, b_all = o_noise + b_noise;
+  if ((rc = pin_reserve(c, c->h_in, b_all)))
     return rc;
   char *hp = (char *)c->h_in.p;
   memcpy(hp, c->q_fans.data(), b_fans);
@@ -598,11 +604,15 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
     memcpy(hp + o_head, c->q_headings.data(), b_head);
   if (b_trig)
     memcpy(hp + o_trig, c->q_trig.data(), b_trig);
+  if (b_noise) {
+    c->q_noise.resize(n_fans); // fans queued without noise after the last noisy one: zeros
+    memcpy(hp + o_noise, c->q_noise.data(), b_noise);
+  }
   // one device block with the same layout as the pinned one: a single upload per batch
-  if ((rc = dev_reserve(c, c->d_in, o_trig + b_trig + 16)) || (rc = reserve_outputs(c, c->d, beams, want)))
+  if ((rc = dev_reserve(c, c->d_in, b_all + 16)) || (rc = reserve_outputs(c, c->d, beams, want)))
     return rc;
-  CU(c, cudaMemcpyAsync(c->d_in.p, hp, o_trig + b_trig, cudaMemcpyHostToDevice, c->stream));
-  c->stats.h2d_bytes += o_trig + b_trig;
+  CU(c, cudaMemcpyAsync(c->d_in.p, hp, b_all, cudaMemcpyHostToDevice, c->stream));
+  c->stats.h2d_bytes += b_all;
 
   if ((want & STG_RT_WANT_RANGES) && (rc = pin_reserve(c, c->h_ranges, beams * 8))) return rc;
   if ((want & STG_RT_WANT_INTENSITIES) && (rc = pin_reserve(c, c->h_intens, beams * 8))) return rc;
@@ -616,6 +626,8 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   v.fan_first_beam = (const uint32_t *)((const char *)c->d_in.p + o_first);
   v.headings_in = b_head ? (const double *)((const char *)c->d_in.p + o_head) : nullptr;
   v.trig_in = c->q_has_trig ? (const double *)((const char *)c->d_in.p + o_trig) : nullptr;
+  v.noise = b_noise ? (const FanNoiseRec *)((const char *)c->d_in.p + o_noise) : nullptr;
+  v.noise_epoch = ++c->noise_epoch;
   // Results go straight to page-locked host memory from inside the march kernel (zero-copy stores
   // over PCIe, overlapped with the marching of the other warps) instead of a device buffer plus a
   // device-to-host copy afterwards: into the caller's own arrays when the batch is one submit whose
@@ -669,6 +681,8 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   c->q_first.clear();
   c->q_headings.clear();
   c->q_trig.clear();
+  c->q_noise.clear();
+  c->q_has_noise = false;
   c->q_beams = 0;
   c->q_has_trig = false;
   return 0;
@@ -957,12 +971,34 @@ static int block_unmap_locked(stg_rt_ctx *c, uint32_t block_id, int layer)
   return STG_RT_OK;
 }
 
+static int fans_submit_locked(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *fans, const double *headings, const double *trig,
+                              const stg_rt_fan_noise *noise, const stg_rt_fan_out *out);
+
 int stg_rt_fans_submit(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *fans, const double *headings, const double *trig,
                        const stg_rt_fan_out *out)
 {
   if (!c)
     return STG_RT_EINVAL;
   std::lock_guard<std::mutex> lk(c->mu);
+  return fans_submit_locked(c, n_fans, fans, headings, trig, nullptr, out);
+}
+
+int stg_rt_fans_submit_noisy(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *fans, const stg_rt_fan_noise *noise,
+                             const stg_rt_fan_out *out)
+{
+  static_assert(sizeof(stg_rt_fan_noise) == sizeof(FanNoiseRec), "noise record layout");
+  if (!c || (n_fans && !noise))
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  for (uint32_t i = 0; i < n_fans; i++)
+    if (fans && fans[i].angles != STG_RT_ANGLES_RANGER)
+      return fail(c, STG_RT_EINVAL, "fans_submit_noisy: fan %u is not a ranger fan", i);
+  return fans_submit_locked(c, n_fans, fans, nullptr, nullptr, noise, out);
+}
+
+static int fans_submit_locked(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *fans, const double *headings, const double *trig,
+                              const stg_rt_fan_noise *noise, const stg_rt_fan_out *out)
+{
   if (!n_fans)
     return STG_RT_OK;
   if (!fans || !out)
@@ -998,6 +1034,17 @@ int stg_rt_fans_submit(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *fans, c
   if (trig) {
     c->q_trig.insert(c->q_trig.end(), trig, trig + 2 * beams);
     c->q_has_trig = true;
+  }
+  if (noise) {
+    FanNoiseRec zero;
+    memset(&zero, 0, sizeof(zero));
+    c->q_noise.resize(c->q_fans.size() - n_fans, zero); // earlier fans of this batch carry none
+    for (uint32_t i = 0; i < n_fans; i++) {
+      FanNoiseRec r;
+      memcpy(&r, &noise[i], sizeof(r));
+      c->q_noise.push_back(r);
+    }
+    c->q_has_noise = true;
   }
   s.n_beams = beams;
   c->q_beams += beams;

@@ -109,6 +109,28 @@ struct FanRec {
 };
 static_assert(sizeof(FanRec) == 64, "FanRec");
 
+// stg_rt_fan_noise
+struct FanNoiseRec {
+  double range_noise_const, range_noise, angle_noise;
+  unsigned long long seed;
+};
+static_assert(sizeof(FanNoiseRec) == 32, "FanNoiseRec");
+
+// Counter-based random numbers for the sensor noise: a 64-bit mix of (seed, beam, launch, draw).
+__host__ __device__ inline unsigned long long noise_bits(unsigned long long seed, unsigned long long beam, unsigned long long epoch,
+                                                         unsigned draw)
+{
+  unsigned long long z = seed * 0x9e3779b97f4a7c15ull + beam * 0xbf58476d1ce4e5b9ull + epoch * 0x94d049bb133111ebull + draw;
+  z ^= z >> 30;
+  z *= 0xbf58476d1ce4e5b9ull;
+  z ^= z >> 27;
+  z *= 0x94d049bb133111ebull;
+  z ^= z >> 31;
+  return z;
+}
+// simpleNoise(), model_ranger.cc:173-177: 2 * (rand() % 1000 * 0.001 - 0.5)
+__host__ __device__ inline double noise_simple(unsigned long long bits) { return 2 * ((double)(bits % 1000ull) * 0.001 - 0.5); }
+
 struct FanBatchView {
   uint32_t n_fans;
   uint64_t n_beams;
@@ -117,6 +139,8 @@ struct FanBatchView {
   const uint32_t *fan_first_beam; // n_fans + 1 prefix sums
   const double *headings_in;      // EXPLICIT headings (may be null)
   const double *trig_in;          // strict mode (cos, sin) per beam (may be null)
+  const FanNoiseRec *noise;       // per fan sensor noise (may be null)
+  uint64_t noise_epoch;           // changes every launch, so every tick draws fresh noise
   double *heading;                // per beam: the heading World::Raytrace receives
   // outputs (any may be null)
   double *ranges, *intensities, *bearings;

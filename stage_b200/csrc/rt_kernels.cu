@@ -317,9 +317,14 @@ __global__ void __launch_bounds__(32) k2_fan_headings(FanBatchView b)
     const double incr = fan.fov / (double)(nm1 > 1u ? nm1 : 1u);
     const double start = n > 1 ? -fan.fov / 2.0 : 0.0;
     double a = fan.oa;
+    const double jitter = b.noise ? b.noise[f].angle_noise : 0.0;
+    const unsigned long long seed = b.noise ? (b.noise[f].seed ? b.noise[f].seed : fan.finder + 1ull) : 0ull;
     for (uint32_t t = 0; t < n; t++) {
-      const float fa = (float)a; // float savedAngle / distortedAngle with zero angle noise
-      heading[t] = (double)fa;
+      const float fa = (float)a; // float savedAngle (model_ranger.cc:237)
+      // float distortedAngle = a + sample_incr * angle_noise * simpleNoise() * 0.5 (:238); the noise
+      // term is exactly 0 without jitter, as there
+      heading[t] = jitter != 0.0 ? (double)(float)(a + incr * jitter * noise_simple(noise_bits(seed, first + t, b.noise_epoch, 0)) * 0.5)
+                                 : (double)fa;
       a = (double)fa + incr;
     }
     if (bearing)

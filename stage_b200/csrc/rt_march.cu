@@ -50,7 +50,22 @@ __global__ void __launch_bounds__(128, 8) k2_ray_march(GridView g, FanBatchView 
   trace::RayResult r;
   trace::trace_ray<kSteps>(g, fan, cosa, sina, r);
 
-  // K3 (ranger epilogue, fused): model_ranger.cc:243-251 with zero noise
+  // K3 (ranger epilogue, fused): model_ranger.cc:243-251
+  if (b.noise) { // "Apply noise only if it is in valid range" (:244-248)
+    const FanNoiseRec nz = b.noise[lo];
+    if ((nz.range_noise != 0.0 || nz.range_noise_const != 0.0) && r.range < fan->range) {
+      const unsigned long long seed = nz.seed ? nz.seed : fan->finder + 1ull;
+      const double u = noise_simple(noise_bits(seed, beam, b.noise_epoch, 1));
+      // generateGaussianNoise(variance), :181-200 (Box-Muller; the reference alternates cos / sin of one
+      // pair of draws, every beam here takes the cos branch of its own pair: same N(0, variance))
+      double r1 = (double)(noise_bits(seed, beam, b.noise_epoch, 2) >> 11) * (1.0 / 9007199254740992.0);
+      const double r2 = (double)(noise_bits(seed, beam, b.noise_epoch, 3) >> 11) * (1.0 / 9007199254740992.0) * 6.283185307179586;
+      if (r1 < 1e-100)
+        r1 = 1e-100;
+      const double gauss = sqrt(nz.range_noise_const * (-2.0 * log(r1))) * cos(r2);
+      r.range = r.range + r.range * nz.range_noise * u + gauss;
+    }
+  }
   if (b.ranges)
     b.ranges[beam] = r.range;
   if (b.intensities)

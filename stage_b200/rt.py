@@ -34,6 +34,7 @@ FIDUCIAL_DTYPE = np.dtype([("target", "<u4"), ("id", "<i4"), ("range", "<f8"), (
 BLOB_FINDER_DTYPE = np.dtype([("finder", "<u4"), ("scan_width", "<u4"), ("scan_height", "<u4"), ("layer", "u1"), ("pad", "u1", (3,)),
                               ("first_color", "<u4"), ("n_colors", "<u4"), ("ox", "<f8"), ("oy", "<f8"), ("oz", "<f8"),
                               ("oa", "<f8"), ("range", "<f8"), ("fov", "<f8")])
+FAN_NOISE_DTYPE = np.dtype([("range_noise_const", "<f8"), ("range_noise", "<f8"), ("angle_noise", "<f8"), ("seed", "<u8")])
 BLOB_DTYPE = np.dtype([("model", "<u4"), ("left", "<u4"), ("top", "<u4"), ("right", "<u4"), ("bottom", "<u4"), ("pad", "<u4"),
                        ("range", "<f8")])
 assert (FID_TARGET_DTYPE.itemsize, FID_FINDER_DTYPE.itemsize, FIDUCIAL_DTYPE.itemsize) == (72, 104, 88)
@@ -89,6 +90,7 @@ def lib():
         "stg_rt_fans_submit": (ctypes.c_int, [vp, u32, vp, vp, vp, ctypes.POINTER(FanOut)]),
         "stg_rt_fiducials_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
         "stg_rt_blobs_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
+        "stg_rt_fans_submit_noisy": (ctypes.c_int, [vp, u32, vp, vp, ctypes.POINTER(FanOut)]),
         "stg_rt_flush": (ctypes.c_int, [vp]),
         "stg_rt_sync": (ctypes.c_int, [vp]),
         "stg_rt_host_alloc": (vp, [vp, sz]),
@@ -121,7 +123,7 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "stg_rt_abi_version stg_rt_create stg_rt_destroy stg_rt_last_error stg_rt_model_upsert stg_rt_block_map "
-    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_blobs_submit stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
+    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
     "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_debug_trig").split()
@@ -243,6 +245,13 @@ class Context:
         self._check(self._L.stg_rt_blobs_submit(self._h, len(finders), _ptr(finders), len(colors),
                                                 _ptr(colors) if len(colors) else None, max_per_finder, _ptr(out), _ptr(cnt)))
         return out, cnt
+
+    def fans_submit_noisy(self, fans, noise, out):
+        fans = np.ascontiguousarray(fans, FAN_DTYPE)
+        noise = np.ascontiguousarray(noise, FAN_NOISE_DTYPE)
+        assert len(noise) == len(fans)
+        self._keep.append(out)
+        self._check(self._L.stg_rt_fans_submit_noisy(self._h, len(fans), _ptr(fans), _ptr(noise), ctypes.byref(out.struct)))
 
     def flush(self):
         self._check(self._L.stg_rt_flush(self._h))
