@@ -133,6 +133,13 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
   int32_t hit_model = -1, hit_x = 0, hit_y = 0;
   uint32_t cell_visits = 0, region_probes = 0;
   const bool layer1 = (fan->layer & 1) != 0;
+  // the direction bits as the loops want them (taken from the packed word, not from dx / dy, so that
+  // those doubles are dead after the set-up)
+  asm volatile("" : "+r"(flags));
+  const bool ymajor = (flags & kYMajor) != 0, runneg = (flags & kRunNeg) != 0;
+  const bool xneg = (flags & kXNeg) != 0, yneg = (flags & kYNeg) != 0;
+  const uint32_t aflip = runneg ? kRegionWidth - 1 : 0u, cflip = (flags & kCrossNeg) ? kRegionWidth - 1 : 0u;
+  const uint32_t wstep = (flags & kCrossNeg) ? ~0u : 1u;
   const uint32_t *occ = layer1 ? g.occ[1] : g.occ[0];
   bool hit = false;
 
@@ -148,36 +155,44 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
     }
     if (count) {
       // ---- populated region: integer walk over the occupancy masks (world.cc:823-882) ----
+      // Both in-region coordinates are counted in the direction of travel: ap along the run axis
+      // (bit ap of the direction-normalised mask), cp along the cross axis (mask number cp ^ cflip).
       need_crossings = true;
       const int32_t cx0 = ix0 & (kRegionWidth - 1), cy0 = iy0 & (kRegionWidth - 1);
-      int32_t c = (flags & kYMajor) ? cx0 : cy0;   // cross coordinate
-      int32_t ap = (flags & kYMajor) ? cy0 : cx0;  // run coordinate ...
-      if (flags & kRunNeg)
-        ap = kRegionWidth - 1 - ap;                // ... counted in the direction of travel
-      int32_t ka = 0, kc = 0;                      // run / cross steps taken in this region
-      const uint32_t *tile = occ + (size_t)region * kTileWords + ((flags & kYMajor) ? kRegionWidth : 0);
-      uint32_t word = __ldg(tile + c);
-      if (flags & kRunNeg)
+      const int32_t cp0 = (int32_t)((uint32_t)(ymajor ? cx0 : cy0) ^ cflip);
+      const int32_t ap0 = (int32_t)((uint32_t)(ymajor ? cy0 : cx0) ^ aflip);
+      int32_t cp = cp0, ap = ap0;
+      // word index of the current mask; the next mask in the direction of travel is wstep words on
+      uint32_t wi = region * kTileWords + (ymajor ? kRegionWidth : 0) + ((uint32_t)cp ^ cflip);
+      uint32_t word = __ldg(occ + wi);
+      if (runneg)
         word = __brev(word);
-      for (;;) {
-        // r = run steps before the next cross step: the smallest r >= 0 with E + r*b_run >= 0.
-        // E >= -b_cross always, so r <= r_max, and right after a cross step r is r_max or r_max-1.
-        int32_t r = 0;
-        if (E < 0) {
-          const int32_t t = -E;
-          r = r_max;
-          if (v1 >= t) {
-            r = r_max - 1;
-            while (r > 0 && (r - 1) * b_run >= t)
-              r--;
-          }
+      // r = run steps before the next cross step: the smallest r >= 0 with E + r*b_run >= 0. E >= -b_cross
+      // always, so r <= r_max. Entering a region E is anywhere in that range (one estimate + fix-up);
+      // right after a cross step r is r_max or r_max - 1 (one compare, below).
+      int32_t r = 0;
+      if (E < 0) {
+        const int32_t t = -E;
+        r = r_max;
+        if (v1 >= t) { // 1 <= ceil(t / b_run) <= r_max - 1 <= 32 and b_run > 0
+          r = __float2int_rz((float)t * __frcp_rn((float)b_run));
+          while (r * b_run < t)
+            r++;
+          while (r > 0 && (r - 1) * b_run >= t)
+            r--;
         }
-        int32_t m = min(min(r + 1, kRegionWidth - ap), n); // cells tested: a cell is only tested while n > 0
-        const uint32_t occupied = word & ((0xffffffffu >> (32 - m)) << ap);
-        if (occupied) {
+      }
+      for (;;) {
+        // the mask the walk needs after this run's cross step, requested before this run is tested
+        uint32_t ahead = 0;
+        if (cp < kRegionWidth - 1)
+          ahead = __ldg(occ + (wi + wstep));
+        const int32_t m = min(min(r + 1, kRegionWidth - ap), n); // cells tested: a cell is only tested while n > 0
+        uint32_t occupied = word & ((0xffffffffu >> (32 - m)) << ap);
+        while (occupied) {
           const int32_t ah = __ffs(occupied) - 1;
-          const uint32_t areal = (flags & kRunNeg) ? (uint32_t)(kRegionWidth - 1 - ah) : (uint32_t)ah;
-          const uint32_t hx = (flags & kYMajor) ? (uint32_t)c : areal, hy = (flags & kYMajor) ? areal : (uint32_t)c;
+          const uint32_t areal = (uint32_t)ah ^ aflip, creal = (uint32_t)cp ^ cflip;
+          const uint32_t hx = ymajor ? creal : areal, hy = ymajor ? areal : creal;
           const int32_t mdl = resolve_cell(layer1 ? g.slots[1] : g.slots[0], g.slot_mask,
                                            reinterpret_cast<const uint4 *>(layer1 ? g.blk_rec[1] : g.blk_rec[0]),
                                            g.mdl_root, fan, (region << (2 * kRBits)) | (hy << kRBits) | hx);
@@ -185,38 +200,38 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
             hit_model = mdl;
             hit_x = (ix0 & ~(kRegionWidth - 1)) + (int32_t)hx;
             hit_y = (iy0 & ~(kRegionWidth - 1)) + (int32_t)hy;
-            ka += ah - ap;
             if (kSteps)
               cell_visits += (uint32_t)(ah - ap) + 1u;
+            ap = ah;
             hit = true;
             break;
           }
-          word &= ~(1u << ah); // nothing in that cell stops this ray: look past it
-          continue;
+          occupied &= occupied - 1u; // nothing in that cell stops this ray: look past it
         }
+        if (hit)
+          break;
         if (kSteps)
           cell_visits += (uint32_t)m;
         n -= m;
-        if (m == r + 1) { // the whole run, then the cross step
-          ap += r;
-          ka += r;
-          c += (flags & kCrossNeg) ? -1 : 1;
-          kc += 1;
-          E += r * b_run - b_cross;
-          if ((uint32_t)c >= (uint32_t)kRegionWidth || n <= 0)
-            break;
-          word = __ldg(tile + c);
-          if (flags & kRunNeg)
-            word = __brev(word);
-        } else { // cut short by the region edge or by the end of the ray
-          ka += m;
+        if (m != r + 1) { // cut short by the region edge or by the end of the ray
+          ap += m;
           E += m * b_run;
           break;
         }
+        // the whole run, then the cross step
+        ap += r;
+        cp += 1;
+        wi += wstep;
+        E += r * b_run - b_cross;
+        if (cp >= kRegionWidth || n <= 0)
+          break;
+        word = runneg ? __brev(ahead) : ahead;
+        r = v1 >= -E ? r_max - 1 : r_max;
       }
       // bring the double position up to date (world.cc:868-877 did it step by step)
-      gx = seq_add(gx, (flags & kYMajor) ? kc : ka, (flags & kXNeg) != 0);
-      gy = seq_add(gy, (flags & kYMajor) ? ka : kc, (flags & kYNeg) != 0);
+      const int32_t ka = ap - ap0, kc = cp - cp0; // run / cross steps taken in this region
+      gx = seq_add(gx, ymajor ? kc : ka, xneg);
+      gy = seq_add(gy, ymajor ? ka : kc, yneg);
       if (hit)
         break;
     } else {
