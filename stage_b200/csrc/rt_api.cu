@@ -769,9 +769,11 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
   g.n_models = cfg->max_models;
   CUC(cudaMalloc(&g.reg_count, c->n_regions * 4));
   CUC(cudaMemsetAsync(g.reg_count, 0, c->n_regions * 4, c->stream));
+  // both layers' tiles in one allocation: the march addresses them with one 32-bit word index
+  CUC(cudaMalloc(&g.occ[0], 2 * c->n_regions * kTileWords * 4));
+  CUC(cudaMemsetAsync(g.occ[0], 0, 2 * c->n_regions * kTileWords * 4, c->stream));
+  g.occ[1] = g.occ[0] + c->n_regions * kTileWords;
   for (int L = 0; L < 2; L++) {
-    CUC(cudaMalloc(&g.occ[L], c->n_regions * kTileWords * 4));
-    CUC(cudaMemsetAsync(g.occ[L], 0, c->n_regions * kTileWords * 4, c->stream));
     CUC(cudaMalloc(&g.slots[L], (size_t)c->slot_cap * 8));
     CUC(cudaMemsetAsync(g.slots[L], 0, (size_t)c->slot_cap * 8, c->stream));
     CUC(cudaMalloc(&g.blk_rec[L], (size_t)cfg->max_blocks * sizeof(BlockRec)));
@@ -806,7 +808,7 @@ int stg_rt_destroy(stg_rt_ctx *c)
   cudaSetDevice(c->cfg.device);
   cudaStreamSynchronize(c->stream);
   GridView &g = c->g;
-  void *dev[] = { g.reg_count, g.occ[0], g.occ[1], g.slots[0], g.slots[1], g.blk_rec[0], g.blk_rec[1], c->spare_slots,
+  void *dev[] = { g.reg_count, g.occ[0], g.slots[0], g.slots[1], g.blk_rec[0], g.blk_rec[1], c->spare_slots,
                   g.mdl_root, g.mdl_ranger_return, g.mdl_flags, c->d_blob.p };
   for (void *p : dev)
     if (p)

@@ -22,8 +22,12 @@ namespace stg {
 
 namespace {
 
+#ifndef STG_MARCH_CTAS_PER_SM
+#define STG_MARCH_CTAS_PER_SM 8 // of 128 threads: 64 registers per thread
+#endif
+
 template <bool kSteps>
-__global__ void __launch_bounds__(128, 8) k2_ray_march(GridView g, FanBatchView b)
+__global__ void __launch_bounds__(128, STG_MARCH_CTAS_PER_SM) k2_ray_march(GridView g, FanBatchView b)
 {
   const uint64_t beam = b.beam_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (beam >= b.beam_end)

@@ -139,8 +139,9 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
   const bool ymajor = (flags & kYMajor) != 0, runneg = (flags & kRunNeg) != 0;
   const bool xneg = (flags & kXNeg) != 0, yneg = (flags & kYNeg) != 0;
   const uint32_t aflip = runneg ? kRegionWidth - 1 : 0u, cflip = (flags & kCrossNeg) ? kRegionWidth - 1 : 0u;
-  const uint32_t wstep = (flags & kCrossNeg) ? ~0u : 1u;
-  const uint32_t *occ = layer1 ? g.occ[1] : g.occ[0];
+  const uint32_t wstep = (flags & kCrossNeg) ? ~0u : 1u, revmask = runneg ? ~0u : 0u;
+  const int32_t rm1 = r_max - 1;
+  const uint32_t occ_layer = layer1 ? (uint32_t)(g.occ[1] - g.occ[0]) : 0u; // one allocation, rt_api.cu
   bool hit = false;
 
   while (n > 0) {
@@ -163,10 +164,9 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
       const int32_t ap0 = (int32_t)((uint32_t)(ymajor ? cy0 : cx0) ^ aflip);
       int32_t cp = cp0, ap = ap0;
       // word index of the current mask; the next mask in the direction of travel is wstep words on
-      uint32_t wi = region * kTileWords + (ymajor ? kRegionWidth : 0) + ((uint32_t)cp ^ cflip);
-      uint32_t word = __ldg(occ + wi);
-      if (runneg)
-        word = __brev(word);
+      uint32_t wi = occ_layer + region * kTileWords + (ymajor ? kRegionWidth : 0) + ((uint32_t)cp ^ cflip);
+      uint32_t word = __ldg(g.occ[0] + wi);
+      word ^= (word ^ __brev(word)) & revmask;
       // r = run steps before the next cross step: the smallest r >= 0 with E + r*b_run >= 0. E >= -b_cross
       // always, so r <= r_max. Entering a region E is anywhere in that range (one estimate + fix-up);
       // right after a cross step r is r_max or r_max - 1 (one compare, below).
@@ -186,7 +186,7 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
         // the mask the walk needs after this run's cross step, requested before this run is tested
         uint32_t ahead = 0;
         if (cp < kRegionWidth - 1)
-          ahead = __ldg(occ + (wi + wstep));
+          ahead = __ldg(g.occ[0] + (wi + wstep));
         const int32_t m = min(min(r + 1, kRegionWidth - ap), n); // cells tested: a cell is only tested while n > 0
         uint32_t occupied = word & ((0xffffffffu >> (32 - m)) << ap);
         while (occupied) {
@@ -225,8 +225,8 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
         E += r * b_run - b_cross;
         if (cp >= kRegionWidth || n <= 0)
           break;
-        word = runneg ? __brev(ahead) : ahead;
-        r = v1 >= -E ? r_max - 1 : r_max;
+        word = ahead ^ ((ahead ^ __brev(ahead)) & revmask);
+        r = rm1 + (int32_t)((uint32_t)(v1 + E) >> 31); // v1 >= -E ? r_max - 1 : r_max
       }
       // bring the double position up to date (world.cc:868-877 did it step by step)
       const int32_t ka = ap - ap0, kc = cp - cp0; // run / cross steps taken in this region

@@ -74,7 +74,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    # STG_RT_LIBRARY: load this build of the library instead (kernel experiments; same ABI, checked below)
+    path = os.environ.get("STG_RT_LIBRARY") or _build.build()
     L = ctypes.CDLL(path)
     vp, u32, i32, f64, u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int32, ctypes.c_double, ctypes.c_uint64
     sz = ctypes.c_size_t
