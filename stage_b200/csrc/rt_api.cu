@@ -763,7 +763,7 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
   c->cell_x1 = c->cell_x0 + g.nrx * 32 - 1;
   c->cell_y1 = c->cell_y0 + g.nry * 32 - 1;
   const uint64_t entries = cfg->max_cell_entries ? cfg->max_cell_entries : (1u << 22);
-  c->slot_cap = next_pow2(2 * entries);
+  c->slot_cap = std::max<uint32_t>(next_pow2(2 * entries), 16 * kSectorSlots);
   g.slot_mask = c->slot_cap - 1;
   g.n_blocks = cfg->max_blocks;
   g.n_models = cfg->max_models;

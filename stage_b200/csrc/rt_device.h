@@ -12,6 +12,32 @@ constexpr int kSRBits = 10;                  // region.hh:15 SRBITS: a SuperRegi
 
 constexpr unsigned long long kSlotEmpty = 0ull;
 constexpr unsigned long long kSlotTomb = ~0ull;
+constexpr uint32_t kSectorSlots = 4; // slots per 32-byte sector
+
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t mix32(uint32_t k)
+{
+  k ^= k >> 16;
+  k *= 0x7feb352du;
+  k ^= k >> 15;
+  k *= 0x846ca68bu;
+  k ^= k >> 16;
+  return k;
+}
+
+// Where the probe sequence of a cell key starts: at a 32-byte sector (4 slots), which the lookup
+// reads whole; from there on it is linear probing, slot by slot. (Tried and dropped: one 64-byte
+// bucket per 4 x 4-cell patch, so that neighbouring beams' lookups share sectors - fewer DRAM
+// sectors but longer probe runs; the march and K1 both got slower.)
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t slot_home(uint32_t key, uint32_t slot_mask)
+{
+  return (mix32(key) * kSectorSlots) & slot_mask;
+}
 
 // The replicated world state one GPU holds. Passed to kernels by value.
 //
@@ -27,6 +53,7 @@ constexpr unsigned long long kSlotTomb = ~0ull;
 //  slots[L][h]         open-addressing multimap (cell -> block) holding the CONTENT of the occupied
 //                      cells: entry = (cell_key << 32) | (block_id + 1), cell_key = r*1024 + cy*32
 //                      + cx. 0 = empty, ~0 = tombstone. Only consulted where an occ bit is set.
+//                      Probing starts at slot_home(cell_key) (above).
 //  blk_rec[L][b]       BlockRec below: what the hit test reads about block b (Block::global_z
 //                      block.cc:177-180, owning model, tree root for Model::IsRelated, Model::vis bits
 //                      stage.hh:1924-1937) plus seq, the order key of b's latest Map on layer L:

@@ -21,16 +21,6 @@ namespace stg {
 // shared helpers
 // ------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ uint32_t mix32(uint32_t k)
-{
-  k ^= k >> 16;
-  k *= 0x7feb352du;
-  k ^= k >> 15;
-  k *= 0x846ca68bu;
-  k ^= k >> 16;
-  return k;
-}
-
 __device__ __forceinline__ unsigned long long ld_slot(const unsigned long long *p)
 {
   return *reinterpret_cast<const volatile unsigned long long *>(p);
@@ -153,7 +143,7 @@ __device__ __forceinline__ void k1_remove(const GridView &g, const unsigned char
       const CellAddr c = cell_addr(g, x, y);
       const unsigned long long entry = ((unsigned long long)c.key << 32) | (unsigned long long)(e.block + 1u);
       unsigned long long *slots = g.slots[e.layer & 1];
-      uint32_t h = mix32(c.key) & g.slot_mask;
+      uint32_t h = slot_home(c.key, g.slot_mask);
       for (uint32_t probes = 0; probes <= g.slot_mask; probes++) { // EraseAll: every copy goes
         const unsigned long long cur = ld_slot(slots + h);
         if (cur == kSlotEmpty)
@@ -181,7 +171,7 @@ __device__ __forceinline__ void k1_fixup(const GridView &g, const unsigned char 
       edge_cell(e, t - e.first_step, x, y);
       const CellAddr c = cell_addr(g, x, y);
       const unsigned long long *slots = g.slots[e.layer & 1];
-      uint32_t h = mix32(c.key) & g.slot_mask;
+      uint32_t h = slot_home(c.key, g.slot_mask);
       for (uint32_t probes = 0; probes <= g.slot_mask; probes++) {
         const unsigned long long cur = ld_slot(slots + h);
         if (cur == kSlotEmpty)
@@ -210,7 +200,7 @@ __device__ __forceinline__ void k1_insert(const GridView &g, const unsigned char
       const CellAddr c = cell_addr(g, x, y);
       const unsigned long long entry = ((unsigned long long)c.key << 32) | (unsigned long long)(e.block + 1u);
       unsigned long long *slots = g.slots[e.layer & 1];
-      uint32_t h = mix32(c.key) & g.slot_mask;
+      uint32_t h = slot_home(c.key, g.slot_mask);
       for (uint32_t probes = 0; probes <= g.slot_mask;) {
         const unsigned long long cur = ld_slot(slots + h);
         if (cur == kSlotEmpty || cur == kSlotTomb) {
@@ -256,7 +246,7 @@ __global__ void __launch_bounds__(256) k1_rehash(const unsigned long long *src, 
     const unsigned long long cur = src[i];
     if (cur == kSlotEmpty || cur == kSlotTomb)
       continue;
-    uint32_t h = mix32((uint32_t)(cur >> 32)) & slot_mask;
+    uint32_t h = slot_home((uint32_t)(cur >> 32), slot_mask);
     for (;;) {
       if (atomicCAS(dst + h, kSlotEmpty, cur) == kSlotEmpty)
         break;

@@ -10,19 +10,10 @@
 namespace stg {
 namespace trace {
 
-__device__ __forceinline__ uint32_t mix32(uint32_t k)
-{
-  k ^= k >> 16;
-  k *= 0x7feb352du;
-  k ^= k >> 15;
-  k *= 0x846ca68bu;
-  k ^= k >> 16;
-  return k;
-}
-
 // Resolve an occupied cell: among the blocks rendered into it that pass the z test and the
 // predicate, the one first in Cell::blocks[layer] order wins (world.cc:841-862). Reads the fan's
 // constants from its (L1-resident) record rather than holding them in registers during the march.
+// The probe sequence is read a 32-byte sector (4 slots) at a time; it ends at the first empty slot.
 static __device__ __noinline__ int32_t resolve_cell(const unsigned long long *slots, uint32_t slot_mask, const uint4 *recs,
                                              const uint32_t *mdl_root, const FanRec *fan, uint32_t key)
 {
@@ -31,12 +22,19 @@ static __device__ __noinline__ int32_t resolve_cell(const unsigned long long *sl
   const uint32_t finder_root = __ldg(mdl_root + finder);
   unsigned long long best_seq = ~0ull;
   int32_t best_model = -1;
-  uint32_t h = mix32(key) & slot_mask;
-  for (uint32_t probes = 0; probes <= slot_mask; probes++) {
-    const unsigned long long cur = __ldg(slots + h);
-    if (cur == kSlotEmpty)
-      break;
-    if ((uint32_t)(cur >> 32) == key) {
+  uint32_t h = slot_home(key, slot_mask);
+  for (uint32_t probes = 0; probes <= slot_mask; probes += 4) {
+    const ulonglong2 p01 = __ldg(reinterpret_cast<const ulonglong2 *>(slots + h));
+    const ulonglong2 p23 = __ldg(reinterpret_cast<const ulonglong2 *>(slots + h + 2));
+    // which of the four precede the first empty slot and hold this cell
+    const bool e0 = p01.x == kSlotEmpty, e1 = e0 || p01.y == kSlotEmpty, e2 = e1 || p23.x == kSlotEmpty,
+               e3 = e2 || p23.y == kSlotEmpty;
+    uint32_t match = (!e0 && (uint32_t)(p01.x >> 32) == key ? 1u : 0u) | (!e1 && (uint32_t)(p01.y >> 32) == key ? 2u : 0u) |
+                     (!e2 && (uint32_t)(p23.x >> 32) == key ? 4u : 0u) | (!e3 && (uint32_t)(p23.y >> 32) == key ? 8u : 0u);
+    while (match) {
+      const uint32_t j = __ffs(match) - 1;
+      match &= match - 1u;
+      const unsigned long long cur = j == 0 ? p01.x : j == 1 ? p01.y : j == 2 ? p23.x : p23.y;
       const uint32_t blk = (uint32_t)cur - 1u;
       const uint4 z = __ldg(recs + 2 * (size_t)blk), o = __ldg(recs + 2 * (size_t)blk + 1);
       const double zmin = __hiloint2double((int)z.y, (int)z.x), zmax = __hiloint2double((int)z.w, (int)z.z);
@@ -58,7 +56,9 @@ static __device__ __noinline__ int32_t resolve_cell(const unsigned long long *sl
         }
       }
     }
-    h = (h + 1) & slot_mask;
+    if (e3)
+      break;
+    h = (h + 4) & slot_mask;
   }
   return best_model;
 }
