@@ -467,6 +467,14 @@ int reserve_outputs(stg_rt_ctx *c, FanArrays &a, uint64_t beams, uint32_t want)
   return rc;
 }
 
+uint32_t uniform_samples_of(const FanRec *fans, size_t n)
+{
+  for (size_t i = 1; i < n; i++)
+    if (fans[i].n_samples != fans[0].n_samples)
+      return 0;
+  return n ? fans[0].n_samples : 0;
+}
+
 FanBatchView view_of(const FanArrays &a, uint32_t n_fans, uint64_t beams, uint32_t want, bool trig, bool headings)
 {
   FanBatchView v;
@@ -622,6 +630,7 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   if ((want & STG_RT_WANT_STEPS) && (rc = pin_reserve(c, c->h_steps, beams * 8))) return rc;
 
   FanBatchView v = view_of(c->d, n_fans, beams, want, c->q_has_trig, b_head != 0);
+  v.uniform_samples = uniform_samples_of(c->q_fans.data(), n_fans);
   v.fans = (const FanRec *)c->d_in.p;
   v.fan_first_beam = (const uint32_t *)((const char *)c->d_in.p + o_first);
   v.headings_in = b_head ? (const double *)((const char *)c->d_in.p + o_head) : nullptr;
@@ -1193,7 +1202,8 @@ int stg_rt_set_trace(stg_rt_ctx *c, stg_rt_set *s)
     c->stats.h2d_bytes += s->fans.size() * sizeof(FanRec);
     s->fans_dirty = false;
   }
-  const FanBatchView v = view_of(s->d, (uint32_t)s->fans.size(), s->n_beams, s->want, s->has_trig, s->has_headings);
+  FanBatchView v = view_of(s->d, (uint32_t)s->fans.size(), s->n_beams, s->want, s->has_trig, s->has_headings);
+  v.uniform_samples = uniform_samples_of(s->fans.data(), s->fans.size());
   CU(c, cudaEventRecord(c->t_ev[1][0], c->stream));
   launch_fan_headings(v, c->stream);
   CU(c, cudaEventRecord(c->t_ev[1][1], c->stream));

@@ -164,6 +164,7 @@ struct FanBatchView {
   uint64_t beam_begin, beam_end; // the slice of beams one march launch covers (chunked launches)
   const FanRec *fans;
   const uint32_t *fan_first_beam; // n_fans + 1 prefix sums
+  uint32_t uniform_samples;       // n_samples if every fan has the same, else 0 (beam -> fan by division)
   const double *headings_in;      // EXPLICIT headings (may be null)
   const double *trig_in;          // strict mode (cos, sin) per beam (may be null)
   const FanNoiseRec *noise;       // per fan sensor noise (may be null)

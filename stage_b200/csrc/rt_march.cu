@@ -35,6 +35,10 @@ __global__ void __launch_bounds__(128, STG_MARCH_CTAS_PER_SM) k2_ray_march(GridV
 
   // which fan does this beam belong to
   uint32_t lo = 0, hi = b.n_fans;
+  if (b.uniform_samples) { // the usual case: one sensor type
+    lo = (uint32_t)beam / b.uniform_samples;
+    hi = lo + 1;
+  }
   while (hi - lo > 1) {
     const uint32_t mid = (lo + hi) >> 1;
     if (__ldg(b.fan_first_beam + mid) <= beam)

@@ -14,7 +14,7 @@ namespace trace {
 // predicate, the one first in Cell::blocks[layer] order wins (world.cc:841-862). Reads the fan's
 // constants from its (L1-resident) record rather than holding them in registers during the march.
 // The probe sequence is read a 32-byte sector (4 slots) at a time; it ends at the first empty slot.
-static __device__ __noinline__ int32_t resolve_cell(const unsigned long long *slots, uint32_t slot_mask, const uint4 *recs,
+static __device__ __forceinline__ int32_t resolve_cell(const unsigned long long *slots, uint32_t slot_mask, const uint4 *recs,
                                              const uint32_t *mdl_root, const FanRec *fan, uint32_t key)
 {
   const uint32_t finder = fan->finder, pred = fan->pred, ztest = fan->ztest;
