@@ -335,6 +335,11 @@ void *stg_rt_get_stream(stg_rt_ctx *ctx);
    (World::Raytrace's zero-heading substitution included, world.cc:773-775). cos_sin = 2n doubles.
    Synchronous. Used to check the device trig against the host C library. */
 int stg_rt_debug_trig(stg_rt_ctx *ctx, uint64_t n, const double *headings, double *cos_sin);
+/* Diagnostics: the per-beam headings the device derives for these fans (the float-rounded running
+   angle of ModelRanger::Sensor::Update, model_ranger.cc:237-241,254; the even spacing of
+   World::Raytrace(fan), world.cc:731-743), sum(n_samples) doubles in fan order. Synchronous. */
+int stg_rt_debug_headings(stg_rt_ctx *ctx, uint32_t n_fans, const stg_rt_fan *fans, const double *headings_in,
+                          double *headings_out);
 
 /* Counters since create: kernel launches by kind, rays traced, bytes copied each way. */
 typedef struct {

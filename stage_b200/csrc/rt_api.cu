@@ -1671,6 +1671,58 @@ int stg_rt_debug_trig(stg_rt_ctx *c, uint64_t n, const double *headings, double 
   return rc;
 }
 
+int stg_rt_debug_headings(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *fans, const double *headings_in, double *headings_out)
+{
+  if (!c || (n_fans && (!fans || !headings_out)))
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  std::vector<uint32_t> first(n_fans + 1, 0);
+  uint64_t n_in = 0;
+  for (uint32_t i = 0; i < n_fans; i++) {
+    if (fans[i].angles > STG_RT_ANGLES_EXPLICIT || (fans[i].angles == STG_RT_ANGLES_EXPLICIT && !headings_in))
+      return fail(c, STG_RT_EINVAL, "debug_headings: fan %u: bad angle mode", i);
+    first[i + 1] = first[i] + fans[i].n_samples;
+    if (fans[i].angles == STG_RT_ANGLES_EXPLICIT)
+      n_in = std::max<uint64_t>(n_in, (uint64_t)fans[i].first_heading + fans[i].n_samples);
+  }
+  const uint64_t beams = first[n_fans];
+  if (!beams)
+    return STG_RT_OK;
+  static_assert(sizeof(stg_rt_fan) == sizeof(FanRec), "fan record");
+  DevBuf dfans, dfirst, din, dout;
+  int rc = dev_reserve(c, dfans, (size_t)n_fans * sizeof(FanRec));
+  if (!rc) rc = dev_reserve(c, dfirst, (size_t)(n_fans + 1) * 4);
+  if (!rc) rc = dev_reserve(c, din, n_in * 8 + 8);
+  if (!rc) rc = dev_reserve(c, dout, beams * 8);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(dfans.p, fans, (size_t)n_fans * sizeof(FanRec), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(dfirst.p, first.data(), (size_t)(n_fans + 1) * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && n_in)
+      e = cudaMemcpyAsync(din.p, headings_in, n_in * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+      FanBatchView v;
+      memset(&v, 0, sizeof(v));
+      v.n_fans = n_fans;
+      v.n_beams = v.beam_end = beams;
+      v.fans = (const FanRec *)dfans.p;
+      v.fan_first_beam = (const uint32_t *)dfirst.p;
+      v.headings_in = n_in ? (const double *)din.p : nullptr;
+      v.heading = (double *)dout.p;
+      launch_fan_headings(v, c->stream);
+      e = cudaMemcpyAsync(headings_out, dout.p, beams * 8, cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (e == cudaSuccess)
+      e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess)
+      rc = fail(c, STG_RT_ECUDA, "debug_headings: %s", cudaGetErrorString(e));
+  }
+  for (DevBuf *b : { &dfans, &dfirst, &din, &dout })
+    if (b->p)
+      cudaFree(b->p);
+  return rc;
+}
+
 int stg_rt_kernel_times(stg_rt_ctx *c, float ms[3])
 {
   if (!c || !ms)

@@ -288,16 +288,35 @@ void launch_rehash(const unsigned long long *src, unsigned long long *dst, uint3
 }
 
 // ------------------------------------------------------------------------------------------
-// K2a: per-beam headings. One thread per fan; the ranger rule is a sequential float-rounding
-// recurrence (model_ranger.cc:237-241,254: the running angle goes through a `float` every beam),
-// so a fan's headings cannot be evaluated per beam independently.
+// K2a: per-beam headings
 // ------------------------------------------------------------------------------------------
+
+// K2a: the heading every beam's World::Raytrace receives. A ranger's headings are a serial
+// recurrence through a float (model_ranger.cc:237-241,254): fa(t) = (float)a(t), a(t+1) = (double)fa(t)
+// + incr. One warp per fan cuts it into 32 chunks. A chunk's entry state is the float of the beam
+// before it, fa(t0 - 1). Every lane runs its chunk from an assumed entry state; the result stands
+// only when every lane's exit state fa(t1 - 1) is, bit for bit, the entry state the next lane
+// assumed - then by induction from a(0) = origin.a every chunk was computed from the true state.
+// Where a link does not hold, the lane after the first broken link takes the (now certain) exit
+// state of its predecessor, and the lanes beyond it re-guess by translation: within a float binade
+// the recurrence adds a constant per step, so a chunk's net advance D = exit - entry does not
+// depend on its entry state. At least one more link becomes certain per round (at most 32 rounds,
+// the serial cost); 2-5 rounds are typical, the extra ones where a fan sweeps through binade
+// borders (|a| = 2, 1, 1/2, ... and the sign change).
+__device__ __forceinline__ float ranger_chunk(bool first_lane, double oa, float entry, double incr, uint32_t steps)
+{
+  double a = first_lane ? oa : (double)entry + incr;
+  float fa = entry; // an empty chunk hands its entry state on
+  for (uint32_t i = 0; i < steps; i++) {
+    fa = (float)a;
+    a = (double)fa + incr;
+  }
+  return fa;
+}
 
 __global__ void __launch_bounds__(32) k2_fan_headings(FanBatchView b)
 {
-  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= b.n_fans)
-    return;
+  const uint32_t f = blockIdx.x, lane = threadIdx.x;
   const FanRec fan = b.fans[f];
   const uint32_t first = b.fan_first_beam[f], n = fan.n_samples;
   double *heading = b.heading + first;
@@ -306,30 +325,56 @@ __global__ void __launch_bounds__(32) k2_fan_headings(FanBatchView b)
     const uint32_t nm1 = n - 1u; // unsigned, like std::max(sample_count - 1, 1u)
     const double incr = fan.fov / (double)(nm1 > 1u ? nm1 : 1u);
     const double start = n > 1 ? -fan.fov / 2.0 : 0.0;
-    double a = fan.oa;
+    const uint32_t chunk = (n + 31u) / 32u;
+    const uint32_t t0 = min(lane * chunk, n), t1 = min(t0 + chunk, n); // this lane's beams
+    // entry state fa(t0 - 1): first guess from the ideal sweep (lane 0 starts from origin.a itself)
+    float entry = t0 > 0 ? (float)(fan.oa + (double)(t0 - 1u) * incr) : 0.0f;
+    for (int round = 0; round < 33; round++) {
+      const float exit = ranger_chunk(lane == 0, fan.oa, entry, incr, t1 - t0);
+      const float next_entry = __shfl_down_sync(0xffffffffu, entry, 1);
+      const bool link_ok = lane == 31 || __float_as_uint(exit) == __float_as_uint(next_entry);
+      const uint32_t broken = __ballot_sync(0xffffffffu, !link_ok);
+      if (!broken)
+        break;
+      const uint32_t j = __ffs(broken) - 1; // lanes 0..j hold the true state; so does the exit of lane j
+      // inclusive scan of the advances of lanes j+1.. (floats and their differences: exact in double)
+      double adv = lane > j ? (double)exit - (double)entry : 0.0;
+      for (int d = 1; d < 32; d <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, adv, d);
+        if (lane >= (uint32_t)d)
+          adv += up;
+      }
+      const float anchor = __shfl_sync(0xffffffffu, exit, j);    // true entry state of lane j+1
+      const double before = __shfl_up_sync(0xffffffffu, adv, 1); // sum of the advances of lanes j+1..lane-1
+      if (lane == j + 1)
+        entry = anchor;
+      else if (lane > j + 1)
+        entry = (float)((double)anchor + before);
+    }
+    // emit (model_ranger.cc:237-238): float savedAngle; float distortedAngle = a + incr * angle_noise *
+    // simpleNoise() * 0.5 - the noise term is exactly 0 without jitter, as there
     const double jitter = b.noise ? b.noise[f].angle_noise : 0.0;
     const unsigned long long seed = b.noise ? (b.noise[f].seed ? b.noise[f].seed : fan.finder + 1ull) : 0ull;
-    for (uint32_t t = 0; t < n; t++) {
-      const float fa = (float)a; // float savedAngle (model_ranger.cc:237)
-      // float distortedAngle = a + sample_incr * angle_noise * simpleNoise() * 0.5 (:238); the noise
-      // term is exactly 0 without jitter, as there
+    double a = lane == 0 ? fan.oa : (double)entry + incr;
+    for (uint32_t t = t0; t < t1; t++) {
+      const float fa = (float)a;
       heading[t] = jitter != 0.0 ? (double)(float)(a + incr * jitter * noise_simple(noise_bits(seed, first + t, b.noise_epoch, 0)) * 0.5)
                                  : (double)fa;
       a = (double)fa + incr;
     }
     if (bearing)
-      for (uint32_t t = 0; t < n; t++)
+      for (uint32_t t = lane; t < n; t += 32)
         bearing[t] = start + ((double)t) * incr;
   } else if (fan.angles == 1 /* STG_RT_ANGLES_EVEN_FOV */) {
     const double starta = fan.fov / 2.0 - fan.oa;
-    for (uint32_t s = 0; s < n; s++) {
+    for (uint32_t s = lane; s < n; s += 32) {
       const double h = ((double)s * fan.fov / (double)(n - 1u)) - starta;
       heading[s] = h;
       if (bearing)
         bearing[s] = h - fan.oa;
     }
   } else {
-    for (uint32_t s = 0; s < n; s++) {
+    for (uint32_t s = lane; s < n; s += 32) {
       const double h = b.headings_in[fan.first_heading + s];
       heading[s] = h;
       if (bearing)
@@ -342,7 +387,7 @@ void launch_fan_headings(const FanBatchView &b, void *stream)
 {
   if (!b.n_fans)
     return;
-  k2_fan_headings<<<(b.n_fans + 31) / 32, 32, 0, (cudaStream_t)stream>>>(b);
+  k2_fan_headings<<<b.n_fans, 32, 0, (cudaStream_t)stream>>>(b);
 }
 
 // K2, the ray march, lives in rt_march.cu.

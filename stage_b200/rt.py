@@ -112,6 +112,7 @@ def lib():
         "stg_rt_get_stats": (ctypes.c_int, [vp, ctypes.POINTER(Stats)]),
         "stg_rt_kernel_times": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_float * 3)]),
         "stg_rt_debug_trig": (ctypes.c_int, [vp, u64, vp, vp]),
+        "stg_rt_debug_headings": (ctypes.c_int, [vp, u32, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)  # AttributeError if the library does not export what the header declares
@@ -127,7 +128,7 @@ EXPORTED_SYMBOLS = (
     "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
-    "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_debug_trig").split()
+    "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_debug_trig stg_rt_debug_headings").split()
 
 
 def _ptr(a):
@@ -311,6 +312,14 @@ class Context:
         h = np.ascontiguousarray(headings, np.float64)
         out = np.empty((len(h), 2), np.float64)
         self._check(self._L.stg_rt_debug_trig(self._h, len(h), _ptr(h), _ptr(out)))
+        return out
+
+    def debug_headings(self, fans, headings=None):
+        """the per-beam headings the device derives for these fans, concatenated in fan order"""
+        fans = np.ascontiguousarray(fans, FAN_DTYPE)
+        h = None if headings is None else np.ascontiguousarray(headings, np.float64)
+        out = np.empty(int(fans["n_samples"].sum()), np.float64)
+        self._check(self._L.stg_rt_debug_headings(self._h, len(fans), _ptr(fans), _ptr(h), _ptr(out)))
         return out
 
     # ---- multi-GPU deltas / plumbing
