@@ -133,8 +133,9 @@ struct stg_rt_ctx {
     uint32_t *user_count = nullptr;
     size_t out_bytes = 0, count_bytes = 0;
     bool pending = false;
+    uint32_t n_finders = 0, max_per_finder = 0; // fiducials: to unpack the packed records
   } fid_job, blob_job;
-  DevBuf d_fid_grid, d_fid_in, d_fid_out, d_fid_count, d_blob_in, d_blob_out, d_blob_count, d_mdl_color;
+  DevBuf d_fid_grid, d_fid_in, d_fid_out, d_fid_count, d_fid_off, d_blob_in, d_blob_out, d_blob_count, d_mdl_color;
   PinBuf h_fid_in, h_fid_out, h_fid_count, h_blob_in, h_blob_out, h_blob_count;
   FanArrays bd; // the blobfinders' scan-line fans
   std::vector<double> mdl_color; // rgba per model
@@ -544,9 +545,19 @@ int deliver_post_locked(stg_rt_ctx *c)
   if (!c->fid_job.pending && !c->blob_job.pending)
     return 0;
   CU(c, cudaStreamSynchronize(c->stream));
-  if (c->fid_job.pending) {
-    memcpy(c->fid_job.user_out, c->h_fid_out.p, c->fid_job.out_bytes);
-    memcpy(c->fid_job.user_count, c->h_fid_count.p, c->fid_job.count_bytes);
+  if (c->fid_job.pending) { // unpack: finder f's records follow finder f-1's in the staging buffer
+    const uint32_t *cnt = (const uint32_t *)c->h_fid_count.p;
+    const FiducialRec *packed = (const FiducialRec *)c->h_fid_out.p;
+    FiducialRec *user = (FiducialRec *)c->fid_job.user_out;
+    size_t at = 0;
+    for (uint32_t f = 0; f < c->fid_job.n_finders; f++) {
+      const uint32_t k = std::min(cnt[f], c->fid_job.max_per_finder);
+      if (k)
+        memcpy(user + (size_t)f * c->fid_job.max_per_finder, packed + at, (size_t)k * sizeof(FiducialRec));
+      at += k;
+    }
+    memcpy(c->fid_job.user_count, cnt, (size_t)c->fid_job.n_finders * 4);
+    c->stats.d2h_bytes += at * sizeof(FiducialRec) + (size_t)c->fid_job.n_finders * 4;
     c->fid_job.pending = false;
   }
   if (c->blob_job.pending) {
@@ -826,7 +837,7 @@ int stg_rt_destroy(stg_rt_ctx *c)
   free_fan_arrays(c->bd);
   if (c->d_in.p)
     cudaFree(c->d_in.p);
-  for (DevBuf *b : { &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
+  for (DevBuf *b : { &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_fid_off, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
     if (b->p)
       cudaFree(b->p);
   for (PinBuf *b : { &c->h_fid_in, &c->h_fid_out, &c->h_fid_count, &c->h_blob_in, &c->h_blob_out, &c->h_blob_count })
@@ -1504,14 +1515,17 @@ int stg_rt_fiducials_submit(stg_rt_ctx *c, uint32_t n_targets, const stg_rt_fid_
     launch_fiducials(c->g, v, c->stream);
     c->stats.launches_post++;
   }
+  // only the records come home (packed, written by the device into the page-locked staging buffer);
+  // stg_rt_sync puts them back at the caller's fixed stride
+  if ((rc = dev_reserve(c, c->d_fid_off, (size_t)(n_finders + 1) * 4)))
+    return rc;
+  launch_fid_pack(v, (uint32_t *)c->d_fid_off.p, c->h_fid_out.p, (uint32_t *)c->h_fid_count.p, c->stream);
+  c->stats.launches_post += 2;
   CU(c, cudaGetLastError());
-  CU(c, cudaMemcpyAsync(c->h_fid_out.p, c->d_fid_out.p, b_out, cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaMemcpyAsync(c->h_fid_count.p, c->d_fid_count.p, b_cnt, cudaMemcpyDeviceToHost, c->stream));
-  c->stats.d2h_bytes += b_out + b_cnt;
   c->fid_job.user_out = out;
   c->fid_job.user_count = out_count;
-  c->fid_job.out_bytes = b_out;
-  c->fid_job.count_bytes = b_cnt;
+  c->fid_job.n_finders = n_finders;
+  c->fid_job.max_per_finder = max_per_finder;
   c->fid_job.pending = true;
   return STG_RT_OK;
 }

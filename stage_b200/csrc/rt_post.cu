@@ -197,6 +197,52 @@ __global__ void __launch_bounds__(128) k3_fiducials_grid(GridView g, FidBatchVie
   }
 }
 
+// ---- packing the fiducial records for the trip home ---------------------------------------------
+// out[] is fixed-stride (max_per_finder records per finder) and mostly empty: at BASELINE config 4
+// (100k finders) it is 845 MB of which 60 MB are records. Only the records cross PCIe: offsets =
+// exclusive scan of min(count, max_per_finder), then one warp per finder copies its records, 8-byte
+// word by word, into page-locked host memory (consecutive finders -> consecutive addresses).
+__global__ void __launch_bounds__(1024) k3_fid_pack_scan(FidBatchView b, uint32_t *offsets)
+{
+  __shared__ uint32_t partial[1024];
+  const uint32_t n = b.n_finders, tid = threadIdx.x;
+  const uint32_t per = (n + 1023) / 1024, lo = min(tid * per, n), hi = min(lo + per, n);
+  uint32_t sum = 0;
+  for (uint32_t i = lo; i < hi; i++)
+    sum += min(b.out_count[i], b.max_per_finder);
+  partial[tid] = sum;
+  __syncthreads();
+  for (uint32_t o = 1; o < 1024; o <<= 1) {
+    const uint32_t add = tid >= o ? partial[tid - o] : 0;
+    __syncthreads();
+    partial[tid] += add;
+    __syncthreads();
+  }
+  uint32_t run = tid ? partial[tid - 1] : 0;
+  for (uint32_t i = lo; i < hi; i++) {
+    offsets[i] = run;
+    run += min(b.out_count[i], b.max_per_finder);
+  }
+  if (tid == 1023)
+    offsets[n] = partial[1023];
+}
+
+__global__ void __launch_bounds__(128) k3_fid_pack(FidBatchView b, const uint32_t *offsets, unsigned long long *packed,
+                                                   uint32_t *count_home)
+{
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= b.n_finders)
+    return;
+  constexpr uint32_t kWords = sizeof(FiducialRec) / 8;
+  const uint32_t cnt = b.out_count[warp], n_words = min(cnt, b.max_per_finder) * kWords;
+  const unsigned long long *src = reinterpret_cast<const unsigned long long *>(b.out + (size_t)warp * b.max_per_finder);
+  unsigned long long *dst = packed + (size_t)offsets[warp] * kWords;
+  for (uint32_t i = lane; i < n_words; i += 32)
+    dst[i] = src[i];
+  if (lane == 0)
+    count_home[warp] = cnt;
+}
+
 // ColorMatchIgnoreAlpha, model_blobfinder.cc:109-113
 __device__ __forceinline__ bool color_match(const double *a, const double *c)
 {
@@ -302,6 +348,15 @@ void launch_fiducials_grid(const GridView &g, const FidBatchView &b, const FidGr
     k3_fid_bin_scan<<<1, 1024, 0, s>>>(v);
   }
   k3_fiducials_grid<<<(b.n_finders * 32 + 127) / 128, 128, 0, s>>>(g, b, v);
+}
+
+void launch_fid_pack(const FidBatchView &b, uint32_t *offsets, void *packed_host, uint32_t *count_host, void *stream)
+{
+  if (!b.n_finders)
+    return;
+  cudaStream_t s = (cudaStream_t)stream;
+  k3_fid_pack_scan<<<1, 1024, 0, s>>>(b, offsets);
+  k3_fid_pack<<<(b.n_finders * 32 + 127) / 128, 128, 0, s>>>(b, offsets, (unsigned long long *)packed_host, count_host);
 }
 
 void launch_blobs(const GridView &g, const BlobBatchView &b, void *stream)

@@ -224,12 +224,18 @@ class Context:
         self._check(self._L.stg_rt_fans_submit(self._h, len(fans), _ptr(fans), _ptr(headings), _ptr(trig),
                                                ctypes.byref(out.struct)))
 
-    def fiducials_submit(self, targets, finders, max_per_finder=16):
-        """-> (out[n_finders, max_per_finder] of FIDUCIAL_DTYPE, count[n_finders]); valid after sync()."""
+    def fiducials_submit(self, targets, finders, max_per_finder=16, into=None):
+        """-> (out[n_finders, max_per_finder] of FIDUCIAL_DTYPE, count[n_finders]); valid after sync().
+        into = (out, count) arrays of those shapes to reuse (only out[f, :count[f]] is written)."""
         targets = np.ascontiguousarray(targets, FID_TARGET_DTYPE)
         finders = np.ascontiguousarray(finders, FID_FINDER_DTYPE)
-        out = np.zeros((len(finders), max_per_finder), FIDUCIAL_DTYPE)
-        cnt = np.zeros(len(finders), np.uint32)
+        if into is None:
+            out = np.zeros((len(finders), max_per_finder), FIDUCIAL_DTYPE)
+            cnt = np.zeros(len(finders), np.uint32)
+        else:
+            out, cnt = into
+            assert out.shape == (len(finders), max_per_finder) and out.dtype == FIDUCIAL_DTYPE and out.flags.c_contiguous
+            assert cnt.shape == (len(finders),) and cnt.dtype == np.uint32
         self._keep.append((out, cnt))
         self._check(self._L.stg_rt_fiducials_submit(self._h, len(targets), _ptr(targets), len(finders), _ptr(finders),
                                                     max_per_finder, _ptr(out), _ptr(cnt)))
