@@ -172,6 +172,40 @@ void Block::UnMap(unsigned int layer)
   rec.events.push_back(e);
 }
 
+static thread_local int tl_collision_depth = 0;
+
+Model *Model::TestCollision()
+{
+  typedef Model *(*fn_t)(Model *);
+  static fn_t fn = real<fn_t>("_ZN3Stg5Model13TestCollisionEv");
+  tl_collision_depth++; // the children's tests come through here too (model.cc:672): log the top call
+  Model *hit = fn(this);
+  tl_collision_depth--;
+  if (tl_collision_depth || !rec.active || tl_quiet)
+    return hit;
+  std::lock_guard<std::mutex> g(rec.mu);
+  TraceEvent e;
+  memset(&e, 0, sizeof(e));
+  e.type = TRACE_EV_COLLISION;
+  e.layer = (uint8_t)(world->updates % 2);
+  e.model = id;
+  e.block = hit ? hit->id + 1 : 0;
+  e.first = (uint32_t)rec.aux.size();
+  std::vector<Model *> todo(1, this); // depth first, children in order
+  uint32_t n = 0;
+  while (!todo.empty()) {
+    Model *m = todo.back();
+    todo.pop_back();
+    for (size_t i = 0; i < m->blockgroup.blocks.size(); i++, n++)
+      rec.aux.push_back((double)block_id_locked(&m->blockgroup.blocks[i]));
+    for (size_t i = m->children.size(); i-- > 0;)
+      todo.push_back(m->children[i]);
+  }
+  e.n_pts = (uint16_t)n;
+  rec.events.push_back(e);
+  return hit;
+}
+
 RaytraceResult World::Raytrace(const Ray &r)
 {
   typedef RaytraceResult (*fn_t)(World *, const Ray &);
@@ -584,6 +618,17 @@ int ref_model_subscribe(void *wv, const char *name)
   if (!m)
     return -1;
   m->Subscribe();
+  return 0;
+}
+
+// ModelPosition::SetSpeed (model_position.cc:595): what a controller does to drive a robot.
+int ref_model_set_speed(void *wv, const char *name, double x, double y, double a)
+{
+  World *w = (World *)wv;
+  ModelPosition *m = dynamic_cast<ModelPosition *>(w->GetModel(std::string(name)));
+  if (!m)
+    return -1;
+  m->SetSpeed(x, y, a);
   return 0;
 }
 

@@ -633,7 +633,48 @@ typedef struct {
   uint64_t scans, scan_mismatch;
   uint64_t fiducial_updates, fiducial_mismatch, blob_updates, blob_mismatch;
   double max_range_err;
+  uint64_t collision_tests, collision_mismatch, collision_hits;
 } T1ReplayStats;
+
+// Model::TestCollision (model.cc:666-679) over BlockGroup::TestCollision (blockgroup.cc:41-50) and
+// Block::TestCollision (block.cc:129-168): `blocks` are the dense ids of the model's own blocks and
+// then its descendants', depth first - the order those three visit them in. Returns the id of the
+// first model found in the way, or -1.
+//   per block: nothing to test unless its own model has obstacle_return (:136); a block reaching
+//   below the floor collides with the ground model, id 0 (:137-138, World::GetGround); otherwise
+//   every cell the block is rendered into on `layer`, in rendering order (Block::rendered_cells,
+//   filled by MapPoly edge by edge), and every block listed in that cell, in list order: the first
+//   whose model is another one, is an obstacle, is not related (same tree) and overlaps in z (:153-157).
+int32_t t1_test_collision(void *wv, int layer, uint32_t n_blocks, const uint32_t *blocks)
+{
+  const T1World *w = (const T1World *)wv;
+  for (uint32_t i = 0; i < n_blocks; i++) {
+    if (blocks[i] >= w->blocks.size() || !w->blocks[blocks[i]].known)
+      continue;
+    const T1Block &b = w->blocks[blocks[i]];
+    const T1Model &own = w->models[b.model];
+    if (!(own.flags & TRACE_FLAG_OBSTACLE_RETURN))
+      continue;
+    if (b.zmin < 0)
+      return 0;
+    const std::vector<int64_t> &cells = b.rendered[layer];
+    for (size_t c = 0; c < cells.size(); c++) {
+      const int32_t x = (int32_t)(uint32_t)cells[c], y = (int32_t)(cells[c] >> 32); // cell_key
+      const T1Region *reg = w->find_region(x >> RBITS, y >> RBITS);
+      if (!reg || reg->cells[layer].empty())
+        continue;
+      const std::vector<uint32_t> &list = reg->cells[layer][(x & (REGIONWIDTH - 1)) + (y & (REGIONWIDTH - 1)) * REGIONWIDTH];
+      for (size_t k = 0; k < list.size(); k++) {
+        const T1Block &tb = w->blocks[list[k]];
+        const T1Model &tm = w->models[tb.model];
+        if (tb.model != b.model && (tm.flags & TRACE_FLAG_OBSTACLE_RETURN) && tm.root != own.root && tb.zmin <= b.zmax &&
+            tb.zmax >= b.zmin)
+          return (int32_t)tb.model;
+      }
+    }
+  }
+  return -1;
+}
 
 // Replay a recorded reference trace through T1 and compare every ray with the reference's answer.
 // Returns the world (caller may dump its grid) or NULL on a malformed file.
@@ -677,6 +718,15 @@ void *t1_replay(const char *path, T1ReplayStats *st)
       st->unmaps++;
     } else if (e.type == TRACE_EV_TICK) {
       st->ticks++;
+    } else if (e.type == TRACE_EV_COLLISION) {
+      std::vector<uint32_t> ids(e.n_pts);
+      for (uint32_t k = 0; k < e.n_pts; k++)
+        ids[k] = (uint32_t)aux[e.first + k];
+      st->collision_tests++;
+      if (t1_test_collision(w, e.layer, e.n_pts, ids.data()) != (int32_t)e.block - 1)
+        st->collision_mismatch++;
+      if (e.block)
+        st->collision_hits++;
     } else if (e.type == TRACE_EV_FIDUCIAL) {
       const double *a = &aux[e.first];
       const uint32_t nt = (uint32_t)a[13], nf = e.block;

@@ -17,10 +17,10 @@
 #define STG_TRACE_FORMAT_H
 #include <stdint.h>
 
-#define STG_TRACE_MAGIC "STGTRC04"
+#define STG_TRACE_MAGIC "STGTRC05"
 
 enum { TRACE_EV_MAP = 1, TRACE_EV_UNMAP = 2, TRACE_EV_RAYS = 3, TRACE_EV_TICK = 4,
-       TRACE_EV_RANGER_SCAN = 5, TRACE_EV_FIDUCIAL = 6, TRACE_EV_BLOB = 7 };
+       TRACE_EV_RANGER_SCAN = 5, TRACE_EV_FIDUCIAL = 6, TRACE_EV_BLOB = 7, TRACE_EV_COLLISION = 8 };
 
 /* predicate kinds: which of the reference's static ray_test_func_t a ray was traced with */
 enum {
@@ -96,5 +96,12 @@ typedef struct {
  *   n_blobs  x { r, g, b, left, top, right, bottom, range }                            8 doubles each */
 #define TRACE_BLOB_HEADER_DOUBLES 9
 #define TRACE_BLOB_RESULT_DOUBLES 8
+
+/* COLLISION: one top-level Model::TestCollision() (model.cc:666-679; ModelPosition::Move calls it
+ * right after re-mapping the model, model_position.cc:549-554). event.model = the model tested,
+ * event.layer = World::updates % 2 (the layer Block::TestCollision reads, block.cc:140),
+ * event.block = id of the model it returned + 1, 0 for no collision, event.n_pts = n, aux[first ..
+ * first + n) = the dense ids of the blocks it may visit, in visiting order: the model's own
+ * BlockGroup, then each child's, depth first (blockgroup.cc:41-50, model.cc:668-676). */
 
 #endif

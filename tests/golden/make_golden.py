@@ -4,8 +4,15 @@ reference World can never be destroyed.
 
     python tests/golden/make_golden.py
 
-Each trace records every Block::Map / Block::UnMap / World::Raytrace / ModelRanger::Sensor::Update
-the reference performed (format: oracle/trace_format.h), compressed with xz.
+Each trace records every Block::Map / Block::UnMap / World::Raytrace / ModelRanger::Sensor::Update /
+ModelFiducial::Update / ModelBlobfinder::Update / Model::TestCollision the reference performed
+(format: oracle/trace_format.h), compressed with xz.
+
+bumper_150 is not one of the reference's shipped worlds: none of those makes robots collide within
+a few hundred ticks, so Model::TestCollision would only ever be seen answering "nothing". It is a
+walled arena with a rotated pillar, a bridge the robots fit under (z separation), a model without
+obstacle_return, and 14 position models - some with a child model sticking out in front - driven
+straight ahead (a few on arcs) by ModelPosition::SetSpeed until they run into things and each other.
 """
 import lzma
 import os
@@ -19,6 +26,45 @@ WORLDS = [("simple.world", 120, "simple_120"),     # BASELINE config 1: Pioneer 
           ("lsp_test.world", 20, "lsp_test_20")]   # the Player-plugin test world: fiducial + blobfinder
 # lsp_test.world has no controllers: switch its sensors on the way a Player client would
 SUBSCRIBE = {"lsp_test.world": ["r0.fiducial:0", "r1.fiducial:0", "r0.blobfinder:0", "r1.blobfinder:0"]}
+
+
+
+def bumper_world_text():
+    import numpy as np
+    rng = np.random.RandomState(3)
+    lines = ["resolution 0.02", "interval_sim 100", "threads 1", "quit_time 3600", ""]
+
+    def box(name, x, y, z, a, sx, sy, sz, extra=""):
+        lines.append('model ( name "%s" pose [ %.3f %.3f %.3f %.3f ] size [ %.3f %.3f %.3f ] %s )' % (name, x, y, z, a, sx, sy, sz, extra))
+    box("wn", 0, 4.05, 0, 0, 8.2, 0.1, 0.5)
+    box("ws", 0, -4.05, 0, 0, 8.2, 0.1, 0.5)
+    box("we", 4.05, 0, 0, 0, 0.1, 8.2, 0.5)
+    box("ww", -4.05, 0, 0, 0, 0.1, 8.2, 0.5)
+    box("pillar", 1.0, 1.0, 0, 30, 0.6, 0.6, 0.5)
+    box("bridge", -1.5, 0, 1.0, 0, 0.3, 5.0, 0.2)
+    box("ghost", 0, -1.5, 0, 0, 1.0, 1.0, 0.5, "obstacle_return 0")
+    for i in range(BUMPERS):
+        x, y = rng.uniform(-3.3, 3.3, 2)
+        a = rng.uniform(-180, 180)
+        child = 'model ( name "arm%d" pose [ 0.25 0 0 0 ] size [ 0.3 0.08 0.1 ] )' % i if i % 3 == 0 else ""
+        lines.append('position ( name "r%d" pose [ %.3f %.3f 0 %.3f ] size [ 0.4 0.3 0.3 ] %s )' % (i, x, y, a, child))
+    return "\n".join(lines) + "\n"
+
+
+BUMPERS = 14
+BUMPER_CHILD = r"""
+import sys, os
+sys.path.insert(0, %r)
+import oracle_lib
+w = oracle_lib.RefWorld(text=open(sys.argv[1]).read())
+for i in range(int(sys.argv[4])):
+    w.subscribe("r%%d" %% i)
+    w.set_speed("r%%d" %% i, 0.5, 0.0, 0.3 if i %% 4 == 0 else 0.0)
+w.update(int(sys.argv[2]))
+w.trace_end(sys.argv[3])
+sys.stdout.flush()
+os._exit(0)
+"""
 
 CHILD = r"""
 import sys, os
@@ -34,10 +80,18 @@ os._exit(0)
 """
 
 if __name__ == "__main__":
-    for world, ticks, name in WORLDS:
+    for world, ticks, name in WORLDS + [("bumper", 150, "bumper_150")]:
         raw = os.path.join(HERE, name + ".trc")
-        subprocess.run([sys.executable, "-c", CHILD % TESTS, world, str(ticks), raw] + SUBSCRIBE.get(world, []), check=True,
-                       stdout=subprocess.DEVNULL)
+        if world == "bumper":
+            wf = os.path.join(HERE, "bumper.world.tmp")
+            with open(wf, "w") as f:
+                f.write(bumper_world_text())
+            subprocess.run([sys.executable, "-c", BUMPER_CHILD % TESTS, wf, str(ticks), raw, str(BUMPERS)], check=True,
+                           stdout=subprocess.DEVNULL)
+            os.remove(wf)
+        else:
+            subprocess.run([sys.executable, "-c", CHILD % TESTS, world, str(ticks), raw] + SUBSCRIBE.get(world, []), check=True,
+                           stdout=subprocess.DEVNULL)
         with open(raw, "rb") as f, lzma.open(raw + ".xz", "wb", preset=9) as g:
             g.write(f.read())
         os.remove(raw)

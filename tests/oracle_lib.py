@@ -28,7 +28,8 @@ class ReplayStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in (
         "rays", "range_mismatch", "model_mismatch", "maps", "unmaps", "ticks", "cell_visits",
         "region_probes", "scans", "scan_mismatch", "fiducial_updates", "fiducial_mismatch", "blob_updates",
-        "blob_mismatch")] + [("max_range_err", ctypes.c_double)]
+        "blob_mismatch")] + [("max_range_err", ctypes.c_double)] + [(n, ctypes.c_uint64) for n in (
+        "collision_tests", "collision_mismatch", "collision_hits")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -58,6 +59,7 @@ def t1():
         L.t1_dump_grid.restype = ctypes.c_int64
         L.t1_dump_grid.argtypes = [vp, vp, ctypes.c_int64, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
         L.t1_replay.restype, L.t1_replay.argtypes = vp, [ctypes.c_char_p, ctypes.POINTER(ReplayStats)]
+        L.t1_test_collision.restype, L.t1_test_collision.argtypes = ctypes.c_int32, [vp, ctypes.c_int, u32, vp]
         _t1 = L
     return _t1
 
@@ -138,6 +140,11 @@ class T1World:
         self.L.t1_even_fan(self.h, finder, layer, kind, ztest, _p(gpose), rng, fov, n, _p(hits))
         return hits
 
+    def test_collision(self, layer, blocks):
+        """Model::TestCollision over these blocks (own, then descendants', depth first) -> model id or -1"""
+        blocks = np.ascontiguousarray(blocks, np.uint32)
+        return int(self.L.t1_test_collision(self.h, layer, len(blocks), _p(blocks)))
+
     def dump_grid(self):
         nc = ctypes.c_int64(0)
         n = self.L.t1_dump_grid(self.h, None, 0, None, 0, ctypes.byref(nc))
@@ -191,6 +198,7 @@ def ref():
         L.ref_ranger_scan.argtypes = [vp, ctypes.c_uint32, ctypes.c_int, vp, vp, vp, ctypes.c_int]
         L.ref_model_subscribe.argtypes = [vp, ctypes.c_char_p]
         L.ref_fiducials_on_main_thread.argtypes = [ctypes.c_int]
+        L.ref_model_set_speed.argtypes = [vp, ctypes.c_char_p, ctypes.c_double, ctypes.c_double, ctypes.c_double]
         _ref = L
     return _ref
 
@@ -238,6 +246,9 @@ class RefWorld:
 
     def subscribe(self, name):
         assert self.L.ref_model_subscribe(self.h, name.encode()) == 0, name
+
+    def set_speed(self, name, x, y, a):
+        assert self.L.ref_model_set_speed(self.h, name.encode(), x, y, a) == 0, name
 
     def model_id(self, name):
         return self.L.ref_model_id(self.h, name.encode())

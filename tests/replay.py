@@ -176,6 +176,7 @@ class T1Replay:
         w = self.world = make_t1(trace)
         self.hits = np.zeros(len(trace.rays), oracle_lib.T1_HIT)
         self.scans = []
+        self.collisions = []
         ticks = 0
         for ev in trace.events:
             t = ev["type"]
@@ -184,6 +185,9 @@ class T1Replay:
                             float(ev["zmax"]), trace.polygon(ev))
             elif t == trace_io.EV_UNMAP:
                 w.block_unmap(int(ev["block"]), int(ev["layer"]))
+            elif t == trace_io.EV_COLLISION:
+                _, layer, blocks, _ = trace.collision(ev)
+                self.collisions.append(w.test_collision(layer, blocks))
             elif t == trace_io.EV_RAYS:
                 first, cnt = int(ev["first"]), int(ev["model"])
                 self.hits[first:first + cnt] = w.raytrace(rays_to_t1(trace.rays[first:first + cnt]))

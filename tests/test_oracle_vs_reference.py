@@ -14,7 +14,7 @@ import replay
 import trace_io
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-TRACES = ["simple_120", "fasr_300", "lsp_test_20"]
+TRACES = ["simple_120", "fasr_300", "lsp_test_20", "bumper_150"]
 
 
 @pytest.fixture(scope="module", params=TRACES)
@@ -29,17 +29,20 @@ def raw_trace(request, tmp_path_factory):
 def test_t1_reproduces_every_reference_ray(raw_trace):
     name, path = raw_trace
     st, _ = oracle_lib.t1_replay(path)
+    if name == "bumper_150":  # no sensors: the Model::TestCollision recording (make_golden.py)
+        assert st["collision_tests"] == 2100 and st["collision_hits"] > 1500 and st["collision_mismatch"] == 0, st
+        return
     assert st["rays"] > (30000 if name != "lsp_test_20" else 3000) and st["ticks"] >= 20
-    assert st["model_mismatch"] == 0
+    assert st["model_mismatch"] == 0 and st["collision_mismatch"] == 0
     # bit-exact on a host with the libm the traces were recorded with; never worse than an ulp or so
     assert st["max_range_err"] <= 1e-12, st
     assert st["range_mismatch"] == 0 or os.environ.get("STG_FOREIGN_LIBM"), st
     assert st["scan_mismatch"] == 0 or os.environ.get("STG_FOREIGN_LIBM"), st
     assert st["fiducial_mismatch"] == 0 and st["blob_mismatch"] == 0, st
     if name == "simple_120":
-        assert st["scans"] == 240
+        assert st["scans"] == 240 and st["collision_tests"] > 200
     if name == "fasr_300":
-        assert st["scans"] > 1000 and st["fiducial_updates"] > 1000
+        assert st["scans"] > 1000 and st["fiducial_updates"] > 1000 and st["collision_tests"] > 5000
     if name == "lsp_test_20":
         assert st["fiducial_updates"] == 40 and st["blob_updates"] == 40
 
@@ -68,6 +71,11 @@ def test_reference_known_answers_lsp_test():
 def test_python_replay_matches_c_replay(raw_trace):
     name, path = raw_trace
     tr = trace_io.load(path)
+    if name == "bumper_150":
+        r = replay.T1Replay(tr)
+        want = [tr.collision(ev)[3] for ev in tr.events if ev["type"] == trace_io.EV_COLLISION]
+        assert r.collisions == want and len(set(want)) > 8  # walls, pillar, robots, a child arm; never the ghost or the bridge
+        return
     r = replay.T1Replay(tr, max_ticks=40)
     n = 0
     for ev in tr.events:

@@ -5,8 +5,8 @@ import lzma
 
 import numpy as np
 
-MAGIC = b"STGTRC04"
-EV_MAP, EV_UNMAP, EV_RAYS, EV_TICK, EV_RANGER_SCAN, EV_FIDUCIAL, EV_BLOB = 1, 2, 3, 4, 5, 6, 7
+MAGIC = b"STGTRC05"
+EV_MAP, EV_UNMAP, EV_RAYS, EV_TICK, EV_RANGER_SCAN, EV_FIDUCIAL, EV_BLOB, EV_COLLISION = 1, 2, 3, 4, 5, 6, 7, 8
 SCAN_HEADER_DOUBLES = 6
 KIND_RANGER, KIND_UNRELATED, KIND_GRIPPER = 0, 1, 2
 
@@ -55,6 +55,11 @@ class Trace:
         d["colors"] = a[9:9 + 3 * nc].reshape(nc, 3)
         d["blobs"] = a[9 + 3 * nc:9 + 3 * nc + 8 * nb].reshape(nb, 8)
         return d
+
+    def collision(self, ev):
+        """COLLISION event -> (model, layer, blocks in visiting order, hit model id or -1)"""
+        n = int(ev["n_pts"])
+        return int(ev["model"]), int(ev["layer"]), self.aux[ev["first"]:ev["first"] + n].astype(np.uint32), int(ev["block"]) - 1
 
     def polygon(self, ev):
         """(n_pts, 2) int32 pixel-space vertices of a MAP event."""
