@@ -239,6 +239,22 @@ int stg_rt_fiducials_submit(stg_rt_ctx *ctx, uint32_t n_targets, const stg_rt_fi
                             uint32_t n_finders, const stg_rt_fid_finder *finders,
                             uint32_t max_per_finder, stg_rt_fiducial *out, uint32_t *out_count);
 
+/* ---- collision tests ------------------------------------------------------------------------ */
+
+/* Model::TestCollision (model.cc:666-679) for n_queries models at once, against the device grid as
+   it stands after every Map / UnMap issued so far. Query q covers blocks[query_first[q] ..
+   query_first[q + 1]): the model's own blocks in BlockGroup order, then its descendants', depth
+   first - the order Model::TestCollision and BlockGroup::TestCollision (blockgroup.cc:41-50) visit
+   them in. layer = World::updates % 2, the layer Block::TestCollision reads (block.cc:140).
+   hit_model[q] = id of the model the reference would return: the first block found, walking the
+   query's blocks, their rendered cells and those cells' block lists in order, that belongs to
+   another, unrelated model with obstacle_return and overlaps in z (block.cc:143-160);
+   ground_model (World::GetGround()'s id) for a block that reaches below z = 0 (:137-138); -1 for no
+   collision. Blocks of models without obstacle_return test nothing (:136). Delivered by
+   stg_rt_sync, like sensor results. */
+int stg_rt_collisions_test(stg_rt_ctx *ctx, int layer, uint32_t n_queries, const uint32_t *query_first,
+                           const uint32_t *blocks, uint32_t ground_model, int32_t *hit_model);
+
 /* ---- blobfinders ----------------------------------------------------------------------------- */
 
 /* One ModelBlobfinder::Update (model_blobfinder.cc:165-250). 72 bytes. */

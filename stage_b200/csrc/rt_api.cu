@@ -138,6 +138,13 @@ struct stg_rt_ctx {
   DevBuf d_fid_grid, d_fid_in, d_fid_out, d_fid_count, d_fid_off, d_blob_in, d_blob_out, d_blob_count, d_mdl_color;
   PinBuf h_fid_in, h_fid_out, h_fid_count, h_blob_in, h_blob_out, h_blob_count;
   FanArrays bd; // the blobfinders' scan-line fans
+  struct CollisionJob {
+    int32_t *user_hit = nullptr;
+    std::vector<int32_t> fallback; // per query: what to report when no cell test hits (-1, or the ground model)
+    bool pending = false;
+  } col_job;
+  DevBuf d_col_in, d_col_hit;
+  PinBuf h_col_in, h_col_hit;
   std::vector<double> mdl_color; // rgba per model
   bool mdl_color_dirty = true;
 
@@ -235,7 +242,7 @@ uint32_t root_flags_of(const stg_rt_ctx *c, uint32_t model)
 {
   const ModelUpd &m = c->models[model];
   return (m.root & kRecRootMask) | (m.ranger_return < 0 ? kRecNoRanger : 0u) |
-         ((m.flags & STG_RT_VIS_GRIPPER_RETURN) ? kRecGripper : 0u);
+         ((m.flags & STG_RT_VIS_GRIPPER_RETURN) ? kRecGripper : 0u) | ((m.flags & STG_RT_VIS_OBSTACLE_RETURN) ? kRecObstacle : 0u);
 }
 
 // Units sorted so that the blob (and, when it has to be split, successive blobs) insert in Map-call
@@ -542,9 +549,15 @@ void deliver_array(stg_rt_ctx *c, void *user, const PinBuf &stage, uint64_t firs
 
 int deliver_post_locked(stg_rt_ctx *c)
 {
-  if (!c->fid_job.pending && !c->blob_job.pending)
+  if (!c->fid_job.pending && !c->blob_job.pending && !c->col_job.pending)
     return 0;
   CU(c, cudaStreamSynchronize(c->stream));
+  if (c->col_job.pending) {
+    const int32_t *hit = (const int32_t *)c->h_col_hit.p;
+    for (size_t q = 0; q < c->col_job.fallback.size(); q++)
+      c->col_job.user_hit[q] = hit[q] >= 0 ? hit[q] : c->col_job.fallback[q];
+    c->col_job.pending = false;
+  }
   if (c->fid_job.pending) { // unpack: finder f's records follow finder f-1's in the staging buffer
     const uint32_t *cnt = (const uint32_t *)c->h_fid_count.p;
     const FiducialRec *packed = (const FiducialRec *)c->h_fid_out.p;
@@ -740,7 +753,7 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
     return fail(nullptr, STG_RT_EINVAL, "stg_rt_create: bad config (struct_size %u, expected %zu)",
                 cfg ? cfg->struct_size : 0u, sizeof(stg_rt_config));
   if (!(cfg->ppm > 0) || cfg->sreg_nx < 1 || cfg->sreg_ny < 1 || (int64_t)cfg->sreg_nx * cfg->sreg_ny > 4095 ||
-      cfg->max_models < 1 || cfg->max_models >= (1u << 30) || cfg->max_blocks < 1)
+      cfg->max_models < 1 || cfg->max_models > kRecRootMask || cfg->max_blocks < 1)
     return fail(nullptr, STG_RT_EINVAL, "stg_rt_create: bad ppm / extent / capacities");
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
@@ -837,10 +850,10 @@ int stg_rt_destroy(stg_rt_ctx *c)
   free_fan_arrays(c->bd);
   if (c->d_in.p)
     cudaFree(c->d_in.p);
-  for (DevBuf *b : { &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_fid_off, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
+  for (DevBuf *b : { &c->d_col_in, &c->d_col_hit, &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_fid_off, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
     if (b->p)
       cudaFree(b->p);
-  for (PinBuf *b : { &c->h_fid_in, &c->h_fid_out, &c->h_fid_count, &c->h_blob_in, &c->h_blob_out, &c->h_blob_count })
+  for (PinBuf *b : { &c->h_col_in, &c->h_col_hit, &c->h_fid_in, &c->h_fid_out, &c->h_fid_count, &c->h_blob_in, &c->h_blob_out, &c->h_blob_count })
     if (b->p)
       cudaFreeHost(b->p);
   PinBuf *pins[] = { &c->h_blob, &c->h_in, &c->h_ranges, &c->h_intens, &c->h_bearings, &c->h_hit_model, &c->h_hit_cell, &c->h_steps };
@@ -1527,6 +1540,74 @@ int stg_rt_fiducials_submit(stg_rt_ctx *c, uint32_t n_targets, const stg_rt_fid_
   c->fid_job.n_finders = n_finders;
   c->fid_job.max_per_finder = max_per_finder;
   c->fid_job.pending = true;
+  return STG_RT_OK;
+}
+
+int stg_rt_collisions_test(stg_rt_ctx *c, int layer, uint32_t n_queries, const uint32_t *query_first, const uint32_t *blocks,
+                           uint32_t ground_model, int32_t *hit_model)
+{
+  if (!c || layer < 0 || layer > 1 || (n_queries && (!query_first || !hit_model)))
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!n_queries)
+    return STG_RT_OK;
+  const uint32_t n_ids = query_first[n_queries];
+  if (n_ids && !blocks)
+    return STG_RT_EINVAL;
+  size_t n_edges = 0;
+  for (uint32_t q = 0; q < n_queries; q++) {
+    if (query_first[q + 1] < query_first[q])
+      return fail(c, STG_RT_EINVAL, "collisions_test: query_first is not ascending at %u", q);
+    for (uint32_t i = query_first[q]; i < query_first[q + 1]; i++) {
+      if (blocks[i] >= c->cfg.max_blocks || !c->blocks[blocks[i]].known)
+        return fail(c, STG_RT_EINVAL, "collisions_test: query %u names unknown block %u", q, blocks[i]);
+      n_edges += c->blocks[blocks[i]].host_mapped[layer] ? c->blocks[blocks[i]].host_xy[layer].size() / 2 : 0;
+      n_edges += c->blocks[blocks[i]].dev_xy[layer].size() / 2; // upper bound: whichever copy is current
+    }
+  }
+  int rc = flush_locked(c); // the grid the test reads includes every Map / UnMap issued so far
+  if (rc || (rc = deliver_post_locked(c)))
+    return rc;
+  const size_t b_q = (size_t)n_queries * sizeof(CollisionQuery), b_in = b_q + n_edges * sizeof(EdgeRec);
+  if ((rc = pin_reserve(c, c->h_col_in, b_in)) || (rc = dev_reserve(c, c->d_col_in, b_in + 16)) ||
+      (rc = pin_reserve(c, c->h_col_hit, (size_t)n_queries * 4)) || (rc = dev_reserve(c, c->d_col_hit, (size_t)n_queries * 4)))
+    return rc;
+  CollisionQuery *qr = (CollisionQuery *)c->h_col_in.p;
+  EdgeRec *e0 = (EdgeRec *)((char *)c->h_col_in.p + b_q), *e = e0;
+  c->col_job.fallback.assign(n_queries, -1);
+  for (uint32_t q = 0; q < n_queries; q++) {
+    qr[q].first_edge = (uint32_t)(e - e0);
+    qr[q].layer = (uint32_t)layer;
+    uint32_t cursor = 0;
+    for (uint32_t i = query_first[q]; i < query_first[q + 1]; i++) {
+      const BlockShadow &b = c->blocks[blocks[i]];
+      if (!(c->models[b.model].flags & STG_RT_VIS_OBSTACLE_RETURN)) // block.cc:136
+        continue;
+      if (b.zmin < 0) { // block.cc:137-138: the ground, unless an earlier block already hit something
+        c->col_job.fallback[q] = (int32_t)ground_model;
+        break;
+      }
+      if (b.dev_mapped[layer]) // after the flush dev_xy is the outline rendered on the device
+        emit_edges(b.dev_xy[layer], blocks[i], (uint32_t)layer, cursor, e);
+    }
+    qr[q].n_edges = (uint32_t)(e - e0) - qr[q].first_edge;
+    qr[q].n_steps = cursor;
+  }
+  const size_t b_used = b_q + (size_t)(e - e0) * sizeof(EdgeRec);
+  CU(c, cudaMemcpyAsync(c->d_col_in.p, c->h_col_in.p, b_used, cudaMemcpyHostToDevice, c->stream));
+  c->stats.h2d_bytes += b_used;
+  CollisionBatchView v;
+  v.n_queries = n_queries;
+  v.queries = (const CollisionQuery *)c->d_col_in.p;
+  v.edges = (const EdgeRec *)((const char *)c->d_col_in.p + b_q);
+  v.hit_model = (int32_t *)c->d_col_hit.p;
+  launch_collisions(c->g, v, c->stream);
+  c->stats.launches_post++;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(c->h_col_hit.p, c->d_col_hit.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, c->stream));
+  c->stats.d2h_bytes += (size_t)n_queries * 4;
+  c->col_job.user_hit = hit_model;
+  c->col_job.pending = true;
   return STG_RT_OK;
 }
 

@@ -66,12 +66,13 @@ struct BlockRec {
   double zmin, zmax;       // Block::global_z (block.cc:177-180)
   unsigned long long seq;  // order key of the latest Map on this layer
   uint32_t model;          // owning model id
-  uint32_t root_flags;     // root id of the model's tree | kRecNoRanger | kRecGripper
+  uint32_t root_flags;     // root id of the model's tree | kRecObstacle | kRecNoRanger | kRecGripper
 };
 static_assert(sizeof(BlockRec) == 32, "BlockRec");
 constexpr uint32_t kRecNoRanger = 1u << 30; // vis.ranger_return < 0: invisible to rangers
 constexpr uint32_t kRecGripper = 1u << 31;  // vis.gripper_return
-constexpr uint32_t kRecRootMask = (1u << 30) - 1u;
+constexpr uint32_t kRecObstacle = 1u << 29; // vis.obstacle_return
+constexpr uint32_t kRecRootMask = (1u << 29) - 1u;
 
 struct GridView {
   int32_t rx0, ry0, nrx, nry;
@@ -175,6 +176,24 @@ struct FanBatchView {
   int32_t *hit_model, *hit_cell;
   uint32_t *steps;
 };
+
+// ---- collision tests (Model::TestCollision) ----------------------------------------------------
+// One query = one top-level Model::TestCollision: the outlines (EdgeRec, first_step running within
+// the query) of the model's blocks and its descendants' in visiting order.
+struct CollisionQuery {
+  uint32_t first_edge, n_edges;
+  uint32_t n_steps; // cell visits of all its edges
+  uint32_t layer;
+};
+static_assert(sizeof(CollisionQuery) == 16, "CollisionQuery");
+
+struct CollisionBatchView {
+  uint32_t n_queries;
+  const CollisionQuery *queries;
+  const EdgeRec *edges;
+  int32_t *hit_model; // per query: id of the first model in the way, -1 for none
+};
+void launch_collisions(const GridView &g, const CollisionBatchView &b, void *stream);
 
 // ---- fiducial finders (same layouts as stg_rt_fid_* in include/stg_rt.h) -----------------------
 struct FidTargetRec {

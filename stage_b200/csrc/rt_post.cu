@@ -243,6 +243,83 @@ __global__ void __launch_bounds__(128) k3_fid_pack(FidBatchView b, const uint32_
     count_home[warp] = cnt;
 }
 
+// ---- K4: collision tests -----------------------------------------------------------------------
+// Model::TestCollision (model.cc:666-679) -> BlockGroup::TestCollision (blockgroup.cc:41-50) ->
+// Block::TestCollision (block.cc:129-168), for a batch of models. One warp per query. The cells a
+// block is rendered into are not stored per block on the device; they are re-derived, in rendering
+// order, from its outline (cell visit k of an edge in closed form, as K1 does). Lane i looks at
+// visit t0 + i: every block listed in that cell that belongs to another model, is an obstacle, is
+// not related and overlaps in z is a candidate, the one first in the cell's list (smallest seq)
+// is what this visit would return; the lowest visit with a candidate wins (ballot), which is the
+// model the reference's nested loops return first. The host has already dropped blocks whose own
+// model is no obstacle and cut the list at a block that reaches below the floor (rt_api.cu).
+__device__ __forceinline__ void edge_cell_post(const EdgeRec &e, uint32_t k, int32_t &x, int32_t &y)
+{ // same arithmetic as edge_cell in rt_kernels.cu (World::MapPoly's walk, world.cc:1000-1052)
+  const int32_t dx = e.x1 - e.x0, dy = e.y1 - e.y0;
+  const int32_t sx = dx < 0 ? -1 : 1, sy = dy < 0 ? -1 : 1;
+  const long long ax = dx < 0 ? -(long long)dx : dx, ay = dy < 0 ? -(long long)dy : dy;
+  const long long i = (2 * ax * (long long)k + ax + ay - 1) / (2 * (ax + ay));
+  x = e.x0 + sx * (int32_t)i;
+  y = e.y0 + sy * (int32_t)((long long)k - i);
+}
+
+__global__ void __launch_bounds__(128) k4_collisions(GridView g, CollisionBatchView b)
+{
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= b.n_queries)
+    return;
+  const CollisionQuery q = b.queries[warp];
+  const EdgeRec *edges = b.edges + q.first_edge;
+  const int L = q.layer & 1;
+  const unsigned long long *slots = g.slots[L];
+  const uint4 *recs = reinterpret_cast<const uint4 *>(g.blk_rec[L]);
+  int32_t result = -1;
+  for (uint32_t t0 = 0; t0 < q.n_steps && result < 0; t0 += 32) {
+    const uint32_t t = t0 + lane;
+    int32_t mine = -1;
+    if (t < q.n_steps) {
+      uint32_t ei = 0;
+      while (ei + 1 < q.n_edges && edges[ei + 1].first_step <= t)
+        ei++;
+      const EdgeRec e = edges[ei];
+      int32_t x, y;
+      edge_cell_post(e, t - e.first_step, x, y);
+      const uint4 oz = __ldg(recs + 2 * (size_t)e.block), oo = __ldg(recs + 2 * (size_t)e.block + 1);
+      const double own_zmin = __hiloint2double((int)oz.y, (int)oz.x), own_zmax = __hiloint2double((int)oz.w, (int)oz.z);
+      const uint32_t own_model = oo.z, own_root = oo.w & kRecRootMask;
+      const int32_t rix = (x >> kRBits) - g.rx0, riy = (y >> kRBits) - g.ry0;
+      const uint32_t region = (uint32_t)(riy * g.nrx + rix);
+      const uint32_t key = (region << (2 * kRBits)) | (((uint32_t)y & (kRegionWidth - 1)) << kRBits) | ((uint32_t)x & (kRegionWidth - 1));
+      unsigned long long best_seq = ~0ull;
+      uint32_t h = slot_home(key, g.slot_mask);
+      for (uint32_t probes = 0; probes <= g.slot_mask; probes++) {
+        const unsigned long long cur = __ldg(slots + h);
+        if (cur == kSlotEmpty)
+          break;
+        if ((uint32_t)(cur >> 32) == key) {
+          const uint32_t blk = (uint32_t)cur - 1u;
+          const uint4 z = __ldg(recs + 2 * (size_t)blk), o = __ldg(recs + 2 * (size_t)blk + 1);
+          const double zmin = __hiloint2double((int)z.y, (int)z.x), zmax = __hiloint2double((int)z.w, (int)z.z);
+          // block.cc:153-157
+          if (o.z != own_model && (o.w & kRecObstacle) && (o.w & kRecRootMask) != own_root && zmin <= own_zmax && zmax >= own_zmin) {
+            const unsigned long long s = ((unsigned long long)o.y << 32) | o.x;
+            if (s < best_seq) {
+              best_seq = s;
+              mine = (int32_t)o.z;
+            }
+          }
+        }
+        h = (h + 1) & g.slot_mask;
+      }
+    }
+    const uint32_t votes = __ballot_sync(0xffffffffu, mine >= 0);
+    if (votes)
+      result = __shfl_sync(0xffffffffu, mine, __ffs(votes) - 1);
+  }
+  if (lane == 0)
+    b.hit_model[warp] = result;
+}
+
 // ColorMatchIgnoreAlpha, model_blobfinder.cc:109-113
 __device__ __forceinline__ bool color_match(const double *a, const double *c)
 {
@@ -357,6 +434,13 @@ void launch_fid_pack(const FidBatchView &b, uint32_t *offsets, void *packed_host
   cudaStream_t s = (cudaStream_t)stream;
   k3_fid_pack_scan<<<1, 1024, 0, s>>>(b, offsets);
   k3_fid_pack<<<(b.n_finders * 32 + 127) / 128, 128, 0, s>>>(b, offsets, (unsigned long long *)packed_host, count_host);
+}
+
+void launch_collisions(const GridView &g, const CollisionBatchView &b, void *stream)
+{
+  if (!b.n_queries)
+    return;
+  k4_collisions<<<(b.n_queries * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g, b);
 }
 
 void launch_blobs(const GridView &g, const BlobBatchView &b, void *stream)

@@ -91,6 +91,7 @@ def lib():
         "stg_rt_fans_submit": (ctypes.c_int, [vp, u32, vp, vp, vp, ctypes.POINTER(FanOut)]),
         "stg_rt_fiducials_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
         "stg_rt_blobs_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
+        "stg_rt_collisions_test": (ctypes.c_int, [vp, ctypes.c_int, u32, vp, vp, u32, vp]),
         "stg_rt_fans_submit_noisy": (ctypes.c_int, [vp, u32, vp, vp, ctypes.POINTER(FanOut)]),
         "stg_rt_flush": (ctypes.c_int, [vp]),
         "stg_rt_sync": (ctypes.c_int, [vp]),
@@ -125,7 +126,7 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "stg_rt_abi_version stg_rt_create stg_rt_destroy stg_rt_last_error stg_rt_model_upsert stg_rt_block_map "
-    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
+    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_collisions_test stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
     "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_debug_trig stg_rt_debug_headings").split()
@@ -240,6 +241,20 @@ class Context:
         self._check(self._L.stg_rt_fiducials_submit(self._h, len(targets), _ptr(targets), len(finders), _ptr(finders),
                                                     max_per_finder, _ptr(out), _ptr(cnt)))
         return out, cnt
+
+    def collisions_test(self, layer, queries, ground_model=0):
+        """queries: one sequence of block ids per model (own blocks, then descendants', depth first)
+        -> int32 array of hit model ids (-1: none); valid after sync()."""
+        if isinstance(queries, tuple):  # already flattened: (query_first[n + 1], blocks[])
+            first, blocks = (np.ascontiguousarray(a, np.uint32) for a in queries)
+        else:
+            first = np.zeros(len(queries) + 1, np.uint32)
+            first[1:] = np.cumsum([len(q) for q in queries])
+            blocks = np.ascontiguousarray(np.concatenate([np.asarray(q, np.uint32) for q in queries]) if len(queries) else np.zeros(0), np.uint32)
+        hit = np.full(len(first) - 1, -2, np.int32)
+        self._keep.append((first, blocks, hit))
+        self._check(self._L.stg_rt_collisions_test(self._h, layer, len(first) - 1, _ptr(first), _ptr(blocks), ground_model, _ptr(hit)))
+        return hit
 
     def blobs_submit(self, finders, colors_rgb=None, max_per_finder=None):
         """-> (out[n_finders, max_per_finder] of BLOB_DTYPE, count[n_finders]); valid after sync()."""

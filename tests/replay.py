@@ -107,6 +107,7 @@ class GpuReplay:
         self.scans = []  # (event, Outputs)
         self.fiducials = []  # (event, dict, out, count)
         self.blobs = []
+        self.collisions = []  # one hit model id (-1: none) per COLLISION event
         pending = []
         ticks = 0
         for ev in trace.events:
@@ -116,6 +117,14 @@ class GpuReplay:
                               float(ev["zmax"]), trace.polygon(ev))
             elif t == trace_io.EV_UNMAP:
                 ctx.block_unmap(int(ev["block"]), int(ev["layer"]))
+            elif t == trace_io.EV_COLLISION:
+                # the reference tests right after re-mapping the mover (model_position.cc:549-554),
+                # against the grid as it stands then: one query, answered before the next event
+                _, layer, blocks, _ = trace.collision(ev)
+                hit = ctx.collisions_test(layer, [blocks])
+                ctx.sync()
+                self._collect(pending)
+                self.collisions.append(int(hit[0]))
             elif t == trace_io.EV_RAYS:
                 first, cnt = int(ev["first"]), int(ev["model"])
                 rays = trace.rays[first:first + cnt]
