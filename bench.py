@@ -456,6 +456,7 @@ def run_ours(args):
             "cpu_baseline": cpu, "parity_vs_reference": parity, "clocks": clocks,
         }
         print(json.dumps(line))
+    ctx.close()
     if n_gpus > 1:
         dist.barrier()
         dist.destroy_process_group()

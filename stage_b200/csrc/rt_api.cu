@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -138,6 +139,10 @@ struct stg_rt_ctx {
   DevBuf d_fid_grid, d_fid_in, d_fid_out, d_fid_count, d_fid_off, d_blob_in, d_blob_out, d_blob_count, d_mdl_color;
   PinBuf h_fid_in, h_fid_out, h_fid_count, h_blob_in, h_blob_out, h_blob_count;
   FanArrays bd; // the blobfinders' scan-line fans
+  // STG_RT_HOST_PROF=1: host microseconds per section of the flush path, printed by stg_rt_destroy
+  double prof_us[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+  uint64_t prof_flushes = 0;
+  bool prof_on = getenv("STG_RT_HOST_PROF") != nullptr;
   struct CollisionJob {
     int32_t *user_hit = nullptr;
     std::vector<int32_t> fallback; // per query: what to report when no cell test hits (-1, or the ground model)
@@ -306,9 +311,25 @@ static inline uint32_t emit_edges(const std::vector<int32_t> &xy, uint32_t block
   return steps;
 }
 
+static inline double prof_now(const stg_rt_ctx *c)
+{
+  if (!c->prof_on)
+    return 0;
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes)
 {
+  double t_prof = prof_now(c);
+  auto lap = [&](int k) {
+    if (c->prof_on) {
+      const double t = prof_now(c);
+      c->prof_us[k] += t - t_prof;
+      t_prof = t;
+    }
+  };
   sort_units(c);
+  lap(1);
   size_t unit = 0;
   bool first_round = true;
   if (out_bytes)
@@ -350,6 +371,7 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
     if (!apply && end_unit < c->dirty_units.size())
       return fail(c, STG_RT_ENOMEM, "deltas of one tick exceed the all-gather slot (%zu bytes)", c->blob_cap);
 
+    lap(2);
     // ---- pass 2: write the records straight into the pinned blob ----
     CU(c, cudaEventSynchronize(c->blob_uploaded)); // the previous upload has left the pinned buffer
     unsigned char *base = (unsigned char *)c->h_blob.p;
@@ -408,6 +430,7 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
     hdr->steps_insert = ins_cursor;
     hdr->rank = (uint32_t)rank;
     const size_t nbytes = bytes;
+    lap(3);
     if (apply)
       for (int L = 0; L < 2; L++)
         if (c->live_entries[L] + d_live[L] > (int64_t)c->slot_cap / 2)
@@ -435,6 +458,7 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
       c->t_rec[0] = true;
       CU(c, cudaGetLastError());
     }
+    lap(4);
     if (out_bytes)
       *out_bytes = nbytes;
     first_round = false;
@@ -612,6 +636,7 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
 {
   if (c->q_subs.empty())
     return with_deltas ? apply_deltas_locked(c) : 0;
+  const double t_prof0 = prof_now(c);
   int rc = deliver_locked(c); // staging buffers are single-buffered
   if (rc)
     return rc;
@@ -688,8 +713,10 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   CU(c, cudaEventRecord(c->t_ev[1][0], c->stream));
   launch_fan_headings(v, c->stream);
   CU(c, cudaEventRecord(c->t_ev[1][1], c->stream));
+  const double t_prof1 = prof_now(c);
   if (with_deltas && (rc = apply_deltas_locked(c)))
     return rc;
+  const double t_prof2 = prof_now(c);
   CU(c, cudaEventRecord(c->t_ev[2][0], c->stream));
   launch_ray_march(c->g, v, c->stream);
   CU(c, cudaEventRecord(c->t_ev[2][1], c->stream));
@@ -718,6 +745,11 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   c->q_has_noise = false;
   c->q_beams = 0;
   c->q_has_trig = false;
+  if (c->prof_on) {
+    c->prof_us[0] += t_prof1 - t_prof0;
+    c->prof_us[5] += prof_now(c) - t_prof2;
+    c->prof_flushes++;
+  }
   return 0;
 }
 
@@ -840,6 +872,12 @@ int stg_rt_destroy(stg_rt_ctx *c)
     return STG_RT_EINVAL;
   cudaSetDevice(c->cfg.device);
   cudaStreamSynchronize(c->stream);
+  if (c->prof_on && c->prof_flushes)
+    fprintf(stderr, "stg_rt host profile over %llu fan launches, us each: stage fans + headings %.1f | sort units %.1f | size deltas %.1f | "
+                    "write deltas %.1f | upload + K1 launches %.1f | march launch %.1f\n",
+            (unsigned long long)c->prof_flushes, c->prof_us[0] / c->prof_flushes, c->prof_us[1] / c->prof_flushes,
+            c->prof_us[2] / c->prof_flushes, c->prof_us[3] / c->prof_flushes, c->prof_us[4] / c->prof_flushes,
+            c->prof_us[5] / c->prof_flushes);
   GridView &g = c->g;
   void *dev[] = { g.reg_count, g.occ[0], g.slots[0], g.slots[1], g.blk_rec[0], g.blk_rec[1], c->spare_slots,
                   g.mdl_root, g.mdl_ranger_return, g.mdl_flags, c->d_blob.p };

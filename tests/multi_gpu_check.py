@@ -28,7 +28,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_robots, ticks = 64 * world_size, 6
-    w = worldgen.make_world(seed=9, n_rects=300, n_robots=n_robots, half_extent_m=20.48)
+    half = 20.48 if world_size <= 4 else 40.96  # room for every rank's 64 robots
+    w = worldgen.make_world(seed=9, n_rects=int(300 * (half / 20.48) ** 2), n_robots=n_robots, half_extent_m=half)
     x0, y0, nx, ny = w.sreg_extent()
     n_bodies = len(w.obstacles) + len(w.robots)
     ctx = rt.Context(w.ppm, x0, y0, nx, ny, max_models=w.n_models + 1, max_blocks=n_bodies, max_cell_entries=1 << 20,
