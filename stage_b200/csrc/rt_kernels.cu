@@ -98,6 +98,36 @@ __device__ __forceinline__ BlobView blob_view(const unsigned char *blobs, int ra
   return v;
 }
 
+// The cell visits of all ranks' blobs as ONE index space, so that a gathered delta (N ranks) is a
+// single grid-stride pass instead of N latency-bound passes. prefix[] (shared, n_ranks + 1 entries)
+// holds the running sums of the ranks' step counts; ranks beyond kMaxRanksFlat fall back to rank-by-
+// rank passes. The order in which visits of different ranks land does not matter: removals are
+// independent, insertions claim slots by CAS, and the order of a cell's list is carried by seq.
+constexpr int kMaxRanksFlat = 64;
+
+template <bool kInsert>
+__device__ __forceinline__ void k1_step_prefix(const unsigned char *blobs, int n_ranks, size_t slot_bytes, uint32_t *prefix)
+{
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int r = 0; r < n_ranks; r++) {
+      prefix[r] = run;
+      const DeltaHeader *h = reinterpret_cast<const DeltaHeader *>(blobs + (size_t)r * slot_bytes);
+      run += kInsert ? h->steps_insert : h->steps_remove;
+    }
+    prefix[n_ranks] = run;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int k1_rank_of(const uint32_t *prefix, int n_ranks, uint32_t t)
+{
+  int r = 0;
+  while (r + 1 < n_ranks && prefix[r + 1] <= t)
+    r++;
+  return r;
+}
+
 __device__ __forceinline__ void k1_table_updates(const GridView &g, const unsigned char *blobs, int n_ranks,
                                                  size_t slot_bytes, unsigned long long epoch)
 {
@@ -131,12 +161,15 @@ __device__ __forceinline__ void k1_table_updates(const GridView &g, const unsign
   }
 }
 
-__device__ __forceinline__ void k1_remove(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes)
+__device__ __forceinline__ void k1_remove(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
+                                          const uint32_t *prefix)
 {
-  for (int rank = 0; rank < n_ranks; rank++) {
-    const BlobView v = blob_view(blobs, rank, slot_bytes);
-    const uint32_t steps = v.hdr->steps_remove, stride = gridDim.x * blockDim.x;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < steps; t += stride) {
+  {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t tt = blockIdx.x * blockDim.x + threadIdx.x; tt < prefix[n_ranks]; tt += stride) {
+      const int rank = k1_rank_of(prefix, n_ranks, tt);
+      const BlobView v = blob_view(blobs, rank, slot_bytes);
+      const uint32_t t = tt - prefix[rank];
       const EdgeRec e = v.remove_edges[find_edge(v.remove_edges, v.hdr->n_remove, t)];
       int32_t x, y;
       edge_cell(e, t - e.first_step, x, y);
@@ -160,12 +193,15 @@ __device__ __forceinline__ void k1_remove(const GridView &g, const unsigned char
   }
 }
 
-__device__ __forceinline__ void k1_fixup(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes)
+__device__ __forceinline__ void k1_fixup(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
+                                         const uint32_t *prefix)
 {
-  for (int rank = 0; rank < n_ranks; rank++) {
-    const BlobView v = blob_view(blobs, rank, slot_bytes);
-    const uint32_t steps = v.hdr->steps_remove, stride = gridDim.x * blockDim.x;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < steps; t += stride) {
+  {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t tt = blockIdx.x * blockDim.x + threadIdx.x; tt < prefix[n_ranks]; tt += stride) {
+      const int rank = k1_rank_of(prefix, n_ranks, tt);
+      const BlobView v = blob_view(blobs, rank, slot_bytes);
+      const uint32_t t = tt - prefix[rank];
       const EdgeRec e = v.remove_edges[find_edge(v.remove_edges, v.hdr->n_remove, t)];
       int32_t x, y;
       edge_cell(e, t - e.first_step, x, y);
@@ -188,12 +224,15 @@ __device__ __forceinline__ void k1_fixup(const GridView &g, const unsigned char 
   }
 }
 
-__device__ __forceinline__ void k1_insert(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes)
+__device__ __forceinline__ void k1_insert(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
+                                          const uint32_t *prefix)
 {
-  for (int rank = 0; rank < n_ranks; rank++) {
-    const BlobView v = blob_view(blobs, rank, slot_bytes);
-    const uint32_t steps = v.hdr->steps_insert, stride = gridDim.x * blockDim.x;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < steps; t += stride) {
+  {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t tt = blockIdx.x * blockDim.x + threadIdx.x; tt < prefix[n_ranks]; tt += stride) {
+      const int rank = k1_rank_of(prefix, n_ranks, tt);
+      const BlobView v = blob_view(blobs, rank, slot_bytes);
+      const uint32_t t = tt - prefix[rank];
       const EdgeRec e = v.insert_edges[find_edge(v.insert_edges, v.hdr->n_insert, t)];
       int32_t x, y;
       edge_cell(e, t - e.first_step, x, y);
@@ -223,8 +262,15 @@ __device__ __forceinline__ void k1_insert(const GridView &g, const unsigned char
 __global__ void __launch_bounds__(256) k1_phase0(GridView g, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
                                                  unsigned long long epoch)
 {
+  __shared__ uint32_t prefix[kMaxRanksFlat + 1];
   k1_table_updates(g, blobs, n_ranks, slot_bytes, epoch);
-  k1_remove(g, blobs, n_ranks, slot_bytes);
+  for (int r0 = 0; r0 < n_ranks; r0 += kMaxRanksFlat) { // one pass unless there are more ranks than that
+    const int nr = min(n_ranks - r0, kMaxRanksFlat);
+    const unsigned char *part = blobs + (size_t)r0 * slot_bytes;
+    k1_step_prefix<false>(part, nr, slot_bytes, prefix);
+    k1_remove(g, part, nr, slot_bytes, prefix);
+    __syncthreads();
+  }
 }
 
 // phase 1, after every removal has landed: mask fix-up of the removed cells and the insertions. The
@@ -232,8 +278,17 @@ __global__ void __launch_bounds__(256) k1_phase0(GridView g, const unsigned char
 // insertion sets anyway, so they can share a launch.
 __global__ void __launch_bounds__(256) k1_phase1(GridView g, const unsigned char *blobs, int n_ranks, size_t slot_bytes)
 {
-  k1_fixup(g, blobs, n_ranks, slot_bytes);
-  k1_insert(g, blobs, n_ranks, slot_bytes);
+  __shared__ uint32_t prefix[kMaxRanksFlat + 1];
+  for (int r0 = 0; r0 < n_ranks; r0 += kMaxRanksFlat) {
+    const int nr = min(n_ranks - r0, kMaxRanksFlat);
+    const unsigned char *part = blobs + (size_t)r0 * slot_bytes;
+    k1_step_prefix<false>(part, nr, slot_bytes, prefix);
+    k1_fixup(g, part, nr, slot_bytes, prefix);
+    __syncthreads();
+    k1_step_prefix<true>(part, nr, slot_bytes, prefix);
+    k1_insert(g, part, nr, slot_bytes, prefix);
+    __syncthreads();
+  }
 }
 
 // Compaction of one layer's cell-content table: re-insert the live entries into a clean table
