@@ -44,10 +44,28 @@ def parse_args():
     ap.add_argument("--half-extent", type=float, default=81.92)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--workload", default="c3", choices=["c3", "cave"],
+                    help="c3 = BASELINE config 3 (the default, the judged line); cave = the denser variant of SURVEY.md 8(d): "
+                         "worlds/bitmaps/cave.png tiled 10x10 (no reference arm: value / e2e / roofline only)")
     return ap.parse_args()
 
 
+def make_workload(args, n_gpus):
+    from stage_b200 import worldgen
+    if args.workload == "cave":
+        return worldgen.make_cave_world(seed=1, tiles=10, n_robots=args.robots * n_gpus)
+    return worldgen.make_world(seed=1, n_rects=args.rects, n_robots=args.robots * n_gpus, half_extent_m=args.half_extent)
+
+
 def workload_config(args, n_gpus):
+    if args.workload == "cave":
+        return {
+            "workload": "C3-cave: worlds/bitmaps/cave.png (16 m floorplan of simple.world) tiled 10x10 = 8000x8000 cells (ppm 50), "
+                        "%d robots/GPU x %d-beam %g-degree %g m laser, z-test, ranger predicate" % (args.robots, SAMPLES, FOV_DEG, RANGE_MAX),
+            "robots_total": args.robots * n_gpus, "beams_per_robot": SAMPLES, "rays_per_step": args.robots * n_gpus * SAMPLES,
+            "parallelism": "robots sharded over %d GPU(s), grid replicated" % n_gpus,
+            "l2": "flushed (256 MiB write) before every timed step of `value`",
+        }
     return {
         "workload": "C3 synthetic: %dx%d-cell world (ppm 50), %d rectangles + walls, %d robots/GPU x %d-beam "
                     "%g-degree %g m laser, z-test, ranger predicate" % (
@@ -171,7 +189,10 @@ def run_reference(args):
         return 0
     from stage_b200 import worldgen
     n_gpus = args.gpus
-    world = worldgen.make_world(seed=1, n_rects=args.rects, n_robots=args.robots * n_gpus, half_extent_m=args.half_extent)
+    if args.workload != "c3":
+        print(json.dumps({"impl": "reference", "unavailable": "the reference arm runs BASELINE config 3 only (--workload c3)"}))
+        return 0
+    world = make_workload(args, n_gpus)
     fans = worldgen.ranger_fans(world, layer=1, fov_deg=FOV_DEG, samples=SAMPLES, range_max=RANGE_MAX)
     threads = args.cpu_threads or os.cpu_count()
     ref, _ = reference_world(world)
@@ -256,11 +277,11 @@ def run_ours(args):
             os.dup2(saved, 1)
             os.close(saved)
 
-    world = worldgen.make_world(seed=1, n_rects=args.rects, n_robots=args.robots * n_gpus, half_extent_m=args.half_extent)
+    world = make_workload(args, n_gpus)
     x0, y0, nx, ny = world.sreg_extent()
-    n_bodies = len(world.obstacles) + len(world.robots)
+    n_bodies = world.n_static_blocks + len(world.robots)
     ctx = rt.Context(world.ppm, x0, y0, nx, ny, max_models=world.n_models + 1, max_blocks=n_bodies,
-                     max_cell_entries=1 << 22, device=local_rank, max_delta_bytes=(1 << 20) if n_gpus > 1 else 0)
+                     max_cell_entries=(1 << 23) if args.workload == "cave" else (1 << 22), device=local_rank, max_delta_bytes=(1 << 20) if n_gpus > 1 else 0)
     # all of the context's work goes on a torch-owned stream so torch.cuda.Event can bracket it
     # (the default stream's handle is NULL, which stg_rt_set_stream reads as "use your own")
     stream = torch.cuda.Stream()
@@ -270,7 +291,7 @@ def run_ours(args):
 
     lo, hi = multi.shard_bounds(args.robots * n_gpus, rank, n_gpus)
     my_ids = world.robot_ids[lo:hi]
-    my_blocks = (len(world.obstacles) + np.arange(lo, hi)).astype(np.uint32)
+    my_blocks = (world.n_static_blocks + np.arange(lo, hi)).astype(np.uint32)
     n_beams = args.robots * SAMPLES
     total_rays = n_beams * n_gpus
 
@@ -387,7 +408,7 @@ def run_ours(args):
     # ---- CPU baseline + parity of the last e2e tick against the unmodified reference ----------
     cpu = None
     parity = None
-    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline and args.workload == "c3":
         threads = args.cpu_threads or os.cpu_count()
         sample_fans = fans0
         res = cpu_reference_throughput(world, sample_fans, threads, reps=3, record=True)

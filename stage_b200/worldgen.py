@@ -11,6 +11,7 @@ All coordinates live on a 1 mm / 0.001 degree lattice so that their decimal text
 to the same doubles.
 """
 import math
+import os
 
 import numpy as np
 
@@ -32,6 +33,11 @@ class World:
     @property
     def n_models(self):
         return 1 + len(self.obstacles) + len(self.robots)
+
+    @property
+    def n_static_blocks(self):
+        """blocks of everything that is not a robot; robot j's body is block n_static_blocks + j"""
+        return len(self.obstacles)
 
     def sreg_extent(self):
         """(x0, y0, nx, ny) in superregions (1024 cells) covering the world"""
@@ -138,6 +144,8 @@ def robot_polygons(w, robots=None):
 def load_into_context(ctx, w, robot_slice=None):
     """Publish every model and map every body on BOTH layers, as World::LoadWorldPostHook does
     (world.cc:459-465). Block ids: obstacle i -> i, robot j -> n_obstacles + j."""
+    if isinstance(w, CaveWorld):
+        return w.load_into_context(ctx)
     ctx.model_upsert(0, 0, 1.0)  # the ground model
     for mid in w.obstacle_ids:
         ctx.model_upsert(int(mid), int(mid), 0.5)
@@ -154,6 +162,93 @@ def load_into_context(ctx, w, robot_slice=None):
         ctx.blocks_remap(blocks, models, layer, z, first, xy)
     ctx.sync()
     return len(polys)
+
+
+class CaveWorld(World):
+    """The denser map of SURVEY.md 8(d): the floorplan of worlds/simple.world (bitmaps/cave.png, 16 m,
+    2 cm cells) tiled tiles x tiles, one floorplan model per tile. The outlines are the polygons the
+    unmodified reference produced for that bitmap (stage_b200/data/cave_polygons.npz, made by
+    tools/extract_cave_polygons.py from a recorded trace), shifted by whole tiles."""
+    TILE_CELLS = 800
+
+    def __init__(self, tiles, robots, ppm=50.0):
+        data = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "cave_polygons.npz"))
+        first, xy = data["first"], data["xy"]
+        self.tile_polygons = [xy[first[i]:first[i + 1]] for i in range(len(first) - 1)]
+        self.tiles = tiles
+        self.tile_height = 0.8
+        half_cells = tiles * self.TILE_CELLS // 2
+        super().__init__(ppm, max(half_cells / ppm, 81.92), np.zeros((tiles * tiles, 4)), robots)
+        # tile (i, j) is centred at cell ((i + 0.5) * 800 - half, (j + 0.5) * 800 - half)
+        self.tile_offsets = [(int((i + 0.5) * self.TILE_CELLS) - half_cells, int((j + 0.5) * self.TILE_CELLS) - half_cells)
+                             for j in range(tiles) for i in range(tiles)]
+
+    @property
+    def n_static_blocks(self):
+        return len(self.tile_offsets) * len(self.tile_polygons)
+
+    def static_blocks(self):
+        """(model id, polygon) of every floorplan block, in block-id order"""
+        for t, (dx, dy) in enumerate(self.tile_offsets):
+            for p in self.tile_polygons:
+                yield int(self.obstacle_ids[t]), p + np.array([dx, dy], np.int32)
+
+    def load_into_context(self, ctx):
+        ctx.model_upsert(0, 0, 1.0)
+        for mid in list(self.obstacle_ids) + list(self.robot_ids):
+            ctx.model_upsert(int(mid), int(mid), 0.5)
+        st = list(self.static_blocks())
+        polys = [p for _, p in st] + robot_polygons(self)
+        models = np.concatenate([np.array([m for m, _ in st], np.uint32), self.robot_ids])
+        zmax = np.concatenate([np.full(len(st), self.tile_height), np.full(len(self.robots), self.robot_size[2])])
+        first = np.zeros(len(polys) + 1, np.uint32)
+        first[1:] = np.cumsum([len(p) for p in polys])
+        xy = np.ascontiguousarray(np.concatenate(polys, 0), np.int32)
+        z = np.stack([np.zeros(len(polys)), zmax], 1)
+        blocks = np.arange(len(polys), dtype=np.uint32)
+        for layer in (0, 1):
+            ctx.blocks_remap(blocks, models, layer, z, first, xy)
+        ctx.sync()
+        return len(polys)
+
+
+def make_cave_world(seed=1, tiles=10, n_robots=1000, clearance_m=0.35):
+    """tiles x tiles cave floorplans and robots dropped on free floor (not within clearance_m of a wall)."""
+    from PIL import Image, ImageDraw
+    from scipy import ndimage
+    rng = np.random.RandomState(seed)
+    w = CaveWorld(tiles, np.zeros((n_robots, 3)))
+    T = CaveWorld.TILE_CELLS
+    img = Image.new("1", (T, T), 0)
+    draw = ImageDraw.Draw(img)
+    for p in w.tile_polygons[1:]:  # polygon 0 is the bounding square (floorplan `boundary 1`)
+        draw.polygon([(int(x) + T // 2, int(y) + T // 2) for x, y in p], fill=1, outline=1)
+    wall = np.array(img, bool)
+    wall[:2, :] = wall[-2:, :] = wall[:, :2] = wall[:, -2:] = True
+    free = ~ndimage.binary_dilation(wall, iterations=int(round(clearance_m * w.ppm)))
+    fy, fx = np.nonzero(free)
+    assert len(fx) > 1000
+    placed, occupied, rounds = 0, {}, 0
+    while placed < n_robots:
+        rounds += 1
+        if rounds > 200:
+            raise ValueError("cannot place %d robots in the cave tiles (placed %d)" % (n_robots, placed))
+        for _ in range(4 * (n_robots - placed) + 16):
+            t = rng.randint(len(w.tile_offsets))
+            k = rng.randint(len(fx))
+            dx, dy = w.tile_offsets[t]
+            x = round((fx[k] - T // 2 + dx + 0.5) / w.ppm, 3)
+            y = round((fy[k] - T // 2 + dy + 0.5) / w.ppm, 3)
+            key = (int(math.floor(x)), int(math.floor(y)))
+            if any((px - x) ** 2 + (py - y) ** 2 < 0.36 for ddx in (-1, 0, 1) for ddy in (-1, 0, 1)
+                   for (px, py) in occupied.get((key[0] + ddx, key[1] + ddy), ())):
+                continue
+            occupied.setdefault(key, []).append((x, y))
+            w.robots[placed] = (x, y, round(rng.uniform(-180.0, 180.0), 3))
+            placed += 1
+            if placed == n_robots:
+                break
+    return w
 
 
 def ranger_fans(w, layer, fov_deg=270.0, samples=1080, range_max=30.0, z=0.5, robots=None, robot_ids=None):

@@ -123,3 +123,35 @@ def test_resident_set_follows_moved_origins():
     assert not np.array_equal(bits(a.ranges), bits(b.ranges))
     s.destroy()
     ctx.close()
+
+
+def test_cave_tiles_match_oracle():
+    """The denser map of SURVEY.md 8(d) in miniature: 2 x 2 tiles of the cave floorplan (concave polygons
+    of up to 91 vertices, as the reference traced them from the bitmap), 60 robots, 360-beam scans."""
+    w = worldgen.make_cave_world(seed=3, tiles=2, n_robots=60)
+    x0, y0, nx, ny = w.sreg_extent()
+    ctx = rt.Context(w.ppm, x0, y0, nx, ny, max_models=w.n_models + 1, max_blocks=w.n_static_blocks + len(w.robots),
+                     max_cell_entries=1 << 20)
+    worldgen.load_into_context(ctx, w)
+    t1 = oracle_lib.T1World(w.ppm)
+    t1.model_upsert(0, 0, 1.0)
+    for mid in list(w.obstacle_ids) + list(w.robot_ids):
+        t1.model_upsert(int(mid), int(mid), 0.5)
+    st = list(w.static_blocks())
+    bodies = [(m, p, w.tile_height) for m, p in st] + [(int(m), p, w.robot_size[2]) for m, p in zip(w.robot_ids, worldgen.robot_polygons(w))]
+    for layer in (0, 1):
+        for b, (m, p, z) in enumerate(bodies):
+            t1.block_map(b, m, layer, 0.0, z, p)
+    rec_g, cnt_g = ctx.grid_dump()
+    rec_o, cnt_o = t1.dump_grid()
+    assert np.array_equal(oracle_lib.sort_grid(rec_g), rec_o) and np.array_equal(oracle_lib.sort_counts(cnt_g), cnt_o)
+    fans = worldgen.ranger_fans(w, layer=1, samples=360, range_max=30.0)
+    rg, it, hits = t1_fans(t1, fans)
+    head = np.concatenate([oracle_lib.ranger_headings(f["oa"], f["fov"], int(f["n_samples"])) for f in fans])
+    g = ctx.trace(fans, trig=oracle_lib.libm_trig(head))
+    assert np.array_equal(g.hit_model, hits["hit_model"]) and np.array_equal(bits(g.ranges), bits(rg))
+    assert np.array_equal(g.steps[:, 0], hits["cell_visits"]) and np.array_equal(g.steps[:, 1], hits["region_probes"])
+    assert (g.hit_model >= 0).mean() > 0.9 and 1.0 < g.ranges.mean() < 8.0  # the robots stand on open floor
+    g2 = ctx.trace(fans)  # device trig
+    assert np.array_equal(g2.hit_model, hits["hit_model"]) and np.array_equal(bits(g2.ranges), bits(rg))
+    ctx.close()
