@@ -255,6 +255,28 @@ int stg_rt_fiducials_submit(stg_rt_ctx *ctx, uint32_t n_targets, const stg_rt_fi
 int stg_rt_collisions_test(stg_rt_ctx *ctx, int layer, uint32_t n_queries, const uint32_t *query_first,
                            const uint32_t *blocks, uint32_t ground_model, int32_t *hit_model);
 
+/* ---- batched ModelPosition::Move ------------------------------------------------------------ */
+
+/* ModelPosition::Move (model_position.cc:526-566) for n_movers position models at once, with the
+   result the reference's one-by-one loop (world.cc:647-648) produces: mover i is re-rendered at the
+   pose it wants (UnMapWithChildren / MapWithChildren on `layer` = World::updates % 2), tested with
+   Model::TestCollision against everything as it stands THEN - the movers before it where they ended
+   up, the movers after it where the layer still has them - and, if it hit something, re-rendered at
+   the pose it has now (stalled[i] = 1, Model::SetStall). Mover i covers blocks[mover_first[i] ..
+   mover_first[i + 1]): its own blocks and its descendants', depth first. Per block: z / first_pt /
+   xy = z range and outline at the wanted pose, z_start / first_pt_start / xy_start = at the present
+   pose (startpose, :541), both as Model::LocalToPixels gives them. The movers must come in the order
+   the reference moves them (World::active_velocity) and belong to different model trees.
+   How: what the wanted outlines touch is collected against the layer as it is and against the layer
+   with every mover at its wanted pose, and what the present outlines touch against the latter; a
+   mover that touches nothing, or something that does not move, is decided right there, and the few
+   that touch other movers are decided in order from those three lists. The cell lists end up in the
+   reference's order (each block's last Map keeps its place in the loop's sequence). Synchronous;
+   single process (not combined with stg_rt_delta_export). */
+int stg_rt_models_move(stg_rt_ctx *ctx, int layer, uint32_t n_movers, const uint32_t *mover_first, const uint32_t *blocks,
+                       const double *z, const uint32_t *first_pt, const int32_t *xy, const double *z_start,
+                       const uint32_t *first_pt_start, const int32_t *xy_start, uint8_t *stalled);
+
 /* ---- blobfinders ----------------------------------------------------------------------------- */
 
 /* One ModelBlobfinder::Update (model_blobfinder.cc:165-250). 72 bytes. */

@@ -150,6 +150,10 @@ struct stg_rt_ctx {
   } col_job;
   DevBuf d_col_in, d_col_hit;
   PinBuf h_col_in, h_col_hit;
+  // stg_rt_models_move
+  DevBuf d_mv_in, d_mv_out, d_mover_of_model;
+  PinBuf h_mv_in, h_mv_out;
+  bool hold_epoch = false; // the undo re-maps of a move belong to the same epoch as the moves
   std::vector<double> mdl_color; // rgba per model
   bool mdl_color_dirty = true;
 
@@ -445,7 +449,8 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
     for (int L = 0; L < 2; L++)
       c->live_entries[L] += d_live[L];
     if (apply) {
-      c->epoch++;
+      if (!c->hold_epoch)
+        c->epoch++;
       CU(c, cudaEventRecord(c->t_ev[0][0], c->stream));
       launch_apply_deltas(c->g, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, 0, c->stream,
                           &c->stats.launches_rasterise);
@@ -888,10 +893,10 @@ int stg_rt_destroy(stg_rt_ctx *c)
   free_fan_arrays(c->bd);
   if (c->d_in.p)
     cudaFree(c->d_in.p);
-  for (DevBuf *b : { &c->d_col_in, &c->d_col_hit, &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_fid_off, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
+  for (DevBuf *b : { &c->d_mv_in, &c->d_mv_out, &c->d_mover_of_model, &c->d_col_in, &c->d_col_hit, &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_fid_off, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
     if (b->p)
       cudaFree(b->p);
-  for (PinBuf *b : { &c->h_col_in, &c->h_col_hit, &c->h_fid_in, &c->h_fid_out, &c->h_fid_count, &c->h_blob_in, &c->h_blob_out, &c->h_blob_count })
+  for (PinBuf *b : { &c->h_mv_in, &c->h_mv_out, &c->h_col_in, &c->h_col_hit, &c->h_fid_in, &c->h_fid_out, &c->h_fid_count, &c->h_blob_in, &c->h_blob_out, &c->h_blob_count })
     if (b->p)
       cudaFreeHost(b->p);
   PinBuf *pins[] = { &c->h_blob, &c->h_in, &c->h_ranges, &c->h_intens, &c->h_bearings, &c->h_hit_model, &c->h_hit_cell, &c->h_steps };
@@ -1647,6 +1652,176 @@ int stg_rt_collisions_test(stg_rt_ctx *c, int layer, uint32_t n_queries, const u
   c->col_job.user_hit = hit_model;
   c->col_job.pending = true;
   return STG_RT_OK;
+}
+
+int stg_rt_models_move(stg_rt_ctx *c, int layer, uint32_t n_movers, const uint32_t *mover_first, const uint32_t *blocks,
+                       const double *z, const uint32_t *first_pt, const int32_t *xy, const double *z_start,
+                       const uint32_t *first_pt_start, const int32_t *xy_start, uint8_t *stalled)
+{
+  if (!c || layer < 0 || layer > 1 ||
+      (n_movers && (!mover_first || !blocks || !z || !first_pt || !xy || !z_start || !first_pt_start || !xy_start || !stalled)))
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!n_movers)
+    return STG_RT_OK;
+  size_t n_edges[2] = { 0, 0 }; // of the new outlines, of the start outlines
+  std::vector<uint32_t> pairs;  // (model, mover index + 1)
+  for (uint32_t i = 0; i < n_movers; i++) {
+    if (mover_first[i + 1] < mover_first[i])
+      return fail(c, STG_RT_EINVAL, "models_move: mover_first is not ascending at %u", i);
+    for (uint32_t k = mover_first[i]; k < mover_first[i + 1]; k++) {
+      if (blocks[k] >= c->cfg.max_blocks || !c->blocks[blocks[k]].known)
+        return fail(c, STG_RT_EINVAL, "models_move: mover %u names unknown block %u", i, blocks[k]);
+      if (first_pt[k + 1] < first_pt[k] || first_pt_start[k + 1] < first_pt_start[k])
+        return fail(c, STG_RT_EINVAL, "models_move: first_pt is not ascending at %u", k);
+      n_edges[0] += first_pt[k + 1] - first_pt[k];
+      n_edges[1] += first_pt_start[k + 1] - first_pt_start[k];
+      const uint32_t model = c->blocks[blocks[k]].model;
+      if (pairs.size() < 2 || pairs[pairs.size() - 2] != model) {
+        pairs.push_back(model);
+        pairs.push_back(i + 1);
+      }
+    }
+  }
+  int rc = flush_locked(c); // the grid as it stands before the first mover moves
+  if (rc || (rc = deliver_locked(c)))
+    return rc;
+  // ---- two sets of queries: the outlines the movers want, and the outlines they have now. Blocks of models that
+  // are no obstacles test nothing and are tested by nobody (block.cc:136,154).
+  const size_t b_q = (size_t)n_movers * sizeof(CollisionQuery);
+  size_t off = 0, o_q[2], o_e[2], o_z[2];
+  for (int s = 0; s < 2; s++) {
+    o_q[s] = off;
+    off += b_q;
+    o_e[s] = off;
+    off += n_edges[s] * sizeof(EdgeRec);
+    o_z[s] = off;
+    off += n_edges[s] * 16;
+  }
+  const size_t o_p = off, b_p = pairs.size() * 4, b_in = o_p + b_p;
+  const size_t b_out = (size_t)n_movers * sizeof(TouchRec);
+  if ((rc = pin_reserve(c, c->h_mv_in, b_in)) || (rc = dev_reserve(c, c->d_mv_in, b_in + 16)) ||
+      (rc = pin_reserve(c, c->h_mv_out, 3 * b_out)) || (rc = dev_reserve(c, c->d_mv_out, 3 * b_out)))
+    return rc;
+  if (!c->d_mover_of_model.p) {
+    if ((rc = dev_reserve(c, c->d_mover_of_model, (size_t)c->cfg.max_models * 4)))
+      return rc;
+    CU(c, cudaMemsetAsync(c->d_mover_of_model.p, 0, (size_t)c->cfg.max_models * 4, c->stream));
+  }
+  char *hp = (char *)c->h_mv_in.p;
+  std::vector<uint8_t> ground(n_movers, 0); // a block of an obstacle model reaching below the floor: block.cc:137-138
+  std::vector<int32_t> tmp_xy;
+  for (int s = 0; s < 2; s++) {
+    const double *zz = s ? z_start : z;
+    const uint32_t *fp = s ? first_pt_start : first_pt;
+    const int32_t *pts = s ? xy_start : xy;
+    CollisionQuery *qr = (CollisionQuery *)(hp + o_q[s]);
+    EdgeRec *e0 = (EdgeRec *)(hp + o_e[s]), *e = e0;
+    double *ez = (double *)(hp + o_z[s]);
+    for (uint32_t i = 0; i < n_movers; i++) {
+      qr[i].first_edge = (uint32_t)(e - e0);
+      qr[i].layer = (uint32_t)layer;
+      uint32_t cursor = 0;
+      for (uint32_t k = mover_first[i]; k < mover_first[i + 1]; k++) {
+        const BlockShadow &b = c->blocks[blocks[k]];
+        if (!(c->models[b.model].flags & STG_RT_VIS_OBSTACLE_RETURN))
+          continue;
+        if (s == 0 && zz[2 * k] < 0)
+          ground[i] = 1;
+        tmp_xy.assign(pts + 2 * (size_t)fp[k], pts + 2 * (size_t)fp[k + 1]);
+        const EdgeRec *before = e;
+        emit_edges(tmp_xy, blocks[k], (uint32_t)layer, cursor, e);
+        for (const EdgeRec *p = before; p < e; p++) {
+          ez[2 * (p - e0)] = zz[2 * k];
+          ez[2 * (p - e0) + 1] = zz[2 * k + 1];
+        }
+      }
+      qr[i].n_edges = (uint32_t)(e - e0) - qr[i].first_edge;
+      qr[i].n_steps = cursor;
+    }
+  }
+  memcpy(hp + o_p, pairs.data(), b_p);
+  CU(c, cudaMemcpyAsync(c->d_mv_in.p, hp, b_in, cudaMemcpyHostToDevice, c->stream));
+  c->stats.h2d_bytes += b_in;
+  const char *dp = (const char *)c->d_mv_in.p;
+  const uint32_t *d_pairs = (const uint32_t *)(dp + o_p);
+  launch_mark_movers(d_pairs, (uint32_t)(pairs.size() / 2), (uint32_t *)c->d_mover_of_model.p, 0, c->stream);
+  TouchBatchView v;
+  v.n_queries = n_movers;
+  v.mover_of_model = (const uint32_t *)c->d_mover_of_model.p;
+  auto touches = [&](int set, int slot) {
+    v.queries = (const CollisionQuery *)(dp + o_q[set]);
+    v.edges = (const EdgeRec *)(dp + o_e[set]);
+    v.edge_z = (const double *)(dp + o_z[set]);
+    v.out = (TouchRec *)c->d_mv_out.p + (size_t)slot * n_movers;
+    launch_touches(c->g, v, c->stream);
+    c->stats.launches_post++;
+  };
+  touches(0, 0); // A: the wanted outlines against everybody where the grid has them now (what the movers still to come look like)
+
+  // ---- move everybody (Block::UnMap + Block::Map per block, in the loop's order); every mover keeps as many
+  // sequence numbers in reserve as it has blocks, for the re-maps of an undo
+  std::vector<uint32_t> undo_seq(n_movers);
+  for (uint32_t i = 0; i < n_movers; i++) {
+    for (uint32_t k = mover_first[i]; k < mover_first[i + 1] && !rc; k++) // UnMapWithChildren
+      rc = block_unmap_locked(c, blocks[k], layer);
+    for (uint32_t k = mover_first[i]; k < mover_first[i + 1] && !rc; k++) // MapWithChildren
+      rc = block_map_locked(c, blocks[k], c->blocks[blocks[k]].model, layer, z[2 * k], z[2 * k + 1],
+                            (int)(first_pt[k + 1] - first_pt[k]), xy + 2 * (size_t)first_pt[k]);
+    if (rc)
+      return rc;
+    undo_seq[i] = c->local_seq;
+    c->local_seq += mover_first[i + 1] - mover_first[i];
+  }
+  if ((rc = flush_locked(c)))
+    return rc;
+  touches(0, 1); // B: the wanted outlines against everybody at the wanted pose (movers already through that were let go)
+  touches(1, 2); // C: the present outlines against everybody at the wanted pose: who would run into a mover that is put back
+  launch_mark_movers(d_pairs, (uint32_t)(pairs.size() / 2), (uint32_t *)c->d_mover_of_model.p, 1, c->stream);
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(c->h_mv_out.p, c->d_mv_out.p, 3 * b_out, cudaMemcpyDeviceToHost, c->stream));
+  c->stats.d2h_bytes += 3 * b_out;
+  CU(c, cudaStreamSynchronize(c->stream));
+
+  // ---- decide in order (model_position.cc:554): mover i sees the movers before it where they ended up - at the wanted
+  // pose, or back at the present one - and the movers after it where the grid had them
+  const TouchRec *ta = (const TouchRec *)c->h_mv_out.p, *tb = ta + n_movers, *tc = tb + n_movers;
+  std::vector<uint8_t> runs_into_undone(n_movers, 0);
+  bool any_hit = false;
+  for (uint32_t i = 0; i < n_movers; i++) {
+    if (ta[i].n_touched > kTouchMax || tb[i].n_touched > kTouchMax || tc[i].n_touched > kTouchMax)
+      return fail(c, STG_RT_ENOMEM, "models_move: mover %u touches more than %u other movers; the movers are at their new poses", i, kTouchMax);
+    bool hit = ground[i] || ta[i].static_hit || tb[i].static_hit || runs_into_undone[i];
+    for (uint32_t k = 0; k < ta[i].n_touched && !hit; k++)
+      hit = ta[i].touched[k] > i;
+    for (uint32_t k = 0; k < tb[i].n_touched && !hit; k++)
+      hit = tb[i].touched[k] < i && !stalled[tb[i].touched[k]];
+    stalled[i] = hit ? 1 : 0;
+    any_hit |= hit;
+    if (hit) // i goes back to its present outline: the later movers whose wanted outline touches that one hit it
+      for (uint32_t k = 0; k < tc[i].n_touched; k++)
+        if (tc[i].touched[k] > i)
+          runs_into_undone[tc[i].touched[k]] = 1;
+  }
+  if (!any_hit)
+    return STG_RT_OK;
+  // ---- undo the movers that hit something: UnMap + Map at the present pose, with the sequence numbers kept for them
+  for (uint32_t i = 0; i < n_movers; i++) {
+    if (!stalled[i])
+      continue;
+    c->local_seq = undo_seq[i];
+    for (uint32_t k = mover_first[i]; k < mover_first[i + 1] && !rc; k++)
+      rc = block_unmap_locked(c, blocks[k], layer);
+    for (uint32_t k = mover_first[i]; k < mover_first[i + 1] && !rc; k++)
+      rc = block_map_locked(c, blocks[k], c->blocks[blocks[k]].model, layer, z_start[2 * k], z_start[2 * k + 1],
+                            (int)(first_pt_start[k + 1] - first_pt_start[k]), xy_start + 2 * (size_t)first_pt_start[k]);
+    if (rc)
+      return rc;
+  }
+  c->hold_epoch = true;
+  rc = flush_locked(c);
+  c->hold_epoch = false;
+  return rc;
 }
 
 int stg_rt_blobs_submit(stg_rt_ctx *c, uint32_t n_finders, const stg_rt_blob_finder *finders, uint32_t n_colors,

@@ -195,6 +195,28 @@ struct CollisionBatchView {
 };
 void launch_collisions(const GridView &g, const CollisionBatchView &b, void *stream);
 
+// ---- batched Move (ModelPosition::Move) ----------------------------------------------------------
+// What a mover's new outline touches (Block::TestCollision's condition, block.cc:153-157), split into
+// "something that does not move this tick" and the list of other movers it touches.
+constexpr uint32_t kTouchMax = 30;
+struct TouchRec {
+  uint32_t static_hit;        // 1: touches a model that is not one of this call's movers
+  uint32_t n_touched;         // entries of touched[] (may hold duplicates; > kTouchMax: overflowed)
+  uint32_t touched[kTouchMax]; // indices of other movers touched
+};
+static_assert(sizeof(TouchRec) == 128, "TouchRec");
+
+struct TouchBatchView {
+  uint32_t n_queries;
+  const CollisionQuery *queries; // outlines to test (need not be rendered), first_step running per query
+  const EdgeRec *edges;          // EdgeRec::block = the block the outline belongs to (its model, root)
+  const double *edge_z;          // per edge: zmin, zmax the block will have (Block::Map sets global_z before the test)
+  const uint32_t *mover_of_model; // per model: index + 1 of the mover whose tree it belongs to, 0 = none
+  TouchRec *out;
+};
+void launch_touches(const GridView &g, const TouchBatchView &b, void *stream);
+void launch_mark_movers(const uint32_t *pairs, uint32_t n, uint32_t *table, int clear, void *stream);
+
 // ---- fiducial finders (same layouts as stg_rt_fid_* in include/stg_rt.h) -----------------------
 struct FidTargetRec {
   uint32_t model;

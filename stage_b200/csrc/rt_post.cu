@@ -320,6 +320,80 @@ __global__ void __launch_bounds__(128) k4_collisions(GridView g, CollisionBatchV
     b.hit_model[warp] = result;
 }
 
+// ---- K5: what the movers' new outlines touch (stg_rt_models_move) ----------------------------------
+// The same cell walk and the same condition as K4, but instead of the first model in the way it
+// reports (a) whether anything that does not move this tick is in the way and (b) which other movers
+// are. The outline walked is the one the mover WANTS (it need not be rendered); the block's z range
+// and ownership come from the edge records' block. One warp per mover.
+__global__ void __launch_bounds__(128) k5_touches(GridView g, TouchBatchView b)
+{
+  __shared__ uint32_t list_all[4][kTouchMax];
+  __shared__ uint32_t count_all[4], static_all[4];
+  const uint32_t wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t warp = blockIdx.x * 4 + wic;
+  if (warp >= b.n_queries)
+    return;
+  uint32_t *list = list_all[wic];
+  if (lane == 0)
+    count_all[wic] = static_all[wic] = 0;
+  __syncwarp();
+  const CollisionQuery q = b.queries[warp];
+  const EdgeRec *edges = b.edges + q.first_edge;
+  const int L = q.layer & 1;
+  const unsigned long long *slots = g.slots[L];
+  const uint4 *recs = reinterpret_cast<const uint4 *>(g.blk_rec[L]);
+  for (uint32_t t = lane; t < q.n_steps; t += 32) {
+    uint32_t ei = 0;
+    while (ei + 1 < q.n_edges && edges[ei + 1].first_step <= t)
+      ei++;
+    const EdgeRec e = edges[ei];
+    int32_t x, y;
+    edge_cell_post(e, t - e.first_step, x, y);
+    const uint4 oo = __ldg(recs + 2 * (size_t)e.block + 1);
+    const double own_zmin = b.edge_z[2 * (q.first_edge + ei)], own_zmax = b.edge_z[2 * (q.first_edge + ei) + 1];
+    const uint32_t own_model = oo.z, own_root = oo.w & kRecRootMask;
+    const int32_t rix = (x >> kRBits) - g.rx0, riy = (y >> kRBits) - g.ry0;
+    const uint32_t region = (uint32_t)(riy * g.nrx + rix);
+    const uint32_t key = (region << (2 * kRBits)) | (((uint32_t)y & (kRegionWidth - 1)) << kRBits) | ((uint32_t)x & (kRegionWidth - 1));
+    uint32_t h = slot_home(key, g.slot_mask);
+    for (uint32_t probes = 0; probes <= g.slot_mask; probes++) {
+      const unsigned long long cur = __ldg(slots + h);
+      if (cur == kSlotEmpty)
+        break;
+      if ((uint32_t)(cur >> 32) == key) {
+        const uint32_t blk = (uint32_t)cur - 1u;
+        const uint4 z = __ldg(recs + 2 * (size_t)blk), o = __ldg(recs + 2 * (size_t)blk + 1);
+        const double zmin = __hiloint2double((int)z.y, (int)z.x), zmax = __hiloint2double((int)z.w, (int)z.z);
+        if (o.z != own_model && (o.w & kRecObstacle) && (o.w & kRecRootMask) != own_root && zmin <= own_zmax && zmax >= own_zmin) {
+          const uint32_t mover = __ldg(b.mover_of_model + o.z); // block.cc:153-157 holds: who is it?
+          if (mover == 0) {
+            static_all[wic] = 1;
+          } else {
+            bool seen = false;
+            const uint32_t n = min(*(volatile uint32_t *)(count_all + wic), kTouchMax);
+            for (uint32_t i = 0; i < n && !seen; i++)
+              seen = ((volatile uint32_t *)list)[i] == mover - 1u;
+            if (!seen) {
+              const uint32_t at = atomicAdd(count_all + wic, 1u);
+              if (at < kTouchMax)
+                list[at] = mover - 1u;
+            }
+          }
+        }
+      }
+      h = (h + 1) & g.slot_mask;
+    }
+  }
+  __syncwarp();
+  TouchRec *out = b.out + warp;
+  if (lane == 0) {
+    out->static_hit = static_all[wic];
+    out->n_touched = count_all[wic];
+  }
+  if (lane < kTouchMax)
+    out->touched[lane] = lane < min(count_all[wic], kTouchMax) ? list[lane] : 0u;
+}
+
 // ColorMatchIgnoreAlpha, model_blobfinder.cc:109-113
 __device__ __forceinline__ bool color_match(const double *a, const double *c)
 {
@@ -441,6 +515,27 @@ void launch_collisions(const GridView &g, const CollisionBatchView &b, void *str
   if (!b.n_queries)
     return;
   k4_collisions<<<(b.n_queries * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g, b);
+}
+
+// table[pairs[2i]] = clear ? 0 : pairs[2i + 1]
+__global__ void __launch_bounds__(256) k5_mark_movers(const uint32_t *pairs, uint32_t n, uint32_t *table, int clear)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    table[pairs[2 * i]] = clear ? 0u : pairs[2 * i + 1];
+}
+
+void launch_mark_movers(const uint32_t *pairs, uint32_t n, uint32_t *table, int clear, void *stream)
+{
+  if (n)
+    k5_mark_movers<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pairs, n, table, clear);
+}
+
+void launch_touches(const GridView &g, const TouchBatchView &b, void *stream)
+{
+  if (!b.n_queries)
+    return;
+  k5_touches<<<(b.n_queries + 3) / 4, 128, 0, (cudaStream_t)stream>>>(g, b);
 }
 
 void launch_blobs(const GridView &g, const BlobBatchView &b, void *stream)

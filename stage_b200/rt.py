@@ -92,6 +92,7 @@ def lib():
         "stg_rt_fiducials_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
         "stg_rt_blobs_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
         "stg_rt_collisions_test": (ctypes.c_int, [vp, ctypes.c_int, u32, vp, vp, u32, vp]),
+        "stg_rt_models_move": (ctypes.c_int, [vp, ctypes.c_int, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "stg_rt_fans_submit_noisy": (ctypes.c_int, [vp, u32, vp, vp, ctypes.POINTER(FanOut)]),
         "stg_rt_flush": (ctypes.c_int, [vp]),
         "stg_rt_sync": (ctypes.c_int, [vp]),
@@ -126,7 +127,7 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "stg_rt_abi_version stg_rt_create stg_rt_destroy stg_rt_last_error stg_rt_model_upsert stg_rt_block_map "
-    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_collisions_test stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
+    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_collisions_test stg_rt_models_move stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
     "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_debug_trig stg_rt_debug_headings").split()
@@ -255,6 +256,28 @@ class Context:
         self._keep.append((first, blocks, hit))
         self._check(self._L.stg_rt_collisions_test(self._h, layer, len(first) - 1, _ptr(first), _ptr(blocks), ground_model, _ptr(hit)))
         return hit
+
+    def models_move(self, layer, movers):
+        """movers: per mover a list of (block id, (zmin, zmax, polygon) wanted, (zmin, zmax, polygon) present) - own
+        blocks, then descendants', depth first - in the order the reference moves them. Synchronous.
+        -> uint8 array: 1 = stalled (re-rendered at the present pose)."""
+        first = np.zeros(len(movers) + 1, np.uint32)
+        first[1:] = np.cumsum([len(m) for m in movers])
+        flat = [b for m in movers for b in m]
+        blocks = np.array([b[0] for b in flat], np.uint32)
+
+        def pack(which):
+            z = np.ascontiguousarray([[b[which][0], b[which][1]] for b in flat], np.float64).reshape(-1, 2)
+            polys = [np.ascontiguousarray(b[which][2], np.int32).reshape(-1, 2) for b in flat]
+            fp = np.zeros(len(flat) + 1, np.uint32)
+            fp[1:] = np.cumsum([len(p) for p in polys])
+            return z, fp, np.ascontiguousarray(np.concatenate(polys, 0) if polys else np.zeros((0, 2)), np.int32)
+        z, fp, xy = pack(1)
+        zs, fps, xys = pack(2)
+        stalled = np.zeros(len(movers), np.uint8)
+        self._check(self._L.stg_rt_models_move(self._h, layer, len(movers), _ptr(first), _ptr(blocks), _ptr(z), _ptr(fp), _ptr(xy),
+                                               _ptr(zs), _ptr(fps), _ptr(xys), _ptr(stalled)))
+        return stalled
 
     def blobs_submit(self, finders, colors_rgb=None, max_per_finder=None):
         """-> (out[n_finders, max_per_finder] of BLOB_DTYPE, count[n_finders]); valid after sync()."""
