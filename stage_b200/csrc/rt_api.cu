@@ -124,6 +124,7 @@ struct stg_rt_ctx {
   std::vector<Submit> f_subs;
   uint64_t f_beams = 0;
   bool f_direct[3] = { false, false, false }; // ranges / intensities / hit_model written in place
+  bool f_copied = false;                       // ... or fetched with the copy engine (STG_RT_RESULTS=copy)
   FanArrays d;
   DevBuf d_in; // fans | first_beam | headings | trig of the batch in flight
   PinBuf h_in, h_ranges, h_intens, h_bearings, h_hit_model, h_hit_cell, h_steps;
@@ -620,9 +621,12 @@ int deliver_locked(stg_rt_ctx *c)
   CU(c, cudaStreamSynchronize(c->stream));
   for (const Submit &s : c->f_subs) {
     // the kernel wrote ranges / intensities / hit models of a solo pinned submit in place
-    deliver_array(c, s.out.ranges, c->h_ranges, s.first_beam, s.n_beams, 8, c->f_direct[0]);
-    deliver_array(c, s.out.intensities, c->h_intens, s.first_beam, s.n_beams, 8, c->f_direct[1]);
-    deliver_array(c, s.out.hit_model, c->h_hit_model, s.first_beam, s.n_beams, 4, c->f_direct[2]);
+    deliver_array(c, s.out.ranges, c->h_ranges, s.first_beam, s.n_beams, 8,
+                  c->f_copied ? is_host_alloc(c, s.out.ranges, s.n_beams * 8) : c->f_direct[0]);
+    deliver_array(c, s.out.intensities, c->h_intens, s.first_beam, s.n_beams, 8,
+                  c->f_copied ? is_host_alloc(c, s.out.intensities, s.n_beams * 8) : c->f_direct[1]);
+    deliver_array(c, s.out.hit_model, c->h_hit_model, s.first_beam, s.n_beams, 4,
+                  c->f_copied ? is_host_alloc(c, s.out.hit_model, s.n_beams * 4) : c->f_direct[2]);
     // these were copied device-to-host, straight into pinned caller memory when possible
     deliver_array(c, s.out.bearings, c->h_bearings, s.first_beam, s.n_beams, 8, is_host_alloc(c, s.out.bearings, s.n_beams * 8));
     deliver_array(c, s.out.hit_cell, c->h_hit_cell, s.first_beam, s.n_beams, 8, is_host_alloc(c, s.out.hit_cell, s.n_beams * 8));
@@ -703,6 +707,10 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   };
   c->f_direct[0] = c->f_direct[1] = c->f_direct[2] = false;
   bool zc_ranges = false, zc_intens = false, zc_model = false;
+  // STG_RT_RESULTS=copy: device buffers + copy engine instead of zero-copy stores (measurements)
+  static const bool copy_results = getenv("STG_RT_RESULTS") && !strcmp(getenv("STG_RT_RESULTS"), "copy");
+  if (copy_results)
+    want &= ~(STG_RT_WANT_RANGES | STG_RT_WANT_INTENSITIES | STG_RT_WANT_HIT_MODEL); // for the zero-copy set-up below only
   if (want & STG_RT_WANT_RANGES) {
     v.ranges = (double *)host_target(solo ? solo->out.ranges : nullptr, c->h_ranges, 8, c->f_direct[0]);
     zc_ranges = true;
@@ -733,12 +741,19 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   c->stats.fans += n_fans;
   c->stats.d2h_bytes += beams * ((zc_ranges ? 8 : 0) + (zc_intens ? 8 : 0) + (zc_model ? 4 : 0));
   for (const Submit &s : c->q_subs) { // what did not go zero-copy
+    if (copy_results) {
+      if ((rc = fetch_array(c, s.out.ranges, c->d.ranges.p, c->h_ranges, s.first_beam, s.n_beams, 8, 0, beams, c->stream)) ||
+          (rc = fetch_array(c, s.out.intensities, c->d.intens.p, c->h_intens, s.first_beam, s.n_beams, 8, 0, beams, c->stream)) ||
+          (rc = fetch_array(c, s.out.hit_model, c->d.hit_model.p, c->h_hit_model, s.first_beam, s.n_beams, 4, 0, beams, c->stream)))
+        return rc;
+    }
     if ((rc = fetch_array(c, s.out.bearings, c->d.bearings.p, c->h_bearings, s.first_beam, s.n_beams, 8, 0, beams, c->stream)) ||
         (rc = fetch_array(c, s.out.hit_cell, c->d.hit_cell.p, c->h_hit_cell, s.first_beam, s.n_beams, 8, 0, beams, c->stream)) ||
         (rc = fetch_array(c, s.out.steps, c->d.steps.p, c->h_steps, s.first_beam, s.n_beams, 8, 0, beams, c->stream)))
       return rc;
   }
 
+  c->f_copied = copy_results;
   c->f_subs.swap(c->q_subs);
   c->f_beams = beams;
   c->q_subs.clear();
