@@ -232,3 +232,65 @@ def test_single_beam_sonar_fans():
         assert bits(g.ranges[i:i + 1])[0] == bits(rg)[0] and g.hit_model[i] == hits["hit_model"][0]
         assert g.bearings[i] == be[0] == 0.0 and g.intensities[i] == it[0]
     p.ctx.close()
+
+
+def test_config5_full_size_timing():
+    """BASELINE config 5 at full size on one replica: the config-3 map plus 10,000 single-rectangle pucks (0.1 m) that
+    all move every tick -> 10 k unmap + 10 k map deltas per tick. Times the delta path (host build + upload + K1) and
+    checks the grid against the oracle at the end. (The 8-GPU exchange of the same blobs: tests/multi_gpu_check.py.)"""
+    import time
+    from stage_b200 import worldgen
+    w = worldgen.make_world(seed=1, n_rects=4096, n_robots=1, half_extent_m=81.92)
+    n, ticks = 10000, 12
+    x0, y0, nx, ny = w.sreg_extent()
+    n_obst = len(w.obstacles)
+    ctx = rt.Context(w.ppm, x0, y0, nx, ny, max_models=w.n_models + 2, max_blocks=n_obst + 1 + n, max_cell_entries=1 << 22)
+    worldgen.load_into_context(ctx, w)
+    t1 = oracle_lib.T1World(w.ppm)
+    for mid in [0] + list(w.obstacle_ids) + list(w.robot_ids):
+        t1.model_upsert(int(mid), int(mid), 0.5)
+    polys = worldgen.obstacle_polygons(w) + worldgen.robot_polygons(w)
+    for b, (p, m) in enumerate(zip(polys, np.concatenate([w.obstacle_ids, w.robot_ids]))):
+        for layer in (0, 1):
+            t1.block_map(b, int(m), layer, 0.0, 1.0, p)
+    puck_model = w.n_models + 1
+    ctx.model_upsert(puck_model, puck_model, 0.5)
+    t1.model_upsert(puck_model, puck_model, 0.5)
+    rng = np.random.RandomState(5)
+    pos = rng.randint(-4000, 4000, size=(n, 2))
+    blocks = (n_obst + 1 + np.arange(n)).astype(np.uint32)
+    models = np.full(n, puck_model, np.uint32)
+    z = np.tile([0.0, 0.1], (n, 1))
+    first = np.arange(n + 1, dtype=np.uint32) * 4
+
+    def outlines(pos):
+        x, y = pos[:, 0], pos[:, 1]
+        return np.ascontiguousarray(np.stack([x, y, x + 5, y, x + 5, y + 5, x, y + 5], 1).reshape(-1, 2), np.int32)
+    for layer in (0, 1):
+        ctx.blocks_remap(blocks, models, layer, z, first, outlines(pos))
+    ctx.sync()
+    last = {0: pos.copy(), 1: pos.copy()}
+    host_ms, k1_ms = [], []
+    for tick in range(1, ticks + 1):
+        layer = tick % 2
+        pos = np.clip(pos + rng.randint(-4, 5, size=(n, 2)), -4050, 4050)
+        xy = outlines(pos)
+        t0 = time.perf_counter()
+        ctx.blocks_remap(blocks, models, layer, z, first, xy)
+        ctx.flush()
+        t1_ = time.perf_counter()
+        ctx.sync()
+        host_ms.append(1e3 * (t1_ - t0))
+        k1_ms.append(ctx.kernel_times()["deltas_ms"])
+        last[layer] = pos.copy()
+    for layer in (0, 1):  # the oracle only needs the final state of each layer
+        xy = outlines(last[layer])
+        for b in range(n):
+            t1.block_map(int(blocks[b]), puck_model, layer, 0.0, 0.1, xy[4 * b:4 * b + 4])
+    rec_g, cnt_g = ctx.grid_dump()
+    rec_o, cnt_o = t1.dump_grid()
+    assert np.array_equal(oracle_lib.sort_grid(rec_g), rec_o)  # list order too: both mapped the pucks in block order last
+    assert np.array_equal(oracle_lib.sort_counts(cnt_g), cnt_o)
+    print("config 5, one replica: 10000 pucks re-rasterised per tick: host (remap + delta build + launches) %.2f ms, K1 on the device %.3f ms"
+          % (np.median(host_ms[2:]), np.median(k1_ms[2:])))
+    ctx.close()
