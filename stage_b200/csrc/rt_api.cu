@@ -892,12 +892,11 @@ int stg_rt_destroy(stg_rt_ctx *c)
     return STG_RT_EINVAL;
   cudaSetDevice(c->cfg.device);
   cudaStreamSynchronize(c->stream);
-  if (c->prof_on && c->prof_flushes)
-    fprintf(stderr, "stg_rt host profile over %llu fan launches, us each: stage fans + headings %.1f | sort units %.1f | size deltas %.1f | "
-                    "write deltas %.1f | upload + K1 launches %.1f | march launch %.1f\n",
-            (unsigned long long)c->prof_flushes, c->prof_us[0] / c->prof_flushes, c->prof_us[1] / c->prof_flushes,
-            c->prof_us[2] / c->prof_flushes, c->prof_us[3] / c->prof_flushes, c->prof_us[4] / c->prof_flushes,
-            c->prof_us[5] / c->prof_flushes);
+  if (c->prof_on)
+    fprintf(stderr, "stg_rt host profile, total us (%llu fan launches): stage fans + headings %.0f | sort units %.0f | size deltas %.0f | "
+                    "write deltas %.0f | upload + K1 launches %.0f | march launch %.0f | blocks_remap calls %.0f\n",
+            (unsigned long long)c->prof_flushes, c->prof_us[0], c->prof_us[1], c->prof_us[2], c->prof_us[3], c->prof_us[4],
+            c->prof_us[5], c->prof_us[6]);
   GridView &g = c->g;
   void *dev[] = { g.reg_count, g.occ[0], g.slots[0], g.slots[1], g.blk_rec[0], g.blk_rec[1], c->spare_slots,
                   g.mdl_root, g.mdl_ranger_return, g.mdl_flags, c->d_blob.p };
@@ -999,6 +998,7 @@ int stg_rt_blocks_remap(stg_rt_ctx *c, uint32_t n, const uint32_t *blocks, const
   if (!c || (n && (!blocks || !models || !z || !first_pt || !xy)))
     return STG_RT_EINVAL;
   std::lock_guard<std::mutex> lk(c->mu);
+  const double t_prof = prof_now(c);
   for (uint32_t i = 0; i < n; i++) {
     int rc = block_unmap_locked(c, blocks[i], layer);
     if (!rc)
@@ -1007,6 +1007,8 @@ int stg_rt_blocks_remap(stg_rt_ctx *c, uint32_t n, const uint32_t *blocks, const
     if (rc)
       return rc;
   }
+  if (c->prof_on)
+    c->prof_us[6] += prof_now(c) - t_prof;
   return STG_RT_OK;
 }
 

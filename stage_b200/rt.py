@@ -133,8 +133,18 @@ EXPORTED_SYMBOLS = (
     "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_debug_trig stg_rt_debug_headings").split()
 
 
+_BYTES0 = ctypes.c_char * 0
+
+
 def _ptr(a):
-    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+    """address of a contiguous numpy array (as an int: every pointer argument is declared c_void_p). Going through
+    the buffer protocol costs a tenth of ndarray.ctypes.data_as, which matters for calls made every tick."""
+    if a is None:
+        return None
+    try:
+        return ctypes.addressof(_BYTES0.from_buffer(a))
+    except (TypeError, ValueError, BufferError):  # read-only buffer
+        return a.ctypes.data
 
 
 def make_fans(n):
