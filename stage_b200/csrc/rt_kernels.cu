@@ -438,11 +438,58 @@ __global__ void __launch_bounds__(32) k2_fan_headings(FanBatchView b)
   }
 }
 
+// The same headings for batches of SHORT fans (single-beam sonars, the one-ray fans of the fiducial and
+// explicit-ray paths: BASELINE config 4 has 1.6 M of them): one thread per fan, the recurrence run as it is.
+__global__ void __launch_bounds__(128) k2_fan_headings_short(FanBatchView b)
+{
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= b.n_fans)
+    return;
+  const FanRec fan = b.fans[f];
+  const uint32_t first = b.fan_first_beam[f], n = fan.n_samples;
+  double *heading = b.heading + first;
+  double *bearing = b.bearings ? b.bearings + first : nullptr;
+  if (fan.angles == 0 /* STG_RT_ANGLES_RANGER */) {
+    const uint32_t nm1 = n - 1u;
+    const double incr = fan.fov / (double)(nm1 > 1u ? nm1 : 1u);
+    const double start = n > 1 ? -fan.fov / 2.0 : 0.0;
+    const double jitter = b.noise ? b.noise[f].angle_noise : 0.0;
+    const unsigned long long seed = b.noise ? (b.noise[f].seed ? b.noise[f].seed : fan.finder + 1ull) : 0ull;
+    double a = fan.oa;
+    for (uint32_t t = 0; t < n; t++) {
+      const float fa = (float)a;
+      heading[t] = jitter != 0.0 ? (double)(float)(a + incr * jitter * noise_simple(noise_bits(seed, first + t, b.noise_epoch, 0)) * 0.5)
+                                 : (double)fa;
+      a = (double)fa + incr;
+      if (bearing)
+        bearing[t] = start + ((double)t) * incr;
+    }
+  } else if (fan.angles == 1 /* STG_RT_ANGLES_EVEN_FOV */) {
+    const double starta = fan.fov / 2.0 - fan.oa;
+    for (uint32_t s = 0; s < n; s++) {
+      const double h = ((double)s * fan.fov / (double)(n - 1u)) - starta;
+      heading[s] = h;
+      if (bearing)
+        bearing[s] = h - fan.oa;
+    }
+  } else {
+    for (uint32_t s = 0; s < n; s++) {
+      const double h = b.headings_in[fan.first_heading + s];
+      heading[s] = h;
+      if (bearing)
+        bearing[s] = h - fan.oa;
+    }
+  }
+}
+
 void launch_fan_headings(const FanBatchView &b, void *stream)
 {
   if (!b.n_fans)
     return;
-  k2_fan_headings<<<b.n_fans, 32, 0, (cudaStream_t)stream>>>(b);
+  if (b.n_beams <= 8ull * b.n_fans) // short fans on average: a warp per fan would idle
+    k2_fan_headings_short<<<(b.n_fans + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b);
+  else
+    k2_fan_headings<<<b.n_fans, 32, 0, (cudaStream_t)stream>>>(b);
 }
 
 // K2, the ray march, lives in rt_march.cu.

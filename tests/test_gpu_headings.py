@@ -68,3 +68,19 @@ def test_even_and_explicit_headings():
         return np.array([(np.float64(s) * fov / np.float64(n - 1)) - (fov / 2.0 - oa) for s in range(n)])
     want = np.concatenate([even(0.3, 1.0471975511965976, 80), explicit, even(-2.0, 3.0, 5)])
     assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+
+
+def test_short_fans_take_the_thread_per_fan_kernel():
+    """batches of short fans (sonars: one beam each) are handled one thread per fan; same rule, same bits"""
+    rng = np.random.RandomState(11)
+    n_fans = 5000
+    ns = rng.choice([1, 1, 1, 2, 3, 5, 8], n_fans)
+    fans = rt.make_fans(n_fans)
+    fans["finder"], fans["pred"], fans["angles"], fans["range"] = 0, rt.PRED_RANGER, rt.ANGLES_RANGER, 1.0
+    fans["oa"], fans["fov"], fans["n_samples"] = rng.uniform(-np.pi, np.pi, n_fans), rng.uniform(0.0, 1.0, n_fans), ns
+    ctx = rt.Context(50.0, -1, -1, 2, 2, max_models=4, max_blocks=4, max_cell_entries=1 << 10)
+    ctx.model_upsert(0, 0)
+    got = ctx.debug_headings(fans)
+    ctx.close()
+    want = np.concatenate([host_headings(f["oa"], f["fov"], int(f["n_samples"])) for f in fans])
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
