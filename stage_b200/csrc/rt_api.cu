@@ -111,7 +111,16 @@ struct stg_rt_ctx {
   bool t_rec[3] = { false, false, false };
 
   // fans queued by stg_rt_fans_submit and not launched yet
-  std::vector<FanRec> q_fans;
+  // the queued fan records live in page-locked memory and are uploaded from where the caller's records were
+  // copied to (a batch of sonars is a million records: every extra pass over them costs milliseconds)
+  struct PinFans {
+    FanRec *p = nullptr;
+    size_t n = 0, cap = 0;
+    size_t size() const { return n; }
+    FanRec *data() { return p; }
+    void clear() { n = 0; }
+  } q_fans;
+  cudaEvent_t fans_uploaded = nullptr;
   std::vector<uint32_t> q_first;
   std::vector<double> q_headings, q_trig;
   std::vector<FanNoiseRec> q_noise; // parallel to q_fans once any noisy fan is queued
@@ -537,6 +546,25 @@ FanBatchView view_of(const FanArrays &a, uint32_t n_fans, uint64_t beams, uint32
   return v;
 }
 
+int pinfans_resize(stg_rt_ctx *c, size_t n)
+{
+  stg_rt_ctx::PinFans &q = c->q_fans;
+  if (n > q.cap) {
+    const size_t cap = std::max<size_t>(std::max(n, 2 * q.cap), 1024);
+    FanRec *p = nullptr;
+    if (cudaMallocHost(&p, cap * sizeof(FanRec)) != cudaSuccess)
+      return fail(c, STG_RT_ENOMEM, "cudaMallocHost(%zu) for the fan queue failed", cap * sizeof(FanRec));
+    if (q.n)
+      memcpy(p, q.p, q.n * sizeof(FanRec));
+    if (q.p)
+      cudaFreeHost(q.p);
+    q.p = p;
+    q.cap = cap;
+  }
+  q.n = n;
+  return 0;
+}
+
 int validate_fans(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *fans, const double *headings)
 {
   for (uint32_t i = 0; i < n_fans; i++) {
@@ -664,7 +692,6 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   if ((rc = pin_reserve(c, c->h_in, b_all)))
     return rc;
   char *hp = (char *)c->h_in.p;
-  memcpy(hp, c->q_fans.data(), b_fans);
   memcpy(hp + o_first, c->q_first.data(), b_first);
   if (b_head)
     memcpy(hp + o_head, c->q_headings.data(), b_head);
@@ -677,7 +704,9 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   // one device block with the same layout as the pinned one: a single upload per batch
   if ((rc = dev_reserve(c, c->d_in, b_all + 16)) || (rc = reserve_outputs(c, c->d, beams, want)))
     return rc;
-  CU(c, cudaMemcpyAsync(c->d_in.p, hp, b_all, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->d_in.p, c->q_fans.data(), b_fans, cudaMemcpyHostToDevice, c->stream)); // from the queue itself
+  CU(c, cudaMemcpyAsync((char *)c->d_in.p + o_first, hp + o_first, b_all - o_first, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaEventRecord(c->fans_uploaded, c->stream));
   c->stats.h2d_bytes += b_all;
 
   if ((want & STG_RT_WANT_RANGES) && (rc = pin_reserve(c, c->h_ranges, beams * 8))) return rc;
@@ -828,6 +857,7 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
   CUC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   CUC(cudaEventCreateWithFlags(&c->blob_uploaded, cudaEventDisableTiming));
+  CUC(cudaEventCreateWithFlags(&c->fans_uploaded, cudaEventDisableTiming));
   for (int k = 0; k < 3; k++)
     for (int j = 0; j < 2; j++)
       CUC(cudaEventCreate(&c->t_ev[k][j]));
@@ -905,6 +935,8 @@ int stg_rt_destroy(stg_rt_ctx *c)
       cudaFree(p);
   free_fan_arrays(c->d);
   free_fan_arrays(c->bd);
+  if (c->q_fans.p)
+    cudaFreeHost(c->q_fans.p);
   if (c->d_in.p)
     cudaFree(c->d_in.p);
   for (DevBuf *b : { &c->d_mv_in, &c->d_mv_out, &c->d_mover_of_model, &c->d_col_in, &c->d_col_hit, &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_fid_off, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
@@ -920,6 +952,7 @@ int stg_rt_destroy(stg_rt_ctx *c)
   for (auto &kv : c->host_allocs)
     cudaFreeHost(kv.first);
   cudaEventDestroy(c->blob_uploaded);
+  cudaEventDestroy(c->fans_uploaded);
   for (int k = 0; k < 8; k++)
     cudaEventDestroy(c->chunk_ev[k]);
   cudaEventDestroy(c->copies_done);
@@ -1098,9 +1131,7 @@ static int fans_submit_locked(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *
     return STG_RT_OK;
   if (!fans || !out)
     return fail(c, STG_RT_EINVAL, "fans_submit: null fans / out");
-  int rc = validate_fans(c, n_fans, fans, headings);
-  if (rc)
-    return rc;
+  int rc = 0;
   if (!c->q_subs.empty() && c->q_has_trig != (trig != nullptr)) { // a batch is all-strict or all-device trig
     if ((rc = flush_locked(c)))
       return rc;
@@ -1109,21 +1140,40 @@ static int fans_submit_locked(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *
   s.first_beam = c->q_beams;
   s.out = *out;
   uint64_t beams = 0;
-  const size_t head_base = c->q_headings.size();
+  const size_t head_base = c->q_headings.size(), fan_base = c->q_fans.size();
   uint32_t max_head = 0;
-  for (uint32_t i = 0; i < n_fans; i++) {
-    FanRec r;
-    memcpy(&r, &fans[i], sizeof(r));
-    c->q_first.push_back((uint32_t)(c->q_beams + beams));
-    if (r.angles == STG_RT_ANGLES_EXPLICIT) {
-      max_head = std::max(max_head, r.first_heading + r.n_samples);
-      r.first_heading += (uint32_t)head_base;
+  static_assert(sizeof(stg_rt_fan) == sizeof(FanRec), "fan record layout");
+  if (!fan_base)
+    CU(c, cudaEventSynchronize(c->fans_uploaded)); // the previous batch has left the queue's memory
+  if ((rc = pinfans_resize(c, fan_base + n_fans)))
+    return rc;
+  c->q_first.resize(fan_base + n_fans);
+  FanRec *qf = c->q_fans.data() + fan_base;
+  uint32_t *first = c->q_first.data() + fan_base;
+  // one pass over the records (a batch of sonars is a million of them): check, copy, book-keep
+  for (uint32_t i = 0; i < n_fans && !rc; i++) {
+    const stg_rt_fan &f = fans[i];
+    if (f.finder >= c->cfg.max_models || !c->model_known[f.finder])
+      rc = fail(c, STG_RT_EINVAL, "fan %u: unknown finder model %u", i, f.finder);
+    else if (f.pred > STG_RT_PRED_GRIPPER || f.angles > STG_RT_ANGLES_EXPLICIT || f.layer > 1)
+      rc = fail(c, STG_RT_EINVAL, "fan %u: bad pred/angles/layer", i);
+    else if (f.angles == STG_RT_ANGLES_EXPLICIT && !headings)
+      rc = fail(c, STG_RT_EINVAL, "fan %u: explicit headings missing", i);
+    memcpy(&qf[i], &f, sizeof(FanRec));
+    first[i] = (uint32_t)(c->q_beams + beams);
+    if (f.angles == STG_RT_ANGLES_EXPLICIT) {
+      max_head = std::max(max_head, f.first_heading + f.n_samples);
+      qf[i].first_heading += (uint32_t)head_base;
     }
-    c->q_fans.push_back(r);
-    beams += r.n_samples;
+    beams += f.n_samples;
   }
-  if (c->q_beams + beams >= (1ull << 32))
-    return fail(c, STG_RT_EINVAL, "more than 2^32 beams in one batch");
+  if (!rc && c->q_beams + beams >= (1ull << 32))
+    rc = fail(c, STG_RT_EINVAL, "more than 2^32 beams in one batch");
+  if (rc) {
+    c->q_fans.n = fan_base;
+    c->q_first.resize(fan_base);
+    return rc;
+  }
   if (max_head)
     c->q_headings.insert(c->q_headings.end(), headings, headings + max_head);
   if (trig) {

@@ -228,3 +228,57 @@ def test_fiducial_query_at_config4_scale_timing():
         k = L.t1_fiducial_update(t1.h, n, targets.ctypes.data, f.ctypes.data, 96, ref.ctypes.data)
         assert k == cnt[i] and np.array_equal(ref[:k]["target"], tg) and np.array_equal(ref[:k]["id"], out[i, :k]["id"])
     ctx.close()
+
+
+def test_config4_sonar_rays_full_size_timing():
+    """BASELINE config 4's rangers at full size: 100,000 robots x 16 one-beam sonars (range 5 m, the pioneer ring of
+    pioneer.inc:24-39: bearings -90..90 and back) = 1.6 M single-beam fans per tick on the config-3 map. Times a tick
+    through the ABI and checks a sample of the beams against the oracle bit for bit."""
+    import time
+    import oracle_lib
+    from stage_b200 import worldgen
+    w = worldgen.make_world(seed=1, n_rects=4096, n_robots=1, half_extent_m=81.92)
+    x0, y0, nx, ny = w.sreg_extent()
+    n_robots, n_sonar = 100000, 16
+    first_id = w.n_models + 1
+    ctx = rt.Context(w.ppm, x0, y0, nx, ny, max_models=first_id + n_robots + 1, max_blocks=len(w.obstacles) + 2, max_cell_entries=1 << 22)
+    worldgen.load_into_context(ctx, w)
+    t1 = oracle_lib.T1World(w.ppm)
+    for mid in [0] + list(w.obstacle_ids) + list(w.robot_ids):
+        t1.model_upsert(int(mid), int(mid), 0.5)
+    polys = worldgen.obstacle_polygons(w) + worldgen.robot_polygons(w)
+    for b, (p, m) in enumerate(zip(polys, np.concatenate([w.obstacle_ids, w.robot_ids]))):
+        t1.block_map(b, int(m), 1, 0.0, 1.0, p)
+    rng = np.random.RandomState(44)
+    ids = first_id + np.arange(n_robots)
+    for m in ids[:: n_robots // 200]:   # the oracle only needs the finders it is asked about
+        t1.model_upsert(int(m), int(m), 0.5)
+    for m in ids:
+        ctx.model_upsert(int(m), int(m), 0.5)
+    pose = np.stack([rng.uniform(-80, 80, n_robots), rng.uniform(-80, 80, n_robots), rng.uniform(-np.pi, np.pi, n_robots)], 1)
+    ring = np.deg2rad([90, 50, 30, 10, -10, -30, -50, -90, -90, -130, -150, -170, 170, 150, 130, 90])
+    fans = rt.make_fans(n_robots * n_sonar)
+    fans["finder"] = np.repeat(ids, n_sonar)
+    fans["n_samples"], fans["pred"], fans["ztest"], fans["layer"], fans["angles"] = 1, rt.PRED_RANGER, 1, 1, rt.ANGLES_RANGER
+    a = (pose[:, 2:3] + ring[None, :]).reshape(-1)
+    fans["ox"] = np.repeat(pose[:, 0], n_sonar) + 0.15 * np.cos(a)
+    fans["oy"] = np.repeat(pose[:, 1], n_sonar) + 0.15 * np.sin(a)
+    fans["oz"], fans["oa"], fans["range"], fans["fov"] = 0.3, np.arctan2(np.sin(a), np.cos(a)), 5.0, 0.26
+    out = rt.Outputs(len(fans), rt.WANT_RANGES | rt.WANT_HIT_MODEL, alloc=ctx.pinned_empty)
+    ctx.fans_submit(fans, out)
+    ctx.sync()  # warm-up: sizes the buffers
+    t0 = time.perf_counter()
+    ctx.fans_submit(fans, out)
+    t_sub = time.perf_counter() - t0
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    kt = ctx.kernel_times()
+    for i in range(0, len(fans), len(fans) // 3000):
+        f = fans[i]
+        if int(f["finder"]) not in set(int(m) for m in ids[:: n_robots // 200]):
+            t1.model_upsert(int(f["finder"]), int(f["finder"]), 0.5)
+        rg, it, be, hits = t1.ranger_fan(int(f["finder"]), 1, [f["ox"], f["oy"], f["oz"], f["oa"]], 5.0, 0.26, 1)
+        assert out.ranges[i] == rg[0] and out.hit_model[i] == hits["hit_model"][0]
+    print("config-4 sonars: 1.6 M one-beam fans: %.2f ms per tick end to end (submit call %.2f ms: 102 MB of fan records staged and "
+          "uploaded; headings %.3f ms, march %.3f ms on the device), %.0f M rays/s" % (1e3 * dt, 1e3 * t_sub, kt["headings_ms"], kt["march_ms"], len(fans) / dt / 1e6))
+    ctx.close()
