@@ -239,6 +239,35 @@ int stg_rt_fiducials_submit(stg_rt_ctx *ctx, uint32_t n_targets, const stg_rt_fi
                             uint32_t n_finders, const stg_rt_fid_finder *finders,
                             uint32_t max_per_finder, stg_rt_fiducial *out, uint32_t *out_count);
 
+/* ---- whole ranger models ---------------------------------------------------------------------- */
+
+/* One ModelRanger::Sensor as the world file describes it (Sensor::Load, model_ranger.cc:129-156): pose
+   relative to the ranger model, size (only z is read, :223), range.max, fov, sample count. 64 bytes. */
+typedef struct {
+  double px, py, pz, pa;
+  double size_z, range_max, fov;
+  uint32_t n_samples, reserved;
+} stg_rt_ranger_sensor;
+
+/* One ranger model this tick: x, y, z, a = GetGlobalPose() + geom.pose, the frame Model::LocalToGlobal
+   composes a sensor's pose on (stage.hh:2296). 40 bytes. */
+typedef struct {
+  uint32_t finder;          /* the ranger model's id */
+  uint8_t layer;            /* (World::updates + 1) % 2 */
+  uint8_t pad[3];
+  double x, y, z, a;
+} stg_rt_ranger_pose;
+
+/* ModelRanger::Update (model_ranger.cc:202-209) for n_rangers ranger models that share one sensor list
+   (16 sonars on every pioneer): what stg_rt_fans_submit does for n_rangers * n_sensors fans, with the
+   fans derived on the device - origin of the first ray = LocalToGlobal(sensor pose + start angle,
+   + size.z / 2) (:218-226; cos / sin of the model's heading as the host C library gives them) - so
+   that 40 bytes per model cross PCIe instead of 64 per sensor. Beams come back model by model,
+   sensor by sensor: beam t of sensor s of model r is at (r * B + first(s) + t), B = samples per
+   model. Must be the only submit of its batch (it flushes what is queued). */
+int stg_rt_rangers_submit(stg_rt_ctx *ctx, uint32_t n_sensors, const stg_rt_ranger_sensor *sensors, uint32_t n_rangers,
+                          const stg_rt_ranger_pose *poses, const stg_rt_fan_out *out);
+
 /* ---- collision tests ------------------------------------------------------------------------ */
 
 /* Model::TestCollision (model.cc:666-679) for n_queries models at once, against the device grid as

@@ -121,6 +121,14 @@ struct stg_rt_ctx {
     void clear() { n = 0; }
   } q_fans;
   cudaEvent_t fans_uploaded = nullptr;
+  // a queued stg_rt_rangers_submit: the fan records are derived on the device from these
+  struct RigJob {
+    bool active = false;
+    uint32_t n_sensors = 0, n_rangers = 0, uniform_samples = 0;
+    size_t o_first = 0, o_poses = 0, bytes = 0; // layout of h_rig / d_rig: sensors | sensor_first | poses
+  } q_rig;
+  PinBuf h_rig;
+  DevBuf d_rig;
   std::vector<uint32_t> q_first;
   std::vector<double> q_headings, q_trig;
   std::vector<FanNoiseRec> q_noise; // parallel to q_fans once any noisy fan is queued
@@ -677,22 +685,25 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   int rc = deliver_locked(c); // staging buffers are single-buffered
   if (rc)
     return rc;
-  const uint32_t n_fans = (uint32_t)c->q_fans.size();
+  const bool rig = c->q_rig.active;
+  const uint32_t n_fans = rig ? c->q_rig.n_rangers * c->q_rig.n_sensors : (uint32_t)c->q_fans.size();
   const uint64_t beams = c->q_beams;
   uint32_t want = 0;
   for (const Submit &s : c->q_subs)
     want |= want_of(s.out);
-  c->q_first.push_back((uint32_t)beams);
+  if (!rig)
+    c->q_first.push_back((uint32_t)beams);
 
   // one pinned block: fans | first | headings | trig
   const size_t b_fans = (size_t)n_fans * sizeof(FanRec), b_first = (size_t)(n_fans + 1) * 4;
   const size_t b_head = c->q_headings.size() * 8, b_trig = c->q_has_trig ? beams * 16 : 0;
   const size_t o_first = b_fans, o_head = (o_first + b_first + 15) & ~(size_t)15, o_trig = o_head + b_head;
   const size_t b_noise = c->q_has_noise ? (size_t)n_fans * sizeof(FanNoiseRec) : 0, o_noise = o_trig + b_trig, b_all = o_noise + b_noise;
-  if ((rc = pin_reserve(c, c->h_in, b_all)))
+  if (!rig && (rc = pin_reserve(c, c->h_in, b_all))) // a ranger-model batch has nothing to stage here
     return rc;
   char *hp = (char *)c->h_in.p;
-  memcpy(hp + o_first, c->q_first.data(), b_first);
+  if (!rig)
+    memcpy(hp + o_first, c->q_first.data(), b_first);
   if (b_head)
     memcpy(hp + o_head, c->q_headings.data(), b_head);
   if (b_trig)
@@ -704,10 +715,22 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   // one device block with the same layout as the pinned one: a single upload per batch
   if ((rc = dev_reserve(c, c->d_in, b_all + 16)) || (rc = reserve_outputs(c, c->d, beams, want)))
     return rc;
-  CU(c, cudaMemcpyAsync(c->d_in.p, c->q_fans.data(), b_fans, cudaMemcpyHostToDevice, c->stream)); // from the queue itself
-  CU(c, cudaMemcpyAsync((char *)c->d_in.p + o_first, hp + o_first, b_all - o_first, cudaMemcpyHostToDevice, c->stream));
-  CU(c, cudaEventRecord(c->fans_uploaded, c->stream));
-  c->stats.h2d_bytes += b_all;
+  if (rig) { // fan records and first-beam prefix are derived on the device (k2_expand_rangers)
+    if ((rc = dev_reserve(c, c->d_rig, c->q_rig.bytes)))
+      return rc;
+    CU(c, cudaMemcpyAsync(c->d_rig.p, c->h_rig.p, c->q_rig.bytes, cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2d_bytes += c->q_rig.bytes;
+    const char *dr = (const char *)c->d_rig.p;
+    launch_expand_rangers((const RangerSensorRec *)dr, c->q_rig.n_sensors, (const uint32_t *)(dr + c->q_rig.o_first),
+                          (const RangerPoseRec *)(dr + c->q_rig.o_poses), c->q_rig.n_rangers, (FanRec *)c->d_in.p,
+                          (uint32_t *)((char *)c->d_in.p + o_first), c->stream);
+    c->stats.launches_post++;
+  } else {
+    CU(c, cudaMemcpyAsync(c->d_in.p, c->q_fans.data(), b_fans, cudaMemcpyHostToDevice, c->stream)); // from the queue itself
+    CU(c, cudaMemcpyAsync((char *)c->d_in.p + o_first, hp + o_first, b_all - o_first, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaEventRecord(c->fans_uploaded, c->stream));
+    c->stats.h2d_bytes += b_all;
+  }
 
   if ((want & STG_RT_WANT_RANGES) && (rc = pin_reserve(c, c->h_ranges, beams * 8))) return rc;
   if ((want & STG_RT_WANT_INTENSITIES) && (rc = pin_reserve(c, c->h_intens, beams * 8))) return rc;
@@ -717,7 +740,7 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   if ((want & STG_RT_WANT_STEPS) && (rc = pin_reserve(c, c->h_steps, beams * 8))) return rc;
 
   FanBatchView v = view_of(c->d, n_fans, beams, want, c->q_has_trig, b_head != 0);
-  v.uniform_samples = uniform_samples_of(c->q_fans.data(), n_fans);
+  v.uniform_samples = rig ? c->q_rig.uniform_samples : uniform_samples_of(c->q_fans.data(), n_fans);
   v.fans = (const FanRec *)c->d_in.p;
   v.fan_first_beam = (const uint32_t *)((const char *)c->d_in.p + o_first);
   v.headings_in = b_head ? (const double *)((const char *)c->d_in.p + o_head) : nullptr;
@@ -787,6 +810,7 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   c->f_beams = beams;
   c->q_subs.clear();
   c->q_fans.clear();
+  c->q_rig.active = false;
   c->q_first.clear();
   c->q_headings.clear();
   c->q_trig.clear();
@@ -939,10 +963,10 @@ int stg_rt_destroy(stg_rt_ctx *c)
     cudaFreeHost(c->q_fans.p);
   if (c->d_in.p)
     cudaFree(c->d_in.p);
-  for (DevBuf *b : { &c->d_mv_in, &c->d_mv_out, &c->d_mover_of_model, &c->d_col_in, &c->d_col_hit, &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_fid_off, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
+  for (DevBuf *b : { &c->d_rig, &c->d_mv_in, &c->d_mv_out, &c->d_mover_of_model, &c->d_col_in, &c->d_col_hit, &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_fid_off, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
     if (b->p)
       cudaFree(b->p);
-  for (PinBuf *b : { &c->h_mv_in, &c->h_mv_out, &c->h_col_in, &c->h_col_hit, &c->h_fid_in, &c->h_fid_out, &c->h_fid_count, &c->h_blob_in, &c->h_blob_out, &c->h_blob_count })
+  for (PinBuf *b : { &c->h_rig, &c->h_mv_in, &c->h_mv_out, &c->h_col_in, &c->h_col_hit, &c->h_fid_in, &c->h_fid_out, &c->h_fid_count, &c->h_blob_in, &c->h_blob_out, &c->h_blob_count })
     if (b->p)
       cudaFreeHost(b->p);
   PinBuf *pins[] = { &c->h_blob, &c->h_in, &c->h_ranges, &c->h_intens, &c->h_bearings, &c->h_hit_model, &c->h_hit_cell, &c->h_steps };
@@ -1132,6 +1156,8 @@ static int fans_submit_locked(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *
   if (!fans || !out)
     return fail(c, STG_RT_EINVAL, "fans_submit: null fans / out");
   int rc = 0;
+  if (c->q_rig.active && (rc = flush_locked(c))) // a ranger-model batch is a batch of its own
+    return rc;
   if (!c->q_subs.empty() && c->q_has_trig != (trig != nullptr)) { // a batch is all-strict or all-device trig
     if ((rc = flush_locked(c)))
       return rc;
@@ -1193,6 +1219,58 @@ static int fans_submit_locked(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *
   }
   s.n_beams = beams;
   c->q_beams += beams;
+  c->q_subs.push_back(s);
+  return STG_RT_OK;
+}
+
+int stg_rt_rangers_submit(stg_rt_ctx *c, uint32_t n_sensors, const stg_rt_ranger_sensor *sensors, uint32_t n_rangers,
+                          const stg_rt_ranger_pose *poses, const stg_rt_fan_out *out)
+{
+  static_assert(sizeof(stg_rt_ranger_sensor) == sizeof(RangerSensorRec) && sizeof(stg_rt_ranger_pose) == sizeof(RangerPoseRec),
+                "ranger record layouts");
+  if (!c || !out || (n_sensors && !sensors) || (n_rangers && !poses))
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!n_sensors || !n_rangers)
+    return STG_RT_OK;
+  uint64_t per_model = 0;
+  for (uint32_t s = 0; s < n_sensors; s++)
+    per_model += sensors[s].n_samples;
+  if ((uint64_t)n_rangers * n_sensors >= (1ull << 32) || per_model * n_rangers >= (1ull << 32))
+    return fail(c, STG_RT_EINVAL, "rangers_submit: more than 2^32 fans or beams");
+  for (uint32_t r = 0; r < n_rangers; r++)
+    if (poses[r].finder >= c->cfg.max_models || !c->model_known[poses[r].finder] || poses[r].layer > 1)
+      return fail(c, STG_RT_EINVAL, "ranger %u: unknown model %u or bad layer", r, poses[r].finder);
+  int rc = flush_locked(c); // a batch of its own
+  if (rc || (rc = deliver_locked(c)))
+    return rc;
+  stg_rt_ctx::RigJob &q = c->q_rig;
+  q.n_sensors = n_sensors;
+  q.n_rangers = n_rangers;
+  q.o_first = (size_t)n_sensors * sizeof(RangerSensorRec);
+  q.o_poses = (q.o_first + (size_t)(n_sensors + 1) * 4 + 15) & ~(size_t)15;
+  q.bytes = q.o_poses + (size_t)n_rangers * sizeof(RangerPoseRec);
+  if ((rc = pin_reserve(c, c->h_rig, q.bytes)))
+    return rc;
+  char *hp = (char *)c->h_rig.p;
+  memcpy(hp, sensors, q.o_first);
+  uint32_t *sf = (uint32_t *)(hp + q.o_first);
+  q.uniform_samples = sensors[0].n_samples;
+  uint32_t run = 0;
+  for (uint32_t s = 0; s < n_sensors; s++) {
+    sf[s] = run;
+    run += sensors[s].n_samples;
+    if (sensors[s].n_samples != sensors[0].n_samples)
+      q.uniform_samples = 0;
+  }
+  sf[n_sensors] = run;
+  memcpy(hp + q.o_poses, poses, (size_t)n_rangers * sizeof(RangerPoseRec));
+  q.active = true;
+  Submit s;
+  s.first_beam = 0;
+  s.n_beams = per_model * n_rangers;
+  s.out = *out;
+  c->q_beams = s.n_beams;
   c->q_subs.push_back(s);
   return STG_RT_OK;
 }

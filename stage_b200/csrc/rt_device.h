@@ -177,6 +177,23 @@ struct FanBatchView {
   uint32_t *steps;
 };
 
+// ---- whole ranger models (same layouts as stg_rt_ranger_* in include/stg_rt.h) ------------------
+struct RangerSensorRec {
+  double px, py, pz, pa;
+  double size_z, range_max, fov;
+  uint32_t n_samples, reserved;
+};
+static_assert(sizeof(RangerSensorRec) == 64, "RangerSensorRec");
+struct RangerPoseRec {
+  uint32_t finder;
+  uint8_t layer, pad[3];
+  double x, y, z, a;
+};
+static_assert(sizeof(RangerPoseRec) == 40, "RangerPoseRec");
+// writes n_rangers * n_sensors fan records and their first-beam prefix (n_fans + 1 entries)
+void launch_expand_rangers(const RangerSensorRec *sensors, uint32_t n_sensors, const uint32_t *sensor_first, const RangerPoseRec *poses,
+                           uint32_t n_rangers, FanRec *fans, uint32_t *first, void *stream);
+
 // ---- collision tests (Model::TestCollision) ----------------------------------------------------
 // One query = one top-level Model::TestCollision: the outlines (EdgeRec, first_step running within
 // the query) of the model's blocks and its descendants' in visiting order.

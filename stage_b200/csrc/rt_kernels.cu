@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "rt_device.h"
+#include "rt_libm.cuh"
 
 namespace stg {
 
@@ -480,6 +481,63 @@ __global__ void __launch_bounds__(128) k2_fan_headings_short(FanBatchView b)
         bearing[s] = h - fan.oa;
     }
   }
+}
+
+// ModelRanger::Sensor::Update's set-up (model_ranger.cc:217-230) for every sensor of every ranger model: the fan
+// record stg_rt_fans_submit would have been given. Pose::operator+ (stage.hh:297-304) with the host C library's
+// cos / sin (rt_libm.cuh), same operation order, no contraction.
+__global__ void __launch_bounds__(128) k2_expand_rangers(const RangerSensorRec *sensors, uint32_t n_sensors, const uint32_t *sensor_first,
+                                                         const RangerPoseRec *poses, uint32_t n_rangers, FanRec *fans, uint32_t *first)
+{
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t n_fans = (uint64_t)n_rangers * n_sensors;
+  const uint32_t per_model = sensor_first[n_sensors];
+  if (idx == 0)
+    first[n_fans] = (uint32_t)((uint64_t)n_rangers * per_model);
+  if (idx >= n_fans)
+    return;
+  const uint32_t r = (uint32_t)(idx / n_sensors), s = (uint32_t)(idx % n_sensors);
+  const RangerSensorRec sn = sensors[s];
+  const RangerPoseRec P = poses[r];
+  const double start_angle = sn.n_samples > 1 ? -sn.fov / 2.0 : 0.0; // :221
+  const double la = sn.pa + start_angle, lz = sn.pz + sn.size_z / 2.0; // :224-225
+  double cosa, sina;
+  if (libm::covered(P.a)) {
+    sina = libm::sin_host_exact(P.a);
+    cosa = libm::cos_host_exact(P.a);
+  } else {
+    sina = sin(P.a);
+    cosa = cos(P.a);
+  }
+  double a = P.a + la; // normalize(), stage.hh:163-170
+  while (a < -3.14159265358979323846)
+    a += 2.0 * 3.14159265358979323846;
+  while (a > 3.14159265358979323846)
+    a -= 2.0 * 3.14159265358979323846;
+  FanRec f;
+  f.finder = P.finder;
+  f.n_samples = sn.n_samples;
+  f.pred = 0; // STG_RT_PRED_RANGER
+  f.ztest = 1;
+  f.layer = P.layer;
+  f.angles = 0; // STG_RT_ANGLES_RANGER
+  f.first_heading = 0;
+  f.ox = P.x + sn.px * cosa - sn.py * sina;
+  f.oy = P.y + sn.px * sina + sn.py * cosa;
+  f.oz = P.z + lz;
+  f.oa = a;
+  f.range = sn.range_max;
+  f.fov = sn.fov;
+  fans[idx] = f;
+  first[idx] = r * per_model + sensor_first[s];
+}
+
+void launch_expand_rangers(const RangerSensorRec *sensors, uint32_t n_sensors, const uint32_t *sensor_first, const RangerPoseRec *poses,
+                           uint32_t n_rangers, FanRec *fans, uint32_t *first, void *stream)
+{
+  const uint64_t n = (uint64_t)n_rangers * n_sensors;
+  if (n)
+    k2_expand_rangers<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(sensors, n_sensors, sensor_first, poses, n_rangers, fans, first);
 }
 
 void launch_fan_headings(const FanBatchView &b, void *stream)

@@ -34,6 +34,10 @@ FIDUCIAL_DTYPE = np.dtype([("target", "<u4"), ("id", "<i4"), ("range", "<f8"), (
 BLOB_FINDER_DTYPE = np.dtype([("finder", "<u4"), ("scan_width", "<u4"), ("scan_height", "<u4"), ("layer", "u1"), ("pad", "u1", (3,)),
                               ("first_color", "<u4"), ("n_colors", "<u4"), ("ox", "<f8"), ("oy", "<f8"), ("oz", "<f8"),
                               ("oa", "<f8"), ("range", "<f8"), ("fov", "<f8")])
+RANGER_SENSOR_DTYPE = np.dtype([("px", "<f8"), ("py", "<f8"), ("pz", "<f8"), ("pa", "<f8"), ("size_z", "<f8"), ("range_max", "<f8"),
+                                ("fov", "<f8"), ("n_samples", "<u4"), ("reserved", "<u4")])
+RANGER_POSE_DTYPE = np.dtype([("finder", "<u4"), ("layer", "u1"), ("pad", "u1", (3,)), ("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("a", "<f8")])
+assert RANGER_SENSOR_DTYPE.itemsize == 64 and RANGER_POSE_DTYPE.itemsize == 40
 FAN_NOISE_DTYPE = np.dtype([("range_noise_const", "<f8"), ("range_noise", "<f8"), ("angle_noise", "<f8"), ("seed", "<u8")])
 BLOB_DTYPE = np.dtype([("model", "<u4"), ("left", "<u4"), ("top", "<u4"), ("right", "<u4"), ("bottom", "<u4"), ("pad", "<u4"),
                        ("range", "<f8")])
@@ -91,6 +95,7 @@ def lib():
         "stg_rt_fans_submit": (ctypes.c_int, [vp, u32, vp, vp, vp, ctypes.POINTER(FanOut)]),
         "stg_rt_fiducials_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
         "stg_rt_blobs_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
+        "stg_rt_rangers_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, ctypes.POINTER(FanOut)]),
         "stg_rt_collisions_test": (ctypes.c_int, [vp, ctypes.c_int, u32, vp, vp, u32, vp]),
         "stg_rt_models_move": (ctypes.c_int, [vp, ctypes.c_int, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "stg_rt_fans_submit_noisy": (ctypes.c_int, [vp, u32, vp, vp, ctypes.POINTER(FanOut)]),
@@ -127,7 +132,7 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "stg_rt_abi_version stg_rt_create stg_rt_destroy stg_rt_last_error stg_rt_model_upsert stg_rt_block_map "
-    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_collisions_test stg_rt_models_move stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
+    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_rangers_submit stg_rt_collisions_test stg_rt_models_move stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
     "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_debug_trig stg_rt_debug_headings").split()
@@ -235,6 +240,13 @@ class Context:
         self._keep.append(out)
         self._check(self._L.stg_rt_fans_submit(self._h, len(fans), _ptr(fans), _ptr(headings), _ptr(trig),
                                                ctypes.byref(out.struct)))
+
+    def rangers_submit(self, sensors, poses, out):
+        """whole ranger models: sensors = RANGER_SENSOR_DTYPE array shared by all, poses = RANGER_POSE_DTYPE array"""
+        sensors = np.ascontiguousarray(sensors, RANGER_SENSOR_DTYPE)
+        poses = np.ascontiguousarray(poses, RANGER_POSE_DTYPE)
+        self._keep.append(out)
+        self._check(self._L.stg_rt_rangers_submit(self._h, len(sensors), _ptr(sensors), len(poses), _ptr(poses), ctypes.byref(out.struct)))
 
     def fiducials_submit(self, targets, finders, max_per_finder=16, into=None):
         """-> (out[n_finders, max_per_finder] of FIDUCIAL_DTYPE, count[n_finders]); valid after sync().

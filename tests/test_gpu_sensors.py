@@ -279,6 +279,81 @@ def test_config4_sonar_rays_full_size_timing():
             t1.model_upsert(int(f["finder"]), int(f["finder"]), 0.5)
         rg, it, be, hits = t1.ranger_fan(int(f["finder"]), 1, [f["ox"], f["oy"], f["oz"], f["oa"]], 5.0, 0.26, 1)
         assert out.ranges[i] == rg[0] and out.hit_model[i] == hits["hit_model"][0]
+    # the same sensors as whole ranger models: 40 bytes per robot instead of 64 per sonar
+    sensors = np.zeros(n_sonar, rt.RANGER_SENSOR_DTYPE)
+    sensors["px"], sensors["py"], sensors["pa"] = 0.15 * np.cos(ring), 0.15 * np.sin(ring), ring
+    sensors["pz"], sensors["size_z"], sensors["range_max"], sensors["fov"], sensors["n_samples"] = 0.3, 0.0, 5.0, 0.26, 1
+    rp = np.zeros(n_robots, rt.RANGER_POSE_DTYPE)
+    rp["finder"], rp["layer"], rp["x"], rp["y"], rp["a"] = ids, 1, pose[:, 0], pose[:, 1], pose[:, 2]
+    out2 = rt.Outputs(len(fans), rt.WANT_RANGES | rt.WANT_HIT_MODEL, alloc=ctx.pinned_empty)
+    ctx.rangers_submit(sensors, rp, out2)
+    ctx.sync()
+    t0 = time.perf_counter()
+    ctx.rangers_submit(sensors, rp, out2)
+    ctx.sync()
+    dt_rig = time.perf_counter() - t0
+    same = np.mean((out2.hit_model == out.hit_model) & (np.abs(out2.ranges - out.ranges) < 1e-9))
+    assert same > 0.999  # the fan origins above were put together with numpy's cos / sin, not operation for operation
+    print("config-4 sonars as 100 k ranger models (stg_rt_rangers_submit): %.2f ms per tick end to end, %.0f M rays/s" % (1e3 * dt_rig, len(fans) / dt_rig / 1e6))
     print("config-4 sonars: 1.6 M one-beam fans: %.2f ms per tick end to end (submit call %.2f ms: 102 MB of fan records staged and "
           "uploaded; headings %.3f ms, march %.3f ms on the device), %.0f M rays/s" % (1e3 * dt, 1e3 * t_sub, kt["headings_ms"], kt["march_ms"], len(fans) / dt / 1e6))
+    ctx.close()
+
+
+def host_ranger_fans(sensors, poses):
+    """the fan records ModelRanger::Sensor::Update sets up (model_ranger.cc:217-230), with the host C library"""
+    import math
+    fans = rt.make_fans(len(poses) * len(sensors))
+    k = 0
+    for P in poses:
+        cosa, sina = math.cos(P["a"]), math.sin(P["a"])
+        for sn in sensors:
+            n = int(sn["n_samples"])
+            start = -sn["fov"] / 2.0 if n > 1 else 0.0
+            la, lz = sn["pa"] + start, sn["pz"] + sn["size_z"] / 2.0
+            a = P["a"] + la
+            while a < -math.pi:
+                a += 2.0 * math.pi
+            while a > math.pi:
+                a -= 2.0 * math.pi
+            f = fans[k]
+            f["finder"], f["n_samples"], f["pred"], f["ztest"], f["layer"], f["angles"] = P["finder"], n, rt.PRED_RANGER, 1, P["layer"], rt.ANGLES_RANGER
+            f["ox"] = P["x"] + sn["px"] * cosa - sn["py"] * sina
+            f["oy"] = P["y"] + sn["px"] * sina + sn["py"] * cosa
+            f["oz"], f["oa"], f["range"], f["fov"] = P["z"] + lz, a, sn["range_max"], sn["fov"]
+            k += 1
+    return fans
+
+
+def test_whole_ranger_models_equal_their_fans():
+    """stg_rt_rangers_submit derives on the device the fans a caller of stg_rt_fans_submit would have set up on the
+    host: same beams, same bits. A sonar ring of 16 one-beam sensors and a rig mixing a 180-beam laser with sonars."""
+    from stage_b200 import worldgen
+    w = worldgen.make_world(seed=6, n_rects=600, n_robots=300, half_extent_m=30.72)
+    x0, y0, nx, ny = w.sreg_extent()
+    ctx = rt.Context(w.ppm, x0, y0, nx, ny, max_models=w.n_models + 1, max_blocks=len(w.obstacles) + len(w.robots), max_cell_entries=1 << 20)
+    worldgen.load_into_context(ctx, w)
+    rng = np.random.RandomState(2)
+    poses = np.zeros(len(w.robots), rt.RANGER_POSE_DTYPE)
+    poses["finder"], poses["layer"] = w.robot_ids, 1
+    poses["x"], poses["y"], poses["z"] = w.robots[:, 0], w.robots[:, 1], 0.1
+    poses["a"] = np.deg2rad(w.robots[:, 2])
+    poses["a"][:5] = [0.0, np.pi, -np.pi, 3.1, -3.1]  # the normalisation's edges
+    ring = np.deg2rad([90, 50, 30, 10, -10, -30, -50, -90, -90, -130, -150, -170, 170, 150, 130, 90])
+    sonar = np.zeros(16, rt.RANGER_SENSOR_DTYPE)
+    sonar["px"], sonar["py"], sonar["pa"] = 0.15 * np.cos(ring), 0.15 * np.sin(ring), ring
+    sonar["size_z"], sonar["range_max"], sonar["fov"], sonar["n_samples"] = 0.04, 5.0, 0.26, 1
+    mixed = np.zeros(4, rt.RANGER_SENSOR_DTYPE)
+    mixed["px"], mixed["py"], mixed["pa"] = [0.1, 0.0, -0.1, 0.05], [0.0, 0.1, 0.0, -0.1], [0.0, 1.5, 3.0, -1.5]
+    mixed["pz"], mixed["size_z"], mixed["range_max"] = 0.2, 0.1, [8.0, 5.0, 5.0, 2.0]
+    mixed["fov"], mixed["n_samples"] = [np.pi, 0.26, 0.5, 0.26], [180, 1, 7, 1]
+    for sensors in (sonar, mixed):
+        n_beams = int(sensors["n_samples"].sum()) * len(poses)
+        a = rt.Outputs(n_beams, rt.WANT_RANGES | rt.WANT_INTENSITIES | rt.WANT_BEARINGS | rt.WANT_HIT_MODEL)
+        ctx.rangers_submit(sensors, poses, a)
+        ctx.sync()
+        b = ctx.trace(host_ranger_fans(sensors, poses), want=rt.WANT_RANGES | rt.WANT_INTENSITIES | rt.WANT_BEARINGS | rt.WANT_HIT_MODEL)
+        assert np.array_equal(a.ranges.view(np.uint64), b.ranges.view(np.uint64)) and np.array_equal(a.hit_model, b.hit_model)
+        assert np.array_equal(a.intensities, b.intensities) and np.array_equal(a.bearings.view(np.uint64), b.bearings.view(np.uint64))
+        assert (a.hit_model >= 0).mean() > 0.3
     ctx.close()
