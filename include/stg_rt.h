@@ -238,6 +238,13 @@ typedef struct {
 int stg_rt_fiducials_submit(stg_rt_ctx *ctx, uint32_t n_targets, const stg_rt_fid_target *targets,
                             uint32_t n_finders, const stg_rt_fid_finder *finders,
                             uint32_t max_per_finder, stg_rt_fiducial *out, uint32_t *out_count);
+/* The same with the records handed over packed: out[] holds finder 0's min(out_count[0], max_per_finder)
+   records, then finder 1's, ... (a caller that walks the finders in order needs no stride, and at
+   100,000 finders the strided array is 845 MB of mostly nothing). out_capacity = records out[] can
+   hold; what does not fit is dropped from the end (the counts still tell). */
+int stg_rt_fiducials_submit_packed(stg_rt_ctx *ctx, uint32_t n_targets, const stg_rt_fid_target *targets,
+                                   uint32_t n_finders, const stg_rt_fid_finder *finders, uint32_t max_per_finder,
+                                   uint64_t out_capacity, stg_rt_fiducial *out, uint32_t *out_count);
 
 /* ---- whole ranger models ---------------------------------------------------------------------- */
 

@@ -153,6 +153,7 @@ struct stg_rt_ctx {
     size_t out_bytes = 0, count_bytes = 0;
     bool pending = false;
     uint32_t n_finders = 0, max_per_finder = 0; // fiducials: to unpack the packed records
+    uint64_t packed_capacity = 0;               // ... or, non-zero, to hand them over packed
   } fid_job, blob_job;
   DevBuf d_fid_grid, d_fid_in, d_fid_out, d_fid_count, d_fid_off, d_blob_in, d_blob_out, d_blob_count, d_mdl_color;
   PinBuf h_fid_in, h_fid_out, h_fid_count, h_blob_in, h_blob_out, h_blob_count;
@@ -625,19 +626,28 @@ int deliver_post_locked(stg_rt_ctx *c)
     c->col_job.pending = false;
   }
   if (c->fid_job.pending) { // unpack: finder f's records follow finder f-1's in the staging buffer
+    const double t_prof = prof_now(c);
     const uint32_t *cnt = (const uint32_t *)c->h_fid_count.p;
     const FiducialRec *packed = (const FiducialRec *)c->h_fid_out.p;
     FiducialRec *user = (FiducialRec *)c->fid_job.user_out;
     size_t at = 0;
-    for (uint32_t f = 0; f < c->fid_job.n_finders; f++) {
-      const uint32_t k = std::min(cnt[f], c->fid_job.max_per_finder);
-      if (k)
-        memcpy(user + (size_t)f * c->fid_job.max_per_finder, packed + at, (size_t)k * sizeof(FiducialRec));
-      at += k;
+    if (c->fid_job.packed_capacity) { // the caller takes them as they are: finder f's records follow finder f-1's
+      for (uint32_t f = 0; f < c->fid_job.n_finders; f++)
+        at += std::min(cnt[f], c->fid_job.max_per_finder);
+      memcpy(user, packed, std::min<size_t>(at, c->fid_job.packed_capacity) * sizeof(FiducialRec));
+    } else {
+      for (uint32_t f = 0; f < c->fid_job.n_finders; f++) {
+        const uint32_t k = std::min(cnt[f], c->fid_job.max_per_finder);
+        if (k)
+          memcpy(user + (size_t)f * c->fid_job.max_per_finder, packed + at, (size_t)k * sizeof(FiducialRec));
+        at += k;
+      }
     }
     memcpy(c->fid_job.user_count, cnt, (size_t)c->fid_job.n_finders * 4);
     c->stats.d2h_bytes += at * sizeof(FiducialRec) + (size_t)c->fid_job.n_finders * 4;
     c->fid_job.pending = false;
+    if (c->prof_on)
+      c->prof_us[7] += prof_now(c) - t_prof;
   }
   if (c->blob_job.pending) {
     memcpy(c->blob_job.user_out, c->h_blob_out.p, c->blob_job.out_bytes);
@@ -948,9 +958,9 @@ int stg_rt_destroy(stg_rt_ctx *c)
   cudaStreamSynchronize(c->stream);
   if (c->prof_on)
     fprintf(stderr, "stg_rt host profile, total us (%llu fan launches): stage fans + headings %.0f | sort units %.0f | size deltas %.0f | "
-                    "write deltas %.0f | upload + K1 launches %.0f | march launch %.0f | blocks_remap calls %.0f\n",
+                    "write deltas %.0f | upload + K1 launches %.0f | march launch %.0f | blocks_remap calls %.0f | fiducial unpack %.0f\n",
             (unsigned long long)c->prof_flushes, c->prof_us[0], c->prof_us[1], c->prof_us[2], c->prof_us[3], c->prof_us[4],
-            c->prof_us[5], c->prof_us[6]);
+            c->prof_us[5], c->prof_us[6], c->prof_us[7]);
   GridView &g = c->g;
   void *dev[] = { g.reg_count, g.occ[0], g.slots[0], g.slots[1], g.blk_rec[0], g.blk_rec[1], c->spare_slots,
                   g.mdl_root, g.mdl_ranger_return, g.mdl_flags, c->d_blob.p };
@@ -1619,8 +1629,28 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_r
 
 // ---- sensor post-processing: fiducial finders and blobfinders ---------------------------------------
 
+static int fiducials_submit_impl(stg_rt_ctx *c, uint32_t n_targets, const stg_rt_fid_target *targets, uint32_t n_finders,
+                                 const stg_rt_fid_finder *finders, uint32_t max_per_finder, stg_rt_fiducial *out, uint32_t *out_count,
+                                 uint64_t packed_capacity);
+
 int stg_rt_fiducials_submit(stg_rt_ctx *c, uint32_t n_targets, const stg_rt_fid_target *targets, uint32_t n_finders,
                             const stg_rt_fid_finder *finders, uint32_t max_per_finder, stg_rt_fiducial *out, uint32_t *out_count)
+{
+  return fiducials_submit_impl(c, n_targets, targets, n_finders, finders, max_per_finder, out, out_count, 0);
+}
+
+int stg_rt_fiducials_submit_packed(stg_rt_ctx *c, uint32_t n_targets, const stg_rt_fid_target *targets, uint32_t n_finders,
+                                   const stg_rt_fid_finder *finders, uint32_t max_per_finder, uint64_t out_capacity, stg_rt_fiducial *out,
+                                   uint32_t *out_count)
+{
+  if (!out_capacity)
+    return STG_RT_EINVAL;
+  return fiducials_submit_impl(c, n_targets, targets, n_finders, finders, max_per_finder, out, out_count, out_capacity);
+}
+
+static int fiducials_submit_impl(stg_rt_ctx *c, uint32_t n_targets, const stg_rt_fid_target *targets, uint32_t n_finders,
+                                 const stg_rt_fid_finder *finders, uint32_t max_per_finder, stg_rt_fiducial *out, uint32_t *out_count,
+                                 uint64_t packed_capacity)
 {
   static_assert(sizeof(stg_rt_fid_target) == sizeof(FidTargetRec) && sizeof(stg_rt_fid_finder) == sizeof(FidFinderRec) &&
                     sizeof(stg_rt_fiducial) == sizeof(FiducialRec), "fiducial record layouts");
@@ -1727,6 +1757,7 @@ int stg_rt_fiducials_submit(stg_rt_ctx *c, uint32_t n_targets, const stg_rt_fid_
   c->fid_job.user_count = out_count;
   c->fid_job.n_finders = n_finders;
   c->fid_job.max_per_finder = max_per_finder;
+  c->fid_job.packed_capacity = packed_capacity;
   c->fid_job.pending = true;
   return STG_RT_OK;
 }

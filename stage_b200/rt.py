@@ -94,6 +94,7 @@ def lib():
         "stg_rt_blocks_remap": (ctypes.c_int, [vp, u32, vp, vp, ctypes.c_int, vp, vp, vp]),
         "stg_rt_fans_submit": (ctypes.c_int, [vp, u32, vp, vp, vp, ctypes.POINTER(FanOut)]),
         "stg_rt_fiducials_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
+        "stg_rt_fiducials_submit_packed": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, u64, vp, vp]),
         "stg_rt_blobs_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
         "stg_rt_rangers_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, ctypes.POINTER(FanOut)]),
         "stg_rt_collisions_test": (ctypes.c_int, [vp, ctypes.c_int, u32, vp, vp, u32, vp]),
@@ -132,7 +133,7 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "stg_rt_abi_version stg_rt_create stg_rt_destroy stg_rt_last_error stg_rt_model_upsert stg_rt_block_map "
-    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_rangers_submit stg_rt_collisions_test stg_rt_models_move stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
+    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_fiducials_submit_packed stg_rt_rangers_submit stg_rt_collisions_test stg_rt_models_move stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
     "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_debug_trig stg_rt_debug_headings").split()
@@ -300,6 +301,16 @@ class Context:
         self._check(self._L.stg_rt_models_move(self._h, layer, len(movers), _ptr(first), _ptr(blocks), _ptr(z), _ptr(fp), _ptr(xy),
                                                _ptr(zs), _ptr(fps), _ptr(xys), _ptr(stalled)))
         return stalled
+
+    def fiducials_submit_packed(self, targets, finders, max_per_finder, capacity, into=None):
+        """-> (records[capacity] packed finder after finder, count[n_finders]); valid after sync()."""
+        targets = np.ascontiguousarray(targets, FID_TARGET_DTYPE)
+        finders = np.ascontiguousarray(finders, FID_FINDER_DTYPE)
+        out, cnt = into if into is not None else (np.zeros(capacity, FIDUCIAL_DTYPE), np.zeros(len(finders), np.uint32))
+        self._keep.append((out, cnt))
+        self._check(self._L.stg_rt_fiducials_submit_packed(self._h, len(targets), _ptr(targets), len(finders), _ptr(finders),
+                                                           max_per_finder, capacity, _ptr(out), _ptr(cnt)))
+        return out, cnt
 
     def blobs_submit(self, finders, colors_rgb=None, max_per_finder=None):
         """-> (out[n_finders, max_per_finder] of BLOB_DTYPE, count[n_finders]); valid after sync()."""

@@ -217,6 +217,18 @@ def test_fiducial_query_at_config4_scale_timing():
           "(submit call %.1f ms; only the %.0f MB of records cross PCIe, packed)"
           % (seen, cnt.max(), 1e3 * dt, 1e3 * (t1s - t0), seen * 88 / 1e6))
     assert seen > 100000 and cnt.max() <= 96
+    # packed hand-over: the same records, finder after finder
+    pk, pc = ctx.fiducials_submit_packed(targets, finders, 96, 1 << 20)
+    ctx.sync()
+    t0 = time.perf_counter()
+    ctx.fiducials_submit_packed(targets, finders, 96, 1 << 20, into=(pk, pc))
+    ctx.sync()
+    dt_packed = time.perf_counter() - t0
+    assert np.array_equal(pc, cnt)
+    at = np.concatenate([[0], np.cumsum(pc.astype(np.int64))]).astype(np.int64)
+    for f in list(range(0, n, 997)) + [n - 1]:
+        assert np.array_equal(pk[int(at[f]):int(at[f + 1])].view(np.uint8), out[f, :int(cnt[f])].view(np.uint8))
+    print("  packed hand-over (stg_rt_fiducials_submit_packed): %.1f ms end to end" % (1e3 * dt_packed))
     L = oracle_lib.t1()
     L.t1_fiducial_update.restype = ctypes.c_uint32
     L.t1_fiducial_update.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
