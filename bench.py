@@ -193,28 +193,46 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "the reference arm runs BASELINE config 3 only (--workload c3)"}))
         return 0
     world = make_workload(args, n_gpus)
-    fans = worldgen.ranger_fans(world, layer=1, fov_deg=FOV_DEG, samples=SAMPLES, range_max=RANGE_MAX)
     threads = args.cpu_threads or os.cpu_count()
     ref, _ = reference_world(world)
     if ref is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built on this box"}))
         return 0
-    rays = host_rays(fans)
-    for _ in range(args.warmup):
-        ref.raytrace(rays, nthreads=threads)
-    t_total = 0.0
-    for _ in range(args.steps):
-        _, secs = ref.raytrace(rays, nthreads=threads)
-        t_total += secs
-    v = len(rays) * args.steps / t_total
+    # The same ticks as this repo's e2e arm: every robot takes its next pose (what ModelPosition::Move does to the grid:
+    # UnMapWithChildren + MapWithChildren on the tick's layer, one robot after the other on one thread, as
+    # World::Update runs its movers, world.cc:647-648), then every laser scans from the new pose (World::Raytrace,
+    # split over all host threads). Poses and rays are prepared outside the timed region, like the e2e arm's.
+    n_ticks = args.warmup + args.steps
+    poses = [world.robots]
+    for t in range(n_ticks):
+        poses.append(worldgen.step_robots(world, poses[-1], t))
+    ticks = []
+    for t in range(1, n_ticks + 1):
+        p = poses[t]
+        fans = worldgen.ranger_fans(world, layer=(t + 1) % 2, fov_deg=FOV_DEG, samples=SAMPLES, range_max=RANGE_MAX, robots=p)
+        xyza = np.stack([p[:, 0], p[:, 1], np.zeros(len(p)), np.array([worldgen.heading_rad(d) for d in p[:, 2]])], 1)
+        ticks.append((t % 2, xyza, host_rays(fans)))
+    t_move = t_rays = 0.0
+    n_rays = len(ticks[0][2])
+    for k, (layer, xyza, rays) in enumerate(ticks):
+        s_move = ref.models_remap(world.robot_ids, xyza, layer)
+        _, s_rays = ref.raytrace(rays, nthreads=threads)
+        if k >= args.warmup:
+            t_move += s_move
+            t_rays += s_rays
+    t_total = t_move + t_rays
+    v = n_rays * args.steps / t_total
     line = {
         "impl": "reference", "metric": "rays/sec", "value": v, "unit": "rays/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "ticks_per_s": args.steps / t_total,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, n_gpus),
         "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": "reference",
-                         "sample": "every step = all %d rays of one tick through the unmodified reference's "
-                                   "World::Raytrace (oracle/_ref), split over %d host threads" % (len(rays), threads)},
+                         "sample": "every step = one tick of the workload through the unmodified reference (oracle/_ref): %d robots "
+                                   "re-rendered at their next pose (UnMapWithChildren + MapWithChildren, serial as in World::Update), "
+                                   "then all %d rays through World::Raytrace split over %d host threads" % (len(world.robots), n_rays, threads)},
+        "tick_split_ms": {"moves_1_thread": 1e3 * t_move / args.steps, "rays_%d_threads" % threads: 1e3 * t_rays / args.steps},
+        "rays_only_value": n_rays * args.steps / t_rays,
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -416,7 +434,8 @@ def run_ours(args):
             one = res["ref"].raytrace(res["rays_arr"][:SAMPLES * 50], nthreads=1)[1]
             cpu = {"value": res["rays_per_s"], "unit": "rays/s", "cores": threads, "kind": "reference",
                    "sample": "all %d rays of one tick (static robots), best of 3, unmodified reference "
-                             "World::Raytrace via oracle/_ref on %d threads; 1 thread: %.3g rays/s"
+                             "World::Raytrace via oracle/_ref on %d threads; 1 thread: %.3g rays/s. Rays only: "
+                             "`--impl reference` times whole ticks (the robots' re-rendering too, as `e2e` does)"
                              % (res["rays"], threads, SAMPLES * 50 / one)}
             # Parity of this very workload with the reference's answers. Which of two overlapping
             # bodies a ray reports depends on the order the reference mapped them in while loading

@@ -621,6 +621,28 @@ int ref_model_subscribe(void *wv, const char *name)
   return 0;
 }
 
+// What ModelPosition::Move does to the grid for one mover that hits nothing (model_position.cc:541-552): take the
+// new pose, UnMapWithChildren(layer), MapWithChildren(layer) - for n models, one after the other on the calling
+// thread, as World::Update runs its movers (world.cc:647-648). Returns the seconds it took. The models need not be
+// position models (the benchmark's robots are plain models with a body). Built with -fno-access-control.
+double ref_models_remap(void *wv, uint32_t n, const uint32_t *ids, const double *xyza, int layer)
+{
+  (void)wv;
+  tl_quiet++;
+  auto t0 = std::chrono::steady_clock::now();
+  for (uint32_t i = 0; i < n; i++) {
+    Model *m = Model::LookupId(ids[i]);
+    if (!m)
+      continue;
+    m->pose = Pose(xyza[4 * i], xyza[4 * i + 1], xyza[4 * i + 2], xyza[4 * i + 3]);
+    m->UnMapWithChildren((unsigned int)layer);
+    m->MapWithChildren((unsigned int)layer);
+  }
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  tl_quiet--;
+  return secs;
+}
+
 // ModelPosition::SetSpeed (model_position.cc:595): what a controller does to drive a robot.
 int ref_model_set_speed(void *wv, const char *name, double x, double y, double a)
 {
