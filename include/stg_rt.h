@@ -40,7 +40,7 @@ enum {
   STG_RT_ECUDA = -2,    /* CUDA runtime error (text in stg_rt_last_error) */
   STG_RT_ENOMEM = -3,   /* a fixed-capacity table is full (models, blocks, cell entries) */
   STG_RT_EEXTENT = -4,  /* a polygon leaves the device grid extent given at create */
-  STG_RT_ESTATE = -5,   /* call not valid in the current state (e.g. map of a mapped block) */
+  STG_RT_ESTATE = -5,   /* call not valid in the current state */
   STG_RT_ENODEV = -6    /* no usable CUDA device */
 };
 
@@ -148,8 +148,10 @@ int stg_rt_model_upsert(stg_rt_ctx *ctx, uint32_t id, uint32_t root_id, double r
 
 /* Block::Map(layer), block.cc:170-181: xy = the n_pts pixel-space vertices Model::LocalToPixels
    produced (model.cc:474-491), i.e. the argument of World::MapPoly (world.cc:990); zmin/zmax =
-   Block::global_z after the call (shared by both layers). The block must not be mapped on that
-   layer (the reference always UnMaps first). */
+   Block::global_z after the call (shared by both layers). Mapping a block that is already mapped
+   on that layer renders it once more on top, as Block::Map does (it does not check; the reference's
+   loader does this to bumper models): duplicate entries in the cells, counted by Region::count,
+   all removed by the next UnMap (region.cc:292-299); the block keeps its place in the cell lists. */
 int stg_rt_block_map(stg_rt_ctx *ctx, uint32_t block_id, uint32_t model_id, int layer, double zmin,
                      double zmax, int n_pts, const int32_t *xy);
 /* Block::UnMap(layer), block.cc:183-189. Unmapping an unmapped block is a no-op, as there. */

@@ -37,6 +37,12 @@ struct BlockShadow {
   bool host_mapped[2] = { false, false }, dev_mapped[2] = { false, false }, dirty[2] = { false, false };
   uint32_t map_seq[2] = { 0, 0 };
   std::vector<int32_t> host_xy[2], dev_xy[2];
+  // Block::Map on a block that is already mapped renders it once more (block.cc:170-181 does not check; the
+  // reference's world loader does it to bumper models): the cells get duplicate entries, Region::count counts them,
+  // UnMap removes them all. Then the outline is several polygons back to back and these hold the points of each
+  // (empty = one polygon, the normal case).
+  std::vector<uint32_t> host_poly[2], dev_poly[2];
+  bool keep_seq[2] = { false, false }; // re-map of a block the device already holds: its place in the cell lists stays
 };
 
 struct Submit {
@@ -309,11 +315,8 @@ int ensure_table_room(stg_rt_ctx *c, const int64_t add[2])
 // apply == false (multi-GPU export): exactly one blob, uploaded to d_blob, not applied.
 // Write the edge records of one outline straight into the blob. Zero-length edges are kept (they
 // own no step, so the kernels' edge search never lands on them).
-static inline uint32_t emit_edges(const std::vector<int32_t> &xy, uint32_t block, uint32_t layer, uint32_t &step_cursor,
-                                  EdgeRec *&dst)
+static inline uint32_t emit_polygon(const int32_t *p, size_t n, uint32_t block, uint32_t layer, uint32_t &step_cursor, EdgeRec *&dst)
 {
-  const size_t n = xy.size() / 2;
-  const int32_t *p = xy.data();
   uint32_t steps = 0;
   for (size_t i = 0; i < n; i++) {
     const size_t j = i + 1 == n ? 0 : i + 1;
@@ -330,6 +333,20 @@ static inline uint32_t emit_edges(const std::vector<int32_t> &xy, uint32_t block
     e.first_step = step_cursor;
     step_cursor += e.n_steps;
     steps += e.n_steps;
+  }
+  return steps;
+}
+
+static inline uint32_t emit_edges(const std::vector<int32_t> &xy, uint32_t block, uint32_t layer, uint32_t &step_cursor,
+                                  EdgeRec *&dst, const std::vector<uint32_t> *polys = nullptr)
+{
+  if (!polys || polys->empty())
+    return emit_polygon(xy.data(), xy.size() / 2, block, layer, step_cursor, dst);
+  uint32_t steps = 0;
+  size_t at = 0;
+  for (uint32_t n : *polys) { // a block rendered more than once: every rendering is a closed outline of its own
+    steps += emit_polygon(xy.data() + 2 * at, n, block, layer, step_cursor, dst);
+    at += n;
   }
   return steps;
 }
@@ -421,9 +438,9 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
       BlockShadow &b = c->blocks[u >> 1];
       const int L = u & 1;
       if (b.dev_mapped[L])
-        d_live[L] -= emit_edges(b.dev_xy[L], u >> 1, L, rem_cursor, rem);
+        d_live[L] -= emit_edges(b.dev_xy[L], u >> 1, L, rem_cursor, rem, &b.dev_poly[L]);
       if (b.host_mapped[L]) {
-        const uint32_t st = emit_edges(b.host_xy[L], u >> 1, L, ins_cursor, ins);
+        const uint32_t st = emit_edges(b.host_xy[L], u >> 1, L, ins_cursor, ins, &b.host_poly[L]);
         d_live[L] += st;
         ins_round[L] += st;
         BlockUpd &up = *bupd++;
@@ -432,12 +449,15 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
         up.zmin = b.zmin;
         up.zmax = b.zmax;
         up.seq_local = b.map_seq[L];
-        up.layer = (uint32_t)L;
+        up.layer = (uint32_t)L | (b.keep_seq[L] ? kUpdKeepSeq : 0u);
         up.root_flags = root_flags_of(c, b.model);
         up.pad = 0;
+        b.keep_seq[L] = false;
         b.dev_xy[L].swap(b.host_xy[L]); // host_xy is rewritten by the next Map before it is read again
+        b.dev_poly[L].swap(b.host_poly[L]);
       } else {
         b.dev_xy[L].clear();
+        b.dev_poly[L].clear();
       }
       b.dev_mapped[L] = b.host_mapped[L];
       b.dirty[L] = false;
@@ -1089,8 +1109,6 @@ static int block_map_locked(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id,
   if (model_id >= c->cfg.max_models || !c->model_known[model_id])
     return fail(c, STG_RT_EINVAL, "block_map: unknown model %u (call stg_rt_model_upsert first)", model_id);
   BlockShadow &b = c->blocks[block_id];
-  if (b.host_mapped[layer])
-    return fail(c, STG_RT_ESTATE, "block %u is already mapped on layer %d (Block::UnMap first, block.cc:183)", block_id, layer);
   for (int i = 0; i < n_pts; i++)
     if (xy[2 * i] < c->cell_x0 || xy[2 * i] > c->cell_x1 || xy[2 * i + 1] < c->cell_y0 || xy[2 * i + 1] > c->cell_y1)
       return fail(c, STG_RT_EEXTENT, "block %u vertex (%d,%d) outside the device grid [%d..%d]x[%d..%d]", block_id, xy[2 * i],
@@ -1104,9 +1122,26 @@ static int block_map_locked(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id,
   b.model = model_id;
   b.zmin = zmin;
   b.zmax = zmax;
-  b.host_mapped[layer] = true;
-  b.host_xy[layer].assign(xy, xy + 2 * (size_t)n_pts);
-  b.map_seq[layer] = ++c->local_seq;
+  if (b.host_mapped[layer]) {
+    // Map on a mapped block (see BlockShadow): one more rendering on top of what is there; the block keeps the
+    // place in the cell lists its first rendering gave it
+    if (!b.dirty[layer]) { // the device holds the current outline; host_xy is scratch since the last flush
+      b.host_xy[layer] = b.dev_xy[layer];
+      b.host_poly[layer] = b.dev_poly[layer];
+      b.keep_seq[layer] = true;
+    }
+    if (b.host_poly[layer].empty())
+      b.host_poly[layer].push_back((uint32_t)(b.host_xy[layer].size() / 2));
+    b.host_poly[layer].push_back((uint32_t)n_pts);
+    b.host_xy[layer].insert(b.host_xy[layer].end(), xy, xy + 2 * (size_t)n_pts);
+    c->local_seq++;
+  } else {
+    b.host_mapped[layer] = true;
+    b.host_xy[layer].assign(xy, xy + 2 * (size_t)n_pts);
+    b.host_poly[layer].clear();
+    b.keep_seq[layer] = false;
+    b.map_seq[layer] = ++c->local_seq;
+  }
   touch_unit(c, block_id, layer);
   c->stats.map_calls++;
   return STG_RT_OK;
@@ -1128,6 +1163,8 @@ static int block_unmap_locked(stg_rt_ctx *c, uint32_t block_id, int layer)
   }
   b.host_mapped[layer] = false;
   b.host_xy[layer].clear();
+  b.host_poly[layer].clear();
+  b.keep_seq[layer] = false;
   touch_unit(c, block_id, layer);
   c->stats.unmap_calls++;
   return STG_RT_OK;
@@ -1807,7 +1844,7 @@ int stg_rt_collisions_test(stg_rt_ctx *c, int layer, uint32_t n_queries, const u
         break;
       }
       if (b.dev_mapped[layer]) // after the flush dev_xy is the outline rendered on the device
-        emit_edges(b.dev_xy[layer], blocks[i], (uint32_t)layer, cursor, e);
+        emit_edges(b.dev_xy[layer], blocks[i], (uint32_t)layer, cursor, e, &b.dev_poly[layer]);
     }
     qr[q].n_edges = (uint32_t)(e - e0) - qr[q].first_edge;
     qr[q].n_steps = cursor;

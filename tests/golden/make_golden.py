@@ -8,6 +8,10 @@ Each trace records every Block::Map / Block::UnMap / World::Raytrace / ModelRang
 ModelFiducial::Update / ModelBlobfinder::Update / Model::TestCollision the reference performed
 (format: oracle/trace_format.h), compressed with xz.
 
+everything_40 is worlds/everything.world (hospital section bitmap, pioneers with 16 sonars, SICK lasers, fiducial
+finders, a gripper, bumpers and a blobfinder, all `alwayson`) minus its one `camera(...)` line: the camera model
+needs OpenGL and is not part of the headless build (oracle/build_ref.sh).
+
 bumper_150 is not one of the reference's shipped worlds: none of those makes robots collide within
 a few hundred ticks, so Model::TestCollision would only ever be seen answering "nothing". It is a
 walled arena with a rotated pillar, a bridge the robots fit under (z separation), a model without
@@ -79,10 +83,34 @@ sys.stdout.flush()
 os._exit(0)
 """
 
+def everything_world_text():
+    sys.path.insert(0, TESTS)
+    import oracle_lib
+    src = open(os.path.join(oracle_lib.REF, "worlds", "everything.world")).read()
+    return "\n".join(line for line in src.split("\n") if not line.strip().startswith("camera(")) + "\n"
+
+
+TEXT_CHILD = r"""
+import sys, os
+sys.path.insert(0, %r)
+import oracle_lib
+w = oracle_lib.RefWorld(text=open(sys.argv[1]).read(), path_hint=os.path.join(oracle_lib.REF, "worlds", "generated.world"))
+w.update(int(sys.argv[2]))
+w.trace_end(sys.argv[3])
+sys.stdout.flush()
+os._exit(0)
+"""
+
 if __name__ == "__main__":
-    for world, ticks, name in WORLDS + [("bumper", 150, "bumper_150")]:
+    for world, ticks, name in WORLDS + [("everything", 40, "everything_40"), ("bumper", 150, "bumper_150")]:
         raw = os.path.join(HERE, name + ".trc")
-        if world == "bumper":
+        if world == "everything":
+            wf = os.path.join(HERE, "everything.world.tmp")
+            with open(wf, "w") as f:
+                f.write(everything_world_text())
+            subprocess.run([sys.executable, "-c", TEXT_CHILD % TESTS, wf, str(ticks), raw], check=True, stdout=subprocess.DEVNULL)
+            os.remove(wf)
+        elif world == "bumper":
             wf = os.path.join(HERE, "bumper.world.tmp")
             with open(wf, "w") as f:
                 f.write(bumper_world_text())

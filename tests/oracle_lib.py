@@ -97,6 +97,29 @@ def sort_grid(rec):
     return rec[idx]
 
 
+def first_occurrences(rec):
+    """{layer,x,y,pos,block} records with the later copies of a block in a cell dropped and the positions renumbered:
+    what decides which block a ray meets first when a block was rendered more than once (Map on a mapped block)"""
+    rec = sort_grid(rec)
+    out, seen, cell, pos = [], set(), None, 0
+    for r in rec:
+        key = (r[0], r[1], r[2])
+        if key != cell:
+            cell, seen, pos = key, set(), 0
+        if r[4] in seen:
+            continue
+        seen.add(r[4])
+        out.append((r[0], r[1], r[2], pos, r[4]))
+        pos += 1
+    return np.array(out, np.int32).reshape(-1, 5)
+
+
+def entry_multiset(rec):
+    """the (layer, x, y, block) entries, duplicates included, in canonical order"""
+    e = rec[:, [0, 1, 2, 4]]
+    return e[np.lexsort((e[:, 3], e[:, 1], e[:, 2], e[:, 0]))]
+
+
 def sort_counts(cnt):
     if len(cnt) == 0:
         return cnt
@@ -208,7 +231,7 @@ def ref():
 class RefWorld:
     """A live World of the unmodified reference. Never destroyed (the reference's ~World crashes)."""
 
-    def __init__(self, path=None, text=None, record=True, fiducials_on_main_thread=True):
+    def __init__(self, path=None, text=None, record=True, fiducials_on_main_thread=True, path_hint="synthetic.world"):
         self.L = ref()
         # on worker threads fiducial updates race with Move() (SURVEY.md 3.1): not reproducible
         self.L.ref_fiducials_on_main_thread(1 if fiducials_on_main_thread else 0)
@@ -217,7 +240,8 @@ class RefWorld:
         if path is not None:
             self.h = self.L.ref_world_load_file(str(path).encode())
         else:
-            self.h = self.L.ref_world_load_text(text.encode(), b"synthetic.world")
+            # path_hint: where the text pretends to live (its includes and bitmaps are looked up next to it)
+            self.h = self.L.ref_world_load_text(text.encode(), str(path_hint).encode())
         if not self.h:
             raise RuntimeError("reference failed to load the world")
 

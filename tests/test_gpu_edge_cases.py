@@ -143,6 +143,44 @@ def test_multi_block_cells_order_ztest_predicates_and_attribute_changes():
     p.ctx.close()
 
 
+def test_map_on_a_mapped_block_renders_it_again():
+    """Block::Map does not check whether the block is mapped (block.cc:170-181); the reference's loader maps bumper
+    models twice (tests/golden/everything_40). The cells then list the block twice, Region::count counts both, one
+    UnMap removes everything - whether the second Map comes in the same flush window or after the device already
+    holds the block. The block keeps the place its first rendering has in the cell lists (what a ray meets first)."""
+    p = Pair()
+    for m in (1, 2, 3):
+        p.model(m, m)
+
+    def same_grid():
+        rec_g, cnt_g = p.ctx.grid_dump()
+        rec_o, cnt_o = p.t1.dump_grid()
+        assert np.array_equal(oracle_lib.entry_multiset(rec_g), oracle_lib.entry_multiset(rec_o))   # copies included
+        assert np.array_equal(oracle_lib.first_occurrences(rec_g), oracle_lib.first_occurrences(rec_o))
+        assert np.array_equal(oracle_lib.sort_counts(cnt_g), cnt_o)
+    p.map(0, 1, 0, (0.0, 1.0), box(10, 10, 30, 30))
+    p.map(0, 1, 0, (0.0, 1.0), box(10, 10, 30, 30))            # again, in the same flush window
+    p.map(1, 2, 0, (0.0, 1.0), box(20, 20, 40, 40))
+    same_grid()
+    p.map(2, 3, 0, (0.0, 1.0), box(25, 5, 35, 45))
+    p.map(1, 2, 0, (0.0, 1.0), box(20, 20, 40, 40))            # again, after the device already holds it and block 2 came
+    same_grid()
+    heads = np.linspace(-np.pi, np.pi, 500)
+    for finder in (1, 2, 3):
+        p.rays(finder, [0.5, 0.52], heads, 3.0, layer=0)
+    p.unmap(1, 0)
+    same_grid()
+    p.map(1, 2, 0, (0.0, 1.0), box(20, 20, 40, 40))            # mapped afresh: now it comes after block 2
+    same_grid()
+    for finder in (1, 2, 3):
+        p.rays(finder, [0.5, 0.52], heads, 3.0, layer=0)
+    p.unmap(0, 0)
+    p.unmap(2, 0)
+    p.unmap(1, 0)
+    same_grid()
+    p.ctx.close()
+
+
 def test_api_errors_and_empty_calls():
     p = Pair()
     p.model(1, 1)
@@ -150,9 +188,6 @@ def test_api_errors_and_empty_calls():
         p.ctx.block_map(0, 9, 0, 0, 1, box(0, 0, 5, 5))          # unknown model
     assert e.value.code == -1
     p.ctx.block_map(0, 1, 0, 0, 1, box(0, 0, 5, 5))
-    with pytest.raises(rt.StgRtError) as e:
-        p.ctx.block_map(0, 1, 0, 0, 1, box(0, 0, 5, 5))          # already mapped on this layer
-    assert e.value.code == -5
     with pytest.raises(rt.StgRtError) as e:
         p.ctx.block_map(1, 1, 0, 0, 1, box(0, 0, 5000, 5))       # leaves the extent
     assert e.value.code == -4

@@ -14,7 +14,7 @@ import replay
 import trace_io
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-TRACES = ["simple_120", "fasr_300", "lsp_test_20", "bumper_150"]
+TRACES = ["simple_120", "fasr_300", "lsp_test_20", "everything_40", "bumper_150"]
 
 
 @pytest.fixture(scope="module", params=TRACES)
@@ -45,6 +45,8 @@ def test_t1_reproduces_every_reference_ray(raw_trace):
         assert st["scans"] > 1000 and st["fiducial_updates"] > 1000 and st["collision_tests"] > 5000
     if name == "lsp_test_20":
         assert st["fiducial_updates"] == 40 and st["blob_updates"] == 40
+    if name == "everything_40":  # sonar rings, lasers, fiducial finders, bumpers, a blobfinder on the hospital map
+        assert st["scans"] == 320 and st["fiducial_updates"] == 320 and st["blob_updates"] == 40
 
 
 def test_reference_known_answers_lsp_test():
