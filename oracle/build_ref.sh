@@ -34,7 +34,7 @@ for s in $SRCS ref_stubs; do OBJS="$OBJS $OUT/obj/$s.o"; done
 $CXX -shared -o "$OUT/libstage_ref.so" $OBJS -lpthread -ldl
 # the reference's own front-end and the controllers its shipped worlds name
 $CXX $FLAGS "$REF/libstage/main.cc" -o "$OUT/stage" -L"$OUT" -lstage_ref -Wl,-rpath,'$ORIGIN' -lpthread -ldl
-for c in wander fasr source sink; do
+for c in wander fasr source sink pioneer_flocking lasernoise; do
   $CXX $FLAGS -shared "$REF/examples/ctrl/$c.cc" -o "$OUT/plugins/$c.so" -L"$OUT" -lstage_ref -Wl,-rpath,'$ORIGIN/..'
 done
 cp "$REF/libstage/rgb.txt" "$OUT/share/stage/rgb.txt"

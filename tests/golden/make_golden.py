@@ -27,7 +27,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 TESTS = os.path.dirname(HERE)
 WORLDS = [("simple.world", 120, "simple_120"),     # BASELINE config 1: Pioneer + SICK laser, wander ctrl
           ("fasr.world", 300, "fasr_300"),         # BASELINE config 2: rangers + fiducials, threads 2
-          ("lsp_test.world", 20, "lsp_test_20")]   # the Player-plugin test world: fiducial + blobfinder
+          ("lsp_test.world", 20, "lsp_test_20"),   # the Player-plugin test world: fiducial + blobfinder
+          ("pioneer_flocking.world", 12, "pioneer_flocking_12")]  # 100 pioneers, 8 sonars + fiducial finder each, threads 4
 # lsp_test.world has no controllers: switch its sensors on the way a Player client would
 SUBSCRIBE = {"lsp_test.world": ["r0.fiducial:0", "r1.fiducial:0", "r0.blobfinder:0", "r1.blobfinder:0"]}
 

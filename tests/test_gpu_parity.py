@@ -23,7 +23,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 RANGE_TOL = 1e-5  # metres; BASELINE.json north_star
 
 
-@pytest.fixture(scope="module", params=["simple_120", "fasr_300", "everything_40"])
+@pytest.fixture(scope="module", params=["simple_120", "fasr_300", "everything_40", "pioneer_flocking_12"])
 def trace(request):
     return trace_io.load(os.path.join(GOLDEN, request.param + ".trc.xz"))
 

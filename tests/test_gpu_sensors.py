@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.fixture(scope="module", params=["fasr_300", "lsp_test_20", "everything_40"])
+@pytest.fixture(scope="module", params=["fasr_300", "lsp_test_20", "everything_40", "pioneer_flocking_12"])
 def run(request):
     tr = trace_io.load(os.path.join(GOLDEN, request.param + ".trc.xz"))
     g = replay.GpuReplay(tr, strict=False, want=rt.WANT_RANGES | rt.WANT_HIT_MODEL)
@@ -40,7 +40,7 @@ def test_fiducials_match_the_reference(run):
 
 def test_blobs_match_the_reference(run):
     name, tr, g = run
-    if name == "fasr_300":
+    if name in ("fasr_300", "pioneer_flocking_12"):
         pytest.skip("no blobfinder in this world")
     colors = {int(m["id"]): m["color"][:3] for m in tr.models}
     assert len(g.blobs) == 40

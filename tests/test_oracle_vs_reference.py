@@ -14,7 +14,7 @@ import replay
 import trace_io
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-TRACES = ["simple_120", "fasr_300", "lsp_test_20", "everything_40", "bumper_150"]
+TRACES = ["simple_120", "fasr_300", "lsp_test_20", "everything_40", "pioneer_flocking_12", "bumper_150"]
 
 
 @pytest.fixture(scope="module", params=TRACES)
@@ -32,7 +32,7 @@ def test_t1_reproduces_every_reference_ray(raw_trace):
     if name == "bumper_150":  # no sensors: the Model::TestCollision recording (make_golden.py)
         assert st["collision_tests"] == 2100 and st["collision_hits"] > 1500 and st["collision_mismatch"] == 0, st
         return
-    assert st["rays"] > (30000 if name != "lsp_test_20" else 3000) and st["ticks"] >= 20
+    assert st["rays"] > (30000 if name != "lsp_test_20" else 3000) and st["ticks"] >= (20 if name != "pioneer_flocking_12" else 12)
     assert st["model_mismatch"] == 0 and st["collision_mismatch"] == 0
     # bit-exact on a host with the libm the traces were recorded with; never worse than an ulp or so
     assert st["max_range_err"] <= 1e-12, st
@@ -45,6 +45,8 @@ def test_t1_reproduces_every_reference_ray(raw_trace):
         assert st["scans"] > 1000 and st["fiducial_updates"] > 1000 and st["collision_tests"] > 5000
     if name == "lsp_test_20":
         assert st["fiducial_updates"] == 40 and st["blob_updates"] == 40
+    if name == "pioneer_flocking_12":  # a swarm: 100 robots x (8 one-beam sonars + a fiducial finder), worker threads
+        assert st["scans"] == 9600 and st["fiducial_updates"] == 1200 and st["collision_tests"] > 1000
     if name == "everything_40":  # sonar rings, lasers, fiducial finders, bumpers, a blobfinder on the hospital map
         assert st["scans"] == 320 and st["fiducial_updates"] == 320 and st["blob_updates"] == 40
 
