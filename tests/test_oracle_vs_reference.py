@@ -126,3 +126,39 @@ sys.stdout.flush(); os._exit(0)
     l0 = {tuple(r[1:]) for r in rec0 if r[0] == 0}
     l1 = {tuple(r[1:]) for r in rec0 if r[0] == 1}
     assert l0 != l1
+
+
+LIVE_CHILD = r"""
+import sys, os, ctypes, json
+sys.path.insert(0, %r)
+import oracle_lib
+src = open(os.path.join(oracle_lib.REF, "worlds", sys.argv[1])).read()
+text = "\n".join(line for line in src.split("\n") if not line.strip().startswith("camera("))  # no OpenGL in the headless build
+w = oracle_lib.RefWorld(text=text, path_hint=os.path.join(oracle_lib.REF, "worlds", "live_" + sys.argv[1]))
+w.update(int(sys.argv[2]))
+w.trace_end(sys.argv[3])
+st, _ = oracle_lib.t1_replay(sys.argv[3])
+print("STATS " + json.dumps(st))
+sys.stdout.flush()
+os._exit(0)
+"""
+
+
+@pytest.mark.skipif(not oracle_lib.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("world", ["autolab.world", "SFU.world", "circuit.world", "pioneer_walle.world"])
+def test_more_shipped_worlds_replay_exactly(world, tmp_path):
+    """The reference itself, run here for a few ticks on more of the worlds it ships (swarms of 94 robots with sonar rings
+    and fiducial finders on big bitmaps, worker threads; a laser robot with its wander controller), and every ray, scan,
+    fiducial update and collision test it made replayed through T1: no mismatch."""
+    import json
+    import subprocess
+    import sys
+    tests = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, "-c", LIVE_CHILD % tests, world, "6", str(tmp_path / "live.trc")], capture_output=True,
+                         text=True, timeout=300)
+    line = [ln for ln in out.stdout.split("\n") if ln.startswith("STATS ")]
+    assert line, out.stdout[-2000:] + out.stderr[-2000:]
+    st = json.loads(line[-1][6:])
+    assert st["rays"] > 500 and st["ticks"] == 6
+    for k in ("range_mismatch", "model_mismatch", "scan_mismatch", "fiducial_mismatch", "blob_mismatch", "collision_mismatch"):
+        assert st[k] == 0 or (k in ("range_mismatch", "scan_mismatch") and os.environ.get("STG_FOREIGN_LIBM")), (k, st)
