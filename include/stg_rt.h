@@ -385,6 +385,12 @@ uint64_t stg_rt_set_beams(const stg_rt_set *set);
 int64_t stg_rt_grid_dump(stg_rt_ctx *ctx, int32_t *records, int64_t cap, int64_t *region_counts,
                          int64_t counts_cap, int64_t *n_counts);
 
+/* The region owner tags the march uses to walk through regions that hold nothing but the finder's own
+   tree (no counterpart in the reference: an acceleration that must never change a result; tests check
+   its invariant against the grid). int64[3] {rx, ry, tag} per region with a non-zero tag; tag = root
+   model id + 1, or 0xffffffff for "more than one tree". Returns the record count (may exceed cap). */
+int64_t stg_rt_debug_region_owners(stg_rt_ctx *ctx, int64_t *records, int64_t cap);
+
 /* ---- multi-GPU: moved-block deltas ---------------------------------------------------------- */
 /* Robots are sharded over ranks (one process per GPU), the grid is replicated. Each tick every rank
    serialises the deltas its own robots produced, the ranks all-gather the byte blobs (NCCL over

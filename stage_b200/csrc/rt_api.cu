@@ -93,6 +93,7 @@ struct stg_rt_ctx {
   std::vector<ModelUpd> model_upd;
   std::vector<bool> model_known;
   std::vector<ModelUpd> models;          // host copy of the model table
+  bool block_reassigned = false;         // a known block id was mapped for another model
   std::vector<uint32_t> models_changed;  // models whose root / visibility changed while blocks are mapped
   uint64_t epoch = 0;
   uint32_t local_seq = 0;
@@ -372,6 +373,10 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
   lap(1);
   size_t unit = 0;
   bool first_round = true;
+  // model or attribute updates may move a rendered block to another tree: the region owners are then rebuilt
+  // on the device (which decides whether that really happened, rt_kernels.cu)
+  const bool owners_suspect = !c->model_upd.empty() || !c->models_changed.empty() || c->block_reassigned;
+  c->block_reassigned = false;
   if (out_bytes)
     *out_bytes = 0;
   while (first_round || unit < c->dirty_units.size()) {
@@ -498,6 +503,8 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
         return rc;
       launch_apply_deltas(c->g, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, 1, c->stream,
                           &c->stats.launches_rasterise);
+      if (owners_suspect)
+        launch_owner_rebuild(c->g, c->stream, &c->stats.launches_rasterise);
       CU(c, cudaEventRecord(c->t_ev[0][1], c->stream));
       c->t_rec[0] = true;
       CU(c, cudaGetLastError());
@@ -938,6 +945,9 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
   g.n_models = cfg->max_models;
   CUC(cudaMalloc(&g.reg_count, c->n_regions * 4));
   CUC(cudaMemsetAsync(g.reg_count, 0, c->n_regions * 4, c->stream));
+  g.n_regions = (uint32_t)c->n_regions;
+  CUC(cudaMalloc(&g.reg_owner, (c->n_regions + 1) * 4)); // + the stale flag
+  CUC(cudaMemsetAsync(g.reg_owner, 0, (c->n_regions + 1) * 4, c->stream));
   // both layers' tiles in one allocation: the march addresses them with one 32-bit word index
   CUC(cudaMalloc(&g.occ[0], 2 * c->n_regions * kTileWords * 4));
   CUC(cudaMemsetAsync(g.occ[0], 0, 2 * c->n_regions * kTileWords * 4, c->stream));
@@ -982,7 +992,7 @@ int stg_rt_destroy(stg_rt_ctx *c)
             (unsigned long long)c->prof_flushes, c->prof_us[0], c->prof_us[1], c->prof_us[2], c->prof_us[3], c->prof_us[4],
             c->prof_us[5], c->prof_us[6], c->prof_us[7]);
   GridView &g = c->g;
-  void *dev[] = { g.reg_count, g.occ[0], g.slots[0], g.slots[1], g.blk_rec[0], g.blk_rec[1], c->spare_slots,
+  void *dev[] = { g.reg_count, g.reg_owner, g.occ[0], g.slots[0], g.slots[1], g.blk_rec[0], g.blk_rec[1], c->spare_slots,
                   g.mdl_root, g.mdl_ranger_return, g.mdl_flags, c->d_blob.p };
   for (void *p : dev)
     if (p)
@@ -1118,6 +1128,8 @@ static int block_map_locked(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id,
     if (rc)
       return rc;
   }
+  if (b.known && b.model != model_id)
+    c->block_reassigned = true; // what is still rendered of it on the other layer changes owner too
   b.known = true;
   b.model = model_id;
   b.zmin = zmin;
@@ -1592,6 +1604,33 @@ int64_t stg_rt_grid_dump(stg_rt_ctx *c, int32_t *records, int64_t cap, int64_t *
   return n;
 }
 
+int64_t stg_rt_debug_region_owners(stg_rt_ctx *c, int64_t *records, int64_t cap)
+{
+  if (!c)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = flush_locked(c);
+  if (rc)
+    return rc;
+  if ((rc = deliver_locked(c)))
+    return rc;
+  const GridView &g = c->g;
+  std::vector<uint32_t> owners(c->n_regions);
+  CU(c, cudaMemcpyAsync(owners.data(), g.reg_owner, c->n_regions * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  int64_t n = 0;
+  for (size_t r = 0; r < owners.size(); r++)
+    if (owners[r]) {
+      if (records && n < cap) {
+        records[3 * n] = g.rx0 + (int64_t)(r % (size_t)g.nrx);
+        records[3 * n + 1] = g.ry0 + (int64_t)(r / (size_t)g.nrx);
+        records[3 * n + 2] = owners[r];
+      }
+      n++;
+    }
+  return n;
+}
+
 // ---- multi-GPU deltas ------------------------------------------------------------------------------
 
 size_t stg_rt_delta_slot_bytes(const stg_rt_ctx *c) { return c ? c->blob_cap : 0; }
@@ -1658,6 +1697,7 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_r
     return rc;
   launch_apply_deltas(c->g, (const unsigned char *)dev_gathered, n_ranks, slot_bytes, c->epoch, 1, c->stream,
                       &c->stats.launches_rasterise);
+  launch_owner_rebuild(c->g, c->stream, &c->stats.launches_rasterise); // other ranks' updates are only known there
   CU(c, cudaEventRecord(c->t_ev[0][1], c->stream));
   c->t_rec[0] = true;
   CU(c, cudaGetLastError());

@@ -44,6 +44,14 @@ inline uint32_t slot_home(uint32_t key, uint32_t slot_mask)
 //  reg_count[r]        Region::count (region.cc:19-34): number of (cell, block) entries of BOTH
 //                      layers in region r. r = (gry - ry0) * nrx + (grx - rx0), row-major over the
 //                      dense extent. 4 B / region.
+//  reg_owner[r]        whose entries region r holds, as far as that is one tree: 0 = nothing, root + 1 = every
+//                      entry (both layers) added since the region was last empty belongs to a model of
+//                      the tree with that root, kOwnerMixed = more than one tree (or unknown). A ray
+//                      whose finder belongs to that tree cannot be stopped there by a predicate that
+//                      rejects related models (Model::IsRelated, model.cc:446-466), so the march walks
+//                      such a region without looking at its masks or cells: a robot alone in its
+//                      regions does not look up its own outline. Conservative by construction: any
+//                      doubt is kOwnerMixed, which is the ordinary walk. 4 B / region.
 //  occ[L][r*64 + ..]   occupancy tile of region r, layer L, 256 bytes = two 128-byte lines:
 //                      words 0..31  row masks:    bit cx of word cy      is set iff the cell's block
 //                      words 32..63 column masks: bit cy of word 32 + cx   list Cell::blocks[L]
@@ -73,11 +81,15 @@ constexpr uint32_t kRecNoRanger = 1u << 30; // vis.ranger_return < 0: invisible 
 constexpr uint32_t kRecGripper = 1u << 31;  // vis.gripper_return
 constexpr uint32_t kRecObstacle = 1u << 29; // vis.obstacle_return
 constexpr uint32_t kRecRootMask = (1u << 29) - 1u;
+constexpr uint32_t kOwnerNone = 0u, kOwnerMixed = 0xffffffffu;
+constexpr uint32_t kOwnerNever = 0xfffffffeu; // a finder tag that matches no region
 
 struct GridView {
   int32_t rx0, ry0, nrx, nry;
   double ppm;
   uint32_t *reg_count;
+  uint32_t *reg_owner;   // n_regions words, then one more: the "owners are stale" flag (launch_owner_rebuild)
+  uint32_t n_regions;
   uint32_t *occ[2];
   unsigned long long *slots[2];
   uint32_t slot_mask;
@@ -318,6 +330,7 @@ void launch_debug_trig(uint64_t n, const double *x, double *cs, void *stream);
 // launch wrappers implemented in rt_kernels.cu; all asynchronous on `stream`
 void launch_apply_deltas(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
                          unsigned long long epoch, int phase, void *stream, uint64_t *launch_counter);
+void launch_owner_rebuild(const GridView &g, void *stream, uint64_t *launch_counter);
 void launch_fan_headings(const FanBatchView &b, void *stream);
 void launch_ray_march(const GridView &g, const FanBatchView &b, void *stream);
 

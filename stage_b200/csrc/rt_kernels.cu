@@ -146,6 +146,15 @@ __device__ __forceinline__ void k1_table_updates(const GridView &g, const unsign
     for (uint32_t i = t0; i < v.hdr->n_block_upd; i += stride) {
       const BlockUpd u = v.block_upd[i];
       if (u.block < g.n_blocks) {
+        // A block rendered before this pass changes trees (its model was re-parented, or the id now names a
+        // block of another model): what the region owners say about its cells no longer holds. "Before this
+        // pass" = it carries a sequence number of an earlier epoch; one written by this very launch (the
+        // block's own Map record may be applied by another thread right now) does not count.
+        if ((g.blk_rec[0][u.block].root_flags ^ u.root_flags) & kRecRootMask) {
+          const unsigned long long s0 = g.blk_rec[0][u.block].seq, s1 = g.blk_rec[1][u.block].seq;
+          if ((s0 && (s0 >> 40) != epoch) || (s1 && (s1 >> 40) != epoch))
+            g.reg_owner[g.n_regions] = 1u;
+        }
         for (int L = 0; L < 2; L++) { // z bounds and ownership are per block: both layers see them
           BlockRec *rec = g.blk_rec[L] + u.block;
           rec->zmin = u.zmin;
@@ -186,7 +195,8 @@ __device__ __forceinline__ void k1_remove(const GridView &g, const unsigned char
           atomicCAS(slots + h, entry, kSlotTomb);
         h = (h + 1) & g.slot_mask;
       }
-      atomicSub(g.reg_count + c.region, 1u);
+      if (atomicSub(g.reg_count + c.region, 1u) == 1u) // the region's last entry: it belongs to nobody again
+        g.reg_owner[c.region] = kOwnerNone;
       uint32_t *tile = g.occ[e.layer & 1] + (size_t)c.region * kTileWords;
       atomicAnd(tile + c.cy, ~(1u << c.cx));
       atomicAnd(tile + kRegionWidth + c.cx, ~(1u << c.cy));
@@ -252,6 +262,15 @@ __device__ __forceinline__ void k1_insert(const GridView &g, const unsigned char
         probes++;
       }
       atomicAdd(g.reg_count + c.region, 1u);
+      { // region owner: stays a tree's tag only while every entry added belongs to that tree
+        const uint32_t tag = (g.blk_rec[0][e.block].root_flags & kRecRootMask) + 1u;
+        uint32_t *owner = g.reg_owner + c.region;
+        uint32_t cur = *reinterpret_cast<volatile uint32_t *>(owner);
+        if (cur == kOwnerNone)
+          cur = atomicCAS(owner, kOwnerNone, tag);
+        if (cur != kOwnerNone && cur != tag && cur != kOwnerMixed)
+          atomicExch(owner, kOwnerMixed);
+      }
       uint32_t *tile = g.occ[e.layer & 1] + (size_t)c.region * kTileWords;
       atomicOr(tile + c.cy, 1u << c.cx);
       atomicOr(tile + kRegionWidth + c.cx, 1u << c.cy);
@@ -291,6 +310,39 @@ __global__ void __launch_bounds__(256) k1_phase1(GridView g, const unsigned char
     __syncthreads();
   }
 }
+
+// After a block changed trees (flag raised by k1_table_updates) the owner tags are rebuilt from the cell-entry
+// tables: clear, re-derive from every live entry of both layers, lower the flag - three launches in stream order,
+// each of which only reads the flag when nothing changed. The host launches them after a pass that carried model
+// or attribute updates, and after every gathered pass (other ranks' updates are only known on the device).
+__global__ void __launch_bounds__(256) k1_owner_clear(GridView g)
+{
+  if (!g.reg_owner[g.n_regions])
+    return;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < g.n_regions; r += gridDim.x * blockDim.x)
+    g.reg_owner[r] = kOwnerNone;
+}
+
+__global__ void __launch_bounds__(256) k1_owner_scan(GridView g)
+{
+  if (!g.reg_owner[g.n_regions])
+    return;
+  const uint64_t n = (uint64_t)g.slot_mask + 1u;
+  for (uint64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long cur = g.slots[i >= n][i >= n ? i - n : i];
+    if (cur == kSlotEmpty || cur == kSlotTomb)
+      continue;
+    const uint32_t tag = (g.blk_rec[0][(uint32_t)cur - 1u].root_flags & kRecRootMask) + 1u;
+    uint32_t *owner = g.reg_owner + (uint32_t)(cur >> (32 + 2 * kRBits));
+    uint32_t seen = *reinterpret_cast<volatile uint32_t *>(owner);
+    if (seen == kOwnerNone)
+      seen = atomicCAS(owner, kOwnerNone, tag);
+    if (seen != kOwnerNone && seen != tag && seen != kOwnerMixed)
+      atomicExch(owner, kOwnerMixed);
+  }
+}
+
+__global__ void k1_owner_done(GridView g) { g.reg_owner[g.n_regions] = 0u; }
 
 // Compaction of one layer's cell-content table: re-insert the live entries into a clean table
 // (tombstones only ever turn into entries again, never into empty slots, so probe chains grow
@@ -336,6 +388,16 @@ void launch_apply_deltas(const GridView &g, const unsigned char *blobs, int n_ra
     k1_phase1<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes);
   if (launch_counter)
     *launch_counter += 1;
+}
+
+void launch_owner_rebuild(const GridView &g, void *stream, uint64_t *launch_counter)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  k1_owner_clear<<<delta_grid_blocks(), 256, 0, s>>>(g);
+  k1_owner_scan<<<delta_grid_blocks(), 256, 0, s>>>(g);
+  k1_owner_done<<<1, 1, 0, s>>>(g);
+  if (launch_counter)
+    *launch_counter += 3;
 }
 
 void launch_rehash(const unsigned long long *src, unsigned long long *dst, uint32_t slot_mask, void *stream)

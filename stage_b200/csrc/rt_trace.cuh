@@ -142,6 +142,9 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
   const uint32_t wstep = (flags & kCrossNeg) ? ~0u : 1u, revmask = runneg ? ~0u : 0u;
   const int32_t rm1 = r_max - 1;
   const uint32_t occ_layer = layer1 ? (uint32_t)(g.occ[1] - g.occ[0]) : 0u; // one allocation, rt_api.cu
+  // The tag of the regions this ray cannot be stopped in (GridView::reg_owner): regions that hold nothing but
+  // blocks of the finder's own tree, under a predicate that rejects related models.
+  const uint32_t finder_tag = fan->pred == 2u ? kOwnerNever : __ldg(g.mdl_root + fan->finder) + 1u;
   bool hit = false;
 
   while (n > 0) {
@@ -165,7 +168,10 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
       int32_t cp = cp0, ap = ap0;
       // word index of the current mask; the next mask in the direction of travel is wstep words on
       uint32_t wi = occ_layer + region * kTileWords + (ymajor ? kRegionWidth : 0) + ((uint32_t)cp ^ cflip);
-      uint32_t word = __ldg(g.occ[0] + wi);
+      const bool foreign = __ldg(g.reg_owner + region) != finder_tag; // else: nothing here can stop this ray
+      uint32_t word = 0;
+      if (foreign)
+        word = __ldg(g.occ[0] + wi);
       word ^= (word ^ __brev(word)) & revmask;
       // r = run steps before the next cross step: the smallest r >= 0 with E + r*b_run >= 0. E >= -b_cross
       // always, so r <= r_max. Entering a region E is anywhere in that range (one estimate + fix-up);
@@ -185,7 +191,7 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
       for (;;) {
         // the mask the walk needs after this run's cross step, requested before this run is tested
         uint32_t ahead = 0;
-        if (cp < kRegionWidth - 1)
+        if (foreign && cp < kRegionWidth - 1)
           ahead = __ldg(g.occ[0] + (wi + wstep));
         const int32_t m = min(min(r + 1, kRegionWidth - ap), n); // cells tested: a cell is only tested while n > 0
         uint32_t occupied = word & ((0xffffffffu >> (32 - m)) << ap);

@@ -112,6 +112,7 @@ def lib():
         "stg_rt_set_device_ptrs": (ctypes.c_int, [vp, vp, ctypes.POINTER(FanOut)]),
         "stg_rt_set_beams": (u64, [vp]),
         "stg_rt_grid_dump": (ctypes.c_int64, [vp, vp, ctypes.c_int64, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
+        "stg_rt_debug_region_owners": (ctypes.c_int64, [vp, vp, ctypes.c_int64]),
         "stg_rt_delta_export": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(sz)]),
         "stg_rt_delta_slot_bytes": (sz, [vp]),
         "stg_rt_delta_apply_gathered": (ctypes.c_int, [vp, vp, ctypes.c_int, sz]),
@@ -136,7 +137,7 @@ EXPORTED_SYMBOLS = (
     "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_fiducials_submit_packed stg_rt_rangers_submit stg_rt_collisions_test stg_rt_models_move stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
-    "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_debug_trig stg_rt_debug_headings").split()
+    "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_debug_trig stg_rt_debug_headings stg_rt_debug_region_owners").split()
 
 
 _BYTES0 = ctypes.c_char * 0
@@ -372,6 +373,13 @@ class Context:
         n2 = self._check(self._L.stg_rt_grid_dump(self._h, _ptr(rec), n, _ptr(cnt), nc.value, ctypes.byref(nc)))
         assert n2 == n
         return rec[:n], cnt[:nc.value]
+
+    def region_owners(self):
+        """int64[m,3] {rx, ry, tag} of the regions with an owner tag (root + 1, or 0xffffffff = several trees)."""
+        n = self._check(self._L.stg_rt_debug_region_owners(self._h, None, 0))
+        rec = np.zeros((max(n, 1), 3), np.int64)
+        assert self._check(self._L.stg_rt_debug_region_owners(self._h, _ptr(rec), n)) == n
+        return rec[:n]
 
     def stats(self):
         s = Stats()

@@ -242,6 +242,92 @@ def test_moving_blocks_stress_with_table_compaction():
     p.ctx.close()
 
 
+def check_owner_tags(p, root_of_block, exact=False):
+    """GridView::reg_owner (rt_device.h): a region without entries has no tag; a tree's tag means every entry of
+    the region, on both layers, belongs to that tree. exact: a region of one tree carries that tree's tag (true of
+    a freshly loaded or rebuilt grid; later a region stays "mixed" until it has been empty once). Returns how many
+    regions carry a tree's tag."""
+    rec, cnt = p.ctx.grid_dump()
+    owners = {(int(rx), int(ry)): int(t) for rx, ry, t in p.ctx.region_owners()}
+    populated = {(int(rx), int(ry)) for rx, ry, _ in cnt}
+    assert set(owners) == populated
+    roots = {}
+    for _, x, y, _, b in rec:
+        roots.setdefault((int(x) >> 5, int(y) >> 5), set()).add(root_of_block[int(b)])
+    tagged = 0
+    for reg, tag in owners.items():
+        if tag != 0xffffffff:
+            assert roots[reg] == {tag - 1}, (reg, tag, roots[reg])
+            tagged += 1
+        elif exact:
+            assert len(roots[reg]) > 1, (reg, roots[reg])
+    return tagged
+
+
+def test_region_owner_tags_follow_moving_trees():
+    """Robots (a body and a child model's block each, one tree per robot) wander among walls and each other on
+    alternating layers; a ranger and an any-unrelated-model ray fan from every robot agree with the oracle each tick,
+    and the owner tags that let a ray skip its own tree's regions keep their invariant - including regions a robot
+    shares with a wall or another robot (mixed) and regions it has left (no tag)."""
+    p = Pair(max_blocks=256)
+    n = 12
+    p.model(1, 1, 0.5)  # walls
+    root_of_block = {}
+    walls = [box(-400, -400, 400, -396), box(-400, 396, 400, 400), box(-400, -400, -396, 400), box(396, -400, 400, 400),
+             box(-40, -200, -36, 200), box(100, 60, 220, 64)]
+    for i, w in enumerate(walls):
+        for layer in (0, 1):
+            p.map(i, 1, layer, (0.0, 1.0), w)
+        root_of_block[i] = 1
+    for r in range(n):
+        p.model(10 + 2 * r, 10 + 2 * r, 0.8)
+        p.model(11 + 2 * r, 10 + 2 * r, 0.8)  # child: same tree
+    rng = np.random.RandomState(11)
+    pos = rng.randint(-330, 330, size=(n, 2))
+    vel = rng.randint(-9, 10, size=(n, 2))
+    body = lambda r: 10 + 2 * r
+    arm = lambda r: 11 + 2 * r
+    total_tagged = 0
+    for tick in range(60):
+        layer = tick % 2
+        for r in range(n):
+            x, y = int(pos[r, 0]), int(pos[r, 1])
+            bb, ba = 20 + 2 * r, 21 + 2 * r
+            root_of_block[bb] = root_of_block[ba] = body(r)
+            if tick >= 2:
+                p.unmap(bb, layer)
+                p.unmap(ba, layer)
+            p.map(bb, body(r), layer, (0.0, 1.0), box(x - 10, y - 9, x + 10, y + 9))
+            p.map(ba, arm(r), layer, (0.0, 1.0), box(x + 10, y - 2, x + 22, y + 2))
+        if tick >= 1:
+            heads = np.linspace(-np.pi, np.pi, 90, endpoint=False)
+            for r in range(n):
+                o = (pos[r] + 0.5) / 50.0
+                p.rays(body(r), o, heads, 6.0, layer=layer)
+                if r % 4 == 0:
+                    p.rays(arm(r), o, heads, 6.0, pred=rt.PRED_UNRELATED, layer=layer, ztest=0)
+                    p.rays(body(r), o, heads, 6.0, pred=rt.PRED_GRIPPER, layer=layer)
+        if tick == 1:  # nothing has moved yet: the tags are exactly "the one tree of this region"
+            assert check_owner_tags(p, root_of_block, exact=True) >= n
+        if tick % 6 == 5:
+            total_tagged += check_owner_tags(p, root_of_block)
+            p.grids_equal()
+        last = pos.copy()
+        pos = pos + vel
+        bounce = np.abs(pos) > 360
+        vel = np.where(bounce, -vel, vel)
+        pos = np.clip(pos, -360, 360)
+    assert total_tagged > 50  # the robots really are alone in most of their regions
+    # a robot's arm is handed to another robot's tree: the tags are rebuilt from the grid, rays see the new relation
+    p.model(arm(0), body(1), 0.8)
+    root_of_block[21] = body(1)
+    heads = np.linspace(-np.pi, np.pi, 180, endpoint=False)
+    g, _ = p.rays(body(0), (last[0] + 0.5) / 50.0, heads, 6.0, layer=59 % 2)
+    assert arm(0) in set(g.hit_model)
+    assert check_owner_tags(p, root_of_block, exact=True) >= n - 2
+    p.ctx.close()
+
+
 def test_single_beam_sonar_fans():
     """BASELINE config 4's ray shape: thousands of one-beam ranger sensors (sample_count 1 ->
     start_angle 0, heading = (double)(float)origin.a)."""
