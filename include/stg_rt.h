@@ -293,6 +293,17 @@ int stg_rt_rangers_submit(stg_rt_ctx *ctx, uint32_t n_sensors, const stg_rt_rang
 int stg_rt_collisions_test(stg_rt_ctx *ctx, int layer, uint32_t n_queries, const uint32_t *query_first,
                            const uint32_t *blocks, uint32_t ground_model, int32_t *hit_model);
 
+/* Model::AppendTouchingModels (model.cc:661-664 -> BlockGroup::AppendTouchingModels blockgroup.cc:35-39 ->
+   Block::AppendTouchingModels block.cc:116-127; called by Model::UpdateCharge, model.cc:700-701, for every
+   model that gives charge) for n_queries models at once. Query q covers the model's OWN blocks
+   blocks[query_first[q] .. query_first[q + 1]) (children are not visited). layer = World::updates % 2
+   (block.cc:118). touchers[q * max_per_query ..] = ids of the models, not related to the query's (other
+   tree), that have a block in any cell those blocks are rendered into - no obstacle_return, no z test -
+   ascending; counts[q] = how many there are (the list is cut at max_per_query; 0xffffffff: more than
+   the 120 distinct models one query can hold). Delivered by stg_rt_sync, like sensor results. */
+int stg_rt_touching_models(stg_rt_ctx *ctx, int layer, uint32_t n_queries, const uint32_t *query_first,
+                           const uint32_t *blocks, uint32_t max_per_query, uint32_t *touchers, uint32_t *counts);
+
 /* ---- batched ModelPosition::Move ------------------------------------------------------------ */
 
 /* ModelPosition::Move (model_position.cc:526-566) for n_movers position models at once, with the

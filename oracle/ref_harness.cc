@@ -16,6 +16,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <set>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -204,6 +205,35 @@ Model *Model::TestCollision()
   e.n_pts = (uint16_t)n;
   rec.events.push_back(e);
   return hit;
+}
+
+void Model::AppendTouchingModels(std::set<Model *> &touchers)
+{
+  typedef void (*fn_t)(Model *, std::set<Model *> &);
+  static fn_t fn = real<fn_t>("_ZN3Stg5Model20AppendTouchingModelsERSt3setIPS0_St4lessIS2_ESaIS2_EE");
+  std::set<Model *> mine; // what THIS call adds, whatever the caller's set already held
+  fn(this, mine);
+  touchers.insert(mine.begin(), mine.end());
+  if (!rec.active || tl_quiet)
+    return;
+  std::lock_guard<std::mutex> g(rec.mu);
+  TraceEvent e;
+  memset(&e, 0, sizeof(e));
+  e.type = TRACE_EV_TOUCHERS;
+  e.layer = (uint8_t)(world->updates % 2);
+  e.model = id;
+  e.first = (uint32_t)rec.aux.size();
+  e.n_pts = (uint16_t)blockgroup.blocks.size();
+  for (size_t i = 0; i < blockgroup.blocks.size(); i++)
+    rec.aux.push_back((double)block_id_locked(&blockgroup.blocks[i]));
+  std::vector<uint32_t> ids;
+  for (std::set<Model *>::iterator it = mine.begin(); it != mine.end(); ++it)
+    ids.push_back((*it)->id);
+  std::sort(ids.begin(), ids.end());
+  e.block = (uint32_t)ids.size();
+  for (size_t i = 0; i < ids.size(); i++)
+    rec.aux.push_back((double)ids[i]);
+  rec.events.push_back(e);
 }
 
 RaytraceResult World::Raytrace(const Ray &r)

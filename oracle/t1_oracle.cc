@@ -30,6 +30,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <unordered_map>
+#include <set>
 #include <vector>
 
 #include "trace_format.h"
@@ -634,6 +635,7 @@ typedef struct {
   uint64_t fiducial_updates, fiducial_mismatch, blob_updates, blob_mismatch;
   double max_range_err;
   uint64_t collision_tests, collision_mismatch, collision_hits;
+  uint64_t toucher_calls, toucher_mismatch, toucher_models;
 } T1ReplayStats;
 
 // Model::TestCollision (model.cc:666-679) over BlockGroup::TestCollision (blockgroup.cc:41-50) and
@@ -674,6 +676,42 @@ int32_t t1_test_collision(void *wv, int layer, uint32_t n_blocks, const uint32_t
     }
   }
   return -1;
+}
+
+// Model::AppendTouchingModels (model.cc:661-664) -> BlockGroup::AppendTouchingModels (blockgroup.cc:35-39) ->
+// Block::AppendTouchingModels (block.cc:116-127): `blocks` are the dense ids of the model's own blocks (its
+// children are not visited). For every cell a block is rendered into on `layer` (= World::updates % 2) and
+// every block listed in that cell: its model joins the set unless it is related to this one (same tree -
+// which covers the block itself). No obstacle_return, no z test. The reference collects a std::set<Model*>;
+// the ids come back ascending, at most `cap` of them; returns how many there are.
+uint32_t t1_touching_models(void *wv, int layer, uint32_t n_blocks, const uint32_t *blocks, uint32_t cap, uint32_t *out)
+{
+  const T1World *w = (const T1World *)wv;
+  std::set<uint32_t> found;
+  for (uint32_t i = 0; i < n_blocks; i++) {
+    if (blocks[i] >= w->blocks.size() || !w->blocks[blocks[i]].known)
+      continue;
+    const T1Block &b = w->blocks[blocks[i]];
+    const T1Model &own = w->models[b.model];
+    const std::vector<int64_t> &cells = b.rendered[layer];
+    for (size_t c = 0; c < cells.size(); c++) {
+      const int32_t x = (int32_t)(uint32_t)cells[c], y = (int32_t)(cells[c] >> 32);
+      const T1Region *reg = w->find_region(x >> RBITS, y >> RBITS);
+      if (!reg || reg->cells[layer].empty())
+        continue;
+      const std::vector<uint32_t> &list = reg->cells[layer][(x & (REGIONWIDTH - 1)) + (y & (REGIONWIDTH - 1)) * REGIONWIDTH];
+      for (size_t k = 0; k < list.size(); k++) {
+        const T1Block &tb = w->blocks[list[k]];
+        if (w->models[tb.model].root != own.root) // !IsRelated, model.cc:446-466
+          found.insert(tb.model);
+      }
+    }
+  }
+  uint32_t n = 0;
+  for (std::set<uint32_t>::const_iterator it = found.begin(); it != found.end(); ++it, n++)
+    if (out && n < cap)
+      out[n] = *it;
+  return n;
 }
 
 // Replay a recorded reference trace through T1 and compare every ray with the reference's answer.
@@ -727,6 +765,18 @@ void *t1_replay(const char *path, T1ReplayStats *st)
         st->collision_mismatch++;
       if (e.block)
         st->collision_hits++;
+    } else if (e.type == TRACE_EV_TOUCHERS) {
+      std::vector<uint32_t> ids(e.n_pts), got(e.block + 1);
+      for (uint32_t k = 0; k < e.n_pts; k++)
+        ids[k] = (uint32_t)aux[e.first + k];
+      const uint32_t n = t1_touching_models(w, e.layer, e.n_pts, ids.data(), e.block + 1, got.data());
+      bool same = n == e.block;
+      for (uint32_t k = 0; same && k < n; k++)
+        same = got[k] == (uint32_t)aux[e.first + e.n_pts + k];
+      st->toucher_calls++;
+      st->toucher_models += e.block;
+      if (!same)
+        st->toucher_mismatch++;
     } else if (e.type == TRACE_EV_FIDUCIAL) {
       const double *a = &aux[e.first];
       const uint32_t nt = (uint32_t)a[13], nf = e.block;

@@ -20,7 +20,8 @@
 #define STG_TRACE_MAGIC "STGTRC05"
 
 enum { TRACE_EV_MAP = 1, TRACE_EV_UNMAP = 2, TRACE_EV_RAYS = 3, TRACE_EV_TICK = 4,
-       TRACE_EV_RANGER_SCAN = 5, TRACE_EV_FIDUCIAL = 6, TRACE_EV_BLOB = 7, TRACE_EV_COLLISION = 8 };
+       TRACE_EV_RANGER_SCAN = 5, TRACE_EV_FIDUCIAL = 6, TRACE_EV_BLOB = 7, TRACE_EV_COLLISION = 8,
+       TRACE_EV_TOUCHERS = 9 /* added without a new magic: older traces simply hold none */ };
 
 /* predicate kinds: which of the reference's static ray_test_func_t a ray was traced with */
 enum {
@@ -103,5 +104,13 @@ typedef struct {
  * event.block = id of the model it returned + 1, 0 for no collision, event.n_pts = n, aux[first ..
  * first + n) = the dense ids of the blocks it may visit, in visiting order: the model's own
  * BlockGroup, then each child's, depth first (blockgroup.cc:41-50, model.cc:668-676). */
+
+/* TOUCHERS: one Model::AppendTouchingModels (model.cc:661-664, called by Model::UpdateCharge :700-701 for
+ * every model that gives charge, each tick) -> BlockGroup / Block::AppendTouchingModels (blockgroup.cc:35-39,
+ * block.cc:116-127): the set of models not related to this one that have a block in any cell this model's own
+ * blocks are rendered into. event.model = the model, event.layer = World::updates % 2 (block.cc:118),
+ * event.n_pts = n own blocks, event.block = m models found, aux[first .. first + n) = the dense ids of the
+ * model's BlockGroup (children are NOT visited), aux[first + n .. first + n + m) = the ids of the models
+ * added to the set, ascending. */
 
 #endif

@@ -176,6 +176,14 @@ struct stg_rt_ctx {
   } col_job;
   DevBuf d_col_in, d_col_hit;
   PinBuf h_col_in, h_col_hit;
+  // stg_rt_touching_models
+  struct ToucherJob {
+    uint32_t *user_out = nullptr, *user_count = nullptr;
+    uint32_t n_queries = 0, max_per_query = 0;
+    bool pending = false;
+  } touch_job;
+  DevBuf d_touch_out;
+  PinBuf h_touch_out;
   // stg_rt_models_move
   DevBuf d_mv_in, d_mv_out, d_mover_of_model;
   PinBuf h_mv_in, h_mv_out;
@@ -643,9 +651,18 @@ void deliver_array(stg_rt_ctx *c, void *user, const PinBuf &stage, uint64_t firs
 
 int deliver_post_locked(stg_rt_ctx *c)
 {
-  if (!c->fid_job.pending && !c->blob_job.pending && !c->col_job.pending)
+  if (!c->fid_job.pending && !c->blob_job.pending && !c->col_job.pending && !c->touch_job.pending)
     return 0;
   CU(c, cudaStreamSynchronize(c->stream));
+  if (c->touch_job.pending) {
+    const stg_rt_ctx::ToucherJob &j = c->touch_job;
+    const uint32_t *cnt = (const uint32_t *)c->h_touch_out.p, *ids = cnt + j.n_queries;
+    memcpy(j.user_count, cnt, (size_t)j.n_queries * 4);
+    for (uint32_t q = 0; q < j.n_queries; q++)
+      memcpy(j.user_out + (size_t)q * j.max_per_query, ids + (size_t)q * j.max_per_query,
+             (size_t)std::min(cnt[q] == 0xffffffffu ? j.max_per_query : cnt[q], j.max_per_query) * 4);
+    c->touch_job.pending = false;
+  }
   if (c->col_job.pending) {
     const int32_t *hit = (const int32_t *)c->h_col_hit.p;
     for (size_t q = 0; q < c->col_job.fallback.size(); q++)
@@ -1003,10 +1020,10 @@ int stg_rt_destroy(stg_rt_ctx *c)
     cudaFreeHost(c->q_fans.p);
   if (c->d_in.p)
     cudaFree(c->d_in.p);
-  for (DevBuf *b : { &c->d_rig, &c->d_mv_in, &c->d_mv_out, &c->d_mover_of_model, &c->d_col_in, &c->d_col_hit, &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_fid_off, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
+  for (DevBuf *b : { &c->d_rig, &c->d_mv_in, &c->d_mv_out, &c->d_mover_of_model, &c->d_col_in, &c->d_col_hit, &c->d_touch_out, &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_fid_off, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
     if (b->p)
       cudaFree(b->p);
-  for (PinBuf *b : { &c->h_rig, &c->h_mv_in, &c->h_mv_out, &c->h_col_in, &c->h_col_hit, &c->h_fid_in, &c->h_fid_out, &c->h_fid_count, &c->h_blob_in, &c->h_blob_out, &c->h_blob_count })
+  for (PinBuf *b : { &c->h_rig, &c->h_mv_in, &c->h_mv_out, &c->h_col_in, &c->h_col_hit, &c->h_touch_out, &c->h_fid_in, &c->h_fid_out, &c->h_fid_count, &c->h_blob_in, &c->h_blob_out, &c->h_blob_count })
     if (b->p)
       cudaFreeHost(b->p);
   PinBuf *pins[] = { &c->h_blob, &c->h_in, &c->h_ranges, &c->h_intens, &c->h_bearings, &c->h_hit_model, &c->h_hit_cell, &c->h_steps };
@@ -1904,6 +1921,72 @@ int stg_rt_collisions_test(stg_rt_ctx *c, int layer, uint32_t n_queries, const u
   c->stats.d2h_bytes += (size_t)n_queries * 4;
   c->col_job.user_hit = hit_model;
   c->col_job.pending = true;
+  return STG_RT_OK;
+}
+
+int stg_rt_touching_models(stg_rt_ctx *c, int layer, uint32_t n_queries, const uint32_t *query_first, const uint32_t *blocks,
+                           uint32_t max_per_query, uint32_t *touchers, uint32_t *counts)
+{
+  if (!c || layer < 0 || layer > 1 || (n_queries && (!query_first || !counts || (max_per_query && !touchers))))
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!n_queries)
+    return STG_RT_OK;
+  const uint32_t n_ids = query_first[n_queries];
+  if (n_ids && !blocks)
+    return STG_RT_EINVAL;
+  for (uint32_t q = 0; q < n_queries; q++) {
+    if (query_first[q + 1] < query_first[q])
+      return fail(c, STG_RT_EINVAL, "touching_models: query_first is not ascending at %u", q);
+    for (uint32_t i = query_first[q]; i < query_first[q + 1]; i++)
+      if (blocks[i] >= c->cfg.max_blocks || !c->blocks[blocks[i]].known)
+        return fail(c, STG_RT_EINVAL, "touching_models: query %u names unknown block %u", q, blocks[i]);
+  }
+  int rc = flush_locked(c); // the grid the walk reads includes every Map / UnMap issued so far
+  if (rc || (rc = deliver_post_locked(c)))
+    return rc;
+  size_t n_edges = 0;
+  for (uint32_t i = 0; i < n_ids; i++)
+    n_edges += c->blocks[blocks[i]].dev_xy[layer].size() / 2;
+  const size_t b_q = (size_t)n_queries * sizeof(CollisionQuery), b_in = b_q + n_edges * sizeof(EdgeRec);
+  const size_t b_out = (size_t)n_queries * 4 * (1 + (size_t)max_per_query);
+  if ((rc = pin_reserve(c, c->h_col_in, b_in)) || (rc = dev_reserve(c, c->d_col_in, b_in + 16)) ||
+      (rc = pin_reserve(c, c->h_touch_out, b_out)) || (rc = dev_reserve(c, c->d_touch_out, b_out)))
+    return rc;
+  CollisionQuery *qr = (CollisionQuery *)c->h_col_in.p;
+  EdgeRec *e0 = (EdgeRec *)((char *)c->h_col_in.p + b_q), *e = e0;
+  for (uint32_t q = 0; q < n_queries; q++) {
+    qr[q].first_edge = (uint32_t)(e - e0);
+    qr[q].layer = (uint32_t)layer;
+    uint32_t cursor = 0;
+    for (uint32_t i = query_first[q]; i < query_first[q + 1]; i++) {
+      const BlockShadow &b = c->blocks[blocks[i]];
+      if (b.dev_mapped[layer]) // Block::rendered_cells[layer]: what the block is rendered into now
+        emit_edges(b.dev_xy[layer], blocks[i], (uint32_t)layer, cursor, e, &b.dev_poly[layer]);
+    }
+    qr[q].n_edges = (uint32_t)(e - e0) - qr[q].first_edge;
+    qr[q].n_steps = cursor;
+  }
+  const size_t b_used = b_q + (size_t)(e - e0) * sizeof(EdgeRec);
+  CU(c, cudaMemcpyAsync(c->d_col_in.p, c->h_col_in.p, b_used, cudaMemcpyHostToDevice, c->stream));
+  c->stats.h2d_bytes += b_used;
+  ToucherBatchView v;
+  v.n_queries = n_queries;
+  v.max_per_query = max_per_query;
+  v.queries = (const CollisionQuery *)c->d_col_in.p;
+  v.edges = (const EdgeRec *)((const char *)c->d_col_in.p + b_q);
+  v.out_count = (uint32_t *)c->d_touch_out.p;
+  v.out = v.out_count + n_queries;
+  launch_touchers(c->g, v, c->stream);
+  c->stats.launches_post++;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(c->h_touch_out.p, c->d_touch_out.p, b_out, cudaMemcpyDeviceToHost, c->stream));
+  c->stats.d2h_bytes += b_out;
+  c->touch_job.user_out = touchers;
+  c->touch_job.user_count = counts;
+  c->touch_job.n_queries = n_queries;
+  c->touch_job.max_per_query = max_per_query;
+  c->touch_job.pending = true;
   return STG_RT_OK;
 }
 

@@ -224,6 +224,17 @@ struct CollisionBatchView {
 };
 void launch_collisions(const GridView &g, const CollisionBatchView &b, void *stream);
 
+// Model::AppendTouchingModels: same queries (own blocks only), a set of models per query
+constexpr uint32_t kTouchersCap = 120; // distinct models one query can report
+struct ToucherBatchView {
+  uint32_t n_queries, max_per_query;
+  const CollisionQuery *queries;
+  const EdgeRec *edges;
+  uint32_t *out;       // [n_queries * max_per_query] model ids, ascending
+  uint32_t *out_count; // per query: how many there are; 0xffffffff: more than kTouchersCap
+};
+void launch_touchers(const GridView &g, const ToucherBatchView &b, void *stream);
+
 // ---- batched Move (ModelPosition::Move) ----------------------------------------------------------
 // What a mover's new outline touches (Block::TestCollision's condition, block.cc:153-157), split into
 // "something that does not move this tick" and the list of other movers it touches.

@@ -320,6 +320,102 @@ __global__ void __launch_bounds__(128) k4_collisions(GridView g, CollisionBatchV
     b.hit_model[warp] = result;
 }
 
+// ---- K4b: Model::AppendTouchingModels (model.cc:661-664 -> block.cc:116-127) -------------------------
+// The set of models, not related to the query's own, that have a block in any cell the query's blocks are
+// rendered into. The same cell walk as K4 (one warp per query, lane i looks at cell visit t0 + i), but no
+// obstacle_return and no z test, and every unrelated entry counts, not the first. The warp keeps the set in
+// shared memory: candidates are handed over one at a time (ballot order), the lanes search the list in
+// parallel, lane 0 appends what is new. Written out ascending (the reference's std::set is ordered by
+// pointer; what callers get from it is membership).
+__global__ void __launch_bounds__(128) k4_touchers(GridView g, ToucherBatchView b)
+{
+  __shared__ uint32_t list_all[4][kTouchersCap];
+  const uint32_t wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t warp = blockIdx.x * 4 + wic;
+  if (warp >= b.n_queries)
+    return;
+  uint32_t *list = list_all[wic];
+  uint32_t count = 0; // warp-uniform
+  bool overflow = false;
+  const CollisionQuery q = b.queries[warp];
+  const EdgeRec *edges = b.edges + q.first_edge;
+  const int L = q.layer & 1;
+  const unsigned long long *slots = g.slots[L];
+  const uint4 *recs = reinterpret_cast<const uint4 *>(g.blk_rec[L]);
+  for (uint32_t t0 = 0; t0 < q.n_steps; t0 += 32) {
+    const uint32_t t = t0 + lane;
+    uint32_t key = 0, own_root = 0, h = 0;
+    bool live = t < q.n_steps;
+    if (live) {
+      uint32_t ei = 0;
+      while (ei + 1 < q.n_edges && edges[ei + 1].first_step <= t)
+        ei++;
+      const EdgeRec e = edges[ei];
+      int32_t x, y;
+      edge_cell_post(e, t - e.first_step, x, y);
+      own_root = __ldg(recs + 2 * (size_t)e.block + 1).w & kRecRootMask;
+      const int32_t rix = (x >> kRBits) - g.rx0, riy = (y >> kRBits) - g.ry0;
+      const uint32_t region = (uint32_t)(riy * g.nrx + rix);
+      key = (region << (2 * kRBits)) | (((uint32_t)y & (kRegionWidth - 1)) << kRBits) | ((uint32_t)x & (kRegionWidth - 1));
+      h = slot_home(key, g.slot_mask);
+    }
+    uint32_t probes = 0;
+    for (;;) {
+      // every lane advances along its cell's probe sequence to the next unrelated entry, if there is one
+      uint32_t cand = 0xffffffffu;
+      while (live) {
+        const unsigned long long cur = __ldg(slots + h);
+        if (cur == kSlotEmpty || probes > g.slot_mask) {
+          live = false;
+          break;
+        }
+        h = (h + 1) & g.slot_mask;
+        probes++;
+        if ((uint32_t)(cur >> 32) == key) {
+          const uint4 o = __ldg(recs + 2 * (size_t)((uint32_t)cur - 1u) + 1);
+          if ((o.w & kRecRootMask) != own_root) { // !IsRelated, block.cc:123
+            cand = o.z;
+            break;
+          }
+        }
+      }
+      uint32_t votes = __ballot_sync(0xffffffffu, cand != 0xffffffffu);
+      if (!votes)
+        break;
+      while (votes) {
+        const uint32_t m = __shfl_sync(0xffffffffu, cand, __ffs(votes) - 1);
+        votes &= votes - 1u;
+        bool seen = false;
+        for (uint32_t i = lane; i < count; i += 32)
+          seen |= list[i] == m;
+        if (!__any_sync(0xffffffffu, seen)) {
+          if (count < kTouchersCap) {
+            if (lane == 0)
+              list[count] = m;
+            count++;
+          } else {
+            overflow = true;
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // ascending: the rank of an element is the number of smaller ones (the list holds no duplicates)
+  uint32_t *out = b.out + (size_t)warp * b.max_per_query;
+  for (uint32_t i = lane; i < count; i += 32) {
+    const uint32_t m = list[i];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < count; j++)
+      rank += list[j] < m;
+    if (rank < b.max_per_query)
+      out[rank] = m;
+  }
+  if (lane == 0)
+    b.out_count[warp] = overflow ? 0xffffffffu : count;
+}
+
 // ---- K5: what the movers' new outlines touch (stg_rt_models_move) ----------------------------------
 // The same cell walk and the same condition as K4, but instead of the first model in the way it
 // reports (a) whether anything that does not move this tick is in the way and (b) which other movers
@@ -515,6 +611,13 @@ void launch_collisions(const GridView &g, const CollisionBatchView &b, void *str
   if (!b.n_queries)
     return;
   k4_collisions<<<(b.n_queries * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g, b);
+}
+
+void launch_touchers(const GridView &g, const ToucherBatchView &b, void *stream)
+{
+  if (!b.n_queries)
+    return;
+  k4_touchers<<<(b.n_queries + 3) / 4, 128, 0, (cudaStream_t)stream>>>(g, b);
 }
 
 // table[pairs[2i]] = clear ? 0 : pairs[2i + 1]

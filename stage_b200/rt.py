@@ -98,6 +98,7 @@ def lib():
         "stg_rt_blobs_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
         "stg_rt_rangers_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, ctypes.POINTER(FanOut)]),
         "stg_rt_collisions_test": (ctypes.c_int, [vp, ctypes.c_int, u32, vp, vp, u32, vp]),
+        "stg_rt_touching_models": (ctypes.c_int, [vp, ctypes.c_int, u32, vp, vp, u32, vp, vp]),
         "stg_rt_models_move": (ctypes.c_int, [vp, ctypes.c_int, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "stg_rt_fans_submit_noisy": (ctypes.c_int, [vp, u32, vp, vp, ctypes.POINTER(FanOut)]),
         "stg_rt_flush": (ctypes.c_int, [vp]),
@@ -134,7 +135,7 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "stg_rt_abi_version stg_rt_create stg_rt_destroy stg_rt_last_error stg_rt_model_upsert stg_rt_block_map "
-    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_fiducials_submit_packed stg_rt_rangers_submit stg_rt_collisions_test stg_rt_models_move stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
+    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_fiducials_submit_packed stg_rt_rangers_submit stg_rt_collisions_test stg_rt_touching_models stg_rt_models_move stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
     "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_debug_trig stg_rt_debug_headings stg_rt_debug_region_owners").split()
@@ -280,6 +281,18 @@ class Context:
         self._keep.append((first, blocks, hit))
         self._check(self._L.stg_rt_collisions_test(self._h, layer, len(first) - 1, _ptr(first), _ptr(blocks), ground_model, _ptr(hit)))
         return hit
+
+    def touching_models(self, layer, queries, max_per_query=32):
+        """queries: one sequence of block ids per model (its own blocks) -> (ids[n, max_per_query] uint32 ascending,
+        counts[n] uint32); valid after sync()."""
+        first = np.zeros(len(queries) + 1, np.uint32)
+        first[1:] = np.cumsum([len(q) for q in queries])
+        blocks = np.ascontiguousarray(np.concatenate([np.asarray(q, np.uint32) for q in queries]) if len(queries) else np.zeros(0), np.uint32)
+        ids = np.zeros((len(queries), max_per_query), np.uint32)
+        counts = np.zeros(len(queries), np.uint32)
+        self._keep.append((first, blocks, ids, counts))
+        self._check(self._L.stg_rt_touching_models(self._h, layer, len(queries), _ptr(first), _ptr(blocks), max_per_query, _ptr(ids), _ptr(counts)))
+        return ids, counts
 
     def models_move(self, layer, movers):
         """movers: per mover a list of (block id, (zmin, zmax, polygon) wanted, (zmin, zmax, polygon) present) - own

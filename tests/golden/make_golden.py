@@ -2,7 +2,7 @@
 that has /root/reference; run oracle/build_ref.sh first). One subprocess per world because a
 reference World can never be destroyed.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [name ...]
 
 Each trace records every Block::Map / Block::UnMap / World::Raytrace / ModelRanger::Sensor::Update /
 ModelFiducial::Update / ModelBlobfinder::Update / Model::TestCollision the reference performed
@@ -56,6 +56,38 @@ def bumper_world_text():
     return "\n".join(lines) + "\n"
 
 
+def charger_world_text():
+    """charger_150, not a shipped world either: Model::AppendTouchingModels only runs for models that give charge
+    (Model::UpdateCharge), and in fasr.world nothing reaches a charger within a few hundred ticks. Four
+    always-on chargers - a floor pad and a thin strip the robots drive across (no obstacle_return), a dock
+    built into the east wall with a related child model, a post standing in the rotated pillar and the ghost -
+    and the driven robots of the bumper world, some carrying an arm."""
+    import numpy as np
+    rng = np.random.RandomState(5)
+    lines = ["resolution 0.02", "interval_sim 100", "threads 1", "quit_time 3600", ""]
+
+    def box(name, x, y, z, a, sx, sy, sz, extra=""):
+        lines.append('model ( name "%s" pose [ %.3f %.3f %.3f %.3f ] size [ %.3f %.3f %.3f ] %s )' % (name, x, y, z, a, sx, sy, sz, extra))
+    box("wn", 0, 4.05, 0, 0, 8.2, 0.1, 0.5)
+    box("ws", 0, -4.05, 0, 0, 8.2, 0.1, 0.5)
+    box("we", 4.05, 0, 0, 0, 0.1, 8.2, 0.5)
+    box("ww", -4.05, 0, 0, 0, 0.1, 8.2, 0.5)
+    box("pillar", 1.0, 1.0, 0, 30, 0.6, 0.6, 0.5)
+    box("ghost", 0.8, 0.8, 0, 0, 1.0, 1.0, 0.5, "obstacle_return 0")
+    give = "joules -1 give_watts 1000 alwayson 1"
+    box("pad", -1.5, -1.0, 0, 10, 2.4, 2.0, 0.02, "obstacle_return 0 " + give)
+    box("strip", 0, 2.4, 0, -4, 7.0, 0.06, 0.02, "obstacle_return 0 " + give)
+    box("dock", 3.95, -1.0, 0, 0, 0.2, 0.5, 0.1, give + ' model ( name "dockside" pose [ -0.1 0 0 0 ] size [ 0.1 0.7 0.2 ] )')
+    box("post", 1.0, 1.0, 0, 0, 0.9, 0.1, 0.6, "obstacle_return 0 " + give)
+    for i in range(BUMPERS):
+        x, y = rng.uniform(-3.3, 3.3, 2)
+        a = rng.uniform(-180, 180)
+        child = 'model ( name "arm%d" pose [ 0.25 0 0 0 ] size [ 0.3 0.08 0.1 ] )' % i if i % 3 == 0 else ""
+        pack = "kjoules 10 take_watts 500" if i % 2 == 0 else ""
+        lines.append('position ( name "r%d" pose [ %.3f %.3f 0 %.3f ] size [ 0.4 0.3 0.3 ] %s %s )' % (i, x, y, a, pack, child))
+    return "\n".join(lines) + "\n"
+
+
 BUMPERS = 14
 BUMPER_CHILD = r"""
 import sys, os
@@ -103,7 +135,10 @@ os._exit(0)
 """
 
 if __name__ == "__main__":
-    for world, ticks, name in WORLDS + [("everything", 40, "everything_40"), ("bumper", 150, "bumper_150")]:
+    for world, ticks, name in WORLDS + [("everything", 40, "everything_40"), ("bumper", 150, "bumper_150"),
+                                       ("charger", 150, "charger_150")]:
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         raw = os.path.join(HERE, name + ".trc")
         if world == "everything":
             wf = os.path.join(HERE, "everything.world.tmp")
@@ -111,10 +146,10 @@ if __name__ == "__main__":
                 f.write(everything_world_text())
             subprocess.run([sys.executable, "-c", TEXT_CHILD % TESTS, wf, str(ticks), raw], check=True, stdout=subprocess.DEVNULL)
             os.remove(wf)
-        elif world == "bumper":
-            wf = os.path.join(HERE, "bumper.world.tmp")
+        elif world in ("bumper", "charger"):
+            wf = os.path.join(HERE, world + ".world.tmp")
             with open(wf, "w") as f:
-                f.write(bumper_world_text())
+                f.write(bumper_world_text() if world == "bumper" else charger_world_text())
             subprocess.run([sys.executable, "-c", BUMPER_CHILD % TESTS, wf, str(ticks), raw, str(BUMPERS)], check=True,
                            stdout=subprocess.DEVNULL)
             os.remove(wf)

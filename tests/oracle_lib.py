@@ -29,7 +29,7 @@ class ReplayStats(ctypes.Structure):
         "rays", "range_mismatch", "model_mismatch", "maps", "unmaps", "ticks", "cell_visits",
         "region_probes", "scans", "scan_mismatch", "fiducial_updates", "fiducial_mismatch", "blob_updates",
         "blob_mismatch")] + [("max_range_err", ctypes.c_double)] + [(n, ctypes.c_uint64) for n in (
-        "collision_tests", "collision_mismatch", "collision_hits")]
+        "collision_tests", "collision_mismatch", "collision_hits", "toucher_calls", "toucher_mismatch", "toucher_models")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -60,6 +60,7 @@ def t1():
         L.t1_dump_grid.argtypes = [vp, vp, ctypes.c_int64, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
         L.t1_replay.restype, L.t1_replay.argtypes = vp, [ctypes.c_char_p, ctypes.POINTER(ReplayStats)]
         L.t1_test_collision.restype, L.t1_test_collision.argtypes = ctypes.c_int32, [vp, ctypes.c_int, u32, vp]
+        L.t1_touching_models.restype, L.t1_touching_models.argtypes = u32, [vp, ctypes.c_int, u32, vp, u32, vp]
         _t1 = L
     return _t1
 
@@ -167,6 +168,14 @@ class T1World:
         """Model::TestCollision over these blocks (own, then descendants', depth first) -> model id or -1"""
         blocks = np.ascontiguousarray(blocks, np.uint32)
         return int(self.L.t1_test_collision(self.h, layer, len(blocks), _p(blocks)))
+
+    def touching_models(self, layer, blocks, cap=256):
+        """Model::AppendTouchingModels over the model's own blocks -> ascending ids of the unrelated models touched"""
+        blocks = np.ascontiguousarray(blocks, np.uint32)
+        out = np.zeros(cap, np.uint32)
+        n = int(self.L.t1_touching_models(self.h, layer, len(blocks), _p(blocks), cap, _p(out)))
+        assert n <= cap
+        return out[:n]
 
     def dump_grid(self):
         nc = ctypes.c_int64(0)

@@ -108,6 +108,7 @@ class GpuReplay:
         self.fiducials = []  # (event, dict, out, count)
         self.blobs = []
         self.collisions = []  # one hit model id (-1: none) per COLLISION event
+        self.touchers = []  # one ascending list of model ids per TOUCHERS event
         pending = []
         ticks = 0
         for ev in trace.events:
@@ -125,6 +126,12 @@ class GpuReplay:
                 ctx.sync()
                 self._collect(pending)
                 self.collisions.append(int(hit[0]))
+            elif t == trace_io.EV_TOUCHERS:
+                _, layer, blocks, _ = trace.touchers(ev)
+                ids, counts = ctx.touching_models(layer, [blocks], max_per_query=16)
+                ctx.sync()
+                self._collect(pending)
+                self.touchers.append([int(x) for x in ids[0, :counts[0]]])
             elif t == trace_io.EV_RAYS:
                 first, cnt = int(ev["first"]), int(ev["model"])
                 rays = trace.rays[first:first + cnt]
@@ -186,6 +193,7 @@ class T1Replay:
         self.hits = np.zeros(len(trace.rays), oracle_lib.T1_HIT)
         self.scans = []
         self.collisions = []
+        self.touchers = []
         ticks = 0
         for ev in trace.events:
             t = ev["type"]
@@ -197,6 +205,9 @@ class T1Replay:
             elif t == trace_io.EV_COLLISION:
                 _, layer, blocks, _ = trace.collision(ev)
                 self.collisions.append(w.test_collision(layer, blocks))
+            elif t == trace_io.EV_TOUCHERS:
+                _, layer, blocks, _ = trace.touchers(ev)
+                self.touchers.append([int(x) for x in w.touching_models(layer, blocks)])
             elif t == trace_io.EV_RAYS:
                 first, cnt = int(ev["first"]), int(ev["model"])
                 self.hits[first:first + cnt] = w.raytrace(rays_to_t1(trace.rays[first:first + cnt]))

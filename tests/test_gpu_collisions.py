@@ -43,6 +43,22 @@ def test_collision_replay_equals_reference(tmp_path):
     g.ctx.close()
 
 
+def test_touching_models_replay_equals_reference(tmp_path):
+    """charger_150 (tests/golden/make_golden.py): 600 Model::AppendTouchingModels calls of the reference - a floor
+    pad and a strip that robots drive across, a dock built into a wall, a post standing in two other models -
+    interleaved with the robots' Map / UnMap and their 2100 collision tests. Same sets, call by call."""
+    tr = load("charger_150", tmp_path)
+    want = [[int(x) for x in tr.touchers(ev)[3]] for ev in tr.events if ev["type"] == trace_io.EV_TOUCHERS]
+    want_col = [tr.collision(ev)[3] for ev in tr.events if ev["type"] == trace_io.EV_COLLISION]
+    assert len(want) == 600 and sum(len(w) for w in want) > 700 and max(len(w) for w in want) >= 4
+    g = replay.GpuReplay(tr, strict=True)
+    assert g.touchers == want
+    assert g.collisions == want_col
+    t1 = replay.T1Replay(tr)
+    assert t1.touchers == want
+    g.ctx.close()
+
+
 def test_collision_replay_no_false_positives_on_shipped_worlds(tmp_path):
     """simple.world: 238 tests, none hits (the wander controller keeps clear) - the device must agree"""
     tr = load("simple_120", tmp_path)
@@ -129,6 +145,17 @@ def test_batched_collisions_equal_oracle_at_scale():
     assert (want >= 0).mean() > 0.15 and (want == -1).mean() > 0.15
     floating = want[(idx % 13 == 0) & (idx != 777)]                   # above everything else: can only meet one another
     assert np.all((floating == -1) | (((floating - first_model) // 2) % 13 == 0)) and np.any(floating == -1)
+    # Model::AppendTouchingModels for the same crowd: each parent model's own blocks (not the child's), every
+    # unrelated model met - obstacle or not, whatever its height
+    own = [q[:2] if i % 2 == 0 else q[:1] for i, q in enumerate(queries)]
+    ids, counts = ctx.touching_models(layer, own, max_per_query=24)
+    ctx.sync()
+    n_sets = 0
+    for i in range(0, n, 3):
+        w_ids = t1.touching_models(layer, own[i])
+        assert counts[i] == len(w_ids) and np.array_equal(ids[i, :counts[i]], w_ids), (i, ids[i, :counts[i]], w_ids)
+        n_sets += len(w_ids) > 1
+    assert n_sets > 100 and counts.max() <= 24
     print("collision tests: %d models, %d hit something; device %.2f ms end to end (the call itself %.2f ms), oracle (1 thread, python loop) %.0f ms"
           % (n, int((want >= 0).sum()), 1e3 * dt, 1e3 * t_call, 1e3 * t_cpu))
     ctx.close()

@@ -14,7 +14,7 @@ import replay
 import trace_io
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-TRACES = ["simple_120", "fasr_300", "lsp_test_20", "everything_40", "pioneer_flocking_12", "bumper_150"]
+TRACES = ["simple_120", "fasr_300", "lsp_test_20", "everything_40", "pioneer_flocking_12", "bumper_150", "charger_150"]
 
 
 @pytest.fixture(scope="module", params=TRACES)
@@ -31,6 +31,10 @@ def test_t1_reproduces_every_reference_ray(raw_trace):
     st, _ = oracle_lib.t1_replay(path)
     if name == "bumper_150":  # no sensors: the Model::TestCollision recording (make_golden.py)
         assert st["collision_tests"] == 2100 and st["collision_hits"] > 1500 and st["collision_mismatch"] == 0, st
+        return
+    if name == "charger_150":  # no sensors: the Model::AppendTouchingModels recording (make_golden.py)
+        assert st["toucher_calls"] == 600 and st["toucher_models"] > 700 and st["toucher_mismatch"] == 0, st
+        assert st["collision_tests"] == 2100 and st["collision_mismatch"] == 0, st
         return
     assert st["rays"] > (30000 if name != "lsp_test_20" else 3000) and st["ticks"] >= (20 if name != "pioneer_flocking_12" else 12)
     assert st["model_mismatch"] == 0 and st["collision_mismatch"] == 0

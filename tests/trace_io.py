@@ -7,6 +7,7 @@ import numpy as np
 
 MAGIC = b"STGTRC05"
 EV_MAP, EV_UNMAP, EV_RAYS, EV_TICK, EV_RANGER_SCAN, EV_FIDUCIAL, EV_BLOB, EV_COLLISION = 1, 2, 3, 4, 5, 6, 7, 8
+EV_TOUCHERS = 9
 SCAN_HEADER_DOUBLES = 6
 KIND_RANGER, KIND_UNRELATED, KIND_GRIPPER = 0, 1, 2
 
@@ -60,6 +61,11 @@ class Trace:
         """COLLISION event -> (model, layer, blocks in visiting order, hit model id or -1)"""
         n = int(ev["n_pts"])
         return int(ev["model"]), int(ev["layer"]), self.aux[ev["first"]:ev["first"] + n].astype(np.uint32), int(ev["block"]) - 1
+
+    def touchers(self, ev):
+        """TOUCHERS event -> (model, layer, the model's own blocks, ids of the touching models, ascending)"""
+        n, m, f = int(ev["n_pts"]), int(ev["block"]), int(ev["first"])
+        return int(ev["model"]), int(ev["layer"]), self.aux[f:f + n].astype(np.uint32), self.aux[f + n:f + n + m].astype(np.uint32)
 
     def polygon(self, ev):
         """(n_pts, 2) int32 pixel-space vertices of a MAP event."""
