@@ -188,14 +188,47 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
             r--;
         }
       }
+      // Walk and look-up alternate: the walk tests run after run until one holds an occupied cell and
+      // leaves its loop there; the lanes of the warp that met something in this region then look their
+      // cells up side by side (one wait for the cell-entry sectors instead of one per lane), and a lane
+      // whose cell does not stop it goes back to walking.
+      uint32_t occupied = 0, ahead = 0;
+      int32_t m = 0;
+      bool more = true; // false: the region, or the ray, has ended
       for (;;) {
-        // the mask the walk needs after this run's cross step, requested before this run is tested
-        uint32_t ahead = 0;
-        if (foreign && cp < kRegionWidth - 1)
-          ahead = __ldg(g.occ[0] + (wi + wstep));
-        const int32_t m = min(min(r + 1, kRegionWidth - ap), n); // cells tested: a cell is only tested while n > 0
-        uint32_t occupied = word & ((0xffffffffu >> (32 - m)) << ap);
-        while (occupied) {
+        for (;;) {
+          // the mask the walk needs after this run's cross step, requested before this run is tested
+          ahead = 0;
+          if (foreign && cp < kRegionWidth - 1)
+            ahead = __ldg(g.occ[0] + (wi + wstep));
+          m = min(min(r + 1, kRegionWidth - ap), n); // cells tested: a cell is only tested while n > 0
+          occupied = word & ((0xffffffffu >> (32 - m)) << ap);
+          if (occupied)
+            break;
+          if (kSteps)
+            cell_visits += (uint32_t)m;
+          n -= m;
+          if (m != r + 1) { // cut short by the region edge or by the end of the ray
+            ap += m;
+            E += m * b_run;
+            more = false;
+            break;
+          }
+          // the whole run, then the cross step
+          ap += r;
+          cp += 1;
+          wi += wstep;
+          E += r * b_run - b_cross;
+          if (cp >= kRegionWidth || n <= 0) {
+            more = false;
+            break;
+          }
+          word = ahead ^ ((ahead ^ __brev(ahead)) & revmask);
+          r = rm1 + (int32_t)((uint32_t)(v1 + E) >> 31); // v1 >= -E ? r_max - 1 : r_max
+        }
+        if (!more)
+          break;
+        do {
           const int32_t ah = __ffs(occupied) - 1;
           const uint32_t areal = (uint32_t)ah ^ aflip, creal = (uint32_t)cp ^ cflip;
           const uint32_t hx = ymajor ? creal : areal, hy = ymajor ? areal : creal;
@@ -213,18 +246,18 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
             break;
           }
           occupied &= occupied - 1u; // nothing in that cell stops this ray: look past it
-        }
+        } while (occupied);
         if (hit)
           break;
+        // nothing in this run stops the ray: past it, as above
         if (kSteps)
           cell_visits += (uint32_t)m;
         n -= m;
-        if (m != r + 1) { // cut short by the region edge or by the end of the ray
+        if (m != r + 1) {
           ap += m;
           E += m * b_run;
           break;
         }
-        // the whole run, then the cross step
         ap += r;
         cp += 1;
         wi += wstep;
@@ -232,7 +265,7 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
         if (cp >= kRegionWidth || n <= 0)
           break;
         word = ahead ^ ((ahead ^ __brev(ahead)) & revmask);
-        r = rm1 + (int32_t)((uint32_t)(v1 + E) >> 31); // v1 >= -E ? r_max - 1 : r_max
+        r = rm1 + (int32_t)((uint32_t)(v1 + E) >> 31);
       }
       // bring the double position up to date (world.cc:868-877 did it step by step)
       const int32_t ka = ap - ap0, kc = cp - cp0; // run / cross steps taken in this region
