@@ -81,6 +81,109 @@ __device__ __forceinline__ double seq_add(double x, int32_t k, bool negative)
   return x;
 }
 
+// m bits from bit a on (0 <= a, 1 <= m, a + m <= 32): one BMSK instead of two shifts and their operands
+__device__ __forceinline__ uint32_t run_mask(int32_t a, int32_t m)
+{
+  uint32_t mask;
+  asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(mask) : "r"(a), "r"(m));
+  return mask;
+}
+
+// What the walk of one populated region needs besides its running state.
+struct WalkConst {
+  int32_t b_run, b_cross, rm1, v1, cp_ahead, wstep;
+  uint32_t revmask, aflip, cflip;
+  bool ymajor;
+};
+
+// The walk of one populated region from (ap, cp) with error term E, r run steps to go before the next cross
+// step, `word` the direction-normalised mask of the current row / column and wnext pointing at the next one.
+// Walk and look-up alternate: the walk tests run after run until one holds an occupied cell and leaves its
+// loop there; the lanes of the warp that met something in this region then look their cells up side by side
+// (one wait for the cell-entry sectors instead of one per lane), and a lane whose cell does not stop it goes
+// back to walking. Returns the model that stops the ray (ap, cp = its cell) or -1 when the region or the ray
+// has ended (ap, cp, E as the reference's cell-by-cell loop leaves them). kBounded: the ray may end inside
+// this region, n is kept up to date; otherwise n is not touched.
+template <bool kSteps, bool kBounded>
+__device__ __forceinline__ int32_t walk_region(const GridView &g, const FanRec *fan, bool layer1, uint32_t region, const WalkConst &wc,
+                                               int32_t &ap, int32_t &cp, int32_t &E, int32_t &n, int32_t r, uint32_t word,
+                                               const uint32_t *wnext, uint32_t &cell_visits)
+{
+  uint32_t occupied = 0, ahead = 0;
+  int32_t m = 0;
+  bool more = true; // false: the region, or the ray, has ended
+  for (;;) {
+    for (;;) {
+      // the mask the walk needs after this run's cross step, requested before this run is tested
+      ahead = 0;
+      if (cp < wc.cp_ahead)
+        ahead = __ldg(wnext);
+      m = min(r + 1, kRegionWidth - ap);
+      if (kBounded)
+        m = min(m, n); // cells tested: a cell is only tested while n > 0
+      occupied = word & run_mask(ap, m);
+      if (occupied)
+        break;
+      if (kSteps)
+        cell_visits += (uint32_t)m;
+      if (kBounded)
+        n -= m;
+      if (m != r + 1) { // cut short by the region edge or by the end of the ray
+        ap += m;
+        E += m * wc.b_run;
+        more = false;
+        break;
+      }
+      // the whole run, then the cross step
+      ap += r;
+      cp += 1;
+      wnext += wc.wstep;
+      E += r * wc.b_run - wc.b_cross;
+      if (cp >= kRegionWidth || (kBounded && n <= 0)) {
+        more = false;
+        break;
+      }
+      word = ahead ^ ((ahead ^ __brev(ahead)) & wc.revmask);
+      r = wc.rm1 + (int32_t)((uint32_t)(wc.v1 + E) >> 31); // v1 >= -E ? r_max - 1 : r_max
+    }
+    if (!more)
+      return -1;
+    do {
+      const int32_t ah = __ffs(occupied) - 1;
+      const uint32_t areal = (uint32_t)ah ^ wc.aflip, creal = (uint32_t)cp ^ wc.cflip;
+      const uint32_t hx = wc.ymajor ? creal : areal, hy = wc.ymajor ? areal : creal;
+      const int32_t mdl = resolve_cell(layer1 ? g.slots[1] : g.slots[0], g.slot_mask,
+                                       reinterpret_cast<const uint4 *>(layer1 ? g.blk_rec[1] : g.blk_rec[0]),
+                                       g.mdl_root, fan, (region << (2 * kRBits)) | (hy << kRBits) | hx);
+      if (mdl >= 0) {
+        if (kSteps)
+          cell_visits += (uint32_t)(ah - ap) + 1u;
+        ap = ah;
+        return mdl;
+      }
+      occupied &= occupied - 1u; // nothing in that cell stops this ray: look past it
+    } while (occupied);
+    // nothing in this run stops the ray: past it, as above
+    if (kSteps)
+      cell_visits += (uint32_t)m;
+    if (kBounded)
+      n -= m;
+    if (m != r + 1) {
+      ap += m;
+      E += m * wc.b_run;
+      return -1;
+    }
+    ap += r;
+    cp += 1;
+    wnext += wc.wstep;
+    E += r * wc.b_run - wc.b_cross;
+    if (cp >= kRegionWidth || (kBounded && n <= 0))
+      return -1;
+    word = ahead ^ ((ahead ^ __brev(ahead)) & wc.revmask);
+    r = wc.rm1 + (int32_t)((uint32_t)(wc.v1 + E) >> 31);
+  }
+}
+
 enum : uint32_t { kYMajor = 1u, kRunNeg = 2u, kCrossNeg = 4u, kXNeg = 8u, kYNeg = 16u };
 
 struct RayResult {
@@ -166,12 +269,13 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
       const int32_t cp0 = (int32_t)((uint32_t)(ymajor ? cx0 : cy0) ^ cflip);
       const int32_t ap0 = (int32_t)((uint32_t)(ymajor ? cy0 : cx0) ^ aflip);
       int32_t cp = cp0, ap = ap0;
-      // word index of the current mask; the next mask in the direction of travel is wstep words on
-      uint32_t wi = occ_layer + region * kTileWords + (ymajor ? kRegionWidth : 0) + ((uint32_t)cp ^ cflip);
-      const bool foreign = __ldg(g.reg_owner + region) != finder_tag; // else: nothing here can stop this ray
+      // the NEXT mask in the direction of travel (the current one is wstep words back); wstep words on per cross step
+      const uint32_t *wnext = g.occ[0] + (occ_layer + region * kTileWords + (ymajor ? kRegionWidth : 0) + ((uint32_t)cp ^ cflip)) + (int32_t)wstep;
+      // no masks are read in a region that holds only the finder's own tree: nothing there can stop this ray
+      const int32_t cp_ahead = __ldg(g.reg_owner + region) != finder_tag ? kRegionWidth - 1 : 0; // masks are requested while cp < this
       uint32_t word = 0;
-      if (foreign)
-        word = __ldg(g.occ[0] + wi);
+      if (cp_ahead)
+        word = __ldg(wnext - (int32_t)wstep);
       word ^= (word ^ __brev(word)) & revmask;
       // r = run steps before the next cross step: the smallest r >= 0 with E + r*b_run >= 0. E >= -b_cross
       // always, so r <= r_max. Entering a region E is anywhere in that range (one estimate + fix-up);
@@ -188,84 +292,25 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
             r--;
         }
       }
-      // Walk and look-up alternate: the walk tests run after run until one holds an occupied cell and
-      // leaves its loop there; the lanes of the warp that met something in this region then look their
-      // cells up side by side (one wait for the cell-entry sectors instead of one per lane), and a lane
-      // whose cell does not stop it goes back to walking.
-      uint32_t occupied = 0, ahead = 0;
-      int32_t m = 0;
-      bool more = true; // false: the region, or the ray, has ended
-      for (;;) {
-        for (;;) {
-          // the mask the walk needs after this run's cross step, requested before this run is tested
-          ahead = 0;
-          if (foreign && cp < kRegionWidth - 1)
-            ahead = __ldg(g.occ[0] + (wi + wstep));
-          m = min(min(r + 1, kRegionWidth - ap), n); // cells tested: a cell is only tested while n > 0
-          occupied = word & ((0xffffffffu >> (32 - m)) << ap);
-          if (occupied)
-            break;
-          if (kSteps)
-            cell_visits += (uint32_t)m;
-          n -= m;
-          if (m != r + 1) { // cut short by the region edge or by the end of the ray
-            ap += m;
-            E += m * b_run;
-            more = false;
-            break;
-          }
-          // the whole run, then the cross step
-          ap += r;
-          cp += 1;
-          wi += wstep;
-          E += r * b_run - b_cross;
-          if (cp >= kRegionWidth || n <= 0) {
-            more = false;
-            break;
-          }
-          word = ahead ^ ((ahead ^ __brev(ahead)) & revmask);
-          r = rm1 + (int32_t)((uint32_t)(v1 + E) >> 31); // v1 >= -E ? r_max - 1 : r_max
-        }
-        if (!more)
-          break;
-        do {
-          const int32_t ah = __ffs(occupied) - 1;
-          const uint32_t areal = (uint32_t)ah ^ aflip, creal = (uint32_t)cp ^ cflip;
-          const uint32_t hx = ymajor ? creal : areal, hy = ymajor ? areal : creal;
-          const int32_t mdl = resolve_cell(layer1 ? g.slots[1] : g.slots[0], g.slot_mask,
-                                           reinterpret_cast<const uint4 *>(layer1 ? g.blk_rec[1] : g.blk_rec[0]),
-                                           g.mdl_root, fan, (region << (2 * kRBits)) | (hy << kRBits) | hx);
-          if (mdl >= 0) {
-            hit_model = mdl;
-            hit_x = (ix0 & ~(kRegionWidth - 1)) + (int32_t)hx;
-            hit_y = (iy0 & ~(kRegionWidth - 1)) + (int32_t)hy;
-            if (kSteps)
-              cell_visits += (uint32_t)(ah - ap) + 1u;
-            ap = ah;
-            hit = true;
-            break;
-          }
-          occupied &= occupied - 1u; // nothing in that cell stops this ray: look past it
-        } while (occupied);
-        if (hit)
-          break;
-        // nothing in this run stops the ray: past it, as above
-        if (kSteps)
-          cell_visits += (uint32_t)m;
-        n -= m;
-        if (m != r + 1) {
-          ap += m;
-          E += m * b_run;
-          break;
-        }
-        ap += r;
-        cp += 1;
-        wi += wstep;
-        E += r * b_run - b_cross;
-        if (cp >= kRegionWidth || n <= 0)
-          break;
-        word = ahead ^ ((ahead ^ __brev(ahead)) & revmask);
-        r = rm1 + (int32_t)((uint32_t)(v1 + E) >> 31);
+      // (n counts the cells the ray may still visit; a region holds at most 2 * 32 - 1 of them, so a ray with
+      // more than that left walks the region without looking at n, which is brought up to date afterwards)
+      WalkConst wc;
+      wc.b_run = b_run; wc.b_cross = b_cross; wc.rm1 = rm1; wc.v1 = v1; wc.cp_ahead = cp_ahead;
+      wc.wstep = (int32_t)wstep; wc.revmask = revmask; wc.aflip = aflip; wc.cflip = cflip; wc.ymajor = ymajor;
+      int32_t mdl;
+      if (n >= 2 * kRegionWidth) {
+        mdl = walk_region<kSteps, false>(g, fan, layer1, region, wc, ap, cp, E, n, r, word, wnext, cell_visits);
+        if (mdl < 0)
+          n -= (ap - ap0) + (cp - cp0); // one cell visited per step taken
+      } else {
+        mdl = walk_region<kSteps, true>(g, fan, layer1, region, wc, ap, cp, E, n, r, word, wnext, cell_visits);
+      }
+      if (mdl >= 0) {
+        const uint32_t areal = (uint32_t)ap ^ aflip, creal = (uint32_t)cp ^ cflip;
+        hit_model = mdl;
+        hit_x = (ix0 & ~(kRegionWidth - 1)) + (int32_t)(ymajor ? creal : areal);
+        hit_y = (iy0 & ~(kRegionWidth - 1)) + (int32_t)(ymajor ? areal : creal);
+        hit = true;
       }
       // bring the double position up to date (world.cc:868-877 did it step by step)
       const int32_t ka = ap - ap0, kc = cp - cp0; // run / cross steps taken in this region
