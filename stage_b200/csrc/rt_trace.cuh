@@ -89,6 +89,22 @@ __device__ __forceinline__ uint32_t run_mask(int32_t a, int32_t m)
   return mask;
 }
 
+// Which region holds the position (gx, gy), and Region::count of it (0: no such region, or nothing in it):
+// the reference truncates the double position toward zero (GETSREG / GETREG(double), world.cc:820-821), so cells
+// at -1 < x < 0 alias cell 0.
+__device__ __forceinline__ uint32_t probe_region(const GridView &g, double gx, double gy, int32_t &ix0, int32_t &iy0, uint32_t &region)
+{
+  ix0 = __double2int_rz(gx);
+  iy0 = __double2int_rz(gy);
+  const int32_t rix = (ix0 >> kRBits) - g.rx0, riy = (iy0 >> kRBits) - g.ry0;
+  region = 0;
+  if ((uint32_t)rix < (uint32_t)g.nrx && (uint32_t)riy < (uint32_t)g.nry) {
+    region = (uint32_t)(riy * g.nrx + rix);
+    return __ldg(g.reg_count + region);
+  }
+  return 0;
+}
+
 // What the walk of one populated region needs besides its running state.
 struct WalkConst {
   int32_t b_run, b_cross, rm1, v1, cp_ahead, wstep;
@@ -231,8 +247,6 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
     yjumpx = (yneg ? -(double)kRegionWidth : (double)kRegionWidth) / tana; // world.cc:797
   }
 
-  double xcrossx = 0, xcrossy = 0, ycrossx = 0, ycrossy = 0, distX = 0, distY = 0;
-  bool need_crossings = true;
   int32_t hit_model = -1, hit_x = 0, hit_y = 0;
   uint32_t cell_visits = 0, region_probes = 0;
   const bool layer1 = (fan->layer & 1) != 0;
@@ -253,18 +267,65 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
   while (n > 0) {
     if (kSteps)
       region_probes++;
-    const int32_t ix0 = __double2int_rz(gx), iy0 = __double2int_rz(gy); // GETSREG/GETREG(double), world.cc:820-821
-    const int32_t rix = (ix0 >> kRBits) - g.rx0, riy = (iy0 >> kRBits) - g.ry0;
-    uint32_t region = 0, count = 0;
-    if ((uint32_t)rix < (uint32_t)g.nrx && (uint32_t)riy < (uint32_t)g.nry) {
-      region = (uint32_t)(riy * g.nrx + rix);
-      count = __ldg(g.reg_count + region);
+    int32_t ix0, iy0;
+    uint32_t region;
+    uint32_t count = probe_region(g, gx, gy, ix0, iy0, region);
+    if (!count) {
+      // ---- a stretch of empty regions: jump from region boundary to region boundary (world.cc:884-957) until a
+      // populated region or the end of the ray. The crossing state is set up at the first of them (the
+      // reference's calculatecrossings, true after every populated region) and lives only here.
+      double xcrossx, xcrossy, ycrossx, ycrossy, distX, distY;
+      {
+        double regionx = (double)(ix0 / kRegionWidth * kRegionWidth);
+        double regiony = (double)(iy0 / kRegionWidth * kRegionWidth);
+        if ((gx < 0) && (ix0 % kRegionWidth))
+          regionx -= kRegionWidth;
+        if ((gy < 0) && (iy0 % kRegionWidth))
+          regiony -= kRegionWidth;
+        const double xdx = (flags & kXNeg) ? regionx - gx - 1.0 : regionx + kRegionWidth - gx;
+        const double xdy = xdx * tana;
+        const double ydy = (flags & kYNeg) ? regiony - gy - 1.0 : regiony + kRegionWidth - gy;
+        const double ydx = ydy / tana;
+        xcrossx = gx + xdx;
+        xcrossy = gy + xdy;
+        ycrossx = gx + ydx;
+        ycrossy = gy + ydy;
+        distX = fabs(xdx) + fabs(xdy);
+        distY = fabs(ydx) + fabs(ydy);
+      }
+      do {
+        if (distX < distY) {
+          gx = xcrossx;
+          gy = xcrossy;
+          n = __double2int_rz((double)n - distX); // int -= double, world.cc:931
+          // xjumpx = sx*32, xjumpy = sx*32*tana (a power-of-two scaling, exact), world.cc:795-796
+          const double xjumpy = ((flags & kXNeg) ? -(double)kRegionWidth : (double)kRegionWidth) * tana;
+          xcrossx += (flags & kXNeg) ? -(double)kRegionWidth : (double)kRegionWidth;
+          xcrossy += xjumpy;
+          distY -= distX;
+          distX = (double)kRegionWidth + fabs(xjumpy); // xjumpdist, world.cc:801
+        } else {
+          gx = ycrossx;
+          gy = ycrossy;
+          n = __double2int_rz((double)n - distY);
+          ycrossx += yjumpx;
+          ycrossy += (flags & kYNeg) ? -(double)kRegionWidth : (double)kRegionWidth;
+          distX -= distY;
+          distY = fabs(yjumpx) + (double)kRegionWidth; // yjumpdist, world.cc:802
+        }
+        if (n <= 0)
+          break;
+        if (kSteps)
+          region_probes++;
+        count = probe_region(g, gx, gy, ix0, iy0, region);
+      } while (!count);
+      if (n <= 0)
+        break;
     }
-    if (count) {
+    {
       // ---- populated region: integer walk over the occupancy masks (world.cc:823-882) ----
       // Both in-region coordinates are counted in the direction of travel: ap along the run axis
       // (bit ap of the direction-normalised mask), cp along the cross axis (mask number cp ^ cflip).
-      need_crossings = true;
       const int32_t cx0 = ix0 & (kRegionWidth - 1), cy0 = iy0 & (kRegionWidth - 1);
       const int32_t cp0 = (int32_t)((uint32_t)(ymajor ? cx0 : cy0) ^ cflip);
       const int32_t ap0 = (int32_t)((uint32_t)(ymajor ? cy0 : cx0) ^ aflip);
@@ -318,49 +379,8 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
       gy = seq_add(gy, ymajor ? ka : kc, yneg);
       if (hit)
         break;
-    } else {
-      // ---- empty region: jump to the next region boundary (world.cc:884-957) ----
-      if (need_crossings) {
-        need_crossings = false;
-        double regionx = (double)(ix0 / kRegionWidth * kRegionWidth);
-        double regiony = (double)(iy0 / kRegionWidth * kRegionWidth);
-        if ((gx < 0) && (ix0 % kRegionWidth))
-          regionx -= kRegionWidth;
-        if ((gy < 0) && (iy0 % kRegionWidth))
-          regiony -= kRegionWidth;
-        const double xdx = (flags & kXNeg) ? regionx - gx - 1.0 : regionx + kRegionWidth - gx;
-        const double xdy = xdx * tana;
-        const double ydy = (flags & kYNeg) ? regiony - gy - 1.0 : regiony + kRegionWidth - gy;
-        const double ydx = ydy / tana;
-        xcrossx = gx + xdx;
-        xcrossy = gy + xdy;
-        ycrossx = gx + ydx;
-        ycrossy = gy + ydy;
-        distX = fabs(xdx) + fabs(xdy);
-        distY = fabs(ydx) + fabs(ydy);
-      }
-      if (distX < distY) {
-        gx = xcrossx;
-        gy = xcrossy;
-        n = __double2int_rz((double)n - distX); // int -= double, world.cc:931
-        // xjumpx = sx*32, xjumpy = sx*32*tana (a power-of-two scaling, exact), world.cc:795-796
-        const double xjumpy = ((flags & kXNeg) ? -(double)kRegionWidth : (double)kRegionWidth) * tana;
-        xcrossx += (flags & kXNeg) ? -(double)kRegionWidth : (double)kRegionWidth;
-        xcrossy += xjumpy;
-        distY -= distX;
-        distX = (double)kRegionWidth + fabs(xjumpy); // xjumpdist, world.cc:801
-      } else {
-        gx = ycrossx;
-        gy = ycrossy;
-        n = __double2int_rz((double)n - distY);
-        ycrossx += yjumpx;
-        ycrossy += (flags & kYNeg) ? -(double)kRegionWidth : (double)kRegionWidth;
-        distX -= distY;
-        distY = fabs(yjumpx) + (double)kRegionWidth; // yjumpdist, world.cc:802
-      }
     }
   }
-
 
   res.range = fan->range;
   if (hit) { // world.cc:856-859
