@@ -244,6 +244,31 @@ def run_reference(args):
 # this repo's path
 # ---------------------------------------------------------------------------------------------
 
+def pin_to_gpu_numa(local_rank):
+    """Restrict this process to the CPUs of the NUMA node the GPU is attached to; returns the node or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pci = pynvml.nvmlDeviceGetPciInfo(hnd).busId
+        pci = pci.decode() if isinstance(pci, bytes) else pci
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % pci.lower()[-12:]).read())
+        if node < 0:
+            return None
+        cpus = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+        ids = []
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(ids) & os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -258,28 +283,11 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if n_gpus > 1:
-        # keep each rank (and the page-locked result buffers it first-touches) on the NUMA node its GPU
-        # hangs off: the results travel GPU -> host every tick and cross-socket hops cost bandwidth
-        try:
-            bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
-            import pynvml
-            pynvml.nvmlInit()
-            hnd = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
-            pci = pynvml.nvmlDeviceGetPciInfo(hnd).busId
-            pci = pci.decode() if isinstance(pci, bytes) else pci
-            node = int(open("/sys/bus/pci/devices/%s/numa_node" % pci.lower()[-12:]).read())
-            if node >= 0:
-                cpus = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
-                ids = []
-                for part in cpus.split(","):
-                    a, _, b = part.partition("-")
-                    ids += list(range(int(a), int(b or a) + 1))
-                allowed = sorted(set(ids) & os.sched_getaffinity(0))
-                if allowed:
-                    os.sched_setaffinity(0, allowed)
-        except Exception:
-            pass
+    # keep the process (and the page-locked result buffers it first-touches) on the NUMA node its GPU hangs off:
+    # the results travel GPU -> host every tick and a cross-socket hop costs bandwidth (matters on multi-socket hosts;
+    # a no-op on a single-node box)
+    affinity0 = os.sched_getaffinity(0)
+    numa_node = pin_to_gpu_numa(local_rank)
     if n_gpus > 1:
         # NCCL prints its version banner on stdout when the communicator is created; stdout must carry
         # nothing but the JSON line, so it is pointed at stderr until the first collective is through
@@ -426,6 +434,7 @@ def run_ours(args):
     # ---- CPU baseline + parity of the last e2e tick against the unmodified reference ----------
     cpu = None
     parity = None
+    os.sched_setaffinity(0, affinity0)  # the reference gets every host core
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline and args.workload == "c3":
         threads = args.cpu_threads or os.cpu_count()
         sample_fans = fans0
@@ -479,7 +488,8 @@ def run_ours(args):
             "metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": t_value_ms / args.steps,
             "ticks_per_s": args.steps / (t_value_ms * 1e-3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_gpus),
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(args, n_gpus), host_numa_node=numa_node),
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": 1e3 * t_e2e / args.steps,
                     "ticks_per_s": args.steps / t_e2e,
                     "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // args.steps,

@@ -107,13 +107,14 @@ __device__ __forceinline__ uint32_t probe_region(const GridView &g, double gx, d
 
 // What the walk of one populated region needs besides its running state.
 struct WalkConst {
-  int32_t b_run, b_cross, rm1, v1, cp_ahead, wstep;
+  int32_t b_run, b_cross, rm1, v1, cp_ahead;
   uint32_t revmask, aflip, cflip;
   bool ymajor;
 };
 
 // The walk of one populated region from (ap, cp) with error term E, r run steps to go before the next cross
-// step, `word` the direction-normalised mask of the current row / column and wnext pointing at the next one.
+// step, `word` the direction-normalised mask of the current row / column; `tile` = word index of the region's
+// row (column) masks in GridView::occ, a multiple of 32: mask number (cp ^ cflip) belongs to cross coordinate cp.
 // Walk and look-up alternate: the walk tests run after run until one holds an occupied cell and leaves its
 // loop there; the lanes of the warp that met something in this region then look their cells up side by side
 // (one wait for the cell-entry sectors instead of one per lane), and a lane whose cell does not stop it goes
@@ -123,7 +124,7 @@ struct WalkConst {
 template <bool kSteps, bool kBounded>
 __device__ __forceinline__ int32_t walk_region(const GridView &g, const FanRec *fan, bool layer1, uint32_t region, const WalkConst &wc,
                                                int32_t &ap, int32_t &cp, int32_t &E, int32_t &n, int32_t r, uint32_t word,
-                                               const uint32_t *wnext, uint32_t &cell_visits)
+                                               uint32_t tile, uint32_t &cell_visits)
 {
   uint32_t occupied = 0, ahead = 0;
   int32_t m = 0;
@@ -133,7 +134,7 @@ __device__ __forceinline__ int32_t walk_region(const GridView &g, const FanRec *
       // the mask the walk needs after this run's cross step, requested before this run is tested
       ahead = 0;
       if (cp < wc.cp_ahead)
-        ahead = __ldg(wnext);
+        ahead = __ldg(g.occ[0] + (tile | ((uint32_t)(cp + 1) ^ wc.cflip))); // one LOP3, one wide multiply-add
       m = min(r + 1, kRegionWidth - ap);
       if (kBounded)
         m = min(m, n); // cells tested: a cell is only tested while n > 0
@@ -153,7 +154,6 @@ __device__ __forceinline__ int32_t walk_region(const GridView &g, const FanRec *
       // the whole run, then the cross step
       ap += r;
       cp += 1;
-      wnext += wc.wstep;
       E += r * wc.b_run - wc.b_cross;
       if (cp >= kRegionWidth || (kBounded && n <= 0)) {
         more = false;
@@ -191,7 +191,6 @@ __device__ __forceinline__ int32_t walk_region(const GridView &g, const FanRec *
     }
     ap += r;
     cp += 1;
-    wnext += wc.wstep;
     E += r * wc.b_run - wc.b_cross;
     if (cp >= kRegionWidth || (kBounded && n <= 0))
       return -1;
@@ -256,7 +255,7 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
   const bool ymajor = (flags & kYMajor) != 0, runneg = (flags & kRunNeg) != 0;
   const bool xneg = (flags & kXNeg) != 0, yneg = (flags & kYNeg) != 0;
   const uint32_t aflip = runneg ? kRegionWidth - 1 : 0u, cflip = (flags & kCrossNeg) ? kRegionWidth - 1 : 0u;
-  const uint32_t wstep = (flags & kCrossNeg) ? ~0u : 1u, revmask = runneg ? ~0u : 0u;
+  const uint32_t revmask = runneg ? ~0u : 0u;
   const int32_t rm1 = r_max - 1;
   const uint32_t occ_layer = layer1 ? (uint32_t)(g.occ[1] - g.occ[0]) : 0u; // one allocation, rt_api.cu
   // The tag of the regions this ray cannot be stopped in (GridView::reg_owner): regions that hold nothing but
@@ -330,13 +329,14 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
       const int32_t cp0 = (int32_t)((uint32_t)(ymajor ? cx0 : cy0) ^ cflip);
       const int32_t ap0 = (int32_t)((uint32_t)(ymajor ? cy0 : cx0) ^ aflip);
       int32_t cp = cp0, ap = ap0;
-      // the NEXT mask in the direction of travel (the current one is wstep words back); wstep words on per cross step
-      const uint32_t *wnext = g.occ[0] + (occ_layer + region * kTileWords + (ymajor ? kRegionWidth : 0) + ((uint32_t)cp ^ cflip)) + (int32_t)wstep;
+      // the region's row masks (x-major rays) or column masks (y-major); mask number (cp ^ cflip) belongs to cp
+      uint32_t tile = occ_layer + region * kTileWords + (ymajor ? kRegionWidth : 0);
+      asm volatile("" : "+r"(tile)); // one register to keep, not five instructions to redo in every run
       // no masks are read in a region that holds only the finder's own tree: nothing there can stop this ray
       const int32_t cp_ahead = __ldg(g.reg_owner + region) != finder_tag ? kRegionWidth - 1 : 0; // masks are requested while cp < this
       uint32_t word = 0;
       if (cp_ahead)
-        word = __ldg(wnext - (int32_t)wstep);
+        word = __ldg(g.occ[0] + (tile | ((uint32_t)cp ^ cflip)));
       word ^= (word ^ __brev(word)) & revmask;
       // r = run steps before the next cross step: the smallest r >= 0 with E + r*b_run >= 0. E >= -b_cross
       // always, so r <= r_max. Entering a region E is anywhere in that range (one estimate + fix-up);
@@ -357,14 +357,14 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
       // more than that left walks the region without looking at n, which is brought up to date afterwards)
       WalkConst wc;
       wc.b_run = b_run; wc.b_cross = b_cross; wc.rm1 = rm1; wc.v1 = v1; wc.cp_ahead = cp_ahead;
-      wc.wstep = (int32_t)wstep; wc.revmask = revmask; wc.aflip = aflip; wc.cflip = cflip; wc.ymajor = ymajor;
+      wc.revmask = revmask; wc.aflip = aflip; wc.cflip = cflip; wc.ymajor = ymajor;
       int32_t mdl;
       if (n >= 2 * kRegionWidth) {
-        mdl = walk_region<kSteps, false>(g, fan, layer1, region, wc, ap, cp, E, n, r, word, wnext, cell_visits);
+        mdl = walk_region<kSteps, false>(g, fan, layer1, region, wc, ap, cp, E, n, r, word, tile, cell_visits);
         if (mdl < 0)
           n -= (ap - ap0) + (cp - cp0); // one cell visited per step taken
       } else {
-        mdl = walk_region<kSteps, true>(g, fan, layer1, region, wc, ap, cp, E, n, r, word, wnext, cell_visits);
+        mdl = walk_region<kSteps, true>(g, fan, layer1, region, wc, ap, cp, E, n, r, word, tile, cell_visits);
       }
       if (mdl >= 0) {
         const uint32_t areal = (uint32_t)ap ^ aflip, creal = (uint32_t)cp ^ cflip;

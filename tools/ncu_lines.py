@@ -38,7 +38,7 @@ def main():
     rows = page(rep, "--page", "source", "--print-source", "cuda,sass")
     cur, hdr, line, agg = None, None, None, {}
     for r in rows:
-        if r and r[0] == "File Name":
+        if r and r[0] in ("File Name", "File Path"):
             cur, hdr = r[1].split("/")[-1], None
         elif r and r[0] == "Line No":
             hdr = r
