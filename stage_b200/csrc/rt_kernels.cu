@@ -421,15 +421,58 @@ void launch_rehash(const unsigned long long *src, unsigned long long *dst, uint3
 // depend on its entry state. At least one more link becomes certain per round (at most 32 rounds,
 // the serial cost); 2-5 rounds are typical, the extra ones where a fan sweeps through binade
 // borders (|a| = 2, 1, 1/2, ... and the sign change).
-__device__ __forceinline__ float ranger_chunk(bool first_lane, double oa, float entry, double incr, uint32_t steps)
+// kKeep: the chunk's values fa(t0 .. t0 + steps) are left in `keep` (shared memory) for the coalesced write-out.
+template <bool kKeep>
+__device__ __forceinline__ float ranger_chunk(bool first_lane, double oa, float entry, double incr, uint32_t steps, float *keep)
 {
   double a = first_lane ? oa : (double)entry + incr;
   float fa = entry; // an empty chunk hands its entry state on
   for (uint32_t i = 0; i < steps; i++) {
     fa = (float)a;
+    if (kKeep)
+      keep[i] = fa;
     a = (double)fa + incr;
   }
   return fa;
+}
+
+constexpr uint32_t kHeadingsKeep = 2048; // fans up to this many samples keep their chain in shared memory
+
+// A first guess of fa(T), good enough to be right almost always (the link verification below decides): while fa
+// stays inside one float binade, with ulp u, every step adds the same d = incr rounded to a multiple of u (fa is a
+// multiple of u, so RN_float(fa + incr) = fa + d), and the guess jumps to the last value inside the binade in one
+// go; the step that leaves the binade is taken as the recurrence takes it. A 270-degree fan passes through some
+// twenty binades (|a| = 2, 1, 1/2 ... on either side of 0), so this costs twenty short iterations instead of the
+// one round of the verification loop per binade border that the ideal sweep oa + T * incr used to cost.
+__device__ __forceinline__ float guess_fa(double oa, double incr, uint32_t T)
+{
+  float f = (float)oa;
+  uint32_t t = 0;
+  for (int iter = 0; iter < 96 && t < T; iter++) {
+    const uint32_t eb = (__float_as_uint(f) >> 23) & 0xffu;
+    if (eb > 1u && eb < 0xffu && incr > 0.0) {
+      const double u = __hiloint2double((int)((eb - 150u + 1023u) << 20), 0); // 2^(eb - 127 - 23)
+      const double d = rint(incr / u) * u;
+      if (d == 0.0)
+        return f; // incr is below half an ulp: fa never moves again
+      const double fd = (double)f;
+      double k_in; // steps whose result is still inside this binade
+      if (f > 0.0f)
+        k_in = ceil((ldexp(u, 24) - fd) / d) - 1.0; // first k with fd + k d >= 2^(eb - 126)
+      else
+        k_in = floor((-ldexp(u, 23) - fd) / d); // last k with fd + k d <= -2^(eb - 127)
+      if (k_in >= 1.0) {
+        const uint32_t k = (uint32_t)fmin(k_in, (double)(T - t));
+        f = (float)(fd + (double)k * d);
+        t += k;
+      }
+    }
+    if (t < T) { // the step that leaves the binade (or any step near zero), as the recurrence takes it
+      f = (float)((double)f + incr);
+      t++;
+    }
+  }
+  return f;
 }
 
 __global__ void __launch_bounds__(32) k2_fan_headings(FanBatchView b)
@@ -439,16 +482,19 @@ __global__ void __launch_bounds__(32) k2_fan_headings(FanBatchView b)
   const uint32_t first = b.fan_first_beam[f], n = fan.n_samples;
   double *heading = b.heading + first;
   double *bearing = b.bearings ? b.bearings + first : nullptr;
+  __shared__ float chain[kHeadingsKeep];
   if (fan.angles == 0 /* STG_RT_ANGLES_RANGER */) {
     const uint32_t nm1 = n - 1u; // unsigned, like std::max(sample_count - 1, 1u)
     const double incr = fan.fov / (double)(nm1 > 1u ? nm1 : 1u);
     const double start = n > 1 ? -fan.fov / 2.0 : 0.0;
     const uint32_t chunk = (n + 31u) / 32u;
+    const bool keep = n <= kHeadingsKeep;
     const uint32_t t0 = min(lane * chunk, n), t1 = min(t0 + chunk, n); // this lane's beams
-    // entry state fa(t0 - 1): first guess from the ideal sweep (lane 0 starts from origin.a itself)
-    float entry = t0 > 0 ? (float)(fan.oa + (double)(t0 - 1u) * incr) : 0.0f;
+    // entry state fa(t0 - 1): first guess binade by binade (lane 0 starts from origin.a itself)
+    float entry = t0 > 0 ? guess_fa(fan.oa, incr, t0 - 1u) : 0.0f;
     for (int round = 0; round < 33; round++) {
-      const float exit = ranger_chunk(lane == 0, fan.oa, entry, incr, t1 - t0);
+      const float exit = keep ? ranger_chunk<true>(lane == 0, fan.oa, entry, incr, t1 - t0, chain + t0)
+                              : ranger_chunk<false>(lane == 0, fan.oa, entry, incr, t1 - t0, nullptr);
       const float next_entry = __shfl_down_sync(0xffffffffu, entry, 1);
       const bool link_ok = lane == 31 || __float_as_uint(exit) == __float_as_uint(next_entry);
       const uint32_t broken = __ballot_sync(0xffffffffu, !link_ok);
@@ -473,12 +519,24 @@ __global__ void __launch_bounds__(32) k2_fan_headings(FanBatchView b)
     // simpleNoise() * 0.5 - the noise term is exactly 0 without jitter, as there
     const double jitter = b.noise ? b.noise[f].angle_noise : 0.0;
     const unsigned long long seed = b.noise ? (b.noise[f].seed ? b.noise[f].seed : fan.finder + 1ull) : 0ull;
-    double a = lane == 0 ? fan.oa : (double)entry + incr;
-    for (uint32_t t = t0; t < t1; t++) {
-      const float fa = (float)a;
-      heading[t] = jitter != 0.0 ? (double)(float)(a + incr * jitter * noise_simple(noise_bits(seed, first + t, b.noise_epoch, 0)) * 0.5)
-                                 : (double)fa;
-      a = (double)fa + incr;
+    if (keep) { // the verified chain is in shared memory: write it out a warp-wide line at a time
+      __syncwarp();
+      for (uint32_t t = lane; t < n; t += 32) {
+        if (jitter != 0.0) {
+          const double a = t == 0 ? fan.oa : (double)chain[t - 1] + incr;
+          heading[t] = (double)(float)(a + incr * jitter * noise_simple(noise_bits(seed, first + t, b.noise_epoch, 0)) * 0.5);
+        } else {
+          heading[t] = (double)chain[t];
+        }
+      }
+    } else {
+      double a = lane == 0 ? fan.oa : (double)entry + incr;
+      for (uint32_t t = t0; t < t1; t++) {
+        const float fa = (float)a;
+        heading[t] = jitter != 0.0 ? (double)(float)(a + incr * jitter * noise_simple(noise_bits(seed, first + t, b.noise_epoch, 0)) * 0.5)
+                                   : (double)fa;
+        a = (double)fa + incr;
+      }
     }
     if (bearing)
       for (uint32_t t = lane; t < n; t += 32)
