@@ -5,7 +5,7 @@ reference World can never be destroyed.
     python tests/golden/make_golden.py [name ...]
 
 Each trace records every Block::Map / Block::UnMap / World::Raytrace / ModelRanger::Sensor::Update /
-ModelFiducial::Update / ModelBlobfinder::Update / Model::TestCollision the reference performed
+ModelFiducial::Update / ModelBlobfinder::Update / Model::TestCollision / Model::AppendTouchingModels the reference performed
 (format: oracle/trace_format.h), compressed with xz.
 
 everything_40 is worlds/everything.world (hospital section bitmap, pioneers with 16 sonars, SICK lasers, fiducial
