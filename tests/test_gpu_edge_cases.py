@@ -206,6 +206,21 @@ def test_api_errors_and_empty_calls():
     out = p.ctx.trace(fans)
     assert len(out.ranges) == 5
     p.ctx.sync()
+    # touching models / collision tests: unknown blocks are refused, empty batches and empty queries are fine
+    with pytest.raises(rt.StgRtError) as e:
+        p.ctx.touching_models(0, [[55]])
+    assert e.value.code == -1
+    with pytest.raises(rt.StgRtError) as e:
+        p.ctx.collisions_test(0, [[55]])
+    assert e.value.code == -1
+    ids, counts = p.ctx.touching_models(0, [])
+    assert ids.shape == (0, 32) and len(counts) == 0
+    p.model(2, 2)
+    p.ctx.block_map(1, 2, 0, 0, 1, box(3, 3, 9, 9))               # crosses block 0's outline
+    p.ctx.block_map(2, 2, 1, 0, 1, box(100, 100, 105, 105))       # mapped on the other layer only
+    ids, counts = p.ctx.touching_models(0, [[0], [], [2], [1, 0]], max_per_query=1)
+    p.ctx.sync()
+    assert list(counts) == [1, 0, 0, 2] and ids[0, 0] == 2      # count says 2 where only one id fits
     p.ctx.close()
 
 
