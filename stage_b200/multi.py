@@ -6,6 +6,12 @@ Each rank serialises the deltas its own robots produced into a fixed-size slot
 in the CPU tests) and every rank applies all slots, in rank order, straight out of the gathered
 buffer (stg_rt_delta_apply_gathered -> K1). Rank order makes every replica - and a single-GPU run
 that issues the same maps rank by rank - hold the same cell lists.
+
+Fiducial finders (BASELINE config 4) need one more thing on every rank: the poses of ALL models that carry a
+fiducial, not only the rank's own (World::models_with_fiducials, world.cc:623-629, is world-wide). They ride in a
+second all-gather of fixed-size records (TargetExchange): every rank contributes its own robots' stg_rt_fid_target
+records and gets the world's, in rank order - which is model-id order for contiguous shards, the order the
+reference visits candidates in (ascending Model*, model_fiducial.cc:245-283).
 """
 import numpy as np
 
@@ -50,3 +56,41 @@ class DeltaExchange:
         else:
             self.gathered.copy_(mine)
         self.ctx.delta_apply_gathered(self.gathered.data_ptr(), self.world_size, self.slot)
+
+
+class TargetExchange:
+    """The per-tick all-gather of fiducial target records (stg_rt_fid_target, 72 bytes each). Shards may differ in
+    size: every rank's share is padded to `max_per_rank` records, the true counts travel in a small header gather."""
+
+    def __init__(self, rank, world_size, max_per_rank, record_dtype, dist=None, device="cuda"):
+        import torch
+        self.rank, self.world_size, self.dist, self.device = rank, world_size, dist, device
+        self.dtype = np.dtype(record_dtype)
+        self.cap = int(max_per_rank)
+        self.mine = torch.zeros(self.cap * self.dtype.itemsize, dtype=torch.uint8, device=device)
+        self.all = torch.zeros(world_size * self.cap * self.dtype.itemsize, dtype=torch.uint8, device=device)
+        self.count = torch.zeros(1, dtype=torch.int64, device=device)
+        self.counts = torch.zeros(world_size, dtype=torch.int64, device=device)
+        self.bytes_sent = 0
+
+    def step(self, my_targets):
+        """my_targets: this rank's records (numpy, record_dtype) -> every rank's, concatenated in rank order"""
+        import torch
+        my_targets = np.ascontiguousarray(my_targets, self.dtype)
+        n = len(my_targets)
+        if n > self.cap:
+            raise ValueError("%d target records exceed the exchange slot of %d" % (n, self.cap))
+        raw = torch.from_numpy(my_targets.view(np.uint8).reshape(-1))
+        self.mine[:raw.numel()].copy_(raw)
+        self.count[0] = n
+        self.bytes_sent += raw.numel()
+        if self.world_size > 1:
+            self.dist.all_gather_into_tensor(self.counts, self.count)
+            self.dist.all_gather_into_tensor(self.all, self.mine)
+        else:
+            self.counts.copy_(self.count)
+            self.all.copy_(self.mine)
+        counts = self.counts.cpu().numpy()
+        flat = self.all.cpu().numpy().reshape(self.world_size, self.cap * self.dtype.itemsize)
+        parts = [flat[r, :int(counts[r]) * self.dtype.itemsize].view(self.dtype) for r in range(self.world_size)]
+        return np.concatenate(parts) if parts else np.zeros(0, self.dtype)

@@ -6,7 +6,11 @@ Robots are sharded over the ranks; every tick each rank re-rasterises its own ro
 all-gathered over NCCL and applied on every rank. Checks, against the T1 oracle fed the same maps in
 rank order: (1) every rank's device grid equals the oracle's cell for cell (both layers, list order,
 region counts) after several ticks; (2) each rank's shard of laser fans matches the oracle bit for
-bit (strict trig). Prints one line per rank and exits non-zero on any mismatch."""
+bit (strict trig); (3) every robot is a fiducial and carries a finder: the ranks all-gather the target records
+(multi.TargetExchange) and each rank's finders, run against the world's targets on the replicated grid, report the
+fiducials the oracle reports (targets, ids, order; ranges to 1e-9). Prints one line per rank and exits non-zero on
+any mismatch."""
+import ctypes
 import os
 import sys
 
@@ -39,6 +43,12 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     worldgen.load_into_context(ctx, w)
     ex = multi.DeltaExchange(ctx, rank, world_size, dist=dist)
+    tex = multi.TargetExchange(rank, world_size, max_per_rank=(n_robots + world_size - 1) // world_size,
+                               record_dtype=rt.FID_TARGET_DTYPE, dist=dist)
+    L = oracle_lib.t1()
+    L.t1_fiducial_update.restype = ctypes.c_uint32
+    L.t1_fiducial_update.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
+    fid_ok, fid_seen = True, 0
 
     # the oracle sees the same calls: initial load, then per tick every rank's remaps in rank order
     t1 = oracle_lib.T1World(w.ppm)
@@ -81,13 +91,38 @@ def main():
             if not (np.array_equal(g.ranges[sl].view(np.uint64), rg.view(np.uint64)) and
                     np.array_equal(g.hit_model[sl], hits["hit_model"])):
                 ok = False
+        # fiducials: this rank's robots as targets go round, its finders look at everybody's
+        mine_t = np.zeros(hi - lo, rt.FID_TARGET_DTYPE)
+        mine_t["model"], mine_t["fiducial_return"] = w.robot_ids[lo:hi], 1 + np.arange(lo, hi) % 7
+        mine_t["x"], mine_t["y"], mine_t["a"] = poses[lo:hi, 0], poses[lo:hi, 1], poses[lo:hi, 2] * (np.pi / 180)
+        mine_t["sx"], mine_t["sy"], mine_t["sz"] = w.robot_size
+        targets = tex.step(mine_t)
+        assert len(targets) == n_robots and np.array_equal(targets["model"], w.robot_ids)
+        finders = np.zeros(hi - lo, rt.FID_FINDER_DTYPE)
+        finders["finder"], finders["layer"] = w.robot_ids[lo:hi], (t + 1) % 2
+        for k, col in (("x", 0), ("y", 1)):
+            finders[k] = finders["o" + k] = poses[lo:hi, col]
+        finders["a"] = finders["oa"] = poses[lo:hi, 2] * (np.pi / 180)
+        finders["oz"], finders["max_range_anon"], finders["max_range_id"], finders["fov"] = 0.3, 8.0, 5.0, np.pi
+        out_f, cnt_f = ctx.fiducials_submit(targets, finders, max_per_finder=32)
+        ctx.sync()
+        for i in range(hi - lo):
+            ref = np.zeros(32, rt.FIDUCIAL_DTYPE)
+            f1 = np.ascontiguousarray(finders[i:i + 1])
+            n = L.t1_fiducial_update(t1.h, len(targets), targets.ctypes.data, f1.ctypes.data, 32, ref.ctypes.data)
+            fid_seen += int(n)
+            if not (n == cnt_f[i] and np.array_equal(out_f[i, :n]["target"], ref[:n]["target"]) and
+                    np.array_equal(out_f[i, :n]["id"], ref[:n]["id"]) and
+                    np.max(np.abs(out_f[i, :n]["range"] - ref[:n]["range"]), initial=0) <= 1e-9):
+                fid_ok = False
+    ok = ok and fid_ok and fid_seen > 0
     rec_g, cnt_g = ctx.grid_dump()
     rec_o, cnt_o = t1.dump_grid()
     grid_ok = np.array_equal(oracle_lib.sort_grid(rec_g), rec_o) and np.array_equal(oracle_lib.sort_counts(cnt_g), cnt_o)
     flag = torch.tensor([int(ok and grid_ok)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    print("rank %d/%d: rays %s, grid %s (%d entries), exported %d delta bytes" % (
-        rank, world_size, "ok" if ok else "MISMATCH", "ok" if grid_ok else "MISMATCH", len(rec_g), ex.bytes_exported), flush=True)
+    print("rank %d/%d: rays + fiducials %s (%d fiducials seen by this rank's finders), grid %s (%d entries), exported %d delta bytes, %d target bytes" % (
+        rank, world_size, "ok" if ok else "MISMATCH", fid_seen, "ok" if grid_ok else "MISMATCH", len(rec_g), ex.bytes_exported, tex.bytes_sent), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)

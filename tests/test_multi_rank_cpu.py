@@ -89,3 +89,54 @@ def test_delta_exchange_over_gloo_two_ranks():
             assert np.array_equal(a0[tick, rank, :n], want.astype(np.uint8))
             assert not a0[tick, rank, n:].any()
     assert got[0][1] == sum(100 + t for t in (1, 2, 3)) and got[1][1] == sum(110 + t for t in (1, 2, 3))
+
+
+REC = np.dtype([("model", "<u4"), ("ret", "<i4"), ("key", "<i4"), ("pad", "<u4"), ("pose", "<f8", (4,)), ("size", "<f8", (3,))])
+assert REC.itemsize == 72  # stg_rt_fid_target
+
+
+def _target_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ex = multi.TargetExchange(rank, world, max_per_rank=6, record_dtype=REC, dist=dist, device="cpu")
+    got = []
+    for tick in range(3):
+        lo, hi = multi.shard_bounds(11, rank, world)  # 11 robots over 2 ranks: shards of 6 and 5
+        mine = np.zeros(hi - lo, REC)
+        mine["model"] = 100 + np.arange(lo, hi)
+        mine["ret"] = tick + 1
+        mine["pose"][:, 0] = np.arange(lo, hi) + 0.25 * tick
+        got.append(ex.step(mine))
+    q.put((rank, [g.tobytes() for g in got], ex.bytes_sent))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_target_exchange_over_gloo_two_ranks_uneven_shards():
+    """Fiducial target records of every rank reach every rank, in rank (= model id) order, shards of unequal size."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    procs = [ctxm.Process(target=_target_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(2):
+        rank, blobs, nbytes = q.get(timeout=120)
+        got[rank] = ([np.frombuffer(b, REC) for b in blobs], nbytes)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for tick in range(3):
+        a, b = got[0][0][tick], got[1][0][tick]
+        assert a.tobytes() == b.tobytes() and len(a) == 11
+        assert np.array_equal(a["model"], 100 + np.arange(11)) and np.all(a["ret"] == tick + 1)
+        assert np.array_equal(a["pose"][:, 0], np.arange(11) + 0.25 * tick)
+    assert got[0][1] == 3 * 6 * 72 and got[1][1] == 3 * 5 * 72
+    with pytest.raises(ValueError):
+        multi.TargetExchange(0, 1, 2, REC, device="cpu").step(np.zeros(3, REC))
+    one = multi.TargetExchange(0, 1, 4, REC, device="cpu").step(np.zeros(3, REC))  # a single rank gets its own back
+    assert len(one) == 3
