@@ -74,34 +74,12 @@ __global__ void __launch_bounds__(128, STG_MARCH_CTAS_PER_SM) k2_ray_march(GridV
       r.range = r.range + r.range * nz.range_noise * u + gauss;
     }
   }
-#ifdef STG_MARCH_BLOCK_EPILOGUE
-  // The three per-beam results a caller takes every tick leave the block together: when they go straight to
-  // page-locked host memory (rt_api.cu) the stores of a whole block reach the PCIe write path as one burst.
-  __shared__ double s_range[128], s_intens[128];
-  __shared__ int32_t s_model[128];
-  const bool whole_block = b.beam_begin + ((uint64_t)blockIdx.x + 1) * blockDim.x <= b.beam_end; // same for every thread
-  if (whole_block) {
-    s_range[threadIdx.x] = r.range;
-    if (b.intensities)
-      s_intens[threadIdx.x] = r.hit_model >= 0 ? __ldg(g.mdl_ranger_return + r.hit_model) : 0.0;
-    s_model[threadIdx.x] = r.hit_model;
-    __syncthreads();
-    if (b.ranges)
-      b.ranges[beam] = s_range[threadIdx.x];
-    if (b.intensities)
-      b.intensities[beam] = s_intens[threadIdx.x];
-    if (b.hit_model)
-      b.hit_model[beam] = s_model[threadIdx.x];
-  } else
-#endif
-  {
-    if (b.ranges)
-      b.ranges[beam] = r.range;
-    if (b.intensities)
-      b.intensities[beam] = r.hit_model >= 0 ? __ldg(g.mdl_ranger_return + r.hit_model) : 0.0;
-    if (b.hit_model)
-      b.hit_model[beam] = r.hit_model;
-  }
+  if (b.ranges)
+    b.ranges[beam] = r.range;
+  if (b.intensities)
+    b.intensities[beam] = r.hit_model >= 0 ? __ldg(g.mdl_ranger_return + r.hit_model) : 0.0;
+  if (b.hit_model)
+    b.hit_model[beam] = r.hit_model;
   if (b.hit_cell) {
     b.hit_cell[2 * beam] = r.hit_x;
     b.hit_cell[2 * beam + 1] = r.hit_y;
