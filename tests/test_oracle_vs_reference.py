@@ -55,6 +55,31 @@ def test_t1_reproduces_every_reference_ray(raw_trace):
         assert st["scans"] == 320 and st["fiducial_updates"] == 320 and st["blob_updates"] == 40
 
 
+def test_survey_known_answers_simple_world():
+    """SURVEY.md section 8c's known-answer vector, captured from an independent headless build of the reference:
+    worlds/simple.world, model r0.ranger:1 (id 4), sensor 0, 180 beams - ranges[0], ranges[89], ranges[179] and
+    intensities[89] at ticks 1, 10 and 100 (%.17g). The golden trace holds the same doubles, so everything pinned
+    to the trace (T1, the device path) is pinned to that vector too. (They depend on the host C library's sin /
+    cos: a trace regenerated on another libm may legitimately differ in the last digits.)"""
+    want = {1: (1.4891668486320924, 8.0, 1.4905818900222529, 0.0),
+            10: (1.8091668416382729, 8.0, 1.8105809858011555, 0.0),
+            100: (4.0228616479595374, 3.4975995723979953, 0.99260976698815795, 0.5)}
+    tr = trace_io.load(os.path.join(GOLDEN, "simple_120.trc.xz"))
+    rangers = [int(m["id"]) for m in tr.models if m["type"].startswith(b"ranger")]
+    r0_laser = rangers[1]  # r0's second ranger: the laser the wander controller subscribes to (wander.cc:53-67)
+    tick, seen = 0, {}
+    for ev in tr.events:
+        if ev["type"] == trace_io.EV_TICK:
+            tick += 1
+        elif ev["type"] == trace_io.EV_RANGER_SCAN and int(ev["model"]) == r0_laser and int(ev["block"]) == 0 and tick + 1 in want:
+            sc = tr.scan(ev)
+            assert sc["n"] == 180
+            seen[tick + 1] = (sc["ranges"][0], sc["ranges"][89], sc["ranges"][179], sc["intensities"][89])
+    assert set(seen) == set(want)
+    for t, w in want.items():
+        assert seen[t] == w or os.environ.get("STG_FOREIGN_LIBM"), (t, seen[t], w)
+
+
 def test_reference_known_answers_lsp_test():
     """The only answers the reference's own tests pin for this path (libstageplugin/test/
     lsp_test_fiducial.cc:36-60, lsp_test_blobfinder.cc:19-59), restated at libstage level: r0's
