@@ -174,11 +174,12 @@ os._exit(0)
 
 
 @pytest.mark.skipif(not oracle_lib.ref_available(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("world", ["autolab.world", "SFU.world", "circuit.world", "pioneer_walle.world"])
+@pytest.mark.parametrize("world", ["autolab.world", "SFU.world", "circuit.world", "pioneer_walle.world", "fasr.world"])
 def test_more_shipped_worlds_replay_exactly(world, tmp_path):
     """The reference itself, run here for a few ticks on more of the worlds it ships (swarms of 94 robots with sonar rings
     and fiducial finders on big bitmaps, worker threads; a laser robot with its wander controller), and every ray, scan,
-    fiducial update and collision test it made replayed through T1: no mismatch."""
+    fiducial update, collision test and set of touching models (fasr.world: its seven charge stations ask every tick)
+    replayed through T1: no mismatch."""
     import json
     import subprocess
     import sys
@@ -189,5 +190,8 @@ def test_more_shipped_worlds_replay_exactly(world, tmp_path):
     assert line, out.stdout[-2000:] + out.stderr[-2000:]
     st = json.loads(line[-1][6:])
     assert st["rays"] > 500 and st["ticks"] == 6
-    for k in ("range_mismatch", "model_mismatch", "scan_mismatch", "fiducial_mismatch", "blob_mismatch", "collision_mismatch"):
+    for k in ("range_mismatch", "model_mismatch", "scan_mismatch", "fiducial_mismatch", "blob_mismatch", "collision_mismatch",
+              "toucher_mismatch"):
         assert st[k] == 0 or (k in ("range_mismatch", "scan_mismatch") and os.environ.get("STG_FOREIGN_LIBM")), (k, st)
+    if world == "fasr.world":
+        assert st["toucher_calls"] >= 7 * 6, st
