@@ -174,12 +174,14 @@ os._exit(0)
 
 
 @pytest.mark.skipif(not oracle_lib.ref_available(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("world", ["autolab.world", "SFU.world", "circuit.world", "pioneer_walle.world", "fasr.world"])
+@pytest.mark.parametrize("world", ["autolab.world", "SFU.world", "circuit.world", "pioneer_walle.world", "fasr.world", "large.world",
+                                   "pioneer_follow.world", "sensor_noise_demo.world"])
 def test_more_shipped_worlds_replay_exactly(world, tmp_path):
     """The reference itself, run here for a few ticks on more of the worlds it ships (swarms of 94 robots with sonar rings
     and fiducial finders on big bitmaps, worker threads; a laser robot with its wander controller), and every ray, scan,
     fiducial update, collision test and set of touching models (fasr.world: its seven charge stations ask every tick)
-    replayed through T1: no mismatch."""
+    replayed through T1: no mismatch. large.world is the widest extent the reference ships; sensor_noise_demo.world's
+    rangers add noise after the ray (its scans are not recorded, its rays are)."""
     import json
     import subprocess
     import sys
