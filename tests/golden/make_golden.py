@@ -28,7 +28,9 @@ TESTS = os.path.dirname(HERE)
 WORLDS = [("simple.world", 120, "simple_120"),     # BASELINE config 1: Pioneer + SICK laser, wander ctrl
           ("fasr.world", 300, "fasr_300"),         # BASELINE config 2: rangers + fiducials, threads 2
           ("lsp_test.world", 20, "lsp_test_20"),   # the Player-plugin test world: fiducial + blobfinder
-          ("pioneer_flocking.world", 12, "pioneer_flocking_12")]  # 100 pioneers, 8 sonars + fiducial finder each, threads 4
+          ("pioneer_flocking.world", 12, "pioneer_flocking_12"),  # 100 pioneers, 8 sonars + fiducial finder each, threads 4
+          ("large.world", 20, "large_20")]  # the widest extent the reference ships: a 1000 m x 700 m floorplan at 2 cm
+                                            # (50 x 36 superregions, 1.9 M cell entries per layer), 10 laser robots
 # lsp_test.world has no controllers: switch its sensors on the way a Player client would
 SUBSCRIBE = {"lsp_test.world": ["r0.fiducial:0", "r1.fiducial:0", "r0.blobfinder:0", "r1.blobfinder:0"]}
 

@@ -15,8 +15,29 @@ def extent_of(trace, margin_sregs=0):
     return x0 - margin_sregs, y0 - margin_sregs, x1 - x0 + 1 + 2 * margin_sregs, y1 - y0 + 1 + 2 * margin_sregs
 
 
+def entries_bound(trace):
+    """upper bound of the (cell, block) entries one layer ever holds: the outline lengths of everything mapped on it"""
+    ev = trace.events[trace.events["type"] == trace_io.EV_MAP]
+    worst = 0
+    for layer in (0, 1):
+        e = ev[ev["layer"] == layer]
+        if not len(e):
+            continue
+        n = e["n_pts"].astype(np.int64)
+        first = e["first"].astype(np.int64)
+        idx = np.repeat(first, n) + (np.arange(int(n.sum())) - np.repeat(np.cumsum(n) - n, n))  # every vertex of every polygon
+        last = np.repeat(first + n - 1, n)
+        nxt = np.where(idx == last, np.repeat(first, n), idx + 1)                                 # its successor, cyclic
+        v = trace.verts.astype(np.int64)
+        worst = max(worst, int(np.abs(v[nxt] - v[idx]).sum()))
+    return worst
+
+
 def make_context(trace, max_cell_entries=1 << 20, **kw):
     x0, y0, nx, ny = extent_of(trace)
+    need = entries_bound(trace)
+    while max_cell_entries < need and max_cell_entries < (1 << 23):  # big maps (large.world: 1.9 M entries per layer)
+        max_cell_entries <<= 1
     n_blocks = int(trace.events["block"][trace.events["type"] == trace_io.EV_MAP].max()) + 1
     ctx = rt.Context(trace.ppm, x0, y0, nx, ny, max_models=int(trace.models["id"].max()) + 1,
                      max_blocks=n_blocks, max_cell_entries=max_cell_entries, **kw)

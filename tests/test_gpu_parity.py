@@ -113,3 +113,32 @@ def test_one_sync_per_run_gives_the_same_answers(trace, t1):
     assert np.array_equal(g.hit_model[:n], t1.hits["hit_model"][:n])
     assert np.array_equal(bits(g.ranges[:n]), bits(t1.hits["range"][:n]))
     g.ctx.close()
+
+
+def test_large_world_extent_replays_exactly():
+    """large.world, the widest extent the reference ships (50 x 36 superregions = 1.8 M regions, 1.9 M cell entries per
+    layer from one traced bitmap, outlines of up to 1765 vertices), 20 ticks of its ten laser robots: rays, scans and
+    the device grid against the oracle and the reference's recorded answers. Most of these rays end in open space
+    after hundreds of empty-region crossings far from the origin."""
+    trace = trace_io.load(os.path.join(GOLDEN, "large_20.trc.xz"))
+    t1 = replay.T1Replay(trace)
+    g = replay.GpuReplay(trace, strict=True)
+    n = len(trace.rays)
+    assert n == 36000 and g.n_ticks == 20
+    assert np.array_equal(g.hit_model, t1.hits["hit_model"]) and np.array_equal(g.hit_model, trace.rays["hit_model"])
+    assert np.array_equal(bits(g.ranges), bits(t1.hits["range"]))
+    assert np.max(np.abs(g.ranges - trace.rays["res_range"])) <= RANGE_TOL
+    hit = g.hit_model >= 0
+    assert 0.05 < hit.mean() < 0.5
+    assert np.array_equal(g.hit_cell[hit, 0], t1.hits["hit_x"][hit]) and np.array_equal(g.hit_cell[hit, 1], t1.hits["hit_y"][hit])
+    assert np.array_equal(g.steps[:, 0], t1.hits["cell_visits"]) and np.array_equal(g.steps[:, 1], t1.hits["region_probes"])
+    assert len(g.scans) == len(t1.scans) == 200
+    for (ev, sc, out), (rg, it, be, hits) in zip(g.scans, t1.scans):
+        assert np.array_equal(bits(out.ranges), bits(rg)) and np.array_equal(bits(out.intensities), bits(it))
+        assert np.array_equal(out.hit_model, hits["hit_model"])
+        assert np.max(np.abs(out.ranges - sc["ranges"])) <= RANGE_TOL
+    rec_g, cnt_g = g.ctx.grid_dump()
+    rec_o, cnt_o = t1.world.dump_grid()
+    assert len(rec_o) > 3000000
+    assert np.array_equal(oracle_lib.sort_grid(rec_g), rec_o) and np.array_equal(oracle_lib.sort_counts(cnt_g), cnt_o)
+    g.ctx.close()

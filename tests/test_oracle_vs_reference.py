@@ -14,7 +14,7 @@ import replay
 import trace_io
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-TRACES = ["simple_120", "fasr_300", "lsp_test_20", "everything_40", "pioneer_flocking_12", "bumper_150", "charger_150"]
+TRACES = ["simple_120", "fasr_300", "lsp_test_20", "everything_40", "pioneer_flocking_12", "bumper_150", "charger_150", "large_20"]
 
 
 @pytest.fixture(scope="module", params=TRACES)
@@ -51,6 +51,8 @@ def test_t1_reproduces_every_reference_ray(raw_trace):
         assert st["fiducial_updates"] == 40 and st["blob_updates"] == 40
     if name == "pioneer_flocking_12":  # a swarm: 100 robots x (8 one-beam sonars + a fiducial finder), worker threads
         assert st["scans"] == 9600 and st["fiducial_updates"] == 1200 and st["collision_tests"] > 1000
+    if name == "large_20":  # 10 laser robots on the 1000 m x 700 m floorplan: most rays end in open space
+        assert st["scans"] == 200 and st["rays"] == 36000 and st["region_probes"] > 500000
     if name == "everything_40":  # sonar rings, lasers, fiducial finders, bumpers, a blobfinder on the hospital map
         assert st["scans"] == 320 and st["fiducial_updates"] == 320 and st["blob_updates"] == 40
 
