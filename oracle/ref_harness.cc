@@ -655,10 +655,12 @@ int ref_model_subscribe(void *wv, const char *name)
 // new pose, UnMapWithChildren(layer), MapWithChildren(layer) - for n models, one after the other on the calling
 // thread, as World::Update runs its movers (world.cc:647-648). Returns the seconds it took. The models need not be
 // position models (the benchmark's robots are plain models with a body). Built with -fno-access-control.
-double ref_models_remap(void *wv, uint32_t n, const uint32_t *ids, const double *xyza, int layer)
+// record != 0: the Map / UnMap calls go into the trace like the reference's own (tests that replay them).
+double ref_models_remap2(void *wv, uint32_t n, const uint32_t *ids, const double *xyza, int layer, int record)
 {
   (void)wv;
-  tl_quiet++;
+  if (!record)
+    tl_quiet++;
   auto t0 = std::chrono::steady_clock::now();
   for (uint32_t i = 0; i < n; i++) {
     Model *m = Model::LookupId(ids[i]);
@@ -669,8 +671,14 @@ double ref_models_remap(void *wv, uint32_t n, const uint32_t *ids, const double 
     m->MapWithChildren((unsigned int)layer);
   }
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  tl_quiet--;
+  if (!record)
+    tl_quiet--;
   return secs;
+}
+
+double ref_models_remap(void *wv, uint32_t n, const uint32_t *ids, const double *xyza, int layer)
+{
+  return ref_models_remap2(wv, n, ids, xyza, layer, 0);
 }
 
 // ModelPosition::SetSpeed (model_position.cc:595): what a controller does to drive a robot.

@@ -233,6 +233,8 @@ def ref():
         L.ref_model_set_speed.argtypes = [vp, ctypes.c_char_p, ctypes.c_double, ctypes.c_double, ctypes.c_double]
         L.ref_models_remap.restype = ctypes.c_double
         L.ref_models_remap.argtypes = [vp, ctypes.c_uint32, vp, vp, ctypes.c_int]
+        L.ref_models_remap2.restype = ctypes.c_double
+        L.ref_models_remap2.argtypes = [vp, ctypes.c_uint32, vp, vp, ctypes.c_int, ctypes.c_int]
         _ref = L
     return _ref
 
@@ -282,11 +284,12 @@ class RefWorld:
     def subscribe(self, name):
         assert self.L.ref_model_subscribe(self.h, name.encode()) == 0, name
 
-    def models_remap(self, ids, xyza, layer):
-        """what Move() does to the grid for these models, one after the other; returns the seconds it took"""
+    def models_remap(self, ids, xyza, layer, record=False):
+        """what Move() does to the grid for these models, one after the other; returns the seconds it took.
+        record: the Map / UnMap calls are logged into the trace (off for the timed benchmark ticks)"""
         ids = np.ascontiguousarray(ids, np.uint32)
         xyza = np.ascontiguousarray(xyza, np.float64).reshape(len(ids), 4)
-        return self.L.ref_models_remap(self.h, len(ids), _p(ids), _p(xyza), layer)
+        return self.L.ref_models_remap2(self.h, len(ids), _p(ids), _p(xyza), layer, 1 if record else 0)
 
     def set_speed(self, name, x, y, a):
         assert self.L.ref_model_set_speed(self.h, name.encode(), x, y, a) == 0, name

@@ -199,3 +199,81 @@ def test_more_shipped_worlds_replay_exactly(world, tmp_path):
         assert st[k] == 0 or (k in ("range_mismatch", "scan_mismatch") and os.environ.get("STG_FOREIGN_LIBM")), (k, st)
     if world == "fasr.world":
         assert st["toucher_calls"] >= 7 * 6, st
+
+
+RANDOM_CHILD = r"""
+import sys, os, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import oracle_lib
+from stage_b200 import worldgen
+seed = int(sys.argv[1])
+w = worldgen.make_world(seed=seed, n_rects=120, n_robots=30, half_extent_m=20.48)
+text = worldgen.to_worldfile_text(w)
+rng = np.random.RandomState(seed)
+extra = []  # models the generator does not make: invisible to rangers, gripper-visible, no obstacle, floating, parent + child
+for i in range(40):
+    x, y, a = rng.uniform(-18, 18), rng.uniform(-18, 18), rng.uniform(-180, 180)
+    attr = ["ranger_return -1", "gripper_return 1", "obstacle_return 0", "ranger_return 0.25", ""][i %% 5]
+    z = 0.0 if i %% 3 else 0.7
+    child = 'model ( name "xc%%d" pose [ 0.4 0 0 30 ] size [ 0.5 0.1 0.3 ] gripper_return 1 )' %% i if i %% 4 == 0 else ""
+    extra.append('model ( name "x%%d" pose [ %%.3f %%.3f %%.3f %%.3f ] size [ %%.3f %%.3f 0.4 ] %%s %%s )'
+                 %% (i, x, y, z, a, rng.uniform(0.2, 1.5), rng.uniform(0.2, 1.5), attr, child))
+ref = oracle_lib.RefWorld(text=text + "\n".join(extra) + "\n")
+# the robots take two more poses, anywhere (also across obstacles and each other), on alternating layers
+for t in (1, 2):
+    xyza = np.stack([rng.uniform(-19, 19, len(w.robots)), rng.uniform(-19, 19, len(w.robots)), np.zeros(len(w.robots)),
+                     rng.uniform(-np.pi, np.pi, len(w.robots))], 1)
+    ref.models_remap(w.robot_ids, xyza, t %% 2, record=True)
+ref.trace_end(sys.argv[2] + "/t.trc")
+finders = [int(i) for i in w.robot_ids] + [int(i) for i in w.obstacle_ids[:20]] + [int(ref.model_id("x%%d" %% i)) for i in range(40)] + \
+          [int(ref.model_id("x%%d.xc%%d" %% (i, i))) for i in range(0, 40, 4)]
+assert min(finders) > 0, finders
+n = 60000
+rays = np.zeros(n, oracle_lib.REF_RAY)
+rays["ox"], rays["oy"] = rng.uniform(-20, 20, n), rng.uniform(-20, 20, n)
+rays["oz"] = rng.choice([0.1, 0.35, 0.5, 0.9, 1.2], n)
+rays["oa"] = rng.uniform(-np.pi, np.pi, n)
+rays["oa"][:200] = rng.choice([0.0, np.pi / 2, -np.pi / 2, np.pi, -np.pi], 200)   # along the axes
+rays["range"] = rng.choice([0.3, 2.0, 8.0, 30.0], n)
+rays["finder"] = rng.choice(finders, n)
+rays["kind"] = rng.randint(0, 3, n)
+rays["ztest"] = rng.randint(0, 2, n)
+hits1, _ = ref.raytrace(rays, nthreads=2)      # World::updates == 0: the rays read layer 1
+ref.update(1)                                   # one tick (nothing moves by itself): now they read layer 0
+hits0, _ = ref.raytrace(rays, nthreads=2)
+np.save(sys.argv[2] + "/rays.npy", rays); np.save(sys.argv[2] + "/hits1.npy", hits1); np.save(sys.argv[2] + "/hits0.npy", hits0)
+sys.stdout.flush(); os._exit(0)
+"""
+
+
+@pytest.mark.skipif(not oracle_lib.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", [5, 6])
+def test_random_rays_on_random_worlds_t1_equals_live_reference(seed, tmp_path):
+    """Beyond the recorded worlds: a generated obstacle field plus models with every attribute the predicates read
+    (ranger_return < 0, gripper_return, obstacle_return 0, floating above the floor, a child model), robots re-rendered
+    anywhere on alternating layers, and 60,000 random rays - all three predicate kinds, with and without the z test,
+    any finder, origins anywhere (inside bodies too), four ranges - traced by the unmodified reference on both layers
+    and by T1 on the grid it builds from the reference's recorded Map / UnMap calls: same model, same range bits."""
+    import subprocess
+    import sys
+    tests = os.path.dirname(os.path.abspath(__file__))
+    subprocess.run([sys.executable, "-c", RANDOM_CHILD % (tests, os.path.dirname(tests)), str(seed), str(tmp_path)], check=True,
+                   stdout=subprocess.DEVNULL, timeout=600)
+    rays = np.load(tmp_path / "rays.npy")
+    st, w1 = oracle_lib.t1_replay(tmp_path / "t.trc")
+    assert st["maps"] > 400 and st["unmaps"] > 100
+    q = np.zeros(len(rays), oracle_lib.T1_RAY)
+    for k in ("ox", "oy", "oz", "oa", "range", "finder", "kind", "ztest"):
+        q[k] = rays[k]
+    kinds_hit = set()
+    for layer in (1, 0):
+        want = np.load(tmp_path / ("hits%d.npy" % layer))
+        q["layer"] = layer
+        got = w1.raytrace(q)
+        bad = np.nonzero((got["hit_model"] != want["hit_model"]) | (got["range"].view(np.uint64) != want["range"].view(np.uint64)))[0]
+        assert len(bad) == 0 or os.environ.get("STG_FOREIGN_LIBM"), (layer, len(bad), rays[bad[:3]], got[bad[:3]], want[bad[:3]])
+        for k in range(3):
+            if np.any(want["hit_model"][rays["kind"] == k] >= 0):
+                kinds_hit.add(k)
+        assert 0.2 < np.mean(want["hit_model"] >= 0) < 0.95
+    assert kinds_hit == {0, 1, 2}  # rangers, any-unrelated-model rays and gripper rays all found something
