@@ -155,3 +155,94 @@ def test_cave_tiles_match_oracle():
     g2 = ctx.trace(fans)  # device trig
     assert np.array_equal(g2.hit_model, hits["hit_model"]) and np.array_equal(bits(g2.ranges), bits(rg))
     ctx.close()
+
+
+def test_random_rays_of_every_kind_match_oracle():
+    """The device against the oracle where tests/test_oracle_vs_reference.py pins the oracle to the live reference: a
+    generated obstacle field plus models with every attribute the predicates read (invisible to rangers, gripper-visible,
+    no obstacle, floating, a related child), robots re-rendered anywhere on alternating layers, and 200,000 random
+    rays - three predicate kinds, z test on and off, any finder, origins anywhere, four ranges, both layers. Model,
+    range bits, hit cell and both step counters; strict trig and the device's own."""
+    w = worldgen.make_world(seed=5, n_rects=120, n_robots=30, half_extent_m=20.48)
+    x0, y0, nx, ny = w.sreg_extent()
+    n_static = len(w.obstacles) + len(w.robots)
+    first_extra = w.n_models + 1
+    ctx = rt.Context(w.ppm, x0, y0, nx, ny, max_models=first_extra + 100, max_blocks=n_static + 100, max_cell_entries=1 << 20)
+    worldgen.load_into_context(ctx, w)
+    t1 = oracle_lib.T1World(w.ppm)
+    t1.model_upsert(0, 0, 1.0)
+    for mid in list(w.obstacle_ids) + list(w.robot_ids):
+        t1.model_upsert(int(mid), int(mid), 0.5)
+    polys = worldgen.obstacle_polygons(w) + worldgen.robot_polygons(w)
+    models = np.concatenate([w.obstacle_ids, w.robot_ids])
+    zmax = [w.obstacle_height] * len(w.obstacles) + [w.robot_size[2]] * len(w.robots)
+    for layer in (0, 1):
+        for b, (p, m, z) in enumerate(zip(polys, models, zmax)):
+            t1.block_map(b, int(m), layer, 0.0, z, p)
+    rng = np.random.RandomState(17)
+    finders = [int(i) for i in w.robot_ids] + [int(i) for i in w.obstacle_ids[:20]]
+    blk, mid = n_static, first_extra
+    for i in range(40):
+        rr, flags = [(-1.0, rt.VIS_OBSTACLE_RETURN), (0.5, rt.VIS_OBSTACLE_RETURN | rt.VIS_GRIPPER_RETURN), (0.5, 0),
+                     (0.25, rt.VIS_OBSTACLE_RETURN), (1.0, rt.VIS_OBSTACLE_RETURN)][i % 5]
+        z0 = 0.0 if i % 3 else 0.7
+        x, y, a = rng.uniform(-18, 18), rng.uniform(-18, 18), rng.uniform(-np.pi, np.pi)
+        bodies = [(mid, mid, rr, flags, 0.0, rng.uniform(0.2, 1.5), rng.uniform(0.2, 1.5))]
+        if i % 4 == 0:  # a child model: same tree, gripper-visible, sticks out
+            bodies.append((mid + 1, mid, 1.0, rt.VIS_OBSTACLE_RETURN | rt.VIS_GRIPPER_RETURN, 0.4, 0.5, 0.1))
+        for m, root, r_ret, fl, off, sx, sy in bodies:
+            for o in (ctx, t1):
+                o.model_upsert(m, root, r_ret, 0, 0, fl)
+            p = worldgen.pixel_polygon(round(x + off * np.cos(a), 3), round(y + off * np.sin(a), 3), a, sx, sy, w.ppm)
+            for layer in (0, 1):
+                ctx.block_map(blk, m, layer, z0, z0 + 0.4, p)
+                t1.block_map(blk, m, layer, z0, z0 + 0.4, p)
+            finders.append(m)
+            blk += 1
+        mid += len(bodies)
+    for t in (1, 2):  # the robots take two more poses, anywhere (across obstacles and each other too)
+        layer = t % 2
+        for j, rid in enumerate(w.robot_ids):
+            p = worldgen.pixel_polygon(round(rng.uniform(-19, 19), 3), round(rng.uniform(-19, 19), 3), rng.uniform(-np.pi, np.pi),
+                                       w.robot_size[0], w.robot_size[1], w.ppm)
+            b = len(w.obstacles) + j
+            ctx.block_unmap(b, layer)
+            ctx.block_map(b, int(rid), layer, 0.0, w.robot_size[2], p)
+            t1.block_unmap(b, layer)
+            t1.block_map(b, int(rid), layer, 0.0, w.robot_size[2], p)
+    rec_g, cnt_g = ctx.grid_dump()
+    rec_o, cnt_o = t1.dump_grid()
+    assert np.array_equal(oracle_lib.sort_grid(rec_g), rec_o) and np.array_equal(oracle_lib.sort_counts(cnt_g), cnt_o)
+    n = 100000
+    q = np.zeros(n, oracle_lib.T1_RAY)
+    q["ox"], q["oy"] = rng.uniform(-20, 20, n), rng.uniform(-20, 20, n)
+    q["oz"] = rng.choice([0.1, 0.35, 0.5, 0.9, 1.2], n)
+    q["oa"] = rng.uniform(-np.pi, np.pi, n)
+    q["oa"][:200] = rng.choice([0.0, np.pi / 2, -np.pi / 2, np.pi, -np.pi], 200)
+    q["range"] = rng.choice([0.3, 2.0, 8.0, 30.0], n)
+    q["finder"] = rng.choice(finders, n)
+    q["kind"] = rng.randint(0, 3, n)
+    q["ztest"] = rng.randint(0, 2, n)
+    kinds_hit = set()
+    for layer in (1, 0):
+        q["layer"] = layer
+        want = t1.raytrace(q)
+        fans = rt.make_fans(n)
+        fans["finder"], fans["n_samples"], fans["pred"], fans["ztest"], fans["layer"] = q["finder"], 1, q["kind"], q["ztest"], layer
+        fans["angles"], fans["first_heading"] = rt.ANGLES_EXPLICIT, np.arange(n)
+        for k in ("ox", "oy", "oz", "oa", "range"):
+            fans[k] = q[k]
+        head = np.ascontiguousarray(q["oa"])
+        for trig in (oracle_lib.libm_trig(head), None):
+            g = ctx.trace(fans, headings=head, trig=trig)
+            bad = np.nonzero((g.hit_model != want["hit_model"]) | (bits(g.ranges) != bits(want["range"])))[0]
+            assert len(bad) == 0, (layer, trig is None, len(bad), q[bad[:3]], g.hit_model[bad[:3]], g.ranges[bad[:3]], want[bad[:3]])
+            h = g.hit_model >= 0
+            assert np.array_equal(g.hit_cell[h, 0], want["hit_x"][h]) and np.array_equal(g.hit_cell[h, 1], want["hit_y"][h])
+            assert np.array_equal(g.steps[:, 0], want["cell_visits"]) and np.array_equal(g.steps[:, 1], want["region_probes"])
+        for k in range(3):
+            if np.any(want["hit_model"][q["kind"] == k] >= 0):
+                kinds_hit.add(k)
+        assert 0.2 < np.mean(want["hit_model"] >= 0) < 0.95
+    assert kinds_hit == {0, 1, 2}
+    ctx.close()
