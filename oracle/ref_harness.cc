@@ -681,6 +681,25 @@ double ref_models_remap(void *wv, uint32_t n, const uint32_t *ids, const double 
   return ref_models_remap2(wv, n, ids, xyza, layer, 0);
 }
 
+// Model::TestCollision() and Model::AppendTouchingModels() for n models, through the interposers above, so that
+// every call lands in the trace with its answer (tests that pin the oracle's restatement of the two on worlds
+// where plenty of models overlap). Returns how many of the collision tests found something.
+int ref_probe_models(void *wv, uint32_t n, const uint32_t *ids)
+{
+  (void)wv;
+  int hits = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    Model *m = Model::LookupId(ids[i]);
+    if (!m)
+      continue;
+    if (m->TestCollision())
+      hits++;
+    std::set<Model *> touchers;
+    m->AppendTouchingModels(touchers);
+  }
+  return hits;
+}
+
 // ModelPosition::SetSpeed (model_position.cc:595): what a controller does to drive a robot.
 int ref_model_set_speed(void *wv, const char *name, double x, double y, double a)
 {

@@ -233,6 +233,7 @@ def ref():
         L.ref_model_set_speed.argtypes = [vp, ctypes.c_char_p, ctypes.c_double, ctypes.c_double, ctypes.c_double]
         L.ref_models_remap.restype = ctypes.c_double
         L.ref_models_remap.argtypes = [vp, ctypes.c_uint32, vp, vp, ctypes.c_int]
+        L.ref_probe_models.restype, L.ref_probe_models.argtypes = ctypes.c_int, [vp, ctypes.c_uint32, vp]
         L.ref_models_remap2.restype = ctypes.c_double
         L.ref_models_remap2.argtypes = [vp, ctypes.c_uint32, vp, vp, ctypes.c_int, ctypes.c_int]
         _ref = L
@@ -290,6 +291,11 @@ class RefWorld:
         ids = np.ascontiguousarray(ids, np.uint32)
         xyza = np.ascontiguousarray(xyza, np.float64).reshape(len(ids), 4)
         return self.L.ref_models_remap2(self.h, len(ids), _p(ids), _p(xyza), layer, 1 if record else 0)
+
+    def probe_models(self, ids):
+        """Model::TestCollision and Model::AppendTouchingModels of these models, recorded into the trace; -> collisions found"""
+        ids = np.ascontiguousarray(ids, np.uint32)
+        return int(self.L.ref_probe_models(self.h, len(ids), _p(ids)))
 
     def set_speed(self, name, x, y, a):
         assert self.L.ref_model_set_speed(self.h, name.encode(), x, y, a) == 0, name

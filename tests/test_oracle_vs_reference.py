@@ -277,3 +277,56 @@ def test_random_rays_on_random_worlds_t1_equals_live_reference(seed, tmp_path):
                 kinds_hit.add(k)
         assert 0.2 < np.mean(want["hit_model"] >= 0) < 0.95
     assert kinds_hit == {0, 1, 2}  # rangers, any-unrelated-model rays and gripper rays all found something
+
+
+PROBE_CHILD = r"""
+import sys, os, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import oracle_lib
+from stage_b200 import worldgen
+seed = int(sys.argv[1])
+w = worldgen.make_world(seed=seed, n_rects=150, n_robots=80, half_extent_m=20.48)
+rng = np.random.RandomState(seed)
+extra = []
+for i in range(60):  # no-obstacle models, floating ones, one reaching below the floor, parents with a child sticking out
+    x, y, a = rng.uniform(-18, 18), rng.uniform(-18, 18), rng.uniform(-180, 180)
+    attr = ["obstacle_return 0", "", "ranger_return -1", ""][i %% 4]
+    z = -0.1 if i == 7 else (0.0 if i %% 3 else 0.7)
+    child = 'model ( name "xc%%d" pose [ 0.4 0 0 30 ] size [ 0.6 0.1 0.3 ] )' %% i if i %% 5 == 0 else ""
+    extra.append('model ( name "x%%d" pose [ %%.3f %%.3f %%.3f %%.3f ] size [ %%.3f %%.3f 0.4 ] %%s %%s )'
+                 %% (i, x, y, z, a, rng.uniform(0.2, 1.5), rng.uniform(0.2, 1.5), attr, child))
+ref = oracle_lib.RefWorld(text=worldgen.to_worldfile_text(w) + "\n".join(extra) + "\n")
+ids = [int(i) for i in w.robot_ids] + [int(i) for i in w.obstacle_ids[:40]] + [int(ref.model_id("x%%d" %% i)) for i in range(60)]
+hits = 0
+for t in (0, 1, 2):
+    if t:  # the robots are dropped anywhere: onto obstacles, onto each other
+        xyza = np.stack([rng.uniform(-19, 19, len(w.robots)), rng.uniform(-19, 19, len(w.robots)), np.zeros(len(w.robots)),
+                         rng.uniform(-np.pi, np.pi, len(w.robots))], 1)
+        ref.models_remap(w.robot_ids, xyza, t %% 2, record=True)
+        ref.update(1)   # World::updates = t: Block::TestCollision / AppendTouchingModels read layer t %% 2
+    hits += ref.probe_models(ids)
+ref.trace_end(sys.argv[2])
+print("HITS %%d" %% hits)
+sys.stdout.flush(); os._exit(0)
+"""
+
+
+@pytest.mark.skipif(not oracle_lib.ref_available(), reason="oracle/_ref not built")
+def test_collisions_and_touching_models_on_crowded_random_worlds(tmp_path):
+    """Model::TestCollision and Model::AppendTouchingModels of 180 models of the unmodified reference - robots dropped
+    onto obstacles and each other, models without obstacle_return, floating ones, one below the floor, parents with a
+    child - on both layers, recorded with their answers and replayed through T1: every returned model and every set."""
+    import subprocess
+    import sys
+    tests = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, "-c", PROBE_CHILD % (tests, os.path.dirname(tests)), "11", str(tmp_path / "p.trc")],
+                         capture_output=True, text=True, timeout=600)
+    assert "HITS " in out.stdout, out.stdout[-1000:] + out.stderr[-2000:]
+    st, _ = oracle_lib.t1_replay(tmp_path / "p.trc")
+    assert st["collision_tests"] == 3 * 180 and st["collision_hits"] > 150 and st["collision_mismatch"] == 0, st
+    assert st["toucher_calls"] == 3 * 180 and st["toucher_models"] > 300 and st["toucher_mismatch"] == 0, st
+    tr = trace_io.load(tmp_path / "p.trc")
+    sets = [tr.touchers(ev)[3] for ev in tr.events if ev["type"] == trace_io.EV_TOUCHERS]
+    assert max(len(s) for s in sets) >= 3
+    answers = {tr.collision(ev)[3] for ev in tr.events if ev["type"] == trace_io.EV_COLLISION}
+    assert 0 in answers and -1 in answers and len(answers) > 50  # the ground, nothing, and many different models
