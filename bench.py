@@ -442,14 +442,15 @@ def run_ours(args):
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline and args.workload == "c3":
         threads = args.cpu_threads or os.cpu_count()
         sample_fans = fans0
-        res = cpu_reference_throughput(world, sample_fans, threads, reps=3, record=True)
+        cpu_reps = 20  # about a second of wall clock on 16 threads: ~15 s of CPU work
+        res = cpu_reference_throughput(world, sample_fans, threads, reps=cpu_reps, record=True)
         if res is not None:
             one = res["ref"].raytrace(res["rays_arr"][:SAMPLES * 50], nthreads=1)[1]
             cpu = {"value": res["rays_per_s"], "unit": "rays/s", "cores": threads, "kind": "reference",
-                   "sample": "all %d rays of one tick (static robots), best of 3, unmodified reference "
+                   "sample": "all %d rays of one tick (static robots), best of %d passes (mean %.3g rays/s), unmodified reference "
                              "World::Raytrace via oracle/_ref on %d threads; 1 thread: %.3g rays/s. Rays only: "
                              "`--impl reference` times whole ticks (the robots' re-rendering too, as `e2e` does)"
-                             % (res["rays"], threads, SAMPLES * 50 / one)}
+                             % (res["rays"], cpu_reps, res["rays"] / res["mean_s"], threads, SAMPLES * 50 / one)}
             # Parity of this very workload with the reference's answers. Which of two overlapping
             # bodies a ray reports depends on the order the reference mapped them in while loading
             # (its std::set<Model*> order, world.cc:459-465), so a second context is loaded from the
