@@ -77,6 +77,21 @@ def workload_config(args, n_gpus):
     }
 
 
+def leave(code):
+    """End the process without running C++ static destructors (a reference World must never be destroyed: ~World
+    crashes in the reference itself) but WITH everything Python registered for exit - the driver's hook
+    that records which shared libraries this process loaded lives there."""
+    import atexit
+    sys.stdout.flush()
+    sys.stderr.flush()
+    try:
+        atexit._run_exitfuncs()
+    finally:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(code)
+
+
 # ---------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------
@@ -236,8 +251,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
-    sys.stdout.flush()
-    os._exit(0)  # a reference World must never be destroyed
+    leave(0)  # a reference World must never be destroyed
 
 
 # ---------------------------------------------------------------------------------------------
@@ -494,7 +508,8 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": t_value_ms / args.steps,
             "ticks_per_s": args.steps / (t_value_ms * 1e-3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args, n_gpus), host_numa_node=numa_node, e2e_warmup_ticks=nw_e2e),
+            "config": workload_config(args, n_gpus),
+            "host": {"numa_node": numa_node, "e2e_warmup_ticks": nw_e2e, "cpus": os.cpu_count()},
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": 1e3 * t_e2e / args.steps,
                     "ticks_per_s": args.steps / t_e2e,
                     "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // args.steps,
@@ -515,8 +530,7 @@ def run_ours(args):
     if n_gpus > 1:
         dist.barrier()
         dist.destroy_process_group()
-    sys.stdout.flush()
-    os._exit(0)  # the reference World loaded for the CPU baseline must never be destroyed
+    leave(0)  # the reference World loaded for the CPU baseline must never be destroyed
 
 
 if __name__ == "__main__":

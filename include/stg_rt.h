@@ -410,12 +410,25 @@ int64_t stg_rt_debug_region_owners(stg_rt_ctx *ctx, int64_t *records, int64_t ca
    issues the same maps in rank order, hold identical grids. */
 
 /* Move the deltas queued since the last flush into a device buffer owned by the context and return
-   its address and size (fixed-size records). They are NOT applied locally yet. */
+   its address and size (fixed-size records). They are NOT applied locally yet.
+   ORDERING: the blob is written by an asynchronous copy on the context's stream (stg_rt_get_stream): it is
+   complete for work queued LATER ON THAT STREAM. A caller whose collective runs on another stream (its own
+   ncclAllGather stream) must call stg_rt_stream_signal(ctx, that_stream) after the export and
+   stg_rt_stream_wait(ctx, that_stream) after enqueuing the collective, before stg_rt_delta_apply_gathered -
+   or hand the context its stream with stg_rt_set_stream. K1 refuses a slot that does not hold a well-formed
+   blob (magic word, record counts that add up to the blob's own size and fit the slot) and the next
+   stg_rt_sync then fails with STG_RT_EINVAL, so a gather that ran too early cannot corrupt the grid silently. */
 int stg_rt_delta_export(stg_rt_ctx *ctx, int rank, void **dev_blob, size_t *n_bytes);
+/* Everything queued so far on the context's stream happens before work queued later on consumer_stream. */
+int stg_rt_stream_signal(stg_rt_ctx *ctx, void *consumer_stream);
+/* Everything queued so far on producer_stream happens before work queued later on the context's stream. */
+int stg_rt_stream_wait(stg_rt_ctx *ctx, void *producer_stream);
 /* Size every rank must use as the per-rank slot of the all-gather buffer. */
 size_t stg_rt_delta_slot_bytes(const stg_rt_ctx *ctx);
 /* Apply n_ranks blobs laid out back to back, slot_bytes apart, in a DEVICE buffer (the all-gather
-   output), in rank order, directly out of that buffer. Includes this rank's own blob. */
+   output), in rank order, directly out of that buffer. Includes this rank's own blob. Runs on the
+   context's stream: the gathered buffer must be complete in that stream's order (see stg_rt_delta_export).
+   Fails with STG_RT_ENOMEM when the cell-entry tables would pass half full (as a local flush does). */
 int stg_rt_delta_apply_gathered(stg_rt_ctx *ctx, const void *dev_gathered, int n_ranks, size_t slot_bytes);
 
 /* ---- plumbing -------------------------------------------------------------------------------- */
@@ -433,6 +446,18 @@ int stg_rt_debug_trig(stg_rt_ctx *ctx, uint64_t n, const double *headings, doubl
    World::Raytrace(fan), world.cc:731-743), sum(n_samples) doubles in fan order. Synchronous. */
 int stg_rt_debug_headings(stg_rt_ctx *ctx, uint32_t n_fans, const stg_rt_fan *fans, const double *headings_in,
                           double *headings_out);
+
+/* ---- libc rand() stream of a ranger whose beam loop no longer runs on the host ------------------- */
+/* ModelRanger::Sensor::Update draws from libc rand() inside its beam loop even when every noise parameter is
+   zero (model_ranger.cc:232-249: one simpleNoise() per beam for the heading jitter, :237; for a beam that
+   returned less than range.max one more simpleNoise() and one generateGaussianNoise(), :244-246, which itself
+   draws two numbers on every second call, :181-199 - all multiplied by 0). Controllers that share the stream
+   (examples/ctrl/lasernoise.cc) see different numbers once the loop is gone. This advances rand() by exactly the
+   draws the loop would have made for one sensor: n_samples beams of which n_in_range came back shorter than
+   range.max. It mirrors generateGaussianNoise's static "spare" flag with one of its own, so every ranger sensor of
+   the process has to go through it (or none). Pure host code; callable without a context. Returns the number of
+   rand() calls made. */
+uint32_t stg_rt_ranger_rand_advance(uint32_t n_samples, uint32_t n_in_range);
 
 /* Counters since create: kernel launches by kind, rays traced, bytes copied each way. */
 typedef struct {

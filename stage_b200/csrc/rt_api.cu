@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -36,6 +37,7 @@ struct BlockShadow {
   // what the caller last said (host_*) and what the device grid currently holds (dev_*)
   bool host_mapped[2] = { false, false }, dev_mapped[2] = { false, false }, dirty[2] = { false, false };
   uint32_t map_seq[2] = { 0, 0 };
+  uint32_t host_steps[2] = { 0, 0 }, dev_steps[2] = { 0, 0 }; // cell visits of host_xy / dev_xy (all renderings)
   std::vector<int32_t> host_xy[2], dev_xy[2];
   // Block::Map on a block that is already mapped renders it once more (block.cc:170-181 does not check; the
   // reference's world loader does it to bumper models): the cells get duplicate entries, Region::count counts them,
@@ -98,11 +100,13 @@ struct stg_rt_ctx {
   uint64_t epoch = 0;
   uint32_t local_seq = 0;
   int last_export_rank = -1; // multi-GPU: this context's rank, learnt from stg_rt_delta_export
-  int64_t last_export_ins = 0, last_gather_ins = 0;
+  bool export_mode = false;  // deltas leave through stg_rt_delta_export (never applied locally)
+  int64_t last_export_ins[2] = { 0, 0 }, last_gather_ins[2] = { 0, 0 };
   PinBuf h_hdrs;
-  cudaEvent_t hdrs_ready = nullptr;
+  cudaEvent_t hdrs_ready = nullptr, xstream_ev = nullptr;
   bool hdrs_pending = false;
   int hdrs_ranks = 0;
+  uint32_t *err_host = nullptr;       // page-locked word the kernels raise kErr* bits in (GridView::err_host)
   int64_t live_entries[2] = { 0, 0 }; // cell visits currently rendered, per layer
   int64_t used_upper[2] = { 0, 0 };   // upper bound of non-empty slots (entries + tombstones)
 
@@ -404,6 +408,7 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
     size_t bytes = sizeof(DeltaHeader) + n_bupd * sizeof(BlockUpd) + n_model * sizeof(ModelUpd);
     if (bytes > c->blob_cap)
       return fail(c, STG_RT_ENOMEM, "model / block attribute updates exceed the delta buffer");
+    int64_t d_live[2] = { 0, 0 }; // net change of rendered cell visits per layer, known before anything is touched
     while (end_unit < c->dirty_units.size()) {
       const uint32_t u = c->dirty_units[end_unit];
       const BlockShadow &b = c->blocks[u >> 1];
@@ -419,10 +424,17 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
       n_rem += re;
       n_ins += ie;
       n_bupd += b.host_mapped[L] ? 1 : 0;
+      d_live[L] += (b.host_mapped[L] ? (int64_t)b.host_steps[L] : 0) - (b.dev_mapped[L] ? (int64_t)b.dev_steps[L] : 0);
       end_unit++;
     }
     if (!apply && end_unit < c->dirty_units.size())
       return fail(c, STG_RT_ENOMEM, "deltas of one tick exceed the all-gather slot (%zu bytes)", c->blob_cap);
+    // the cell-entry tables must keep half their slots free; checked here, while the shadow still says what the
+    // device holds, so that a caller who gets this error can unmap something and carry on
+    for (int L = 0; L < 2; L++)
+      if (c->live_entries[L] + d_live[L] > (int64_t)c->slot_cap / 2)
+        return fail(c, STG_RT_ENOMEM, "cell-entry table of layer %d full (%lld entries, capacity %u/2); raise max_cell_entries",
+                    L, (long long)(c->live_entries[L] + d_live[L]), c->slot_cap);
 
     lap(2);
     // ---- pass 2: write the records straight into the pinned blob ----
@@ -445,16 +457,15 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
       up.pad = 0;
     }
     uint32_t rem_cursor = 0, ins_cursor = 0;
-    int64_t d_live[2] = { 0, 0 }, ins_round[2] = { 0, 0 };
+    int64_t ins_round[2] = { 0, 0 }, rem_round[2] = { 0, 0 };
     for (; unit < end_unit; unit++) {
       const uint32_t u = c->dirty_units[unit];
       BlockShadow &b = c->blocks[u >> 1];
       const int L = u & 1;
       if (b.dev_mapped[L])
-        d_live[L] -= emit_edges(b.dev_xy[L], u >> 1, L, rem_cursor, rem, &b.dev_poly[L]);
+        rem_round[L] += emit_edges(b.dev_xy[L], u >> 1, L, rem_cursor, rem, &b.dev_poly[L]);
       if (b.host_mapped[L]) {
         const uint32_t st = emit_edges(b.host_xy[L], u >> 1, L, ins_cursor, ins, &b.host_poly[L]);
-        d_live[L] += st;
         ins_round[L] += st;
         BlockUpd &up = *bupd++;
         up.block = u >> 1;
@@ -468,9 +479,11 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
         b.keep_seq[L] = false;
         b.dev_xy[L].swap(b.host_xy[L]); // host_xy is rewritten by the next Map before it is read again
         b.dev_poly[L].swap(b.host_poly[L]);
+        b.dev_steps[L] = b.host_steps[L];
       } else {
         b.dev_xy[L].clear();
         b.dev_poly[L].clear();
+        b.dev_steps[L] = 0;
       }
       b.dev_mapped[L] = b.host_mapped[L];
       b.dirty[L] = false;
@@ -485,19 +498,22 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
     hdr->steps_remove = rem_cursor;
     hdr->steps_insert = ins_cursor;
     hdr->rank = (uint32_t)rank;
+    hdr->magic = kDeltaMagic;
+    for (int L = 0; L < 2; L++) {
+      hdr->steps_remove_l[L] = (uint32_t)rem_round[L];
+      hdr->steps_insert_l[L] = (uint32_t)ins_round[L];
+    }
+    hdr->n_bytes = (uint32_t)bytes;
+    hdr->epoch = c->epoch + 1; // what this sender would call the pass; a gathered pass takes the largest proposal
     const size_t nbytes = bytes;
     lap(3);
-    if (apply)
-      for (int L = 0; L < 2; L++)
-        if (c->live_entries[L] + d_live[L] > (int64_t)c->slot_cap / 2)
-          return fail(c, STG_RT_ENOMEM, "cell-entry table of layer %d full (%lld entries, capacity %u/2); raise max_cell_entries",
-                      L, (long long)(c->live_entries[L] + d_live[L]), c->slot_cap);
     CU(c, cudaMemcpyAsync(c->d_blob.p, c->h_blob.p, nbytes, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaEventRecord(c->blob_uploaded, c->stream));
     c->stats.h2d_bytes += nbytes;
     c->stats.edge_steps += rem_cursor + ins_cursor;
     if (!apply)
-      c->last_export_ins = ins_cursor;
+      for (int L = 0; L < 2; L++)
+        c->last_export_ins[L] = ins_round[L];
     for (int L = 0; L < 2; L++)
       c->live_entries[L] += d_live[L];
     if (apply) {
@@ -885,6 +901,22 @@ int flush_locked(stg_rt_ctx *c)
   return launch_fans_locked(c, true);
 }
 
+// What K1 could not do and said so (GridView::err_host); the stream must be idle. The grid may be incomplete after
+// any of these: the caller should treat the context as lost (libstage falls back to its CPU path).
+int device_errors_locked(stg_rt_ctx *c)
+{
+  const uint32_t e = *(volatile uint32_t *)c->err_host;
+  if (!e)
+    return STG_RT_OK;
+  *(volatile uint32_t *)c->err_host = 0;
+  if (e & kErrTableFull)
+    return fail(c, STG_RT_ENOMEM, "the device ran out of cell-entry slots while inserting (raise max_cell_entries); entries were dropped");
+  if (e & kErrBadBlob)
+    return fail(c, STG_RT_EINVAL, "a delta slot did not hold a well-formed blob (gathered before the export had landed, or a foreign "
+                                  "buffer); it was skipped");
+  return fail(c, STG_RT_EINVAL, "a delta record named a cell outside the device extent or an unknown block; it was skipped");
+}
+
 void touch_unit(stg_rt_ctx *c, uint32_t block, int layer)
 {
   BlockShadow &b = c->blocks[block];
@@ -944,6 +976,7 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
     CUC(cudaEventCreateWithFlags(&c->chunk_ev[k], cudaEventDisableTiming));
   CUC(cudaEventCreateWithFlags(&c->copies_done, cudaEventDisableTiming));
   CUC(cudaEventCreateWithFlags(&c->hdrs_ready, cudaEventDisableTiming));
+  CUC(cudaEventCreateWithFlags(&c->xstream_ev, cudaEventDisableTiming));
   GridView &g = c->g;
   g.ppm = cfg->ppm;
   g.rx0 = cfg->sreg_x0 * 32;
@@ -982,6 +1015,9 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
   CUC(cudaMemsetAsync(g.mdl_root, 0, (size_t)cfg->max_models * 4, c->stream));
   CUC(cudaMemsetAsync(g.mdl_ranger_return, 0, (size_t)cfg->max_models * 8, c->stream));
   CUC(cudaMemsetAsync(g.mdl_flags, 0, (size_t)cfg->max_models * 4, c->stream));
+  CUC(cudaMallocHost(&c->err_host, 64));
+  *c->err_host = 0;
+  g.err_host = c->err_host;
   c->blob_cap = cfg->max_delta_bytes ? std::max<size_t>(cfg->max_delta_bytes, 4096) : (8u << 20);
   CUC(cudaMalloc(&c->d_blob.p, c->blob_cap));
   c->d_blob.cap = c->blob_cap;
@@ -1038,8 +1074,11 @@ int stg_rt_destroy(stg_rt_ctx *c)
     cudaEventDestroy(c->chunk_ev[k]);
   cudaEventDestroy(c->copies_done);
   cudaEventDestroy(c->hdrs_ready);
+  cudaEventDestroy(c->xstream_ev);
   if (c->h_hdrs.p)
     cudaFreeHost(c->h_hdrs.p);
+  if (c->err_host)
+    cudaFreeHost(c->err_host);
   cudaStreamDestroy(c->copy_stream);
   for (int k = 0; k < 3; k++)
     for (int j = 0; j < 2; j++)
@@ -1136,12 +1175,25 @@ static int block_map_locked(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id,
   if (model_id >= c->cfg.max_models || !c->model_known[model_id])
     return fail(c, STG_RT_EINVAL, "block_map: unknown model %u (call stg_rt_model_upsert first)", model_id);
   BlockShadow &b = c->blocks[block_id];
-  for (int i = 0; i < n_pts; i++)
+  uint64_t steps = 0; // cell visits of this outline: |dx| + |dy| per edge (world.cc:1000-1002)
+  for (int i = 0; i < n_pts; i++) {
     if (xy[2 * i] < c->cell_x0 || xy[2 * i] > c->cell_x1 || xy[2 * i + 1] < c->cell_y0 || xy[2 * i + 1] > c->cell_y1)
       return fail(c, STG_RT_EEXTENT, "block %u vertex (%d,%d) outside the device grid [%d..%d]x[%d..%d]", block_id, xy[2 * i],
                   xy[2 * i + 1], c->cell_x0, c->cell_x1, c->cell_y0, c->cell_y1);
+    const int j = i + 1 == n_pts ? 0 : i + 1;
+    steps += (uint64_t)std::llabs((long long)xy[2 * j] - xy[2 * i]) + (uint64_t)std::llabs((long long)xy[2 * j + 1] - xy[2 * i + 1]);
+  }
+  if (steps + b.host_steps[layer] > 0x7fffffffull)
+    return fail(c, STG_RT_EINVAL, "block %u: outline of %llu cell visits", block_id, (unsigned long long)steps);
   if (!c->q_subs.empty()) { // issue order: queued fans must be traced against the grid as it was
     int rc = flush_locked(c);
+    if (rc)
+      return rc;
+  }
+  if (c->local_seq >= kSeqLocalMax) { // the call-order field of a sequence number is full: close this round of deltas
+    if (c->export_mode)
+      return fail(c, STG_RT_ENOMEM, "more than %u Map calls between two delta exchanges", kSeqLocalMax);
+    int rc = apply_deltas_locked(c);
     if (rc)
       return rc;
   }
@@ -1157,15 +1209,18 @@ static int block_map_locked(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id,
     if (!b.dirty[layer]) { // the device holds the current outline; host_xy is scratch since the last flush
       b.host_xy[layer] = b.dev_xy[layer];
       b.host_poly[layer] = b.dev_poly[layer];
+      b.host_steps[layer] = b.dev_steps[layer];
       b.keep_seq[layer] = true;
     }
     if (b.host_poly[layer].empty())
       b.host_poly[layer].push_back((uint32_t)(b.host_xy[layer].size() / 2));
     b.host_poly[layer].push_back((uint32_t)n_pts);
     b.host_xy[layer].insert(b.host_xy[layer].end(), xy, xy + 2 * (size_t)n_pts);
+    b.host_steps[layer] += (uint32_t)steps;
     c->local_seq++;
   } else {
     b.host_mapped[layer] = true;
+    b.host_steps[layer] = (uint32_t)steps;
     b.host_xy[layer].assign(xy, xy + 2 * (size_t)n_pts);
     b.host_poly[layer].clear();
     b.keep_seq[layer] = false;
@@ -1191,6 +1246,7 @@ static int block_unmap_locked(stg_rt_ctx *c, uint32_t block_id, int layer)
       return rc;
   }
   b.host_mapped[layer] = false;
+  b.host_steps[layer] = 0;
   b.host_xy[layer].clear();
   b.host_poly[layer].clear();
   b.keep_seq[layer] = false;
@@ -1370,7 +1426,7 @@ int stg_rt_sync(stg_rt_ctx *c)
   if ((rc = deliver_locked(c)))
     return rc;
   CU(c, cudaStreamSynchronize(c->stream));
-  return STG_RT_OK;
+  return device_errors_locked(c);
 }
 
 void *stg_rt_host_alloc(stg_rt_ctx *c, size_t bytes)
@@ -1661,10 +1717,35 @@ int stg_rt_delta_export(stg_rt_ctx *c, int rank, void **dev_blob, size_t *n_byte
   if (rc)
     return rc;
   c->last_export_rank = rank;
+  c->export_mode = true;
   // the entry accounting of exported deltas happens here for this rank's own share
   if ((rc = build_and_send_deltas(c, false, rank, n_bytes)))
     return rc;
   *dev_blob = c->d_blob.p;
+  return STG_RT_OK;
+}
+
+int stg_rt_stream_signal(stg_rt_ctx *c, void *consumer_stream)
+{
+  if (!c)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if ((cudaStream_t)consumer_stream == c->stream)
+    return STG_RT_OK;
+  CU(c, cudaEventRecord(c->xstream_ev, c->stream));
+  CU(c, cudaStreamWaitEvent((cudaStream_t)consumer_stream, c->xstream_ev, 0));
+  return STG_RT_OK;
+}
+
+int stg_rt_stream_wait(stg_rt_ctx *c, void *producer_stream)
+{
+  if (!c)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if ((cudaStream_t)producer_stream == c->stream)
+    return STG_RT_OK;
+  CU(c, cudaEventRecord(c->xstream_ev, (cudaStream_t)producer_stream));
+  CU(c, cudaStreamWaitEvent(c->stream, c->xstream_ev, 0));
   return STG_RT_OK;
 }
 
@@ -1679,21 +1760,24 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_r
   // Table accounting needs what the OTHER ranks inserted / removed, which only their headers (now on
   // the device) know. They are read back asynchronously and booked one exchange late, so the host
   // never waits for the GPU here; until then this tick is charged like the last one (the compaction
-  // threshold of 3/4 leaves ample slack for a tick's worth of error).
+  // threshold of 3/4 and the half-empty rule leave ample slack for a tick's worth of error; an insert that
+  // finds no slot all the same raises kErrTableFull on the device and fails the next stg_rt_sync).
   if (c->hdrs_pending) {
     CU(c, cudaEventSynchronize(c->hdrs_ready));
     const DeltaHeader *h = (const DeltaHeader *)c->h_hdrs.p;
-    int64_t other_ins = 0, other_rem = 0, all_ins = 0;
+    int64_t all_ins[2] = { 0, 0 };
     for (int r = 0; r < c->hdrs_ranks; r++) {
-      all_ins += h[r].steps_insert;
-      if ((int)h[r].rank != c->last_export_rank) {
-        other_ins += h[r].steps_insert;
-        other_rem += h[r].steps_remove;
+      if (h[r].magic != kDeltaMagic)
+        continue; // K1 skipped it and said so
+      c->epoch = std::max<uint64_t>(c->epoch, h[r].epoch); // the epoch that pass really used
+      for (int L = 0; L < 2; L++) {
+        all_ins[L] += h[r].steps_insert_l[L];
+        if ((int)h[r].rank != c->last_export_rank) // this rank's own share was booked at export; the others' net change, signed
+          c->live_entries[L] += (int64_t)h[r].steps_insert_l[L] - (int64_t)h[r].steps_remove_l[L];
       }
     }
-    for (int L = 0; L < 2; L++) // the headers do not split layers: charge both (upper bound)
-      c->live_entries[L] += std::max<int64_t>(other_ins - other_rem, 0);
-    c->last_gather_ins = all_ins;
+    for (int L = 0; L < 2; L++)
+      c->last_gather_ins[L] = all_ins[L];
     c->hdrs_pending = false;
   }
   int rcp = pin_reserve(c, c->h_hdrs, (size_t)n_ranks * sizeof(DeltaHeader));
@@ -1704,9 +1788,14 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_r
   CU(c, cudaEventRecord(c->hdrs_ready, c->stream));
   c->hdrs_pending = true;
   c->hdrs_ranks = n_ranks;
-  const int64_t ins = std::max<int64_t>(c->last_gather_ins, (int64_t)n_ranks * c->last_export_ins);
-  const int64_t add[2] = { ins, ins };
-  c->epoch++;
+  int64_t add[2];
+  for (int L = 0; L < 2; L++) {
+    add[L] = std::max<int64_t>(c->last_gather_ins[L], (int64_t)n_ranks * c->last_export_ins[L]);
+    if (c->live_entries[L] + add[L] > (int64_t)c->slot_cap / 2)
+      return fail(c, STG_RT_ENOMEM, "cell-entry table of layer %d full (%lld entries + %lld arriving, capacity %u/2); raise max_cell_entries",
+                  L, (long long)c->live_entries[L], (long long)add[L], c->slot_cap);
+  }
+  c->epoch++; // K1 takes the largest proposal among the blobs, which is at least this (every sender proposed its own epoch + 1)
   CU(c, cudaEventRecord(c->t_ev[0][0], c->stream));
   launch_apply_deltas(c->g, (const unsigned char *)dev_gathered, n_ranks, slot_bytes, c->epoch, 0, c->stream,
                       &c->stats.launches_rasterise);
@@ -2365,6 +2454,27 @@ int stg_rt_debug_headings(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *fans
     if (b->p)
       cudaFree(b->p);
   return rc;
+}
+
+uint32_t stg_rt_ranger_rand_advance(uint32_t n_samples, uint32_t n_in_range)
+{
+  static bool have_spare = false; // generateGaussianNoise's static of the same name, model_ranger.cc:183
+  uint32_t draws = 0;
+  for (uint32_t t = 0; t < n_samples; t++, draws++)
+    (void)rand(); // the heading jitter's simpleNoise(), :237
+  for (uint32_t t = 0; t < n_in_range; t++) {
+    (void)rand(); // range_noise * simpleNoise(), :245
+    draws++;
+    if (have_spare) { // generateGaussianNoise(range_noise_const), :246 -> :186-189
+      have_spare = false;
+    } else {
+      have_spare = true;
+      (void)rand(); // rand1, :193
+      (void)rand(); // rand2, :197
+      draws += 2;
+    }
+  }
+  return draws;
 }
 
 int stg_rt_kernel_times(stg_rt_ctx *c, float ms[3])

@@ -82,6 +82,12 @@ constexpr uint32_t kRecGripper = 1u << 31;  // vis.gripper_return
 constexpr uint32_t kRecObstacle = 1u << 29; // vis.obstacle_return
 constexpr uint32_t kRecRootMask = (1u << 29) - 1u;
 constexpr uint32_t kOwnerNone = 0u, kOwnerMixed = 0xffffffffu;
+// BlockRec::seq = epoch (36 bits) | rank (8 bits) | call order within the rank's blob (20 bits): the order of the
+// latest Map across the whole job. An epoch is one K1 pass; 2^36 of them is 79 days at 10,000 passes a second.
+constexpr int kSeqEpochShift = 28, kSeqRankShift = 20;
+constexpr uint32_t kSeqLocalMax = (1u << kSeqRankShift) - 1u;
+// device-side error bits (GridView::err_host, a word of page-locked host memory the kernels OR into)
+constexpr uint32_t kErrTableFull = 1u, kErrBadBlob = 2u, kErrOutOfExtent = 4u;
 constexpr uint32_t kOwnerNever = 0xfffffffeu; // a finder tag that matches no region
 
 struct GridView {
@@ -98,6 +104,7 @@ struct GridView {
   uint32_t *mdl_root;
   double *mdl_ranger_return;
   uint32_t *mdl_flags;
+  uint32_t *err_host;    // page-locked host word: kErr* bits raised by K1 (read by stg_rt_sync)
 };
 
 // ---- moved-block delta blob (host -> device, and rank -> rank through the all-gather) ----------
@@ -106,9 +113,14 @@ struct DeltaHeader {
   uint32_t n_remove, n_insert;       // edge records: removals first, then insertions
   uint32_t n_block_upd, n_model_upd;
   uint32_t steps_remove, steps_insert; // total cell visits of the remove / insert edges
-  uint32_t rank, reserved;
+  uint32_t rank, magic;              // kDeltaMagic: K1 refuses a slot that does not carry it (a torn or stale gather)
+  uint32_t steps_remove_l[2], steps_insert_l[2]; // the same per layer: every replica books the other ranks' net change
+  uint32_t n_bytes;                  // size of the whole blob; K1 checks the counts against it and against the slot
+  uint32_t n_pose_upd;               // PoseUpd records after the model updates (outlines derived on the device)
+  unsigned long long epoch;          // the sender's next epoch; a gathered pass uses the largest one it finds
 };
-static_assert(sizeof(DeltaHeader) == 32, "DeltaHeader");
+static_assert(sizeof(DeltaHeader) == 64, "DeltaHeader");
+constexpr uint32_t kDeltaMagic = 0x53544744u; // "STGD"
 
 // One polygon edge = one integer line of World::MapPoly (world.cc:995-1052): start cell included,
 // end cell excluded, n_steps = |dx| + |dy| cell visits. first_step = running sum within its group.

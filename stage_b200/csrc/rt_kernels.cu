@@ -59,12 +59,14 @@ struct CellAddr {
   uint32_t region; // row-major region index inside the extent
   uint32_t key;    // region*1024 + cy*32 + cx
   uint32_t cx, cy;
+  bool inside;     // the cell lies in the device extent (the host checks every outline; a record that fails here is corrupt)
 };
 
 __device__ __forceinline__ CellAddr cell_addr(const GridView &g, int32_t x, int32_t y)
 {
   CellAddr c;
   const int32_t rix = (x >> kRBits) - g.rx0, riy = (y >> kRBits) - g.ry0;
+  c.inside = (uint32_t)rix < (uint32_t)g.nrx && (uint32_t)riy < (uint32_t)g.nry;
   c.region = (uint32_t)(riy * g.nrx + rix);
   c.cx = (uint32_t)x & (kRegionWidth - 1);
   c.cy = (uint32_t)y & (kRegionWidth - 1);
@@ -85,17 +87,42 @@ struct BlobView {
   const EdgeRec *remove_edges, *insert_edges;
   const BlockUpd *block_upd;
   const ModelUpd *model_upd;
+  uint32_t n_remove, n_insert, n_block_upd, n_model_upd; // 0 for a slot that does not hold a well-formed blob
 };
+
+// A slot holds a blob only if it says so itself: the magic word, and record counts that add up to its own size and
+// fit the slot. Anything else (a gather that ran before the export had landed, a stale or foreign buffer) is treated as
+// an empty blob and reported through GridView::err_host, so a torn header can never index past its slot.
+__device__ __forceinline__ bool blob_ok(const DeltaHeader *h, size_t slot_bytes)
+{
+  if (h->magic != kDeltaMagic)
+    return false;
+  const unsigned long long need = sizeof(DeltaHeader) + ((unsigned long long)h->n_remove + h->n_insert) * sizeof(EdgeRec) +
+                                  (unsigned long long)h->n_block_upd * sizeof(BlockUpd) + (unsigned long long)h->n_model_upd * sizeof(ModelUpd);
+  return need <= slot_bytes && need == h->n_bytes && h->n_pose_upd == 0u && h->steps_remove == h->steps_remove_l[0] + h->steps_remove_l[1] &&
+         h->steps_insert == h->steps_insert_l[0] + h->steps_insert_l[1];
+}
+
+__device__ __forceinline__ void raise_error(const GridView &g, uint32_t bit)
+{
+  if (g.err_host)
+    *reinterpret_cast<volatile uint32_t *>(g.err_host) = bit; // a plain store: any non-zero value fails the next stg_rt_sync
+}
 
 __device__ __forceinline__ BlobView blob_view(const unsigned char *blobs, int rank, size_t slot_bytes)
 {
   BlobView v;
   const unsigned char *p = blobs + (size_t)rank * slot_bytes;
   v.hdr = reinterpret_cast<const DeltaHeader *>(p);
+  const bool ok = blob_ok(v.hdr, slot_bytes);
+  v.n_remove = ok ? v.hdr->n_remove : 0u;
+  v.n_insert = ok ? v.hdr->n_insert : 0u;
+  v.n_block_upd = ok ? v.hdr->n_block_upd : 0u;
+  v.n_model_upd = ok ? v.hdr->n_model_upd : 0u;
   v.remove_edges = reinterpret_cast<const EdgeRec *>(p + sizeof(DeltaHeader));
-  v.insert_edges = v.remove_edges + v.hdr->n_remove;
-  v.block_upd = reinterpret_cast<const BlockUpd *>(v.insert_edges + v.hdr->n_insert);
-  v.model_upd = reinterpret_cast<const ModelUpd *>(v.block_upd + v.hdr->n_block_upd);
+  v.insert_edges = v.remove_edges + v.n_remove;
+  v.block_upd = reinterpret_cast<const BlockUpd *>(v.insert_edges + v.n_insert);
+  v.model_upd = reinterpret_cast<const ModelUpd *>(v.block_upd + v.n_block_upd);
   return v;
 }
 
@@ -107,14 +134,17 @@ __device__ __forceinline__ BlobView blob_view(const unsigned char *blobs, int ra
 constexpr int kMaxRanksFlat = 64;
 
 template <bool kInsert>
-__device__ __forceinline__ void k1_step_prefix(const unsigned char *blobs, int n_ranks, size_t slot_bytes, uint32_t *prefix)
+__device__ __forceinline__ void k1_step_prefix(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes, uint32_t *prefix)
 {
   if (threadIdx.x == 0) {
     uint32_t run = 0;
     for (int r = 0; r < n_ranks; r++) {
       prefix[r] = run;
       const DeltaHeader *h = reinterpret_cast<const DeltaHeader *>(blobs + (size_t)r * slot_bytes);
-      run += kInsert ? h->steps_insert : h->steps_remove;
+      if (blob_ok(h, slot_bytes))
+        run += kInsert ? h->steps_insert : h->steps_remove;
+      else if (blockIdx.x == 0)
+        raise_error(g, kErrBadBlob);
     }
     prefix[n_ranks] = run;
   }
@@ -129,13 +159,26 @@ __device__ __forceinline__ int k1_rank_of(const uint32_t *prefix, int n_ranks, u
   return r;
 }
 
+// The epoch of a pass: the largest one any of its blobs proposes (every sender proposes its own next epoch; replicas
+// that exchanged the same blobs therefore stamp the same sequence numbers, whatever each did locally before).
+__device__ __forceinline__ unsigned long long k1_pass_epoch(const unsigned char *blobs, int n_ranks, size_t slot_bytes, unsigned long long epoch)
+{
+  for (int r = 0; r < n_ranks; r++) {
+    const DeltaHeader *h = reinterpret_cast<const DeltaHeader *>(blobs + (size_t)r * slot_bytes);
+    if (blob_ok(h, slot_bytes) && h->epoch > epoch)
+      epoch = h->epoch;
+  }
+  return epoch;
+}
+
 __device__ __forceinline__ void k1_table_updates(const GridView &g, const unsigned char *blobs, int n_ranks,
                                                  size_t slot_bytes, unsigned long long epoch)
 {
+  epoch = k1_pass_epoch(blobs, n_ranks, slot_bytes, epoch);
   for (int rank = 0; rank < n_ranks; rank++) {
     const BlobView v = blob_view(blobs, rank, slot_bytes);
     const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint32_t i = t0; i < v.hdr->n_model_upd; i += stride) {
+    for (uint32_t i = t0; i < v.n_model_upd; i += stride) {
       const ModelUpd u = v.model_upd[i];
       if (u.id < g.n_models) {
         g.mdl_root[u.id] = u.root;
@@ -143,7 +186,7 @@ __device__ __forceinline__ void k1_table_updates(const GridView &g, const unsign
         g.mdl_flags[u.id] = u.flags;
       }
     }
-    for (uint32_t i = t0; i < v.hdr->n_block_upd; i += stride) {
+    for (uint32_t i = t0; i < v.n_block_upd; i += stride) {
       const BlockUpd u = v.block_upd[i];
       if (u.block < g.n_blocks) {
         // A block rendered before this pass changes trees (its model was re-parented, or the id now names a
@@ -152,7 +195,7 @@ __device__ __forceinline__ void k1_table_updates(const GridView &g, const unsign
         // block's own Map record may be applied by another thread right now) does not count.
         if ((g.blk_rec[0][u.block].root_flags ^ u.root_flags) & kRecRootMask) {
           const unsigned long long s0 = g.blk_rec[0][u.block].seq, s1 = g.blk_rec[1][u.block].seq;
-          if ((s0 && (s0 >> 40) != epoch) || (s1 && (s1 >> 40) != epoch))
+          if ((s0 && (s0 >> kSeqEpochShift) != epoch) || (s1 && (s1 >> kSeqEpochShift) != epoch))
             g.reg_owner[g.n_regions] = 1u;
         }
         for (int L = 0; L < 2; L++) { // z bounds and ownership are per block: both layers see them
@@ -164,8 +207,8 @@ __device__ __forceinline__ void k1_table_updates(const GridView &g, const unsign
         }
         // insertion order across the whole job: epoch, then rank, then call order within the rank
         if (!(u.layer & kUpdKeepSeq))
-          g.blk_rec[u.layer & 1][u.block].seq =
-              (epoch << 40) | ((unsigned long long)(v.hdr->rank & 0xff) << 32) | u.seq_local;
+          g.blk_rec[u.layer & 1][u.block].seq = (epoch << kSeqEpochShift) |
+                                                ((unsigned long long)(v.hdr->rank & 0xff) << kSeqRankShift) | (u.seq_local & kSeqLocalMax);
       }
     }
   }
@@ -180,10 +223,14 @@ __device__ __forceinline__ void k1_remove(const GridView &g, const unsigned char
       const int rank = k1_rank_of(prefix, n_ranks, tt);
       const BlobView v = blob_view(blobs, rank, slot_bytes);
       const uint32_t t = tt - prefix[rank];
-      const EdgeRec e = v.remove_edges[find_edge(v.remove_edges, v.hdr->n_remove, t)];
+      const EdgeRec e = v.remove_edges[find_edge(v.remove_edges, v.n_remove, t)];
       int32_t x, y;
       edge_cell(e, t - e.first_step, x, y);
       const CellAddr c = cell_addr(g, x, y);
+      if (!c.inside || e.block >= g.n_blocks) {
+        raise_error(g, kErrOutOfExtent);
+        continue;
+      }
       const unsigned long long entry = ((unsigned long long)c.key << 32) | (unsigned long long)(e.block + 1u);
       unsigned long long *slots = g.slots[e.layer & 1];
       uint32_t h = slot_home(c.key, g.slot_mask);
@@ -213,10 +260,14 @@ __device__ __forceinline__ void k1_fixup(const GridView &g, const unsigned char 
       const int rank = k1_rank_of(prefix, n_ranks, tt);
       const BlobView v = blob_view(blobs, rank, slot_bytes);
       const uint32_t t = tt - prefix[rank];
-      const EdgeRec e = v.remove_edges[find_edge(v.remove_edges, v.hdr->n_remove, t)];
+      const EdgeRec e = v.remove_edges[find_edge(v.remove_edges, v.n_remove, t)];
       int32_t x, y;
       edge_cell(e, t - e.first_step, x, y);
       const CellAddr c = cell_addr(g, x, y);
+      if (!c.inside || e.block >= g.n_blocks) {
+        raise_error(g, kErrOutOfExtent);
+        continue;
+      }
       const unsigned long long *slots = g.slots[e.layer & 1];
       uint32_t h = slot_home(c.key, g.slot_mask);
       for (uint32_t probes = 0; probes <= g.slot_mask; probes++) {
@@ -244,22 +295,33 @@ __device__ __forceinline__ void k1_insert(const GridView &g, const unsigned char
       const int rank = k1_rank_of(prefix, n_ranks, tt);
       const BlobView v = blob_view(blobs, rank, slot_bytes);
       const uint32_t t = tt - prefix[rank];
-      const EdgeRec e = v.insert_edges[find_edge(v.insert_edges, v.hdr->n_insert, t)];
+      const EdgeRec e = v.insert_edges[find_edge(v.insert_edges, v.n_insert, t)];
       int32_t x, y;
       edge_cell(e, t - e.first_step, x, y);
       const CellAddr c = cell_addr(g, x, y);
+      if (!c.inside || e.block >= g.n_blocks) {
+        raise_error(g, kErrOutOfExtent);
+        continue;
+      }
       const unsigned long long entry = ((unsigned long long)c.key << 32) | (unsigned long long)(e.block + 1u);
       unsigned long long *slots = g.slots[e.layer & 1];
       uint32_t h = slot_home(c.key, g.slot_mask);
+      bool placed = false;
       for (uint32_t probes = 0; probes <= g.slot_mask;) {
         const unsigned long long cur = ld_slot(slots + h);
         if (cur == kSlotEmpty || cur == kSlotTomb) {
-          if (atomicCAS(slots + h, cur, entry) == cur)
+          if (atomicCAS(slots + h, cur, entry) == cur) {
+            placed = true;
             break;
+          }
           continue; // lost the race for this slot: look at it again
         }
         h = (h + 1) & g.slot_mask;
         probes++;
+      }
+      if (!placed) { // every slot taken: no entry, so no count and no mask bit either (a bit nothing resolves would make
+        raise_error(g, kErrTableFull); // the cell transparent and the region count could never return to zero)
+        continue;
       }
       atomicAdd(g.reg_count + c.region, 1u);
       { // region owner: stays a tree's tag only while every entry added belongs to that tree
@@ -287,7 +349,7 @@ __global__ void __launch_bounds__(256) k1_phase0(GridView g, const unsigned char
   for (int r0 = 0; r0 < n_ranks; r0 += kMaxRanksFlat) { // one pass unless there are more ranks than that
     const int nr = min(n_ranks - r0, kMaxRanksFlat);
     const unsigned char *part = blobs + (size_t)r0 * slot_bytes;
-    k1_step_prefix<false>(part, nr, slot_bytes, prefix);
+    k1_step_prefix<false>(g, part, nr, slot_bytes, prefix);
     k1_remove(g, part, nr, slot_bytes, prefix);
     __syncthreads();
   }
@@ -302,10 +364,10 @@ __global__ void __launch_bounds__(256) k1_phase1(GridView g, const unsigned char
   for (int r0 = 0; r0 < n_ranks; r0 += kMaxRanksFlat) {
     const int nr = min(n_ranks - r0, kMaxRanksFlat);
     const unsigned char *part = blobs + (size_t)r0 * slot_bytes;
-    k1_step_prefix<false>(part, nr, slot_bytes, prefix);
+    k1_step_prefix<false>(g, part, nr, slot_bytes, prefix);
     k1_fixup(g, part, nr, slot_bytes, prefix);
     __syncthreads();
-    k1_step_prefix<true>(part, nr, slot_bytes, prefix);
+    k1_step_prefix<true>(g, part, nr, slot_bytes, prefix);
     k1_insert(g, part, nr, slot_bytes, prefix);
     __syncthreads();
   }
@@ -355,7 +417,7 @@ __global__ void __launch_bounds__(256) k1_rehash(const unsigned long long *src, 
     if (cur == kSlotEmpty || cur == kSlotTomb)
       continue;
     uint32_t h = slot_home((uint32_t)(cur >> 32), slot_mask);
-    for (;;) {
+    for (uint32_t probes = 0; probes <= slot_mask; probes++) { // the destination is as large as the source: a free slot exists
       if (atomicCAS(dst + h, kSlotEmpty, cur) == kSlotEmpty)
         break;
       h = (h + 1) & slot_mask;

@@ -46,15 +46,30 @@ class DeltaExchange:
         self.gathered = torch.empty(self.slot * world_size, dtype=torch.uint8, device=device)
         self.bytes_exported = 0
 
+    def _collective_stream(self):
+        """the stream torch queues this process's collectives and copies on (the device tests pass a fake ctx / cpu tensors)"""
+        if self.gathered.device.type != "cuda":
+            return None
+        import torch
+        return torch.cuda.current_stream(self.gathered.device).cuda_stream
+
     def step(self):
         """export this rank's queued deltas, all-gather, apply every rank's in rank order"""
         ptr, nbytes = self.ctx.delta_export(self.rank)
         self.bytes_exported += nbytes
         mine = self.as_tensor(ptr, self.slot)
+        # The blob is uploaded on the context's stream, the collective runs on torch's current stream and K1 reads
+        # the gathered buffer on the context's stream again: order the three explicitly (include/stg_rt.h,
+        # stg_rt_delta_export). Both calls are no-ops when the context has been given torch's stream.
+        cs = self._collective_stream()
+        if cs is not None:
+            self.ctx.stream_signal(cs)
         if self.world_size > 1:
             self.dist.all_gather_into_tensor(self.gathered, mine)
         else:
             self.gathered.copy_(mine)
+        if cs is not None:
+            self.ctx.stream_wait(cs)
         self.ctx.delta_apply_gathered(self.gathered.data_ptr(), self.world_size, self.slot)
 
 

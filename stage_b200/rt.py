@@ -117,6 +117,9 @@ def lib():
         "stg_rt_delta_export": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(sz)]),
         "stg_rt_delta_slot_bytes": (sz, [vp]),
         "stg_rt_delta_apply_gathered": (ctypes.c_int, [vp, vp, ctypes.c_int, sz]),
+        "stg_rt_stream_signal": (ctypes.c_int, [vp, vp]),
+        "stg_rt_stream_wait": (ctypes.c_int, [vp, vp]),
+        "stg_rt_ranger_rand_advance": (u32, [u32, u32]),
         "stg_rt_set_stream": (ctypes.c_int, [vp, vp]),
         "stg_rt_get_stream": (vp, [vp]),
         "stg_rt_get_stats": (ctypes.c_int, [vp, ctypes.POINTER(Stats)]),
@@ -138,7 +141,7 @@ EXPORTED_SYMBOLS = (
     "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_fiducials_submit_packed stg_rt_rangers_submit stg_rt_collisions_test stg_rt_touching_models stg_rt_models_move stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
-    "stg_rt_delta_apply_gathered stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_debug_trig stg_rt_debug_headings stg_rt_debug_region_owners").split()
+    "stg_rt_delta_apply_gathered stg_rt_stream_signal stg_rt_stream_wait stg_rt_ranger_rand_advance stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_debug_trig stg_rt_debug_headings stg_rt_debug_region_owners").split()
 
 
 _BYTES0 = ctypes.c_char * 0
@@ -431,6 +434,12 @@ class Context:
 
     def delta_apply_gathered(self, dev_ptr, n_ranks, slot_bytes):
         self._check(self._L.stg_rt_delta_apply_gathered(self._h, dev_ptr, n_ranks, slot_bytes))
+
+    def stream_signal(self, consumer_stream):
+        self._check(self._L.stg_rt_stream_signal(self._h, consumer_stream))
+
+    def stream_wait(self, producer_stream):
+        self._check(self._L.stg_rt_stream_wait(self._h, producer_stream))
 
     def set_stream(self, cuda_stream):
         self._check(self._L.stg_rt_set_stream(self._h, cuda_stream))
