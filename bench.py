@@ -44,6 +44,11 @@ def parse_args():
     ap.add_argument("--half-extent", type=float, default=81.92)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--only", default="all", choices=["all", "c3", "c4", "c5"],
+                    help="all (default): the config-3 line with configs 4 and 5 as sub-records under `configs`; c3 / c4 / c5: that one alone")
+    ap.add_argument("--c4-robots", type=int, default=100000, help="config 4: robots in total (sharded over the GPUs)")
+    ap.add_argument("--c4-max-fiducials", type=int, default=64, help="config 4: records kept per finder (the counts are exact beyond it)")
+    ap.add_argument("--c5-pucks", type=int, default=10000, help="config 5: pucks in total, all moved every tick")
     ap.add_argument("--workload", default="c3", choices=["c3", "cave"],
                     help="c3 = BASELINE config 3 (the default, the judged line); cave = the denser variant of SURVEY.md 8(d): "
                          "worlds/bitmaps/cave.png tiled 10x10 (no reference arm: value / e2e / roofline only)")
@@ -258,6 +263,14 @@ def run_reference(args):
 # this repo's path
 # ---------------------------------------------------------------------------------------------
 
+def peak_hbm_gbs():
+    """(GB/s, where it came from): the driver-measured copy bandwidth of this pool's B200s, else the profiling guide's fallback"""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6650.0, "fallback 6650 (B200_PROFILING.md)"
+
+
 def pin_to_gpu_numa(local_rank):
     """Restrict this process to the CPUs of the NUMA node the GPU is attached to; returns the node or None."""
     try:
@@ -316,6 +329,20 @@ def run_ours(args):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
+
+    if args.only in ("c4", "c5"):   # development aid: one of the sub-records alone, without the config-3 line around it
+        import bench_swarm
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)
+        env = bench_swarm.Env(torch, dist if n_gpus > 1 else None, rank, n_gpus, local_rank, stream, peak_hbm_gbs()[0], ClockSampler)
+        rec = bench_swarm.run_c4(env, args) if args.only == "c4" else bench_swarm.run_c5(env, args, FOV_DEG, SAMPLES, RANGE_MAX)
+        if rank == 0:
+            print(json.dumps(dict(rec, n_gpus=n_gpus, steps=args.steps, warmup=max(args.warmup, 3), higher_is_better=True, vs_baseline=None,
+                                  dtype="f64", data="synthetic", config={"workload": rec["workload"]})))
+        if n_gpus > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        leave(0)
 
     world = make_workload(args, n_gpus)
     x0, y0, nx, ny = world.sreg_extent()
@@ -393,9 +420,10 @@ def run_ours(args):
     # is at least 20 ticks (said in `config.e2e_warmup_ticks`); the timed region is exactly K ticks either way
     nw_e2e = max(args.warmup, 3, 20)
     n_e2e = args.steps + nw_e2e
-    poses = [world.robots[lo:hi]]
+    poses_all = [world.robots]
     for t in range(n_e2e):
-        poses.append(worldgen.step_robots(world, poses[-1], t))
+        poses_all.append(worldgen.step_robots(world, poses_all[-1], t))
+    poses = [p[lo:hi] for p in poses_all]
     ticks = []   # what libstage's Move() / Sensor::Update would hand over each tick (caller-side work)
     for t in range(1, n_e2e + 1):
         polys = worldgen.robot_polygons(world, poses[t])
@@ -489,13 +517,26 @@ def run_ours(args):
                       "max_range_err_m": float(np.max(np.abs(g.ranges - h["range"]))),
                       "how": "device trig; grid loaded from the reference's recorded Map/UnMap calls; vs the unmodified reference's World::Raytrace on this host"}
 
+    peak, peak_source = peak_hbm_gbs()
+    import bench_swarm
+    env = bench_swarm.Env(torch, dist if n_gpus > 1 else None, rank, n_gpus, local_rank, stream, peak, ClockSampler)
+    # every rank: a sample of its own rays of the last e2e tick against the T1 oracle, and its grid against the oracle's
+    # and every other rank's (the only parity there is at N > 1; at N = 1 it stands next to the whole-tick check against
+    # the unmodified reference above)
+    parity_ranks = None
+    if args.workload == "c3":
+        T = n_e2e
+        n_all = args.robots * n_gpus
+        movers = [(world.n_static_blocks, world.robot_ids, world.robot_size[2], lambda t: worldgen.robot_boxes(world, poses_all[t]), n_all)]
+        parity_ranks = bench_swarm.laser_parity(env, ctx, world, movers, T, ticks[-1]["fans"], out.ranges, SAMPLES)
+    ctx.close()
+    configs = {}
+    if args.only in ("all", "c4") and args.workload == "c3":
+        configs["c4"] = bench_swarm.run_c4(env, args)
+    if args.only in ("all", "c5") and args.workload == "c3":
+        configs["c5"] = bench_swarm.run_c5(env, args, FOV_DEG, SAMPLES, RANGE_MAX)
+
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None
         try:  # DRAM bytes per launch of the march kernel from the committed ncu --set full capture
             traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["dram_bytes_per_launch"]
@@ -519,14 +560,14 @@ def run_ours(args):
             "kernel_ms": {"ray_march": march_avg_ms, "fan_headings": float(np.mean(head_ms)),
                           "share_of_step": march_avg_ms / (t_value_ms / args.steps) if n_gpus == 1 else None},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "traffic": traffic, "peak_source": peak_source,
                          "algorithmic_bytes_per_launch": algo_bytes, "cell_visits": C, "region_probes": R,
                          "beams": n_beams, "hit_fraction": hit_frac,
                          "note": "bytes = 4*C + 4*R + 40 per beam (SURVEY.md 8d), C/R counted by the kernel and proven equal to the oracle's in tests"},
-            "cpu_baseline": cpu, "parity_vs_reference": parity, "clocks": clocks,
+            "cpu_baseline": cpu, "parity_vs_reference": parity, "parity": parity_ranks, "clocks": clocks,
+            "configs": configs,
         }
         print(json.dumps(line))
-    ctx.close()
     if n_gpus > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -396,6 +396,14 @@ uint64_t stg_rt_set_beams(const stg_rt_set *set);
 int64_t stg_rt_grid_dump(stg_rt_ctx *ctx, int32_t *records, int64_t cap, int64_t *region_counts,
                          int64_t counts_cap, int64_t *n_counts);
 
+/* A digest of the whole device grid without moving it: out[0], out[1] = per layer, the sum over every distinct
+   (cell, block) entry of a 64-bit mix of (x, y, block, position of the block in Cell::blocks[layer] order); out[2],
+   out[3] = the number of such entries per layer; out[4] = the same kind of sum over (region, Region::count). Two grids
+   agree on all five iff they hold the same blocks in the same order in every cell (up to 2^-64). Replicas of a
+   multi-GPU run compare it with each other; the tests compare it with the digest a CPU restatement of the reference takes of its own lists.
+   Synchronous. */
+int stg_rt_grid_hash(stg_rt_ctx *ctx, uint64_t out[5]);
+
 /* The region owner tags the march uses to walk through regions that hold nothing but the finder's own
    tree (no counterpart in the reference: an acceleration that must never change a result; tests check
    its invariant against the grid). int64[3] {rx, ry, tag} per region with a non-zero tag; tag = root
@@ -472,6 +480,10 @@ int stg_rt_get_stats(stg_rt_ctx *ctx, stg_rt_stats *out);
    ms[1] = fan headings (K2a), ms[2] = ray march with fused epilogue (K2+K3). -1 = never launched.
    Waits for the stream. */
 int stg_rt_kernel_times(stg_rt_ctx *ctx, float ms[3]);
+/* The same for the first n of: [0] delta application (K1), [1] fan headings (K2a), [2] ray march (K2 + ranger
+   epilogue), [3] fiducial finders (K3: candidate query, line-of-sight rays, packing), [4] blobfinders (scan fan +
+   segmentation), [5] collision tests / touching models (K4, K4b). -1 = never launched. */
+int stg_rt_kernel_times_ex(stg_rt_ctx *ctx, float *ms, int n);
 
 #ifdef __cplusplus
 }

@@ -628,6 +628,68 @@ int64_t t1_dump_grid(void *wv, int32_t *out, int64_t cap, int64_t *counts, int64
   return n;
 }
 
+// n times { Block::UnMap(layer); Block::Map(layer) } in one call (what ModelPosition::Move does to the grid for
+// n moving models, model_position.cc:549-552): the loop a caller of t1_block_unmap / t1_block_map would write.
+int t1_blocks_remap(void *wv, uint32_t n, const uint32_t *blocks, const uint32_t *models, int layer, const double *z,
+                    const uint32_t *first_pt, const int32_t *xy)
+{
+  for (uint32_t i = 0; i < n; i++) {
+    const T1World *w = (const T1World *)wv;
+    if (blocks[i] < w->blocks.size() && w->blocks[blocks[i]].known)
+      t1_block_unmap(wv, blocks[i], layer);
+    if (t1_block_map(wv, blocks[i], models[i], layer, z[2 * i], z[2 * i + 1], (int)(first_pt[i + 1] - first_pt[i]), xy + 2 * (size_t)first_pt[i]))
+      return -1;
+  }
+  return 0;
+}
+
+// An order-independent digest of the whole grid, list order included: the sum over every (cell, block) entry of a
+// 64-bit mix of (layer, x, y, position in Cell::blocks[layer], block). Two grids agree on it iff (up to 2^-64) they hold
+// the same blocks in the same order in every cell. The device computes the same sum over its own tables
+// (stg_rt_grid_hash), so replicas can be compared with each other and with this without moving the grid.
+static inline uint64_t t1_mix64(uint64_t z)
+{
+  z ^= z >> 30;
+  z *= 0xbf58476d1ce4e5b9ull;
+  z ^= z >> 27;
+  z *= 0x94d049bb133111ebull;
+  z ^= z >> 31;
+  return z;
+}
+
+void t1_grid_hash(void *wv, uint64_t out[5])
+{
+  const T1World *w = (const T1World *)wv;
+  for (int i = 0; i < 5; i++)
+    out[i] = 0;
+  for (std::unordered_map<int64_t, T1Region *>::const_iterator it = w->regions.begin(); it != w->regions.end(); ++it) {
+    const int32_t grx = (int32_t)(uint32_t)(it->first & 0xffffffff), gry = (int32_t)(it->first >> 32);
+    const T1Region *reg = it->second;
+    if (reg->count)
+      out[4] += t1_mix64(t1_mix64(((uint64_t)(uint32_t)grx << 32) | (uint32_t)gry) ^ ((uint64_t)reg->count * 0x9e3779b97f4a7c15ull));
+    for (int layer = 0; layer < 2; layer++) {
+      if (reg->cells[layer].empty())
+        continue;
+      for (int c = 0; c < REGIONSIZE; c++) {
+        const std::vector<uint32_t> &lst = reg->cells[layer][c];
+        const int32_t x = grx * REGIONWIDTH + (c & (REGIONWIDTH - 1)), y = gry * REGIONWIDTH + (c >> RBITS);
+        uint32_t pos = 0;
+        for (size_t p = 0; p < lst.size(); p++) {
+          bool seen = false; // a block rendered twice into a cell (Map on a mapped block) counts where it first stands
+          for (size_t q = 0; q < p && !seen; q++)
+            seen = lst[q] == lst[p];
+          if (seen)
+            continue;
+          const uint64_t a = ((uint64_t)(uint32_t)x << 32) | (uint32_t)y, b = ((uint64_t)lst[p] << 32) | pos;
+          out[layer] += t1_mix64(t1_mix64(a) ^ (b * 0x9e3779b97f4a7c15ull));
+          out[2 + layer]++;
+          pos++;
+        }
+      }
+    }
+  }
+}
+
 typedef struct {
   uint64_t rays, range_mismatch, model_mismatch, maps, unmaps, ticks;
   uint64_t cell_visits, region_probes;

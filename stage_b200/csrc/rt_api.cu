@@ -19,6 +19,7 @@
 
 namespace stg {
 void launch_rehash(const unsigned long long *src, unsigned long long *dst, uint32_t slot_mask, void *stream);
+void launch_grid_hash(const GridView &g, unsigned long long *out, void *stream);
 }
 
 using namespace stg;
@@ -115,11 +116,11 @@ struct stg_rt_ctx {
   DevBuf d_blob;
   size_t blob_cap = 0;
   cudaEvent_t blob_uploaded = nullptr; // the pinned blob may be rewritten once this has fired
-  cudaEvent_t t_ev[3][2] = {};          // [deltas, headings, march][start, stop]
+  cudaEvent_t t_ev[6][2] = {};          // [deltas, headings, march, fiducials, blobs, collisions / touchers][start, stop]
   cudaStream_t copy_stream = nullptr;   // result copies of chunk i overlap the march of chunk i+1
   cudaEvent_t chunk_ev[8] = {};
   cudaEvent_t copies_done = nullptr;
-  bool t_rec[3] = { false, false, false };
+  bool t_rec[6] = { false, false, false, false, false, false };
 
   // fans queued by stg_rt_fans_submit and not launched yet
   // the queued fan records live in page-locked memory and are uploaded from where the caller's records were
@@ -968,7 +969,7 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
   c->stream = c->own_stream;
   CUC(cudaEventCreateWithFlags(&c->blob_uploaded, cudaEventDisableTiming));
   CUC(cudaEventCreateWithFlags(&c->fans_uploaded, cudaEventDisableTiming));
-  for (int k = 0; k < 3; k++)
+  for (int k = 0; k < 6; k++)
     for (int j = 0; j < 2; j++)
       CUC(cudaEventCreate(&c->t_ev[k][j]));
   CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -1080,7 +1081,7 @@ int stg_rt_destroy(stg_rt_ctx *c)
   if (c->err_host)
     cudaFreeHost(c->err_host);
   cudaStreamDestroy(c->copy_stream);
-  for (int k = 0; k < 3; k++)
+  for (int k = 0; k < 6; k++)
     for (int j = 0; j < 2; j++)
       cudaEventDestroy(c->t_ev[k][j]);
   cudaStreamDestroy(c->own_stream);
@@ -1677,6 +1678,31 @@ int64_t stg_rt_grid_dump(stg_rt_ctx *c, int32_t *records, int64_t cap, int64_t *
   return n;
 }
 
+int stg_rt_grid_hash(stg_rt_ctx *c, uint64_t out[5])
+{
+  if (!c || !out)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = flush_locked(c);
+  if (rc || (rc = deliver_locked(c)))
+    return rc;
+  DevBuf d;
+  if ((rc = dev_reserve(c, d, 5 * 8)))
+    return rc;
+  cudaError_t e = cudaMemsetAsync(d.p, 0, 5 * 8, c->stream);
+  if (e == cudaSuccess) {
+    launch_grid_hash(c->g, (unsigned long long *)d.p, c->stream);
+    c->stats.launches_other++;
+    e = cudaMemcpyAsync(out, d.p, 5 * 8, cudaMemcpyDeviceToHost, c->stream);
+  }
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(c->stream);
+  cudaFree(d.p);
+  if (e != cudaSuccess)
+    return fail(c, STG_RT_ECUDA, "grid_hash: %s", cudaGetErrorString(e));
+  return STG_RT_OK;
+}
+
 int64_t stg_rt_debug_region_owners(stg_rt_ctx *c, int64_t *records, int64_t cap)
 {
   if (!c)
@@ -1892,6 +1918,7 @@ static int fiducials_submit_impl(stg_rt_ctx *c, uint32_t n_targets, const stg_rt
   // Candidate query: brute force over the target list for small problems, a per-submit uniform grid
   // (bins as wide as the longest detection range) beyond ~4 M finder x target pairs.
   // STG_RT_FID_GRID=0/1 forces one or the other (tests compare the two).
+  CU(c, cudaEventRecord(c->t_ev[3][0], c->stream));
   const char *force = getenv("STG_RT_FID_GRID");
   const bool use_grid = force ? atoi(force) != 0 : (uint64_t)n_targets * n_finders > (4u << 20);
   if (use_grid && n_targets) {
@@ -1934,6 +1961,8 @@ static int fiducials_submit_impl(stg_rt_ctx *c, uint32_t n_targets, const stg_rt
   if ((rc = dev_reserve(c, c->d_fid_off, (size_t)(n_finders + 1) * 4)))
     return rc;
   launch_fid_pack(v, (uint32_t *)c->d_fid_off.p, c->h_fid_out.p, (uint32_t *)c->h_fid_count.p, c->stream);
+  CU(c, cudaEventRecord(c->t_ev[3][1], c->stream));
+  c->t_rec[3] = true;
   c->stats.launches_post += 2;
   CU(c, cudaGetLastError());
   c->fid_job.user_out = out;
@@ -2003,7 +2032,10 @@ int stg_rt_collisions_test(stg_rt_ctx *c, int layer, uint32_t n_queries, const u
   v.queries = (const CollisionQuery *)c->d_col_in.p;
   v.edges = (const EdgeRec *)((const char *)c->d_col_in.p + b_q);
   v.hit_model = (int32_t *)c->d_col_hit.p;
+  CU(c, cudaEventRecord(c->t_ev[5][0], c->stream));
   launch_collisions(c->g, v, c->stream);
+  CU(c, cudaEventRecord(c->t_ev[5][1], c->stream));
+  c->t_rec[5] = true;
   c->stats.launches_post++;
   CU(c, cudaGetLastError());
   CU(c, cudaMemcpyAsync(c->h_col_hit.p, c->d_col_hit.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -2066,7 +2098,10 @@ int stg_rt_touching_models(stg_rt_ctx *c, int layer, uint32_t n_queries, const u
   v.edges = (const EdgeRec *)((const char *)c->d_col_in.p + b_q);
   v.out_count = (uint32_t *)c->d_touch_out.p;
   v.out = v.out_count + n_queries;
+  CU(c, cudaEventRecord(c->t_ev[5][0], c->stream));
   launch_touchers(c->g, v, c->stream);
+  CU(c, cudaEventRecord(c->t_ev[5][1], c->stream));
+  c->t_rec[5] = true;
   c->stats.launches_post++;
   CU(c, cudaGetLastError());
   CU(c, cudaMemcpyAsync(c->h_touch_out.p, c->d_touch_out.p, b_out, cudaMemcpyDeviceToHost, c->stream));
@@ -2328,6 +2363,7 @@ int stg_rt_blobs_submit(stg_rt_ctx *c, uint32_t n_finders, const stg_rt_blob_fin
   fv.heading = (double *)c->bd.heading.p;
   fv.ranges = (double *)c->bd.ranges.p;
   fv.hit_model = (int32_t *)c->bd.hit_model.p;
+  CU(c, cudaEventRecord(c->t_ev[4][0], c->stream));
   launch_fan_headings(fv, c->stream);
   launch_ray_march(c->g, fv, c->stream);
   BlobBatchView bv;
@@ -2342,6 +2378,8 @@ int stg_rt_blobs_submit(stg_rt_ctx *c, uint32_t n_finders, const stg_rt_blob_fin
   bv.out = (BlobRec *)c->d_blob_out.p;
   bv.out_count = (uint32_t *)c->d_blob_count.p;
   launch_blobs(c->g, bv, c->stream);
+  CU(c, cudaEventRecord(c->t_ev[4][1], c->stream));
+  c->t_rec[4] = true;
   CU(c, cudaGetLastError());
   c->stats.launches_post += 2;
   c->stats.launches_march += 1;
@@ -2486,6 +2524,20 @@ int stg_rt_kernel_times(stg_rt_ctx *c, float ms[3])
   for (int k = 0; k < 3; k++) {
     ms[k] = -1.0f;
     if (c->t_rec[k])
+      CU(c, cudaEventElapsedTime(&ms[k], c->t_ev[k][0], c->t_ev[k][1]));
+  }
+  return STG_RT_OK;
+}
+
+int stg_rt_kernel_times_ex(stg_rt_ctx *c, float *ms, int n)
+{
+  if (!c || !ms || n < 0)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < n; k++) {
+    ms[k] = -1.0f;
+    if (k < 6 && c->t_rec[k])
       CU(c, cudaEventElapsedTime(&ms[k], c->t_ev[k][0], c->t_ev[k][1]));
   }
   return STG_RT_OK;

@@ -425,6 +425,98 @@ __global__ void __launch_bounds__(256) k1_rehash(const unsigned long long *src, 
   }
 }
 
+// ---- grid digest ----------------------------------------------------------------------------
+// Sum over every distinct (cell, block) entry of a 64-bit mix of (x, y, block, position of the block in the cell's
+// list), per layer, plus a digest of the region counts: what two replicas - or a replica and a CPU
+// world that computes the same sums from its own lists - compare instead of shipping the grid. The position is the number of
+// distinct blocks of the cell that come earlier in Cell::blocks[layer] order (smaller seq).
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+  z ^= z >> 30;
+  z *= 0xbf58476d1ce4e5b9ull;
+  z ^= z >> 27;
+  z *= 0x94d049bb133111ebull;
+  z ^= z >> 31;
+  return z;
+}
+
+__global__ void __launch_bounds__(256) k1_grid_hash(GridView g, unsigned long long *out /* [5] */)
+{
+  unsigned long long h[2] = { 0ull, 0ull }, n[2] = { 0ull, 0ull }, hc = 0ull;
+  const uint64_t slots_n = (uint64_t)g.slot_mask + 1u;
+  for (uint64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * slots_n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const int L = i >= slots_n;
+    const uint32_t at = (uint32_t)(L ? i - slots_n : i);
+    const unsigned long long e = g.slots[L][at];
+    if (e == kSlotEmpty || e == kSlotTomb)
+      continue;
+    const uint32_t key = (uint32_t)(e >> 32), blk = (uint32_t)e - 1u;
+    const unsigned long long seq = g.blk_rec[L][blk].seq;
+    // walk the cell's probe sequence: am I the first copy of this (cell, block)? how many distinct blocks precede me?
+    bool first = true;
+    uint32_t pos = 0;
+    uint32_t hh = slot_home(key, g.slot_mask);
+    for (uint32_t probes = 0; probes <= g.slot_mask; probes++, hh = (hh + 1) & g.slot_mask) {
+      const unsigned long long o = g.slots[L][hh];
+      if (o == kSlotEmpty)
+        break;
+      if ((uint32_t)(o >> 32) != key)
+        continue;
+      if (o == e) {
+        if (hh == at)
+          continue;
+        // another copy of the same entry: the one met first in probe order stands for all of them
+        uint32_t d_me = (at - slot_home(key, g.slot_mask)) & g.slot_mask, d_o = (hh - slot_home(key, g.slot_mask)) & g.slot_mask;
+        if (d_o < d_me)
+          first = false;
+        continue;
+      }
+      const uint32_t ob = (uint32_t)o - 1u;
+      const unsigned long long os = g.blk_rec[L][ob].seq;
+      if (os < seq || (os == seq && ob < blk)) {
+        // count a preceding block once: only at its own first copy in probe order
+        bool o_first = true;
+        uint32_t h2 = slot_home(key, g.slot_mask);
+        for (uint32_t p2 = 0; p2 <= g.slot_mask && h2 != hh; p2++, h2 = (h2 + 1) & g.slot_mask)
+          if (g.slots[L][h2] == o) {
+            o_first = false;
+            break;
+          }
+        pos += o_first ? 1u : 0u;
+      }
+    }
+    if (!first)
+      continue;
+    const uint32_t region = key >> (2 * kRBits), cy = (key >> kRBits) & (kRegionWidth - 1), cx = key & (kRegionWidth - 1);
+    const int32_t x = (g.rx0 + (int32_t)(region % (uint32_t)g.nrx)) * kRegionWidth + (int32_t)cx;
+    const int32_t y = (g.ry0 + (int32_t)(region / (uint32_t)g.nrx)) * kRegionWidth + (int32_t)cy;
+    const unsigned long long a = ((unsigned long long)(uint32_t)x << 32) | (uint32_t)y, b = ((unsigned long long)blk << 32) | pos;
+    h[L] += mix64(mix64(a) ^ (b * 0x9e3779b97f4a7c15ull));
+    n[L]++;
+  }
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < g.n_regions; r += gridDim.x * blockDim.x) {
+    const uint32_t c = g.reg_count[r];
+    if (c) {
+      const int32_t rx = g.rx0 + (int32_t)(r % (uint32_t)g.nrx), ry = g.ry0 + (int32_t)(r / (uint32_t)g.nrx);
+      hc += mix64(mix64(((unsigned long long)(uint32_t)rx << 32) | (uint32_t)ry) ^ ((unsigned long long)c * 0x9e3779b97f4a7c15ull));
+    }
+  }
+  for (int off = 16; off; off >>= 1) {
+    h[0] += __shfl_down_sync(0xffffffffu, h[0], off);
+    h[1] += __shfl_down_sync(0xffffffffu, h[1], off);
+    n[0] += __shfl_down_sync(0xffffffffu, n[0], off);
+    n[1] += __shfl_down_sync(0xffffffffu, n[1], off);
+    hc += __shfl_down_sync(0xffffffffu, hc, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out + 0, h[0]);
+    atomicAdd(out + 1, h[1]);
+    atomicAdd(out + 2, n[0]);
+    atomicAdd(out + 3, n[1]);
+    atomicAdd(out + 4, hc);
+  }
+}
+
 static int delta_grid_blocks()
 {
   static int blocks = 0;
@@ -460,6 +552,11 @@ void launch_owner_rebuild(const GridView &g, void *stream, uint64_t *launch_coun
   k1_owner_done<<<1, 1, 0, s>>>(g);
   if (launch_counter)
     *launch_counter += 3;
+}
+
+void launch_grid_hash(const GridView &g, unsigned long long *out, void *stream)
+{
+  k1_grid_hash<<<delta_grid_blocks(), 256, 0, (cudaStream_t)stream>>>(g, out);
 }
 
 void launch_rehash(const unsigned long long *src, unsigned long long *dst, uint32_t slot_mask, void *stream)

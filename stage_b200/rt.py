@@ -114,6 +114,7 @@ def lib():
         "stg_rt_set_beams": (u64, [vp]),
         "stg_rt_grid_dump": (ctypes.c_int64, [vp, vp, ctypes.c_int64, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
         "stg_rt_debug_region_owners": (ctypes.c_int64, [vp, vp, ctypes.c_int64]),
+        "stg_rt_grid_hash": (ctypes.c_int, [vp, ctypes.POINTER(u64 * 5)]),
         "stg_rt_delta_export": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(sz)]),
         "stg_rt_delta_slot_bytes": (sz, [vp]),
         "stg_rt_delta_apply_gathered": (ctypes.c_int, [vp, vp, ctypes.c_int, sz]),
@@ -124,6 +125,7 @@ def lib():
         "stg_rt_get_stream": (vp, [vp]),
         "stg_rt_get_stats": (ctypes.c_int, [vp, ctypes.POINTER(Stats)]),
         "stg_rt_kernel_times": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_float * 3)]),
+        "stg_rt_kernel_times_ex": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_float * 6), ctypes.c_int]),
         "stg_rt_debug_trig": (ctypes.c_int, [vp, u64, vp, vp]),
         "stg_rt_debug_headings": (ctypes.c_int, [vp, u32, vp, vp, vp]),
     }
@@ -141,7 +143,7 @@ EXPORTED_SYMBOLS = (
     "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_fiducials_submit_packed stg_rt_rangers_submit stg_rt_collisions_test stg_rt_touching_models stg_rt_models_move stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
-    "stg_rt_delta_apply_gathered stg_rt_stream_signal stg_rt_stream_wait stg_rt_ranger_rand_advance stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_debug_trig stg_rt_debug_headings stg_rt_debug_region_owners").split()
+    "stg_rt_delta_apply_gathered stg_rt_stream_signal stg_rt_stream_wait stg_rt_ranger_rand_advance stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_kernel_times_ex stg_rt_debug_trig stg_rt_debug_headings stg_rt_debug_region_owners stg_rt_grid_hash").split()
 
 
 _BYTES0 = ctypes.c_char * 0
@@ -390,6 +392,12 @@ class Context:
         assert n2 == n
         return rec[:n], cnt[:nc.value]
 
+    def grid_hash(self):
+        """(hash[2], entries[2], region_count_hash): the digest stg_rt_grid_hash computes on the device"""
+        out = (ctypes.c_uint64 * 5)()
+        self._check(self._L.stg_rt_grid_hash(self._h, ctypes.byref(out)))
+        return [int(out[0]), int(out[1])], [int(out[2]), int(out[3])], int(out[4])
+
     def region_owners(self):
         """int64[m,3] {rx, ry, tag} of the regions with an owner tag (root + 1, or 0xffffffff = several trees)."""
         n = self._check(self._L.stg_rt_debug_region_owners(self._h, None, 0))
@@ -403,10 +411,11 @@ class Context:
         return {n: getattr(s, n) for n, _ in Stats._fields_}
 
     def kernel_times(self):
-        """dict(deltas_ms, headings_ms, march_ms) of the most recent launches (device time)."""
-        ms = (ctypes.c_float * 3)()
-        self._check(self._L.stg_rt_kernel_times(self._h, ctypes.byref(ms)))
-        return {"deltas_ms": ms[0], "headings_ms": ms[1], "march_ms": ms[2]}
+        """device time of the most recent launch of each kernel group, in ms (-1: never launched)"""
+        ms = (ctypes.c_float * 6)()
+        self._check(self._L.stg_rt_kernel_times_ex(self._h, ctypes.byref(ms), 6))
+        return {"deltas_ms": ms[0], "headings_ms": ms[1], "march_ms": ms[2], "fiducials_ms": ms[3], "blobs_ms": ms[4],
+                "collisions_ms": ms[5]}
 
     def debug_trig(self, headings):
         """(n, 2) array of the device's (cos, sin) for the given headings"""

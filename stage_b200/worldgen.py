@@ -306,3 +306,139 @@ def step_robots(w, robots, tick, speed_m=0.05):
     out[:, 2] = np.where(ok, out[:, 2] + 1.0, out[:, 2] + 180.0)
     out[:, 2] = np.round(((out[:, 2] + 180.0) % 360.0 - 180.0) * 1000) / 1000.0
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE config 4 (SURVEY.md 8d "C4"): a swarm of small robots with sonar rings and fiducial finders;
+# config 5 ("C5"): pucks that all move every tick
+# ---------------------------------------------------------------------------------------------------
+
+# worlds/pioneer.inc:24-39, `define p2dx_sonar ranger`: pose [x y z heading-in-degrees] of the 16 transducers;
+# :9-19 `define p2dxsonar sensor`: size [0.01 0.05 0.01], range [0 5.0], fov 15, samples 1
+P2DX_SONAR_POSES = (
+    (0.075, 0.130, 90), (0.115, 0.115, 50), (0.150, 0.080, 30), (0.170, 0.025, 10),
+    (0.170, -0.025, -10), (0.150, -0.080, -30), (0.115, -0.115, -50), (0.075, -0.130, -90),
+    (-0.155, -0.130, -90), (-0.195, -0.115, -130), (-0.230, -0.080, -150), (-0.250, -0.025, -170),
+    (-0.250, 0.025, 170), (-0.230, 0.080, 150), (-0.195, 0.115, 130), (-0.155, 0.130, 90))
+
+
+def p2dx_sonar_sensors():
+    """the sensor list of a p2dx_sonar ranger as stg_rt_ranger_sensor records (what Sensor::Load reads, model_ranger.cc:129-156)"""
+    s = np.zeros(len(P2DX_SONAR_POSES), rt.RANGER_SENSOR_DTYPE)
+    for i, (x, y, deg) in enumerate(P2DX_SONAR_POSES):
+        s[i]["px"], s[i]["py"], s[i]["pz"], s[i]["pa"] = x, y, 0.0, heading_rad(deg)
+    s["size_z"], s["range_max"], s["fov"], s["n_samples"] = 0.01, 5.0, heading_rad(15.0), 1
+    return s
+
+
+def libm_cos_sin(a):
+    """cos / sin of every heading from the C library (math.cos / math.sin), not numpy's own vector routines: the pixel
+    outlines must be the ones Model::LocalToPixels computes"""
+    a = np.asarray(a, np.float64)
+    return np.fromiter(map(math.cos, a), np.float64, len(a)), np.fromiter(map(math.sin, a), np.float64, len(a))
+
+
+def box_polygons(x, y, a_rad, sx, sy, ppm):
+    """pixel_polygon for many boxes at once: (n, 4, 2) int32, operation for operation the same arithmetic"""
+    x, y = np.asarray(x, np.float64), np.asarray(y, np.float64)
+    cosa, sina = libm_cos_sin(a_rad)
+    gx = (x + 0.0 * cosa) - 0.0 * sina
+    gy = (y + 0.0 * sina) + 0.0 * cosa
+    out = np.zeros((len(x), 4, 2), np.int32)
+    for i, (ux, uy) in enumerate(((-0.5, -0.5), (0.5, -0.5), (0.5, 0.5), (-0.5, 0.5))):
+        lx = (ux - 0.0) * (sx / 1.0)
+        ly = (uy - 0.0) * (sy / 1.0)
+        px = (gx + lx * cosa) - ly * sina
+        py = (gy + lx * sina) + ly * cosa
+        out[:, i, 0] = np.floor(px * ppm).astype(np.int32)
+        out[:, i, 1] = np.floor(py * ppm).astype(np.int32)
+    return out
+
+
+def robot_boxes(w, robots=None):
+    """robot_polygons as one (n, 4, 2) array (swarms: no Python loop per robot)"""
+    robots = w.robots if robots is None else robots
+    return box_polygons(robots[:, 0], robots[:, 1], robots[:, 2] * (math.pi / 180.0), w.robot_size[0], w.robot_size[1], w.ppm)
+
+
+def make_swarm_world(seed=1, n_rects=4096, n_robots=100000, half_extent_m=81.92, ppm=50.0, robot_size=(0.1, 0.1, 0.1),
+                     pitch_m=0.25, jitter_m=0.03, clearance_m=0.1):
+    """The config-3 obstacle field with n_robots small bodies (C4: 0.1 m squares carrying fiducials; C5: pucks) on a
+    jittered lattice: never inside or within clearance_m of a rectangle, never closer than pitch - 2 jitter to each other."""
+    base = make_world(seed=seed, n_rects=n_rects, n_robots=0, half_extent_m=half_extent_m, ppm=ppm)
+    rng = np.random.RandomState(seed + 1000)
+    H = half_extent_m - 1.0
+    k = int(math.floor(2 * H / pitch_m))
+    gx, gy = np.meshgrid(np.arange(k), np.arange(k), indexing="ij")
+    cx = -H + (gx.reshape(-1) + 0.5) * pitch_m + rng.uniform(-jitter_m, jitter_m, k * k)
+    cy = -H + (gy.reshape(-1) + 0.5) * pitch_m + rng.uniform(-jitter_m, jitter_m, k * k)
+    cx, cy = np.round(cx * 1000) / 1000.0, np.round(cy * 1000) / 1000.0
+    # a coarse bitmap of where the rectangles (grown by the clearance and half a body diagonal) are
+    res = 0.05
+    n = int(math.ceil(2 * half_extent_m / res))
+    blocked = np.zeros((n, n), bool)
+    grow = clearance_m + 0.75 * max(robot_size[0], robot_size[1])
+    o = base.obstacles
+    x0 = np.clip(np.floor((o[:, 0] - o[:, 2] / 2 - grow + half_extent_m) / res).astype(int), 0, n)
+    x1 = np.clip(np.ceil((o[:, 0] + o[:, 2] / 2 + grow + half_extent_m) / res).astype(int), 0, n)
+    y0 = np.clip(np.floor((o[:, 1] - o[:, 3] / 2 - grow + half_extent_m) / res).astype(int), 0, n)
+    y1 = np.clip(np.ceil((o[:, 1] + o[:, 3] / 2 + grow + half_extent_m) / res).astype(int), 0, n)
+    for i in range(len(o)):
+        blocked[x0[i]:x1[i], y0[i]:y1[i]] = True
+    ix = np.clip(((cx + half_extent_m) / res).astype(int), 0, n - 1)
+    iy = np.clip(((cy + half_extent_m) / res).astype(int), 0, n - 1)
+    free = np.nonzero(~blocked[ix, iy])[0]
+    if len(free) < n_robots:
+        raise ValueError("only %d free lattice points for %d robots; lower pitch_m" % (len(free), n_robots))
+    pick = np.sort(rng.permutation(free)[:n_robots])
+    robots = np.stack([cx[pick], cy[pick], np.round(rng.uniform(-180.0, 180.0, n_robots) * 1000) / 1000.0], 1)
+    return World(ppm, half_extent_m, base.obstacles, robots, robot_size=robot_size)
+
+
+def load_swarm_into_context(ctx, w, fiducial_return=0, chunk=20000):
+    """load_into_context for worlds with many robots: same calls, same order, the outlines built with numpy.
+    fiducial_return: Model::vis.fiducial_return of every robot (C4: 1)."""
+    ctx.model_upsert(0, 0, 1.0)
+    for mid in w.obstacle_ids:
+        ctx.model_upsert(int(mid), int(mid), 0.5)
+    for mid in w.robot_ids:
+        ctx.model_upsert(int(mid), int(mid), 0.5, fiducial_return)
+    ob = np.array(obstacle_polygons(w), np.int32).reshape(-1, 4, 2)
+    polys = np.concatenate([ob, robot_boxes(w)], 0)
+    models = np.concatenate([w.obstacle_ids, w.robot_ids])
+    zmax = np.concatenate([np.full(len(w.obstacles), w.obstacle_height), np.full(len(w.robots), w.robot_size[2])])
+    z = np.stack([np.zeros(len(polys)), zmax], 1)
+    blocks = np.arange(len(polys), dtype=np.uint32)
+    for layer in (0, 1):
+        for lo in range(0, len(polys), chunk):
+            hi = min(lo + chunk, len(polys))
+            ctx.blocks_remap(blocks[lo:hi], models[lo:hi], layer, z[lo:hi], np.arange(hi - lo + 1, dtype=np.uint32) * 4,
+                             np.ascontiguousarray(polys[lo:hi].reshape(-1, 2)))
+    ctx.sync()
+    return len(polys)
+
+
+def fiducial_records(w, robots, robot_ids, layer, fiducial_return=1, range_max=8.0, range_max_id=5.0, fov=math.pi):
+    """(targets, finders) for robots that each carry a fiducial and a fiducial finder at their centre (model_fiducial.cc:77-78
+    defaults: range_max 8, range_max_id 5, fov pi, ignore_zloc 0); the finder looks out at half the body's height"""
+    n = len(robots)
+    a = robots[:, 2] * (math.pi / 180.0)
+    t = np.zeros(n, rt.FID_TARGET_DTYPE)
+    t["model"], t["fiducial_return"] = robot_ids, fiducial_return
+    t["x"], t["y"], t["a"] = robots[:, 0], robots[:, 1], a
+    t["sx"], t["sy"], t["sz"] = w.robot_size
+    f = np.zeros(n, rt.FID_FINDER_DTYPE)
+    f["finder"], f["layer"] = robot_ids, layer
+    for k in ("x", "y", "a"):
+        f[k] = f["o" + k] = t[k]
+    f["oz"] = w.robot_size[2] / 2.0
+    f["max_range_anon"], f["max_range_id"], f["fov"] = range_max, range_max_id, fov
+    return t, f
+
+
+def ranger_poses(robots, robot_ids, layer, z=0.0):
+    """stg_rt_ranger_pose records: GetGlobalPose() + geom.pose of a ranger sitting at its robot's origin"""
+    p = np.zeros(len(robots), rt.RANGER_POSE_DTYPE)
+    p["finder"], p["layer"] = robot_ids, layer
+    p["x"], p["y"], p["z"], p["a"] = robots[:, 0], robots[:, 1], z, robots[:, 2] * (math.pi / 180.0)
+    return p

@@ -59,6 +59,8 @@ def t1():
         L.t1_dump_grid.restype = ctypes.c_int64
         L.t1_dump_grid.argtypes = [vp, vp, ctypes.c_int64, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
         L.t1_replay.restype, L.t1_replay.argtypes = vp, [ctypes.c_char_p, ctypes.POINTER(ReplayStats)]
+        L.t1_blocks_remap.restype, L.t1_blocks_remap.argtypes = ctypes.c_int, [vp, u32, vp, vp, ctypes.c_int, vp, vp, vp]
+        L.t1_grid_hash.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64 * 5)]
         L.t1_test_collision.restype, L.t1_test_collision.argtypes = ctypes.c_int32, [vp, ctypes.c_int, u32, vp]
         L.t1_touching_models.restype, L.t1_touching_models.argtypes = u32, [vp, ctypes.c_int, u32, vp, u32, vp]
         _t1 = L
@@ -176,6 +178,21 @@ class T1World:
         n = int(self.L.t1_touching_models(self.h, layer, len(blocks), _p(blocks), cap, _p(out)))
         assert n <= cap
         return out[:n]
+
+    def blocks_remap(self, blocks, models, layer, z, first_pt, xy):
+        """n x (Block::UnMap + Block::Map): the oracle's side of stg_rt_blocks_remap"""
+        blocks = np.ascontiguousarray(blocks, np.uint32)
+        models = np.ascontiguousarray(models, np.uint32)
+        z = np.ascontiguousarray(z, np.float64)
+        first_pt = np.ascontiguousarray(first_pt, np.uint32)
+        xy = np.ascontiguousarray(xy, np.int32)
+        assert self.L.t1_blocks_remap(self.h, len(blocks), _p(blocks), _p(models), layer, _p(z), _p(first_pt), _p(xy)) == 0
+
+    def grid_hash(self):
+        """(hash[2], entries[2], region_count_hash): the digest stg_rt_grid_hash computes, from the oracle's own lists"""
+        out = (ctypes.c_uint64 * 5)()
+        self.L.t1_grid_hash(ctypes.c_void_p(self.h), out)
+        return [int(out[0]), int(out[1])], [int(out[2]), int(out[3])], int(out[4])
 
     def dump_grid(self):
         nc = ctypes.c_int64(0)

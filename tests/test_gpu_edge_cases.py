@@ -57,6 +57,8 @@ class Pair:
         rec_o, cnt_o = self.t1.dump_grid()
         assert np.array_equal(oracle_lib.sort_grid(rec_g), rec_o)
         assert np.array_equal(oracle_lib.sort_counts(cnt_g), cnt_o)
+        if len(oracle_lib.first_occurrences(rec_o)) == len(rec_o):  # the digest counts a block rendered twice into a cell once
+            assert self.ctx.grid_hash() == self.t1.grid_hash()
 
 
 def box(x0, y0, x1, y1):
@@ -430,3 +432,27 @@ def test_config5_full_size_timing():
     print("config 5, one replica: 10000 pucks re-rasterised per tick: host (remap + delta build + launches) %.2f ms, K1 on the device %.3f ms"
           % (np.median(host_ms[2:]), np.median(k1_ms[2:])))
     ctx.close()
+
+
+def test_grid_digest_sees_entries_counts_and_list_order():
+    """stg_rt_grid_hash / the oracle's digest: equal for equal grids, different when one entry, one region count or the
+    order of two blocks inside a cell differs."""
+    sq = lambda x, y, s: np.array([[x, y], [x + s, y], [x + s, y + s], [x, y + s]], np.int32)
+    def build(order, extra=False):
+        p = Pair()
+        p.model(0, 0)
+        p.model(1, 1)
+        p.model(2, 2)
+        for b in order:  # blocks 0 and 1 share an edge's cells; the one mapped first comes first in those cells
+            p.map(b, 1 + b, 0, (0.0, 1.0), sq(10 + 8 * b, 10, 8))
+        if extra:
+            p.map(5, 1, 1, (0.0, 1.0), sq(-200, -200, 3))
+        return p
+    a, b, c = build([0, 1]), build([1, 0]), build([0, 1], extra=True)
+    for p in (a, b, c):
+        p.grids_equal()
+    ha, hb, hc = a.ctx.grid_hash(), b.ctx.grid_hash(), c.ctx.grid_hash()
+    assert ha[1] == hb[1] and ha[2] == hb[2] and ha[0][0] != hb[0][0] and ha[0][1] == hb[0][1]  # same entries, other order on layer 0
+    assert hc[0][0] == ha[0][0] and hc[0][1] != ha[0][1] and hc[1][1] == ha[1][1] + 12 and hc[2] != ha[2]
+    for p in (a, b, c):
+        p.ctx.close()

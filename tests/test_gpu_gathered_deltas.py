@@ -67,6 +67,8 @@ def test_gathered_deltas_from_n_ranks(n_ranks):
         rec_g, cnt_g = ctx.grid_dump()
         assert np.array_equal(oracle_lib.sort_grid(rec_g), rec_o)
         assert np.array_equal(oracle_lib.sort_counts(cnt_g), cnt_o)
+    digests = [ctx.grid_hash() for ctx in ctxs]
+    assert all(d == digests[0] for d in digests) and digests[0] == t1.grid_hash()
     # rays of the last rank's shard, read layer = the one just written
     lo, hi = multi.shard_bounds(n_robots, n_ranks - 1, n_ranks)
     fans = worldgen.ranger_fans(w, layer=ticks % 2, samples=180, range_max=20.0, robots=poses[lo:hi], robot_ids=w.robot_ids[lo:hi])
