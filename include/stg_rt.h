@@ -75,6 +75,11 @@ enum {
 
 /* stg_rt_config.flags */
 #define STG_RT_CFG_DEFAULT 0u
+/* Fiducial records: range and bearing (and the id cut-off at max_range_id) are computed once more on the host with
+   the host C library's hypot / atan2 when the results are delivered, so that they agree with a CPU run of
+   ModelFiducial::AddModelIfVisible (model_fiducial.cc:130,144,218) to the last bit; without it they are CUDA's
+   (within 1e-9). Costs a pass over the delivered records on the calling thread: meant for libstage-sized worlds. */
+#define STG_RT_CFG_HOST_EXACT_FIDUCIALS 1u
 
 typedef struct stg_rt_ctx stg_rt_ctx;
 
@@ -163,6 +168,27 @@ int stg_rt_block_unmap(stg_rt_ctx *ctx, uint32_t block_id, int layer);
    callers that move many bodies at once. first_pt has n+1 entries. */
 int stg_rt_blocks_remap(stg_rt_ctx *ctx, uint32_t n, const uint32_t *blocks, const uint32_t *models, int layer,
                         const double *z, const uint32_t *first_pt, const int32_t *xy);
+
+/* ---- poses in, outlines on the device -------------------------------------------------------- */
+
+/* Register the geometry of a block once, so that the device can render it from its model's pose: pts_xy = the
+   n_pts polygon points in model coordinates exactly as Block::pts holds them after BlockGroup::CalcSize
+   (blockgroup.cc:84-112; x0 y0 x1 y1 ...), local_zmin / local_zmax = Block::local_z. Blocks of one model are
+   rendered in the order they were defined in (BlockGroup::Map's order, blockgroup.cc:114-121). A block defined again
+   takes the new geometry at its next rendering; it must not be rendered from the old one at that moment. */
+int stg_rt_block_define(stg_rt_ctx *ctx, uint32_t block_id, uint32_t model_id, double local_zmin, double local_zmax,
+                        int n_pts, const double *pts_xy);
+
+/* Model::UnMap(layer) + Model::Map(layer) (model.cc:493-519: every block of the model's BlockGroup) for n models at
+   once, with the outlines derived ON THE DEVICE: gpose_xyza[4i..4i+3] = GetGlobalPose() + geom.pose of models[i],
+   the frame Model::LocalToPixels (model.cc:474-491) composes every vertex on - pixel = floor((gpose + Pose(pt)) * ppm),
+   with the host C library's cos / sin of gpose.a reproduced bit for bit - and z of which Block::Map adds to local_z
+   (block.cc:177-180). What ModelPosition::Move does to the grid for every moving model each tick
+   (model_position.cc:549-552) then costs 32 bytes per model from the caller and 48 per block in the moved-block deltas
+   (stg_rt_delta_export), instead of a rasterised outline per block. Children are models of their own: list them too.
+   A block rendered this way can still be unmapped, re-mapped with stg_rt_block_map, collision-tested ...: the library
+   fetches its outline from the device when a call needs it on the host. */
+int stg_rt_models_pose_update(stg_rt_ctx *ctx, uint32_t n, const uint32_t *models, const double *gpose_xyza, int layer);
 
 /* ---- rays --------------------------------------------------------------------------------- */
 
@@ -403,6 +429,11 @@ int64_t stg_rt_grid_dump(stg_rt_ctx *ctx, int32_t *records, int64_t cap, int64_t
    multi-GPU run compare it with each other; the tests compare it with the digest a CPU restatement of the reference takes of its own lists.
    Synchronous. */
 int stg_rt_grid_hash(stg_rt_ctx *ctx, uint64_t out[5]);
+
+/* The pixel outline block `block_id` is rendered with on `layer` right now (as World::MapPoly received it), whether the
+   caller supplied it or the device derived it from a pose: up to cap_pts points into xy (2 x int32 each). Returns the
+   number of points (0: not mapped). Synchronous; for parity tests of the pose path against Model::LocalToPixels. */
+int stg_rt_debug_block_outline(stg_rt_ctx *ctx, uint32_t block_id, int layer, int32_t *xy, int cap_pts);
 
 /* The region owner tags the march uses to walk through regions that hold nothing but the finder's own
    tree (no counterpart in the reference: an acceleration that must never change a result; tests check

@@ -718,6 +718,50 @@ int ref_model_set_speed(void *wv, const char *name, double x, double y, double a
 // Model::Startup, model.cc:577) with queue 0 for them.
 void ref_fiducials_on_main_thread(int on) { g_fiducials_on_main = on != 0; }
 
+// Every block of every model as the reference holds it right now: what stg_rt_block_define / stg_rt_models_pose_update
+// take (the block's polygon in model coordinates after BlockGroup::CalcSize, Block::local_z, the model's frame
+// GetGlobalPose() + geom.pose) and what Model::LocalToPixels (model.cc:474-491) makes of them - the reference's own answer
+// for the device's pose path to be held to. Models in ascending id order, blocks in BlockGroup order.
+//   hdr:  int64[4] per block {model id, n_pts, first point (index into pts / pix), 0}
+//   num:  double[6] per block {gpose x, y, z, a, local_z min, max}
+//   pts:  double[2] per point (Block::pts);  pix: int32[2] per point (LocalToPixels)
+// Returns the number of blocks (may exceed cap_blocks; n_points gets the total point count). Any out array may be NULL.
+int64_t ref_block_geometry(void *wv, int64_t *hdr, double *num, int64_t cap_blocks, double *pts, int32_t *pix, int64_t cap_points,
+                           int64_t *n_points)
+{
+  World *w = (World *)wv;
+  std::vector<Model *> models(w->models.begin(), w->models.end());
+  std::sort(models.begin(), models.end(), [](const Model *a, const Model *b) { return a->id < b->id; });
+  int64_t nb = 0, np = 0;
+  for (size_t i = 0; i < models.size(); i++) {
+    Model *m = models[i];
+    const Pose gp = m->GetGlobalPose() + m->geom.pose;
+    for (size_t k = 0; k < m->blockgroup.blocks.size(); k++) {
+      const Block &b = m->blockgroup.blocks[k];
+      const std::vector<point_int_t> px = m->LocalToPixels(b.pts);
+      if (nb < cap_blocks && hdr && num) {
+        hdr[4 * nb] = m->id;
+        hdr[4 * nb + 1] = (int64_t)b.pts.size();
+        hdr[4 * nb + 2] = np;
+        hdr[4 * nb + 3] = 0;
+        const double d[6] = { gp.x, gp.y, gp.z, gp.a, b.local_z.min, b.local_z.max };
+        memcpy(num + 6 * nb, d, sizeof(d));
+      }
+      for (size_t j = 0; j < b.pts.size(); j++, np++)
+        if (np < cap_points && pts && pix) {
+          pts[2 * np] = b.pts[j].x;
+          pts[2 * np + 1] = b.pts[j].y;
+          pix[2 * np] = px[j].x;
+          pix[2 * np + 1] = px[j].y;
+        }
+      nb++;
+    }
+  }
+  if (n_points)
+    *n_points = np;
+  return nb;
+}
+
 // Look a model up by name (World::GetModel, world.cc) -> Model::id, or -1.
 int32_t ref_model_id(void *wv, const char *name)
 {

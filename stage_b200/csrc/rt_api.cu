@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -46,6 +47,18 @@ struct BlockShadow {
   // (empty = one polygon, the normal case).
   std::vector<uint32_t> host_poly[2], dev_poly[2];
   bool keep_seq[2] = { false, false }; // re-map of a block the device already holds: its place in the cell lists stays
+  // pose path (stg_rt_models_pose_update): the outline is derived on the device from the block's registered polygon
+  bool pose_pending[2] = { false, false }; // the queued Map of this layer is a pose, not an outline
+  bool dev_owned[2] = { false, false };    // the device rendered the outline it holds itself (GeomView::pix); dev_xy is empty
+  double pose[2][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 } };
+};
+
+struct GeomShadow { // stg_rt_block_define: host copy of BlockGeom plus what the host needs to reason without the pixels
+  bool defined = false;
+  uint32_t first_pt = 0, n_pts = 0, model = 0;
+  double zmin = 0, zmax = 0;
+  double radius = 0;      // farthest vertex from the model origin: bounds the outline at any pose
+  uint32_t est_steps = 0; // upper estimate of the outline's cell visits at any pose
 };
 
 struct Submit {
@@ -112,6 +125,13 @@ struct stg_rt_ctx {
   int64_t used_upper[2] = { 0, 0 };   // upper bound of non-empty slots (entries + tombstones)
 
   std::vector<uint32_t> attr_blocks;
+  // registered block geometry (pose path)
+  std::vector<GeomShadow> geom;
+  std::vector<double> h_pts;                      // pool of local points, 2 doubles each
+  std::vector<std::vector<uint32_t> > model_blocks; // per model: its defined blocks in definition (= BlockGroup) order
+  DevBuf d_geom, d_pts, d_pix[2], d_pix_new[2];
+  bool geom_dirty = false;
+  GeomView gv;
   PinBuf h_blob;
   DevBuf d_blob;
   size_t blob_cap = 0;
@@ -164,7 +184,7 @@ struct stg_rt_ctx {
     uint32_t *user_count = nullptr;
     size_t out_bytes = 0, count_bytes = 0;
     bool pending = false;
-    uint32_t n_finders = 0, max_per_finder = 0; // fiducials: to unpack the packed records
+    uint32_t n_finders = 0, max_per_finder = 0, n_targets = 0; // fiducials: to unpack the packed records
     uint64_t packed_capacity = 0;               // ... or, non-zero, to hand them over packed
   } fid_job, blob_job;
   DevBuf d_fid_grid, d_fid_in, d_fid_out, d_fid_count, d_fid_off, d_blob_in, d_blob_out, d_blob_count, d_mdl_color;
@@ -199,7 +219,7 @@ struct stg_rt_ctx {
   std::map<char *, size_t> host_allocs; // stg_rt_host_alloc regions
   stg_rt_stats stats;
 
-  stg_rt_ctx() { memset(&stats, 0, sizeof(stats)); memset(&g, 0, sizeof(g)); }
+  stg_rt_ctx() { memset(&stats, 0, sizeof(stats)); memset(&g, 0, sizeof(g)); memset(&gv, 0, sizeof(gv)); }
 };
 
 namespace {
@@ -372,8 +392,65 @@ static inline double prof_now(const stg_rt_ctx *c)
   return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Bring the device copy of the registered block geometry up to date (after stg_rt_block_define calls) and make sure
+// the per-layer pixel pools cover it. The pools grow by reallocation; what they hold is copied over.
+int upload_geometry_locked(stg_rt_ctx *c)
+{
+  if (!c->geom_dirty)
+    return 0;
+  const size_t n_blocks = c->geom.size(), n_vals = c->h_pts.size(); // values = 2 per point
+  std::vector<BlockGeom> recs(n_blocks);
+  for (size_t b = 0; b < n_blocks; b++) {
+    const GeomShadow &g = c->geom[b];
+    memset(&recs[b], 0, sizeof(BlockGeom));
+    recs[b].first_pt = g.first_pt;
+    recs[b].n_pts = g.defined ? g.n_pts : 0;
+    recs[b].model = g.model;
+    recs[b].zmin = g.zmin;
+    recs[b].zmax = g.zmax;
+  }
+  int rc;
+  if ((rc = dev_reserve(c, c->d_geom, std::max<size_t>(n_blocks * sizeof(BlockGeom), 32))) ||
+      (rc = dev_reserve(c, c->d_pts, std::max<size_t>(n_vals * 8, 16))))
+    return rc;
+  for (int L = 0; L < 2; L++)
+    for (DevBuf *pool : { &c->d_pix[L], &c->d_pix_new[L] }) {
+      if (n_vals * 4 <= pool->cap)
+        continue;
+      DevBuf grown;
+      if ((rc = dev_reserve(c, grown, std::max<size_t>(n_vals * 4, 16))))
+        return rc;
+      CU(c, cudaMemsetAsync(grown.p, 0, grown.cap, c->stream));
+      if (pool->p) {
+        CU(c, cudaMemcpyAsync(grown.p, pool->p, pool->cap, cudaMemcpyDeviceToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        CU(c, cudaFree(pool->p));
+      }
+      *pool = grown;
+    }
+  CU(c, cudaMemcpyAsync(c->d_geom.p, recs.data(), n_blocks * sizeof(BlockGeom), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->d_pts.p, c->h_pts.data(), n_vals * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream)); // pageable sources
+  c->stats.h2d_bytes += n_blocks * sizeof(BlockGeom) + n_vals * 8;
+  c->gv.geom = (const BlockGeom *)c->d_geom.p;
+  c->gv.pts = (const double *)c->d_pts.p;
+  for (int L = 0; L < 2; L++) {
+    c->gv.pix[L] = (int32_t *)c->d_pix[L].p;
+    c->gv.pix_new[L] = (int32_t *)c->d_pix_new[L].p;
+  }
+  c->gv.n_blocks = (uint32_t)n_blocks;
+  c->geom_dirty = false;
+  return 0;
+}
+
 int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes)
 {
+  static const GeomView no_geom = GeomView();
+  {
+    const int rcg = upload_geometry_locked(c);
+    if (rcg)
+      return rcg;
+  }
   double t_prof = prof_now(c);
   auto lap = [&](int k) {
     if (c->prof_on) {
@@ -405,7 +482,7 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
       c->models_changed.clear();
     }
     const size_t n_model = first_round ? c->model_upd.size() : 0;
-    size_t n_rem = 0, n_ins = 0, n_bupd = attr_blocks.size(), end_unit = unit;
+    size_t n_rem = 0, n_ins = 0, n_bupd = attr_blocks.size(), n_pose = 0, end_unit = unit;
     size_t bytes = sizeof(DeltaHeader) + n_bupd * sizeof(BlockUpd) + n_model * sizeof(ModelUpd);
     if (bytes > c->blob_cap)
       return fail(c, STG_RT_ENOMEM, "model / block attribute updates exceed the delta buffer");
@@ -414,8 +491,13 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
       const uint32_t u = c->dirty_units[end_unit];
       const BlockShadow &b = c->blocks[u >> 1];
       const int L = u & 1;
-      const size_t re = b.dev_mapped[L] ? b.dev_xy[L].size() / 2 : 0, ie = b.host_mapped[L] ? b.host_xy[L].size() / 2 : 0;
-      const size_t add = (re + ie) * sizeof(EdgeRec) + (b.host_mapped[L] ? sizeof(BlockUpd) : 0);
+      // the outline the device holds goes out through edge records when the host rendered it, through a pose record
+      // (the device knows it: GeomView::pix) when the device did; the new one comes in either as edge records or as a pose
+      const bool old_by_dev = b.dev_mapped[L] && b.dev_owned[L], new_by_pose = b.host_mapped[L] && b.pose_pending[L];
+      const bool new_by_edges = b.host_mapped[L] && !b.pose_pending[L];
+      const size_t re = (b.dev_mapped[L] && !b.dev_owned[L]) ? b.dev_xy[L].size() / 2 : 0, ie = new_by_edges ? b.host_xy[L].size() / 2 : 0;
+      const size_t pr = (old_by_dev || new_by_pose) ? 1 : 0;
+      const size_t add = (re + ie) * sizeof(EdgeRec) + (new_by_edges ? sizeof(BlockUpd) : 0) + pr * sizeof(PoseUpd);
       if (bytes + add > c->blob_cap) {
         if (end_unit == unit)
           return fail(c, STG_RT_ENOMEM, "one block's outline (%zu edges) exceeds the delta buffer", re + ie);
@@ -424,7 +506,8 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
       bytes += add;
       n_rem += re;
       n_ins += ie;
-      n_bupd += b.host_mapped[L] ? 1 : 0;
+      n_pose += pr;
+      n_bupd += new_by_edges ? 1 : 0;
       d_live[L] += (b.host_mapped[L] ? (int64_t)b.host_steps[L] : 0) - (b.dev_mapped[L] ? (int64_t)b.dev_steps[L] : 0);
       end_unit++;
     }
@@ -445,6 +528,8 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
     EdgeRec *rem = (EdgeRec *)(base + sizeof(DeltaHeader)), *ins = rem + n_rem;
     BlockUpd *bupd = (BlockUpd *)(ins + n_ins);
     ModelUpd *mupd = (ModelUpd *)(bupd + n_bupd);
+    PoseUpd *pupd = (PoseUpd *)(mupd + n_model);
+    int64_t est_rem[2] = { 0, 0 }, est_ins[2] = { 0, 0 };
     for (uint32_t bi : attr_blocks) {
       const BlockShadow &b = c->blocks[bi];
       BlockUpd &up = *bupd++;
@@ -463,8 +548,37 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
       const uint32_t u = c->dirty_units[unit];
       BlockShadow &b = c->blocks[u >> 1];
       const int L = u & 1;
-      if (b.dev_mapped[L])
+      const bool old_by_dev = b.dev_mapped[L] && b.dev_owned[L], new_by_pose = b.host_mapped[L] && b.pose_pending[L];
+      if (old_by_dev || new_by_pose) {
+        PoseUpd &pu = *pupd++;
+        memset(&pu, 0, sizeof(pu));
+        pu.block = u >> 1;
+        pu.layer_flags = (uint32_t)L | (old_by_dev ? kPoseRemoveOld : 0u) | (new_by_pose ? 0u : kPoseNoInsert);
+        pu.seq_local = b.map_seq[L];
+        pu.root_flags = root_flags_of(c, b.model);
+        pu.x = b.pose[L][0];
+        pu.y = b.pose[L][1];
+        pu.z = b.pose[L][2];
+        pu.a = b.pose[L][3];
+        if (old_by_dev)
+          est_rem[L] += b.dev_steps[L];
+        if (new_by_pose)
+          est_ins[L] += b.host_steps[L];
+      }
+      if (new_by_pose) { // the device renders it: nothing of the outline is known here
+        b.dev_xy[L].clear();
+        b.dev_poly[L].clear();
+        b.dev_steps[L] = b.host_steps[L];
+        b.dev_mapped[L] = true;
+        b.dev_owned[L] = true;
+        b.pose_pending[L] = false;
+        b.keep_seq[L] = false;
+        b.dirty[L] = false;
+        continue;
+      }
+      if (b.dev_mapped[L] && !b.dev_owned[L])
         rem_round[L] += emit_edges(b.dev_xy[L], u >> 1, L, rem_cursor, rem, &b.dev_poly[L]);
+      b.dev_owned[L] = false;
       if (b.host_mapped[L]) {
         const uint32_t st = emit_edges(b.host_xy[L], u >> 1, L, ins_cursor, ins, &b.host_poly[L]);
         ins_round[L] += st;
@@ -505,6 +619,12 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
       hdr->steps_insert_l[L] = (uint32_t)ins_round[L];
     }
     hdr->n_bytes = (uint32_t)bytes;
+    hdr->n_pose_upd = (uint32_t)n_pose;
+    for (int L = 0; L < 2; L++) {
+      hdr->est_remove_l[L] = (uint32_t)est_rem[L];
+      hdr->est_insert_l[L] = (uint32_t)est_ins[L];
+      ins_round[L] += est_ins[L]; // slots the insertions may claim, for the compaction policy
+    }
     hdr->epoch = c->epoch + 1; // what this sender would call the pass; a gathered pass takes the largest proposal
     const size_t nbytes = bytes;
     lap(3);
@@ -521,12 +641,12 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
       if (!c->hold_epoch)
         c->epoch++;
       CU(c, cudaEventRecord(c->t_ev[0][0], c->stream));
-      launch_apply_deltas(c->g, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, 0, c->stream,
+      launch_apply_deltas(c->g, n_pose ? c->gv : no_geom, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, 0, c->stream,
                           &c->stats.launches_rasterise);
       int rc = ensure_table_room(c, ins_round); // live entries grew by the net change, used slots by every insertion
       if (rc)
         return rc;
-      launch_apply_deltas(c->g, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, 1, c->stream,
+      launch_apply_deltas(c->g, n_pose ? c->gv : no_geom, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, 1, c->stream,
                           &c->stats.launches_rasterise);
       if (owners_suspect)
         launch_owner_rebuild(c->g, c->stream, &c->stats.launches_rasterise);
@@ -689,6 +809,32 @@ int deliver_post_locked(stg_rt_ctx *c)
   if (c->fid_job.pending) { // unpack: finder f's records follow finder f-1's in the staging buffer
     const double t_prof = prof_now(c);
     const uint32_t *cnt = (const uint32_t *)c->h_fid_count.p;
+    if (c->cfg.flags & STG_RT_CFG_HOST_EXACT_FIDUCIALS) {
+      // range and bearing once more with the HOST C library's hypot / atan2 (model_fiducial.cc:130,144), from the
+      // records the submit staged: a caller that must agree with a CPU run to the last bit (the libstage binding)
+      // gets the reference's own arithmetic; what was seen was decided on the device
+      const char *in = (const char *)c->h_fid_in.p;
+      const FidTargetRec *tg = (const FidTargetRec *)in;
+      const FidFinderRec *fdr = (const FidFinderRec *)(in + (size_t)c->fid_job.n_targets * sizeof(FidTargetRec));
+      FiducialRec *rec = (FiducialRec *)c->h_fid_out.p;
+      auto norm = [](double a) {
+        while (a < -M_PI)
+          a += 2.0 * M_PI;
+        while (a > M_PI)
+          a -= 2.0 * M_PI;
+        return a;
+      };
+      for (uint32_t f = 0; f < c->fid_job.n_finders; f++) {
+        const FidFinderRec &fd = fdr[f];
+        for (uint32_t k = 0, n = std::min(cnt[f], c->fid_job.max_per_finder); k < n; k++, rec++) {
+          const FidTargetRec &him = tg[rec->target];
+          const double dx = him.x - fd.x, dy = him.y - fd.y;
+          rec->range = hypot(dy, dx);
+          rec->bearing = norm(atan2(dy, dx) - fd.a);
+          rec->id = rec->range < fd.max_range_id ? him.fiducial_return : 0;
+        }
+      }
+    }
     const FiducialRec *packed = (const FiducialRec *)c->h_fid_out.p;
     FiducialRec *user = (FiducialRec *)c->fid_job.user_out;
     size_t at = 0;
@@ -1057,7 +1203,7 @@ int stg_rt_destroy(stg_rt_ctx *c)
     cudaFreeHost(c->q_fans.p);
   if (c->d_in.p)
     cudaFree(c->d_in.p);
-  for (DevBuf *b : { &c->d_rig, &c->d_mv_in, &c->d_mv_out, &c->d_mover_of_model, &c->d_col_in, &c->d_col_hit, &c->d_touch_out, &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_fid_off, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
+  for (DevBuf *b : { &c->d_geom, &c->d_pts, &c->d_pix[0], &c->d_pix[1], &c->d_pix_new[0], &c->d_pix_new[1], &c->d_rig, &c->d_mv_in, &c->d_mv_out, &c->d_mover_of_model, &c->d_col_in, &c->d_col_hit, &c->d_touch_out, &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_fid_off, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
     if (b->p)
       cudaFree(b->p);
   for (PinBuf *b : { &c->h_rig, &c->h_mv_in, &c->h_mv_out, &c->h_col_in, &c->h_col_hit, &c->h_touch_out, &c->h_fid_in, &c->h_fid_out, &c->h_fid_count, &c->h_blob_in, &c->h_blob_out, &c->h_blob_count })
@@ -1129,6 +1275,38 @@ static int block_map_locked(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id,
                             const int32_t *xy);
 static int block_unmap_locked(stg_rt_ctx *c, uint32_t block_id, int layer);
 
+// The outline of (block, layer) as the device rendered it from a pose comes home: afterwards the host shadow holds it
+// like an outline the caller supplied (needed by callers that re-derive a block's cells from its outline: collision
+// tests, touching models, batched moves, a second Map on top). Applies what is queued first.
+static int fetch_outline_locked(stg_rt_ctx *c, uint32_t block_id, int layer)
+{
+  int rc = flush_locked(c);
+  if (rc)
+    return rc;
+  BlockShadow &b = c->blocks[block_id];
+  if (!b.dev_mapped[layer] || !b.dev_owned[layer])
+    return STG_RT_OK;
+  const GeomShadow &g = c->geom[block_id];
+  b.dev_xy[layer].resize(2 * (size_t)g.n_pts);
+  CU(c, cudaMemcpyAsync(b.dev_xy[layer].data(), (const int32_t *)c->d_pix[layer].p + 2 * (size_t)g.first_pt, (size_t)g.n_pts * 8,
+                        cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->stats.d2h_bytes += (size_t)g.n_pts * 8;
+  uint64_t steps = 0;
+  const std::vector<int32_t> &xy = b.dev_xy[layer];
+  for (uint32_t i = 0; i < g.n_pts; i++) {
+    const uint32_t j = i + 1 == g.n_pts ? 0 : i + 1;
+    steps += (uint64_t)std::llabs((long long)xy[2 * j] - xy[2 * i]) + (uint64_t)std::llabs((long long)xy[2 * j + 1] - xy[2 * i + 1]);
+  }
+  c->live_entries[layer] += (int64_t)steps - (int64_t)b.dev_steps[layer]; // the estimate gives way to the count
+  b.dev_steps[layer] = (uint32_t)steps;
+  b.dev_poly[layer].clear();
+  b.dev_owned[layer] = false;
+  if (b.host_mapped[layer] && !b.dirty[layer])
+    b.host_steps[layer] = b.dev_steps[layer];
+  return STG_RT_OK;
+}
+
 int stg_rt_block_map(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id, int layer, double zmin, double zmax, int n_pts,
                      const int32_t *xy)
 {
@@ -1144,6 +1322,150 @@ int stg_rt_block_unmap(stg_rt_ctx *c, uint32_t block_id, int layer)
     return STG_RT_EINVAL;
   std::lock_guard<std::mutex> lk(c->mu);
   return block_unmap_locked(c, block_id, layer);
+}
+
+int stg_rt_block_define(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id, double local_zmin, double local_zmax, int n_pts,
+                        const double *pts_xy)
+{
+  if (!c || n_pts < 1 || !pts_xy)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (block_id >= c->cfg.max_blocks)
+    return fail(c, STG_RT_ENOMEM, "block id %u beyond max_blocks %u", block_id, c->cfg.max_blocks);
+  if (model_id >= c->cfg.max_models || !c->model_known[model_id])
+    return fail(c, STG_RT_EINVAL, "block_define: unknown model %u (call stg_rt_model_upsert first)", model_id);
+  BlockShadow &b = c->blocks[block_id];
+  for (int L = 0; L < 2; L++)
+    if ((b.dev_mapped[L] && b.dev_owned[L]) || (b.host_mapped[L] && b.pose_pending[L]))
+      return fail(c, STG_RT_ESTATE, "block_define: block %u is rendered from its present definition on layer %d; unmap it first", block_id, L);
+  if (c->geom.size() <= block_id)
+    c->geom.resize((size_t)block_id + 1);
+  GeomShadow &g = c->geom[block_id];
+  if (g.defined && g.model != model_id) { // the block id now names a block of another model
+    std::vector<uint32_t> &lst = c->model_blocks[g.model];
+    lst.erase(std::remove(lst.begin(), lst.end(), block_id), lst.end());
+    g.defined = false;
+  }
+  if (!g.defined || g.n_pts != (uint32_t)n_pts) { // a fresh stretch of the point pools
+    g.first_pt = (uint32_t)(c->h_pts.size() / 2);
+    c->h_pts.resize(c->h_pts.size() + 2 * (size_t)n_pts);
+  }
+  if (!g.defined) {
+    if (c->model_blocks.size() <= model_id)
+      c->model_blocks.resize((size_t)model_id + 1);
+    c->model_blocks[model_id].push_back(block_id);
+  }
+  g.defined = true;
+  g.n_pts = (uint32_t)n_pts;
+  g.model = model_id;
+  g.zmin = local_zmin;
+  g.zmax = local_zmax;
+  memcpy(&c->h_pts[2 * (size_t)g.first_pt], pts_xy, 2 * (size_t)n_pts * sizeof(double));
+  double r2 = 0, perimeter = 0;
+  for (int i = 0; i < n_pts; i++) {
+    const int j = i + 1 == n_pts ? 0 : i + 1;
+    r2 = std::max(r2, pts_xy[2 * i] * pts_xy[2 * i] + pts_xy[2 * i + 1] * pts_xy[2 * i + 1]);
+    perimeter += fabs(pts_xy[2 * j] - pts_xy[2 * i]) + fabs(pts_xy[2 * j + 1] - pts_xy[2 * i + 1]);
+  }
+  g.radius = sqrt(r2);
+  // |dx| + |dy| of a rotated edge is at most sqrt(2) times its length, and floor() moves each end by less than a cell
+  g.est_steps = (uint32_t)std::min(1.0e9, ceil(1.4142135623730951 * perimeter * c->cfg.ppm) + 2.0 * n_pts);
+  b.known = true;
+  if (b.model != model_id && (b.host_mapped[0] || b.host_mapped[1] || b.dev_mapped[0] || b.dev_mapped[1]))
+    c->block_reassigned = true;
+  b.model = model_id;
+  c->geom_dirty = true;
+  return STG_RT_OK;
+}
+
+int stg_rt_models_pose_update(stg_rt_ctx *c, uint32_t n, const uint32_t *models, const double *gpose_xyza, int layer)
+{
+  if (!c || layer < 0 || layer > 1 || (n && (!models || !gpose_xyza)))
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const double t_prof = prof_now(c);
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t m = models[i];
+    if (m >= c->model_blocks.size() || c->model_blocks[m].empty())
+      return fail(c, STG_RT_EINVAL, "models_pose_update: model %u has no defined blocks (stg_rt_block_define)", m);
+    const double *P = gpose_xyza + 4 * (size_t)i;
+    const std::vector<uint32_t> &lst = c->model_blocks[m];
+    for (size_t k = 0; k < lst.size(); k++) { // BlockGroup::UnMap then BlockGroup::Map: per block, in BlockGroup order
+      const uint32_t block_id = lst[k];
+      const GeomShadow &g = c->geom[block_id];
+      // every vertex lies within `radius` of the model origin: a pose this far inside the extent cannot leave it
+      const double reach = (g.radius + 2.0 / c->cfg.ppm) * c->cfg.ppm;
+      if (!(P[0] * c->cfg.ppm - reach >= c->cell_x0 && P[0] * c->cfg.ppm + reach <= c->cell_x1 + 1 && P[1] * c->cfg.ppm - reach >= c->cell_y0 &&
+            P[1] * c->cfg.ppm + reach <= c->cell_y1 + 1)) {
+        // too close to the edge for the bound to decide (a floorplan as large as the world): the vertices themselves, as
+        // Model::LocalToPixels places them
+        const double cosa = cos(P[3]), sina = sin(P[3]);
+        const double *pt = &c->h_pts[2 * (size_t)g.first_pt];
+        for (uint32_t v = 0; v < g.n_pts; v++) {
+          const double px = floor((P[0] + pt[2 * v] * cosa - pt[2 * v + 1] * sina) * c->cfg.ppm);
+          const double py = floor((P[1] + pt[2 * v] * sina + pt[2 * v + 1] * cosa) * c->cfg.ppm);
+          if (!(px >= c->cell_x0 && px <= c->cell_x1 && py >= c->cell_y0 && py <= c->cell_y1))
+            return fail(c, STG_RT_EEXTENT, "model %u at (%.3f, %.3f): block %u vertex (%.0f,%.0f) outside the device grid [%d..%d]x[%d..%d]", m, P[0],
+                        P[1], block_id, px, py, c->cell_x0, c->cell_x1, c->cell_y0, c->cell_y1);
+        }
+      }
+      if (!c->q_subs.empty()) { // issue order: queued fans must be traced against the grid as it was
+        int rc = flush_locked(c);
+        if (rc)
+          return rc;
+      }
+      if (c->local_seq >= kSeqLocalMax) {
+        if (c->export_mode)
+          return fail(c, STG_RT_ENOMEM, "more than %u Map calls between two delta exchanges", kSeqLocalMax);
+        int rc = apply_deltas_locked(c);
+        if (rc)
+          return rc;
+      }
+      BlockShadow &b = c->blocks[block_id];
+      b.zmin = g.zmin + P[2]; // Block::Map, block.cc:177-180 (what the host-side collision queries read)
+      b.zmax = g.zmax + P[2];
+      b.host_mapped[layer] = true;
+      b.pose_pending[layer] = true;
+      memcpy(b.pose[layer], P, 4 * sizeof(double));
+      b.host_steps[layer] = g.est_steps;
+      b.host_xy[layer].clear();
+      b.host_poly[layer].clear();
+      b.keep_seq[layer] = false;
+      b.map_seq[layer] = ++c->local_seq;
+      touch_unit(c, block_id, layer);
+      c->stats.map_calls++;
+      c->stats.unmap_calls++;
+    }
+  }
+  if (c->prof_on)
+    c->prof_us[6] += prof_now(c) - t_prof;
+  return STG_RT_OK;
+}
+
+int stg_rt_debug_block_outline(stg_rt_ctx *c, uint32_t block_id, int layer, int32_t *xy, int cap_pts)
+{
+  if (!c || layer < 0 || layer > 1 || block_id >= c->cfg.max_blocks)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = flush_locked(c);
+  if (rc || (rc = deliver_locked(c)))
+    return rc;
+  const BlockShadow &b = c->blocks[block_id];
+  if (!b.dev_mapped[layer])
+    return 0;
+  if (!b.dev_owned[layer]) {
+    const int n = (int)(b.dev_xy[layer].size() / 2);
+    if (xy)
+      memcpy(xy, b.dev_xy[layer].data(), (size_t)std::min(n, cap_pts) * 8);
+    return n;
+  }
+  const GeomShadow &g = c->geom[block_id];
+  if (xy && cap_pts > 0) {
+    CU(c, cudaMemcpyAsync(xy, (const int32_t *)c->d_pix[layer].p + 2 * (size_t)g.first_pt, (size_t)std::min<uint32_t>(g.n_pts, (uint32_t)cap_pts) * 8,
+                          cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+  }
+  return (int)g.n_pts;
 }
 
 int stg_rt_blocks_remap(stg_rt_ctx *c, uint32_t n, const uint32_t *blocks, const uint32_t *models, int layer, const double *z,
@@ -1198,6 +1520,13 @@ static int block_map_locked(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id,
     if (rc)
       return rc;
   }
+  if (b.host_mapped[layer] && ((b.dirty[layer] && b.pose_pending[layer]) || (!b.dirty[layer] && b.dev_owned[layer]))) {
+    // one more rendering on top of an outline only the device knows: bring that outline home first
+    int rc = fetch_outline_locked(c, block_id, layer);
+    if (rc)
+      return rc;
+  }
+  b.pose_pending[layer] = false;
   if (b.known && b.model != model_id)
     c->block_reassigned = true; // what is still rendered of it on the other layer changes owner too
   b.known = true;
@@ -1247,6 +1576,7 @@ static int block_unmap_locked(stg_rt_ctx *c, uint32_t block_id, int layer)
       return rc;
   }
   b.host_mapped[layer] = false;
+  b.pose_pending[layer] = false;
   b.host_steps[layer] = 0;
   b.host_xy[layer].clear();
   b.host_poly[layer].clear();
@@ -1797,15 +2127,17 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_r
         continue; // K1 skipped it and said so
       c->epoch = std::max<uint64_t>(c->epoch, h[r].epoch); // the epoch that pass really used
       for (int L = 0; L < 2; L++) {
-        all_ins[L] += h[r].steps_insert_l[L];
+        all_ins[L] += (int64_t)h[r].steps_insert_l[L] + h[r].est_insert_l[L];
         if ((int)h[r].rank != c->last_export_rank) // this rank's own share was booked at export; the others' net change, signed
-          c->live_entries[L] += (int64_t)h[r].steps_insert_l[L] - (int64_t)h[r].steps_remove_l[L];
+          c->live_entries[L] += (int64_t)h[r].steps_insert_l[L] + h[r].est_insert_l[L] - (int64_t)h[r].steps_remove_l[L] - h[r].est_remove_l[L];
       }
     }
     for (int L = 0; L < 2; L++)
       c->last_gather_ins[L] = all_ins[L];
     c->hdrs_pending = false;
   }
+  if ((rc = upload_geometry_locked(c)))
+    return rc;
   int rcp = pin_reserve(c, c->h_hdrs, (size_t)n_ranks * sizeof(DeltaHeader));
   if (rcp)
     return rcp;
@@ -1823,11 +2155,11 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_r
   }
   c->epoch++; // K1 takes the largest proposal among the blobs, which is at least this (every sender proposed its own epoch + 1)
   CU(c, cudaEventRecord(c->t_ev[0][0], c->stream));
-  launch_apply_deltas(c->g, (const unsigned char *)dev_gathered, n_ranks, slot_bytes, c->epoch, 0, c->stream,
+  launch_apply_deltas(c->g, c->gv, (const unsigned char *)dev_gathered, n_ranks, slot_bytes, c->epoch, 0, c->stream,
                       &c->stats.launches_rasterise);
   if ((rc = ensure_table_room(c, add)))
     return rc;
-  launch_apply_deltas(c->g, (const unsigned char *)dev_gathered, n_ranks, slot_bytes, c->epoch, 1, c->stream,
+  launch_apply_deltas(c->g, c->gv, (const unsigned char *)dev_gathered, n_ranks, slot_bytes, c->epoch, 1, c->stream,
                       &c->stats.launches_rasterise);
   launch_owner_rebuild(c->g, c->stream, &c->stats.launches_rasterise); // other ranks' updates are only known there
   CU(c, cudaEventRecord(c->t_ev[0][1], c->stream));
@@ -1968,6 +2300,7 @@ static int fiducials_submit_impl(stg_rt_ctx *c, uint32_t n_targets, const stg_rt
   c->fid_job.user_out = out;
   c->fid_job.user_count = out_count;
   c->fid_job.n_finders = n_finders;
+  c->fid_job.n_targets = n_targets;
   c->fid_job.max_per_finder = max_per_finder;
   c->fid_job.packed_capacity = packed_capacity;
   c->fid_job.pending = true;
@@ -1985,20 +2318,22 @@ int stg_rt_collisions_test(stg_rt_ctx *c, int layer, uint32_t n_queries, const u
   const uint32_t n_ids = query_first[n_queries];
   if (n_ids && !blocks)
     return STG_RT_EINVAL;
-  size_t n_edges = 0;
   for (uint32_t q = 0; q < n_queries; q++) {
     if (query_first[q + 1] < query_first[q])
       return fail(c, STG_RT_EINVAL, "collisions_test: query_first is not ascending at %u", q);
-    for (uint32_t i = query_first[q]; i < query_first[q + 1]; i++) {
+    for (uint32_t i = query_first[q]; i < query_first[q + 1]; i++)
       if (blocks[i] >= c->cfg.max_blocks || !c->blocks[blocks[i]].known)
         return fail(c, STG_RT_EINVAL, "collisions_test: query %u names unknown block %u", q, blocks[i]);
-      n_edges += c->blocks[blocks[i]].host_mapped[layer] ? c->blocks[blocks[i]].host_xy[layer].size() / 2 : 0;
-      n_edges += c->blocks[blocks[i]].dev_xy[layer].size() / 2; // upper bound: whichever copy is current
-    }
   }
   int rc = flush_locked(c); // the grid the test reads includes every Map / UnMap issued so far
   if (rc || (rc = deliver_post_locked(c)))
     return rc;
+  size_t n_edges = 0;
+  for (uint32_t i = 0; i < n_ids; i++) {
+    if (c->blocks[blocks[i]].dev_mapped[layer] && c->blocks[blocks[i]].dev_owned[layer] && (rc = fetch_outline_locked(c, blocks[i], layer)))
+      return rc; // rendered by the device from a pose: the walk below needs the outline
+    n_edges += c->blocks[blocks[i]].dev_xy[layer].size() / 2;
+  }
   const size_t b_q = (size_t)n_queries * sizeof(CollisionQuery), b_in = b_q + n_edges * sizeof(EdgeRec);
   if ((rc = pin_reserve(c, c->h_col_in, b_in)) || (rc = dev_reserve(c, c->d_col_in, b_in + 16)) ||
       (rc = pin_reserve(c, c->h_col_hit, (size_t)n_queries * 4)) || (rc = dev_reserve(c, c->d_col_hit, (size_t)n_queries * 4)))
@@ -2067,8 +2402,11 @@ int stg_rt_touching_models(stg_rt_ctx *c, int layer, uint32_t n_queries, const u
   if (rc || (rc = deliver_post_locked(c)))
     return rc;
   size_t n_edges = 0;
-  for (uint32_t i = 0; i < n_ids; i++)
+  for (uint32_t i = 0; i < n_ids; i++) {
+    if (c->blocks[blocks[i]].dev_mapped[layer] && c->blocks[blocks[i]].dev_owned[layer] && (rc = fetch_outline_locked(c, blocks[i], layer)))
+      return rc;
     n_edges += c->blocks[blocks[i]].dev_xy[layer].size() / 2;
+  }
   const size_t b_q = (size_t)n_queries * sizeof(CollisionQuery), b_in = b_q + n_edges * sizeof(EdgeRec);
   const size_t b_out = (size_t)n_queries * 4 * (1 + (size_t)max_per_query);
   if ((rc = pin_reserve(c, c->h_col_in, b_in)) || (rc = dev_reserve(c, c->d_col_in, b_in + 16)) ||

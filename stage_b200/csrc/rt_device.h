@@ -108,7 +108,7 @@ struct GridView {
 };
 
 // ---- moved-block delta blob (host -> device, and rank -> rank through the all-gather) ----------
-// [DeltaHeader][EdgeRec x (n_remove + n_insert)][BlockUpd x n_block_upd][ModelUpd x n_model_upd]
+// [DeltaHeader][EdgeRec x (n_remove + n_insert)][BlockUpd x n_block_upd][ModelUpd x n_model_upd][PoseUpd x n_pose_upd]
 struct DeltaHeader {
   uint32_t n_remove, n_insert;       // edge records: removals first, then insertions
   uint32_t n_block_upd, n_model_upd;
@@ -118,9 +118,44 @@ struct DeltaHeader {
   uint32_t n_bytes;                  // size of the whole blob; K1 checks the counts against it and against the slot
   uint32_t n_pose_upd;               // PoseUpd records after the model updates (outlines derived on the device)
   unsigned long long epoch;          // the sender's next epoch; a gathered pass uses the largest one it finds
+  // cell visits of the outlines the pose records take out / put in, per layer, as far as the sender can tell without
+  // computing them (an upper estimate from the blocks' perimeters): for the receivers' table accounting only
+  uint32_t est_remove_l[2], est_insert_l[2];
+  uint32_t reserved[4];
 };
-static_assert(sizeof(DeltaHeader) == 64, "DeltaHeader");
+static_assert(sizeof(DeltaHeader) == 96, "DeltaHeader");
 constexpr uint32_t kDeltaMagic = 0x53544744u; // "STGD"
+
+// Block::UnMap(layer) + Block::Map(layer) of one block whose outline the DEVICE derives from the model's pose
+// (Model::LocalToPixels, model.cc:474-491): x, y, z, a = GetGlobalPose() + geom.pose. 48 bytes instead of the 8 edge
+// records + 1 block update (296 bytes) the same move costs with host-rasterised outlines.
+struct PoseUpd {
+  uint32_t block;
+  uint32_t layer_flags; // layer | kPose*
+  uint32_t seq_local;   // order of the Map call within this rank's blob
+  uint32_t root_flags;  // BlockRec::root_flags of the block's model, as the sender knows it
+  double x, y, z, a;
+};
+static_assert(sizeof(PoseUpd) == 48, "PoseUpd");
+constexpr uint32_t kPoseRemoveOld = 0x100u; // the device holds this block's outline on that layer (GeomView::pix): take it out first
+constexpr uint32_t kPoseNoInsert = 0x200u;  // UnMap only
+
+// Local geometry of a block, registered once (stg_rt_block_define): its polygon in model coordinates as Block::pts
+// holds it after BlockGroup::CalcSize (blockgroup.cc:84-112) and Block::local_z.
+struct BlockGeom {
+  uint32_t first_pt, n_pts; // into GeomView::pts / pix (2 values per point)
+  uint32_t model, pad;
+  double zmin, zmax;
+};
+static_assert(sizeof(BlockGeom) == 32, "BlockGeom");
+
+struct GeomView {
+  const BlockGeom *geom;  // [n_blocks]
+  const double *pts;      // local points, x then y
+  int32_t *pix[2];        // per layer: the pixel outline the device rendered last for each defined block (valid while it is mapped through a PoseUpd)
+  int32_t *pix_new[2];    // per layer: outlines computed in phase 0 of the running pass, committed to pix in phase 1
+  uint32_t n_blocks;      // blocks the table covers
+};
 
 // One polygon edge = one integer line of World::MapPoly (world.cc:995-1052): start cell included,
 // end cell excluded, n_steps = |dx| + |dy| cell visits. first_step = running sum within its group.
@@ -351,7 +386,7 @@ void launch_blobs(const GridView &g, const BlobBatchView &b, void *stream);
 void launch_debug_trig(uint64_t n, const double *x, double *cs, void *stream);
 
 // launch wrappers implemented in rt_kernels.cu; all asynchronous on `stream`
-void launch_apply_deltas(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
+void launch_apply_deltas(const GridView &g, const GeomView &gv, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
                          unsigned long long epoch, int phase, void *stream, uint64_t *launch_counter);
 void launch_owner_rebuild(const GridView &g, void *stream, uint64_t *launch_counter);
 void launch_fan_headings(const FanBatchView &b, void *stream);

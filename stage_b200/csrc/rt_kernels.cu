@@ -87,7 +87,8 @@ struct BlobView {
   const EdgeRec *remove_edges, *insert_edges;
   const BlockUpd *block_upd;
   const ModelUpd *model_upd;
-  uint32_t n_remove, n_insert, n_block_upd, n_model_upd; // 0 for a slot that does not hold a well-formed blob
+  const PoseUpd *pose_upd;
+  uint32_t n_remove, n_insert, n_block_upd, n_model_upd, n_pose_upd; // 0 for a slot that does not hold a well-formed blob
 };
 
 // A slot holds a blob only if it says so itself: the magic word, and record counts that add up to its own size and
@@ -98,8 +99,9 @@ __device__ __forceinline__ bool blob_ok(const DeltaHeader *h, size_t slot_bytes)
   if (h->magic != kDeltaMagic)
     return false;
   const unsigned long long need = sizeof(DeltaHeader) + ((unsigned long long)h->n_remove + h->n_insert) * sizeof(EdgeRec) +
-                                  (unsigned long long)h->n_block_upd * sizeof(BlockUpd) + (unsigned long long)h->n_model_upd * sizeof(ModelUpd);
-  return need <= slot_bytes && need == h->n_bytes && h->n_pose_upd == 0u && h->steps_remove == h->steps_remove_l[0] + h->steps_remove_l[1] &&
+                                  (unsigned long long)h->n_block_upd * sizeof(BlockUpd) + (unsigned long long)h->n_model_upd * sizeof(ModelUpd) +
+                                  (unsigned long long)h->n_pose_upd * sizeof(PoseUpd);
+  return need <= slot_bytes && need == h->n_bytes && h->steps_remove == h->steps_remove_l[0] + h->steps_remove_l[1] &&
          h->steps_insert == h->steps_insert_l[0] + h->steps_insert_l[1];
 }
 
@@ -119,11 +121,92 @@ __device__ __forceinline__ BlobView blob_view(const unsigned char *blobs, int ra
   v.n_insert = ok ? v.hdr->n_insert : 0u;
   v.n_block_upd = ok ? v.hdr->n_block_upd : 0u;
   v.n_model_upd = ok ? v.hdr->n_model_upd : 0u;
+  v.n_pose_upd = ok ? v.hdr->n_pose_upd : 0u;
   v.remove_edges = reinterpret_cast<const EdgeRec *>(p + sizeof(DeltaHeader));
   v.insert_edges = v.remove_edges + v.n_remove;
   v.block_upd = reinterpret_cast<const BlockUpd *>(v.insert_edges + v.n_insert);
   v.model_upd = reinterpret_cast<const ModelUpd *>(v.block_upd + v.n_block_upd);
+  v.pose_upd = reinterpret_cast<const PoseUpd *>(v.model_upd + v.n_model_upd);
   return v;
+}
+
+// ---- what one cell visit does to the grid (shared by the edge-record path and the pose path) ------------------
+// Cell::RemoveBlock (region.cc:292-299, EraseAll: every copy goes) + Region::RemoveBlock's count
+__device__ __forceinline__ void cell_remove(const GridView &g, const CellAddr &c, uint32_t block, uint32_t L)
+{
+  const unsigned long long entry = ((unsigned long long)c.key << 32) | (unsigned long long)(block + 1u);
+  unsigned long long *slots = g.slots[L];
+  uint32_t h = slot_home(c.key, g.slot_mask);
+  for (uint32_t probes = 0; probes <= g.slot_mask; probes++) {
+    const unsigned long long cur = ld_slot(slots + h);
+    if (cur == kSlotEmpty)
+      break;
+    if (cur == entry)
+      atomicCAS(slots + h, entry, kSlotTomb);
+    h = (h + 1) & g.slot_mask;
+  }
+  if (atomicSub(g.reg_count + c.region, 1u) == 1u) // the region's last entry: it belongs to nobody again
+    g.reg_owner[c.region] = kOwnerNone;
+  uint32_t *tile = g.occ[L] + (size_t)c.region * kTileWords;
+  atomicAnd(tile + c.cy, ~(1u << c.cx));
+  atomicAnd(tile + kRegionWidth + c.cx, ~(1u << c.cy));
+}
+
+// after every removal has landed: a cell that lost an entry but still holds another block gets its mask bits back
+__device__ __forceinline__ void cell_fixup(const GridView &g, const CellAddr &c, uint32_t L)
+{
+  const unsigned long long *slots = g.slots[L];
+  uint32_t h = slot_home(c.key, g.slot_mask);
+  for (uint32_t probes = 0; probes <= g.slot_mask; probes++) {
+    const unsigned long long cur = ld_slot(slots + h);
+    if (cur == kSlotEmpty)
+      break;
+    if ((uint32_t)(cur >> 32) == c.key) { // tombstones carry key 0xffffffff, never a cell key
+      uint32_t *tile = g.occ[L] + (size_t)c.region * kTileWords;
+      atomicOr(tile + c.cy, 1u << c.cx);
+      atomicOr(tile + kRegionWidth + c.cx, 1u << c.cy);
+      break;
+    }
+    h = (h + 1) & g.slot_mask;
+  }
+}
+
+// Cell::AddBlock (region.cc:283-290) + Region::AddBlock's count, the occupancy bits and the region's owner tag
+__device__ __forceinline__ void cell_insert(const GridView &g, const CellAddr &c, uint32_t block, uint32_t L)
+{
+  const unsigned long long entry = ((unsigned long long)c.key << 32) | (unsigned long long)(block + 1u);
+  unsigned long long *slots = g.slots[L];
+  uint32_t h = slot_home(c.key, g.slot_mask);
+  bool placed = false;
+  for (uint32_t probes = 0; probes <= g.slot_mask;) {
+    const unsigned long long cur = ld_slot(slots + h);
+    if (cur == kSlotEmpty || cur == kSlotTomb) {
+      if (atomicCAS(slots + h, cur, entry) == cur) {
+        placed = true;
+        break;
+      }
+      continue; // lost the race for this slot: look at it again
+    }
+    h = (h + 1) & g.slot_mask;
+    probes++;
+  }
+  if (!placed) { // every slot taken: no entry, so no count and no mask bit either (a bit nothing resolves would make
+    raise_error(g, kErrTableFull); // the cell transparent and the region count could never return to zero)
+    return;
+  }
+  atomicAdd(g.reg_count + c.region, 1u);
+  { // region owner: stays a tree's tag only while every entry added belongs to that tree
+    const uint32_t tag = (g.blk_rec[0][block].root_flags & kRecRootMask) + 1u;
+    uint32_t *owner = g.reg_owner + c.region;
+    uint32_t cur = *reinterpret_cast<volatile uint32_t *>(owner);
+    if (cur == kOwnerNone)
+      cur = atomicCAS(owner, kOwnerNone, tag);
+    if (cur != kOwnerNone && cur != tag && cur != kOwnerMixed)
+      atomicExch(owner, kOwnerMixed);
+  }
+  uint32_t *tile = g.occ[L] + (size_t)c.region * kTileWords;
+  atomicOr(tile + c.cy, 1u << c.cx);
+  atomicOr(tile + kRegionWidth + c.cx, 1u << c.cy);
 }
 
 // The cell visits of all ranks' blobs as ONE index space, so that a gathered delta (N ranks) is a
@@ -231,22 +314,7 @@ __device__ __forceinline__ void k1_remove(const GridView &g, const unsigned char
         raise_error(g, kErrOutOfExtent);
         continue;
       }
-      const unsigned long long entry = ((unsigned long long)c.key << 32) | (unsigned long long)(e.block + 1u);
-      unsigned long long *slots = g.slots[e.layer & 1];
-      uint32_t h = slot_home(c.key, g.slot_mask);
-      for (uint32_t probes = 0; probes <= g.slot_mask; probes++) { // EraseAll: every copy goes
-        const unsigned long long cur = ld_slot(slots + h);
-        if (cur == kSlotEmpty)
-          break;
-        if (cur == entry)
-          atomicCAS(slots + h, entry, kSlotTomb);
-        h = (h + 1) & g.slot_mask;
-      }
-      if (atomicSub(g.reg_count + c.region, 1u) == 1u) // the region's last entry: it belongs to nobody again
-        g.reg_owner[c.region] = kOwnerNone;
-      uint32_t *tile = g.occ[e.layer & 1] + (size_t)c.region * kTileWords;
-      atomicAnd(tile + c.cy, ~(1u << c.cx));
-      atomicAnd(tile + kRegionWidth + c.cx, ~(1u << c.cy));
+      cell_remove(g, c, e.block, e.layer & 1);
     }
   }
 }
@@ -268,20 +336,7 @@ __device__ __forceinline__ void k1_fixup(const GridView &g, const unsigned char 
         raise_error(g, kErrOutOfExtent);
         continue;
       }
-      const unsigned long long *slots = g.slots[e.layer & 1];
-      uint32_t h = slot_home(c.key, g.slot_mask);
-      for (uint32_t probes = 0; probes <= g.slot_mask; probes++) {
-        const unsigned long long cur = ld_slot(slots + h);
-        if (cur == kSlotEmpty)
-          break;
-        if ((uint32_t)(cur >> 32) == c.key) { // tombstones carry key 0xffffffff, never a cell key
-          uint32_t *tile = g.occ[e.layer & 1] + (size_t)c.region * kTileWords;
-          atomicOr(tile + c.cy, 1u << c.cx);
-          atomicOr(tile + kRegionWidth + c.cx, 1u << c.cy);
-          break;
-        }
-        h = (h + 1) & g.slot_mask;
-      }
+      cell_fixup(g, c, e.layer & 1);
     }
   }
 }
@@ -303,39 +358,7 @@ __device__ __forceinline__ void k1_insert(const GridView &g, const unsigned char
         raise_error(g, kErrOutOfExtent);
         continue;
       }
-      const unsigned long long entry = ((unsigned long long)c.key << 32) | (unsigned long long)(e.block + 1u);
-      unsigned long long *slots = g.slots[e.layer & 1];
-      uint32_t h = slot_home(c.key, g.slot_mask);
-      bool placed = false;
-      for (uint32_t probes = 0; probes <= g.slot_mask;) {
-        const unsigned long long cur = ld_slot(slots + h);
-        if (cur == kSlotEmpty || cur == kSlotTomb) {
-          if (atomicCAS(slots + h, cur, entry) == cur) {
-            placed = true;
-            break;
-          }
-          continue; // lost the race for this slot: look at it again
-        }
-        h = (h + 1) & g.slot_mask;
-        probes++;
-      }
-      if (!placed) { // every slot taken: no entry, so no count and no mask bit either (a bit nothing resolves would make
-        raise_error(g, kErrTableFull); // the cell transparent and the region count could never return to zero)
-        continue;
-      }
-      atomicAdd(g.reg_count + c.region, 1u);
-      { // region owner: stays a tree's tag only while every entry added belongs to that tree
-        const uint32_t tag = (g.blk_rec[0][e.block].root_flags & kRecRootMask) + 1u;
-        uint32_t *owner = g.reg_owner + c.region;
-        uint32_t cur = *reinterpret_cast<volatile uint32_t *>(owner);
-        if (cur == kOwnerNone)
-          cur = atomicCAS(owner, kOwnerNone, tag);
-        if (cur != kOwnerNone && cur != tag && cur != kOwnerMixed)
-          atomicExch(owner, kOwnerMixed);
-      }
-      uint32_t *tile = g.occ[e.layer & 1] + (size_t)c.region * kTileWords;
-      atomicOr(tile + c.cy, 1u << c.cx);
-      atomicOr(tile + kRegionWidth + c.cx, 1u << c.cy);
+      cell_insert(g, c, e.block, e.layer & 1);
     }
   }
 }
@@ -369,6 +392,172 @@ __global__ void __launch_bounds__(256) k1_phase1(GridView g, const unsigned char
     __syncthreads();
     k1_step_prefix<true>(g, part, nr, slot_bytes, prefix);
     k1_insert(g, part, nr, slot_bytes, prefix);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1, pose path: Block::UnMap + Block::Map of blocks whose outline the device derives itself from the model's pose
+// (Model::LocalToPixels, model.cc:474-491) and the block's registered local polygon. One warp per PoseUpd record, all
+// ranks' records as one index space; the lanes share the cell visits of each edge of the outline. Same two phases as
+// the edge-record path, launched right behind them:
+//   phase 0: the new pixel outline -> GeomView::pix_new; the block's BlockRec (global_z = local_z + pose z,
+//            block.cc:177-180; owner; sequence number); removal of the outline rendered before (GeomView::pix)
+//   phase 1: mask fix-up over the old outline, insertion of the new one, pix <- pix_new
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void k1_pose_prefix(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes, uint32_t *prefix)
+{
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int r = 0; r < n_ranks; r++) {
+      prefix[r] = run;
+      const DeltaHeader *h = reinterpret_cast<const DeltaHeader *>(blobs + (size_t)r * slot_bytes);
+      if (blob_ok(h, slot_bytes))
+        run += h->n_pose_upd;
+    }
+    prefix[n_ranks] = run;
+  }
+  __syncthreads();
+}
+
+// the cell visits of a closed pixel outline, edge after edge as World::MapPoly walks them (world.cc:995-1052),
+// shared out over the lanes of the warp
+template <class Op>
+__device__ __forceinline__ void outline_cells(const GridView &g, const int32_t *pix, uint32_t n_pts, uint32_t lane, Op op)
+{
+  for (uint32_t i = 0; i < n_pts; i++) {
+    const uint32_t j = i + 1 == n_pts ? 0 : i + 1;
+    EdgeRec e;
+    e.x0 = pix[2 * i];
+    e.y0 = pix[2 * i + 1];
+    e.x1 = pix[2 * j];
+    e.y1 = pix[2 * j + 1];
+    const long long adx = e.x1 > e.x0 ? (long long)e.x1 - e.x0 : (long long)e.x0 - e.x1;
+    const long long ady = e.y1 > e.y0 ? (long long)e.y1 - e.y0 : (long long)e.y0 - e.y1;
+    const uint32_t n_steps = (uint32_t)(adx + ady);
+    for (uint32_t k = lane; k < n_steps; k += 32) {
+      int32_t x, y;
+      edge_cell(e, k, x, y);
+      const CellAddr c = cell_addr(g, x, y);
+      if (!c.inside) {
+        raise_error(g, kErrOutOfExtent);
+        continue;
+      }
+      op(c);
+    }
+  }
+}
+
+struct OpRemove {
+  const GridView &g;
+  uint32_t block, L;
+  __device__ void operator()(const CellAddr &c) const { cell_remove(g, c, block, L); }
+};
+struct OpFixup {
+  const GridView &g;
+  uint32_t L;
+  __device__ void operator()(const CellAddr &c) const { cell_fixup(g, c, L); }
+};
+struct OpInsert {
+  const GridView &g;
+  uint32_t block, L;
+  __device__ void operator()(const CellAddr &c) const { cell_insert(g, c, block, L); }
+};
+
+__global__ void __launch_bounds__(256) k1_pose_phase0(GridView g, GeomView gv, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
+                                                      unsigned long long epoch)
+{
+  __shared__ uint32_t prefix[kMaxRanksFlat + 1];
+  const uint32_t lane = threadIdx.x & 31u, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  epoch = k1_pass_epoch(blobs, n_ranks, slot_bytes, epoch);
+  for (int r0 = 0; r0 < n_ranks; r0 += kMaxRanksFlat) {
+    const int nr = min(n_ranks - r0, kMaxRanksFlat);
+    const unsigned char *part = blobs + (size_t)r0 * slot_bytes;
+    k1_pose_prefix(g, part, nr, slot_bytes, prefix);
+    for (uint32_t w = warp; w < prefix[nr]; w += n_warps) {
+      const int rank = k1_rank_of(prefix, nr, w);
+      const BlobView v = blob_view(part, rank, slot_bytes);
+      const PoseUpd u = v.pose_upd[w - prefix[rank]];
+      if (u.block >= gv.n_blocks || u.block >= g.n_blocks) {
+        if (lane == 0)
+          raise_error(g, kErrOutOfExtent);
+        continue;
+      }
+      const BlockGeom bg = gv.geom[u.block];
+      const uint32_t L = u.layer_flags & 1u;
+      if (!(u.layer_flags & kPoseNoInsert)) {
+        // Model::LocalToPixels: ptpose = gpose + Pose(pt) (Pose::operator+, stage.hh:297-304: cos / sin of gpose.a from the
+        // host C library's algorithm, rt_libm.cuh; no contraction), pixel = (int32)floor(coordinate * ppm)
+        double cosa, sina;
+        if (libm::covered(u.a)) {
+          sina = libm::sin_host_exact(u.a);
+          cosa = libm::cos_host_exact(u.a);
+        } else {
+          sina = sin(u.a);
+          cosa = cos(u.a);
+        }
+        for (uint32_t i = lane; i < bg.n_pts; i += 32) {
+          const double px = gv.pts[2 * (size_t)(bg.first_pt + i)], py = gv.pts[2 * (size_t)(bg.first_pt + i) + 1];
+          const double gx = u.x + px * cosa - py * sina, gy = u.y + px * sina + py * cosa;
+          gv.pix_new[L][2 * (size_t)(bg.first_pt + i)] = (int32_t)floor(gx * g.ppm);
+          gv.pix_new[L][2 * (size_t)(bg.first_pt + i) + 1] = (int32_t)floor(gy * g.ppm);
+        }
+        if (lane == 0) { // Block::Map's second half (block.cc:176-180) and the block's place in the cell lists
+          if ((g.blk_rec[0][u.block].root_flags ^ u.root_flags) & kRecRootMask) {
+            const unsigned long long s0 = g.blk_rec[0][u.block].seq, s1 = g.blk_rec[1][u.block].seq;
+            if ((s0 && (s0 >> kSeqEpochShift) != epoch) || (s1 && (s1 >> kSeqEpochShift) != epoch))
+              g.reg_owner[g.n_regions] = 1u;
+          }
+          for (int l = 0; l < 2; l++) {
+            BlockRec *rec = g.blk_rec[l] + u.block;
+            rec->zmin = bg.zmin + u.z;
+            rec->zmax = bg.zmax + u.z;
+            rec->model = bg.model;
+            rec->root_flags = u.root_flags;
+          }
+          g.blk_rec[L][u.block].seq = (epoch << kSeqEpochShift) | ((unsigned long long)(v.hdr->rank & 0xff) << kSeqRankShift) | (u.seq_local & kSeqLocalMax);
+        }
+      }
+      if (u.layer_flags & kPoseRemoveOld) {
+        const OpRemove op = { g, u.block, L };
+        outline_cells(g, gv.pix[L] + 2 * (size_t)bg.first_pt, bg.n_pts, lane, op);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k1_pose_phase1(GridView g, GeomView gv, const unsigned char *blobs, int n_ranks, size_t slot_bytes)
+{
+  __shared__ uint32_t prefix[kMaxRanksFlat + 1];
+  const uint32_t lane = threadIdx.x & 31u, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r0 = 0; r0 < n_ranks; r0 += kMaxRanksFlat) {
+    const int nr = min(n_ranks - r0, kMaxRanksFlat);
+    const unsigned char *part = blobs + (size_t)r0 * slot_bytes;
+    k1_pose_prefix(g, part, nr, slot_bytes, prefix);
+    for (uint32_t w = warp; w < prefix[nr]; w += n_warps) {
+      const int rank = k1_rank_of(prefix, nr, w);
+      const BlobView v = blob_view(part, rank, slot_bytes);
+      const PoseUpd u = v.pose_upd[w - prefix[rank]];
+      if (u.block >= gv.n_blocks || u.block >= g.n_blocks)
+        continue;
+      const BlockGeom bg = gv.geom[u.block];
+      const uint32_t L = u.layer_flags & 1u;
+      int32_t *pix = gv.pix[L] + 2 * (size_t)bg.first_pt;
+      if (u.layer_flags & kPoseRemoveOld) {
+        const OpFixup op = { g, L };
+        outline_cells(g, pix, bg.n_pts, lane, op);
+      }
+      if (!(u.layer_flags & kPoseNoInsert)) {
+        const int32_t *fresh = gv.pix_new[L] + 2 * (size_t)bg.first_pt;
+        const OpInsert op = { g, u.block, L };
+        outline_cells(g, fresh, bg.n_pts, lane, op);
+        __syncwarp(); // every lane is done with the old outline: the new one takes its place
+        for (uint32_t i = lane; i < 2 * bg.n_pts; i += 32)
+          pix[i] = fresh[i];
+      }
+    }
     __syncthreads();
   }
 }
@@ -531,7 +720,7 @@ static int delta_grid_blocks()
 
 // phase 0: table updates, removals.  phase 1: mask fix-up, insertions. The host may compact the
 // cell-entry table between the two (every tombstone of phase 0 is reclaimed before new entries land).
-void launch_apply_deltas(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
+void launch_apply_deltas(const GridView &g, const GeomView &gv, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
                          unsigned long long epoch, int phase, void *stream, uint64_t *launch_counter)
 {
   cudaStream_t s = (cudaStream_t)stream;
@@ -542,6 +731,14 @@ void launch_apply_deltas(const GridView &g, const unsigned char *blobs, int n_ra
     k1_phase1<<<blocks, 256, 0, s>>>(g, blobs, n_ranks, slot_bytes);
   if (launch_counter)
     *launch_counter += 1;
+  if (gv.geom) { // the pose path's share of the same phase (the host passes a null table when no blob can hold pose records)
+    if (phase == 0)
+      k1_pose_phase0<<<blocks, 256, 0, s>>>(g, gv, blobs, n_ranks, slot_bytes, epoch);
+    else
+      k1_pose_phase1<<<blocks, 256, 0, s>>>(g, gv, blobs, n_ranks, slot_bytes);
+    if (launch_counter)
+      *launch_counter += 1;
+  }
 }
 
 void launch_owner_rebuild(const GridView &g, void *stream, uint64_t *launch_counter)

@@ -12,6 +12,7 @@ from . import build as _build
 PRED_RANGER, PRED_UNRELATED, PRED_GRIPPER = 0, 1, 2
 ANGLES_RANGER, ANGLES_EVEN_FOV, ANGLES_EXPLICIT = 0, 1, 2
 VIS_GRIPPER_RETURN, VIS_OBSTACLE_RETURN, VIS_BLOB_RETURN = 1, 2, 4
+CFG_HOST_EXACT_FIDUCIALS = 1
 WANT_RANGES, WANT_INTENSITIES, WANT_BEARINGS, WANT_HIT_MODEL, WANT_HIT_CELL, WANT_STEPS = 1, 2, 4, 8, 16, 32
 WANT_ALL = 63
 
@@ -92,6 +93,9 @@ def lib():
         "stg_rt_block_map": (ctypes.c_int, [vp, u32, u32, ctypes.c_int, f64, f64, ctypes.c_int, vp]),
         "stg_rt_block_unmap": (ctypes.c_int, [vp, u32, ctypes.c_int]),
         "stg_rt_blocks_remap": (ctypes.c_int, [vp, u32, vp, vp, ctypes.c_int, vp, vp, vp]),
+        "stg_rt_block_define": (ctypes.c_int, [vp, u32, u32, f64, f64, ctypes.c_int, vp]),
+        "stg_rt_models_pose_update": (ctypes.c_int, [vp, u32, vp, vp, ctypes.c_int]),
+        "stg_rt_debug_block_outline": (ctypes.c_int, [vp, u32, ctypes.c_int, vp, ctypes.c_int]),
         "stg_rt_fans_submit": (ctypes.c_int, [vp, u32, vp, vp, vp, ctypes.POINTER(FanOut)]),
         "stg_rt_fiducials_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
         "stg_rt_fiducials_submit_packed": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, u64, vp, vp]),
@@ -140,7 +144,7 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "stg_rt_abi_version stg_rt_create stg_rt_destroy stg_rt_last_error stg_rt_model_upsert stg_rt_block_map "
-    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_fiducials_submit stg_rt_fiducials_submit_packed stg_rt_rangers_submit stg_rt_collisions_test stg_rt_touching_models stg_rt_models_move stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
+    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_block_define stg_rt_models_pose_update stg_rt_debug_block_outline stg_rt_fiducials_submit stg_rt_fiducials_submit_packed stg_rt_rangers_submit stg_rt_collisions_test stg_rt_touching_models stg_rt_models_move stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
     "stg_rt_delta_apply_gathered stg_rt_stream_signal stg_rt_stream_wait stg_rt_ranger_rand_advance stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_kernel_times_ex stg_rt_debug_trig stg_rt_debug_headings stg_rt_debug_region_owners stg_rt_grid_hash").split()
@@ -188,10 +192,10 @@ class Context:
     """One stg_rt_ctx: the replicated world state of one GPU plus its queues."""
 
     def __init__(self, ppm, sreg_x0, sreg_y0, sreg_nx, sreg_ny, max_models=1 << 16, max_blocks=1 << 16,
-                 max_cell_entries=0, device=0, max_delta_bytes=0):
+                 max_cell_entries=0, device=0, max_delta_bytes=0, flags=0):
         self._L = lib()
         cfg = Config(ctypes.sizeof(Config), device, ppm, sreg_x0, sreg_y0, sreg_nx, sreg_ny, max_models,
-                     max_blocks, max_cell_entries, 0, max_delta_bytes, 0)
+                     max_blocks, max_cell_entries, flags, max_delta_bytes, 0)
         h = ctypes.c_void_p()
         rc = self._L.stg_rt_create(ctypes.byref(cfg), ctypes.byref(h))
         if rc:
@@ -239,6 +243,25 @@ class Context:
         assert len(first_pt) == len(blocks) + 1 and len(models) == len(blocks) and z.size == 2 * len(blocks)
         self._check(self._L.stg_rt_blocks_remap(self._h, len(blocks), _ptr(blocks), _ptr(models), layer, _ptr(z),
                                                 _ptr(first_pt), _ptr(xy)))
+
+    def block_define(self, block, model, local_zmin, local_zmax, pts):
+        """register a block's polygon in model coordinates (Block::pts after CalcSize) and its local z range"""
+        pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 2)
+        self._check(self._L.stg_rt_block_define(self._h, block, model, local_zmin, local_zmax, len(pts), _ptr(pts)))
+
+    def models_pose_update(self, models, gpose_xyza, layer):
+        """UnMap + Map of every defined block of these models at gpose = GetGlobalPose() + geom.pose, outlines derived on the device"""
+        models = np.ascontiguousarray(models, np.uint32)
+        gp = np.ascontiguousarray(gpose_xyza, np.float64).reshape(len(models), 4)
+        self._check(self._L.stg_rt_models_pose_update(self._h, len(models), _ptr(models), _ptr(gp), layer))
+
+    def block_outline(self, block, layer):
+        """(n, 2) int32 pixel outline the block is rendered with on that layer now (empty: not mapped)"""
+        n = self._check(self._L.stg_rt_debug_block_outline(self._h, block, layer, None, 0))
+        xy = np.zeros((max(n, 1), 2), np.int32)
+        if n:
+            self._check(self._L.stg_rt_debug_block_outline(self._h, block, layer, _ptr(xy), n))
+        return xy[:n]
 
     # ---- rays
     def fans_submit(self, fans, out, headings=None, trig=None):

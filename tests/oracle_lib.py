@@ -251,6 +251,8 @@ def ref():
         L.ref_models_remap.restype = ctypes.c_double
         L.ref_models_remap.argtypes = [vp, ctypes.c_uint32, vp, vp, ctypes.c_int]
         L.ref_probe_models.restype, L.ref_probe_models.argtypes = ctypes.c_int, [vp, ctypes.c_uint32, vp]
+        L.ref_block_geometry.restype = ctypes.c_int64
+        L.ref_block_geometry.argtypes = [vp, vp, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
         L.ref_models_remap2.restype = ctypes.c_double
         L.ref_models_remap2.argtypes = [vp, ctypes.c_uint32, vp, vp, ctypes.c_int, ctypes.c_int]
         _ref = L
@@ -298,6 +300,18 @@ class RefWorld:
         cnt = np.zeros((max(nc.value, 1), 3), np.int64)
         self.L.ref_dump_grid(self.h, _p(rec), n, _p(cnt), nc.value, ctypes.byref(nc))
         return sort_grid(rec[:n]), sort_counts(cnt[:nc.value])
+
+    def block_geometry(self):
+        """every block as the reference holds it now: dict(model[nb], first[nb + 1], gpose[nb, 4], local_z[nb, 2], pts[np, 2] in
+        model coordinates, pix[np, 2] = Model::LocalToPixels of them) - models by id, blocks in BlockGroup order"""
+        npts = ctypes.c_int64(0)
+        nb = self.L.ref_block_geometry(self.h, None, None, 0, None, None, 0, ctypes.byref(npts))
+        hdr, num = np.zeros((max(nb, 1), 4), np.int64), np.zeros((max(nb, 1), 6), np.float64)
+        pts, pix = np.zeros((max(npts.value, 1), 2), np.float64), np.zeros((max(npts.value, 1), 2), np.int32)
+        assert self.L.ref_block_geometry(self.h, _p(hdr), _p(num), nb, _p(pts), _p(pix), npts.value, ctypes.byref(npts)) == nb
+        first = np.concatenate([hdr[:nb, 2], [npts.value]]).astype(np.int64)
+        return {"model": hdr[:nb, 0].astype(np.uint32), "first": first, "gpose": num[:nb, :4].copy(), "local_z": num[:nb, 4:6].copy(),
+                "pts": pts[:npts.value], "pix": pix[:npts.value]}
 
     def subscribe(self, name):
         assert self.L.ref_model_subscribe(self.h, name.encode()) == 0, name
