@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--c4-robots", type=int, default=100000, help="config 4: robots in total (sharded over the GPUs)")
     ap.add_argument("--c4-max-fiducials", type=int, default=64, help="config 4: records kept per finder (the counts are exact beyond it)")
     ap.add_argument("--c5-pucks", type=int, default=10000, help="config 5: pucks in total, all moved every tick")
+    ap.add_argument("--deltas", default="poses", choices=["poses", "outlines"],
+                    help="how a tick's moved bodies reach the grid: poses (default) = stg_rt_models_pose_update, the outlines are derived on the "
+                         "device (Model::LocalToPixels); outlines = stg_rt_blocks_remap with outlines rasterised by the caller")
     ap.add_argument("--workload", default="c3", choices=["c3", "cave"],
                     help="c3 = BASELINE config 3 (the default, the judged line); cave = the denser variant of SURVEY.md 8(d): "
                          "worlds/bitmaps/cave.png tiled 10x10 (no reference arm: value / e2e / roofline only)")
@@ -355,6 +358,8 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     worldgen.load_into_context(ctx, world)
+    if args.deltas == "poses":   # every replica knows every robot's body: the moved-block deltas are poses (48 B per block)
+        worldgen.define_boxes(ctx, world.n_static_blocks, world.robot_ids, world.robot_size)
 
     lo, hi = multi.shard_bounds(args.robots * n_gpus, rank, n_gpus)
     my_ids = world.robot_ids[lo:hi]
@@ -413,8 +418,15 @@ def run_ours(args):
     launches1 = ctx.stats()
 
     # ---- e2e: one whole tick per step through the C ABI, host buffers ---------------------------
-    want_e2e = rt.WANT_RANGES | rt.WANT_HIT_MODEL
+    # what ModelRanger::Sensor::Update fills (model_ranger.cc:243-251): ranges and intensities every tick; bearings are a
+    # function of the sensor's geometry alone (start_angle + t * sample_incr), so a caller fills them once per sensor
+    # type - here from one submit before the timed ticks - and keeps them
+    want_e2e = rt.WANT_RANGES | rt.WANT_INTENSITIES
     out = rt.Outputs(n_beams, want_e2e, alloc=ctx.pinned_empty)
+    once = rt.Outputs(n_beams, rt.WANT_BEARINGS)
+    ctx.fans_submit(fans0, once)
+    ctx.sync()
+    bearings = once.bearings
     # e2e ticks take under a millisecond each: W of them are over before the host's clocks, caches and page tables
     # have settled on a fresh box (first run of a box seen 0.47 ms per tick, the second 0.44), so the untimed lead-in
     # is at least 20 ticks (said in `config.e2e_warmup_ticks`); the timed region is exactly K ticks either way
@@ -432,7 +444,7 @@ def run_ours(args):
             "xy": np.ascontiguousarray(np.concatenate(polys, 0), np.int32),
             "first": np.arange(len(polys) + 1, dtype=np.uint32) * 4,
             "z": np.ascontiguousarray(np.stack([np.zeros(len(polys)), np.full(len(polys), world.robot_size[2])], 1)),
-            "layer_w": layer_w,
+            "layer_w": layer_w, "gpose": worldgen.gposes(poses[t]),
             "fans": worldgen.ranger_fans(world, layer=(t + 1) % 2, fov_deg=FOV_DEG, samples=SAMPLES, range_max=RANGE_MAX,
                                          robots=poses[t], robot_ids=my_ids),
         })
@@ -442,7 +454,10 @@ def run_ours(args):
 
     def tick(tk):
         t0 = time.perf_counter()
-        ctx.blocks_remap(my_blocks, my_ids, tk["layer_w"], tk["z"], tk["first"], tk["xy"])
+        if args.deltas == "poses":
+            ctx.models_pose_update(my_ids, tk["gpose"], tk["layer_w"])
+        else:
+            ctx.blocks_remap(my_blocks, my_ids, tk["layer_w"], tk["z"], tk["first"], tk["xy"])
         t1 = time.perf_counter()
         if exchange is not None:  # all-gather the moved-block deltas, apply all ranks' in rank order
             exchange.step()
@@ -555,6 +570,10 @@ def run_ours(args):
                     "ticks_per_s": args.steps / t_e2e,
                     "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // args.steps,
                     "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) // args.steps,
+                    "delivers": ["ranges (f64, written by the march kernel straight into the caller's page-locked array)",
+                                 "intensities (f64 in the caller's array: one palette byte per beam over PCIe, expanded by stg_rt_sync)",
+                                 "bearings (f64, filled once per sensor type before the timed ticks: they depend on the sensor's geometry only)"],
+                    "bearings_checked": bool(np.array_equal(bearings[:SAMPLES], -np.deg2rad(FOV_DEG) / 2.0 + np.arange(SAMPLES) * (np.deg2rad(FOV_DEG) / (SAMPLES - 1)))),
                     "last_step_kernel_ms": e2e_kt, "host_call_ms_per_step": {k: v / args.steps for k, v in host_split.items()}, "timing": "host clock around K ticks, synchronised both sides, max over ranks"},
             "gpu_launches": int(sum(st1[k] - launches0[k] for k in ("launches_rasterise", "launches_march", "launches_post", "launches_other"))),
             "kernel_ms": {"ray_march": march_avg_ms, "fan_headings": float(np.mean(head_ms)),

@@ -234,6 +234,9 @@ def run_c4(env, args):
                      device=env.local_rank, max_delta_bytes=slot_bytes)
     ctx.set_stream(env.stream.cuda_stream)
     worldgen.load_swarm_into_context(ctx, w, fiducial_return=1)
+    poses_in = getattr(args, "deltas", "poses") == "poses"
+    if poses_in:
+        worldgen.define_boxes(ctx, n_ob, w.robot_ids, w.robot_size)
     sensors = worldgen.p2dx_sonar_sensors()
     n_beams = n_mine * len(sensors)
     total_beams = n_total * len(sensors)
@@ -251,7 +254,7 @@ def run_c4(env, args):
         """what libstage's Move() / sensor Update()s hand over at tick t (caller-side work, outside the timed regions)"""
         p = poses[t][lo:hi]
         tg, fd = worldgen.fiducial_records(w, p, my_ids, layer=(t + 1) % 2)
-        return {"t": t, "layer_w": t % 2, "xy": np.ascontiguousarray(worldgen.robot_boxes(w, p).reshape(-1, 2)),
+        return {"t": t, "layer_w": t % 2, "xy": np.ascontiguousarray(worldgen.robot_boxes(w, p).reshape(-1, 2)), "gpose": worldgen.gposes(p),
                 "rposes": worldgen.ranger_poses(p, my_ids, layer=(t + 1) % 2), "targets": tg, "finders": fd}
 
     ticks = [prepare(t) for t in range(1, n_ticks + 1)]
@@ -266,7 +269,10 @@ def run_c4(env, args):
 
     def tick(tk):
         t0 = time.perf_counter()
-        ctx.blocks_remap(my_blocks, my_ids, tk["layer_w"], z_mine, first4, tk["xy"])
+        if poses_in:
+            ctx.models_pose_update(my_ids, tk["gpose"], tk["layer_w"])
+        else:
+            ctx.blocks_remap(my_blocks, my_ids, tk["layer_w"], z_mine, first4, tk["xy"])
         t1 = time.perf_counter()
         if exchange is not None:
             exchange.step()
@@ -455,6 +461,10 @@ def run_c5(env, args, fov_deg, samples, range_max):
     for layer in (0, 1):
         ctx.blocks_remap(puck_blocks, puck_ids, layer, pz, np.arange(n_pucks + 1, dtype=np.uint32) * 4, b0)
     ctx.sync()
+    poses_in = getattr(args, "deltas", "poses") == "poses"
+    if poses_in:
+        worldgen.define_boxes(ctx, n_ob, w.robot_ids, w.robot_size)
+        worldgen.define_boxes(ctx, n_ob + n_robots, puck_ids, puck_size)
 
     my_ids = w.robot_ids[lo:hi]
     my_blocks = (n_ob + np.arange(lo, hi)).astype(np.uint32)
@@ -469,7 +479,7 @@ def run_c5(env, args, fov_deg, samples, range_max):
     rfirst, pfirst = np.arange(hi - lo + 1, dtype=np.uint32) * 4, np.arange(n_pm + 1, dtype=np.uint32) * 4
 
     def prepare(t):
-        return {"t": t, "layer_w": t % 2,
+        return {"t": t, "layer_w": t % 2, "rgpose": worldgen.gposes(rposes[t][lo:hi]), "pgpose": worldgen.gposes(pposes[t][plo:phi]),
                 "rxy": np.ascontiguousarray(worldgen.robot_boxes(w, rposes[t][lo:hi]).reshape(-1, 2)),
                 "pxy": np.ascontiguousarray(puck_boxes(pposes[t][plo:phi]).reshape(-1, 2)),
                 "fans": worldgen.ranger_fans(w, layer=(t + 1) % 2, fov_deg=fov_deg, samples=samples, range_max=range_max,
@@ -481,8 +491,12 @@ def run_c5(env, args, fov_deg, samples, range_max):
 
     def tick(tk):
         t0 = time.perf_counter()
-        ctx.blocks_remap(my_blocks, my_ids, tk["layer_w"], rz, rfirst, tk["rxy"])           # this rank's robots move ...
-        ctx.blocks_remap(puck_blocks[plo:phi], puck_ids[plo:phi], tk["layer_w"], pz[plo:phi], pfirst, tk["pxy"])   # ... and its share of the pucks
+        if poses_in:
+            ctx.models_pose_update(my_ids, tk["rgpose"], tk["layer_w"])                      # this rank's robots move ...
+            ctx.models_pose_update(puck_ids[plo:phi], tk["pgpose"], tk["layer_w"])           # ... and its share of the pucks
+        else:
+            ctx.blocks_remap(my_blocks, my_ids, tk["layer_w"], rz, rfirst, tk["rxy"])
+            ctx.blocks_remap(puck_blocks[plo:phi], puck_ids[plo:phi], tk["layer_w"], pz[plo:phi], pfirst, tk["pxy"])
         t1 = time.perf_counter()
         if exchange is not None:
             exchange.step()

@@ -12,7 +12,10 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <condition_variable>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/stg_rt.h"
@@ -82,6 +85,87 @@ struct FanArrays { // device arrays of one batch / resident set
 };
 
 } // namespace
+
+// A few host threads for the per-beam passes stg_rt_sync makes over large result arrays (expanding intensity palette
+// indices into doubles: 8 MB of stores per million beams, more than one core writes in the time the GPU takes to trace
+// them). Started on first use; STG_RT_HOST_THREADS sets the count (default: half the cores, at most 8; 1 = inline).
+class HostPool {
+public:
+  ~HostPool()
+  {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (std::thread &t : threads_)
+      t.join();
+  }
+  void parallel_for(size_t n, size_t grain, const std::function<void(size_t, size_t)> &fn)
+  {
+    start();
+    const size_t parts = std::min<size_t>(threads_.size() + 1, std::max<size_t>(1, n / std::max<size_t>(grain, 1)));
+    if (parts <= 1) {
+      fn(0, n);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      n_ = n;
+      parts_ = parts;
+      next_ = 1; // part 0 is the caller's
+      pending_ = parts - 1;
+      generation_++;
+    }
+    cv_.notify_all();
+    fn(0, n / parts);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+private:
+  void start()
+  {
+    if (started_)
+      return;
+    started_ = true;
+    unsigned want = std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    if (const char *e = getenv("STG_RT_HOST_THREADS"))
+      want = (unsigned)std::max(1, atoi(e));
+    for (unsigned i = 1; i < want; i++)
+      threads_.emplace_back([this] { work(); });
+  }
+  void work()
+  {
+    uint64_t seen = 0;
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+      cv_.wait(lk, [&] { return stop_ || (generation_ != seen && next_ < parts_); });
+      if (stop_)
+        return;
+      while (fn_ && next_ < parts_) {
+        const size_t p = next_++;
+        const size_t lo = n_ * p / parts_, hi = n_ * (p + 1) / parts_;
+        const std::function<void(size_t, size_t)> *fn = fn_;
+        lk.unlock();
+        (*fn)(lo, hi);
+        lk.lock();
+        if (--pending_ == 0)
+          done_.notify_all();
+      }
+      seen = generation_;
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  std::vector<std::thread> threads_;
+  const std::function<void(size_t, size_t)> *fn_ = nullptr;
+  size_t n_ = 0, parts_ = 0, next_ = 0, pending_ = 0;
+  uint64_t generation_ = 0;
+  bool started_ = false, stop_ = false;
+};
 
 struct stg_rt_set {
   std::vector<FanRec> fans;
@@ -215,6 +299,13 @@ struct stg_rt_ctx {
   bool hold_epoch = false; // the undo re-maps of a move belong to the same epoch as the moves
   std::vector<double> mdl_color; // rgba per model
   bool mdl_color_dirty = true;
+  // the distinct ranger_return values of the world (index 0 = "no hit" = 0.0): with at most 255 of them a beam's
+  // intensity crosses PCIe as one byte and stg_rt_sync expands it into the caller's doubles
+  std::vector<double> palette = std::vector<double>(1, 0.0);
+  bool palette_ok = true;
+  bool f_compact_intens = false; // the batch in flight delivers intensities as palette indices
+  PinBuf h_intens_idx;
+  HostPool pool;
 
   std::map<char *, size_t> host_allocs; // stg_rt_host_alloc regions
   stg_rt_stats stats;
@@ -445,7 +536,6 @@ int upload_geometry_locked(stg_rt_ctx *c)
 
 int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes)
 {
-  static const GeomView no_geom = GeomView();
   {
     const int rcg = upload_geometry_locked(c);
     if (rcg)
@@ -565,6 +655,8 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
         if (new_by_pose)
           est_ins[L] += b.host_steps[L];
       }
+      if (b.dev_mapped[L] && !b.dev_owned[L]) // an outline the host rendered leaves through edge records, whatever replaces it
+        rem_round[L] += emit_edges(b.dev_xy[L], u >> 1, L, rem_cursor, rem, &b.dev_poly[L]);
       if (new_by_pose) { // the device renders it: nothing of the outline is known here
         b.dev_xy[L].clear();
         b.dev_poly[L].clear();
@@ -576,8 +668,6 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
         b.dirty[L] = false;
         continue;
       }
-      if (b.dev_mapped[L] && !b.dev_owned[L])
-        rem_round[L] += emit_edges(b.dev_xy[L], u >> 1, L, rem_cursor, rem, &b.dev_poly[L]);
       b.dev_owned[L] = false;
       if (b.host_mapped[L]) {
         const uint32_t st = emit_edges(b.host_xy[L], u >> 1, L, ins_cursor, ins, &b.host_poly[L]);
@@ -640,13 +730,14 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
     if (apply) {
       if (!c->hold_epoch)
         c->epoch++;
+      const int what = ((n_rem + n_ins + n_bupd + n_model) ? kDeltaEdgeRecords : 0) | (n_pose ? kDeltaPoseRecords : 0);
       CU(c, cudaEventRecord(c->t_ev[0][0], c->stream));
-      launch_apply_deltas(c->g, n_pose ? c->gv : no_geom, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, 0, c->stream,
+      launch_apply_deltas(c->g, c->gv, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, 0, what, c->stream,
                           &c->stats.launches_rasterise);
       int rc = ensure_table_room(c, ins_round); // live entries grew by the net change, used slots by every insertion
       if (rc)
         return rc;
-      launch_apply_deltas(c->g, n_pose ? c->gv : no_geom, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, 1, c->stream,
+      launch_apply_deltas(c->g, c->gv, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, 1, what, c->stream,
                           &c->stats.launches_rasterise);
       if (owners_suspect)
         launch_owner_rebuild(c->g, c->stream, &c->stats.launches_rasterise);
@@ -876,8 +967,18 @@ int deliver_locked(stg_rt_ctx *c)
     // the kernel wrote ranges / intensities / hit models of a solo pinned submit in place
     deliver_array(c, s.out.ranges, c->h_ranges, s.first_beam, s.n_beams, 8,
                   c->f_copied ? is_host_alloc(c, s.out.ranges, s.n_beams * 8) : c->f_direct[0]);
-    deliver_array(c, s.out.intensities, c->h_intens, s.first_beam, s.n_beams, 8,
-                  c->f_copied ? is_host_alloc(c, s.out.intensities, s.n_beams * 8) : c->f_direct[1]);
+    if (c->f_compact_intens && s.out.intensities) { // palette indices -> the caller's doubles (model_ranger.cc:250)
+      const uint8_t *idx = (const uint8_t *)c->h_intens_idx.p + s.first_beam;
+      double *dst = s.out.intensities;
+      const double *pal = c->palette.data();
+      c->pool.parallel_for((size_t)s.n_beams, 1 << 16, [idx, dst, pal](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++)
+          dst[i] = pal[idx[i]];
+      });
+    } else {
+      deliver_array(c, s.out.intensities, c->h_intens, s.first_beam, s.n_beams, 8,
+                    c->f_copied ? is_host_alloc(c, s.out.intensities, s.n_beams * 8) : c->f_direct[1]);
+    }
     deliver_array(c, s.out.hit_model, c->h_hit_model, s.first_beam, s.n_beams, 4,
                   c->f_copied ? is_host_alloc(c, s.out.hit_model, s.n_beams * 4) : c->f_direct[2]);
     // these were copied device-to-host, straight into pinned caller memory when possible
@@ -978,13 +1079,23 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   bool zc_ranges = false, zc_intens = false, zc_model = false;
   // STG_RT_RESULTS=copy: device buffers + copy engine instead of zero-copy stores (measurements)
   static const bool copy_results = getenv("STG_RT_RESULTS") && !strcmp(getenv("STG_RT_RESULTS"), "copy");
+  const bool want_intens_copy = copy_results && (want & STG_RT_WANT_INTENSITIES);
+  (void)want_intens_copy;
   if (copy_results)
     want &= ~(STG_RT_WANT_RANGES | STG_RT_WANT_INTENSITIES | STG_RT_WANT_HIT_MODEL); // for the zero-copy set-up below only
   if (want & STG_RT_WANT_RANGES) {
     v.ranges = (double *)host_target(solo ? solo->out.ranges : nullptr, c->h_ranges, 8, c->f_direct[0]);
     zc_ranges = true;
   }
-  if (want & STG_RT_WANT_INTENSITIES) {
+  c->f_compact_intens = false;
+  static const bool wide_intens = getenv("STG_RT_INTENSITIES") && !strcmp(getenv("STG_RT_INTENSITIES"), "f64"); // measurements
+  if ((want & STG_RT_WANT_INTENSITIES) && c->palette_ok && !wide_intens) {
+    if ((rc = pin_reserve(c, c->h_intens_idx, beams)))
+      return rc;
+    v.intensities = nullptr;
+    v.intens_idx = (uint8_t *)c->h_intens_idx.p;
+    c->f_compact_intens = true;
+  } else if (want & STG_RT_WANT_INTENSITIES) {
     v.intensities = (double *)host_target(solo ? solo->out.intensities : nullptr, c->h_intens, 8, c->f_direct[1]);
     zc_intens = true;
   }
@@ -992,12 +1103,24 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
     v.hit_model = (int32_t *)host_target(solo ? solo->out.hit_model : nullptr, c->h_hit_model, 4, c->f_direct[2]);
     zc_model = true;
   }
-  CU(c, cudaEventRecord(c->t_ev[1][0], c->stream));
-  launch_fan_headings(v, c->stream);
-  CU(c, cudaEventRecord(c->t_ev[1][1], c->stream));
+  // The headings do not read the grid: when a delta pass is about to run they go on the side stream and overlap it
+  // (the march waits for both).
+  const bool side = with_deltas && (!c->dirty_units.empty() || !c->model_upd.empty());
+  cudaStream_t hs = side ? c->copy_stream : c->stream;
+  if (side) {
+    CU(c, cudaEventRecord(c->chunk_ev[0], c->stream)); // the fan records are uploaded
+    CU(c, cudaStreamWaitEvent(hs, c->chunk_ev[0], 0));
+  }
+  CU(c, cudaEventRecord(c->t_ev[1][0], hs));
+  launch_fan_headings(v, hs);
+  CU(c, cudaEventRecord(c->t_ev[1][1], hs));
   const double t_prof1 = prof_now(c);
   if (with_deltas && (rc = apply_deltas_locked(c)))
     return rc;
+  if (side) {
+    CU(c, cudaEventRecord(c->chunk_ev[1], hs));
+    CU(c, cudaStreamWaitEvent(c->stream, c->chunk_ev[1], 0));
+  }
   const double t_prof2 = prof_now(c);
   CU(c, cudaEventRecord(c->t_ev[2][0], c->stream));
   launch_ray_march(c->g, v, c->stream);
@@ -1008,7 +1131,7 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   c->stats.launches_post += 1;
   c->stats.beams += beams;
   c->stats.fans += n_fans;
-  c->stats.d2h_bytes += beams * ((zc_ranges ? 8 : 0) + (zc_intens ? 8 : 0) + (zc_model ? 4 : 0));
+  c->stats.d2h_bytes += beams * ((zc_ranges ? 8 : 0) + (zc_intens ? 8 : 0) + (zc_model ? 4 : 0) + (c->f_compact_intens ? 1 : 0));
   for (const Submit &s : c->q_subs) { // what did not go zero-copy
     if (copy_results) {
       if ((rc = fetch_array(c, s.out.ranges, c->d.ranges.p, c->h_ranges, s.first_beam, s.n_beams, 8, 0, beams, c->stream)) ||
@@ -1159,6 +1282,8 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
   CUC(cudaMalloc(&g.mdl_root, (size_t)cfg->max_models * 4));
   CUC(cudaMalloc(&g.mdl_ranger_return, (size_t)cfg->max_models * 8));
   CUC(cudaMalloc(&g.mdl_flags, (size_t)cfg->max_models * 4));
+  CUC(cudaMalloc(&g.mdl_pal, (size_t)cfg->max_models));
+  CUC(cudaMemsetAsync(g.mdl_pal, 0, (size_t)cfg->max_models, c->stream));
   CUC(cudaMemsetAsync(g.mdl_root, 0, (size_t)cfg->max_models * 4, c->stream));
   CUC(cudaMemsetAsync(g.mdl_ranger_return, 0, (size_t)cfg->max_models * 8, c->stream));
   CUC(cudaMemsetAsync(g.mdl_flags, 0, (size_t)cfg->max_models * 4, c->stream));
@@ -1193,7 +1318,7 @@ int stg_rt_destroy(stg_rt_ctx *c)
             c->prof_us[5], c->prof_us[6], c->prof_us[7]);
   GridView &g = c->g;
   void *dev[] = { g.reg_count, g.reg_owner, g.occ[0], g.slots[0], g.slots[1], g.blk_rec[0], g.blk_rec[1], c->spare_slots,
-                  g.mdl_root, g.mdl_ranger_return, g.mdl_flags, c->d_blob.p };
+                  g.mdl_root, g.mdl_ranger_return, g.mdl_flags, g.mdl_pal, c->d_blob.p };
   for (void *p : dev)
     if (p)
       cudaFree(p);
@@ -1260,6 +1385,19 @@ int stg_rt_model_upsert(stg_rt_ctx *c, uint32_t id, uint32_t root_id, double ran
   u.fiducial_return = fiducial_return;
   u.fiducial_key = fiducial_key;
   u.flags = vis_flags;
+  u.pal = 0;
+  if (c->palette_ok) {
+    size_t k = 1;
+    while (k < c->palette.size() && memcmp(&c->palette[k], &ranger_return, sizeof(double)))
+      k++;
+    if (k == c->palette.size()) {
+      if (k < 256)
+        c->palette.push_back(ranger_return);
+      else
+        c->palette_ok = false; // more distinct values than a byte names: intensities travel as doubles from now on
+    }
+    u.pal = c->palette_ok ? (uint32_t)k : 0u;
+  }
   c->model_upd.push_back(u);
   if (c->model_known[id] && (c->models[id].root != u.root || c->models[id].flags != u.flags ||
                              (c->models[id].ranger_return < 0) != (u.ranger_return < 0)))
@@ -2155,11 +2293,11 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_r
   }
   c->epoch++; // K1 takes the largest proposal among the blobs, which is at least this (every sender proposed its own epoch + 1)
   CU(c, cudaEventRecord(c->t_ev[0][0], c->stream));
-  launch_apply_deltas(c->g, c->gv, (const unsigned char *)dev_gathered, n_ranks, slot_bytes, c->epoch, 0, c->stream,
+  launch_apply_deltas(c->g, c->gv, (const unsigned char *)dev_gathered, n_ranks, slot_bytes, c->epoch, 0, kDeltaEdgeRecords | kDeltaPoseRecords, c->stream,
                       &c->stats.launches_rasterise);
   if ((rc = ensure_table_room(c, add)))
     return rc;
-  launch_apply_deltas(c->g, c->gv, (const unsigned char *)dev_gathered, n_ranks, slot_bytes, c->epoch, 1, c->stream,
+  launch_apply_deltas(c->g, c->gv, (const unsigned char *)dev_gathered, n_ranks, slot_bytes, c->epoch, 1, kDeltaEdgeRecords | kDeltaPoseRecords, c->stream,
                       &c->stats.launches_rasterise);
   launch_owner_rebuild(c->g, c->stream, &c->stats.launches_rasterise); // other ranks' updates are only known there
   CU(c, cudaEventRecord(c->t_ev[0][1], c->stream));

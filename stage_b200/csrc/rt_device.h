@@ -104,6 +104,7 @@ struct GridView {
   uint32_t *mdl_root;
   double *mdl_ranger_return;
   uint32_t *mdl_flags;
+  uint8_t *mdl_pal;      // per model: index of its ranger_return in the host's palette of distinct values (0 is "no hit")
   uint32_t *err_host;    // page-locked host word: kErr* bits raised by K1 (read by stg_rt_sync)
 };
 
@@ -182,7 +183,7 @@ struct ModelUpd {
   uint32_t id, root;
   double ranger_return;
   int32_t fiducial_return, fiducial_key;
-  uint32_t flags, pad;
+  uint32_t flags, pal; // pal: palette index of ranger_return (GridView::mdl_pal)
 };
 static_assert(sizeof(ModelUpd) == 32, "ModelUpd");
 
@@ -234,6 +235,7 @@ struct FanBatchView {
   double *ranges, *intensities, *bearings;
   int32_t *hit_model, *hit_cell;
   uint32_t *steps;
+  uint8_t *intens_idx; // intensities as one palette index per beam (GridView::mdl_pal): 1 byte over PCIe instead of 8
 };
 
 // ---- whole ranger models (same layouts as stg_rt_ranger_* in include/stg_rt.h) ------------------
@@ -386,8 +388,10 @@ void launch_blobs(const GridView &g, const BlobBatchView &b, void *stream);
 void launch_debug_trig(uint64_t n, const double *x, double *cs, void *stream);
 
 // launch wrappers implemented in rt_kernels.cu; all asynchronous on `stream`
+// what: which kinds of record the blobs may hold (a local pass knows; a gathered pass says both)
+constexpr int kDeltaEdgeRecords = 1, kDeltaPoseRecords = 2;
 void launch_apply_deltas(const GridView &g, const GeomView &gv, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
-                         unsigned long long epoch, int phase, void *stream, uint64_t *launch_counter);
+                         unsigned long long epoch, int phase, int what, void *stream, uint64_t *launch_counter);
 void launch_owner_rebuild(const GridView &g, void *stream, uint64_t *launch_counter);
 void launch_fan_headings(const FanBatchView &b, void *stream);
 void launch_ray_march(const GridView &g, const FanBatchView &b, void *stream);

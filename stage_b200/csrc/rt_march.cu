@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(128, STG_MARCH_CTAS_PER_SM) k2_ray_march(GridV
     b.ranges[beam] = r.range;
   if (b.intensities)
     b.intensities[beam] = r.hit_model >= 0 ? __ldg(g.mdl_ranger_return + r.hit_model) : 0.0;
+  if (b.intens_idx)
+    b.intens_idx[beam] = r.hit_model >= 0 ? __ldg(g.mdl_pal + r.hit_model) : (uint8_t)0;
   if (b.hit_model)
     b.hit_model[beam] = r.hit_model;
   if (b.hit_cell) {

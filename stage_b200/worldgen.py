@@ -442,3 +442,23 @@ def ranger_poses(robots, robot_ids, layer, z=0.0):
     p["finder"], p["layer"] = robot_ids, layer
     p["x"], p["y"], p["z"], p["a"] = robots[:, 0], robots[:, 1], z, robots[:, 2] * (math.pi / 180.0)
     return p
+
+
+def local_box(size):
+    """Block::pts of the default unit-square block after BlockGroup::CalcSize scaled it to the model's size (blockgroup.cc:84-112)"""
+    sx, sy = size[0], size[1]
+    return np.array([[(-0.5 - 0.0) * (sx / 1.0), (-0.5 - 0.0) * (sy / 1.0)], [(0.5 - 0.0) * (sx / 1.0), (-0.5 - 0.0) * (sy / 1.0)],
+                     [(0.5 - 0.0) * (sx / 1.0), (0.5 - 0.0) * (sy / 1.0)], [(-0.5 - 0.0) * (sx / 1.0), (0.5 - 0.0) * (sy / 1.0)]])
+
+
+def define_boxes(ctx, first_block, model_ids, size):
+    """stg_rt_block_define for one box-shaped block per model (blocks first_block, first_block + 1, ...): from then on
+    stg_rt_models_pose_update renders them from poses alone"""
+    pts = local_box(size)
+    for j, mid in enumerate(model_ids):
+        ctx.block_define(int(first_block) + j, int(mid), 0.0, float(size[2]), pts)
+
+
+def gposes(robots, z=0.0):
+    """GetGlobalPose() + geom.pose of models whose geom.pose is zero: (n, 4) x, y, z, heading in radians"""
+    return np.ascontiguousarray(np.stack([robots[:, 0], robots[:, 1], np.full(len(robots), z), robots[:, 2] * (math.pi / 180.0)], 1))

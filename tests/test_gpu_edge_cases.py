@@ -456,3 +456,37 @@ def test_grid_digest_sees_entries_counts_and_list_order():
     assert hc[0][0] == ha[0][0] and hc[0][1] != ha[0][1] and hc[1][1] == ha[1][1] + 12 and hc[2] != ha[2]
     for p in (a, b, c):
         p.ctx.close()
+
+
+@pytest.mark.parametrize("n_values", [7, 255, 400])
+def test_intensities_through_the_palette_and_past_it(n_values):
+    """Sensor::intensities = the hit model's ranger_return (model_ranger.cc:250). Up to 255 distinct values cross PCIe as
+    one palette byte per beam and are expanded by stg_rt_sync; a world with more falls back to doubles. Same answers
+    either way, a re-published value included."""
+    ctx = rt.Context(50.0, -1, -1, 2, 2, max_models=n_values + 8, max_blocks=n_values + 8, max_cell_entries=1 << 18)
+    ctx.model_upsert(0, 0, 1.0)
+    ctx.model_upsert(1, 1, 0.25)            # the finder
+    vals = np.round(np.linspace(0.001, 0.999, n_values), 6)
+    rng = np.random.RandomState(5)
+    ang = np.linspace(-np.pi, np.pi, n_values, endpoint=False)
+    for k in range(n_values):               # a ring of small boxes around the origin, one model each, all seen from the centre
+        ctx.model_upsert(2 + k, 2 + k, float(vals[k]))
+        r = 300 + (k % 7) * 18
+        x, y = int(r * np.cos(ang[k])), int(r * np.sin(ang[k]))
+        ctx.block_map(k, 2 + k, 0, 0.0, 1.0, np.array([[x - 3, y - 3], [x + 3, y - 3], [x + 3, y + 3], [x - 3, y + 3]], np.int32))
+    fans = rt.make_fans(1)
+    fans["finder"], fans["n_samples"], fans["pred"], fans["ztest"], fans["layer"], fans["angles"] = 1, 4096, rt.PRED_RANGER, 1, 0, rt.ANGLES_RANGER
+    fans["ox"], fans["oy"], fans["oz"], fans["oa"], fans["range"], fans["fov"] = 0.001, 0.001, 0.5, -3.1, 9.0, 6.2
+    for round_ in range(2):
+        out = rt.Outputs(4096, rt.WANT_RANGES | rt.WANT_INTENSITIES | rt.WANT_HIT_MODEL, alloc=ctx.pinned_empty if round_ else None)
+        ctx.fans_submit(fans, out)
+        ctx.sync()
+        hit = out.hit_model >= 2
+        assert hit.sum() > n_values            # most boxes are seen by several beams
+        assert len(np.unique(out.hit_model[hit])) > 0.8 * n_values
+        want = np.where(hit, vals[np.clip(out.hit_model - 2, 0, n_values - 1)], 0.0)
+        assert np.array_equal(out.intensities, want)
+        k = int(rng.randint(n_values))         # SetRangerReturn on a model already published
+        vals[k] = 0.123456
+        ctx.model_upsert(2 + k, 2 + k, float(vals[k]))
+    ctx.close()

@@ -123,8 +123,16 @@ def test_moving_swarm_pose_path_equals_host_rasterised_path_and_oracle():
     ga, gb = a.trace(fans), b.trace(fans)
     assert np.array_equal(ga.ranges.view(np.uint64), gb.ranges.view(np.uint64)) and np.array_equal(ga.hit_model, gb.hit_model)
     assert np.array_equal(ga.steps, gb.steps)
+    # one more tick, counted: a moved robot costs 48 bytes of deltas instead of 296
+    poses = worldgen.step_robots(w, poses, 9, speed_m=0.3)
     st_a, st_b = a.stats(), b.stats()
-    assert st_a["h2d_bytes"] < st_b["h2d_bytes"] / 3   # 48 bytes per moved block instead of 296
+    a.models_pose_update(w.robot_ids, gposes(poses), 1)
+    b.blocks_remap(blocks, w.robot_ids, 1, z[n_ob:], first[:n + 1], worldgen.robot_boxes(w, poses).reshape(-1, 2))
+    a.sync()
+    b.sync()
+    da, db = a.stats()["h2d_bytes"] - st_a["h2d_bytes"], b.stats()["h2d_bytes"] - st_b["h2d_bytes"]
+    assert da == 96 + 48 * n and db == 96 + 296 * n
+    assert a.grid_hash() == b.grid_hash()
     a.close()
     b.close()
 
@@ -237,7 +245,7 @@ def test_pose_deltas_cross_the_rank_exchange():
     want = t1.grid_hash()
     for ctx in ctxs:
         assert ctx.grid_hash() == want
-    # the first tick replaces host-rasterised outlines (4 removal edges per robot); after that a robot costs 48 bytes
-    assert sent < n * (4 * 32 + 48) + 4 * n * 48 + 5 * n_ranks * 96 + 64
+    # the first tick of each layer replaces host-rasterised outlines (4 removal edges per robot); after that a robot costs 48 bytes
+    assert sent == 2 * n * (4 * 32 + 48) + 3 * n * 48 + 5 * n_ranks * 96
     for ctx in ctxs:
         ctx.close()

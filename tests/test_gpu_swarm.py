@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 
 def small_args(**kw):
-    a = argparse.Namespace(steps=3, warmup=3, rects=300, half_extent=20.48, robots=40, c4_robots=3000, c4_max_fiducials=64, c5_pucks=800)
+    a = argparse.Namespace(steps=3, warmup=3, rects=300, half_extent=20.48, robots=40, c4_robots=3000, c4_max_fiducials=64, c5_pucks=800, deltas="poses")
     for k, v in kw.items():
         setattr(a, k, v)
     return a
@@ -28,9 +28,10 @@ def make_env():
     return bench_swarm.Env(torch, None, 0, 1, 0, stream, 6450.3)
 
 
-def test_config4_swarm_record_is_exact():
+@pytest.mark.parametrize("deltas", ["poses", "outlines"])
+def test_config4_swarm_record_is_exact(deltas):
     import bench_swarm
-    rec = bench_swarm.run_c4(make_env(), small_args())
+    rec = bench_swarm.run_c4(make_env(), small_args(deltas=deltas))
     p = rec["parity"]
     assert p["mismatches_total"] == 0, p
     assert p["rays_checked"] >= 10000 and p["fiducials_checked"] > 200 and p["grid_digest_equals_oracle_on_every_rank"]
@@ -39,9 +40,10 @@ def test_config4_swarm_record_is_exact():
     assert rec["e2e"]["fiducials_seen_per_step"] > 1000
 
 
-def test_config5_moving_pucks_record_is_exact():
+@pytest.mark.parametrize("deltas", ["poses", "outlines"])
+def test_config5_moving_pucks_record_is_exact(deltas):
     import bench_swarm
-    rec = bench_swarm.run_c5(make_env(), small_args(), 270.0, 1080, 30.0)
+    rec = bench_swarm.run_c5(make_env(), small_args(deltas=deltas), 270.0, 1080, 30.0)
     p = rec["parity"]
     assert p["mismatches_total"] == 0, p
     assert p["rays_checked"] >= 10000 and p["grid_digest_equals_oracle_on_every_rank"] and p["rays_that_hit_a_puck"] > 0
