@@ -274,6 +274,28 @@ def peak_hbm_gbs():
         return 6650.0, "fallback 6650 (B200_PROFILING.md)"
 
 
+def kernel_source_digest():
+    """what the committed ncu capture of the march kernel is tied to: the sources the kernel is compiled from"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("rt_trace.cuh", "rt_march.cu", "rt_device.h", "rt_libm.cuh"):
+        h.update(open(os.path.join(ROOT, "stage_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def march_traffic():
+    """DRAM bytes per launch of the march kernel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of
+    this workload, profiles/r02_traffic.json) - reported only while the kernel's sources are the ones that capture was taken
+    from; a bench run cannot measure it itself (no profiler inside a timed run)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    except Exception:
+        return None, "no capture committed"
+    if t.get("kernel_source_digest") != kernel_source_digest():
+        return None, "the committed capture (profiles/r02_traffic.json) is of an older build of the kernel"
+    return t["dram_bytes_per_launch"], "ncu --set full capture of this kernel build, %s" % t.get("capture", "profiles/")
+
+
 def pin_to_gpu_numa(local_rank):
     """Restrict this process to the CPUs of the NUMA node the GPU is attached to; returns the node or None."""
     try:
@@ -551,10 +573,24 @@ def run_ours(args):
     if args.only in ("all", "c5") and args.workload == "c3":
         configs["c5"] = bench_swarm.run_c5(env, args, FOV_DEG, SAMPLES, RANGE_MAX)
 
+    # what bounds an e2e tick: the march stores its results into host memory as it goes, so its duration inside the e2e tick
+    # against the bytes it delivers is the link rate this run saw; profiles/r02_link_ceiling.json holds what the host takes
+    # from N GPUs at once (tools/link_ceiling.py on the 8-GPU box)
+    e2e_march_ms = env.max(e2e_kt["march_ms"])
     if rank == 0:
-        traffic = None
-        try:  # DRAM bytes per launch of the march kernel from the committed ncu --set full capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["dram_bytes_per_launch"]
+        traffic, traffic_note = march_traffic()
+        bytes_per_tick = (st1["d2h_bytes"] - st0["d2h_bytes"]) / args.steps
+        limiter = {"delivered_gb_per_s_per_gpu": bytes_per_tick / (e2e_march_ms * 1e-3) / 1e9, "march_ms_inside_the_tick": e2e_march_ms,
+                   "march_ms_results_in_hbm": float(np.mean(march_ms))}
+        try:
+            ceil = json.load(open(os.path.join(ROOT, "profiles", "r02_link_ceiling.json")))
+            c = ceil["kernel_stores"].get(str(n_gpus))
+            if c:
+                limiter["host_link_ceiling_gb_per_s_per_gpu"] = c
+                limiter["ceiling_source"] = "profiles/r02_link_ceiling.json (tools/link_ceiling.py, %d GPUs storing at once)" % n_gpus
+                limiter["what"] = ("the link to host memory: the march delivers at %.0f %% of what this host takes from %d GPU(s) at once"
+                                   % (100 * limiter["delivered_gb_per_s_per_gpu"] / c, n_gpus)) if limiter["delivered_gb_per_s_per_gpu"] > 0.7 * c \
+                    else "kernels and host calls (the link is not saturated)"
         except Exception:
             pass
         march_avg_ms = float(np.mean(march_ms))
@@ -574,12 +610,12 @@ def run_ours(args):
                                  "intensities (f64 in the caller's array: one palette byte per beam over PCIe, expanded by stg_rt_sync)",
                                  "bearings (f64, filled once per sensor type before the timed ticks: they depend on the sensor's geometry only)"],
                     "bearings_checked": bool(np.array_equal(bearings[:SAMPLES], -np.deg2rad(FOV_DEG) / 2.0 + np.arange(SAMPLES) * (np.deg2rad(FOV_DEG) / (SAMPLES - 1)))),
-                    "last_step_kernel_ms": e2e_kt, "host_call_ms_per_step": {k: v / args.steps for k, v in host_split.items()}, "timing": "host clock around K ticks, synchronised both sides, max over ranks"},
+                    "limiter": limiter, "last_step_kernel_ms": e2e_kt, "host_call_ms_per_step": {k: v / args.steps for k, v in host_split.items()}, "timing": "host clock around K ticks, synchronised both sides, max over ranks"},
             "gpu_launches": int(sum(st1[k] - launches0[k] for k in ("launches_rasterise", "launches_march", "launches_post", "launches_other"))),
             "kernel_ms": {"ray_march": march_avg_ms, "fan_headings": float(np.mean(head_ms)),
                           "share_of_step": march_avg_ms / (t_value_ms / args.steps) if n_gpus == 1 else None},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_source,
+                         "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_source,
                          "algorithmic_bytes_per_launch": algo_bytes, "cell_visits": C, "region_probes": R,
                          "beams": n_beams, "hit_fraction": hit_frac,
                          "note": "bytes = 4*C + 4*R + 40 per beam (SURVEY.md 8d), C/R counted by the kernel and proven equal to the oracle's in tests"},

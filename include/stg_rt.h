@@ -498,6 +498,12 @@ int stg_rt_debug_headings(stg_rt_ctx *ctx, uint32_t n_fans, const stg_rt_fan *fa
    rand() calls made. */
 uint32_t stg_rt_ranger_rand_advance(uint32_t n_samples, uint32_t n_in_range);
 
+/* Diagnostics: what the link from this GPU to page-locked host memory sustains, in GB/s, over `reps` transfers of
+   `bytes`: mode 0 = stores from a kernel straight into host memory (how the march delivers ranges and intensities),
+   mode 1 = cudaMemcpyAsync device-to-host. Run on several GPUs at once (tools/link_ceiling.py) it shows the ceiling the
+   host's PCIe / memory system puts on N result streams. Synchronous. */
+int stg_rt_debug_link_bandwidth(stg_rt_ctx *ctx, int mode, size_t bytes, int reps, double *gb_per_s);
+
 /* Counters since create: kernel launches by kind, rays traced, bytes copied each way. */
 typedef struct {
   uint64_t launches_rasterise, launches_march, launches_post, launches_other;

@@ -24,6 +24,7 @@
 namespace stg {
 void launch_rehash(const unsigned long long *src, unsigned long long *dst, uint32_t slot_mask, void *stream);
 void launch_grid_hash(const GridView &g, unsigned long long *out, void *stream);
+void launch_host_store(void *dst, size_t n_words, unsigned long long seed, void *stream);
 }
 
 using namespace stg;
@@ -199,7 +200,7 @@ struct stg_rt_ctx {
   uint32_t local_seq = 0;
   int last_export_rank = -1; // multi-GPU: this context's rank, learnt from stg_rt_delta_export
   bool export_mode = false;  // deltas leave through stg_rt_delta_export (never applied locally)
-  int64_t last_export_ins[2] = { 0, 0 }, last_gather_ins[2] = { 0, 0 };
+  int64_t last_export_ins[2] = { 0, 0 }, last_gather_ins[2] = { 0, 0 }, last_export_rem[2] = { 0, 0 }, last_gather_rem[2] = { 0, 0 };
   PinBuf h_hdrs;
   cudaEvent_t hdrs_ready = nullptr, xstream_ev = nullptr;
   bool hdrs_pending = false;
@@ -723,8 +724,10 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
     c->stats.h2d_bytes += nbytes;
     c->stats.edge_steps += rem_cursor + ins_cursor;
     if (!apply)
-      for (int L = 0; L < 2; L++)
+      for (int L = 0; L < 2; L++) {
         c->last_export_ins[L] = ins_round[L];
+        c->last_export_rem[L] = rem_round[L] + est_rem[L];
+      }
     for (int L = 0; L < 2; L++)
       c->live_entries[L] += d_live[L];
     if (apply) {
@@ -2259,19 +2262,22 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_r
   if (c->hdrs_pending) {
     CU(c, cudaEventSynchronize(c->hdrs_ready));
     const DeltaHeader *h = (const DeltaHeader *)c->h_hdrs.p;
-    int64_t all_ins[2] = { 0, 0 };
+    int64_t all_ins[2] = { 0, 0 }, all_rem[2] = { 0, 0 };
     for (int r = 0; r < c->hdrs_ranks; r++) {
       if (h[r].magic != kDeltaMagic)
         continue; // K1 skipped it and said so
       c->epoch = std::max<uint64_t>(c->epoch, h[r].epoch); // the epoch that pass really used
       for (int L = 0; L < 2; L++) {
         all_ins[L] += (int64_t)h[r].steps_insert_l[L] + h[r].est_insert_l[L];
+        all_rem[L] += (int64_t)h[r].steps_remove_l[L] + h[r].est_remove_l[L];
         if ((int)h[r].rank != c->last_export_rank) // this rank's own share was booked at export; the others' net change, signed
           c->live_entries[L] += (int64_t)h[r].steps_insert_l[L] + h[r].est_insert_l[L] - (int64_t)h[r].steps_remove_l[L] - h[r].est_remove_l[L];
       }
     }
-    for (int L = 0; L < 2; L++)
+    for (int L = 0; L < 2; L++) {
       c->last_gather_ins[L] = all_ins[L];
+      c->last_gather_rem[L] = all_rem[L];
+    }
     c->hdrs_pending = false;
   }
   if ((rc = upload_geometry_locked(c)))
@@ -2287,9 +2293,12 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_r
   int64_t add[2];
   for (int L = 0; L < 2; L++) {
     add[L] = std::max<int64_t>(c->last_gather_ins[L], (int64_t)n_ranks * c->last_export_ins[L]);
-    if (c->live_entries[L] + add[L] > (int64_t)c->slot_cap / 2)
-      return fail(c, STG_RT_ENOMEM, "cell-entry table of layer %d full (%lld entries + %lld arriving, capacity %u/2); raise max_cell_entries",
-                  L, (long long)c->live_entries[L], (long long)add[L], c->slot_cap);
+    // what this exchange is expected to leave in the table: as the last one did (every rank's movers re-rendered: as much
+    // goes as comes), or this rank's own share times the ranks before anything is known
+    const int64_t going = c->last_gather_ins[L] ? c->last_gather_rem[L] : (int64_t)n_ranks * c->last_export_rem[L];
+    if (c->live_entries[L] + std::max<int64_t>(add[L] - going, 0) > (int64_t)c->slot_cap / 2)
+      return fail(c, STG_RT_ENOMEM, "cell-entry table of layer %d full (%lld entries, %lld arriving, %lld leaving, capacity %u/2); raise max_cell_entries",
+                  L, (long long)c->live_entries[L], (long long)add[L], (long long)going, c->slot_cap);
   }
   c->epoch++; // K1 takes the largest proposal among the blobs, which is at least this (every sender proposed its own epoch + 1)
   CU(c, cudaEventRecord(c->t_ev[0][0], c->stream));
@@ -2968,6 +2977,57 @@ int stg_rt_debug_headings(stg_rt_ctx *c, uint32_t n_fans, const stg_rt_fan *fans
     if (b->p)
       cudaFree(b->p);
   return rc;
+}
+
+int stg_rt_debug_link_bandwidth(stg_rt_ctx *c, int mode, size_t bytes, int reps, double *gb_per_s)
+{
+  if (!c || !gb_per_s || bytes < 4096 || reps < 1 || mode < 0 || mode > 1)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = flush_locked(c);
+  if (rc || (rc = deliver_locked(c)))
+    return rc;
+  void *host = nullptr, *dev = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t e = cudaMallocHost(&host, bytes);
+  if (e == cudaSuccess)
+    e = cudaMalloc(&dev, bytes);
+  if (e == cudaSuccess)
+    e = cudaMemsetAsync(dev, 1, bytes, c->stream);
+  if (e == cudaSuccess)
+    e = cudaEventCreate(&e0);
+  if (e == cudaSuccess)
+    e = cudaEventCreate(&e1);
+  float ms = 0;
+  if (e == cudaSuccess) {
+    memset(host, 0, bytes); // fault the pages in
+    for (int r = -1; r < reps && e == cudaSuccess; r++) { // one untimed round first
+      if (r == 0)
+        e = cudaEventRecord(e0, c->stream);
+      if (mode == 0)
+        launch_host_store(host, bytes / 8, (unsigned long long)r + 2, c->stream);
+      else if (e == cudaSuccess)
+        e = cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (e == cudaSuccess)
+      e = cudaEventRecord(e1, c->stream);
+    if (e == cudaSuccess)
+      e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess)
+      e = cudaEventElapsedTime(&ms, e0, e1);
+  }
+  if (e0)
+    cudaEventDestroy(e0);
+  if (e1)
+    cudaEventDestroy(e1);
+  if (dev)
+    cudaFree(dev);
+  if (host)
+    cudaFreeHost(host);
+  if (e != cudaSuccess)
+    return fail(c, STG_RT_ECUDA, "debug_link_bandwidth: %s", cudaGetErrorString(e));
+  *gb_per_s = (double)bytes * reps / (ms * 1e-3) / 1e9;
+  return STG_RT_OK;
 }
 
 uint32_t stg_rt_ranger_rand_advance(uint32_t n_samples, uint32_t n_in_range)

@@ -1077,6 +1077,19 @@ void launch_fan_headings(const FanBatchView &b, void *stream)
     k2_fan_headings<<<b.n_fans, 32, 0, (cudaStream_t)stream>>>(b);
 }
 
+// Diagnostics: the store pattern the march uses for its results - every warp writes 256 contiguous bytes - aimed at
+// page-locked host memory, to measure what the link to the host takes (stg_rt_debug_link_bandwidth).
+__global__ void __launch_bounds__(128) k_host_store(unsigned long long *dst, size_t n_words, unsigned long long seed)
+{
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = seed + i;
+}
+
+void launch_host_store(void *dst, size_t n_words, unsigned long long seed, void *stream)
+{
+  k_host_store<<<148 * 16, 128, 0, (cudaStream_t)stream>>>((unsigned long long *)dst, n_words, seed);
+}
+
 // K2, the ray march, lives in rt_march.cu.
 
 } // namespace stg

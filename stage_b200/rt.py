@@ -130,6 +130,7 @@ def lib():
         "stg_rt_get_stats": (ctypes.c_int, [vp, ctypes.POINTER(Stats)]),
         "stg_rt_kernel_times": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_float * 3)]),
         "stg_rt_kernel_times_ex": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_float * 6), ctypes.c_int]),
+        "stg_rt_debug_link_bandwidth": (ctypes.c_int, [vp, ctypes.c_int, sz, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
         "stg_rt_debug_trig": (ctypes.c_int, [vp, u64, vp, vp]),
         "stg_rt_debug_headings": (ctypes.c_int, [vp, u32, vp, vp, vp]),
     }
@@ -147,7 +148,7 @@ EXPORTED_SYMBOLS = (
     "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_block_define stg_rt_models_pose_update stg_rt_debug_block_outline stg_rt_fiducials_submit stg_rt_fiducials_submit_packed stg_rt_rangers_submit stg_rt_collisions_test stg_rt_touching_models stg_rt_models_move stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
-    "stg_rt_delta_apply_gathered stg_rt_stream_signal stg_rt_stream_wait stg_rt_ranger_rand_advance stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_kernel_times_ex stg_rt_debug_trig stg_rt_debug_headings stg_rt_debug_region_owners stg_rt_grid_hash").split()
+    "stg_rt_delta_apply_gathered stg_rt_stream_signal stg_rt_stream_wait stg_rt_ranger_rand_advance stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_kernel_times_ex stg_rt_debug_link_bandwidth stg_rt_debug_trig stg_rt_debug_headings stg_rt_debug_region_owners stg_rt_grid_hash").split()
 
 
 _BYTES0 = ctypes.c_char * 0
@@ -439,6 +440,12 @@ class Context:
         self._check(self._L.stg_rt_kernel_times_ex(self._h, ctypes.byref(ms), 6))
         return {"deltas_ms": ms[0], "headings_ms": ms[1], "march_ms": ms[2], "fiducials_ms": ms[3], "blobs_ms": ms[4],
                 "collisions_ms": ms[5]}
+
+    def link_bandwidth(self, mode, nbytes, reps=20):
+        """GB/s into page-locked host memory: mode 0 = kernel stores (zero-copy), 1 = cudaMemcpyAsync D2H"""
+        v = ctypes.c_double(0)
+        self._check(self._L.stg_rt_debug_link_bandwidth(self._h, mode, nbytes, reps, ctypes.byref(v)))
+        return v.value
 
     def debug_trig(self, headings):
         """(n, 2) array of the device's (cos, sin) for the given headings"""
