@@ -26,6 +26,17 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(out_path, defines):
+    """the same library with extra -D flags (kernel experiments: STG_RT_LIBRARY=<out_path> makes rt.py load it)"""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out_path]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building %s" % out_path)
+    return out_path
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB

@@ -81,7 +81,7 @@ struct PinBuf {
 };
 
 struct FanArrays { // device arrays of one batch / resident set
-  DevBuf fans, first, headings_in, trig, heading;
+  DevBuf fans, first, headings_in, trig, heading, trigw; // trigw: per-beam (cos, sin) computed on the device for the refill march
   DevBuf ranges, intens, bearings, hit_model, hit_cell, steps;
 };
 
@@ -215,6 +215,7 @@ struct stg_rt_ctx {
   std::vector<double> h_pts;                      // pool of local points, 2 doubles each
   std::vector<std::vector<uint32_t> > model_blocks; // per model: its defined blocks in definition (= BlockGroup) order
   DevBuf d_geom, d_pts, d_pix[2], d_pix_new[2];
+  DevBuf d_work_counter; // the refill march's chunk counter
   bool geom_dirty = false;
   GeomView gv;
   PinBuf h_blob;
@@ -367,7 +368,7 @@ int pin_reserve(stg_rt_ctx *c, PinBuf &b, size_t bytes)
 
 void free_fan_arrays(FanArrays &a)
 {
-  DevBuf *all[] = { &a.fans, &a.first, &a.headings_in, &a.trig, &a.heading, &a.ranges,
+  DevBuf *all[] = { &a.fans, &a.first, &a.headings_in, &a.trig, &a.heading, &a.trigw, &a.ranges,
                     &a.intens, &a.bearings, &a.hit_model, &a.hit_cell, &a.steps };
   for (DevBuf *b : all) {
     if (b->p)
@@ -1114,8 +1115,15 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
     CU(c, cudaEventRecord(c->chunk_ev[0], c->stream)); // the fan records are uploaded
     CU(c, cudaStreamWaitEvent(hs, c->chunk_ev[0], 0));
   }
+  const bool refill = ray_march_refill_wanted(v);
+  if (refill && !v.trig_in && (rc = dev_reserve(c, c->d.trigw, beams * 16)))
+    return rc;
   CU(c, cudaEventRecord(c->t_ev[1][0], hs));
   launch_fan_headings(v, hs);
+  if (refill && !v.trig_in) { // cos / sin of every heading with all lanes busy, instead of inside the march's refills
+    launch_beam_trig(v, (double *)c->d.trigw.p, hs);
+    c->stats.launches_post++;
+  }
   CU(c, cudaEventRecord(c->t_ev[1][1], hs));
   const double t_prof1 = prof_now(c);
   if (with_deltas && (rc = apply_deltas_locked(c)))
@@ -1126,7 +1134,10 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   }
   const double t_prof2 = prof_now(c);
   CU(c, cudaEventRecord(c->t_ev[2][0], c->stream));
-  launch_ray_march(c->g, v, c->stream);
+  if (refill)
+    launch_ray_march_refill(c->g, v, v.trig_in ? v.trig_in : (const double *)c->d.trigw.p, (uint32_t *)c->d_work_counter.p, c->stream);
+  else
+    launch_ray_march(c->g, v, c->stream);
   CU(c, cudaEventRecord(c->t_ev[2][1], c->stream));
   c->t_rec[1] = c->t_rec[2] = true;
   CU(c, cudaGetLastError());
@@ -1290,6 +1301,8 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
   CUC(cudaMemsetAsync(g.mdl_root, 0, (size_t)cfg->max_models * 4, c->stream));
   CUC(cudaMemsetAsync(g.mdl_ranger_return, 0, (size_t)cfg->max_models * 8, c->stream));
   CUC(cudaMemsetAsync(g.mdl_flags, 0, (size_t)cfg->max_models * 4, c->stream));
+  CUC(cudaMalloc(&c->d_work_counter.p, 64));
+  c->d_work_counter.cap = 64;
   CUC(cudaMallocHost(&c->err_host, 64));
   *c->err_host = 0;
   g.err_host = c->err_host;
@@ -1331,7 +1344,7 @@ int stg_rt_destroy(stg_rt_ctx *c)
     cudaFreeHost(c->q_fans.p);
   if (c->d_in.p)
     cudaFree(c->d_in.p);
-  for (DevBuf *b : { &c->d_geom, &c->d_pts, &c->d_pix[0], &c->d_pix[1], &c->d_pix_new[0], &c->d_pix_new[1], &c->d_rig, &c->d_mv_in, &c->d_mv_out, &c->d_mover_of_model, &c->d_col_in, &c->d_col_hit, &c->d_touch_out, &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_fid_off, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
+  for (DevBuf *b : { &c->d_work_counter, &c->d_geom, &c->d_pts, &c->d_pix[0], &c->d_pix[1], &c->d_pix_new[0], &c->d_pix_new[1], &c->d_rig, &c->d_mv_in, &c->d_mv_out, &c->d_mover_of_model, &c->d_col_in, &c->d_col_hit, &c->d_touch_out, &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_fid_off, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
     if (b->p)
       cudaFree(b->p);
   for (PinBuf *b : { &c->h_rig, &c->h_mv_in, &c->h_mv_out, &c->h_col_in, &c->h_col_hit, &c->h_touch_out, &c->h_fid_in, &c->h_fid_out, &c->h_fid_count, &c->h_blob_in, &c->h_blob_out, &c->h_blob_count })
@@ -2020,11 +2033,21 @@ int stg_rt_set_trace(stg_rt_ctx *c, stg_rt_set *s)
   }
   FanBatchView v = view_of(s->d, (uint32_t)s->fans.size(), s->n_beams, s->want, s->has_trig, s->has_headings);
   v.uniform_samples = uniform_samples_of(s->fans.data(), s->fans.size());
+  const bool refill = ray_march_refill_wanted(v);
+  if (refill && !v.trig_in && (rc = dev_reserve(c, s->d.trigw, s->n_beams * 16)))
+    return rc;
   CU(c, cudaEventRecord(c->t_ev[1][0], c->stream));
   launch_fan_headings(v, c->stream);
+  if (refill && !v.trig_in) {
+    launch_beam_trig(v, (double *)s->d.trigw.p, c->stream);
+    c->stats.launches_post++;
+  }
   CU(c, cudaEventRecord(c->t_ev[1][1], c->stream));
   CU(c, cudaEventRecord(c->t_ev[2][0], c->stream));
-  launch_ray_march(c->g, v, c->stream);
+  if (refill)
+    launch_ray_march_refill(c->g, v, v.trig_in ? v.trig_in : (const double *)s->d.trigw.p, (uint32_t *)c->d_work_counter.p, c->stream);
+  else
+    launch_ray_march(c->g, v, c->stream);
   CU(c, cudaEventRecord(c->t_ev[2][1], c->stream));
   c->t_rec[1] = c->t_rec[2] = true;
   CU(c, cudaGetLastError());

@@ -395,5 +395,9 @@ void launch_apply_deltas(const GridView &g, const GeomView &gv, const unsigned c
 void launch_owner_rebuild(const GridView &g, void *stream, uint64_t *launch_counter);
 void launch_fan_headings(const FanBatchView &b, void *stream);
 void launch_ray_march(const GridView &g, const FanBatchView &b, void *stream);
+// the march with lane refill (rt_march.cu): per-beam (cos, sin) first, then the kernel
+bool ray_march_refill_wanted(const FanBatchView &b);
+void launch_beam_trig(const FanBatchView &b, double *trig, void *stream);
+void launch_ray_march_refill(const GridView &g, const FanBatchView &b, const double *trig, uint32_t *work_counter, void *stream);
 
 } // namespace stg

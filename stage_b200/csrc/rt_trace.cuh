@@ -397,6 +397,174 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
   res.region_probes = region_probes;
 }
 
+// ---- the same ray as a resumable state: set-up, one region step at a time, the hit range -------------------------
+// For the march kernel that hands a lane its next beam as soon as its ray has ended (rt_march.cu): what trace_ray keeps
+// in registers between two iterations of its outer loop, and that loop's body as a function. Same arithmetic, same
+// order of operations; only who executes it when differs.
+struct RayState {
+  double gx, gy, tana, trig_major, yjumpx;
+  int32_t n, E, b_run, b_cross, rm1, v1;
+  uint32_t flags;      // kYMajor ... kYNeg, | kLayer1
+  uint32_t finder_tag;
+  const FanRec *fan;
+  int32_t hit_x, hit_y; // global cell of the hit (valid once ray_step reports one)
+};
+enum : uint32_t { kLayer1 = 32u };
+
+__device__ __forceinline__ void ray_setup(const GridView &g, const FanRec *fan, double cosa, double sina, RayState &s)
+{
+  const double ppm = g.ppm;
+  s.fan = fan;
+  s.gx = fan->ox * ppm; // world.cc:765-766
+  s.gy = fan->oy * ppm;
+  s.tana = sina / cosa;
+  const double range = fan->range;
+  const double dx = ppm * range * cosa, dy = ppm * range * sina; // world.cc:780-781
+  const int32_t ax = __double2int_rz(fabs(dx)), ay = __double2int_rz(fabs(dy));
+  s.n = ax + ay; // world.cc:792
+  const bool ymajor = ay > ax;
+  s.b_run = ymajor ? 2 * ax : 2 * ay;
+  s.b_cross = ymajor ? 2 * ay : 2 * ax;
+  s.E = ymajor ? -(ay - ax) - 1 : (ay - ax);
+  const bool xneg = dx < 0, yneg = dy < 0;
+  s.flags = (ymajor ? kYMajor : 0u) | ((ymajor ? yneg : xneg) ? kRunNeg : 0u) | ((ymajor ? xneg : yneg) ? kCrossNeg : 0u) |
+            (xneg ? kXNeg : 0u) | (yneg ? kYNeg : 0u) | ((fan->layer & 1) ? kLayer1 : 0u);
+  int32_t r_max = 33;
+  if (s.b_run > 0 && (long long)s.b_run * 33 > s.b_cross)
+    r_max = (s.b_cross + s.b_run - 1) / s.b_run;
+  s.rm1 = r_max - 1;
+  s.v1 = (r_max - 1) * s.b_run;
+  s.trig_major = ax > ay ? cosa : sina; // world.cc:856-859
+  s.yjumpx = (yneg ? -(double)kRegionWidth : (double)kRegionWidth) / s.tana; // world.cc:797
+  s.finder_tag = fan->pred == 2u ? kOwnerNever : __ldg(g.mdl_root + fan->finder) + 1u;
+}
+
+// One iteration of World::Raytrace's outer loop (world.cc:818-957): a stretch of empty regions, if the ray stands in one,
+// then the walk of the populated region it reaches. Returns true when the ray has ended: hit_model >= 0, or -1 (out of range).
+__device__ __forceinline__ bool ray_step(const GridView &g, RayState &s, int32_t &hit_model)
+{
+  const uint32_t flags = s.flags;
+  const bool ymajor = (flags & kYMajor) != 0, runneg = (flags & kRunNeg) != 0;
+  const bool xneg = (flags & kXNeg) != 0, yneg = (flags & kYNeg) != 0, layer1 = (flags & kLayer1) != 0;
+  const uint32_t aflip = runneg ? kRegionWidth - 1 : 0u, cflip = (flags & kCrossNeg) ? kRegionWidth - 1 : 0u;
+  const uint32_t revmask = runneg ? ~0u : 0u;
+  const uint32_t occ_layer = layer1 ? (uint32_t)(g.occ[1] - g.occ[0]) : 0u;
+  double gx = s.gx, gy = s.gy;
+  int32_t n = s.n, E = s.E;
+  hit_model = -1;
+  int32_t ix0, iy0;
+  uint32_t region;
+  uint32_t count = probe_region(g, gx, gy, ix0, iy0, region);
+  if (!count) {
+    const double tana = s.tana;
+    double xcrossx, xcrossy, ycrossx, ycrossy, distX, distY;
+    {
+      double regionx = (double)(ix0 / kRegionWidth * kRegionWidth);
+      double regiony = (double)(iy0 / kRegionWidth * kRegionWidth);
+      if ((gx < 0) && (ix0 % kRegionWidth))
+        regionx -= kRegionWidth;
+      if ((gy < 0) && (iy0 % kRegionWidth))
+        regiony -= kRegionWidth;
+      const double xdx = xneg ? regionx - gx - 1.0 : regionx + kRegionWidth - gx;
+      const double xdy = xdx * tana;
+      const double ydy = yneg ? regiony - gy - 1.0 : regiony + kRegionWidth - gy;
+      const double ydx = ydy / tana;
+      xcrossx = gx + xdx;
+      xcrossy = gy + xdy;
+      ycrossx = gx + ydx;
+      ycrossy = gy + ydy;
+      distX = fabs(xdx) + fabs(xdy);
+      distY = fabs(ydx) + fabs(ydy);
+    }
+    do {
+      if (distX < distY) {
+        gx = xcrossx;
+        gy = xcrossy;
+        n = __double2int_rz((double)n - distX); // int -= double, world.cc:931
+        const double xjumpy = (xneg ? -(double)kRegionWidth : (double)kRegionWidth) * tana;
+        xcrossx += xneg ? -(double)kRegionWidth : (double)kRegionWidth;
+        xcrossy += xjumpy;
+        distY -= distX;
+        distX = (double)kRegionWidth + fabs(xjumpy);
+      } else {
+        gx = ycrossx;
+        gy = ycrossy;
+        n = __double2int_rz((double)n - distY);
+        ycrossx += s.yjumpx;
+        ycrossy += yneg ? -(double)kRegionWidth : (double)kRegionWidth;
+        distX -= distY;
+        distY = fabs(s.yjumpx) + (double)kRegionWidth;
+      }
+      if (n <= 0)
+        break;
+      count = probe_region(g, gx, gy, ix0, iy0, region);
+    } while (!count);
+    if (n <= 0) {
+      s.gx = gx;
+      s.gy = gy;
+      s.n = n;
+      return true;
+    }
+  }
+  // populated region (world.cc:823-882)
+  const int32_t cx0 = ix0 & (kRegionWidth - 1), cy0 = iy0 & (kRegionWidth - 1);
+  const int32_t cp0 = (int32_t)((uint32_t)(ymajor ? cx0 : cy0) ^ cflip);
+  const int32_t ap0 = (int32_t)((uint32_t)(ymajor ? cy0 : cx0) ^ aflip);
+  int32_t cp = cp0, ap = ap0;
+  uint32_t tile = occ_layer + region * kTileWords + (ymajor ? kRegionWidth : 0);
+  const int32_t cp_ahead = __ldg(g.reg_owner + region) != s.finder_tag ? kRegionWidth - 1 : 0;
+  uint32_t word = 0;
+  if (cp_ahead)
+    word = __ldg(g.occ[0] + (tile | ((uint32_t)cp ^ cflip)));
+  word ^= (word ^ __brev(word)) & revmask;
+  int32_t r = 0;
+  if (E < 0) {
+    const int32_t t = -E;
+    r = s.rm1 + 1;
+    if (s.v1 >= t) {
+      r = __float2int_rz((float)t * __frcp_rn((float)s.b_run));
+      while (r * s.b_run < t)
+        r++;
+      while (r > 0 && (r - 1) * s.b_run >= t)
+        r--;
+    }
+  }
+  WalkConst wc;
+  wc.b_run = s.b_run; wc.b_cross = s.b_cross; wc.rm1 = s.rm1; wc.v1 = s.v1; wc.cp_ahead = cp_ahead;
+  wc.revmask = revmask; wc.aflip = aflip; wc.cflip = cflip; wc.ymajor = ymajor;
+  uint32_t unused = 0;
+  int32_t mdl;
+  if (n >= 2 * kRegionWidth) {
+    mdl = walk_region<false, false>(g, s.fan, layer1, region, wc, ap, cp, E, n, r, word, tile, unused);
+    if (mdl < 0)
+      n -= (ap - ap0) + (cp - cp0);
+  } else {
+    mdl = walk_region<false, true>(g, s.fan, layer1, region, wc, ap, cp, E, n, r, word, tile, unused);
+  }
+  if (mdl >= 0) {
+    const uint32_t areal = (uint32_t)ap ^ aflip, creal = (uint32_t)cp ^ cflip;
+    s.hit_x = (ix0 & ~(kRegionWidth - 1)) + (int32_t)(ymajor ? creal : areal);
+    s.hit_y = (iy0 & ~(kRegionWidth - 1)) + (int32_t)(ymajor ? areal : creal);
+  }
+  const int32_t ka = ap - ap0, kc = cp - cp0;
+  s.gx = seq_add(gx, ymajor ? kc : ka, xneg);
+  s.gy = seq_add(gy, ymajor ? ka : kc, yneg);
+  s.n = n;
+  s.E = E;
+  hit_model = mdl;
+  return mdl >= 0 || n <= 0;
+}
+
+// RaytraceResult::range (world.cc:856-859; the ray's own range when nothing was hit)
+__device__ __forceinline__ double ray_range(const GridView &g, const RayState &s, int32_t hit_model)
+{
+  if (hit_model < 0)
+    return s.fan->range;
+  if (!(s.flags & kYMajor) && s.b_cross > s.b_run)
+    return fabs((s.gx - s.fan->ox * g.ppm) / s.trig_major) / g.ppm;
+  return fabs((s.gy - s.fan->oy * g.ppm) / s.trig_major) / g.ppm;
+}
+
 // cos / sin of a heading as World::Raytrace takes them (world.cc:773-775): the host C library's
 // values, bit for bit (rt_libm.cuh), because the traversal is chaotic in their last bit.
 __device__ __forceinline__ void heading_trig(double heading, double &cosa, double &sina)

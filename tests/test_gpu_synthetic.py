@@ -246,3 +246,28 @@ def test_random_rays_of_every_kind_match_oracle():
         assert 0.2 < np.mean(want["hit_model"] >= 0) < 0.95
     assert kinds_hit == {0, 1, 2}
     ctx.close()
+
+
+def test_refill_march_kernel_equals_the_plain_one(monkeypatch):
+    """k2_ray_march_refill (rt_march.cu: lanes take the next beam of their warp's chunk when their ray has ended; an
+    experiment kept off by default because it is slower) must give k2_ray_march's results bit for bit: ranges, intensities,
+    hit models, hit cells - with and without sensor noise, on fans that do not fill their chunks."""
+    from stage_b200 import worldgen
+    w = worldgen.make_world(seed=12, n_rects=500, n_robots=60, half_extent_m=30.72)
+    x0, y0, nx, ny = w.sreg_extent()
+    ctx = rt.Context(w.ppm, x0, y0, nx, ny, max_models=w.n_models + 1, max_blocks=len(w.obstacles) + len(w.robots), max_cell_entries=1 << 20)
+    worldgen.load_into_context(ctx, w)
+    want = rt.WANT_RANGES | rt.WANT_INTENSITIES | rt.WANT_HIT_MODEL | rt.WANT_HIT_CELL
+    for samples in (1080, 333):
+        fans = worldgen.ranger_fans(w, layer=1, samples=samples, range_max=25.0)
+        fans["range"][::7] = 0.0   # rays of no length
+        monkeypatch.setenv("STG_RT_MARCH", "plain")
+        a = ctx.trace(fans, want=want)
+        monkeypatch.setenv("STG_RT_MARCH", "refill")
+        st0 = ctx.stats()
+        b = ctx.trace(fans, want=want)
+        assert ctx.stats()["launches_post"] - st0["launches_post"] == 2   # headings + the per-beam trig kernel: the refill path ran
+        assert np.array_equal(a.ranges.view(np.uint64), b.ranges.view(np.uint64)) and np.array_equal(a.intensities, b.intensities)
+        assert np.array_equal(a.hit_model, b.hit_model) and np.array_equal(a.hit_cell, b.hit_cell)
+        assert (a.hit_model >= 0).mean() > 0.5
+    ctx.close()
