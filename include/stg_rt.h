@@ -39,7 +39,7 @@ enum {
   STG_RT_EINVAL = -1,   /* bad argument */
   STG_RT_ECUDA = -2,    /* CUDA runtime error (text in stg_rt_last_error) */
   STG_RT_ENOMEM = -3,   /* a fixed-capacity table is full (models, blocks, cell entries) */
-  STG_RT_EEXTENT = -4,  /* a polygon leaves the device grid extent given at create */
+  STG_RT_EEXTENT = -4,  /* the world would span more than 4095 SuperRegions (the device grid's limit) */
   STG_RT_ESTATE = -5,   /* call not valid in the current state */
   STG_RT_ENODEV = -6    /* no usable CUDA device */
 };
@@ -87,9 +87,12 @@ typedef struct {
   uint32_t struct_size;   /* sizeof(stg_rt_config), for ABI growth */
   int32_t device;         /* CUDA device ordinal */
   double ppm;             /* World::ppm = 1/resolution (world.cc:406) */
-  /* Dense device grid extent in SuperRegion units (1024 x 1024 cells each, region.hh:13-18):
-     superregions [sreg_x0, sreg_x0+sreg_nx) x [sreg_y0, sreg_y0+sreg_ny). Rays may leave it
-     (outside is empty space, as for a missing SuperRegion, world.cc:820-823); polygons may not. */
+  /* Initial extent of the dense device grid in SuperRegion units (1024 x 1024 cells each, region.hh:13-18):
+     superregions [sreg_x0, sreg_x0+sreg_nx) x [sreg_y0, sreg_y0+sreg_ny). Rays may leave it (outside is empty
+     space, as for a missing SuperRegion, world.cc:820-823). A polygon rendered outside it makes the grid GROW, as
+     World::AddSuperRegion grows the reference's world (world.cc:1072-1093): the arrays are re-laid over the larger
+     rectangle on the device (stg_rt_stats.extent_grows counts it; O(grid), so give the expected extent here).
+     STG_RT_EEXTENT is left for worlds beyond 4095 SuperRegions. */
   int32_t sreg_x0, sreg_y0, sreg_nx, sreg_ny;
   uint32_t max_models;    /* capacity of the model table */
   uint32_t max_blocks;    /* capacity of the block table */
@@ -509,6 +512,7 @@ typedef struct {
   uint64_t launches_rasterise, launches_march, launches_post, launches_other;
   uint64_t beams, fans, map_calls, unmap_calls, edge_steps;
   uint64_t h2d_bytes, d2h_bytes;
+  uint64_t extent_grows; /* times the device grid was re-laid over a larger extent (World::AddSuperRegion) */
 } stg_rt_stats;
 int stg_rt_get_stats(stg_rt_ctx *ctx, stg_rt_stats *out);
 

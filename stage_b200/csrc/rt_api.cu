@@ -25,6 +25,7 @@ namespace stg {
 void launch_rehash(const unsigned long long *src, unsigned long long *dst, uint32_t slot_mask, void *stream);
 void launch_grid_hash(const GridView &g, unsigned long long *out, void *stream);
 void launch_host_store(void *dst, size_t n_words, unsigned long long seed, void *stream);
+void launch_grow(const GridView &from, const GridView &to, void *stream);
 }
 
 using namespace stg;
@@ -1478,6 +1479,76 @@ int stg_rt_block_unmap(stg_rt_ctx *c, uint32_t block_id, int layer)
   return block_unmap_locked(c, block_id, layer);
 }
 
+// World::AddSuperRegion (world.cc:1072-1093): the reference's world grows whenever something is rendered outside it. Here
+// the dense extent is re-laid over the larger rectangle of SuperRegions that holds the old one and the cells
+// [x0..x1] x [y0..y1] (plus one SuperRegion of room on the sides that grew), on the device (launch_grow).
+static int grow_extent_locked(stg_rt_ctx *c, int32_t x0, int32_t y0, int32_t x1, int32_t y1)
+{
+  GridView &g = c->g;
+  const int32_t osx0 = g.rx0 >> 5, osy0 = g.ry0 >> 5, osx1 = osx0 + (g.nrx >> 5) - 1, osy1 = osy0 + (g.nry >> 5) - 1;
+  int32_t sx0 = std::min(osx0, x0 >> 10), sy0 = std::min(osy0, y0 >> 10), sx1 = std::max(osx1, x1 >> 10), sy1 = std::max(osy1, y1 >> 10);
+  if (sx0 < osx0) sx0--; // room to keep going that way
+  if (sy0 < osy0) sy0--;
+  if (sx1 > osx1) sx1++;
+  if (sy1 > osy1) sy1++;
+  const int64_t nsx = (int64_t)sx1 - sx0 + 1, nsy = (int64_t)sy1 - sy0 + 1;
+  if (nsx * nsy > 4095)
+    return fail(c, STG_RT_EEXTENT, "the world would span %lld x %lld SuperRegions; the device grid holds at most 4095", (long long)nsx, (long long)nsy);
+  int rc = flush_locked(c); // what is queued belongs to the grid as it is
+  if (rc || (rc = deliver_locked(c)))
+    return rc;
+  GridView to = g;
+  to.rx0 = sx0 * 32;
+  to.ry0 = sy0 * 32;
+  to.nrx = (int32_t)nsx * 32;
+  to.nry = (int32_t)nsy * 32;
+  const size_t n_new = (size_t)to.nrx * to.nry;
+  to.n_regions = (uint32_t)n_new;
+  to.reg_count = to.reg_owner = to.occ[0] = nullptr;
+  to.slots[0] = to.slots[1] = nullptr;
+  unsigned long long *fresh[2] = { nullptr, nullptr };
+  cudaError_t e = cudaMalloc(&to.reg_count, n_new * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&to.reg_owner, (n_new + 1) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&to.occ[0], 2 * n_new * kTileWords * 4);
+  for (int L = 0; L < 2 && e == cudaSuccess; L++)
+    e = cudaMalloc(&fresh[L], (size_t)c->slot_cap * 8);
+  if (e == cudaSuccess) e = cudaMemsetAsync(to.reg_count, 0, n_new * 4, c->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(to.reg_owner, 0, (n_new + 1) * 4, c->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(to.occ[0], 0, 2 * n_new * kTileWords * 4, c->stream);
+  for (int L = 0; L < 2 && e == cudaSuccess; L++)
+    e = cudaMemsetAsync(fresh[L], 0, (size_t)c->slot_cap * 8, c->stream);
+  if (e != cudaSuccess) {
+    for (void *p : { (void *)to.reg_count, (void *)to.reg_owner, (void *)to.occ[0], (void *)fresh[0], (void *)fresh[1] })
+      if (p)
+        cudaFree(p);
+    cudaGetLastError();
+    return fail(c, STG_RT_ENOMEM, "no device memory for a grid of %lld x %lld SuperRegions: %s", (long long)nsx, (long long)nsy, cudaGetErrorString(e));
+  }
+  to.occ[1] = to.occ[0] + n_new * kTileWords;
+  to.slots[0] = fresh[0];
+  to.slots[1] = fresh[1];
+  launch_grow(g, to, c->stream);
+  c->stats.launches_other += 3;
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaGetLastError());
+  for (void *p : { (void *)g.reg_count, (void *)g.reg_owner, (void *)g.occ[0], (void *)g.slots[0], (void *)g.slots[1] })
+    cudaFree(p);
+  g = to;
+  c->n_regions = n_new;
+  c->cell_x0 = g.rx0 * 32;
+  c->cell_y0 = g.ry0 * 32;
+  c->cell_x1 = c->cell_x0 + g.nrx * 32 - 1;
+  c->cell_y1 = c->cell_y0 + g.nry * 32 - 1;
+  c->cfg.sreg_x0 = sx0;
+  c->cfg.sreg_y0 = sy0;
+  c->cfg.sreg_nx = (int32_t)nsx;
+  c->cfg.sreg_ny = (int32_t)nsy;
+  for (int L = 0; L < 2; L++)
+    c->used_upper[L] = c->live_entries[L]; // fresh tables: no tombstones
+  c->stats.extent_grows++;
+  return STG_RT_OK;
+}
+
 int stg_rt_block_define(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id, double local_zmin, double local_zmax, int n_pts,
                         const double *pts_xy)
 {
@@ -1558,9 +1629,13 @@ int stg_rt_models_pose_update(stg_rt_ctx *c, uint32_t n, const uint32_t *models,
         for (uint32_t v = 0; v < g.n_pts; v++) {
           const double px = floor((P[0] + pt[2 * v] * cosa - pt[2 * v + 1] * sina) * c->cfg.ppm);
           const double py = floor((P[1] + pt[2 * v] * sina + pt[2 * v + 1] * cosa) * c->cfg.ppm);
-          if (!(px >= c->cell_x0 && px <= c->cell_x1 && py >= c->cell_y0 && py <= c->cell_y1))
-            return fail(c, STG_RT_EEXTENT, "model %u at (%.3f, %.3f): block %u vertex (%.0f,%.0f) outside the device grid [%d..%d]x[%d..%d]", m, P[0],
-                        P[1], block_id, px, py, c->cell_x0, c->cell_x1, c->cell_y0, c->cell_y1);
+          if (!(px >= c->cell_x0 && px <= c->cell_x1 && py >= c->cell_y0 && py <= c->cell_y1)) {
+            if (!(fabs(px) < 2.0e9 && fabs(py) < 2.0e9))
+              return fail(c, STG_RT_EEXTENT, "model %u at (%.3f, %.3f): block %u vertex beyond 32-bit cell coordinates", m, P[0], P[1], block_id);
+            const int rcg = grow_extent_locked(c, (int32_t)px, (int32_t)py, (int32_t)px, (int32_t)py); // the world grows
+            if (rcg)
+              return rcg;
+          }
         }
       }
       if (!c->q_subs.empty()) { // issue order: queued fans must be traced against the grid as it was
@@ -1653,10 +1728,21 @@ static int block_map_locked(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id,
     return fail(c, STG_RT_EINVAL, "block_map: unknown model %u (call stg_rt_model_upsert first)", model_id);
   BlockShadow &b = c->blocks[block_id];
   uint64_t steps = 0; // cell visits of this outline: |dx| + |dy| per edge (world.cc:1000-1002)
+  {
+    int32_t bx0 = c->cell_x0, by0 = c->cell_y0, bx1 = c->cell_x1, by1 = c->cell_y1;
+    for (int i = 0; i < n_pts; i++) {
+      bx0 = std::min(bx0, xy[2 * i]);
+      bx1 = std::max(bx1, xy[2 * i]);
+      by0 = std::min(by0, xy[2 * i + 1]);
+      by1 = std::max(by1, xy[2 * i + 1]);
+    }
+    if (bx0 < c->cell_x0 || by0 < c->cell_y0 || bx1 > c->cell_x1 || by1 > c->cell_y1) { // the world grows, as the reference's does
+      const int rcg = grow_extent_locked(c, bx0, by0, bx1, by1);
+      if (rcg)
+        return rcg;
+    }
+  }
   for (int i = 0; i < n_pts; i++) {
-    if (xy[2 * i] < c->cell_x0 || xy[2 * i] > c->cell_x1 || xy[2 * i + 1] < c->cell_y0 || xy[2 * i + 1] > c->cell_y1)
-      return fail(c, STG_RT_EEXTENT, "block %u vertex (%d,%d) outside the device grid [%d..%d]x[%d..%d]", block_id, xy[2 * i],
-                  xy[2 * i + 1], c->cell_x0, c->cell_x1, c->cell_y0, c->cell_y1);
     const int j = i + 1 == n_pts ? 0 : i + 1;
     steps += (uint64_t)std::llabs((long long)xy[2 * j] - xy[2 * i]) + (uint64_t)std::llabs((long long)xy[2 * j + 1] - xy[2 * i + 1]);
   }

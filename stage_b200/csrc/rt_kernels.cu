@@ -755,6 +755,57 @@ __global__ void __launch_bounds__(256) k1_grid_hash(GridView g, unsigned long lo
   }
 }
 
+static int delta_grid_blocks();
+
+// ---- growing the extent (World::AddSuperRegion, world.cc:1072-1093: the reference's world grows whenever a polygon is
+// rendered outside it) -------------------------------------------------------------------------------------------
+// The grid is dense over a rectangle of SuperRegions; growing it means new arrays over the larger rectangle and every
+// region's count, owner tag and occupancy tiles copied to its new index, then every cell entry re-keyed (a cell key
+// starts with the region index) into fresh tables. Rare (a robot driving off the map), O(grid), entirely on the device.
+__global__ void __launch_bounds__(256) k1_grow_regions(GridView from, GridView to)
+{
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < from.n_regions; r += gridDim.x * blockDim.x) {
+    const int32_t rx = from.rx0 + (int32_t)(r % (uint32_t)from.nrx), ry = from.ry0 + (int32_t)(r / (uint32_t)from.nrx);
+    const uint32_t rn = (uint32_t)((ry - to.ry0) * to.nrx + (rx - to.rx0));
+    to.reg_count[rn] = from.reg_count[r];
+    to.reg_owner[rn] = from.reg_owner[r];
+    if (from.reg_count[r])
+      for (int L = 0; L < 2; L++)
+        for (int w = 0; w < kTileWords; w++)
+          to.occ[L][(size_t)rn * kTileWords + w] = from.occ[L][(size_t)r * kTileWords + w];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    to.reg_owner[to.n_regions] = from.reg_owner[from.n_regions]; // the "owners are stale" flag
+}
+
+__global__ void __launch_bounds__(256) k1_grow_rehash(GridView from, GridView to, int L)
+{
+  for (uint64_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= from.slot_mask; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long cur = from.slots[L][i];
+    if (cur == kSlotEmpty || cur == kSlotTomb)
+      continue;
+    const uint32_t key = (uint32_t)(cur >> 32), r = key >> (2 * kRBits);
+    const int32_t rx = from.rx0 + (int32_t)(r % (uint32_t)from.nrx), ry = from.ry0 + (int32_t)(r / (uint32_t)from.nrx);
+    const uint32_t rn = (uint32_t)((ry - to.ry0) * to.nrx + (rx - to.rx0));
+    const uint32_t nkey = (rn << (2 * kRBits)) | (key & ((1u << (2 * kRBits)) - 1u));
+    const unsigned long long entry = ((unsigned long long)nkey << 32) | (cur & 0xffffffffull);
+    uint32_t h = slot_home(nkey, to.slot_mask);
+    for (uint32_t probes = 0; probes <= to.slot_mask; probes++) {
+      if (atomicCAS(to.slots[L] + h, kSlotEmpty, entry) == kSlotEmpty)
+        break;
+      h = (h + 1) & to.slot_mask;
+    }
+  }
+}
+
+void launch_grow(const GridView &from, const GridView &to, void *stream)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  k1_grow_regions<<<delta_grid_blocks(), 256, 0, s>>>(from, to);
+  for (int L = 0; L < 2; L++)
+    k1_grow_rehash<<<delta_grid_blocks(), 256, 0, s>>>(from, to, L);
+}
+
 static int delta_grid_blocks()
 {
   static int blocks = 0;

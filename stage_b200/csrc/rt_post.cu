@@ -20,10 +20,13 @@ __device__ __forceinline__ double normalize_angle(double a)
   return a;
 }
 
-// AddModelIfVisible (model_fiducial.cc:109-224) for one (finder, target) pair, after the x / y
-// window of the candidate query (:245-262, bounds inclusive). True = the target is seen; rec filled.
-__device__ __forceinline__ bool fid_try(const GridView &g, const FidFinderRec &fd, const FanRec *fan, uint32_t finder_root,
-                                        const FidTargetRec &him, uint32_t t, FiducialRec &rec)
+// AddModelIfVisible (model_fiducial.cc:109-224) for one (finder, target) pair, in three parts so that a warp can first
+// sift a finder's candidates with all lanes and then trace only the survivors, again with all lanes (k3_fiducials_grid):
+//   fid_cull    the x / y window of the candidate query (:245-262, bounds inclusive), key, range, field of view, relatedness
+//   fid_sees    the line-of-sight ray and the accept rule (:179-193)
+//   fid_record  the Fiducial record (:199-221)
+__device__ __forceinline__ bool fid_cull(const GridView &g, const FidFinderRec &fd, uint32_t finder_root, const FidTargetRec &him, double &range,
+                                         double &dtheta)
 {
   if (him.model == fd.finder || him.x < fd.x - fd.max_range_anon || him.x > fd.x + fd.max_range_anon ||
       him.y < fd.y - fd.max_range_anon || him.y > fd.y + fd.max_range_anon)
@@ -31,14 +34,17 @@ __device__ __forceinline__ bool fid_try(const GridView &g, const FidFinderRec &f
   if (him.fiducial_key != fd.fiducial_key) // :117
     return false;
   const double dx = him.x - fd.x, dy = him.y - fd.y;
-  const double range = hypot(dy, dx);                              // :130
+  range = hypot(dy, dx);                                            // :130
   if (range >= fd.max_range_anon)                                   // :134
     return false;
-  const double dtheta = normalize_angle(atan2(dy, dx) - fd.a);     // :144-145
+  dtheta = normalize_angle(atan2(dy, dx) - fd.a);                  // :144-145
   if (fabs(dtheta) > fd.fov / 2.0)                                  // :147
     return false;
-  if (__ldg(g.mdl_root + him.model) == finder_root)                // IsRelated, :152
-    return false;
+  return __ldg(g.mdl_root + him.model) != finder_root;             // IsRelated, :152
+}
+
+__device__ __forceinline__ bool fid_sees(const GridView &g, const FidFinderRec &fd, const FanRec *fan, uint32_t him_model, double dtheta)
+{
   // Raytrace(Pose(0,0,0,dtheta), max_range_anon, fiducial_raytrace_match, NULL, true), :179:
   // LocalToGlobal adds the heading onto (GetGlobalPose() + geom.pose) and normalises it
   double cosa, sina;
@@ -47,9 +53,12 @@ __device__ __forceinline__ bool fid_try(const GridView &g, const FidFinderRec &f
   trace::trace_ray<false>(g, fan, cosa, sina, r);
   int32_t seen = r.hit_model;
   if (fd.ignore_zloc && seen < 0) // :184
-    seen = (int32_t)him.model;
-  if (seen != (int32_t)him.model) // :192
-    return false;
+    seen = (int32_t)him_model;
+  return seen == (int32_t)him_model; // :192
+}
+
+__device__ __forceinline__ void fid_record(const FidFinderRec &fd, const FidTargetRec &him, uint32_t t, double range, double dtheta, FiducialRec &rec)
+{
   rec.target = t;
   rec.id = range < fd.max_range_id ? him.fiducial_return : 0; // :219
   rec.range = range;
@@ -62,6 +71,15 @@ __device__ __forceinline__ bool fid_try(const GridView &g, const FidFinderRec &f
   rec.pose[1] = him.y;
   rec.pose[2] = him.z;
   rec.pose[3] = him.a;
+}
+
+__device__ __forceinline__ bool fid_try(const GridView &g, const FidFinderRec &fd, const FanRec *fan, uint32_t finder_root,
+                                        const FidTargetRec &him, uint32_t t, FiducialRec &rec)
+{
+  double range, dtheta;
+  if (!fid_cull(g, fd, finder_root, him, range, dtheta) || !fid_sees(g, fd, fan, him.model, dtheta))
+    return false;
+  fid_record(fd, him, t, range, dtheta, rec);
   return true;
 }
 
@@ -145,44 +163,96 @@ __global__ void __launch_bounds__(256) k3_fid_bin_scatter(FidGridView v, uint32_
     v.sorted[atomicAdd(v.cursor + v.bin_of[t], 1u)] = t;
 }
 
+// One warp per finder, in two alternating phases so that both run with full lanes: the lanes SIFT 32 candidates of the
+// window's bins at a time (fid_cull: cheap, and four of five candidates fall out - 2100 in the 3 x 3 bins of a config-4
+// finder, 370 inside its half disc) and queue the survivors in shared memory; whenever 32 are queued the lanes TRACE one
+// line of sight each (fid_sees). Tracing straight from the sift kept 9 of 32 lanes busy (profiles/).
+constexpr uint32_t kFidQueue = 64;
+
 __global__ void __launch_bounds__(128) k3_fiducials_grid(GridView g, FidBatchView b, FidGridView v)
 {
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  __shared__ uint32_t q_t[4][kFidQueue];
+  __shared__ double q_range[4][kFidQueue], q_dtheta[4][kFidQueue];
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   if (warp >= b.n_finders)
     return;
   const FidFinderRec fd = b.finders[warp];
   const FanRec *fan = b.fans + warp;
   const uint32_t finder_root = __ldg(g.mdl_root + fd.finder);
+  const uint32_t lt = (1u << lane) - 1u;
   FiducialRec *out = b.out + (size_t)warp * b.max_per_finder;
   const int32_t bx0 = min(max((int32_t)floor((fd.x - fd.max_range_anon - v.x0) / v.cell), 0), v.nbx - 1);
   const int32_t bx1 = min(max((int32_t)floor((fd.x + fd.max_range_anon - v.x0) / v.cell), 0), v.nbx - 1);
   const int32_t by0 = min(max((int32_t)floor((fd.y - fd.max_range_anon - v.y0) / v.cell), 0), v.nby - 1);
   const int32_t by1 = min(max((int32_t)floor((fd.y + fd.max_range_anon - v.y0) / v.cell), 0), v.nby - 1);
-  uint32_t n_out = 0;
+  uint32_t n_out = 0, q_n = 0;
+  // trace the first `take` queued candidates, one per lane, and keep the records of those that are seen
+  auto drain = [&](uint32_t take) {
+    bool accept = false;
+    uint32_t t = 0;
+    double range = 0, dtheta = 0;
+    if (lane < take) {
+      t = q_t[wib][lane];
+      range = q_range[wib][lane];
+      dtheta = q_dtheta[wib][lane];
+      accept = fid_sees(g, fd, fan, __ldg(&b.targets[t].model), dtheta);
+    }
+    const uint32_t votes = __ballot_sync(0xffffffffu, accept);
+    if (accept) {
+      const uint32_t slot = n_out + __popc(votes & lt);
+      if (slot < b.max_per_finder)
+        fid_record(fd, b.targets[t], t, range, dtheta, out[slot]);
+    }
+    n_out += __popc(votes);
+    // what is left of the queue moves to its front
+    const uint32_t rest = q_n - take;
+    uint32_t mt = 0;
+    double mr = 0, md = 0;
+    if (lane < rest) {
+      mt = q_t[wib][take + lane];
+      mr = q_range[wib][take + lane];
+      md = q_dtheta[wib][take + lane];
+    }
+    __syncwarp();
+    if (lane < rest) {
+      q_t[wib][lane] = mt;
+      q_range[wib][lane] = mr;
+      q_dtheta[wib][lane] = md;
+    }
+    q_n = rest;
+    __syncwarp();
+  };
   for (int32_t by = by0; by <= by1; by++)
     for (int32_t bx = bx0; bx <= bx1; bx++) {
       const uint32_t bin = (uint32_t)(by * v.nbx + bx);
       const uint32_t lo = __ldg(v.start + bin), hi = __ldg(v.start + bin + 1);
       for (uint32_t i0 = lo; i0 < hi; i0 += 32) {
         const uint32_t i = i0 + lane;
-        FiducialRec rec;
-        bool accept = false;
+        bool pass = false;
+        uint32_t t = 0;
+        double range = 0, dtheta = 0;
         if (i < hi) {
-          const uint32_t t = __ldg(v.sorted + i);
-          accept = fid_try(g, fd, fan, finder_root, b.targets[t], t, rec);
+          t = __ldg(v.sorted + i);
+          pass = fid_cull(g, fd, finder_root, b.targets[t], range, dtheta);
         }
-        const uint32_t votes = __ballot_sync(0xffffffffu, accept);
-        if (accept) {
-          const uint32_t slot = n_out + __popc(votes & ((1u << lane) - 1u));
-          if (slot < b.max_per_finder)
-            out[slot] = rec;
+        const uint32_t votes = __ballot_sync(0xffffffffu, pass);
+        if (pass) { // q_n < 32 here, so at most 63 entries are ever queued
+          const uint32_t at = q_n + __popc(votes & lt);
+          q_t[wib][at] = t;
+          q_range[wib][at] = range;
+          q_dtheta[wib][at] = dtheta;
         }
-        n_out += __popc(votes);
+        q_n += __popc(votes);
+        __syncwarp();
+        if (q_n >= 32)
+          drain(32);
       }
     }
+  if (q_n)
+    drain(q_n);
   __syncwarp();
   if (lane == 0) {
-    // bins were visited in grid order: put the records back into target order (ascending Model*)
+    // candidates were traced in bin order: put the records back into target order (ascending Model*)
     const uint32_t k = min(n_out, b.max_per_finder);
     for (uint32_t i = 1; i < k; i++) {
       const FiducialRec r = out[i];

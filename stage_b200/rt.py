@@ -62,7 +62,7 @@ class FanOut(ctypes.Structure):
 class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in (
         "launches_rasterise", "launches_march", "launches_post", "launches_other", "beams", "fans",
-        "map_calls", "unmap_calls", "edge_steps", "h2d_bytes", "d2h_bytes")]
+        "map_calls", "unmap_calls", "edge_steps", "h2d_bytes", "d2h_bytes", "extent_grows")]
 
 
 class StgRtError(RuntimeError):

@@ -31,7 +31,7 @@ def test_struct_layouts_match_the_header():
     assert rt.FAN_DTYPE.itemsize == 64
     assert ctypes.sizeof(rt.Config) == 56
     assert ctypes.sizeof(rt.FanOut) == 6 * 8
-    assert ctypes.sizeof(rt.Stats) == 11 * 8
+    assert ctypes.sizeof(rt.Stats) == 12 * 8
     assert rt.lib().stg_rt_abi_version() == 1
 
 

