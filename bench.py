@@ -330,6 +330,9 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    # the library's host threads (stg_rt_sync expands intensity palette indices with them): the box's cores are shared by
+    # the ranks, one of each rank's share stays with the thread that calls the ABI
+    os.environ.setdefault("STG_RT_HOST_THREADS", str(max(1, min(8, (os.cpu_count() or 8) // max(1, n_gpus) - 1))))
     if world_size != n_gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torchrun --nproc-per-node %d" % (n_gpus, world_size, n_gpus))
     if not torch.cuda.is_available():

@@ -259,13 +259,13 @@ def run_c4(env, args):
 
     ticks = [prepare(t) for t in range(1, n_ticks + 1)]
     exchange = multi.DeltaExchange(ctx, rank, N, dist=dist) if N > 1 else None
-    tex = multi.TargetExchange(rank, N, max_per_rank=multi.shard_bounds(n_total, 0, N)[1], record_dtype=rt.FID_TARGET_DTYPE, dist=dist) if N > 1 else None
+    # the fiducial target records of every rank's robots, all-gathered on the device: only a rank's own share crosses PCIe
+    tex = multi.TargetExchange(rank, N, max_per_rank=multi.shard_bounds(n_total, 0, N)[1], record_dtype=rt.FID_TARGET_DTYPE, dist=dist)
     out = rt.Outputs(n_beams, rt.WANT_RANGES | rt.WANT_INTENSITIES, alloc=ctx.pinned_empty)
     max_per_finder, fid_cap = args.c4_max_fiducials, max(n_mine * args.c4_max_fiducials // 2, 1 << 16)
     fid_out = np.zeros(fid_cap, rt.FIDUCIAL_DTYPE)
     fid_cnt = np.zeros(n_mine, np.uint32)
     split = {"remap_ms": 0.0, "delta_exchange_ms": 0.0, "rangers_submit_ms": 0.0, "target_exchange_ms": 0.0, "fiducials_submit_ms": 0.0, "sync_ms": 0.0}
-    state = {"targets": None}
 
     def tick(tk):
         t0 = time.perf_counter()
@@ -279,13 +279,12 @@ def run_c4(env, args):
         t2 = time.perf_counter()
         ctx.rangers_submit(sensors, tk["rposes"], out)
         t3 = time.perf_counter()
-        targets = tex.step(tk["targets"]) if tex is not None else tk["targets"]
+        dev_targets, n_targets = tex.step_device(tk["targets"], ctx)
         t4 = time.perf_counter()
-        ctx.fiducials_submit_packed(targets, tk["finders"], max_per_finder, fid_cap, into=(fid_out, fid_cnt))
+        ctx.fiducials_submit_device_targets(dev_targets, n_targets, tk["finders"], max_per_finder, fid_cap, into=(fid_out, fid_cnt))
         t5 = time.perf_counter()
         ctx.sync()
         t6 = time.perf_counter()
-        state["targets"] = targets
         for k, v in zip(split, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t6 - t5)):
             split[k] += 1e3 * v
 
@@ -331,7 +330,10 @@ def run_c4(env, args):
     ranges_timed = out.ranges.copy()
 
     # ---- parity of the last tick, per rank, against the T1 oracle (after the timed regions)
-    parity = c4_parity(env, ctx, w, poses, T, lo, hi, sensors, ranges_timed, fid_out, fid_cnt, max_per_finder, state["targets"], last, rt, worldgen)
+    # the gathered target array as every rank's finders saw it (padding records included), rebuilt on the host for the checker
+    all_t, _ = worldgen.fiducial_records(w, poses[T], w.robot_ids, layer=(T + 1) % 2)
+    gathered_targets = tex.host_view([all_t[a:b] for a, b in (multi.shard_bounds(n_total, r, N) for r in range(N))])
+    parity = c4_parity(env, ctx, w, poses, T, lo, hi, sensors, ranges_timed, fid_out, fid_cnt, max_per_finder, gathered_targets, last, rt, worldgen)
     k1_ms_avg = kms["deltas_ms"] / steps
     rec = {
         "workload": "C4 synthetic: config-3 map (%d rectangles + walls, %dx%d cells), %d robots in total with 0.1 m bodies in the grid, each 16 one-beam "
@@ -384,7 +386,9 @@ def c4_parity(env, ctx, w, poses, T, lo, hi, sensors, ranges_timed, fid_out, fid
     L.t1_fiducial_update.restype = ctypes.c_uint32
     L.t1_fiducial_update.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
     at = np.concatenate([[0], np.cumsum(np.minimum(fid_cnt, max_per_finder).astype(np.int64))])
-    targets = np.ascontiguousarray(targets)
+    valid = targets["model"] != 0xffffffff                # the oracle gets the records without the slots' padding ...
+    index_of = np.cumsum(valid) - 1                        # ... so the device's target indices are mapped onto that array
+    targets = np.ascontiguousarray(targets[valid])
     fsample = np.arange(0, n_mine, max(1, n_mine // 250))
     fid_bad = fid_checked = 0
     fid_err = 0.0
@@ -394,7 +398,7 @@ def c4_parity(env, ctx, w, poses, T, lo, hi, sensors, ranges_timed, fid_out, fid
         n = int(L.t1_fiducial_update(t1.h, len(targets), targets.ctypes.data, f1.ctypes.data, max_per_finder, ref.ctypes.data))
         got = fid_out[int(at[i]):int(at[i + 1])]
         fid_checked += n
-        if n != int(fid_cnt[i]) or not np.array_equal(got["target"], ref[:n]["target"]) or not np.array_equal(got["id"], ref[:n]["id"]):
+        if n != int(fid_cnt[i]) or not np.array_equal(index_of[got["target"]], ref[:n]["target"]) or not np.array_equal(got["id"], ref[:n]["id"]):
             fid_bad += 1
         elif n:
             fid_err = max(fid_err, float(np.max(np.abs(got["range"] - ref[:n]["range"]))), float(np.max(np.abs(got["bearing"] - ref[:n]["bearing"]))))

@@ -277,6 +277,15 @@ int stg_rt_fiducials_submit_packed(stg_rt_ctx *ctx, uint32_t n_targets, const st
                                    uint32_t n_finders, const stg_rt_fid_finder *finders, uint32_t max_per_finder,
                                    uint64_t out_capacity, stg_rt_fiducial *out, uint32_t *out_count);
 
+/* stg_rt_fiducials_submit_packed with the target records already in DEVICE memory - the output of the ranks' all-gather
+   of their own robots' stg_rt_fid_target records (World::models_with_fiducials is world-wide, world.cc:623-629), which
+   then never visits the host. Records whose model id is not below max_models are skipped: ranks pad their slots of the
+   gathered array with them (model = 0xffffffff). The array must be complete in the order of the context's stream
+   (stg_rt_stream_wait). Not available with STG_RT_CFG_HOST_EXACT_FIDUCIALS. */
+int stg_rt_fiducials_submit_device_targets(stg_rt_ctx *ctx, uint32_t n_targets, const void *dev_targets, uint32_t n_finders,
+                                           const stg_rt_fid_finder *finders, uint32_t max_per_finder, uint64_t out_capacity,
+                                           stg_rt_fiducial *out, uint32_t *out_count);
+
 /* ---- whole ranger models ---------------------------------------------------------------------- */
 
 /* One ModelRanger::Sensor as the world file describes it (Sensor::Load, model_ranger.cc:129-156): pose

@@ -2428,7 +2428,7 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_r
 
 static int fiducials_submit_impl(stg_rt_ctx *c, uint32_t n_targets, const stg_rt_fid_target *targets, uint32_t n_finders,
                                  const stg_rt_fid_finder *finders, uint32_t max_per_finder, stg_rt_fiducial *out, uint32_t *out_count,
-                                 uint64_t packed_capacity);
+                                 uint64_t packed_capacity, const void *dev_targets = nullptr);
 
 int stg_rt_fiducials_submit(stg_rt_ctx *c, uint32_t n_targets, const stg_rt_fid_target *targets, uint32_t n_finders,
                             const stg_rt_fid_finder *finders, uint32_t max_per_finder, stg_rt_fiducial *out, uint32_t *out_count)
@@ -2445,13 +2445,22 @@ int stg_rt_fiducials_submit_packed(stg_rt_ctx *c, uint32_t n_targets, const stg_
   return fiducials_submit_impl(c, n_targets, targets, n_finders, finders, max_per_finder, out, out_count, out_capacity);
 }
 
+int stg_rt_fiducials_submit_device_targets(stg_rt_ctx *c, uint32_t n_targets, const void *dev_targets, uint32_t n_finders,
+                                           const stg_rt_fid_finder *finders, uint32_t max_per_finder, uint64_t out_capacity, stg_rt_fiducial *out,
+                                           uint32_t *out_count)
+{
+  if (!out_capacity || (n_targets && !dev_targets))
+    return STG_RT_EINVAL;
+  return fiducials_submit_impl(c, n_targets, nullptr, n_finders, finders, max_per_finder, out, out_count, out_capacity, dev_targets);
+}
+
 static int fiducials_submit_impl(stg_rt_ctx *c, uint32_t n_targets, const stg_rt_fid_target *targets, uint32_t n_finders,
                                  const stg_rt_fid_finder *finders, uint32_t max_per_finder, stg_rt_fiducial *out, uint32_t *out_count,
-                                 uint64_t packed_capacity)
+                                 uint64_t packed_capacity, const void *dev_targets)
 {
   static_assert(sizeof(stg_rt_fid_target) == sizeof(FidTargetRec) && sizeof(stg_rt_fid_finder) == sizeof(FidFinderRec) &&
                     sizeof(stg_rt_fiducial) == sizeof(FiducialRec), "fiducial record layouts");
-  if (!c || (n_targets && !targets) || (n_finders && (!finders || !out || !out_count)) || !max_per_finder)
+  if (!c || (n_targets && !targets && !dev_targets) || (n_finders && (!finders || !out || !out_count)) || !max_per_finder)
     return STG_RT_EINVAL;
   std::lock_guard<std::mutex> lk(c->mu);
   if (!n_finders)
@@ -2459,13 +2468,16 @@ static int fiducials_submit_impl(stg_rt_ctx *c, uint32_t n_targets, const stg_rt
   for (uint32_t i = 0; i < n_finders; i++)
     if (finders[i].finder >= c->cfg.max_models || !c->model_known[finders[i].finder] || finders[i].layer > 1)
       return fail(c, STG_RT_EINVAL, "fiducial finder %u: unknown model %u or bad layer", i, finders[i].finder);
-  for (uint32_t i = 0; i < n_targets; i++)
+  for (uint32_t i = 0; i < n_targets && targets; i++)
     if (targets[i].model >= c->cfg.max_models || !c->model_known[targets[i].model])
       return fail(c, STG_RT_EINVAL, "fiducial target %u: unknown model %u", i, targets[i].model);
+  if (dev_targets && (c->cfg.flags & STG_RT_CFG_HOST_EXACT_FIDUCIALS))
+    return fail(c, STG_RT_ESTATE, "fiducials_submit_device_targets: STG_RT_CFG_HOST_EXACT_FIDUCIALS needs the targets on the host");
   int rc = flush_locked(c); // issue order: everything submitted before is on the stream first
   if (rc || (rc = deliver_post_locked(c)))
     return rc;
-  const size_t b_t = (size_t)n_targets * sizeof(FidTargetRec), b_f = (size_t)n_finders * sizeof(FidFinderRec);
+  // targets already on the device (the output of the ranks' all-gather) are read where they are; only the finders go up
+  const size_t b_t = dev_targets ? 0 : (size_t)n_targets * sizeof(FidTargetRec), b_f = (size_t)n_finders * sizeof(FidFinderRec);
   const size_t b_fan = (size_t)n_finders * sizeof(FanRec), b_in = b_t + b_f + b_fan;
   const size_t b_out = (size_t)n_finders * max_per_finder * sizeof(FiducialRec), b_cnt = (size_t)n_finders * 4;
   if ((rc = pin_reserve(c, c->h_fid_in, b_in)) || (rc = dev_reserve(c, c->d_fid_in, b_in)) ||
@@ -2498,7 +2510,7 @@ static int fiducials_submit_impl(stg_rt_ctx *c, uint32_t n_targets, const stg_rt
   v.n_targets = n_targets;
   v.n_finders = n_finders;
   v.max_per_finder = max_per_finder;
-  v.targets = (const FidTargetRec *)c->d_fid_in.p;
+  v.targets = dev_targets ? (const FidTargetRec *)dev_targets : (const FidTargetRec *)c->d_fid_in.p;
   v.finders = (const FidFinderRec *)((char *)c->d_fid_in.p + b_t);
   v.fans = (const FanRec *)((char *)c->d_fid_in.p + b_t + b_f);
   v.out = (FiducialRec *)c->d_fid_out.p;
@@ -2510,8 +2522,14 @@ static int fiducials_submit_impl(stg_rt_ctx *c, uint32_t n_targets, const stg_rt
   const char *force = getenv("STG_RT_FID_GRID");
   const bool use_grid = force ? atoi(force) != 0 : (uint64_t)n_targets * n_finders > (4u << 20);
   if (use_grid && n_targets) {
-    double x0 = targets[0].x, x1 = x0, y0 = targets[0].y, y1 = y0, cell = 0;
-    for (uint32_t i = 1; i < n_targets; i++) {
+    // the bins cover the targets' bounding box - or, when the targets are only on the device, the grid's extent
+    // (targets outside it fall into the border bins, which the finders' windows reach like any other)
+    double x0 = c->cell_x0 / c->cfg.ppm, x1 = (c->cell_x1 + 1) / c->cfg.ppm, y0 = c->cell_y0 / c->cfg.ppm, y1 = (c->cell_y1 + 1) / c->cfg.ppm, cell = 0;
+    if (targets) {
+      x0 = x1 = targets[0].x;
+      y0 = y1 = targets[0].y;
+    }
+    for (uint32_t i = 1; i < n_targets && targets; i++) {
       x0 = std::min(x0, targets[i].x);
       x1 = std::max(x1, targets[i].x);
       y0 = std::min(y0, targets[i].y);

@@ -28,6 +28,8 @@ __device__ __forceinline__ double normalize_angle(double a)
 __device__ __forceinline__ bool fid_cull(const GridView &g, const FidFinderRec &fd, uint32_t finder_root, const FidTargetRec &him, double &range,
                                          double &dtheta)
 {
+  if (him.model >= g.n_models) // a padding record of a rank's slot in the gathered target array, or an id nobody published
+    return false;
   if (him.model == fd.finder || him.x < fd.x - fd.max_range_anon || him.x > fd.x + fd.max_range_anon ||
       him.y < fd.y - fd.max_range_anon || him.y > fd.y + fd.max_range_anon)
     return false;

@@ -84,9 +84,47 @@ class TargetExchange:
         self.cap = int(max_per_rank)
         self.mine = torch.zeros(self.cap * self.dtype.itemsize, dtype=torch.uint8, device=device)
         self.all = torch.zeros(world_size * self.cap * self.dtype.itemsize, dtype=torch.uint8, device=device)
+        # page-locked staging for this rank's own records; a slot's unused tail is padding records (model id 0xffffffff)
+        self.stage = torch.zeros(self.cap * self.dtype.itemsize, dtype=torch.uint8)
+        if device != "cpu":
+            self.stage = self.stage.pin_memory()
+        pad = np.zeros(self.cap, self.dtype)
+        pad["model"] = 0xffffffff
+        self.pad = pad
         self.count = torch.zeros(1, dtype=torch.int64, device=device)
         self.counts = torch.zeros(world_size, dtype=torch.int64, device=device)
         self.bytes_sent = 0
+
+    def step_device(self, my_targets, ctx=None):
+        """my_targets: this rank's records -> (device pointer, n_records) of the world's, rank after rank, each rank's slot
+        padded to `max_per_rank` with records the finders skip: nothing but this rank's own share crosses PCIe, and nothing
+        comes back. For stg_rt_fiducials_submit_device_targets; ctx (if given) is made to wait for the collective."""
+        import torch
+        my_targets = np.ascontiguousarray(my_targets, self.dtype)
+        n = len(my_targets)
+        if n > self.cap:
+            raise ValueError("%d target records exceed the exchange slot of %d" % (n, self.cap))
+        host = self.stage.numpy().view(self.dtype)
+        host[:n] = my_targets
+        host[n:] = self.pad[n:]
+        self.mine.copy_(self.stage, non_blocking=True)
+        self.bytes_sent += n * self.dtype.itemsize
+        if self.world_size > 1:
+            self.dist.all_gather_into_tensor(self.all, self.mine)
+        else:
+            self.all.copy_(self.mine)
+        if ctx is not None and self.all.device.type == "cuda":
+            ctx.stream_wait(torch.cuda.current_stream(self.all.device).cuda_stream)
+        return self.all.data_ptr(), self.world_size * self.cap
+
+    def host_view(self, my_targets_by_rank):
+        """the array step_device builds, on the host, from every rank's records (tests / checkers)"""
+        parts = []
+        for t in my_targets_by_rank:
+            slot = self.pad.copy()
+            slot[:len(t)] = np.ascontiguousarray(t, self.dtype)
+            parts.append(slot)
+        return np.concatenate(parts)
 
     def step(self, my_targets):
         """my_targets: this rank's records (numpy, record_dtype) -> every rank's, concatenated in rank order"""

@@ -99,6 +99,7 @@ def lib():
         "stg_rt_fans_submit": (ctypes.c_int, [vp, u32, vp, vp, vp, ctypes.POINTER(FanOut)]),
         "stg_rt_fiducials_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
         "stg_rt_fiducials_submit_packed": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, u64, vp, vp]),
+        "stg_rt_fiducials_submit_device_targets": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, u64, vp, vp]),
         "stg_rt_blobs_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, u32, vp, vp]),
         "stg_rt_rangers_submit": (ctypes.c_int, [vp, u32, vp, u32, vp, ctypes.POINTER(FanOut)]),
         "stg_rt_collisions_test": (ctypes.c_int, [vp, ctypes.c_int, u32, vp, vp, u32, vp]),
@@ -145,7 +146,7 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "stg_rt_abi_version stg_rt_create stg_rt_destroy stg_rt_last_error stg_rt_model_upsert stg_rt_block_map "
-    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_block_define stg_rt_models_pose_update stg_rt_debug_block_outline stg_rt_fiducials_submit stg_rt_fiducials_submit_packed stg_rt_rangers_submit stg_rt_collisions_test stg_rt_touching_models stg_rt_models_move stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
+    "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_block_define stg_rt_models_pose_update stg_rt_debug_block_outline stg_rt_fiducials_submit stg_rt_fiducials_submit_packed stg_rt_fiducials_submit_device_targets stg_rt_rangers_submit stg_rt_collisions_test stg_rt_touching_models stg_rt_models_move stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
     "stg_rt_delta_apply_gathered stg_rt_stream_signal stg_rt_stream_wait stg_rt_ranger_rand_advance stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_kernel_times_ex stg_rt_debug_link_bandwidth stg_rt_debug_trig stg_rt_debug_headings stg_rt_debug_region_owners stg_rt_grid_hash").split()
@@ -353,6 +354,15 @@ class Context:
         self._keep.append((out, cnt))
         self._check(self._L.stg_rt_fiducials_submit_packed(self._h, len(targets), _ptr(targets), len(finders), _ptr(finders),
                                                            max_per_finder, capacity, _ptr(out), _ptr(cnt)))
+        return out, cnt
+
+    def fiducials_submit_device_targets(self, dev_ptr, n_targets, finders, max_per_finder, capacity, into=None):
+        """fiducials_submit_packed with the target records already on the device (the all-gathered array)"""
+        finders = np.ascontiguousarray(finders, FID_FINDER_DTYPE)
+        out, cnt = into if into is not None else (np.zeros(capacity, FIDUCIAL_DTYPE), np.zeros(len(finders), np.uint32))
+        self._keep.append((out, cnt))
+        self._check(self._L.stg_rt_fiducials_submit_device_targets(self._h, n_targets, dev_ptr, len(finders), _ptr(finders), max_per_finder,
+                                                                   capacity, _ptr(out), _ptr(cnt)))
         return out, cnt
 
     def blobs_submit(self, finders, colors_rgb=None, max_per_finder=None):

@@ -107,6 +107,18 @@ def _target_worker(rank, world, port, q):
         mine["ret"] = tick + 1
         mine["pose"][:, 0] = np.arange(lo, hi) + 0.25 * tick
         got.append(ex.step(mine))
+        # the device-resident form of the same exchange: slots padded with records the finders skip, nothing returned to the host
+        ptr, n = ex.step_device(mine)
+        raw = np.frombuffer((ctypes.c_uint8 * (n * REC.itemsize)).from_address(ptr), REC).copy()
+        shards = []
+        for r in range(world):
+            a, b = multi.shard_bounds(11, r, world)
+            t = np.zeros(b - a, REC)
+            t["model"], t["ret"] = 100 + np.arange(a, b), tick + 1
+            t["pose"][:, 0] = np.arange(a, b) + 0.25 * tick
+            shards.append(t)
+        assert n == world * 6 and raw.tobytes() == ex.host_view(shards).tobytes()
+        assert np.array_equal(raw["model"][raw["model"] != 0xffffffff], 100 + np.arange(11)) and int((raw["model"] == 0xffffffff).sum()) == 1
     q.put((rank, [g.tobytes() for g in got], ex.bytes_sent))
     dist.barrier()
     dist.destroy_process_group()
@@ -135,7 +147,7 @@ def test_target_exchange_over_gloo_two_ranks_uneven_shards():
         assert a.tobytes() == b.tobytes() and len(a) == 11
         assert np.array_equal(a["model"], 100 + np.arange(11)) and np.all(a["ret"] == tick + 1)
         assert np.array_equal(a["pose"][:, 0], np.arange(11) + 0.25 * tick)
-    assert got[0][1] == 3 * 6 * 72 and got[1][1] == 3 * 5 * 72
+    assert got[0][1] == 2 * 3 * 6 * 72 and got[1][1] == 2 * 3 * 5 * 72
     with pytest.raises(ValueError):
         multi.TargetExchange(0, 1, 2, REC, device="cpu").step(np.zeros(3, REC))
     one = multi.TargetExchange(0, 1, 4, REC, device="cpu").step(np.zeros(3, REC))  # a single rank gets its own back
