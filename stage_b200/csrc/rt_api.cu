@@ -2,8 +2,10 @@
 // delta coalescing and blob building, fan batching, pinned staging, stream plumbing.
 // The compute is in rt_kernels.cu; there is no CPU implementation of any of it here.
 #include <cuda_runtime.h>
+#include <emmintrin.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -98,6 +100,7 @@ public:
     {
       std::lock_guard<std::mutex> lk(mu_);
       stop_ = true;
+      stop_flag_.store(true);
     }
     cv_.notify_all();
     for (std::thread &t : threads_)
@@ -119,15 +122,67 @@ public:
       next_ = 1; // part 0 is the caller's
       pending_ = parts - 1;
       generation_++;
+      gen_.store(generation_, std::memory_order_release);
     }
     cv_.notify_all();
     fn(0, n / parts);
+    for (int spin = 0; spin < 20000 && pend_peek() != 0; spin++) // the others are about as long as this part was
+      _mm_pause();
     std::unique_lock<std::mutex> lk(mu_);
     done_.wait(lk, [this] { return pending_ == 0; });
     fn_ = nullptr;
   }
 
+  // The same without waiting: the parts are taken by the workers as they come free; finish() takes what is left itself
+  // and returns when every part is done. One job at a time.
+  void begin(size_t parts, std::function<void(size_t)> part_fn)
+  {
+    start();
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      async_fn_ = std::move(part_fn);
+      wrapped_ = [this](size_t lo, size_t hi) {
+        for (size_t p = lo; p < hi; p++)
+          async_fn_(p);
+      };
+      fn_ = &wrapped_;
+      n_ = parts;
+      parts_ = parts;
+      next_ = 0;
+      pending_ = parts;
+      generation_++;
+      gen_.store(generation_, std::memory_order_release);
+      async_open_ = true;
+    }
+    cv_.notify_all();
+  }
+  void finish()
+  {
+    std::unique_lock<std::mutex> lk(mu_);
+    if (!async_open_)
+      return;
+    while (next_ < parts_) {
+      const size_t p = next_++;
+      lk.unlock();
+      async_fn_(p);
+      lk.lock();
+      if (--pending_ == 0)
+        done_.notify_all();
+    }
+    done_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+    async_open_ = false;
+  }
+  bool busy()
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    return async_open_;
+  }
+
 private:
+  std::function<void(size_t)> async_fn_;
+  std::function<void(size_t, size_t)> wrapped_;
+  bool async_open_ = false;
   void start()
   {
     if (started_)
@@ -142,9 +197,15 @@ private:
   void work()
   {
     uint64_t seen = 0;
-    std::unique_lock<std::mutex> lk(mu_);
     for (;;) {
-      cv_.wait(lk, [&] { return stop_ || (generation_ != seen && next_ < parts_); });
+      // Ticks follow each other within a millisecond: a worker that has just finished polls for the next job for a
+      // while before it goes to sleep (waking a sleeping thread costs more than the job it is woken for).
+      const std::chrono::steady_clock::time_point until = std::chrono::steady_clock::now() + std::chrono::milliseconds(2);
+      while (gen_.load(std::memory_order_acquire) == seen && !stop_flag_.load(std::memory_order_relaxed) &&
+             std::chrono::steady_clock::now() < until)
+        _mm_pause();
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [&] { return stop_ || (generation_ != seen && next_ < parts_) || generation_ != seen; });
       if (stop_)
         return;
       while (fn_ && next_ < parts_) {
@@ -160,6 +221,13 @@ private:
       seen = generation_;
     }
   }
+  size_t pend_peek()
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    return pending_;
+  }
+  std::atomic<uint64_t> gen_{ 0 };
+  std::atomic<bool> stop_flag_{ false };
   std::mutex mu_;
   std::condition_variable cv_, done_;
   std::vector<std::thread> threads_;
@@ -278,7 +346,7 @@ struct stg_rt_ctx {
   PinBuf h_fid_in, h_fid_out, h_fid_count, h_blob_in, h_blob_out, h_blob_count;
   FanArrays bd; // the blobfinders' scan-line fans
   // STG_RT_HOST_PROF=1: host microseconds per section of the flush path, printed by stg_rt_destroy
-  double prof_us[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+  double prof_us[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
   uint64_t prof_flushes = 0;
   bool prof_on = getenv("STG_RT_HOST_PROF") != nullptr;
   struct CollisionJob {
@@ -308,6 +376,12 @@ struct stg_rt_ctx {
   bool palette_ok = true;
   bool f_compact_intens = false; // the batch in flight delivers intensities as palette indices
   PinBuf h_intens_idx;
+  // streamed delivery: the march tells the host, warp by warp, which results have landed (FanBatchView::done_flags), and
+  // the pool's threads expand intensities of finished stretches while the kernel is still running
+  PinBuf h_done_flags;
+  uint32_t done_seq = 0;
+  bool f_streaming = false;
+  std::atomic<bool> stream_gave_up{ false };
   HostPool pool;
 
   std::map<char *, size_t> host_allocs; // stg_rt_host_alloc regions
@@ -967,18 +1041,36 @@ int deliver_locked(stg_rt_ctx *c)
     return prc;
   if (c->f_subs.empty())
     return 0;
+  const double t_wait0 = prof_now(c);
   CU(c, cudaStreamSynchronize(c->stream));
+  const double t_wait1 = prof_now(c);
+  if (c->prof_on)
+    c->prof_us[8] += t_wait1 - t_wait0;
   for (const Submit &s : c->f_subs) {
     // the kernel wrote ranges / intensities / hit models of a solo pinned submit in place
     deliver_array(c, s.out.ranges, c->h_ranges, s.first_beam, s.n_beams, 8,
                   c->f_copied ? is_host_alloc(c, s.out.ranges, s.n_beams * 8) : c->f_direct[0]);
-    if (c->f_compact_intens && s.out.intensities) { // palette indices -> the caller's doubles (model_ranger.cc:250)
+    if (c->f_streaming && s.out.intensities) { // expanded while the kernel ran; whatever is left is finished here
+      c->pool.finish();
+      if (c->stream_gave_up.load()) { // (only after a failed launch) do it the plain way
+        const uint8_t *idx = (const uint8_t *)c->h_intens_idx.p + s.first_beam;
+        for (uint64_t i = 0; i < s.n_beams; i++)
+          s.out.intensities[i] = c->palette[idx[i]];
+      }
+    } else if (c->f_compact_intens && s.out.intensities) { // palette indices -> the caller's doubles (model_ranger.cc:250)
       const uint8_t *idx = (const uint8_t *)c->h_intens_idx.p + s.first_beam;
       double *dst = s.out.intensities;
       const double *pal = c->palette.data();
       c->pool.parallel_for((size_t)s.n_beams, 1 << 16, [idx, dst, pal](size_t lo, size_t hi) {
-        for (size_t i = lo; i < hi; i++)
+        // streaming stores: the lines are written whole and not read again soon, so they need not be fetched first
+        size_t i = lo;
+        for (; i < hi && ((uintptr_t)(dst + i) & 15u); i++)
           dst[i] = pal[idx[i]];
+        for (; i + 2 <= hi; i += 2)
+          _mm_stream_pd(dst + i, _mm_set_pd(pal[idx[i + 1]], pal[idx[i]]));
+        for (; i < hi; i++)
+          dst[i] = pal[idx[i]];
+        _mm_sfence();
       });
     } else {
       deliver_array(c, s.out.intensities, c->h_intens, s.first_beam, s.n_beams, 8,
@@ -991,6 +1083,8 @@ int deliver_locked(stg_rt_ctx *c)
     deliver_array(c, s.out.hit_cell, c->h_hit_cell, s.first_beam, s.n_beams, 8, is_host_alloc(c, s.out.hit_cell, s.n_beams * 8));
     deliver_array(c, s.out.steps, c->h_steps, s.first_beam, s.n_beams, 8, is_host_alloc(c, s.out.steps, s.n_beams * 8));
   }
+  if (c->prof_on)
+    c->prof_us[9] += prof_now(c) - t_wait1;
   c->f_subs.clear();
   c->f_beams = 0;
   return 0;
@@ -1134,6 +1228,27 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
     CU(c, cudaStreamWaitEvent(c->stream, c->chunk_ev[1], 0));
   }
   const double t_prof2 = prof_now(c);
+  // A large batch of one submit that wants intensities as doubles: stream them (see h_done_flags)
+  const char *stream_env = getenv("STG_RT_STREAM");
+  const bool no_stream = stream_env && !strcmp(stream_env, "0");
+  c->f_streaming = false;
+  if (c->f_compact_intens && solo && solo->out.intensities && !refill && !no_stream && beams >= (1u << 17) && !c->pool.busy()) {
+    const size_t n_flags = (size_t)((beams + 31) / 32);
+    const bool fresh = n_flags * 4 > c->h_done_flags.cap;
+    if ((rc = pin_reserve(c, c->h_done_flags, n_flags * 4)))
+      return rc;
+    if (fresh) {
+      memset(c->h_done_flags.p, 0, c->h_done_flags.cap);
+      c->done_seq = 0;
+    }
+    if (++c->done_seq == 0) { // wrapped: start over with clean flags
+      memset(c->h_done_flags.p, 0, c->h_done_flags.cap);
+      c->done_seq = 1;
+    }
+    v.done_flags = (uint32_t *)c->h_done_flags.p;
+    v.done_seq = c->done_seq;
+    c->f_streaming = true;
+  }
   CU(c, cudaEventRecord(c->t_ev[2][0], c->stream));
   if (refill)
     launch_ray_march_refill(c->g, v, v.trig_in ? v.trig_in : (const double *)c->d.trigw.p, (uint32_t *)c->d_work_counter.p, c->stream);
@@ -1142,6 +1257,39 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   CU(c, cudaEventRecord(c->t_ev[2][1], c->stream));
   c->t_rec[1] = c->t_rec[2] = true;
   CU(c, cudaGetLastError());
+  if (c->f_streaming) {
+    // stretches of 8192 beams (256 warps): a stretch is expanded as soon as all its warps have reported
+    constexpr size_t kStretch = 8192;
+    const uint8_t *idx = (const uint8_t *)c->h_intens_idx.p;
+    double *dst = solo->out.intensities;
+    const double *pal = c->palette.data();
+    const volatile uint32_t *flags = (const volatile uint32_t *)c->h_done_flags.p;
+    const uint32_t seq = c->done_seq;
+    const size_t n = (size_t)beams;
+    std::atomic<bool> *gave_up = &c->stream_gave_up;
+    gave_up->store(false);
+    c->pool.begin((n + kStretch - 1) / kStretch, [idx, dst, pal, flags, seq, n, gave_up](size_t part) {
+      const size_t lo = part * kStretch, hi = std::min(n, lo + kStretch);
+      const std::chrono::steady_clock::time_point until = std::chrono::steady_clock::now() + std::chrono::seconds(2);
+      for (size_t w = lo / 32; w < (hi + 31) / 32; w++)
+        while (flags[w] != seq) {
+          if (gave_up->load(std::memory_order_relaxed) || std::chrono::steady_clock::now() > until) {
+            gave_up->store(true); // the kernel did not finish (an error the sync will report): nothing to expand
+            return;
+          }
+          _mm_pause();
+        }
+      std::atomic_thread_fence(std::memory_order_acquire);
+      size_t i = lo;
+      for (; i < hi && ((uintptr_t)(dst + i) & 15u); i++)
+        dst[i] = pal[idx[i]];
+      for (; i + 2 <= hi; i += 2)
+        _mm_stream_pd(dst + i, _mm_set_pd(pal[idx[i + 1]], pal[idx[i]]));
+      for (; i < hi; i++)
+        dst[i] = pal[idx[i]];
+      _mm_sfence();
+    });
+  }
   c->stats.launches_march += 1;
   c->stats.launches_post += 1;
   c->stats.beams += beams;
@@ -1330,9 +1478,10 @@ int stg_rt_destroy(stg_rt_ctx *c)
   cudaStreamSynchronize(c->stream);
   if (c->prof_on)
     fprintf(stderr, "stg_rt host profile, total us (%llu fan launches): stage fans + headings %.0f | sort units %.0f | size deltas %.0f | "
-                    "write deltas %.0f | upload + K1 launches %.0f | march launch %.0f | blocks_remap calls %.0f | fiducial unpack %.0f\n",
+                    "write deltas %.0f | upload + K1 launches %.0f | march launch %.0f | blocks_remap calls %.0f | fiducial unpack %.0f | "
+                    "waiting for the GPU in sync %.0f | delivering fan results (copies, intensity expansion) %.0f\n",
             (unsigned long long)c->prof_flushes, c->prof_us[0], c->prof_us[1], c->prof_us[2], c->prof_us[3], c->prof_us[4],
-            c->prof_us[5], c->prof_us[6], c->prof_us[7]);
+            c->prof_us[5], c->prof_us[6], c->prof_us[7], c->prof_us[8], c->prof_us[9]);
   GridView &g = c->g;
   void *dev[] = { g.reg_count, g.reg_owner, g.occ[0], g.slots[0], g.slots[1], g.blk_rec[0], g.blk_rec[1], c->spare_slots,
                   g.mdl_root, g.mdl_ranger_return, g.mdl_flags, g.mdl_pal, c->d_blob.p };

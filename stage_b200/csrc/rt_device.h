@@ -236,6 +236,11 @@ struct FanBatchView {
   int32_t *hit_model, *hit_cell;
   uint32_t *steps;
   uint8_t *intens_idx; // intensities as one palette index per beam (GridView::mdl_pal): 1 byte over PCIe instead of 8
+  // page-locked host words, one per 32 beams of the batch: a warp of the march writes `done_seq` there once its results have
+  // been stored (behind a system-wide fence), so that host threads can start on a stretch of beams while the kernel is still
+  // marching the rest (null: nobody is listening)
+  uint32_t *done_flags;
+  uint32_t done_seq;
 };
 
 // ---- whole ranger models (same layouts as stg_rt_ranger_* in include/stg_rt.h) ------------------

@@ -524,18 +524,22 @@ __global__ void __launch_bounds__(256) k1_pose_phase0(GridView g, GeomView gv, c
     const int nr = min(n_ranks - r0, kMaxRanksFlat);
     const unsigned char *part = blobs + (size_t)r0 * slot_bytes;
     k1_pose_prefix(g, part, nr, slot_bytes, prefix);
-    for (uint32_t w = warp; w < prefix[nr]; w += n_warps) {
+    // two warps share a record: the even one derives the new outline and the block's record, the odd one takes the old
+    // outline out - two dependent chains side by side instead of one after the other (a pass over 1000 robots is all latency)
+    for (uint32_t ww = warp; ww < 2 * prefix[nr]; ww += n_warps) {
+      const uint32_t w = ww >> 1;
+      const bool second = (ww & 1u) != 0;
       const int rank = k1_rank_of(prefix, nr, w);
       const BlobView v = blob_view(part, rank, slot_bytes);
       const PoseUpd u = v.pose_upd[w - prefix[rank]];
       if (u.block >= gv.n_blocks || u.block >= g.n_blocks) {
-        if (lane == 0)
+        if (lane == 0 && !second)
           raise_error(g, kErrOutOfExtent);
         continue;
       }
       const BlockGeom bg = gv.geom[u.block];
       const uint32_t L = u.layer_flags & 1u;
-      if (!(u.layer_flags & kPoseNoInsert)) {
+      if (!second && !(u.layer_flags & kPoseNoInsert)) {
         // Model::LocalToPixels: ptpose = gpose + Pose(pt) (Pose::operator+, stage.hh:297-304: cos / sin of gpose.a from the
         // host C library's algorithm, rt_libm.cuh; no contraction), pixel = (int32)floor(coordinate * ppm)
         double cosa, sina;
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(256) k1_pose_phase0(GridView g, GeomView gv, c
           g.blk_rec[L][u.block].seq = (epoch << kSeqEpochShift) | ((unsigned long long)(v.hdr->rank & 0xff) << kSeqRankShift) | (u.seq_local & kSeqLocalMax);
         }
       }
-      if (u.layer_flags & kPoseRemoveOld) {
+      if (second && (u.layer_flags & kPoseRemoveOld)) {
         const OpRemove op = { g, u.block, L };
         outline_cells(g, gv.pix[L] + 2 * (size_t)bg.first_pt, bg.n_pts, lane, op);
       }
@@ -585,7 +589,11 @@ __global__ void __launch_bounds__(256) k1_pose_phase1(GridView g, GeomView gv, c
     const int nr = min(n_ranks - r0, kMaxRanksFlat);
     const unsigned char *part = blobs + (size_t)r0 * slot_bytes;
     k1_pose_prefix(g, part, nr, slot_bytes, prefix);
-    for (uint32_t w = warp; w < prefix[nr]; w += n_warps) {
+    // again two warps per record: the even one inserts the new outline, the odd one fixes the masks up over the old one and
+    // then - it is the only reader of the old outline - puts the new one in its place
+    for (uint32_t ww = warp; ww < 2 * prefix[nr]; ww += n_warps) {
+      const uint32_t w = ww >> 1;
+      const bool second = (ww & 1u) != 0;
       const int rank = k1_rank_of(prefix, nr, w);
       const BlobView v = blob_view(part, rank, slot_bytes);
       const PoseUpd u = v.pose_upd[w - prefix[rank]];
@@ -594,15 +602,20 @@ __global__ void __launch_bounds__(256) k1_pose_phase1(GridView g, GeomView gv, c
       const BlockGeom bg = gv.geom[u.block];
       const uint32_t L = u.layer_flags & 1u;
       int32_t *pix = gv.pix[L] + 2 * (size_t)bg.first_pt;
+      const int32_t *fresh = gv.pix_new[L] + 2 * (size_t)bg.first_pt;
+      if (!second) {
+        if (!(u.layer_flags & kPoseNoInsert)) {
+          const OpInsert op = { g, u.block, L };
+          outline_cells(g, fresh, bg.n_pts, lane, op);
+        }
+        continue;
+      }
       if (u.layer_flags & kPoseRemoveOld) {
         const OpFixup op = { g, L };
         outline_cells(g, pix, bg.n_pts, lane, op);
       }
       if (!(u.layer_flags & kPoseNoInsert)) {
-        const int32_t *fresh = gv.pix_new[L] + 2 * (size_t)bg.first_pt;
-        const OpInsert op = { g, u.block, L };
-        outline_cells(g, fresh, bg.n_pts, lane, op);
-        __syncwarp(); // every lane is done with the old outline: the new one takes its place
+        __syncwarp(); // every lane is done with the old outline
         for (uint32_t i = lane; i < 2 * bg.n_pts; i += 32)
           pix[i] = fresh[i];
       }

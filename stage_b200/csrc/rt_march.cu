@@ -91,6 +91,14 @@ __global__ void __launch_bounds__(128, STG_MARCH_CTAS_PER_SM) k2_ray_march(GridV
     b.steps[2 * beam] = r.cell_visits;
     b.steps[2 * beam + 1] = r.region_probes;
   }
+  if (b.done_flags) { // tell the host this warp's 32 results have landed (the listener expands intensities meanwhile)
+    const unsigned active = __activemask();
+    __syncwarp(active);
+    if ((threadIdx.x & 31u) == (unsigned)(__ffs(active) - 1)) {
+      __threadfence_system();
+      *reinterpret_cast<volatile uint32_t *>(b.done_flags + ((beam - b.beam_begin) >> 5)) = b.done_seq;
+    }
+  }
 }
 
 // ---- the march with lane refill ---------------------------------------------------------------------------------

@@ -271,3 +271,33 @@ def test_refill_march_kernel_equals_the_plain_one(monkeypatch):
         assert np.array_equal(a.hit_model, b.hit_model) and np.array_equal(a.hit_cell, b.hit_cell)
         assert (a.hit_model >= 0).mean() > 0.5
     ctx.close()
+
+
+def test_streamed_intensities_equal_the_plain_delivery(monkeypatch):
+    """Large batches deliver intensities while the march is still running: warps report their finished beams through flags
+    in page-locked memory and host threads expand the palette bytes of finished stretches meanwhile. Same doubles as the
+    delivery after the sync, tick after tick (the flags carry a sequence number), into pinned and ordinary arrays."""
+    from stage_b200 import worldgen
+    w = worldgen.make_world(seed=14, n_rects=600, n_robots=220, half_extent_m=40.96)
+    x0, y0, nx, ny = w.sreg_extent()
+    ctx = rt.Context(w.ppm, x0, y0, nx, ny, max_models=w.n_models + 1, max_blocks=len(w.obstacles) + len(w.robots), max_cell_entries=1 << 20)
+    worldgen.load_into_context(ctx, w)
+    for k, mid in enumerate(w.robot_ids):   # a few distinct ranger_return values
+        ctx.model_upsert(int(mid), int(mid), 0.1 + 0.05 * (k % 9))
+    ctx.sync()
+    poses = w.robots
+    for tick in range(4):
+        poses = worldgen.step_robots(w, poses, tick, speed_m=0.3)
+        fans = worldgen.ranger_fans(w, layer=1, samples=1080, range_max=25.0, robots=poses)
+        res = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("STG_RT_STREAM", mode)
+            out = rt.Outputs(len(fans) * 1080, rt.WANT_RANGES | rt.WANT_INTENSITIES | rt.WANT_HIT_MODEL, alloc=ctx.pinned_empty if tick % 2 else None)
+            out.intensities[:] = -7.0
+            ctx.fans_submit(fans, out)
+            ctx.sync()
+            res[mode] = out
+        a, b = res["0"], res["1"]
+        assert np.array_equal(a.intensities, b.intensities) and np.array_equal(a.ranges.view(np.uint64), b.ranges.view(np.uint64))
+        assert np.array_equal(a.hit_model, b.hit_model) and (b.intensities >= 0).all() and len(np.unique(b.intensities)) >= 5
+    ctx.close()
