@@ -591,9 +591,15 @@ def run_ours(args):
             if c:
                 limiter["host_link_ceiling_gb_per_s_per_gpu"] = c
                 limiter["ceiling_source"] = "profiles/r02_link_ceiling.json (tools/link_ceiling.py, %d GPUs storing at once)" % n_gpus
-                limiter["what"] = ("the link to host memory: the march delivers at %.0f %% of what this host takes from %d GPU(s) at once"
-                                   % (100 * limiter["delivered_gb_per_s_per_gpu"] / c, n_gpus)) if limiter["delivered_gb_per_s_per_gpu"] > 0.7 * c \
-                    else "kernels and host calls (the link is not saturated)"
+                floor_ms = bytes_per_tick / (c * 1e9) * 1e3
+                limiter["link_floor_ms"] = floor_ms
+                hbm_ms = limiter["march_ms_results_in_hbm"]
+                if e2e_march_ms > 1.4 * hbm_ms:
+                    limiter["what"] = ("result delivery into host memory: the march takes %.2f ms storing its %.1f MB of results to the host against %.2f ms "
+                                       "into HBM; what this host takes from %d GPU(s) storing at once (%.1f GB/s each, measured) allows no less than %.2f ms"
+                                       % (e2e_march_ms, bytes_per_tick / 1e6, hbm_ms, n_gpus, c, floor_ms))
+                else:
+                    limiter["what"] = "kernels and host calls (delivery costs the march less than 40 % extra)"
         except Exception:
             pass
         march_avg_ms = float(np.mean(march_ms))

@@ -15,6 +15,7 @@
 // compile device code with -fmad=false and host code with -ffp-contract=off.
 // tests/test_libm_port.py checks the host build against libm on tens of millions of arguments, and
 // tests/test_gpu_trig.py checks the device build against libm on the GPU box.
+// Derived from glibc (LGPL-2.1-or-later): see NOTICE.md at the repository root.
 #pragma once
 #include <math.h>
 #include <stdint.h>
