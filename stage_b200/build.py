@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libstg_rt.so")
 SOURCES = ["rt_kernels.cu", "rt_march.cu", "rt_post.cu", "rt_api.cu"]
 EXTRA_DEPS = ["rt_trace.cuh"]
-HEADERS = ["rt_device.h", "rt_trace.cuh", "rt_libm.cuh", "rt_sincos_tab.h", os.path.join("..", "..", "include", "stg_rt.h")]
+HEADERS = ["rt_device.h", "rt_trace.cuh", "rt_libm.cuh", "rt_sincos_tab.h", "rt_walk.h", os.path.join("..", "..", "include", "stg_rt.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # the traversal's FP64 math must round like the reference's x86-64 build: no a*b+c contraction

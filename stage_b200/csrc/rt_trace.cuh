@@ -6,6 +6,7 @@
 
 #include "rt_device.h"
 #include "rt_libm.cuh"
+#include "rt_walk.h"
 
 namespace stg {
 namespace trace {
@@ -199,7 +200,7 @@ __device__ __forceinline__ int32_t walk_region(const GridView &g, const FanRec *
   }
 }
 
-enum : uint32_t { kYMajor = 1u, kRunNeg = 2u, kCrossNeg = 4u, kXNeg = 8u, kYNeg = 16u };
+enum : uint32_t { kYMajor = 1u, kRunNeg = 2u, kCrossNeg = 4u, kXNeg = 8u, kYNeg = 16u, kClosedForms = 64u };
 
 struct RayResult {
   double range;
@@ -236,7 +237,7 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
     E = ymajor ? -(ay - ax) - 1 : (ay - ax);
     const bool xneg = dx < 0, yneg = dy < 0;
     flags = (ymajor ? kYMajor : 0u) | ((ymajor ? yneg : xneg) ? kRunNeg : 0u) | ((ymajor ? xneg : yneg) ? kCrossNeg : 0u) |
-            (xneg ? kXNeg : 0u) | (yneg ? kYNeg : 0u);
+            (xneg ? kXNeg : 0u) | (yneg ? kYNeg : 0u) | (b_cross <= 2 * walk::kMaxMajorCells ? kClosedForms : 0u);
     // r_max = min(ceil(b_cross / b_run), 33): the longest possible run; 33 = "past the region edge"
     r_max = 33;
     if (b_run > 0 && (long long)b_run * 33 > b_cross)
@@ -329,42 +330,53 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
       const int32_t cp0 = (int32_t)((uint32_t)(ymajor ? cx0 : cy0) ^ cflip);
       const int32_t ap0 = (int32_t)((uint32_t)(ymajor ? cy0 : cx0) ^ aflip);
       int32_t cp = cp0, ap = ap0;
-      // the region's row masks (x-major rays) or column masks (y-major); mask number (cp ^ cflip) belongs to cp
-      uint32_t tile = occ_layer + region * kTileWords + (ymajor ? kRegionWidth : 0);
-      asm volatile("" : "+r"(tile)); // one register to keep, not five instructions to redo in every run
-      // no masks are read in a region that holds only the finder's own tree: nothing there can stop this ray
-      const int32_t cp_ahead = __ldg(g.reg_owner + region) != finder_tag ? kRegionWidth - 1 : 0; // masks are requested while cp < this
-      uint32_t word = 0;
-      if (cp_ahead)
-        word = __ldg(g.occ[0] + (tile | ((uint32_t)cp ^ cflip)));
-      word ^= (word ^ __brev(word)) & revmask;
-      // r = run steps before the next cross step: the smallest r >= 0 with E + r*b_run >= 0. E >= -b_cross
-      // always, so r <= r_max. Entering a region E is anywhere in that range (one estimate + fix-up);
-      // right after a cross step r is r_max or r_max - 1 (one compare, below).
-      int32_t r = 0;
-      if (E < 0) {
-        const int32_t t = -E;
-        r = r_max;
-        if (v1 >= t) { // 1 <= ceil(t / b_run) <= r_max - 1 <= 32 and b_run > 0
-          r = __float2int_rz((float)t * __frcp_rn((float)b_run));
-          while (r * b_run < t)
-            r++;
-          while (r > 0 && (r - 1) * b_run >= t)
-            r--;
-        }
-      }
-      // (n counts the cells the ray may still visit; a region holds at most 2 * 32 - 1 of them, so a ray with
-      // more than that left walks the region without looking at n, which is brought up to date afterwards)
-      WalkConst wc;
-      wc.b_run = b_run; wc.b_cross = b_cross; wc.rm1 = rm1; wc.v1 = v1; wc.cp_ahead = cp_ahead;
-      wc.revmask = revmask; wc.aflip = aflip; wc.cflip = cflip; wc.ymajor = ymajor;
-      int32_t mdl;
-      if (n >= 2 * kRegionWidth) {
-        mdl = walk_region<kSteps, false>(g, fan, layer1, region, wc, ap, cp, E, n, r, word, tile, cell_visits);
-        if (mdl < 0)
-          n -= (ap - ap0) + (cp - cp0); // one cell visited per step taken
+      int32_t mdl = -1;
+      const bool own = __ldg(g.reg_owner + region) == finder_tag;
+      if (own && n >= 2 * kRegionWidth && (flags & kClosedForms)) {
+        // A region that holds only the finder's own tree cannot stop this ray, and the ray does not end in it (a region
+        // holds at most 2 * 32 - 1 of its cells): where and how the cell-by-cell walk leaves is a closed form (rt_walk.h).
+        walk::region_exit(ap0, cp0, E, b_run, b_cross, ap, cp, E);
+        const int32_t steps = (ap - ap0) + (cp - cp0); // one cell visited per step taken
+        if (kSteps)
+          cell_visits += (uint32_t)steps;
+        n -= steps;
       } else {
-        mdl = walk_region<kSteps, true>(g, fan, layer1, region, wc, ap, cp, E, n, r, word, tile, cell_visits);
+        // the region's row masks (x-major rays) or column masks (y-major); mask number (cp ^ cflip) belongs to cp
+        uint32_t tile = occ_layer + region * kTileWords + (ymajor ? kRegionWidth : 0);
+        asm volatile("" : "+r"(tile)); // one register to keep, not five instructions to redo in every run
+        // no masks are read in a region that holds only the finder's own tree: nothing there can stop this ray
+        const int32_t cp_ahead = own ? 0 : kRegionWidth - 1; // masks are requested while cp < this
+        uint32_t word = 0;
+        if (cp_ahead)
+          word = __ldg(g.occ[0] + (tile | ((uint32_t)cp ^ cflip)));
+        word ^= (word ^ __brev(word)) & revmask;
+        // r = run steps before the next cross step: the smallest r >= 0 with E + r*b_run >= 0. E >= -b_cross
+        // always, so r <= r_max. Entering a region E is anywhere in that range (one estimate + fix-up);
+        // right after a cross step r is r_max or r_max - 1 (one compare, below).
+        int32_t r = 0;
+        if (E < 0) {
+          const int32_t t = -E;
+          r = r_max;
+          if (v1 >= t) { // 1 <= ceil(t / b_run) <= r_max - 1 <= 32 and b_run > 0
+            r = __float2int_rz((float)t * __frcp_rn((float)b_run));
+            while (r * b_run < t)
+              r++;
+            while (r > 0 && (r - 1) * b_run >= t)
+              r--;
+          }
+        }
+        // (n counts the cells the ray may still visit; a region holds at most 2 * 32 - 1 of them, so a ray with
+        // more than that left walks the region without looking at n, which is brought up to date afterwards)
+        WalkConst wc;
+        wc.b_run = b_run; wc.b_cross = b_cross; wc.rm1 = rm1; wc.v1 = v1; wc.cp_ahead = cp_ahead;
+        wc.revmask = revmask; wc.aflip = aflip; wc.cflip = cflip; wc.ymajor = ymajor;
+        if (n >= 2 * kRegionWidth) {
+          mdl = walk_region<kSteps, false>(g, fan, layer1, region, wc, ap, cp, E, n, r, word, tile, cell_visits);
+          if (mdl < 0)
+            n -= (ap - ap0) + (cp - cp0); // one cell visited per step taken
+        } else {
+          mdl = walk_region<kSteps, true>(g, fan, layer1, region, wc, ap, cp, E, n, r, word, tile, cell_visits);
+        }
       }
       if (mdl >= 0) {
         const uint32_t areal = (uint32_t)ap ^ aflip, creal = (uint32_t)cp ^ cflip;
