@@ -453,6 +453,13 @@ int stg_rt_debug_block_outline(stg_rt_ctx *ctx, uint32_t block_id, int layer, in
    model id + 1, or 0xffffffff for "more than one tree". Returns the record count (may exceed cap). */
 int64_t stg_rt_debug_region_owners(stg_rt_ctx *ctx, int64_t *records, int64_t cap);
 
+/* The occupancy tiles and their summary words (what the march reads instead of Cell::blocks, region.hh:47) against the
+   cell entries they stand for: out[0] = cells whose bit in a row or column mask differs from "the cell holds an entry",
+   out[1] = summary bits that differ from "that row / column mask is non-zero", out[2] = occupied cells seen (both
+   layers). No counterpart in the reference: accelerations that must never change a result; the tests expect zeros
+   after every kind of update. Synchronous. */
+int stg_rt_debug_occupancy_check(stg_rt_ctx *ctx, uint64_t out[3]);
+
 /* ---- multi-GPU: moved-block deltas ---------------------------------------------------------- */
 /* Robots are sharded over ranks (one process per GPU), the grid is replicated. Each tick every rank
    serialises the deltas its own robots produced, the ranks all-gather the byte blobs (NCCL over

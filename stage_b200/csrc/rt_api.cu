@@ -293,6 +293,11 @@ struct stg_rt_ctx {
   cudaEvent_t blob_uploaded = nullptr; // the pinned blob may be rewritten once this has fired
   cudaEvent_t t_ev[6][2] = {};          // [deltas, headings, march, fiducials, blobs, collisions / touchers][start, stop]
   cudaStream_t copy_stream = nullptr;   // result copies of chunk i overlap the march of chunk i+1
+  // k1_summaries runs here after every K1 pass, beside whatever the main stream does next (the march may read either
+  // version of a summary word); the next pass waits for it
+  cudaStream_t sum_stream = nullptr;
+  cudaEvent_t sum_ready = nullptr, sum_done = nullptr;
+  bool sum_pending = false;
   cudaEvent_t chunk_ev[8] = {};
   cudaEvent_t copies_done = nullptr;
   bool t_rec[6] = { false, false, false, false, false, false };
@@ -412,6 +417,9 @@ int fail(stg_rt_ctx *c, int code, const char *fmt, ...)
     if (e_ != cudaSuccess)                                                                         \
       return fail(ctx, STG_RT_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
+
+int summaries_fence_locked(stg_rt_ctx *c);
+int summaries_launch_locked(stg_rt_ctx *c);
 
 int dev_reserve(stg_rt_ctx *c, DevBuf &b, size_t bytes)
 {
@@ -810,17 +818,21 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
       if (!c->hold_epoch)
         c->epoch++;
       const int what = ((n_rem + n_ins + n_bupd + n_model) ? kDeltaEdgeRecords : 0) | (n_pose ? kDeltaPoseRecords : 0);
+      int rc = summaries_fence_locked(c);
+      if (rc)
+        return rc;
       CU(c, cudaEventRecord(c->t_ev[0][0], c->stream));
       launch_apply_deltas(c->g, c->gv, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, 0, what, c->stream,
                           &c->stats.launches_rasterise);
-      int rc = ensure_table_room(c, ins_round); // live entries grew by the net change, used slots by every insertion
-      if (rc)
+      if ((rc = ensure_table_room(c, ins_round))) // live entries grew by the net change, used slots by every insertion
         return rc;
       launch_apply_deltas(c->g, c->gv, (const unsigned char *)c->d_blob.p, 1, c->blob_cap, c->epoch, 1, what, c->stream,
                           &c->stats.launches_rasterise);
       if (owners_suspect)
         launch_owner_rebuild(c->g, c->stream, &c->stats.launches_rasterise);
       CU(c, cudaEventRecord(c->t_ev[0][1], c->stream));
+      if ((rc = summaries_launch_locked(c)))
+        return rc;
       c->t_rec[0] = true;
       CU(c, cudaGetLastError());
     }
@@ -851,6 +863,25 @@ uint32_t want_of(const stg_rt_fan_out &o)
   return (o.ranges ? STG_RT_WANT_RANGES : 0) | (o.intensities ? STG_RT_WANT_INTENSITIES : 0) |
          (o.bearings ? STG_RT_WANT_BEARINGS : 0) | (o.hit_model ? STG_RT_WANT_HIT_MODEL : 0) |
          (o.hit_cell ? STG_RT_WANT_HIT_CELL : 0) | (o.steps ? STG_RT_WANT_STEPS : 0);
+}
+
+// A K1 pass must not start while k1_summaries of the pass before is still reading the tiles ...
+int summaries_fence_locked(stg_rt_ctx *c)
+{
+  if (c->sum_pending)
+    CU(c, cudaStreamWaitEvent(c->stream, c->sum_done, 0));
+  return 0;
+}
+// ... and hands the regions it took bits out of to the next one (behind the pass, beside the main stream's next work)
+int summaries_launch_locked(stg_rt_ctx *c)
+{
+  CU(c, cudaEventRecord(c->sum_ready, c->stream));
+  CU(c, cudaStreamWaitEvent(c->sum_stream, c->sum_ready, 0));
+  launch_summaries(c->g, c->sum_stream);
+  CU(c, cudaEventRecord(c->sum_done, c->sum_stream));
+  c->sum_pending = true;
+  c->stats.launches_rasterise++;
+  return 0;
 }
 
 int reserve_outputs(stg_rt_ctx *c, FanArrays &a, uint64_t beams, uint32_t want)
@@ -1405,6 +1436,9 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
     for (int j = 0; j < 2; j++)
       CUC(cudaEventCreate(&c->t_ev[k][j]));
   CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&c->sum_stream, cudaStreamNonBlocking));
+  CUC(cudaEventCreateWithFlags(&c->sum_ready, cudaEventDisableTiming));
+  CUC(cudaEventCreateWithFlags(&c->sum_done, cudaEventDisableTiming));
   for (int k = 0; k < 8; k++)
     CUC(cudaEventCreateWithFlags(&c->chunk_ev[k], cudaEventDisableTiming));
   CUC(cudaEventCreateWithFlags(&c->copies_done, cudaEventDisableTiming));
@@ -1432,9 +1466,13 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
   CUC(cudaMalloc(&g.reg_owner, (c->n_regions + 1) * 4)); // + the stale flag
   CUC(cudaMemsetAsync(g.reg_owner, 0, (c->n_regions + 1) * 4, c->stream));
   // both layers' tiles in one allocation: the march addresses them with one 32-bit word index
-  CUC(cudaMalloc(&g.occ[0], 2 * c->n_regions * kTileWords * 4));
-  CUC(cudaMemsetAsync(g.occ[0], 0, 2 * c->n_regions * kTileWords * 4, c->stream));
+  // (and behind them both layers' summary words)
+  CUC(cudaMalloc(&g.occ[0], occ_alloc_words(c->n_regions) * 4));
+  CUC(cudaMemsetAsync(g.occ[0], 0, occ_alloc_words(c->n_regions) * 4, c->stream));
   g.occ[1] = g.occ[0] + c->n_regions * kTileWords;
+  g.occ_sum[0] = g.occ[0] + 2 * c->n_regions * kTileWords;
+  g.occ_sum[1] = g.occ_sum[0] + 2 * c->n_regions;
+  g.occ_dirty = g.occ_sum[1] + 2 * c->n_regions;
   for (int L = 0; L < 2; L++) {
     CUC(cudaMalloc(&g.slots[L], (size_t)c->slot_cap * 8));
     CUC(cudaMemsetAsync(g.slots[L], 0, (size_t)c->slot_cap * 8, c->stream));
@@ -1518,6 +1556,14 @@ int stg_rt_destroy(stg_rt_ctx *c)
   if (c->err_host)
     cudaFreeHost(c->err_host);
   cudaStreamDestroy(c->copy_stream);
+  if (c->sum_stream) {
+    cudaStreamSynchronize(c->sum_stream);
+    cudaStreamDestroy(c->sum_stream);
+  }
+  if (c->sum_ready)
+    cudaEventDestroy(c->sum_ready);
+  if (c->sum_done)
+    cudaEventDestroy(c->sum_done);
   for (int k = 0; k < 6; k++)
     for (int j = 0; j < 2; j++)
       cudaEventDestroy(c->t_ev[k][j]);
@@ -1658,12 +1704,12 @@ static int grow_extent_locked(stg_rt_ctx *c, int32_t x0, int32_t y0, int32_t x1,
   unsigned long long *fresh[2] = { nullptr, nullptr };
   cudaError_t e = cudaMalloc(&to.reg_count, n_new * 4);
   if (e == cudaSuccess) e = cudaMalloc(&to.reg_owner, (n_new + 1) * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&to.occ[0], 2 * n_new * kTileWords * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&to.occ[0], occ_alloc_words(n_new) * 4);
   for (int L = 0; L < 2 && e == cudaSuccess; L++)
     e = cudaMalloc(&fresh[L], (size_t)c->slot_cap * 8);
   if (e == cudaSuccess) e = cudaMemsetAsync(to.reg_count, 0, n_new * 4, c->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(to.reg_owner, 0, (n_new + 1) * 4, c->stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(to.occ[0], 0, 2 * n_new * kTileWords * 4, c->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(to.occ[0], 0, occ_alloc_words(n_new) * 4, c->stream);
   for (int L = 0; L < 2 && e == cudaSuccess; L++)
     e = cudaMemsetAsync(fresh[L], 0, (size_t)c->slot_cap * 8, c->stream);
   if (e != cudaSuccess) {
@@ -1674,8 +1720,12 @@ static int grow_extent_locked(stg_rt_ctx *c, int32_t x0, int32_t y0, int32_t x1,
     return fail(c, STG_RT_ENOMEM, "no device memory for a grid of %lld x %lld SuperRegions: %s", (long long)nsx, (long long)nsy, cudaGetErrorString(e));
   }
   to.occ[1] = to.occ[0] + n_new * kTileWords;
+  to.occ_sum[0] = to.occ[0] + 2 * n_new * kTileWords;
+  to.occ_sum[1] = to.occ_sum[0] + 2 * n_new;
+  to.occ_dirty = to.occ_sum[1] + 2 * n_new;
   to.slots[0] = fresh[0];
   to.slots[1] = fresh[1];
+  CU(c, cudaStreamSynchronize(c->sum_stream)); // the old arrays are about to be read whole and freed
   launch_grow(g, to, c->stream);
   c->stats.launches_other += 3;
   CU(c, cudaStreamSynchronize(c->stream));
@@ -2459,6 +2509,56 @@ int64_t stg_rt_debug_region_owners(stg_rt_ctx *c, int64_t *records, int64_t cap)
   return n;
 }
 
+int stg_rt_debug_occupancy_check(stg_rt_ctx *c, uint64_t out[3])
+{
+  if (!c || !out)
+    return STG_RT_EINVAL;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = flush_locked(c);
+  if (rc)
+    return rc;
+  if ((rc = deliver_locked(c)))
+    return rc;
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaStreamSynchronize(c->sum_stream)); // k1_summaries of the last pass has run: the summaries are exact now
+  const GridView &g = c->g;
+  const size_t nr = c->n_regions;
+  std::vector<uint32_t> occ(occ_alloc_words(nr)), want(2 * nr * kTileWords, 0u);
+  std::vector<unsigned long long> slots(c->slot_cap);
+  CU(c, cudaMemcpyAsync(occ.data(), g.occ[0], occ.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+  for (int L = 0; L < 2; L++) {
+    CU(c, cudaMemcpyAsync(slots.data(), g.slots[L], (size_t)c->slot_cap * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    uint32_t *w = want.data() + (size_t)L * nr * kTileWords;
+    for (const unsigned long long e : slots) {
+      if (e == kSlotEmpty || e == kSlotTomb)
+        continue;
+      const uint32_t key = (uint32_t)(e >> 32), region = key >> 10, cy = (key >> 5) & 31, cx = key & 31;
+      if (region >= nr)
+        continue;
+      w[(size_t)region * kTileWords + cy] |= 1u << cx;
+      w[(size_t)region * kTileWords + kRegionWidth + cx] |= 1u << cy;
+    }
+  }
+  out[0] = out[1] = out[2] = 0;
+  for (int L = 0; L < 2; L++)
+    for (size_t r = 0; r < nr; r++) {
+      const uint32_t *have = occ.data() + ((size_t)L * nr + r) * kTileWords, *w = want.data() + ((size_t)L * nr + r) * kTileWords;
+      const uint32_t *sum = occ.data() + 2 * nr * kTileWords + ((size_t)L * nr + r) * 2;
+      uint32_t rows = 0, cols = 0;
+      for (int i = 0; i < kRegionWidth; i++) {
+        out[0] += (uint64_t)__builtin_popcount(have[i] ^ w[i]) + (uint64_t)__builtin_popcount(have[kRegionWidth + i] ^ w[kRegionWidth + i]);
+        out[2] += (uint64_t)__builtin_popcount(w[i]);
+        rows |= have[i] ? 1u << i : 0u;
+        cols |= have[kRegionWidth + i] ? 1u << i : 0u;
+      }
+      out[1] += (uint64_t)__builtin_popcount(rows ^ sum[0]) + (uint64_t)__builtin_popcount(cols ^ sum[1]);
+    }
+  for (size_t i = 0; i < (nr + 31) / 32; i++) // a dirty bit left standing is a summary nobody will bring up to date
+    out[1] += (uint64_t)__builtin_popcount(occ[2 * nr * kTileWords + 4 * nr + i]);
+  return STG_RT_OK;
+}
+
 // ---- multi-GPU deltas ------------------------------------------------------------------------------
 
 size_t stg_rt_delta_slot_bytes(const stg_rt_ctx *c) { return c ? c->blob_cap : 0; }
@@ -2559,6 +2659,8 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_r
                   L, (long long)c->live_entries[L], (long long)add[L], (long long)going, c->slot_cap);
   }
   c->epoch++; // K1 takes the largest proposal among the blobs, which is at least this (every sender proposed its own epoch + 1)
+  if ((rc = summaries_fence_locked(c)))
+    return rc;
   CU(c, cudaEventRecord(c->t_ev[0][0], c->stream));
   launch_apply_deltas(c->g, c->gv, (const unsigned char *)dev_gathered, n_ranks, slot_bytes, c->epoch, 0, kDeltaEdgeRecords | kDeltaPoseRecords, c->stream,
                       &c->stats.launches_rasterise);
@@ -2568,6 +2670,8 @@ int stg_rt_delta_apply_gathered(stg_rt_ctx *c, const void *dev_gathered, int n_r
                       &c->stats.launches_rasterise);
   launch_owner_rebuild(c->g, c->stream, &c->stats.launches_rasterise); // other ranks' updates are only known there
   CU(c, cudaEventRecord(c->t_ev[0][1], c->stream));
+  if ((rc = summaries_launch_locked(c)))
+    return rc;
   c->t_rec[0] = true;
   CU(c, cudaGetLastError());
   return STG_RT_OK;

@@ -8,6 +8,8 @@ namespace stg {
 constexpr int kRBits = 5;                    // region.hh:13 RBITS: a Region is 32 x 32 cells
 constexpr int kRegionWidth = 1 << kRBits;    // region.hh:17
 constexpr int kTileWords = 2 * kRegionWidth; // row masks then column masks
+// words of the GridView::occ allocation for n regions: both layers' tiles, both layers' summary words (2 per tile), dirty bits
+constexpr size_t occ_alloc_words(size_t n) { return 2 * n * kTileWords + 2 * n * 2 + (n + 31) / 32; }
 constexpr int kSRBits = 10;                  // region.hh:15 SRBITS: a SuperRegion is 1024 x 1024 cells
 
 constexpr unsigned long long kSlotEmpty = 0ull;
@@ -58,6 +60,13 @@ inline uint32_t slot_home(uint32_t key, uint32_t slot_mask)
 //                      (region.hh:47) is non-empty. This is what the ray march reads: an x-major
 //                      ray tests a whole run of cells of one row with one AND, a y-major ray does
 //                      the same on a column.
+//  occ_sum[L][r*2 ..]  two summary words per tile: bit cy of word 0 is set iff row mask cy is non-zero, bit cx of
+//                      word 1 iff column mask cx is (the tile's projections on the two axes). The march uses them to
+//                      leave a region whose occupied cells lie off its path in closed form, and to jump to the first
+//                      row / column that can hold a hit (rt_walk.h). Same allocation as the tiles, behind them.
+//                      Between K1 passes a word may hold bits too many (never too few): see occ_dirty.
+//  occ_dirty[r / 32]   bit r % 32: a K1 pass cleared a bit of region r's tiles and left the summary bits standing;
+//                      k1_summaries recomputes those regions' words after the pass, beside the march. Same allocation.
 //  slots[L][h]         open-addressing multimap (cell -> block) holding the CONTENT of the occupied
 //                      cells: entry = (cell_key << 32) | (block_id + 1), cell_key = r*1024 + cy*32
 //                      + cx. 0 = empty, ~0 = tombstone. Only consulted where an occ bit is set.
@@ -97,6 +106,8 @@ struct GridView {
   uint32_t *reg_owner;   // n_regions words, then one more: the "owners are stale" flag (launch_owner_rebuild)
   uint32_t n_regions;
   uint32_t *occ[2];
+  uint32_t *occ_sum[2];
+  uint32_t *occ_dirty;
   unsigned long long *slots[2];
   uint32_t slot_mask;
   uint32_t n_blocks, n_models;
@@ -398,6 +409,7 @@ constexpr int kDeltaEdgeRecords = 1, kDeltaPoseRecords = 2;
 void launch_apply_deltas(const GridView &g, const GeomView &gv, const unsigned char *blobs, int n_ranks, size_t slot_bytes,
                          unsigned long long epoch, int phase, int what, void *stream, uint64_t *launch_counter);
 void launch_owner_rebuild(const GridView &g, void *stream, uint64_t *launch_counter);
+void launch_summaries(const GridView &g, void *stream); // tighten GridView::occ_sum over the regions marked in occ_dirty
 void launch_fan_headings(const FanBatchView &b, void *stream);
 void launch_ray_march(const GridView &g, const FanBatchView &b, void *stream);
 // the march with lane refill (rt_march.cu): per-beam (cos, sin) first, then the kernel

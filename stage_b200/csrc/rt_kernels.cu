@@ -131,6 +131,32 @@ __device__ __forceinline__ BlobView blob_view(const unsigned char *blobs, int ra
 }
 
 // ---- what one cell visit does to the grid (shared by the edge-record path and the pose path) ------------------
+// The occupancy bits of a cell in its region's tile, and the tile's summary words (GridView::occ_sum: which row masks
+// and which column masks are non-zero). The summaries only ever have to be a SUPERSET of the truth for the march to be
+// right (a bit too many costs it a walk it could have skipped), so K1 keeps them that way at no cost to its dependent
+// chains: setting a tile bit sets the two summary bits with fire-and-forget atomics, clearing one leaves them standing
+// and marks the region in GridView::occ_dirty; k1_summaries recomputes the marked regions' words from their tiles after
+// the pass, on a stream of its own, while the march is already running (it may read either version of a word).
+// (Tried first: whoever clears the last bit of a mask clears its summary bit, whoever sets the first sets it - those
+// atomics have to return their old values, and the round trips made a 1000-robot pass 0.024 ms longer; then the
+// recomputing kernel in line behind the pass: 0.013 ms.)
+__device__ __forceinline__ void occ_clear(const GridView &g, const CellAddr &c, uint32_t L)
+{
+  uint32_t *tile = g.occ[L] + (size_t)c.region * kTileWords;
+  atomicAnd(tile + c.cy, ~(1u << c.cx));
+  atomicAnd(tile + kRegionWidth + c.cx, ~(1u << c.cy));
+  atomicOr(g.occ_dirty + (c.region >> 5), 1u << (c.region & 31u));
+}
+__device__ __forceinline__ void occ_set(const GridView &g, const CellAddr &c, uint32_t L)
+{
+  uint32_t *tile = g.occ[L] + (size_t)c.region * kTileWords;
+  uint32_t *sum = g.occ_sum[L] + (size_t)c.region * 2;
+  atomicOr(tile + c.cy, 1u << c.cx);
+  atomicOr(tile + kRegionWidth + c.cx, 1u << c.cy);
+  atomicOr(sum, 1u << c.cy);
+  atomicOr(sum + 1, 1u << c.cx);
+}
+
 // Cell::RemoveBlock (region.cc:292-299, EraseAll: every copy goes) + Region::RemoveBlock's count
 __device__ __forceinline__ void cell_remove(const GridView &g, const CellAddr &c, uint32_t block, uint32_t L)
 {
@@ -147,9 +173,7 @@ __device__ __forceinline__ void cell_remove(const GridView &g, const CellAddr &c
   }
   if (atomicSub(g.reg_count + c.region, 1u) == 1u) // the region's last entry: it belongs to nobody again
     g.reg_owner[c.region] = kOwnerNone;
-  uint32_t *tile = g.occ[L] + (size_t)c.region * kTileWords;
-  atomicAnd(tile + c.cy, ~(1u << c.cx));
-  atomicAnd(tile + kRegionWidth + c.cx, ~(1u << c.cy));
+  occ_clear(g, c, L);
 }
 
 // after every removal has landed: a cell that lost an entry but still holds another block gets its mask bits back
@@ -162,9 +186,7 @@ __device__ __forceinline__ void cell_fixup(const GridView &g, const CellAddr &c,
     if (cur == kSlotEmpty)
       break;
     if ((uint32_t)(cur >> 32) == c.key) { // tombstones carry key 0xffffffff, never a cell key
-      uint32_t *tile = g.occ[L] + (size_t)c.region * kTileWords;
-      atomicOr(tile + c.cy, 1u << c.cx);
-      atomicOr(tile + kRegionWidth + c.cx, 1u << c.cy);
+      occ_set(g, c, L);
       break;
     }
     h = (h + 1) & g.slot_mask;
@@ -204,9 +226,7 @@ __device__ __forceinline__ void cell_insert(const GridView &g, const CellAddr &c
     if (cur != kOwnerNone && cur != tag && cur != kOwnerMixed)
       atomicExch(owner, kOwnerMixed);
   }
-  uint32_t *tile = g.occ[L] + (size_t)c.region * kTileWords;
-  atomicOr(tile + c.cy, 1u << c.cx);
-  atomicOr(tile + kRegionWidth + c.cx, 1u << c.cy);
+  occ_set(g, c, L);
 }
 
 // The cell visits of all ranks' blobs as ONE index space, so that a gathered delta (N ranks) is a
@@ -624,6 +644,31 @@ __global__ void __launch_bounds__(256) k1_pose_phase1(GridView g, GeomView gv, c
   }
 }
 
+// The summary words of the regions a pass took bits out of (GridView::occ_dirty), recomputed from their tiles (between
+// passes the words are exact or a superset, see occ_clear): a warp per word of dirty bits, lane i looks at row mask i and column mask i of the region, two ballots per layer are the two words.
+__global__ void __launch_bounds__(256) k1_summaries(GridView g)
+{
+  const uint32_t lane = threadIdx.x & 31u, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_words = (g.n_regions + 31u) >> 5;
+  for (uint32_t i = warp; i < n_words; i += n_warps) {
+    uint32_t dirty = g.occ_dirty[i];
+    if (!dirty)
+      continue;
+    __syncwarp();
+    if (lane == 0)
+      g.occ_dirty[i] = 0u;
+    for (; dirty; dirty &= dirty - 1u) {
+      const uint32_t r = i * 32u + (uint32_t)(__ffs(dirty) - 1);
+      for (int L = 0; L < 2; L++) {
+        const uint32_t *tile = g.occ[L] + (size_t)r * kTileWords;
+        const uint32_t rows = __ballot_sync(0xffffffffu, tile[lane] != 0u), cols = __ballot_sync(0xffffffffu, tile[kRegionWidth + lane] != 0u);
+        if (lane == 0)
+          *reinterpret_cast<uint2 *>(g.occ_sum[L] + (size_t)r * 2) = make_uint2(rows, cols);
+      }
+    }
+  }
+}
+
 // After a block changed trees (flag raised by k1_table_updates) the owner tags are rebuilt from the cell-entry
 // tables: clear, re-derive from every live entry of both layers, lower the flag - three launches in stream order,
 // each of which only reads the flag when nothing changed. The host launches them after a pass that carried model
@@ -783,9 +828,12 @@ __global__ void __launch_bounds__(256) k1_grow_regions(GridView from, GridView t
     to.reg_count[rn] = from.reg_count[r];
     to.reg_owner[rn] = from.reg_owner[r];
     if (from.reg_count[r])
-      for (int L = 0; L < 2; L++)
+      for (int L = 0; L < 2; L++) {
         for (int w = 0; w < kTileWords; w++)
           to.occ[L][(size_t)rn * kTileWords + w] = from.occ[L][(size_t)r * kTileWords + w];
+        to.occ_sum[L][(size_t)rn * 2] = from.occ_sum[L][(size_t)r * 2];
+        to.occ_sum[L][(size_t)rn * 2 + 1] = from.occ_sum[L][(size_t)r * 2 + 1];
+      }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0)
     to.reg_owner[to.n_regions] = from.reg_owner[from.n_regions]; // the "owners are stale" flag
@@ -854,6 +902,12 @@ void launch_apply_deltas(const GridView &g, const GeomView &gv, const unsigned c
     if (launch_counter)
       *launch_counter += 1;
   }
+}
+
+void launch_summaries(const GridView &g, void *stream)
+{
+  const int words = (int)((g.n_regions + 31u) >> 5);
+  k1_summaries<<<min(delta_grid_blocks(), (words + 7) / 8), 256, 0, (cudaStream_t)stream>>>(g);
 }
 
 void launch_owner_rebuild(const GridView &g, void *stream, uint64_t *launch_counter)

@@ -332,15 +332,48 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
       int32_t cp = cp0, ap = ap0;
       int32_t mdl = -1;
       const bool own = __ldg(g.reg_owner + region) == finder_tag;
-      if (own && n >= 2 * kRegionWidth && (flags & kClosedForms)) {
-        // A region that holds only the finder's own tree cannot stop this ray, and the ray does not end in it (a region
-        // holds at most 2 * 32 - 1 of its cells): where and how the cell-by-cell walk leaves is a closed form (rt_walk.h).
-        walk::region_exit(ap0, cp0, E, b_run, b_cross, ap, cp, E);
-        const int32_t steps = (ap - ap0) + (cp - cp0); // one cell visited per step taken
-        if (kSteps)
-          cell_visits += (uint32_t)steps;
-        n -= steps;
-      } else {
+      bool walk_it = true;
+      if (n >= 2 * kRegionWidth && (flags & kClosedForms)) {
+        // The ray does not end in this region (a region holds at most 2 * 32 - 1 of its cells): where and in which state
+        // the cell-by-cell walk leaves it, if nothing stops the ray, is a closed form (rt_walk.h).
+        int32_t xa, xc, xe;
+        walk::region_exit(ap0, cp0, E, b_run, b_cross, xa, xc, xe);
+        // Nothing can stop it in a region that holds only the finder's own tree, nor where the occupied cells lie off
+        // its path: the tile's summary words say which rows and which columns hold anything at all, and a cell on the
+        // path can only be occupied if its row and its column both do.
+        bool leave = own;
+        if (!own) {
+          const uint2 sum = __ldg(reinterpret_cast<const uint2 *>(layer1 ? g.occ_sum[1] : g.occ_sum[0]) + region);
+          uint32_t rs = ymajor ? sum.x : sum.y, cs = ymajor ? sum.y : sum.x; // along the run axis / the cross axis
+          rs ^= (rs ^ __brev(rs)) & revmask;
+          cs = cflip ? __brev(cs) : cs;
+          rs &= run_mask(ap0, min(xa, kRegionWidth - 1) - ap0 + 1); // the coordinates the walk stands in inside the region
+          cs &= run_mask(cp0, min(xc, kRegionWidth - 1) - cp0 + 1);
+          leave = !rs || !cs;
+          if (!leave) {
+            // no cell before the first such row AND the first such column can stop the ray: start the walk where it
+            // first stands in both (the later of the two states, each one division away)
+            const int32_t a1 = __ffs(rs) - 1, c1 = __ffs(cs) - 1;
+            if (c1 > cp0)
+              walk::jump_cross(ap0, cp0, E, b_run, b_cross, c1 - cp0, ap, cp, E);
+            if (a1 > ap)
+              walk::jump_run(ap, cp, E, b_run, b_cross, a1 - ap, ap, cp, E);
+            if (kSteps)
+              cell_visits += (uint32_t)((ap - ap0) + (cp - cp0));
+          }
+        }
+        if (leave) {
+          ap = xa;
+          cp = xc;
+          E = xe;
+          const int32_t steps = (ap - ap0) + (cp - cp0); // one cell visited per step taken
+          if (kSteps)
+            cell_visits += (uint32_t)steps;
+          n -= steps;
+          walk_it = false;
+        }
+      }
+      if (walk_it) {
         // the region's row masks (x-major rays) or column masks (y-major); mask number (cp ^ cflip) belongs to cp
         uint32_t tile = occ_layer + region * kTileWords + (ymajor ? kRegionWidth : 0);
         asm volatile("" : "+r"(tile)); // one register to keep, not five instructions to redo in every run

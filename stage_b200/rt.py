@@ -119,6 +119,7 @@ def lib():
         "stg_rt_set_beams": (u64, [vp]),
         "stg_rt_grid_dump": (ctypes.c_int64, [vp, vp, ctypes.c_int64, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
         "stg_rt_debug_region_owners": (ctypes.c_int64, [vp, vp, ctypes.c_int64]),
+        "stg_rt_debug_occupancy_check": (ctypes.c_int, [vp, ctypes.POINTER(u64 * 3)]),
         "stg_rt_grid_hash": (ctypes.c_int, [vp, ctypes.POINTER(u64 * 5)]),
         "stg_rt_delta_export": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(sz)]),
         "stg_rt_delta_slot_bytes": (sz, [vp]),
@@ -149,7 +150,7 @@ EXPORTED_SYMBOLS = (
     "stg_rt_block_unmap stg_rt_blocks_remap stg_rt_block_define stg_rt_models_pose_update stg_rt_debug_block_outline stg_rt_fiducials_submit stg_rt_fiducials_submit_packed stg_rt_fiducials_submit_device_targets stg_rt_rangers_submit stg_rt_collisions_test stg_rt_touching_models stg_rt_models_move stg_rt_blobs_submit stg_rt_fans_submit_noisy stg_rt_fans_submit stg_rt_flush stg_rt_sync stg_rt_host_alloc stg_rt_host_free "
     "stg_rt_set_create stg_rt_set_destroy stg_rt_set_update_origins stg_rt_set_trace stg_rt_set_download "
     "stg_rt_set_device_ptrs stg_rt_set_beams stg_rt_grid_dump stg_rt_delta_export stg_rt_delta_slot_bytes "
-    "stg_rt_delta_apply_gathered stg_rt_stream_signal stg_rt_stream_wait stg_rt_ranger_rand_advance stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_kernel_times_ex stg_rt_debug_link_bandwidth stg_rt_debug_trig stg_rt_debug_headings stg_rt_debug_region_owners stg_rt_grid_hash").split()
+    "stg_rt_delta_apply_gathered stg_rt_stream_signal stg_rt_stream_wait stg_rt_ranger_rand_advance stg_rt_set_stream stg_rt_get_stream stg_rt_get_stats stg_rt_kernel_times stg_rt_kernel_times_ex stg_rt_debug_link_bandwidth stg_rt_debug_trig stg_rt_debug_headings stg_rt_debug_region_owners stg_rt_debug_occupancy_check stg_rt_grid_hash").split()
 
 
 _BYTES0 = ctypes.c_char * 0
@@ -438,6 +439,13 @@ class Context:
         rec = np.zeros((max(n, 1), 3), np.int64)
         assert self._check(self._L.stg_rt_debug_region_owners(self._h, _ptr(rec), n)) == n
         return rec[:n]
+
+    def occupancy_check(self):
+        """(cells whose mask bits disagree with the cell entries, summary bits that disagree with the masks, occupied
+        cells seen): the first two are 0 on a sound grid."""
+        out = (ctypes.c_uint64 * 3)()
+        self._check(self._L.stg_rt_debug_occupancy_check(self._h, ctypes.byref(out)))
+        return int(out[0]), int(out[1]), int(out[2])
 
     def stats(self):
         s = Stats()

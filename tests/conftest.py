@@ -26,3 +26,24 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _occupancy_checked_with_every_grid_comparison(request, monkeypatch):
+    """Whenever a GPU test takes the device grid (dump or digest) to compare it with the oracle's, the occupancy tiles
+    and their summary words - what the march reads instead of the cell lists - are checked against the cell entries too
+    (stg_rt_debug_occupancy_check): no bit without an entry, no entry without its bits, summaries equal to the masks."""
+    if "gpu" not in request.keywords:
+        return
+    from stage_b200 import rt
+
+    def checked(method):
+        def wrapper(self, *a, **k):
+            bad_bits, bad_summaries, _ = self.occupancy_check()
+            assert (bad_bits, bad_summaries) == (0, 0), "occupancy tiles / summaries disagree with the cell entries"
+            return method(self, *a, **k)
+        return wrapper
+
+    for name in ("grid_dump", "dump_grid", "grid_hash"):
+        if hasattr(rt.Context, name):
+            monkeypatch.setattr(rt.Context, name, checked(getattr(rt.Context, name)))
