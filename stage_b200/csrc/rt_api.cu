@@ -381,9 +381,11 @@ struct stg_rt_ctx {
   bool palette_ok = true;
   bool f_compact_intens = false; // the batch in flight delivers intensities as palette indices
   PinBuf h_intens_idx;
-  // streamed delivery: the march tells the host, warp by warp, which results have landed (FanBatchView::done_flags), and
-  // the pool's threads expand intensities of finished stretches while the kernel is still running
+  // streamed delivery: the march tells the host, stretch by stretch, which results have landed (FanBatchView::stretch_done;
+  // d_stretch_count = its per-stretch warp counters), and the pool's threads expand intensities of finished stretches while
+  // the kernel is still running
   PinBuf h_done_flags;
+  DevBuf d_stretch_count;
   uint32_t done_seq = 0;
   bool f_streaming = false;
   std::atomic<bool> stream_gave_up{ false };
@@ -1259,16 +1261,20 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
     CU(c, cudaStreamWaitEvent(c->stream, c->chunk_ev[1], 0));
   }
   const double t_prof2 = prof_now(c);
-  // A large batch of one submit that wants intensities as doubles: stream them (see h_done_flags)
+  // A large batch of one submit that wants intensities as doubles: stream them (see h_done_flags), in stretches of 8192
+  // beams (256 warps): a stretch is expanded as soon as the march has reported it complete
+  constexpr uint32_t kStretchShift = 13;
+  constexpr size_t kStretch = (size_t)1 << kStretchShift;
   const char *stream_env = getenv("STG_RT_STREAM");
   const bool no_stream = stream_env && !strcmp(stream_env, "0");
   c->f_streaming = false;
   if (c->f_compact_intens && solo && solo->out.intensities && !refill && !no_stream && beams >= (1u << 17) && !c->pool.busy()) {
-    const size_t n_flags = (size_t)((beams + 31) / 32);
+    const size_t n_flags = (size_t)((beams + kStretch - 1) / kStretch);
     const bool fresh = n_flags * 4 > c->h_done_flags.cap;
-    if ((rc = pin_reserve(c, c->h_done_flags, n_flags * 4)))
+    if ((rc = pin_reserve(c, c->h_done_flags, n_flags * 4)) || (rc = dev_reserve(c, c->d_stretch_count, c->h_done_flags.cap)))
       return rc;
-    if (fresh) {
+    if (fresh) { // (every launch leaves the counters at zero again)
+      CU(c, cudaMemsetAsync(c->d_stretch_count.p, 0, c->d_stretch_count.cap, c->stream));
       memset(c->h_done_flags.p, 0, c->h_done_flags.cap);
       c->done_seq = 0;
     }
@@ -1276,8 +1282,10 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
       memset(c->h_done_flags.p, 0, c->h_done_flags.cap);
       c->done_seq = 1;
     }
-    v.done_flags = (uint32_t *)c->h_done_flags.p;
+    v.stretch_count = (uint32_t *)c->d_stretch_count.p;
+    v.stretch_done = (uint32_t *)c->h_done_flags.p;
     v.done_seq = c->done_seq;
+    v.stretch_shift = kStretchShift;
     c->f_streaming = true;
   }
   CU(c, cudaEventRecord(c->t_ev[2][0], c->stream));
@@ -1289,8 +1297,6 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   c->t_rec[1] = c->t_rec[2] = true;
   CU(c, cudaGetLastError());
   if (c->f_streaming) {
-    // stretches of 8192 beams (256 warps): a stretch is expanded as soon as all its warps have reported
-    constexpr size_t kStretch = 8192;
     const uint8_t *idx = (const uint8_t *)c->h_intens_idx.p;
     double *dst = solo->out.intensities;
     const double *pal = c->palette.data();
@@ -1302,14 +1308,13 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
     c->pool.begin((n + kStretch - 1) / kStretch, [idx, dst, pal, flags, seq, n, gave_up](size_t part) {
       const size_t lo = part * kStretch, hi = std::min(n, lo + kStretch);
       const std::chrono::steady_clock::time_point until = std::chrono::steady_clock::now() + std::chrono::seconds(2);
-      for (size_t w = lo / 32; w < (hi + 31) / 32; w++)
-        while (flags[w] != seq) {
-          if (gave_up->load(std::memory_order_relaxed) || std::chrono::steady_clock::now() > until) {
-            gave_up->store(true); // the kernel did not finish (an error the sync will report): nothing to expand
-            return;
-          }
-          _mm_pause();
+      while (flags[part] != seq) {
+        if (gave_up->load(std::memory_order_relaxed) || std::chrono::steady_clock::now() > until) {
+          gave_up->store(true); // the kernel did not finish (an error the sync will report): nothing to expand
+          return;
         }
+        _mm_pause();
+      }
       std::atomic_thread_fence(std::memory_order_acquire);
       size_t i = lo;
       for (; i < hi && ((uintptr_t)(dst + i) & 15u); i++)
@@ -1532,13 +1537,14 @@ int stg_rt_destroy(stg_rt_ctx *c)
     cudaFreeHost(c->q_fans.p);
   if (c->d_in.p)
     cudaFree(c->d_in.p);
-  for (DevBuf *b : { &c->d_work_counter, &c->d_geom, &c->d_pts, &c->d_pix[0], &c->d_pix[1], &c->d_pix_new[0], &c->d_pix_new[1], &c->d_rig, &c->d_mv_in, &c->d_mv_out, &c->d_mover_of_model, &c->d_col_in, &c->d_col_hit, &c->d_touch_out, &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_fid_off, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color })
+  for (DevBuf *b : { &c->d_work_counter, &c->d_geom, &c->d_pts, &c->d_pix[0], &c->d_pix[1], &c->d_pix_new[0], &c->d_pix_new[1], &c->d_rig, &c->d_mv_in, &c->d_mv_out, &c->d_mover_of_model, &c->d_col_in, &c->d_col_hit, &c->d_touch_out, &c->d_fid_grid, &c->d_fid_in, &c->d_fid_out, &c->d_fid_count, &c->d_fid_off, &c->d_blob_in, &c->d_blob_out, &c->d_blob_count, &c->d_mdl_color, &c->d_stretch_count })
     if (b->p)
       cudaFree(b->p);
   for (PinBuf *b : { &c->h_rig, &c->h_mv_in, &c->h_mv_out, &c->h_col_in, &c->h_col_hit, &c->h_touch_out, &c->h_fid_in, &c->h_fid_out, &c->h_fid_count, &c->h_blob_in, &c->h_blob_out, &c->h_blob_count })
     if (b->p)
       cudaFreeHost(b->p);
-  PinBuf *pins[] = { &c->h_blob, &c->h_in, &c->h_ranges, &c->h_intens, &c->h_bearings, &c->h_hit_model, &c->h_hit_cell, &c->h_steps };
+  PinBuf *pins[] = { &c->h_blob, &c->h_in, &c->h_ranges, &c->h_intens, &c->h_bearings, &c->h_hit_model, &c->h_hit_cell, &c->h_steps,
+                     &c->h_intens_idx, &c->h_done_flags };
   for (PinBuf *p : pins)
     if (p->p)
       cudaFreeHost(p->p);

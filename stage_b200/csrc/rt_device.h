@@ -247,11 +247,15 @@ struct FanBatchView {
   int32_t *hit_model, *hit_cell;
   uint32_t *steps;
   uint8_t *intens_idx; // intensities as one palette index per beam (GridView::mdl_pal): 1 byte over PCIe instead of 8
-  // page-locked host words, one per 32 beams of the batch: a warp of the march writes `done_seq` there once its results have
-  // been stored (behind a system-wide fence), so that host threads can start on a stretch of beams while the kernel is still
-  // marching the rest (null: nobody is listening)
-  uint32_t *done_flags;
-  uint32_t done_seq;
+  // Streamed delivery. The batch is cut into stretches of 2^stretch_shift beams; stretch_count holds one DEVICE word per
+  // stretch, stretch_done one word of PAGE-LOCKED HOST memory. A warp of the march, once its 32 results have been stored
+  // (into page-locked host memory) and fenced system-wide, adds one to its stretch's counter; the warp that completes a
+  // stretch puts the counter back to zero and writes done_seq into the stretch's host word, so that host threads can start
+  // on the stretch while the kernel is still marching the rest - one small write over the link per stretch, not per warp.
+  // Null: nobody is listening.
+  uint32_t *stretch_count;
+  uint32_t *stretch_done;
+  uint32_t done_seq, stretch_shift;
 };
 
 // ---- whole ranger models (same layouts as stg_rt_ranger_* in include/stg_rt.h) ------------------

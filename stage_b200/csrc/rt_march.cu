@@ -91,12 +91,24 @@ __global__ void __launch_bounds__(128, STG_MARCH_CTAS_PER_SM) k2_ray_march(GridV
     b.steps[2 * beam] = r.cell_visits;
     b.steps[2 * beam + 1] = r.region_probes;
   }
-  if (b.done_flags) { // tell the host this warp's 32 results have landed (the listener expands intensities meanwhile)
-    const unsigned active = __activemask();
-    __syncwarp(active);
-    if ((threadIdx.x & 31u) == (unsigned)(__ffs(active) - 1)) {
-      __threadfence_system();
-      *reinterpret_cast<volatile uint32_t *>(b.done_flags + ((beam - b.beam_begin) >> 5)) = b.done_seq;
+  if (b.stretch_count) { // tell the host when this warp's stretch of beams has landed (the listener expands intensities meanwhile)
+    // every lane of the warp that has a beam meets here (not "whoever happens to be converged": the lanes the report speaks
+    // for must all have stored)
+    const uint64_t left = b.beam_end - (beam - (threadIdx.x & 31u));
+    __syncwarp(left >= 32 ? 0xffffffffu : (1u << (unsigned)left) - 1u);
+    if ((threadIdx.x & 31u) == 0u) {
+      const uint64_t k = (beam - b.beam_begin) >> b.stretch_shift;
+      const uint64_t in_stretch = min((uint64_t)1 << b.stretch_shift, b.beam_end - b.beam_begin - (k << b.stretch_shift));
+      // the warp's results, then its count: device scope here (the counter lives on the device); the warp that completes the
+      // stretch fences system-wide behind every count it has seen, which orders all the stretch's results before the flag
+      // for the host as well (a system-wide fence per warp would make each wait out its own stores' way across the link:
+      // +0.05 ms on a 1 M-beam march)
+      __threadfence();
+      if (atomicAdd(b.stretch_count + k, 1u) + 1u == (uint32_t)((in_stretch + 31) >> 5)) { // the stretch's last warp
+        b.stretch_count[k] = 0u; // for the next launch
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t *>(b.stretch_done + k) = b.done_seq;
+      }
     }
   }
 }

@@ -274,9 +274,10 @@ def test_refill_march_kernel_equals_the_plain_one(monkeypatch):
 
 
 def test_streamed_intensities_equal_the_plain_delivery(monkeypatch):
-    """Large batches deliver intensities while the march is still running: warps report their finished beams through flags
-    in page-locked memory and host threads expand the palette bytes of finished stretches meanwhile. Same doubles as the
-    delivery after the sync, tick after tick (the flags carry a sequence number), into pinned and ordinary arrays."""
+    """Large batches deliver intensities while the march is still running: the warp that completes a stretch of 8192 beams
+    says so through a flag in page-locked memory and host threads expand the palette bytes of finished stretches meanwhile.
+    Same doubles as the delivery after the sync, tick after tick (the flags carry a sequence number), into pinned and
+    ordinary arrays."""
     from stage_b200 import worldgen
     w = worldgen.make_world(seed=14, n_rects=600, n_robots=220, half_extent_m=40.96)
     x0, y0, nx, ny = w.sreg_extent()
@@ -286,7 +287,7 @@ def test_streamed_intensities_equal_the_plain_delivery(monkeypatch):
         ctx.model_upsert(int(mid), int(mid), 0.1 + 0.05 * (k % 9))
     ctx.sync()
     poses = w.robots
-    for tick in range(4):
+    for tick in range(12):
         poses = worldgen.step_robots(w, poses, tick, speed_m=0.3)
         fans = worldgen.ranger_fans(w, layer=1, samples=1080, range_max=25.0, robots=poses)
         res = {}
