@@ -1465,19 +1465,15 @@ int stg_rt_create(const stg_rt_config *cfg, stg_rt_ctx **out)
   g.slot_mask = c->slot_cap - 1;
   g.n_blocks = cfg->max_blocks;
   g.n_models = cfg->max_models;
-  CUC(cudaMalloc(&g.reg_count, c->n_regions * 4));
-  CUC(cudaMemsetAsync(g.reg_count, 0, c->n_regions * 4, c->stream));
+  CUC(cudaMalloc(&g.head, (c->n_regions + 1) * sizeof(RegionHead))); // + the record that holds the "owners are stale" flag
+  CUC(cudaMemsetAsync(g.head, 0, (c->n_regions + 1) * sizeof(RegionHead), c->stream));
   g.n_regions = (uint32_t)c->n_regions;
-  CUC(cudaMalloc(&g.reg_owner, (c->n_regions + 1) * 4)); // + the stale flag
-  CUC(cudaMemsetAsync(g.reg_owner, 0, (c->n_regions + 1) * 4, c->stream));
   // both layers' tiles in one allocation: the march addresses them with one 32-bit word index
   // (and behind them both layers' summary words)
   CUC(cudaMalloc(&g.occ[0], occ_alloc_words(c->n_regions) * 4));
   CUC(cudaMemsetAsync(g.occ[0], 0, occ_alloc_words(c->n_regions) * 4, c->stream));
   g.occ[1] = g.occ[0] + c->n_regions * kTileWords;
-  g.occ_sum[0] = g.occ[0] + 2 * c->n_regions * kTileWords;
-  g.occ_sum[1] = g.occ_sum[0] + 2 * c->n_regions;
-  g.occ_dirty = g.occ_sum[1] + 2 * c->n_regions;
+  g.occ_dirty = g.occ[0] + 2 * c->n_regions * kTileWords;
   for (int L = 0; L < 2; L++) {
     CUC(cudaMalloc(&g.slots[L], (size_t)c->slot_cap * 8));
     CUC(cudaMemsetAsync(g.slots[L], 0, (size_t)c->slot_cap * 8, c->stream));
@@ -1526,7 +1522,7 @@ int stg_rt_destroy(stg_rt_ctx *c)
             (unsigned long long)c->prof_flushes, c->prof_us[0], c->prof_us[1], c->prof_us[2], c->prof_us[3], c->prof_us[4],
             c->prof_us[5], c->prof_us[6], c->prof_us[7], c->prof_us[8], c->prof_us[9]);
   GridView &g = c->g;
-  void *dev[] = { g.reg_count, g.reg_owner, g.occ[0], g.slots[0], g.slots[1], g.blk_rec[0], g.blk_rec[1], c->spare_slots,
+  void *dev[] = { g.head, g.occ[0], g.slots[0], g.slots[1], g.blk_rec[0], g.blk_rec[1], c->spare_slots,
                   g.mdl_root, g.mdl_ranger_return, g.mdl_flags, g.mdl_pal, c->d_blob.p };
   for (void *p : dev)
     if (p)
@@ -1705,30 +1701,27 @@ static int grow_extent_locked(stg_rt_ctx *c, int32_t x0, int32_t y0, int32_t x1,
   to.nry = (int32_t)nsy * 32;
   const size_t n_new = (size_t)to.nrx * to.nry;
   to.n_regions = (uint32_t)n_new;
-  to.reg_count = to.reg_owner = to.occ[0] = nullptr;
+  to.head = nullptr;
+  to.occ[0] = nullptr;
   to.slots[0] = to.slots[1] = nullptr;
   unsigned long long *fresh[2] = { nullptr, nullptr };
-  cudaError_t e = cudaMalloc(&to.reg_count, n_new * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&to.reg_owner, (n_new + 1) * 4);
+  cudaError_t e = cudaMalloc(&to.head, (n_new + 1) * sizeof(RegionHead));
   if (e == cudaSuccess) e = cudaMalloc(&to.occ[0], occ_alloc_words(n_new) * 4);
   for (int L = 0; L < 2 && e == cudaSuccess; L++)
     e = cudaMalloc(&fresh[L], (size_t)c->slot_cap * 8);
-  if (e == cudaSuccess) e = cudaMemsetAsync(to.reg_count, 0, n_new * 4, c->stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(to.reg_owner, 0, (n_new + 1) * 4, c->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(to.head, 0, (n_new + 1) * sizeof(RegionHead), c->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(to.occ[0], 0, occ_alloc_words(n_new) * 4, c->stream);
   for (int L = 0; L < 2 && e == cudaSuccess; L++)
     e = cudaMemsetAsync(fresh[L], 0, (size_t)c->slot_cap * 8, c->stream);
   if (e != cudaSuccess) {
-    for (void *p : { (void *)to.reg_count, (void *)to.reg_owner, (void *)to.occ[0], (void *)fresh[0], (void *)fresh[1] })
+    for (void *p : { (void *)to.head, (void *)to.occ[0], (void *)fresh[0], (void *)fresh[1] })
       if (p)
         cudaFree(p);
     cudaGetLastError();
     return fail(c, STG_RT_ENOMEM, "no device memory for a grid of %lld x %lld SuperRegions: %s", (long long)nsx, (long long)nsy, cudaGetErrorString(e));
   }
   to.occ[1] = to.occ[0] + n_new * kTileWords;
-  to.occ_sum[0] = to.occ[0] + 2 * n_new * kTileWords;
-  to.occ_sum[1] = to.occ_sum[0] + 2 * n_new;
-  to.occ_dirty = to.occ_sum[1] + 2 * n_new;
+  to.occ_dirty = to.occ[0] + 2 * n_new * kTileWords;
   to.slots[0] = fresh[0];
   to.slots[1] = fresh[1];
   CU(c, cudaStreamSynchronize(c->sum_stream)); // the old arrays are about to be read whole and freed
@@ -1736,7 +1729,7 @@ static int grow_extent_locked(stg_rt_ctx *c, int32_t x0, int32_t y0, int32_t x1,
   c->stats.launches_other += 3;
   CU(c, cudaStreamSynchronize(c->stream));
   CU(c, cudaGetLastError());
-  for (void *p : { (void *)g.reg_count, (void *)g.reg_owner, (void *)g.occ[0], (void *)g.slots[0], (void *)g.slots[1] })
+  for (void *p : { (void *)g.head, (void *)g.occ[0], (void *)g.slots[0], (void *)g.slots[1] })
     cudaFree(p);
   g = to;
   c->n_regions = n_new;
@@ -2446,7 +2439,7 @@ int64_t stg_rt_grid_dump(stg_rt_ctx *c, int32_t *records, int64_t cap, int64_t *
     }
     n++;
   }
-  CU(c, cudaMemcpyAsync(counts.data(), g.reg_count, c->n_regions * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpy2DAsync(counts.data(), 4, &g.head[0].count, sizeof(RegionHead), 4, c->n_regions, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   int64_t nc = 0;
   for (size_t r = 0; r < counts.size(); r++)
@@ -2500,7 +2493,7 @@ int64_t stg_rt_debug_region_owners(stg_rt_ctx *c, int64_t *records, int64_t cap)
     return rc;
   const GridView &g = c->g;
   std::vector<uint32_t> owners(c->n_regions);
-  CU(c, cudaMemcpyAsync(owners.data(), g.reg_owner, c->n_regions * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpy2DAsync(owners.data(), 4, &g.head[0].owner, sizeof(RegionHead), 4, c->n_regions, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   int64_t n = 0;
   for (size_t r = 0; r < owners.size(); r++)
@@ -2530,8 +2523,10 @@ int stg_rt_debug_occupancy_check(stg_rt_ctx *c, uint64_t out[3])
   const GridView &g = c->g;
   const size_t nr = c->n_regions;
   std::vector<uint32_t> occ(occ_alloc_words(nr)), want(2 * nr * kTileWords, 0u);
+  std::vector<RegionHead> heads(nr);
   std::vector<unsigned long long> slots(c->slot_cap);
   CU(c, cudaMemcpyAsync(occ.data(), g.occ[0], occ.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(heads.data(), g.head, nr * sizeof(RegionHead), cudaMemcpyDeviceToHost, c->stream));
   for (int L = 0; L < 2; L++) {
     CU(c, cudaMemcpyAsync(slots.data(), g.slots[L], (size_t)c->slot_cap * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
@@ -2550,7 +2545,7 @@ int stg_rt_debug_occupancy_check(stg_rt_ctx *c, uint64_t out[3])
   for (int L = 0; L < 2; L++)
     for (size_t r = 0; r < nr; r++) {
       const uint32_t *have = occ.data() + ((size_t)L * nr + r) * kTileWords, *w = want.data() + ((size_t)L * nr + r) * kTileWords;
-      const uint32_t *sum = occ.data() + 2 * nr * kTileWords + ((size_t)L * nr + r) * 2;
+      const uint32_t *sum = heads[r].sum[L];
       uint32_t rows = 0, cols = 0;
       for (int i = 0; i < kRegionWidth; i++) {
         out[0] += (uint64_t)__builtin_popcount(have[i] ^ w[i]) + (uint64_t)__builtin_popcount(have[kRegionWidth + i] ^ w[kRegionWidth + i]);
@@ -2561,7 +2556,7 @@ int stg_rt_debug_occupancy_check(stg_rt_ctx *c, uint64_t out[3])
       out[1] += (uint64_t)__builtin_popcount(rows ^ sum[0]) + (uint64_t)__builtin_popcount(cols ^ sum[1]);
     }
   for (size_t i = 0; i < (nr + 31) / 32; i++) // a dirty bit left standing is a summary nobody will bring up to date
-    out[1] += (uint64_t)__builtin_popcount(occ[2 * nr * kTileWords + 4 * nr + i]);
+    out[1] += (uint64_t)__builtin_popcount(occ[2 * nr * kTileWords + i]);
   return STG_RT_OK;
 }
 

@@ -8,8 +8,8 @@ namespace stg {
 constexpr int kRBits = 5;                    // region.hh:13 RBITS: a Region is 32 x 32 cells
 constexpr int kRegionWidth = 1 << kRBits;    // region.hh:17
 constexpr int kTileWords = 2 * kRegionWidth; // row masks then column masks
-// words of the GridView::occ allocation for n regions: both layers' tiles, both layers' summary words (2 per tile), dirty bits
-constexpr size_t occ_alloc_words(size_t n) { return 2 * n * kTileWords + 2 * n * 2 + (n + 31) / 32; }
+// words of the GridView::occ allocation for n regions: both layers' tiles, then the dirty bits
+constexpr size_t occ_alloc_words(size_t n) { return 2 * n * kTileWords + (n + 31) / 32; }
 constexpr int kSRBits = 10;                  // region.hh:15 SRBITS: a SuperRegion is 1024 x 1024 cells
 
 constexpr unsigned long long kSlotEmpty = 0ull;
@@ -43,6 +43,7 @@ inline uint32_t slot_home(uint32_t key, uint32_t slot_mask)
 
 // The replicated world state one GPU holds. Passed to kernels by value.
 //
+//  (reg_count, reg_owner and occ_sum are fields of head[r], see RegionHead)
 //  reg_count[r]        Region::count (region.cc:19-34): number of (cell, block) entries of BOTH
 //                      layers in region r. r = (gry - ry0) * nrx + (grx - rx0), row-major over the
 //                      dense extent. 4 B / region.
@@ -63,10 +64,10 @@ inline uint32_t slot_home(uint32_t key, uint32_t slot_mask)
 //  occ_sum[L][r*2 ..]  two summary words per tile: bit cy of word 0 is set iff row mask cy is non-zero, bit cx of
 //                      word 1 iff column mask cx is (the tile's projections on the two axes). The march uses them to
 //                      leave a region whose occupied cells lie off its path in closed form, and to jump to the first
-//                      row / column that can hold a hit (rt_walk.h). Same allocation as the tiles, behind them.
+//                      row / column that can hold a hit (rt_walk.h). Kept in the region's RegionHead.
 //                      Between K1 passes a word may hold bits too many (never too few): see occ_dirty.
 //  occ_dirty[r / 32]   bit r % 32: a K1 pass cleared a bit of region r's tiles and left the summary bits standing;
-//                      k1_summaries recomputes those regions' words after the pass, beside the march. Same allocation.
+//                      k1_summaries recomputes those regions' words after the pass, beside the march. Same allocation as the tiles, behind them.
 //  slots[L][h]         open-addressing multimap (cell -> block) holding the CONTENT of the occupied
 //                      cells: entry = (cell_key << 32) | (block_id + 1), cell_key = r*1024 + cy*32
 //                      + cx. 0 = empty, ~0 = tombstone. Only consulted where an occ bit is set.
@@ -99,14 +100,23 @@ constexpr uint32_t kSeqLocalMax = (1u << kSeqRankShift) - 1u;
 constexpr uint32_t kErrTableFull = 1u, kErrBadBlob = 2u, kErrOutOfExtent = 4u;
 constexpr uint32_t kOwnerNever = 0xfffffffeu; // a finder tag that matches no region
 
+// What the march asks about a region before it looks at its tile, in ONE 32-byte sector: the probe of a region
+// (Region::count) brings the owner tag and the tile summaries of both layers along, so the two or three questions a
+// populated region answers cost one trip to L2 or DRAM, and K1's updates of them land in one sector as well.
+struct RegionHead {
+  uint32_t count;     // reg_count
+  uint32_t owner;     // reg_owner
+  uint32_t sum[2][2]; // occ_sum: per layer, which row masks / which column masks of the tile are non-zero
+  uint32_t pad[2];
+};
+static_assert(sizeof(RegionHead) == 32, "RegionHead");
+
 struct GridView {
   int32_t rx0, ry0, nrx, nry;
   double ppm;
-  uint32_t *reg_count;
-  uint32_t *reg_owner;   // n_regions words, then one more: the "owners are stale" flag (launch_owner_rebuild)
+  RegionHead *head;      // n_regions records, then one more whose `owner` is the "owners are stale" flag (launch_owner_rebuild)
   uint32_t n_regions;
   uint32_t *occ[2];
-  uint32_t *occ_sum[2];
   uint32_t *occ_dirty;
   unsigned long long *slots[2];
   uint32_t slot_mask;

@@ -150,7 +150,7 @@ __device__ __forceinline__ void occ_clear(const GridView &g, const CellAddr &c, 
 __device__ __forceinline__ void occ_set(const GridView &g, const CellAddr &c, uint32_t L)
 {
   uint32_t *tile = g.occ[L] + (size_t)c.region * kTileWords;
-  uint32_t *sum = g.occ_sum[L] + (size_t)c.region * 2;
+  uint32_t *sum = g.head[c.region].sum[L];
   atomicOr(tile + c.cy, 1u << c.cx);
   atomicOr(tile + kRegionWidth + c.cx, 1u << c.cy);
   atomicOr(sum, 1u << c.cy);
@@ -171,8 +171,8 @@ __device__ __forceinline__ void cell_remove(const GridView &g, const CellAddr &c
       atomicCAS(slots + h, entry, kSlotTomb);
     h = (h + 1) & g.slot_mask;
   }
-  if (atomicSub(g.reg_count + c.region, 1u) == 1u) // the region's last entry: it belongs to nobody again
-    g.reg_owner[c.region] = kOwnerNone;
+  if (atomicSub(&g.head[c.region].count, 1u) == 1u) // the region's last entry: it belongs to nobody again
+    g.head[c.region].owner = kOwnerNone;
   occ_clear(g, c, L);
 }
 
@@ -216,10 +216,10 @@ __device__ __forceinline__ void cell_insert(const GridView &g, const CellAddr &c
     raise_error(g, kErrTableFull); // the cell transparent and the region count could never return to zero)
     return;
   }
-  atomicAdd(g.reg_count + c.region, 1u);
+  atomicAdd(&g.head[c.region].count, 1u);
   { // region owner: stays a tree's tag only while every entry added belongs to that tree
     const uint32_t tag = (g.blk_rec[0][block].root_flags & kRecRootMask) + 1u;
-    uint32_t *owner = g.reg_owner + c.region;
+    uint32_t *owner = &g.head[c.region].owner;
     uint32_t cur = *reinterpret_cast<volatile uint32_t *>(owner);
     if (cur == kOwnerNone)
       cur = atomicCAS(owner, kOwnerNone, tag);
@@ -300,7 +300,7 @@ __device__ __forceinline__ void k1_table_updates(const GridView &g, const unsign
         if ((g.blk_rec[0][u.block].root_flags ^ u.root_flags) & kRecRootMask) {
           const unsigned long long s0 = g.blk_rec[0][u.block].seq, s1 = g.blk_rec[1][u.block].seq;
           if ((s0 && (s0 >> kSeqEpochShift) != epoch) || (s1 && (s1 >> kSeqEpochShift) != epoch))
-            g.reg_owner[g.n_regions] = 1u;
+            g.head[g.n_regions].owner = 1u;
         }
         for (int L = 0; L < 2; L++) { // z bounds and ownership are per block: both layers see them
           BlockRec *rec = g.blk_rec[L] + u.block;
@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(256) k1_pose_phase0(GridView g, GeomView gv, c
           if ((g.blk_rec[0][u.block].root_flags ^ u.root_flags) & kRecRootMask) {
             const unsigned long long s0 = g.blk_rec[0][u.block].seq, s1 = g.blk_rec[1][u.block].seq;
             if ((s0 && (s0 >> kSeqEpochShift) != epoch) || (s1 && (s1 >> kSeqEpochShift) != epoch))
-              g.reg_owner[g.n_regions] = 1u;
+              g.head[g.n_regions].owner = 1u;
           }
           for (int l = 0; l < 2; l++) {
             BlockRec *rec = g.blk_rec[l] + u.block;
@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(256) k1_summaries(GridView g)
         const uint32_t *tile = g.occ[L] + (size_t)r * kTileWords;
         const uint32_t rows = __ballot_sync(0xffffffffu, tile[lane] != 0u), cols = __ballot_sync(0xffffffffu, tile[kRegionWidth + lane] != 0u);
         if (lane == 0)
-          *reinterpret_cast<uint2 *>(g.occ_sum[L] + (size_t)r * 2) = make_uint2(rows, cols);
+          *reinterpret_cast<uint2 *>(g.head[r].sum[L]) = make_uint2(rows, cols);
       }
     }
   }
@@ -675,15 +675,15 @@ __global__ void __launch_bounds__(256) k1_summaries(GridView g)
 // or attribute updates, and after every gathered pass (other ranks' updates are only known on the device).
 __global__ void __launch_bounds__(256) k1_owner_clear(GridView g)
 {
-  if (!g.reg_owner[g.n_regions])
+  if (!g.head[g.n_regions].owner)
     return;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < g.n_regions; r += gridDim.x * blockDim.x)
-    g.reg_owner[r] = kOwnerNone;
+    g.head[r].owner = kOwnerNone;
 }
 
 __global__ void __launch_bounds__(256) k1_owner_scan(GridView g)
 {
-  if (!g.reg_owner[g.n_regions])
+  if (!g.head[g.n_regions].owner)
     return;
   const uint64_t n = (uint64_t)g.slot_mask + 1u;
   for (uint64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(256) k1_owner_scan(GridView g)
     if (cur == kSlotEmpty || cur == kSlotTomb)
       continue;
     const uint32_t tag = (g.blk_rec[0][(uint32_t)cur - 1u].root_flags & kRecRootMask) + 1u;
-    uint32_t *owner = g.reg_owner + (uint32_t)(cur >> (32 + 2 * kRBits));
+    uint32_t *owner = &g.head[(uint32_t)(cur >> (32 + 2 * kRBits))].owner;
     uint32_t seen = *reinterpret_cast<volatile uint32_t *>(owner);
     if (seen == kOwnerNone)
       seen = atomicCAS(owner, kOwnerNone, tag);
@@ -700,7 +700,7 @@ __global__ void __launch_bounds__(256) k1_owner_scan(GridView g)
   }
 }
 
-__global__ void k1_owner_done(GridView g) { g.reg_owner[g.n_regions] = 0u; }
+__global__ void k1_owner_done(GridView g) { g.head[g.n_regions].owner = 0u; }
 
 // Compaction of one layer's cell-content table: re-insert the live entries into a clean table
 // (tombstones only ever turn into entries again, never into empty slots, so probe chains grow
@@ -791,7 +791,7 @@ __global__ void __launch_bounds__(256) k1_grid_hash(GridView g, unsigned long lo
     n[L]++;
   }
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < g.n_regions; r += gridDim.x * blockDim.x) {
-    const uint32_t c = g.reg_count[r];
+    const uint32_t c = g.head[r].count;
     if (c) {
       const int32_t rx = g.rx0 + (int32_t)(r % (uint32_t)g.nrx), ry = g.ry0 + (int32_t)(r / (uint32_t)g.nrx);
       hc += mix64(mix64(((unsigned long long)(uint32_t)rx << 32) | (uint32_t)ry) ^ ((unsigned long long)c * 0x9e3779b97f4a7c15ull));
@@ -825,18 +825,14 @@ __global__ void __launch_bounds__(256) k1_grow_regions(GridView from, GridView t
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < from.n_regions; r += gridDim.x * blockDim.x) {
     const int32_t rx = from.rx0 + (int32_t)(r % (uint32_t)from.nrx), ry = from.ry0 + (int32_t)(r / (uint32_t)from.nrx);
     const uint32_t rn = (uint32_t)((ry - to.ry0) * to.nrx + (rx - to.rx0));
-    to.reg_count[rn] = from.reg_count[r];
-    to.reg_owner[rn] = from.reg_owner[r];
-    if (from.reg_count[r])
-      for (int L = 0; L < 2; L++) {
+    to.head[rn] = from.head[r];
+    if (from.head[r].count)
+      for (int L = 0; L < 2; L++)
         for (int w = 0; w < kTileWords; w++)
           to.occ[L][(size_t)rn * kTileWords + w] = from.occ[L][(size_t)r * kTileWords + w];
-        to.occ_sum[L][(size_t)rn * 2] = from.occ_sum[L][(size_t)r * 2];
-        to.occ_sum[L][(size_t)rn * 2 + 1] = from.occ_sum[L][(size_t)r * 2 + 1];
-      }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0)
-    to.reg_owner[to.n_regions] = from.reg_owner[from.n_regions]; // the "owners are stale" flag
+    to.head[to.n_regions].owner = from.head[from.n_regions].owner; // the "owners are stale" flag
 }
 
 __global__ void __launch_bounds__(256) k1_grow_rehash(GridView from, GridView to, int L)

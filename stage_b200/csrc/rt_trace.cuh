@@ -101,7 +101,7 @@ __device__ __forceinline__ uint32_t probe_region(const GridView &g, double gx, d
   region = 0;
   if ((uint32_t)rix < (uint32_t)g.nrx && (uint32_t)riy < (uint32_t)g.nry) {
     region = (uint32_t)(riy * g.nrx + rix);
-    return __ldg(g.reg_count + region);
+    return __ldg(&g.head[region].count);
   }
   return 0;
 }
@@ -331,7 +331,7 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
       const int32_t ap0 = (int32_t)((uint32_t)(ymajor ? cy0 : cx0) ^ aflip);
       int32_t cp = cp0, ap = ap0;
       int32_t mdl = -1;
-      const bool own = __ldg(g.reg_owner + region) == finder_tag;
+      const bool own = __ldg(&g.head[region].owner) == finder_tag; // (the probe brought its sector in)
       bool walk_it = true;
       if (n >= 2 * kRegionWidth && (flags & kClosedForms)) {
         // The ray does not end in this region (a region holds at most 2 * 32 - 1 of its cells): where and in which state
@@ -343,7 +343,7 @@ __device__ __forceinline__ void trace_ray(const GridView &g, const FanRec *fan, 
         // path can only be occupied if its row and its column both do.
         bool leave = own;
         if (!own) {
-          const uint2 sum = __ldg(reinterpret_cast<const uint2 *>(layer1 ? g.occ_sum[1] : g.occ_sum[0]) + region);
+          const uint2 sum = __ldg(reinterpret_cast<const uint2 *>(layer1 ? g.head[region].sum[1] : g.head[region].sum[0]));
           uint32_t rs = ymajor ? sum.x : sum.y, cs = ymajor ? sum.y : sum.x; // along the run axis / the cross axis
           rs ^= (rs ^ __brev(rs)) & revmask;
           cs = cflip ? __brev(cs) : cs;
@@ -557,7 +557,7 @@ __device__ __forceinline__ bool ray_step(const GridView &g, RayState &s, int32_t
   const int32_t ap0 = (int32_t)((uint32_t)(ymajor ? cy0 : cx0) ^ aflip);
   int32_t cp = cp0, ap = ap0;
   uint32_t tile = occ_layer + region * kTileWords + (ymajor ? kRegionWidth : 0);
-  const int32_t cp_ahead = __ldg(g.reg_owner + region) != s.finder_tag ? kRegionWidth - 1 : 0;
+  const int32_t cp_ahead = __ldg(&g.head[region].owner) != s.finder_tag ? kRegionWidth - 1 : 0;
   uint32_t word = 0;
   if (cp_ahead)
     word = __ldg(g.occ[0] + (tile | ((uint32_t)cp ^ cflip)));
