@@ -141,6 +141,13 @@ def host_sonar_fans(sensors, poses, rt):
     return fans
 
 
+def outline_cell_visits(boxes):
+    """cell visits World::MapPoly makes for closed 4-point outlines ((n, 4, 2) pixel arrays): |dx| + |dy| per edge. With poses in,
+    the device derives the outlines and the host never counts them: the roofline's numerator is taken from the same boxes."""
+    d = np.abs(np.roll(boxes.astype(np.int64), -1, axis=1) - boxes.astype(np.int64))
+    return int(d.sum())
+
+
 def k1_roofline(edge_steps, blocks_moved, n_pts, k1_ms, peak_gbs):
     """B_blk = 8 n_pts + 16 + 4 (cells unmapped + cells mapped) per moved block"""
     algo = blocks_moved * (8 * n_pts + 16) + 4 * edge_steps
@@ -335,6 +342,8 @@ def run_c4(env, args):
     gathered_targets = tex.host_view([all_t[a:b] for a, b in (multi.shard_bounds(n_total, r, N) for r in range(N))])
     parity = c4_parity(env, ctx, w, poses, T, lo, hi, sensors, ranges_timed, fid_out, fid_cnt, max_per_finder, gathered_targets, last, rt, worldgen)
     k1_ms_avg = kms["deltas_ms"] / steps
+    if poses_in:   # an unmap of the outline of two ticks ago (same layer) and a map of this tick's, for every robot of every rank
+        edge_steps = outline_cell_visits(worldgen.robot_boxes(w, poses[T])) + outline_cell_visits(worldgen.robot_boxes(w, poses[T - 2]))
     rec = {
         "workload": "C4 synthetic: config-3 map (%d rectangles + walls, %dx%d cells), %d robots in total with 0.1 m bodies in the grid, each 16 one-beam "
                     "p2dx sonars (5 m) + a fiducial finder (fov pi, range_max 8, range_max_id 5); robots sharded over %d GPU(s), grid replicated"
@@ -557,6 +566,8 @@ def run_c5(env, args, fov_deg, samples, range_max):
               (n_ob + n_robots, puck_ids, puck_size[2], lambda t: puck_boxes(pposes[t]), n_pucks)]
     parity = laser_parity(env, ctx, w, movers, T, last["fans"], out.ranges, samples, first_puck_id=int(puck_ids[0]))
     k1_avg = k1_ms / steps
+    if poses_in:   # every robot and every puck of every rank: the outline of two ticks ago (same layer) out, this tick's in
+        edge_steps_all = sum(outline_cell_visits(worldgen.robot_boxes(w, rposes[t])) + outline_cell_visits(puck_boxes(pposes[t])) for t in (T, T - 2))
     rec = {
         "workload": "C5 moving-block stress: the config-3 world (%d laser robots per GPU, %d beams each) + %d pucks (0.1 m squares) in total that all "
                     "take a seeded random step every tick, sharded over %d GPU(s): delta export -> all-gather -> K1 on every replica, then the lasers scan"

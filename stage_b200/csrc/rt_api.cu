@@ -2739,27 +2739,20 @@ static int fiducials_submit_impl(stg_rt_ctx *c, uint32_t n_targets, const stg_rt
       (rc = pin_reserve(c, c->h_fid_count, b_cnt)) || (rc = dev_reserve(c, c->d_fid_count, b_cnt)))
     return rc;
   char *hp = (char *)c->h_fid_in.p;
-  if (b_t)
-    memcpy(hp, targets, b_t);
-  memcpy(hp + b_t, finders, b_f);
-  FanRec *fans = (FanRec *)(hp + b_t + b_f);
-  for (uint32_t i = 0; i < n_finders; i++) { // the line-of-sight ray of AddModelIfVisible (model_fiducial.cc:179)
-    FanRec &r = fans[i];
-    memset(&r, 0, sizeof(r));
-    r.finder = finders[i].finder;
-    r.n_samples = 1;
-    r.pred = STG_RT_PRED_UNRELATED;
-    r.ztest = 1;
-    r.layer = finders[i].layer;
-    r.angles = STG_RT_ANGLES_EXPLICIT;
-    r.ox = finders[i].ox;
-    r.oy = finders[i].oy;
-    r.oz = finders[i].oz;
-    r.oa = finders[i].oa;
-    r.range = finders[i].max_range_anon;
-  }
-  CU(c, cudaMemcpyAsync(c->d_fid_in.p, hp, b_in, cudaMemcpyHostToDevice, c->stream));
-  c->stats.h2d_bytes += b_in;
+  // staged by the host threads side by side (100,000 finders are 10 MB; one core copies them in a millisecond)
+  // (inline when they are busy expanding the intensities of a march still running)
+  c->pool.parallel_for(b_t + b_f, c->pool.busy() ? b_t + b_f + 1 : (size_t)1 << 20, [hp, targets, finders, b_t](size_t lo, size_t hi) {
+    if (lo < b_t)
+      memcpy(hp + lo, (const char *)targets + lo, std::min(hi, b_t) - lo);
+    if (hi > b_t) {
+      const size_t from = std::max(lo, b_t);
+      memcpy(hp + from, (const char *)finders + (from - b_t), hi - from);
+    }
+  });
+  CU(c, cudaMemcpyAsync(c->d_fid_in.p, hp, b_t + b_f, cudaMemcpyHostToDevice, c->stream));
+  launch_fid_fans((const FidFinderRec *)((char *)c->d_fid_in.p + b_t), (FanRec *)((char *)c->d_fid_in.p + b_t + b_f), n_finders, c->stream);
+  c->stats.launches_post++;
+  c->stats.h2d_bytes += b_t + b_f;
   FidBatchView v;
   v.n_targets = n_targets;
   v.n_finders = n_finders;
@@ -2770,7 +2763,7 @@ static int fiducials_submit_impl(stg_rt_ctx *c, uint32_t n_targets, const stg_rt
   v.out = (FiducialRec *)c->d_fid_out.p;
   v.out_count = (uint32_t *)c->d_fid_count.p;
   // Candidate query: brute force over the target list for small problems, a per-submit uniform grid
-  // (bins as wide as the longest detection range) beyond ~4 M finder x target pairs.
+  // (bins a quarter of the longest detection range wide) beyond ~4 M finder x target pairs.
   // STG_RT_FID_GRID=0/1 forces one or the other (tests compare the two).
   CU(c, cudaEventRecord(c->t_ev[3][0], c->stream));
   const char *force = getenv("STG_RT_FID_GRID");
@@ -2793,6 +2786,7 @@ static int fiducials_submit_impl(stg_rt_ctx *c, uint32_t n_targets, const stg_rt
       cell = std::max(cell, finders[i].max_range_anon);
     if (!(cell > 0))
       cell = 1.0;
+    cell /= 4; // a finder's window is at most 9 rows of bins; each row is sifted only where it meets the finder's (half) disc
     while ((x1 - x0) / cell * ((y1 - y0) / cell) > 4.0e6) // keep the bin table small
       cell *= 2;
     FidGridView gv;

@@ -413,6 +413,7 @@ struct BlobBatchView {
 
 void launch_fiducials(const GridView &g, const FidBatchView &b, void *stream);
 void launch_fiducials_grid(const GridView &g, const FidBatchView &b, const FidGridView &v, void *stream);
+void launch_fid_fans(const FidFinderRec *finders, FanRec *fans, uint32_t n, void *stream);
 void launch_fid_pack(const FidBatchView &b, uint32_t *offsets, void *packed_host, uint32_t *count_host, void *stream);
 void launch_blobs(const GridView &g, const BlobBatchView &b, void *stream);
 void launch_debug_trig(uint64_t n, const double *x, double *cs, void *stream);

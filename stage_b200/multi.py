@@ -94,6 +94,7 @@ class TargetExchange:
         self.count = torch.zeros(1, dtype=torch.int64, device=device)
         self.counts = torch.zeros(world_size, dtype=torch.int64, device=device)
         self.bytes_sent = 0
+        self._staged = -1   # how many records the staging buffer's padding was laid out for
 
     def step_device(self, my_targets, ctx=None):
         """my_targets: this rank's records -> (device pointer, n_records) of the world's, rank after rank, each rank's slot
@@ -104,15 +105,17 @@ class TargetExchange:
         n = len(my_targets)
         if n > self.cap:
             raise ValueError("%d target records exceed the exchange slot of %d" % (n, self.cap))
-        host = self.stage.numpy().view(self.dtype)
-        host[:n] = my_targets
-        host[n:] = self.pad[n:]
-        self.mine.copy_(self.stage, non_blocking=True)
-        self.bytes_sent += n * self.dtype.itemsize
+        # bytes, not records: numpy assigns structured arrays field by field (4 ms for 100,000 records against 0.7 ms)
+        host, size = self.stage.numpy(), self.dtype.itemsize
+        host[:n * size] = my_targets.view(np.uint8).reshape(-1)
+        if n != self._staged:   # the slot's tail beyond this rank's records: padding (written again only when the count changes)
+            host[n * size:] = self.pad.view(np.uint8).reshape(-1)[n * size:]
+            self._staged = n
+        dst = self.mine if self.world_size > 1 else self.all   # alone, the slot is the whole array
+        dst.copy_(self.stage, non_blocking=True)
+        self.bytes_sent += n * size
         if self.world_size > 1:
             self.dist.all_gather_into_tensor(self.all, self.mine)
-        else:
-            self.all.copy_(self.mine)
         if ctx is not None and self.all.device.type == "cuda":
             ctx.stream_wait(torch.cuda.current_stream(self.all.device).cuda_stream)
         return self.all.data_ptr(), self.world_size * self.cap
