@@ -38,26 +38,30 @@ namespace {
 
 thread_local std::string g_create_error;
 
-struct BlockShadow {
+// What the host remembers of a block. The scalars come first and fit two cache lines: a tick that moves 100,000 bodies by
+// pose walks these records four times (queue, sort check, size, write) and, laid out this way, never touches the vectors
+// behind them (vec_used says whether any of a layer's four may hold something).
+struct alignas(64) BlockShadow {
   bool known = false;
-  uint32_t model = 0;
-  double zmin = 0, zmax = 0;
   bool z_dirty = false;
   // what the caller last said (host_*) and what the device grid currently holds (dev_*)
   bool host_mapped[2] = { false, false }, dev_mapped[2] = { false, false }, dirty[2] = { false, false };
+  bool keep_seq[2] = { false, false }; // re-map of a block the device already holds: its place in the cell lists stays
+  // pose path (stg_rt_models_pose_update): the outline is derived on the device from the block's registered polygon
+  bool pose_pending[2] = { false, false }; // the queued Map of this layer is a pose, not an outline
+  bool dev_owned[2] = { false, false };    // the device rendered the outline it holds itself (GeomView::pix); dev_xy is empty
+  bool vec_used[2] = { false, false };     // host_xy / host_poly / dev_xy / dev_poly of the layer may be non-empty
+  uint32_t model = 0;
   uint32_t map_seq[2] = { 0, 0 };
   uint32_t host_steps[2] = { 0, 0 }, dev_steps[2] = { 0, 0 }; // cell visits of host_xy / dev_xy (all renderings)
+  double zmin = 0, zmax = 0;
+  double pose[2][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 } };
   std::vector<int32_t> host_xy[2], dev_xy[2];
   // Block::Map on a block that is already mapped renders it once more (block.cc:170-181 does not check; the
   // reference's world loader does it to bumper models): the cells get duplicate entries, Region::count counts them,
   // UnMap removes them all. Then the outline is several polygons back to back and these hold the points of each
   // (empty = one polygon, the normal case).
   std::vector<uint32_t> host_poly[2], dev_poly[2];
-  bool keep_seq[2] = { false, false }; // re-map of a block the device already holds: its place in the cell lists stays
-  // pose path (stg_rt_models_pose_update): the outline is derived on the device from the block's registered polygon
-  bool pose_pending[2] = { false, false }; // the queued Map of this layer is a pose, not an outline
-  bool dev_owned[2] = { false, false };    // the device rendered the outline it holds itself (GeomView::pix); dev_xy is empty
-  double pose[2][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 } };
 };
 
 struct GeomShadow { // stg_rt_block_define: host copy of BlockGeom plus what the host needs to reason without the pixels
@@ -260,6 +264,8 @@ struct stg_rt_ctx {
 
   std::vector<BlockShadow> blocks;
   std::vector<uint32_t> dirty_units; // block*2 + layer, in order of first touch
+  bool units_in_order = true;        // ... which so far is also ascending order of sort_units' key (touch_unit)
+  uint32_t last_unit_key = 0;
   std::vector<ModelUpd> model_upd;
   std::vector<bool> model_known;
   std::vector<ModelUpd> models;          // host copy of the model table
@@ -500,6 +506,8 @@ void sort_units(stg_rt_ctx *c)
     return b.host_mapped[u & 1] ? b.map_seq[u & 1] : 0u;
   };
   auto less = [&key](uint32_t a, uint32_t b) { return key(a) < key(b); };
+  if (c->units_in_order) // queued in ascending key order (touch_unit kept track): nothing to do, nothing to read
+    return;
   if (!std::is_sorted(c->dirty_units.begin(), c->dirty_units.end(), less)) // usually already in Map-call order
     std::stable_sort(c->dirty_units.begin(), c->dirty_units.end(), less);
 }
@@ -664,8 +672,12 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
     if (bytes > c->blob_cap)
       return fail(c, STG_RT_ENOMEM, "model / block attribute updates exceed the delta buffer");
     int64_t d_live[2] = { 0, 0 }; // net change of rendered cell visits per layer, known before anything is touched
-    while (end_unit < c->dirty_units.size()) {
-      const uint32_t u = c->dirty_units[end_unit];
+    // what one unit adds to the blob and to the tables
+    struct UnitTally {
+      size_t bytes = 0, n_rem = 0, n_ins = 0, n_pose = 0, n_bupd = 0, max_edges = 0;
+      int64_t d_live[2] = { 0, 0 };
+    };
+    auto tally_unit = [c](uint32_t u, UnitTally &t) {
       const BlockShadow &b = c->blocks[u >> 1];
       const int L = u & 1;
       // the outline the device holds goes out through edge records when the host rendered it, through a pose record
@@ -674,18 +686,55 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
       const bool new_by_edges = b.host_mapped[L] && !b.pose_pending[L];
       const size_t re = (b.dev_mapped[L] && !b.dev_owned[L]) ? b.dev_xy[L].size() / 2 : 0, ie = new_by_edges ? b.host_xy[L].size() / 2 : 0;
       const size_t pr = (old_by_dev || new_by_pose) ? 1 : 0;
-      const size_t add = (re + ie) * sizeof(EdgeRec) + (new_by_edges ? sizeof(BlockUpd) : 0) + pr * sizeof(PoseUpd);
-      if (bytes + add > c->blob_cap) {
+      t.bytes += (re + ie) * sizeof(EdgeRec) + (new_by_edges ? sizeof(BlockUpd) : 0) + pr * sizeof(PoseUpd);
+      t.n_rem += re;
+      t.n_ins += ie;
+      t.n_pose += pr;
+      t.n_bupd += new_by_edges ? 1 : 0;
+      t.max_edges = re + ie;
+      t.d_live[L] += (b.host_mapped[L] ? (int64_t)b.host_steps[L] : 0) - (b.dev_mapped[L] ? (int64_t)b.dev_steps[L] : 0);
+    };
+    // A tick that moves a swarm queues 100,000 units: the host threads tally them side by side, in kUnitChunks stretches
+    // (pass 2 writes the same stretches side by side when there is nothing but pose records in them). If the whole
+    // queue fits this blob - the usual case - that is the sizing; otherwise unit by unit up to the one that does not fit.
+    constexpr size_t kUnitChunks = 32;
+    UnitTally chunk_tally[kUnitChunks];
+    bool chunked = false;
+    const size_t n_queued = c->dirty_units.size() - unit;
+    if (n_queued >= 8192 && !c->pool.busy()) {
+      const uint32_t *units = c->dirty_units.data() + unit;
+      c->pool.parallel_for(kUnitChunks, 1, [&](size_t k0, size_t k1) {
+        for (size_t k = k0; k < k1; k++)
+          for (size_t i = k * n_queued / kUnitChunks, e = (k + 1) * n_queued / kUnitChunks; i < e; i++)
+            tally_unit(units[i], chunk_tally[k]);
+      });
+      UnitTally all;
+      for (const UnitTally &t : chunk_tally) {
+        all.bytes += t.bytes; all.n_rem += t.n_rem; all.n_ins += t.n_ins; all.n_pose += t.n_pose; all.n_bupd += t.n_bupd;
+        all.d_live[0] += t.d_live[0]; all.d_live[1] += t.d_live[1];
+      }
+      if (bytes + all.bytes <= c->blob_cap) {
+        chunked = true;
+        bytes += all.bytes; n_rem += all.n_rem; n_ins += all.n_ins; n_pose += all.n_pose; n_bupd += all.n_bupd;
+        d_live[0] += all.d_live[0]; d_live[1] += all.d_live[1];
+        end_unit = c->dirty_units.size();
+      }
+    }
+    while (!chunked && end_unit < c->dirty_units.size()) {
+      UnitTally t;
+      tally_unit(c->dirty_units[end_unit], t);
+      if (bytes + t.bytes > c->blob_cap) {
         if (end_unit == unit)
-          return fail(c, STG_RT_ENOMEM, "one block's outline (%zu edges) exceeds the delta buffer", re + ie);
+          return fail(c, STG_RT_ENOMEM, "one block's outline (%zu edges) exceeds the delta buffer", t.max_edges);
         break;
       }
-      bytes += add;
-      n_rem += re;
-      n_ins += ie;
-      n_pose += pr;
-      n_bupd += new_by_edges ? 1 : 0;
-      d_live[L] += (b.host_mapped[L] ? (int64_t)b.host_steps[L] : 0) - (b.dev_mapped[L] ? (int64_t)b.dev_steps[L] : 0);
+      bytes += t.bytes;
+      n_rem += t.n_rem;
+      n_ins += t.n_ins;
+      n_pose += t.n_pose;
+      n_bupd += t.n_bupd;
+      d_live[0] += t.d_live[0];
+      d_live[1] += t.d_live[1];
       end_unit++;
     }
     if (!apply && end_unit < c->dirty_units.size())
@@ -721,8 +770,9 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
     }
     uint32_t rem_cursor = 0, ins_cursor = 0;
     int64_t ins_round[2] = { 0, 0 }, rem_round[2] = { 0, 0 };
-    for (; unit < end_unit; unit++) {
-      const uint32_t u = c->dirty_units[unit];
+    // one unit: its records, and the shadow brought to "the device holds what the caller last said"
+    auto write_unit = [c, &rem, &ins](uint32_t u, PoseUpd *&pupd, BlockUpd *&bupd, uint32_t &rem_cursor, uint32_t &ins_cursor, int64_t *est_rem,
+                                   int64_t *est_ins, int64_t *rem_round, int64_t *ins_round) {
       BlockShadow &b = c->blocks[u >> 1];
       const int L = u & 1;
       const bool old_by_dev = b.dev_mapped[L] && b.dev_owned[L], new_by_pose = b.host_mapped[L] && b.pose_pending[L];
@@ -745,15 +795,18 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
       if (b.dev_mapped[L] && !b.dev_owned[L]) // an outline the host rendered leaves through edge records, whatever replaces it
         rem_round[L] += emit_edges(b.dev_xy[L], u >> 1, L, rem_cursor, rem, &b.dev_poly[L]);
       if (new_by_pose) { // the device renders it: nothing of the outline is known here
-        b.dev_xy[L].clear();
-        b.dev_poly[L].clear();
+        if (b.vec_used[L]) { // (the host-side pair was emptied when the pose was queued)
+          b.dev_xy[L].clear();
+          b.dev_poly[L].clear();
+          b.vec_used[L] = false;
+        }
         b.dev_steps[L] = b.host_steps[L];
         b.dev_mapped[L] = true;
         b.dev_owned[L] = true;
         b.pose_pending[L] = false;
         b.keep_seq[L] = false;
         b.dirty[L] = false;
-        continue;
+        return;
       }
       b.dev_owned[L] = false;
       if (b.host_mapped[L]) {
@@ -771,6 +824,7 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
         b.keep_seq[L] = false;
         b.dev_xy[L].swap(b.host_xy[L]); // host_xy is rewritten by the next Map before it is read again
         b.dev_poly[L].swap(b.host_poly[L]);
+        b.vec_used[L] = true;
         b.dev_steps[L] = b.host_steps[L];
       } else {
         b.dev_xy[L].clear();
@@ -779,7 +833,35 @@ int build_and_send_deltas(stg_rt_ctx *c, bool apply, int rank, size_t *out_bytes
       }
       b.dev_mapped[L] = b.host_mapped[L];
       b.dirty[L] = false;
+    };
+    if (chunked && n_rem == 0 && n_ins == 0 && n_bupd == attr_blocks.size() && !c->pool.busy()) {
+      // nothing but pose records (no unit emits an edge or a block update, so the cursors those share stay untouched):
+      // stretch k's records start where the stretches before it end
+      size_t first_pose[kUnitChunks + 1];
+      first_pose[0] = 0;
+      for (size_t k = 0; k < kUnitChunks; k++)
+        first_pose[k + 1] = first_pose[k] + chunk_tally[k].n_pose;
+      int64_t part_rem[kUnitChunks][2] = {}, part_ins[kUnitChunks][2] = {};
+      const uint32_t *units = c->dirty_units.data() + unit;
+      c->pool.parallel_for(kUnitChunks, 1, [&](size_t k0, size_t k1) {
+        for (size_t k = k0; k < k1; k++) {
+          PoseUpd *p = pupd + first_pose[k];
+          BlockUpd *none = nullptr;
+          uint32_t cur_r = 0, cur_i = 0;
+          int64_t rr[2] = { 0, 0 }, ir[2] = { 0, 0 };
+          for (size_t i = k * n_queued / kUnitChunks, e = (k + 1) * n_queued / kUnitChunks; i < e; i++)
+            write_unit(units[i], p, none, cur_r, cur_i, part_rem[k], part_ins[k], rr, ir);
+        }
+      });
+      for (size_t k = 0; k < kUnitChunks; k++)
+        for (int L = 0; L < 2; L++) {
+          est_rem[L] += part_rem[k][L];
+          est_ins[L] += part_ins[k][L];
+        }
+      unit = end_unit;
     }
+    for (; unit < end_unit; unit++)
+      write_unit(c->dirty_units[unit], pupd, bupd, rem_cursor, ins_cursor, est_rem, est_ins, rem_round, ins_round);
     if (n_model)
       memcpy(mupd, c->model_upd.data(), n_model * sizeof(ModelUpd));
     memset(hdr, 0, sizeof(*hdr));
@@ -1044,7 +1126,14 @@ int deliver_post_locked(stg_rt_ctx *c)
     if (c->fid_job.packed_capacity) { // the caller takes them as they are: finder f's records follow finder f-1's
       for (uint32_t f = 0; f < c->fid_job.n_finders; f++)
         at += std::min(cnt[f], c->fid_job.max_per_finder);
-      memcpy(user, packed, std::min<size_t>(at, c->fid_job.packed_capacity) * sizeof(FiducialRec));
+      // (config 4: 65 MB of records per tick - 4.5 ms for one core, so the host threads share the copy; a streamed
+      // expansion still open on them belongs to a march that ended before these records were made: it is closed first)
+      if (c->pool.busy())
+        c->pool.finish();
+      const size_t bytes = std::min<size_t>(at, c->fid_job.packed_capacity) * sizeof(FiducialRec);
+      char *dst = (char *)user;
+      const char *src = (const char *)packed;
+      c->pool.parallel_for(bytes, (size_t)2 << 20, [dst, src](size_t lo, size_t hi) { memcpy(dst + lo, src + lo, hi - lo); });
     } else {
       for (uint32_t f = 0; f < c->fid_job.n_finders; f++) {
         const uint32_t k = std::min(cnt[f], c->fid_job.max_per_finder);
@@ -1389,9 +1478,17 @@ int device_errors_locked(stg_rt_ctx *c)
 void touch_unit(stg_rt_ctx *c, uint32_t block, int layer)
 {
   BlockShadow &b = c->blocks[block];
+  const uint32_t key = b.host_mapped[layer] ? b.map_seq[layer] : 0u; // sort_units' key, as the caller has just set it
   if (!b.dirty[layer]) {
     b.dirty[layer] = true;
+    if (c->dirty_units.empty())
+      c->units_in_order = true;
+    else if (key < c->last_unit_key)
+      c->units_in_order = false;
+    c->last_unit_key = key;
     c->dirty_units.push_back(block * 2 + (uint32_t)layer);
+  } else {
+    c->units_in_order = false; // a queued unit's key changed where it stands
   }
 }
 
@@ -1639,6 +1736,7 @@ static int fetch_outline_locked(stg_rt_ctx *c, uint32_t block_id, int layer)
   if (!b.dev_mapped[layer] || !b.dev_owned[layer])
     return STG_RT_OK;
   const GeomShadow &g = c->geom[block_id];
+  b.vec_used[layer] = true;
   b.dev_xy[layer].resize(2 * (size_t)g.n_pts);
   CU(c, cudaMemcpyAsync(b.dev_xy[layer].data(), (const int32_t *)c->d_pix[layer].p + 2 * (size_t)g.first_pt, (size_t)g.n_pts * 8,
                         cudaMemcpyDeviceToHost, c->stream));
@@ -1807,6 +1905,70 @@ int stg_rt_models_pose_update(stg_rt_ctx *c, uint32_t n, const uint32_t *models,
     return STG_RT_EINVAL;
   std::lock_guard<std::mutex> lk(c->mu);
   const double t_prof = prof_now(c);
+  // A swarm's tick: many models of one block each, in ascending id order, well inside the extent, none of them queued yet,
+  // no fans waiting for the grid as it was. The host threads first make sure of all that side by side, then queue the
+  // poses side by side (model i's Map gets sequence number local_seq + i + 1 and unit number queue length + i, as the
+  // loop below would give them). Anything else takes the loop.
+  if (n >= 8192 && c->q_subs.empty() && (uint64_t)c->local_seq + n < kSeqLocalMax && !c->pool.busy()) {
+    std::atomic<bool> plain{ true };
+    const double ppm = c->cfg.ppm;
+    c->pool.parallel_for(n, 4096, [&](size_t lo, size_t hi) {
+      for (size_t i = lo; i < hi; i++) {
+        const uint32_t m = models[i];
+        if ((i && models[i - 1] >= m) || m >= c->model_blocks.size() || c->model_blocks[m].size() != 1) {
+          plain.store(false, std::memory_order_relaxed);
+          return;
+        }
+        const uint32_t block_id = c->model_blocks[m][0];
+        const GeomShadow &g = c->geom[block_id];
+        const double *P = gpose_xyza + 4 * i, reach = (g.radius + 2.0 / ppm) * ppm;
+        if (!(P[0] * ppm - reach >= c->cell_x0 && P[0] * ppm + reach <= c->cell_x1 + 1 && P[1] * ppm - reach >= c->cell_y0 &&
+              P[1] * ppm + reach <= c->cell_y1 + 1) || c->blocks[block_id].dirty[layer]) {
+          plain.store(false, std::memory_order_relaxed);
+          return;
+        }
+      }
+    });
+    if (plain.load()) {
+      const uint32_t seq0 = c->local_seq;
+      const size_t unit0 = c->dirty_units.size();
+      if (unit0 == 0)
+        c->units_in_order = true;
+      else if (seq0 + 1 < c->last_unit_key)
+        c->units_in_order = false;
+      c->dirty_units.resize(unit0 + n);
+      uint32_t *units = c->dirty_units.data() + unit0;
+      c->pool.parallel_for(n, 4096, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+          const uint32_t block_id = c->model_blocks[models[i]][0];
+          const GeomShadow &g = c->geom[block_id];
+          const double *P = gpose_xyza + 4 * i;
+          BlockShadow &b = c->blocks[block_id];
+          b.zmin = g.zmin + P[2];
+          b.zmax = g.zmax + P[2];
+          b.host_mapped[layer] = true;
+          b.pose_pending[layer] = true;
+          memcpy(b.pose[layer], P, 4 * sizeof(double));
+          b.host_steps[layer] = g.est_steps;
+          if (b.vec_used[layer]) {
+            b.host_xy[layer].clear();
+            b.host_poly[layer].clear();
+          }
+          b.keep_seq[layer] = false;
+          b.map_seq[layer] = seq0 + (uint32_t)i + 1u;
+          b.dirty[layer] = true;
+          units[i] = block_id * 2 + (uint32_t)layer;
+        }
+      });
+      c->local_seq = seq0 + n;
+      c->last_unit_key = seq0 + n;
+      c->stats.map_calls += n;
+      c->stats.unmap_calls += n;
+      if (c->prof_on)
+        c->prof_us[6] += prof_now(c) - t_prof;
+      return STG_RT_OK;
+    }
+  }
   for (uint32_t i = 0; i < n; i++) {
     const uint32_t m = models[i];
     if (m >= c->model_blocks.size() || c->model_blocks[m].empty())
@@ -1855,8 +2017,10 @@ int stg_rt_models_pose_update(stg_rt_ctx *c, uint32_t n, const uint32_t *models,
       b.pose_pending[layer] = true;
       memcpy(b.pose[layer], P, 4 * sizeof(double));
       b.host_steps[layer] = g.est_steps;
-      b.host_xy[layer].clear();
-      b.host_poly[layer].clear();
+      if (b.vec_used[layer]) {
+        b.host_xy[layer].clear();
+        b.host_poly[layer].clear();
+      }
       b.keep_seq[layer] = false;
       b.map_seq[layer] = ++c->local_seq;
       touch_unit(c, block_id, layer);
@@ -1965,6 +2129,7 @@ static int block_map_locked(stg_rt_ctx *c, uint32_t block_id, uint32_t model_id,
       return rc;
   }
   b.pose_pending[layer] = false;
+  b.vec_used[layer] = true;
   if (b.known && b.model != model_id)
     c->block_reassigned = true; // what is still rendered of it on the other layer changes owner too
   b.known = true;
