@@ -278,7 +278,7 @@ def kernel_source_digest():
     """what the committed ncu capture of the march kernel is tied to: the sources the kernel is compiled from"""
     import hashlib
     h = hashlib.sha256()
-    for f in ("rt_trace.cuh", "rt_march.cu", "rt_device.h", "rt_libm.cuh"):
+    for f in ("rt_trace.cuh", "rt_walk.h", "rt_march.cu", "rt_device.h", "rt_libm.cuh"):
         h.update(open(os.path.join(ROOT, "stage_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]
 

@@ -536,3 +536,42 @@ def test_the_world_grows_when_something_is_rendered_outside_it():
     p.ctx.sync()
     assert hit.tolist() == [p.t1.test_collision(0, [1]), p.t1.test_collision(0, [2])]
     p.ctx.close()
+
+
+def test_closed_form_region_walks_and_their_fallback():
+    """The march leaves a populated region in closed form when nothing on the ray's path can stop it (the region holds only
+    the finder's own tree, or its tile's summary words say the occupied rows / columns lie elsewhere) and otherwise starts
+    the walk at the first row and column that can hold a hit (rt_walk.h). Same hit, same range bits, same cell and
+    CELL-VISIT / REGION-PROBE COUNTERS as the oracle's cell-by-cell loop: from inside a two-model robot that spans four
+    regions, past thin walls on every side (single rows and columns of cells, diagonals, an L whose corner the rays
+    graze), on both layers with the robot re-rendered in between - and with rays far longer than the closed forms serve
+    (2 * 10^7 cells along the major axis), which take the step-by-step walk through the same regions."""
+    p = Pair(sregs=(-1, -1, 2, 2))
+    p.model(1, 1, 0.5)                       # walls
+    p.model(2, 2)                            # robot body (finder's tree) ...
+    p.model(3, 2)                            # ... and its child
+    walls = [box(200, -300, 201, 300), box(-300, 200, 300, 201), box(-260, -300, -259, 300), box(-300, -230, 300, -229),
+             np.array([[90, 90], [140, 140], [141, 140], [91, 90]], np.int32),           # a diagonal sliver
+             np.array([[-150, 60], [-100, 60], [-100, 110], [-101, 110], [-101, 61], [-150, 61]], np.int32)]  # an L
+    for k, w in enumerate(walls):
+        for layer in (0, 1):
+            p.map(k, 1, layer, (0.0, 1.0), w)
+    rng_ = np.random.RandomState(5)
+    heads = np.concatenate([np.linspace(-np.pi, np.pi, 1441), rng_.uniform(-np.pi, np.pi, 600),
+                            [0.0, np.pi / 2, -np.pi / 2, np.pi, np.pi / 4, 3 * np.pi / 4, 1e-9, np.pi / 2 + 1e-9]])
+    for step, (cx, cy) in enumerate(((31, 31), (-33, 30), (2, -64), (-1, -1), (63, 0))):   # the robot straddles region borders
+        layer = step % 2
+        if step >= 2:   # Map on a mapped block would render it once more on top
+            p.unmap(10, layer)
+            p.unmap(11, layer)
+        p.map(10, 2, layer, (0.0, 0.6), box(cx - 11, cy - 9, cx + 11, cy + 9))
+        p.map(11, 3, layer, (0.2, 0.8), box(cx - 3, cy - 3, cx + 3, cy + 3))
+        p.grids_equal()
+        origin = [(cx + 0.37) / 50.0, (cy + 0.41) / 50.0]
+        for finder in (2, 3):
+            for r in (0.3, 2.0, 9.0, 30.0):
+                p.rays(finder, origin, heads, r, layer=layer)
+            p.rays(finder, origin, heads[::7], 9.0, layer=layer, pred=rt.PRED_GRIPPER)    # no owner shortcut for this predicate
+        p.rays(1, [1.0, -2.0], heads, 30.0, layer=layer)                                   # a wall's own rays: the robot is in the way
+        p.rays(2, origin, heads[::40], 4.0e5, layer=layer)                                 # 2 * 10^7 cells: beyond the closed forms
+    p.ctx.close()
