@@ -249,3 +249,49 @@ def test_pose_deltas_cross_the_rank_exchange():
     assert sent == 2 * n * (4 * 32 + 48) + 3 * n * 48 + 5 * n_ranks * 96
     for ctx in ctxs:
         ctx.close()
+
+
+def test_bulk_pose_update_on_the_host_threads_equals_the_loop():
+    """A swarm's pose update (>= 8192 models of one block each, ascending ids, nothing queued) is checked, queued, sized and
+    written by the library's host threads side by side; fewer models per call take the one-by-one loop. The same grid either
+    way, tick after tick on alternating layers - the digest (entries, their order in every cell, region counts), outlines,
+    bytes uploaded - and the same as a third context that is handed the ids in descending order (the loop again; other
+    sequence numbers, so only entries and counts are compared there)."""
+    w = worldgen.make_swarm_world(seed=4, n_rects=100, n_robots=9000, half_extent_m=20.48)
+    ext = w.sreg_extent()
+    n_ob, n = len(w.obstacles), len(w.robots)
+    mk = lambda: rt.Context(w.ppm, *ext, max_models=w.n_models + 1, max_blocks=n_ob + n, max_cell_entries=1 << 21)
+    a, b, c = mk(), mk(), mk()
+    for ctx in (a, b, c):
+        worldgen.load_swarm_into_context(ctx, w)
+        worldgen.define_boxes(ctx, n_ob, w.robot_ids, w.robot_size)
+    poses = w.robots.copy()
+    half = n // 2
+    back = np.arange(n - 1, -1, -1)
+    for t in range(1, 6):
+        poses = worldgen.step_robots(w, poses, t, speed_m=0.05)
+        layer, gp = t % 2, worldgen.gposes(poses)
+        sa, sb = a.stats(), b.stats()
+        a.models_pose_update(w.robot_ids, gp, layer)
+        b.models_pose_update(w.robot_ids[:half], gp[:half], layer)
+        b.models_pose_update(w.robot_ids[half:], gp[half:], layer)
+        c.models_pose_update(w.robot_ids[back], np.ascontiguousarray(gp[back]), layer)
+        for ctx in (a, b, c):
+            ctx.sync()
+        if t >= 3:   # (the first Map of a layer also takes the load-time outline out through edge records)
+            assert a.stats()["h2d_bytes"] - sa["h2d_bytes"] == b.stats()["h2d_bytes"] - sb["h2d_bytes"] == 96 + 48 * n
+        boxes = worldgen.robot_boxes(w, poses)
+        for j in (0, 1, half - 1, half, n - 1):
+            assert np.array_equal(a.block_outline(n_ob + j, layer), boxes[j]) and np.array_equal(b.block_outline(n_ob + j, layer), boxes[j])
+        assert a.grid_hash() == b.grid_hash()
+    ha, hc = a.grid_hash(), c.grid_hash()
+    assert ha[1] == hc[1] and ha[2] == hc[2]
+    rec_a, cnt_a = a.grid_dump()
+    rec_c, cnt_c = c.grid_dump()
+    assert np.array_equal(oracle_lib.entry_multiset(rec_a), oracle_lib.entry_multiset(rec_c))
+    assert np.array_equal(oracle_lib.sort_counts(cnt_a), oracle_lib.sort_counts(cnt_c))
+    fans = worldgen.ranger_fans(w, layer=1, samples=64, range_max=6.0, robots=poses[:300], robot_ids=w.robot_ids[:300])
+    ga, gb = a.trace(fans), b.trace(fans)
+    assert np.array_equal(ga.ranges.view(np.uint64), gb.ranges.view(np.uint64)) and np.array_equal(ga.hit_model, gb.hit_model)
+    for ctx in (a, b, c):
+        ctx.close()
