@@ -592,6 +592,7 @@ int upload_geometry_locked(stg_rt_ctx *c)
     recs[b].first_pt = g.first_pt;
     recs[b].n_pts = g.defined ? g.n_pts : 0;
     recs[b].model = g.model;
+    recs[b].est_steps = g.est_steps;
     recs[b].zmin = g.zmin;
     recs[b].zmax = g.zmax;
   }

@@ -166,7 +166,7 @@ constexpr uint32_t kPoseNoInsert = 0x200u;  // UnMap only
 // holds it after BlockGroup::CalcSize (blockgroup.cc:84-112) and Block::local_z.
 struct BlockGeom {
   uint32_t first_pt, n_pts; // into GeomView::pts / pix (2 values per point)
-  uint32_t model, pad;
+  uint32_t model, est_steps; // est_steps: upper estimate of the outline's cell visits at any pose (how many warps its rounds of 32 can use)
   double zmin, zmax;
 };
 static_assert(sizeof(BlockGeom) == 32, "BlockGeom");

@@ -446,8 +446,11 @@ __device__ __forceinline__ void k1_pose_prefix(const GridView &g, const unsigned
 // out over the lanes of the warp. Outlines of up to 32 vertices (every robot body) are one index space: lane i holds
 // edge i's step count, a warp scan turns them into offsets, and visit s of the outline goes to lane s % 32 - a 0.1 m
 // puck (20 visits) or a 0.44 x 0.38 m robot (82) is done in one to three rounds instead of one round per edge.
+// part / n_parts: the rounds of 32 visits are dealt out to n_parts warps that share the outline (round r goes to warp
+// r % n_parts), so that a robot's three rounds are three dependent chains side by side instead of one after the other.
 template <class Op>
-__device__ __forceinline__ void outline_cells(const GridView &g, const int32_t *pix, uint32_t n_pts, uint32_t lane, Op op)
+__device__ __forceinline__ void outline_cells(const GridView &g, const int32_t *pix, uint32_t n_pts, uint32_t lane, Op op, uint32_t part = 0,
+                                              uint32_t n_parts = 1)
 {
   if (n_pts <= 32) {
     int32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
@@ -469,7 +472,7 @@ __device__ __forceinline__ void outline_cells(const GridView &g, const int32_t *
         incl += up;
     }
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    for (uint32_t s0 = 0; s0 < total; s0 += 32) {
+    for (uint32_t s0 = 32 * part; s0 < total; s0 += 32 * n_parts) {
       const uint32_t s = s0 + lane;
       // which edge holds visit s: the first lane whose inclusive count exceeds it
       uint32_t e = 0;
@@ -495,7 +498,7 @@ __device__ __forceinline__ void outline_cells(const GridView &g, const int32_t *
     }
     return;
   }
-  for (uint32_t i = 0; i < n_pts; i++) { // long outlines (a traced floorplan): edge by edge
+  for (uint32_t i = part; i < n_pts; i += n_parts) { // long outlines (a traced floorplan): edge by edge
     const uint32_t j = i + 1 == n_pts ? 0 : i + 1;
     EdgeRec e;
     e.x0 = pix[2 * i];
@@ -518,6 +521,11 @@ __device__ __forceinline__ void outline_cells(const GridView &g, const int32_t *
   }
 }
 
+// Warps that share the cell visits of one pose record's outline (82 visits for a 0.44 x 0.38 m robot: three rounds of 32). A
+// pass over a few thousand records is all latency and leaves most of the device idle: three chains side by side shorten it
+// (1000 robots: 0.077 -> 0.057 ms). A pass over a swarm is throughput: the extra warps only get in the way (100,000 pucks of
+// one round each: 0.87 -> 1.42 ms with three), so it keeps one.
+__device__ __forceinline__ uint32_t pose_parts(uint32_t n_records) { return n_records <= 4096u ? 3u : 1u; }
 struct OpRemove {
   const GridView &g;
   uint32_t block, L;
@@ -544,11 +552,13 @@ __global__ void __launch_bounds__(256) k1_pose_phase0(GridView g, GeomView gv, c
     const int nr = min(n_ranks - r0, kMaxRanksFlat);
     const unsigned char *part = blobs + (size_t)r0 * slot_bytes;
     k1_pose_prefix(g, part, nr, slot_bytes, prefix);
-    // two warps share a record: the even one derives the new outline and the block's record, the odd one takes the old
-    // outline out - two dependent chains side by side instead of one after the other (a pass over 1000 robots is all latency)
-    for (uint32_t ww = warp; ww < 2 * prefix[nr]; ww += n_warps) {
-      const uint32_t w = ww >> 1;
-      const bool second = (ww & 1u) != 0;
+    // 1 + kPoseParts warps share a record: one derives the new outline and the block's record, the others take the old
+    // outline out, a round of 32 cell visits each - dependent chains side by side instead of one after the other (a pass
+    // over 1000 robots is all latency)
+    const uint32_t kPoseParts = pose_parts(prefix[nr]);
+    for (uint32_t ww = warp; ww < (1 + kPoseParts) * prefix[nr]; ww += n_warps) {
+      const uint32_t w = ww / (1 + kPoseParts), task = ww % (1 + kPoseParts);
+      const bool second = task != 0;
       const int rank = k1_rank_of(prefix, nr, w);
       const BlobView v = blob_view(part, rank, slot_bytes);
       const PoseUpd u = v.pose_upd[w - prefix[rank]];
@@ -592,9 +602,9 @@ __global__ void __launch_bounds__(256) k1_pose_phase0(GridView g, GeomView gv, c
           g.blk_rec[L][u.block].seq = (epoch << kSeqEpochShift) | ((unsigned long long)(v.hdr->rank & 0xff) << kSeqRankShift) | (u.seq_local & kSeqLocalMax);
         }
       }
-      if (second && (u.layer_flags & kPoseRemoveOld)) {
+      if (second && (u.layer_flags & kPoseRemoveOld) && 32u * (task - 1) < bg.est_steps) { // (a puck's 20 visits are one round)
         const OpRemove op = { g, u.block, L };
-        outline_cells(g, gv.pix[L] + 2 * (size_t)bg.first_pt, bg.n_pts, lane, op);
+        outline_cells(g, gv.pix[L] + 2 * (size_t)bg.first_pt, bg.n_pts, lane, op, task - 1, kPoseParts);
       }
     }
     __syncthreads();
@@ -609,11 +619,12 @@ __global__ void __launch_bounds__(256) k1_pose_phase1(GridView g, GeomView gv, c
     const int nr = min(n_ranks - r0, kMaxRanksFlat);
     const unsigned char *part = blobs + (size_t)r0 * slot_bytes;
     k1_pose_prefix(g, part, nr, slot_bytes, prefix);
-    // again two warps per record: the even one inserts the new outline, the odd one fixes the masks up over the old one and
-    // then - it is the only reader of the old outline - puts the new one in its place
-    for (uint32_t ww = warp; ww < 2 * prefix[nr]; ww += n_warps) {
-      const uint32_t w = ww >> 1;
-      const bool second = (ww & 1u) != 0;
+    // again 1 + kPoseParts warps per record: kPoseParts insert the new outline, a round of 32 cell visits each, the last one
+    // fixes the masks up over the old one and then - it is the only reader of the old outline - puts the new one in its place
+    const uint32_t kPoseParts = pose_parts(prefix[nr]);
+    for (uint32_t ww = warp; ww < (1 + kPoseParts) * prefix[nr]; ww += n_warps) {
+      const uint32_t w = ww / (1 + kPoseParts), task = ww % (1 + kPoseParts);
+      const bool second = task == kPoseParts;
       const int rank = k1_rank_of(prefix, nr, w);
       const BlobView v = blob_view(part, rank, slot_bytes);
       const PoseUpd u = v.pose_upd[w - prefix[rank]];
@@ -624,9 +635,9 @@ __global__ void __launch_bounds__(256) k1_pose_phase1(GridView g, GeomView gv, c
       int32_t *pix = gv.pix[L] + 2 * (size_t)bg.first_pt;
       const int32_t *fresh = gv.pix_new[L] + 2 * (size_t)bg.first_pt;
       if (!second) {
-        if (!(u.layer_flags & kPoseNoInsert)) {
+        if (!(u.layer_flags & kPoseNoInsert) && 32u * task < bg.est_steps) {
           const OpInsert op = { g, u.block, L };
-          outline_cells(g, fresh, bg.n_pts, lane, op);
+          outline_cells(g, fresh, bg.n_pts, lane, op, task, kPoseParts);
         }
         continue;
       }
