@@ -1,8 +1,8 @@
 // libstage_gpu.so - binds an UNMODIFIED libstage (rtv/Stage 4.3.0) to libstg_rt.so (include/stg_rt.h).
 //
 // libstage is a shared library built -fPIC with default symbol visibility, so its internal calls to
-// Block::Map, Block::UnMap, ModelRanger::Sensor::Update, ModelFiducial::Update and
-// World::CallUpdateCallbacks go through the PLT. This library defines those five symbols itself; loaded
+// Block::Map, Block::UnMap, ModelRanger::Sensor::Update, ModelFiducial::Update, ModelBlobfinder::Update and
+// World::CallUpdateCallbacks go through the PLT. This library defines those six symbols itself; loaded
 // before libstage (LD_PRELOAD=libstage_gpu.so stage -g worlds/simple.world, or linked ahead of it) it is
 // bound first, does the GPU side, and forwards to libstage's own definition where the CPU side is still
 // wanted. No header, no source file and no binary of Stage changes: controllers, ctrl plugins and
@@ -16,9 +16,12 @@
 //   ModelRanger::Sensor::Update (model_ranger.cc:211-256)   set-up as there, beam loop replaced by stg_rt_fans_submit
 //   ModelFiducial::Update (model_fiducial.cc:229-293)       candidate search, culls and line-of-sight rays replaced by
 //                                                  stg_rt_fiducials_submit (all finders of a tick in one batch)
-//   World::CallUpdateCallbacks (world.cc:668)      first stg_rt_sync: ranges / intensities / fiducials are in the
+//   ModelBlobfinder::Update (model_blobfinder.cc:165-250)   scan fan and colour segmentation replaced by stg_rt_blobs_submit
+//                                                  (all blobfinders of a tick in one batch; a blob's colour is the colour of
+//                                                  the model its first sample hit, world.cc:854)
+//   World::CallUpdateCallbacks (world.cc:668)      first stg_rt_sync: ranges / intensities / fiducials / blobs are in the
 //                                                  sensors' std::vectors before any controller callback reads them
-// Everything else (blobfinder, bumper, gripper rays, collisions) keeps calling World::Raytrace on the CPU grid, which
+// Everything else (bumper, gripper rays, collisions) keeps calling World::Raytrace on the CPU grid, which
 // this library never lets go stale. Any error from the C ABI is printed once, the context is dropped, the tick is
 // redone with libstage's own loops and the process carries on as plain Stage (include/stg_rt.h: no CPU path INSIDE
 // libstg_rt.so; the fallback is the caller's, as SURVEY.md 8b specifies).
@@ -122,6 +125,13 @@ struct FidBatch { // finders that saw the same target list (normally all finders
   std::vector<std::vector<ModelFiducial::Fiducial> > expected; // verify: what libstage's own Update found, per finder
 };
 
+struct BlobJob { // one ModelBlobfinder::Update of the tick
+  ModelBlobfinder *owner;
+  stg_rt_blob_finder rec;
+  std::vector<double> colors;                      // this finder's tracked colours, rgb
+  std::vector<ModelBlobfinder::Blob> expected;     // verify / emulate: what libstage's own Update found
+};
+
 struct Shim {
   std::mutex mu;
   bool wanted = false, failed = false, verbose = false;
@@ -140,6 +150,8 @@ struct Shim {
   uint64_t published_at_update = ~0ull;
   std::vector<RangerJob> rangers;
   std::vector<FidBatch> fid;
+  std::vector<BlobJob> blobs;
+  uint64_t blob_updates = 0, verified_blobs = 0, mismatched_blob_updates = 0;
   uint64_t fans = 0, fid_updates = 0, maps = 0, ticks = 0;
 
   Shim()
@@ -316,17 +328,26 @@ sensor_update_fn real_sensor_update()
   return fn;
 }
 
+typedef void (*blob_update_fn)(ModelBlobfinder *);
+blob_update_fn real_blob_update()
+{
+  static blob_update_fn fn = next_symbol<blob_update_fn>("_ZN3Stg15ModelBlobfinder6UpdateEv");
+  return fn;
+}
+
 // The tick's GPU work is waited for and handed to the sensors; on any error the same sensors are updated by libstage's
 // own loops instead (the layer they read, (updates + 1) % 2, is not written during the tick, so the answer is the same).
 void finish_tick(World *w)
 {
   std::unique_lock<std::mutex> lk(shim.mu);
-  if (shim.rangers.empty() && shim.fid.empty())
+  if (shim.rangers.empty() && shim.fid.empty() && shim.blobs.empty())
     return;
   std::vector<RangerJob> rangers;
   std::vector<FidBatch> fid;
+  std::vector<BlobJob> blobs;
   rangers.swap(shim.rangers);
   fid.swap(shim.fid);
+  blobs.swap(shim.blobs);
   if (shim.emulate) { // hand over what was held back, as the GPU path does after its sync
     shim.ticks++;
     lk.unlock();
@@ -344,6 +365,8 @@ void finish_tick(World *w)
     for (size_t b = 0; b < fid.size(); b++)
       for (size_t i = 0; i < fid[b].owners.size(); i++)
         fid[b].owners[i]->fiducials = fid[b].expected[i];
+    for (size_t i = 0; i < blobs.size(); i++)
+      blobs[i].owner->blobs = blobs[i].expected;
     return;
   }
   bool ok = shim.ctx != nullptr;
@@ -359,6 +382,28 @@ void finish_tick(World *w)
       ok = false;
     }
   }
+  // all blobfinders of the tick in one batch; a finder's tracked colours are its stretch of one colour table
+  std::vector<stg_rt_blob_finder> blob_recs(blobs.size());
+  std::vector<double> blob_colors;
+  std::vector<stg_rt_blob> blob_out;
+  std::vector<uint32_t> blob_count(blobs.size(), 0);
+  uint32_t blob_max = 1;
+  if (ok && !blobs.empty()) {
+    for (size_t i = 0; i < blobs.size(); i++) {
+      blob_recs[i] = blobs[i].rec;
+      blob_recs[i].first_color = (uint32_t)(blob_colors.size() / 3);
+      blob_recs[i].n_colors = (uint32_t)(blobs[i].colors.size() / 3);
+      blob_colors.insert(blob_colors.end(), blobs[i].colors.begin(), blobs[i].colors.end());
+      blob_max = std::max(blob_max, blobs[i].rec.scan_width); // a blob needs at least one sample
+    }
+    blob_out.resize(blobs.size() * (size_t)blob_max);
+    const int rc = stg_rt_blobs_submit(shim.ctx, (uint32_t)blobs.size(), &blob_recs[0], (uint32_t)(blob_colors.size() / 3),
+                                       blob_colors.empty() ? nullptr : &blob_colors[0], blob_max, &blob_out[0], &blob_count[0]);
+    if (rc) {
+      give_up("stg_rt_blobs_submit", rc);
+      ok = false;
+    }
+  }
   if (ok) {
     const int rc = stg_rt_sync(shim.ctx);
     if (rc) {
@@ -368,6 +413,19 @@ void finish_tick(World *w)
   }
   shim.ticks++;
   lk.unlock();
+  // a blob as ModelBlobfinder::Update makes it (model_blobfinder.cc:231-238) from a record of the batch
+  auto blob_of = [&](size_t i, uint32_t k) {
+    const stg_rt_blob &r = blob_out[i * (size_t)blob_max + k];
+    ModelBlobfinder::Blob b;
+    const Model *seen = Model::LookupId(r.model);
+    b.color = seen ? seen->GetColor() : Color();
+    b.left = r.left;
+    b.top = r.top;
+    b.right = r.right;
+    b.bottom = r.bottom;
+    b.range = r.range;
+    return b;
+  };
   if (!ok && shim.verify) {
     for (size_t i = 0; i < rangers.size(); i++) {
       delete rangers[i].gpu_ranges;
@@ -385,6 +443,8 @@ void finish_tick(World *w)
         for (std::vector<Model *>::const_iterator it = w->models_with_fiducials.begin(); it != w->models_with_fiducials.end(); ++it)
           f->AddModelIfVisible(*it); // model_fiducial.cc:286-287, the reference's own alternative to the windowed search
       }
+    for (size_t i = 0; i < blobs.size(); i++)
+      real_blob_update()(blobs[i].owner); // (its Model::Update() sets last_update to the same sim_time once more)
     return;
   }
   if (shim.verify) { // the sensors hold libstage's own answers; the GPU's must be the same
@@ -424,7 +484,22 @@ void finish_tick(World *w)
         bad_updates += same ? 0 : 1;
       }
     }
+    uint64_t n_blobs = 0, bad_blob_updates = 0;
+    for (size_t i = 0; i < blobs.size(); i++) {
+      const std::vector<ModelBlobfinder::Blob> &want = blobs[i].expected;
+      const uint32_t n = std::min(blob_count[i], blob_max);
+      bool same = n == want.size();
+      for (uint32_t k = 0; k < n && same; k++) {
+        const ModelBlobfinder::Blob got = blob_of(i, k);
+        same = got.left == want[k].left && got.right == want[k].right && got.top == want[k].top && got.bottom == want[k].bottom &&
+               !memcmp(&got.range, &want[k].range, 8) && got.color == want[k].color;
+      }
+      n_blobs += n;
+      bad_blob_updates += same ? 0 : 1;
+    }
     std::lock_guard<std::mutex> lk2(shim.mu);
+    shim.verified_blobs += n_blobs;
+    shim.mismatched_blob_updates += bad_blob_updates;
     shim.verified_beams += beams;
     shim.mismatched_beams += bad_beams;
     shim.verified_fiducials += fids;
@@ -458,6 +533,12 @@ void finish_tick(World *w)
         dst.push_back(f);
       }
     }
+  }
+  for (size_t i = 0; i < blobs.size(); i++) {
+    std::vector<ModelBlobfinder::Blob> &dst = blobs[i].owner->blobs;
+    dst.clear();
+    for (uint32_t k = 0, n = std::min(blob_count[i], blob_max); k < n; k++)
+      dst.push_back(blob_of(i, k));
   }
 }
 
@@ -679,6 +760,51 @@ void ModelFiducial::Update(void)
     Model::Update(); // :292
 }
 
+void ModelBlobfinder::Update(void)
+{
+  bool gpu = shim.active();
+  if (gpu) {
+    std::lock_guard<std::mutex> lk(shim.mu);
+    gpu = ensure_context_locked(world) && publish_changed_locked(world);
+  }
+  if (!gpu) {
+    real_blob_update()(this);
+    return;
+  }
+  BlobJob j;
+  j.owner = this;
+  if (shim.verify || shim.emulate) { // libstage's own Update, Model::Update() included
+    real_blob_update()(this);
+    j.expected = blobs;
+    if (shim.emulate)
+      blobs.clear(); // held back until the sync point
+  } else {
+    blobs.clear(); // model_blobfinder.cc:175; filled at the sync point
+  }
+  // Raytrace(Pose(0, 0, 0, pan), range, fov, blob_match, NULL, false, samples), :170 - the pose the fan leaves from, taken NOW
+  const Pose origin = LocalToGlobal(Pose(0, 0, 0, pan));
+  memset(&j.rec, 0, sizeof(j.rec));
+  j.rec.finder = id;
+  j.rec.scan_width = scan_width;
+  j.rec.scan_height = scan_height;
+  j.rec.layer = (uint8_t)((world->updates + 1) % 2);
+  j.rec.ox = origin.x; j.rec.oy = origin.y; j.rec.oz = origin.z; j.rec.oa = origin.a;
+  j.rec.range = range;
+  j.rec.fov = fov;
+  for (size_t c = 0; c < colors.size(); c++) {
+    j.colors.push_back(colors[c].r);
+    j.colors.push_back(colors[c].g);
+    j.colors.push_back(colors[c].b);
+  }
+  {
+    std::lock_guard<std::mutex> lk(shim.mu);
+    shim.blobs.push_back(j);
+    shim.blob_updates++;
+  }
+  if (!shim.verify && !shim.emulate)
+    Model::Update(); // :249
+}
+
 void World::CallUpdateCallbacks()
 {
   typedef void (*fn_t)(World *);
@@ -689,7 +815,7 @@ void World::CallUpdateCallbacks()
 }
 
 // for the driver's summary line (integration/stage_run.cc): how much of the run went through the GPU
-extern "C" void stage_gpu_counters(unsigned long long out[10])
+extern "C" void stage_gpu_counters(unsigned long long out[13])
 {
   std::lock_guard<std::mutex> lk(shim.mu);
   out[0] = shim.fans;
@@ -702,4 +828,7 @@ extern "C" void stage_gpu_counters(unsigned long long out[10])
   out[7] = shim.verified_fiducials;
   out[8] = shim.mismatched_fiducial_updates;
   out[9] = (unsigned long long)(shim.fiducial_max_err * 1e18); // in attometres / attoradians: fits an integer
+  out[10] = shim.blob_updates;
+  out[11] = shim.verified_blobs;
+  out[12] = shim.mismatched_blob_updates;
 }

@@ -86,7 +86,13 @@ int main(int argc, char **argv)
     models.assign(all.begin(), all.end());
     std::sort(models.begin(), models.end(), by_id);
   }
-  unsigned long long rays = 0, fid_records = 0, fid_updates = 0;
+  // STAGE_RUN_SUBSCRIBE_ALL=1: every ranger, fiducial finder and blobfinder is subscribed to, as a client or the GUI's data
+  // views would: worlds without controllers (lsp_test.world) then update their sensors every tick
+  if (getenv("STAGE_RUN_SUBSCRIBE_ALL") && atoi(getenv("STAGE_RUN_SUBSCRIBE_ALL")))
+    for (size_t i = 0; i < models.size(); i++)
+      if (dynamic_cast<ModelRanger *>(models[i]) || dynamic_cast<ModelFiducial *>(models[i]) || dynamic_cast<ModelBlobfinder *>(models[i]))
+        models[i]->Subscribe();
+  unsigned long long rays = 0, fid_records = 0, fid_updates = 0, blob_records = 0;
   const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
   double in_update = 0;
   for (long t = 0; t < ticks; t++) {
@@ -127,8 +133,9 @@ int main(int argc, char **argv)
       Model *m = models[i];
       ModelRanger *r = dynamic_cast<ModelRanger *>(m);
       ModelFiducial *fm = r ? NULL : dynamic_cast<ModelFiducial *>(m);
+      ModelBlobfinder *bm = (r || fm) ? NULL : dynamic_cast<ModelBlobfinder *>(m);
       put_u32(dump, m->GetId());
-      put_u32(dump, r ? 1u : fm ? 2u : 0u); // record kind: what follows the pose
+      put_u32(dump, r ? 1u : fm ? 2u : bm ? 3u : 0u); // record kind: what follows the pose
       put_pose(dump, m->GetGlobalPose());
       if (r) {
         const std::vector<ModelRanger::Sensor> &s = r->GetSensors();
@@ -153,24 +160,37 @@ int main(int argc, char **argv)
           put_u32(dump, (uint32_t)fs[k].id);
           fid_records++;
         }
+      } else if (bm) {
+        const std::vector<ModelBlobfinder::Blob> &bs = bm->GetBlobs();
+        put_u32(dump, (uint32_t)bs.size());
+        for (size_t k = 0; k < bs.size(); k++) {
+          const double d[5] = { bs[k].color.r, bs[k].color.g, bs[k].color.b, bs[k].color.a, bs[k].range };
+          put(dump, d, sizeof(d));
+          put_u32(dump, bs[k].left);
+          put_u32(dump, bs[k].top);
+          put_u32(dump, bs[k].right);
+          put_u32(dump, bs[k].bottom);
+          blob_records++;
+        }
       }
     }
   }
   const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (dump)
     fclose(dump);
-  unsigned long long gpu[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+  unsigned long long gpu[13] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
   typedef void (*cnt_t)(unsigned long long *);
   if (cnt_t cnt = (cnt_t)dlsym(RTLD_DEFAULT, "stage_gpu_counters"))
     cnt(gpu);
   // one line, machine-readable (the dumps carry the data; rays = ranger samples held by the sensors, summed over ticks)
   printf("\nstage_run: {\"world\": \"%s\", \"ticks\": %llu, \"seconds_in_update\": %.6f, \"seconds_wall\": %.6f, \"ticks_per_s\": %.3f, "
-         "\"ranger_samples\": %llu, \"fiducial_records\": %llu, \"gpu\": {\"fans\": %llu, \"fiducial_updates\": %llu, \"map_calls\": %llu, "
+         "\"ranger_samples\": %llu, \"fiducial_records\": %llu, \"blob_records\": %llu, \"gpu\": {\"fans\": %llu, \"fiducial_updates\": %llu, \"map_calls\": %llu, "
          "\"ticks\": %llu, \"state\": \"%s\", \"verified_beams\": %llu, \"mismatched_beams\": %llu, \"verified_fiducials\": %llu, "
-         "\"mismatched_fiducial_updates\": %llu, \"fiducial_max_abs_err\": %.3e}}\n",
-         argv[1], (unsigned long long)world->GetUpdateCount(), in_update, wall, world->GetUpdateCount() / in_update, rays, fid_records, gpu[0], gpu[1],
+         "\"mismatched_fiducial_updates\": %llu, \"fiducial_max_abs_err\": %.3e, \"blob_updates\": %llu, \"verified_blobs\": %llu, "
+         "\"mismatched_blob_updates\": %llu}}\n",
+         argv[1], (unsigned long long)world->GetUpdateCount(), in_update, wall, world->GetUpdateCount() / in_update, rays, fid_records, blob_records, gpu[0], gpu[1],
          gpu[2], gpu[3], gpu[4] == 4 ? "emulated on the cpu" : gpu[4] == 3 ? "gpu, verified against libstage's own loops in place" : gpu[4] == 2 ? "gpu" : gpu[4] == 1 ? "fell back to cpu" : "cpu",
-         gpu[5], gpu[6], gpu[7], gpu[8], gpu[9] * 1e-18);
+         gpu[5], gpu[6], gpu[7], gpu[8], gpu[9] * 1e-18, gpu[10], gpu[11], gpu[12]);
   fflush(stdout);
   _exit(0);
 }

@@ -1,5 +1,5 @@
 """Reader for the binary dumps integration/stage_run.cc writes (one record per tick: every model's id and global pose,
-every ranger sensor's ranges / intensities / bearings, every fiducial finder's records)."""
+every ranger sensor's ranges / intensities / bearings, every fiducial finder's records, every blobfinder's blobs)."""
 import struct
 
 import numpy as np
@@ -21,7 +21,7 @@ def read(path):
         mid, kind = struct.unpack_from("<II", raw, off)
         pose = struct.unpack_from("<4d", raw, off + 8)
         off += 40
-        rec = {"pose": pose, "sensors": None, "fiducials": None}
+        rec = {"pose": pose, "sensors": None, "fiducials": None, "blobs": None}
         if kind == 1:
             (ns,) = struct.unpack_from("<I", raw, off)
             off += 4
@@ -41,6 +41,15 @@ def read(path):
                 mod, fid = struct.unpack_from("<Ii", raw, off + 80)
                 off += 88
                 rec["fiducials"].append((d[0], d[1], d[2:6], d[6:10], mod, fid))
+        elif kind == 3:
+            (nb,) = struct.unpack_from("<I", raw, off)
+            off += 4
+            rec["blobs"] = []
+            for _ in range(nb):
+                d = struct.unpack_from("<5d", raw, off)
+                box = struct.unpack_from("<4I", raw, off + 40)
+                off += 56
+                rec["blobs"].append((d[:4], d[4], box))   # (rgba, range, (left, top, right, bottom))
         cur[mid] = rec
     return ticks
 
@@ -64,6 +73,8 @@ def describe_first_difference(a_path, b_path):
                                 k, name, len(bad), len(xa), bad[:1], xa[bad[:1]], xb[bad[:1]])
             if ra["fiducials"] is not None and ra["fiducials"] != rb["fiducials"]:
                 return t, mid, "fiducials %r vs %r" % (ra["fiducials"][:3], rb["fiducials"][:3])
+            if ra["blobs"] is not None and ra["blobs"] != rb["blobs"]:
+                return t, mid, "blobs %r vs %r" % (ra["blobs"][:3], rb["blobs"][:3])
     if len(A) != len(B):
         return min(len(A), len(B)), None, "tick counts %d vs %d" % (len(A), len(B))
     return None

@@ -28,7 +28,7 @@ def have_binding():
     return os.path.exists(RUN) and os.path.exists(SHIM) and os.path.exists(os.path.join(REF, "libstage_ref.so"))
 
 
-def stage_run(world, ticks, dump=None, gpu=0, fiducials_on_main=False, timeout=600, fallback=False):
+def stage_run(world, ticks, dump=None, gpu=0, fiducials_on_main=False, timeout=600, fallback=False, subscribe_all=False):
     """gpu: 0 = no binding loaded, 1 = through the GPU, 2 = GPU verified in place, 3 = emulated on the CPU.
     fallback: the binding is loaded and behaves like a GPU run until its first sensor update, then leaves everything to
     libstage: the reference itself, with the heap layout of a GPU run. That matters because Stage orders its work by
@@ -45,6 +45,8 @@ def stage_run(world, ticks, dump=None, gpu=0, fiducials_on_main=False, timeout=6
         env["STAGE_GPU"] = str(gpu)
     if fiducials_on_main:
         env["STAGE_FIDUCIALS_ON_MAIN"] = "1"
+    if subscribe_all:   # worlds without controllers: every ranger / fiducial finder / blobfinder updates every tick
+        env["STAGE_RUN_SUBSCRIBE_ALL"] = "1"
     cmd = [RUN, os.path.join("worlds", world), str(ticks)] + ([dump] if dump else [])
     r = subprocess.run(cmd, cwd=REF, env=env, capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -52,11 +54,11 @@ def stage_run(world, ticks, dump=None, gpu=0, fiducials_on_main=False, timeout=6
     return json.loads(line[len("stage_run: "):]), r.stderr
 
 
-def compare(world, ticks, tmp_path, fiducials_on_main=False, mode=1):
+def compare(world, ticks, tmp_path, fiducials_on_main=False, mode=1, subscribe_all=False):
     a, b = str(tmp_path / "cpu.bin"), str(tmp_path / "gpu.bin")
-    cpu, _ = stage_run(world, ticks, a, fallback=True, fiducials_on_main=fiducials_on_main)
+    cpu, _ = stage_run(world, ticks, a, fallback=True, fiducials_on_main=fiducials_on_main, subscribe_all=subscribe_all)
     assert cpu["gpu"]["state"] == "fell back to cpu"
-    gpu, err = stage_run(world, ticks, b, gpu=mode, fiducials_on_main=fiducials_on_main)
+    gpu, err = stage_run(world, ticks, b, gpu=mode, fiducials_on_main=fiducials_on_main, subscribe_all=subscribe_all)
     assert gpu["gpu"]["state"] == ("gpu" if mode == 1 else "emulated on the cpu"), err[-2000:]
     off = stage_dump.first_difference(a, b)
     assert off is None, "dumps differ at byte %d: %r" % (off, stage_dump.describe_first_difference(a, b))
@@ -94,6 +96,22 @@ def test_pioneer_flocking_60_ticks_identical_with_the_flocking_controller(tmp_pa
     assert gpu["gpu"]["fans"] == 800 * 60 and gpu["gpu"]["fiducial_updates"] == 100 * 60
     assert gpu["fiducial_records"] == cpu["fiducial_records"] > 30000
     print("pioneer_flocking.world, 60 ticks: reference %.0f ticks/s, through libstage_gpu.so %.0f ticks/s" % (cpu["ticks_per_s"], gpu["ticks_per_s"]))
+
+
+@gpu
+@pytest.mark.skipif(not have_binding(), reason="integration/_build or oracle/_ref not built (integration/build.sh)")
+def test_lsp_test_world_blobfinders_lasers_and_fiducials_identical(tmp_path):
+    """worlds/lsp_test.world (the world the reference's own libstageplugin test pins its known answers on: two Pioneers
+    with sonar rings, SICK lasers, fiducial finders and six-channel blobfinders in the cave), every sensor subscribed to:
+    ModelBlobfinder::Update goes through stg_rt_blobs_submit - colours, column spans, rows and ranges of every blob byte for
+    byte as libstage computes them - and, verified in place, every answer of every update agrees."""
+    cpu, gpu = compare("lsp_test.world", 30, tmp_path, fiducials_on_main=True, subscribe_all=True)
+    assert gpu["blob_records"] == cpu["blob_records"] > 30 and gpu["gpu"]["blob_updates"] == 2 * 30
+    assert gpu["gpu"]["fans"] > 0 and gpu["fiducial_records"] == cpu["fiducial_records"] > 0
+    res, err = stage_run("lsp_test.world", 30, gpu=2, fiducials_on_main=True, subscribe_all=True)
+    g = res["gpu"]
+    assert g["state"].startswith("gpu, verified"), err[-2000:]
+    assert g["mismatched_blob_updates"] == 0 and g["verified_blobs"] > 30 and g["mismatched_beams"] == 0 and g["mismatched_fiducial_updates"] == 0, (g, err[-1500:])
 
 
 @gpu

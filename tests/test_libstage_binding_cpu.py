@@ -13,17 +13,20 @@ from test_gpu_libstage import REF, RUN, SHIM, have_binding, stage_run
 
 
 @pytest.mark.skipif(not have_binding(), reason="integration/_build or oracle/_ref not built (integration/build.sh)")
-@pytest.mark.parametrize("world,ticks", [("simple.world", 1000), ("fasr.world", 300), ("pioneer_flocking.world", 40)])
+@pytest.mark.parametrize("world,ticks", [("simple.world", 1000), ("fasr.world", 300), ("pioneer_flocking.world", 40), ("lsp_test.world", 30)])
 def test_emulated_binding_equals_plain_libstage(world, ticks, tmp_path):
     a, b = str(tmp_path / "cpu.bin"), str(tmp_path / "emu.bin")
-    cpu, _ = stage_run(world, ticks, a, fallback=True, fiducials_on_main=True)
-    emu, err = stage_run(world, ticks, b, gpu=3, fiducials_on_main=True)
+    sub = world == "lsp_test.world"   # no controllers there: every ranger, fiducial finder and blobfinder is subscribed to instead
+    cpu, _ = stage_run(world, ticks, a, fallback=True, fiducials_on_main=True, subscribe_all=sub)
+    emu, err = stage_run(world, ticks, b, gpu=3, fiducials_on_main=True, subscribe_all=sub)
     assert cpu["gpu"]["state"] == "fell back to cpu" and emu["gpu"]["state"] == "emulated on the cpu", err[-1000:]
     off = stage_dump.first_difference(a, b)
     assert off is None, "dumps differ at byte %d: %r" % (off, stage_dump.describe_first_difference(a, b))
     assert emu["gpu"]["fans"] > 0 and emu["ranger_samples"] == cpu["ranger_samples"]
     if world == "pioneer_flocking.world":
         assert emu["fiducial_records"] == cpu["fiducial_records"] > 10000
+    if world == "lsp_test.world":   # blobfinders: held back and delivered at the sync point like the rest
+        assert emu["blob_records"] == cpu["blob_records"] > 30 and emu["gpu"]["blob_updates"] == 2 * ticks
 
 
 @pytest.mark.skipif(not have_binding(), reason="integration/_build or oracle/_ref not built (integration/build.sh)")
