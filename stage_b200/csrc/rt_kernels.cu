@@ -427,17 +427,25 @@ __global__ void __launch_bounds__(256) k1_phase1(GridView g, const unsigned char
 //   phase 1: mask fix-up over the old outline, insertion of the new one, pix <- pix_new
 // ------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ void k1_pose_prefix(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes, uint32_t *prefix)
+// prefix[r] = pose records of the ranks before r; *est_steps = the senders' estimate of the cell visits of the outlines those
+// records take out or put in, whichever is more (DeltaHeader::est_remove_l / est_insert_l)
+__device__ __forceinline__ void k1_pose_prefix(const GridView &g, const unsigned char *blobs, int n_ranks, size_t slot_bytes, uint32_t *prefix,
+                                               uint32_t *est_steps)
 {
   if (threadIdx.x == 0) {
     uint32_t run = 0;
+    unsigned long long out = 0, in = 0;
     for (int r = 0; r < n_ranks; r++) {
       prefix[r] = run;
       const DeltaHeader *h = reinterpret_cast<const DeltaHeader *>(blobs + (size_t)r * slot_bytes);
-      if (blob_ok(h, slot_bytes))
+      if (blob_ok(h, slot_bytes)) {
         run += h->n_pose_upd;
+        out += (unsigned long long)h->est_remove_l[0] + h->est_remove_l[1];
+        in += (unsigned long long)h->est_insert_l[0] + h->est_insert_l[1];
+      }
     }
     prefix[n_ranks] = run;
+    *est_steps = (uint32_t)min(max(out, in), 0xffffffffull);
   }
   __syncthreads();
 }
@@ -523,9 +531,14 @@ __device__ __forceinline__ void outline_cells(const GridView &g, const int32_t *
 
 // Warps that share the cell visits of one pose record's outline (82 visits for a 0.44 x 0.38 m robot: three rounds of 32). A
 // pass over a few thousand records is all latency and leaves most of the device idle: three chains side by side shorten it
-// (1000 robots: 0.077 -> 0.057 ms). A pass over a swarm is throughput: the extra warps only get in the way (100,000 pucks of
-// one round each: 0.87 -> 1.42 ms with three), so it keeps one.
-__device__ __forceinline__ uint32_t pose_parts(uint32_t n_records) { return n_records <= 4096u ? 3u : 1u; }
+// (1000 robots: 0.077 -> 0.054 ms). Bodies of one round gain nothing and the extra warps get in the way (100,000 pucks:
+// 0.87 -> 1.42 ms with three), so they keep one.
+// Decided by what the records hold (the senders' estimate of their outlines' cell visits, DeltaHeader) rather than by how
+// many there are: three warps where an outline is two and more rounds on average (8000 robots: 0.267 -> 0.249 ms).
+__device__ __forceinline__ uint32_t pose_parts(uint32_t n_records, uint32_t est_steps)
+{
+  return n_records && est_steps / n_records >= 64u ? 3u : 1u;
+}
 struct OpRemove {
   const GridView &g;
   uint32_t block, L;
@@ -546,16 +559,17 @@ __global__ void __launch_bounds__(256) k1_pose_phase0(GridView g, GeomView gv, c
                                                       unsigned long long epoch)
 {
   __shared__ uint32_t prefix[kMaxRanksFlat + 1];
+  __shared__ uint32_t est_steps;
   const uint32_t lane = threadIdx.x & 31u, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   epoch = k1_pass_epoch(blobs, n_ranks, slot_bytes, epoch);
   for (int r0 = 0; r0 < n_ranks; r0 += kMaxRanksFlat) {
     const int nr = min(n_ranks - r0, kMaxRanksFlat);
     const unsigned char *part = blobs + (size_t)r0 * slot_bytes;
-    k1_pose_prefix(g, part, nr, slot_bytes, prefix);
+    k1_pose_prefix(g, part, nr, slot_bytes, prefix, &est_steps);
     // 1 + kPoseParts warps share a record: one derives the new outline and the block's record, the others take the old
     // outline out, a round of 32 cell visits each - dependent chains side by side instead of one after the other (a pass
     // over 1000 robots is all latency)
-    const uint32_t kPoseParts = pose_parts(prefix[nr]);
+    const uint32_t kPoseParts = pose_parts(prefix[nr], est_steps);
     for (uint32_t ww = warp; ww < (1 + kPoseParts) * prefix[nr]; ww += n_warps) {
       const uint32_t w = ww / (1 + kPoseParts), task = ww % (1 + kPoseParts);
       const bool second = task != 0;
@@ -614,14 +628,15 @@ __global__ void __launch_bounds__(256) k1_pose_phase0(GridView g, GeomView gv, c
 __global__ void __launch_bounds__(256) k1_pose_phase1(GridView g, GeomView gv, const unsigned char *blobs, int n_ranks, size_t slot_bytes)
 {
   __shared__ uint32_t prefix[kMaxRanksFlat + 1];
+  __shared__ uint32_t est_steps;
   const uint32_t lane = threadIdx.x & 31u, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   for (int r0 = 0; r0 < n_ranks; r0 += kMaxRanksFlat) {
     const int nr = min(n_ranks - r0, kMaxRanksFlat);
     const unsigned char *part = blobs + (size_t)r0 * slot_bytes;
-    k1_pose_prefix(g, part, nr, slot_bytes, prefix);
+    k1_pose_prefix(g, part, nr, slot_bytes, prefix, &est_steps);
     // again 1 + kPoseParts warps per record: kPoseParts insert the new outline, a round of 32 cell visits each, the last one
     // fixes the masks up over the old one and then - it is the only reader of the old outline - puts the new one in its place
-    const uint32_t kPoseParts = pose_parts(prefix[nr]);
+    const uint32_t kPoseParts = pose_parts(prefix[nr], est_steps);
     for (uint32_t ww = warp; ww < (1 + kPoseParts) * prefix[nr]; ww += n_warps) {
       const uint32_t w = ww / (1 + kPoseParts), task = ww % (1 + kPoseParts);
       const bool second = task == kPoseParts;
