@@ -87,6 +87,12 @@ struct PinBuf {
   size_t cap = 0;
 };
 
+// A palette index no model has: what the streamed expansion leaves behind in the staging bytes it has read, so that a byte
+// still holding it after its stretch's flag has been seen can only be one the march's store has not reached the host with
+// yet - the expansion waits for it. The flag protocol (one system-wide fence per stretch, FanBatchView) orders the stores by
+// the memory model's fence cumulativity; this makes the delivery right even where that did not hold.
+constexpr uint32_t kPaletteUnwritten = 255;
+
 struct FanArrays { // device arrays of one batch / resident set
   DevBuf fans, first, headings_in, trig, heading, trigw; // trigw: per-beam (cos, sin) computed on the device for the refill march
   DevBuf ranges, intens, bearings, hit_model, hit_cell, steps;
@@ -381,10 +387,12 @@ struct stg_rt_ctx {
   bool hold_epoch = false; // the undo re-maps of a move belong to the same epoch as the moves
   std::vector<double> mdl_color; // rgba per model
   bool mdl_color_dirty = true;
-  // the distinct ranger_return values of the world (index 0 = "no hit" = 0.0): with at most 255 of them a beam's
+  // the distinct ranger_return values of the world (index 0 = "no hit" = 0.0): with at most 254 of them a beam's
   // intensity crosses PCIe as one byte and stg_rt_sync expands it into the caller's doubles
   std::vector<double> palette = std::vector<double>(1, 0.0);
   bool palette_ok = true;
+  size_t idx_clean_bytes = 0; // so many leading bytes of h_intens_idx read kPaletteUnwritten (the streamed expansion puts them back as it goes)
+  const void *idx_clean_base = nullptr; // ... of the buffer at this address
   bool f_compact_intens = false; // the batch in flight delivers intensities as palette indices
   PinBuf h_intens_idx;
   // streamed delivery: the march tells the host, stretch by stretch, which results have landed (FanBatchView::stretch_done;
@@ -1176,11 +1184,13 @@ int deliver_locked(stg_rt_ctx *c)
     if (c->f_streaming && s.out.intensities) { // expanded while the kernel ran; whatever is left is finished here
       c->pool.finish();
       if (c->stream_gave_up.load()) { // (only after a failed launch) do it the plain way
+        c->idx_clean_bytes = 0;
         const uint8_t *idx = (const uint8_t *)c->h_intens_idx.p + s.first_beam;
         for (uint64_t i = 0; i < s.n_beams; i++)
           s.out.intensities[i] = c->palette[idx[i]];
       }
     } else if (c->f_compact_intens && s.out.intensities) { // palette indices -> the caller's doubles (model_ranger.cc:250)
+      c->idx_clean_bytes = 0;
       const uint8_t *idx = (const uint8_t *)c->h_intens_idx.p + s.first_beam;
       double *dst = s.out.intensities;
       const double *pal = c->palette.data();
@@ -1377,6 +1387,14 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
     v.done_seq = c->done_seq;
     v.stretch_shift = kStretchShift;
     c->f_streaming = true;
+    // every staging byte the march is about to write holds "not written yet" (normally left so by the last expansion)
+    if (c->idx_clean_base != c->h_intens_idx.p || c->idx_clean_bytes < beams) {
+      memset(c->h_intens_idx.p, (int)kPaletteUnwritten, (size_t)beams);
+      c->idx_clean_base = c->h_intens_idx.p;
+      c->idx_clean_bytes = (size_t)beams;
+    }
+  } else if (c->f_compact_intens) {
+    c->idx_clean_bytes = 0; // the march writes the staging bytes and nobody puts them back
   }
   CU(c, cudaEventRecord(c->t_ev[2][0], c->stream));
   if (refill)
@@ -1387,7 +1405,7 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
   c->t_rec[1] = c->t_rec[2] = true;
   CU(c, cudaGetLastError());
   if (c->f_streaming) {
-    const uint8_t *idx = (const uint8_t *)c->h_intens_idx.p;
+    uint8_t *idx = (uint8_t *)c->h_intens_idx.p;
     double *dst = solo->out.intensities;
     const double *pal = c->palette.data();
     const volatile uint32_t *flags = (const volatile uint32_t *)c->h_done_flags.p;
@@ -1398,14 +1416,25 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
     c->pool.begin((n + kStretch - 1) / kStretch, [idx, dst, pal, flags, seq, n, gave_up](size_t part) {
       const size_t lo = part * kStretch, hi = std::min(n, lo + kStretch);
       const std::chrono::steady_clock::time_point until = std::chrono::steady_clock::now() + std::chrono::seconds(2);
-      while (flags[part] != seq) {
+      auto late = [&]() { // the kernel did not finish (an error the sync will report): nothing to expand
         if (gave_up->load(std::memory_order_relaxed) || std::chrono::steady_clock::now() > until) {
-          gave_up->store(true); // the kernel did not finish (an error the sync will report): nothing to expand
-          return;
+          gave_up->store(true);
+          return true;
         }
         _mm_pause();
-      }
+        return false;
+      };
+      while (flags[part] != seq)
+        if (late())
+          return;
       std::atomic_thread_fence(std::memory_order_acquire);
+      // belt and braces: a byte that still reads "not written yet" is a store that has not arrived; wait for it
+      for (const uint8_t *q = (const uint8_t *)memchr(idx + lo, (int)kPaletteUnwritten, hi - lo); q;
+           q = (const uint8_t *)memchr(q, (int)kPaletteUnwritten, (size_t)(idx + hi - q))) {
+        while (*(const volatile uint8_t *)q == kPaletteUnwritten)
+          if (late())
+            return;
+      }
       size_t i = lo;
       for (; i < hi && ((uintptr_t)(dst + i) & 15u); i++)
         dst[i] = pal[idx[i]];
@@ -1414,6 +1443,7 @@ int launch_fans_locked(stg_rt_ctx *c, bool with_deltas = false)
       for (; i < hi; i++)
         dst[i] = pal[idx[i]];
       _mm_sfence();
+      memset(idx + lo, (int)kPaletteUnwritten, hi - lo); // read: ready for the next tick's march
     });
   }
   c->stats.launches_march += 1;
@@ -1703,7 +1733,7 @@ int stg_rt_model_upsert(stg_rt_ctx *c, uint32_t id, uint32_t root_id, double ran
     while (k < c->palette.size() && memcmp(&c->palette[k], &ranger_return, sizeof(double)))
       k++;
     if (k == c->palette.size()) {
-      if (k < 256)
+      if (k < kPaletteUnwritten) // (index 255 is never a palette entry: it marks a byte the march has not written yet)
         c->palette.push_back(ranger_return);
       else
         c->palette_ok = false; // more distinct values than a byte names: intensities travel as doubles from now on

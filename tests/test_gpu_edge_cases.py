@@ -461,9 +461,9 @@ def test_grid_digest_sees_entries_counts_and_list_order():
         p.ctx.close()
 
 
-@pytest.mark.parametrize("n_values", [7, 255, 400])
+@pytest.mark.parametrize("n_values", [7, 252, 400])
 def test_intensities_through_the_palette_and_past_it(n_values):
-    """Sensor::intensities = the hit model's ranger_return (model_ranger.cc:250). Up to 255 distinct values cross PCIe as
+    """Sensor::intensities = the hit model's ranger_return (model_ranger.cc:250). Up to 254 distinct values cross PCIe as
     one palette byte per beam and are expanded by stg_rt_sync; a world with more falls back to doubles. Same answers
     either way, a re-published value included."""
     ctx = rt.Context(50.0, -1, -1, 2, 2, max_models=n_values + 8, max_blocks=n_values + 8, max_cell_entries=1 << 18)
